@@ -1,0 +1,662 @@
+"""Host-side mirror of the Gridap-facing API of GridapGeosciences.jl for the GPU hot path.
+
+Julia is not available in this environment, so the host side above the C ABI (include/geosgpu.h) is
+written in Python with the reference's own names and argument meaning
+(`AtlasDiscreteModel(CubedSphereMesh(r), nref)`, `Triangulation`, `Measure`, `TestFESpace`,
+`assemble_matrix`, `assemble_vector`, `AffineFEOperator`, `RungeKutta` / `solve`); INTEGRATION.md shows the
+equivalent Julia `ccall` shim.  Every numeric call goes through libgeosgpu.so -- hand-written sm_100a
+kernels -- and fails loudly when the library or a B200 is missing.  Nothing here imports `oracle/`.
+
+Deviation from the reference: Gridap forms are arbitrary Julia closures; here a form is
+a descriptor object (`LaplaceBeltrami(dΩ)`, `Helmholtz(dΩ)`, `ScalarMass(dΩ)`, `RTMass(dΩ)`, `Div(dΩ)`,
+`Source(dΩ, f_q)`) that selects one of the library's kernels.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import GGError  # noqa: F401
+
+lagrangian = "lagrangian"
+raviart_thomas = "raviart_thomas"
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _ip64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+# ---- context ----------------------------------------------------------------------------------------
+
+class Context:
+    """One per process: one GPU, one stream (`gg_init`)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_init(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def synchronize(self):
+        _lib.check(self.lib.gg_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.gg_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.gg_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.gg_finalize(self.h)
+            self.h = None
+
+
+_default_ctx = None
+
+
+def get_context(device=None):
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+# ---- geometry / model ---------------------------------------------------------------------------------
+
+class IntrinsicManifold:
+    pass
+
+
+class ExtrinsicManifold:
+    pass
+
+
+class CubedSphereMesh:
+    """CubedSphereMesh(radius) -- src/Geometry/CubedSphereMesh.jl:32-35."""
+
+    def __init__(self, radius=1.0):
+        self.radius = float(radius)
+
+
+class AtlasDiscreteModel:
+    """AtlasDiscreteModel(CubedSphereMesh(r), nref; manifold_style) -- src/Geometry/AtlasDiscreteModels.jl:222-229.
+
+    `n` (cells per panel edge) may be given instead of `nref` (n = 2**nref); the reference only offers powers of two."""
+
+    def __init__(self, mesh, nref=None, *, n=None, manifold_style=None, ctx=None, _handle=None):
+        self.ctx = ctx or get_context()
+        self.lib = self.ctx.lib
+        self.mesh = mesh
+        self.manifold_style = manifold_style or IntrinsicManifold()
+        if _handle is not None:
+            self.h = _handle
+            self.n = 0
+        else:
+            if n is None:
+                if nref is None:
+                    raise ValueError("give nref or n")
+                n = 2 ** int(nref)
+            self.n = int(n)
+            h = C.c_void_p()
+            _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, 0, C.byref(h)))
+            self.h = h
+        nc, nn, ne = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_mesh_info(self.h, C.byref(nc), C.byref(nn), C.byref(ne)))
+        self.num_cells, self.num_nodes, self.num_edges = nc.value, nn.value, ne.value
+
+    @classmethod
+    def from_arrays(cls, mesh, cell_to_chart, cell_chart_coords, cell_node_ids, n_nodes, ctx=None, manifold_style=None):
+        """Connectivity owned by the caller (1-based ids, as Gridap Tables)."""
+        ctx = ctx or get_context()
+        c2c = np.ascontiguousarray(cell_to_chart, dtype=np.int32)
+        xy = np.ascontiguousarray(cell_chart_coords, dtype=np.float64)
+        cn = np.ascontiguousarray(cell_node_ids, dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(ctx.lib.gg_mesh_from_arrays(ctx.h, 2, len(c2c), int(n_nodes), _ip32(c2c), _dp(xy), _ip32(cn), mesh.radius, 0.0, C.byref(h)))
+        return cls(mesh, ctx=ctx, manifold_style=manifold_style, _handle=h)
+
+    def restrict(self, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_mesh_restrict(self.h, len(cells), _ip64(cells), C.byref(h)))
+        return AtlasDiscreteModel(self.mesh, ctx=self.ctx, manifold_style=self.manifold_style, _handle=h)
+
+    def ghost_cells(self, first, last):
+        n = C.c_int64()
+        _lib.check(self.lib.gg_mesh_ghost_cells(self.h, first, last, C.byref(n), None))
+        out = np.empty(n.value, dtype=np.int64)
+        _lib.check(self.lib.gg_mesh_ghost_cells(self.h, first, last, C.byref(n), _ip64(out)))
+        return out
+
+    def get_cell_node_ids(self):
+        out = np.empty((self.num_cells, 4), dtype=np.int32)
+        _lib.check(self.lib.gg_mesh_get_cell_nodes(self.h, _ip32(out)))
+        return out
+
+    def get_cell_to_chart(self):
+        out = np.empty(self.num_cells, dtype=np.int32)
+        _lib.check(self.lib.gg_mesh_get_cell_to_chart(self.h, _ip32(out)))
+        return out
+
+    def get_cell_coordinates(self):
+        out = np.empty((self.num_cells, 4, 2))
+        _lib.check(self.lib.gg_mesh_get_chart_coords(self.h, _dp(out)))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.lib.gg_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+def partition_range(num_cells, nparts, part):
+    """Owned cell range of the reference's linear partition (AtlasDistributedDiscreteModels.jl:31), 0-based [first,last)."""
+    lib = _lib.load()
+    a, b = C.c_int64(), C.c_int64()
+    _lib.check(lib.gg_partition_range(num_cells, nparts, part, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def num_cells(model):
+    return model.num_cells
+
+
+def get_sphere_radius(model):
+    return model.mesh.radius
+
+
+def dx(model):
+    """src/ConvergenceTools/Tools.jl:228-232."""
+    return math.sqrt(4 * math.pi * model.mesh.radius ** 2 / model.num_cells)
+
+
+class Triangulation:
+    def __init__(self, model):
+        self.model = model
+
+
+class Measure:
+    """Measure(Ω, degree): tensor Gauss-Legendre rule with ceil((degree+1)/2) points per direction."""
+
+    def __init__(self, trian, degree):
+        self.trian = trian
+        self.model = trian.model
+        self.degree = int(degree)
+        self.nq1 = (self.degree + 2) // 2
+        self.num_points = self.nq1 ** 2
+
+    def quadrature_points(self, chart=True, ambient=True):
+        m = self.model
+        ch = np.empty((m.num_cells, self.num_points, 2)) if chart else None
+        xyz = np.empty((m.num_cells, self.num_points, 3)) if ambient else None
+        _lib.check(m.lib.gg_quadrature_points(m.h, self.degree, _dp(ch) if chart else None, _dp(xyz) if ambient else None))
+        return ch, xyz
+
+    def integrate(self, fq=None):
+        """sum(∫(f * meas_cf)dΩ) with f given at the quadrature points (None = 1)."""
+        m = self.model
+        out = C.c_double()
+        v = DeviceVector.from_numpy(m.ctx, np.ascontiguousarray(fq, dtype=np.float64).reshape(-1)) if fq is not None else None
+        _lib.check(m.lib.gg_integrate(m.h, self.degree, v.h if v is not None else None, C.byref(out)))
+        return out.value
+
+
+def ReferenceFE(name, T, order):
+    return (name, int(order))
+
+
+class FESpace:
+    def __init__(self, model, kind, order, constraint=0, _handle=None):
+        self.model = model
+        self.lib = model.lib
+        self.kind, self.order = kind, order
+        if _handle is None:
+            h = C.c_void_p()
+            _lib.check(self.lib.gg_space_builtin(model.h, kind, order, constraint, C.byref(h)))
+            _handle = h
+        self.h = _handle
+        nf, ml, nd = C.c_int64(), C.c_int32(), C.c_int64()
+        _lib.check(self.lib.gg_space_info(self.h, C.byref(nf), C.byref(ml), C.byref(nd)))
+        self.num_free_dofs, self.ndofs_loc, self.num_dirichlet_dofs = nf.value, ml.value, nd.value
+
+    @classmethod
+    def from_arrays(cls, model, kind, order, n_free, cell_dof_ids, cell_dof_signs=None):
+        ids = np.ascontiguousarray(cell_dof_ids, dtype=np.int32)
+        sg = None if cell_dof_signs is None else np.ascontiguousarray(cell_dof_signs, dtype=np.int8)
+        h = C.c_void_p()
+        _lib.check(model.lib.gg_space_from_arrays(model.h, kind, order, int(n_free), _ip32(ids),
+                                                  None if sg is None else sg.ctypes.data_as(C.POINTER(C.c_int8)), C.byref(h)))
+        return cls(model, kind, order, _handle=h)
+
+    def get_cell_dof_ids(self):
+        out = np.empty((self.model.num_cells, self.ndofs_loc), dtype=np.int32)
+        _lib.check(self.lib.gg_space_get_cell_dofs(self.h, _ip32(out)))
+        return out
+
+    def get_cell_dof_signs(self):
+        out = np.empty((self.model.num_cells, self.ndofs_loc), dtype=np.int8)
+        _lib.check(self.lib.gg_space_get_cell_signs(self.h, out.ctypes.data_as(C.POINTER(C.c_int8))))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.model.ctx.h:
+                self.lib.gg_space_destroy(self.h)
+        except Exception:
+            pass
+
+
+def TestFESpace(model_or_trian, reffe, conformity="H1", constraint=None):
+    model = model_or_trian.model if isinstance(model_or_trian, Triangulation) else model_or_trian
+    name, order = reffe
+    conformity = conformity.lstrip(":")
+    if name == lagrangian:
+        kind = {"H1": _lib.SPACE_CG, "L2": _lib.SPACE_DG}[conformity]
+    elif name == raviart_thomas:
+        kind = _lib.SPACE_RT
+    else:
+        raise ValueError(f"unknown reference FE {name}")
+    cons = {None: 0, "zeromean": 1, ":zeromean": 1}[constraint]
+    return FESpace(model, kind, order, cons)
+
+
+def TrialFESpace(V):
+    return V
+
+
+def num_free_dofs(V):
+    return V.num_free_dofs
+
+
+# ---- device vectors / matrices --------------------------------------------------------------------------
+
+class DeviceVector:
+    def __init__(self, ctx, n):
+        self.ctx, self.lib, self.n = ctx, ctx.lib, int(n)
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_vec_create(ctx.h, self.n, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_numpy(cls, ctx, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        v = cls(ctx, a.size)
+        v.set(a)
+        return v
+
+    def set(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        assert a.size == self.n
+        _lib.check(self.lib.gg_vec_set(self.h, _dp(a)))
+
+    def get(self, out=None):
+        out = np.empty(self.n) if out is None else out
+        _lib.check(self.lib.gg_vec_get(self.h, _dp(out)))
+        return out
+
+    def fill(self, v):
+        _lib.check(self.lib.gg_vec_fill(self.h, float(v)))
+
+    @property
+    def device_ptr(self):
+        return self.lib.gg_vec_device_ptr(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.lib.gg_vec_destroy(self.h)
+        except Exception:
+            pass
+
+
+class CSRMatrix:
+    """Device CSR matrix with a fixed pattern (`gg_pattern`); `to_scipy()` exports it."""
+
+    def __init__(self, test, trial):
+        self.test, self.trial = test, trial
+        self.ctx, self.lib = test.model.ctx, test.lib
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_pattern(test.h, trial.h, C.byref(h)))
+        self.h = h
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_csr_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        self.shape, self.nnz = (a.value, b.value), c.value
+
+    def pattern(self, index_base=0):
+        rp = np.empty(self.shape[0] + 1, dtype=np.int64)
+        ci = np.empty(self.nnz, dtype=np.int64)
+        _lib.check(self.lib.gg_csr_export(self.h, _ip64(rp), _ip64(ci), None, index_base))
+        return rp, ci
+
+    def values(self, out=None):
+        out = np.empty(self.nnz) if out is None else out
+        _lib.check(self.lib.gg_csr_export(self.h, None, None, _dp(out), 0))
+        return out
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        rp, ci = self.pattern()
+        return sp.csr_matrix((self.values(), ci, rp), shape=self.shape)
+
+    def spmv(self, x, y, alpha=1.0, beta=0.0):
+        _lib.check(self.lib.gg_csr_spmv(self.h, alpha, x.h, beta, y.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.lib.gg_csr_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ---- forms -----------------------------------------------------------------------------------------------
+
+class Form:
+    form_id = None
+    bilinear = True
+
+    def __init__(self, dΩ, u=None, qdata=None, dirichlet=0.0, scale=1.0):
+        self.dΩ, self.u, self.qdata, self.dirichlet, self.scale = dΩ, u, qdata, dirichlet, scale
+        self._keep = []
+
+    def args(self, test, trial):
+        ctx = test.model.ctx
+        a = _lib.FormArgs()
+        a.test = test.h
+        a.trial = trial.h if trial is not None else None
+        a.degree = self.dΩ.degree
+        self._keep = []
+        for name in ("u", "qdata"):
+            v = getattr(self, name)
+            if v is not None and not isinstance(v, DeviceVector):
+                v = DeviceVector.from_numpy(ctx, v)
+            self._keep.append(v)
+            setattr(a, name, v.h if v is not None else None)
+        a.dirichlet = self.dirichlet
+        a.scale = self.scale
+        return a
+
+
+class LaplaceBeltrami(Form):
+    """a(u,v) = ∫( ∇(v)⋅(inv_metric_cf⋅∇(u)) * meas_cf )dΩ -- test/Laplacian/LaplaceBeltrami.jl:47.
+    With `extrinsic=True`: a(u,v) = ∫( ∇(v)⋅∇(u) )dΩ on the ExtrinsicManifold model (AmbientLaplaceBeltrami.jl:44)."""
+
+    def __init__(self, dΩ, extrinsic=None, **kw):
+        super().__init__(dΩ, **kw)
+        if extrinsic is None:
+            extrinsic = isinstance(dΩ.model.manifold_style, ExtrinsicManifold)
+        self.form_id = _lib.FORM_LAPLACE_BELTRAMI_EXTRINSIC if extrinsic else _lib.FORM_LAPLACE_BELTRAMI
+
+
+class Helmholtz(Form):
+    """a(u,v) = ∫(u*v*meas_cf)dΩ - ∫( ∇(v)⋅(inv_metric_cf⋅∇(u)) * meas_cf )dΩ -- test/Laplacian/Helmholtz.jl:43."""
+    form_id = _lib.FORM_HELMHOLTZ
+
+
+class ScalarMass(Form):
+    """m(p,q) = ∫( (q*p)*meas_cf )dΩ (optionally times a coefficient given at the quadrature points)."""
+    form_id = _lib.FORM_MASS_SCALAR
+
+
+class RTMass(Form):
+    """m(u,v) = ∫( (v⋅(metric_cf⋅u))*(1.0/meas_cf) )dΩ -- test/Transient/TransientWaveEquation.jl:63."""
+    form_id = _lib.FORM_MASS_RT
+
+
+class Div(Form):
+    """b(u,q) = ∫( q*(∇⋅u) )dΩ -- test/Transient/TransientWaveEquation.jl:64."""
+    form_id = _lib.FORM_DIV
+
+
+class Source(Form):
+    """l(v) = ∫( (f*v)*meas_cf )dΩ with f at the quadrature points -- test/Laplacian/LaplaceBeltrami.jl:53."""
+    form_id = _lib.FORM_SOURCE
+    bilinear = False
+
+    def __init__(self, dΩ, fq, **kw):
+        super().__init__(dΩ, qdata=np.ascontiguousarray(fq, dtype=np.float64).reshape(-1), **kw)
+
+
+# ---- assembly ---------------------------------------------------------------------------------------------
+
+class SparseMatrixAssembler:
+    """SparseMatrixAssembler(U, V): owns the device CSR pattern (built once) and the numeric-phase maps."""
+
+    def __init__(self, U, V):
+        self.trial, self.test = U, V
+        self.matrix = CSRMatrix(V, U)
+
+
+def allocate_matrix(assem):
+    return assem.matrix
+
+
+def assemble_matrix(form, U_or_assem, V=None, add=False):
+    """assemble_matrix(a, U, V) / assemble_matrix!(A, assem, ...): numeric phase on the device."""
+    assem = U_or_assem if isinstance(U_or_assem, SparseMatrixAssembler) else SparseMatrixAssembler(U_or_assem, V)
+    A = assem.matrix
+    args = form.args(assem.test, assem.trial)
+    _lib.check(A.lib.gg_assemble_matrix(form.form_id, C.byref(args), A.h, 1 if add else 0))
+    A._assembler = assem
+    return A
+
+
+def assemble_vector(form, V, U=None, out=None, add=False):
+    """assemble_vector(l, V).  For a bilinear form with `form.u` set this is the residual a(u_h, v)."""
+    ctx = V.model.ctx
+    b = out if out is not None else DeviceVector(ctx, V.num_free_dofs)
+    trial = U if U is not None else (V if form.bilinear else None)
+    args = form.args(V, trial)
+    _lib.check(V.lib.gg_assemble_vector(form.form_id, C.byref(args), b.h, 1 if add else 0))
+    return b
+
+
+def assemble_matrix_and_vector(form, assem, b=None):
+    """Jacobian and residual in one pass over the cells (A = a(.,.), b_i = a(u_h, φ_i))."""
+    A = assem.matrix
+    b = b if b is not None else DeviceVector(A.ctx, assem.test.num_free_dofs)
+    args = form.args(assem.test, assem.trial)
+    _lib.check(A.lib.gg_assemble_matrix_and_vector(form.form_id, C.byref(args), A.h, b.h))
+    return A, b
+
+
+def element_matrices(form, U, V, first=0, n=None):
+    n = V.model.num_cells - first if n is None else n
+    out = np.empty((n, V.ndofs_loc, U.ndofs_loc))
+    args = form.args(V, U)
+    _lib.check(V.lib.gg_element_matrices(form.form_id, C.byref(args), first, n, _dp(out)))
+    return out
+
+
+def element_vectors(form, V, U=None, first=0, n=None):
+    n = V.model.num_cells - first if n is None else n
+    out = np.empty((n, V.ndofs_loc))
+    trial = U if U is not None else (V if form.bilinear else None)
+    args = form.args(V, trial)
+    _lib.check(V.lib.gg_element_vectors(form.form_id, C.byref(args), first, n, _dp(out)))
+    return out
+
+
+def eval_geometry(panel, radius, pts, ctx=None):
+    """Device evaluation of CubedSphereMap / its Jacobian / metric / inverse metric / sqrt(det g) at chart points."""
+    ctx = ctx or get_context()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+    n = pts.shape[0]
+    xyz, jac, g, gi, sq = np.empty((n, 3)), np.empty((n, 2, 3)), np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+    _lib.check(ctx.lib.gg_eval_geometry(ctx.h, panel, radius, n, _dp(pts), _dp(xyz), _dp(jac), _dp(g), _dp(gi), _dp(sq)))
+    return xyz, jac, g, gi, sq
+
+
+class AffineFEOperator:
+    """AffineFEOperator(a, l, U, V): assembles A and b on the device (test/Laplacian/LaplaceBeltrami.jl:68)."""
+
+    def __init__(self, a, l, U, V):
+        self.assem = SparseMatrixAssembler(U, V)
+        self.A = assemble_matrix(a, self.assem)
+        self.b = assemble_vector(l, V)
+
+    def get_matrix(self):
+        return self.A
+
+    def get_vector(self):
+        return self.b
+
+
+# ---- linear solver ------------------------------------------------------------------------------------------
+
+class CGSolver:
+    """CGSolver(JacobiLinearSolver(); rtol) on the device (persistent single-launch PCG)."""
+
+    def __init__(self, rtol=1e-12, maxiter=2000):
+        self.rtol, self.maxiter = rtol, maxiter
+
+    def numerical_setup(self, A):
+        return NumericalSetup(self, A)
+
+
+class NumericalSetup:
+    def __init__(self, ls, A):
+        self.A, self.lib = A, A.lib
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_solver_pcg_create(A.h, ls.rtol, ls.maxiter, C.byref(h)))
+        self.h = h
+        self.iterations, self.rel_res = 0, 0.0
+
+    def update(self):
+        _lib.check(self.lib.gg_solver_update(self.h))
+
+    def solve(self, b, x=None):
+        x = x if x is not None else DeviceVector(self.A.ctx, self.A.shape[0])
+        it, rr = C.c_int32(), C.c_double()
+        _lib.check(self.lib.gg_solver_solve(self.h, b.h, x.h, C.byref(it), C.byref(rr)))
+        self.iterations, self.rel_res = it.value, rr.value
+        return x
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.A.ctx.h:
+                self.lib.gg_solver_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ---- explicit Runge-Kutta (linear wave) -------------------------------------------------------------------
+
+TABLEAUS = {  # Gridap names
+    "EXRK_SSP_3_3": ([[0, 0, 0], [1, 0, 0], [0.25, 0.25, 0]], [1 / 6, 1 / 6, 2 / 3], [0, 1, 0.5]),
+    "EXRK_SSP_2_2": ([[0, 0], [1, 0]], [0.5, 0.5], [0, 1.0]),
+    "EXRK_Euler_1_1": ([[0.0]], [1.0], [0.0]),
+}
+
+
+class RungeKutta:
+    """RungeKutta(ls, ls, dt, :EXRK_SSP_3_3)."""
+
+    def __init__(self, sysslvr, sysslvr2, dt, tableau):
+        self.ls = sysslvr
+        self.dt = float(dt)
+        self.tableau = tableau.lstrip(":")
+
+
+class WaveOperator:
+    """TransientSemilinearFEOperator(mass, res, (jac, jac_t), X, Y, constant_mass=true) of the linear wave driver
+    (test/Transient/TransientWaveEquation.jl:63-68) for X = RT_p x DG_p."""
+
+    def __init__(self, model, p_fe, degree=None):
+        self.model, self.p_fe = model, p_fe
+        self.degree = 5 * (p_fe + 1) if degree is None else degree
+
+
+class WaveStepper:
+    def __init__(self, solver, op):
+        m = op.model
+        self.lib, self.ctx = m.lib, m.ctx
+        A, b, c = TABLEAUS[solver.tableau]
+        s = len(b)
+        self._A = (C.c_double * (s * s))(*[float(v) for row in A for v in row])
+        self._b = (C.c_double * s)(*[float(v) for v in b])
+        self._c = (C.c_double * s)(*[float(v) for v in c])
+        a = _lib.RKArgs()
+        a.problem, a.order, a.degree, a.n_stages = _lib.PROBLEM_WAVE, op.p_fe, op.degree, s
+        a.A, a.b, a.c = self._A, self._b, self._c
+        a.dt = solver.dt
+        a.rtol = getattr(solver.ls, "rtol", 1e-12) or 1e-12
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_rk_create(m.h, C.byref(a), C.byref(h)))
+        self.h = h
+        self._model = m
+        nu, np_ = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_rk_info(self.h, C.byref(nu), C.byref(np_)))
+        self.nu, self.np_ = nu.value, np_.value
+        self.dt = solver.dt
+
+    def set_state(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.nu + self.np_
+        _lib.check(self.lib.gg_rk_set_state(self.h, _dp(x)))
+
+    def get_state(self, out=None):
+        out = np.empty(self.nu + self.np_) if out is None else out
+        _lib.check(self.lib.gg_rk_get_state(self.h, _dp(out)))
+        return out
+
+    def step(self, n=1):
+        _lib.check(self.lib.gg_rk_step(self.h, int(n)))
+
+    def residual(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.empty_like(x)
+        _lib.check(self.lib.gg_rk_residual(self.h, _dp(x), _dp(r)))
+        return r
+
+    def stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_rk_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @property
+    def state_device_ptr(self):
+        return self.lib.gg_rk_state_device_ptr(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.lib.gg_rk_destroy(self.h)
+        except Exception:
+            pass
+
+
+def gridap_num_steps(t0, tF, dt):
+    """Steps taken by Gridap's ODE-solution iterator: stop when t >= tF - 100 eps, t accumulated as t += dt."""
+    eps = 100 * np.finfo(np.float64).eps
+    t, n = t0, 0
+    while not (t >= tF - eps):
+        t = t + dt
+        n += 1
+    return n
+
+
+def solve(solver, op, t0, tF, x0):
+    """solve(RungeKutta(...), op, t0, tF, xh0): marches to tF on the device, returns (tF, x_F, stepper)."""
+    st = WaveStepper(solver, op)
+    st.set_state(x0)
+    n = gridap_num_steps(t0, tF, solver.dt)
+    st.step(n)
+    return t0 + n * solver.dt, st.get_state(), st

@@ -1,0 +1,185 @@
+// Internal declarations shared by the translation units of libgeosgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+#include <stdexcept>
+
+#include "../../include/geosgpu.h"
+
+namespace gg {
+
+// ---- error handling: C++ exceptions inside, codes at the ABI ---------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+#define GG_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      throw gg::Error(GG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                                       ":" + std::to_string(__LINE__) + ")");                           \
+  } while (0)
+#define GG_REQUIRE(cond, code, msg)              \
+  do {                                           \
+    if (!(cond)) throw gg::Error((code), (msg)); \
+  } while (0)
+// wraps the body of every extern "C" entry point
+#define GG_API_BEGIN try {
+#define GG_API_END                         \
+  }                                        \
+  catch (const gg::Error& e) {             \
+    gg::set_last_error(e.what());          \
+    return e.code;                         \
+  }                                        \
+  catch (const std::bad_alloc&) {          \
+    gg::set_last_error("host out of memory"); \
+    return GG_ERR_NOMEM;                   \
+  }                                        \
+  catch (const std::exception& e) {        \
+    gg::set_last_error(e.what());          \
+    return GG_ERR_INVALID;                 \
+  }                                        \
+  return GG_OK;
+
+// ---- device buffer ------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) {
+      cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+      if (e != cudaSuccess) { p = nullptr; n = 0; throw Error(GG_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    }
+  }
+  void upload(const T* h, size_t cnt, cudaStream_t s) {
+    if (cnt != n) alloc(cnt);
+    if (cnt) GG_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T* h, cudaStream_t s) const {
+    if (n) GG_CUDA(cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    GG_CUDA(cudaStreamSynchronize(s));
+  }
+};
+
+}  // namespace gg
+
+// ---- handle types (opaque at the ABI) ---------------------------------------------------------------
+namespace gg { struct FormTab; }
+struct gg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // device tabulations of reference bases at quadrature points, keyed by (kind, order, nq)
+  std::map<uint64_t, std::shared_ptr<gg::FormTab>> tabs;
+  // scratch: entry-major element matrix / vector buffers, grown on demand and reused across calls
+  gg::DevBuf<double> ebuf, vbuf;
+  // (order, nq) currently resident in the __constant__ tables of the fast scalar kernels
+  int const_order = -1, const_nq = -1;
+};
+
+// Reference-element tables for one (order, nq) pair, host copies; see gg_refel.cu
+struct gg_tables;
+
+struct gg_mesh {
+  gg_ctx* ctx = nullptr;
+  int dim = 2;
+  int n = 0;  // cells per panel edge if built by gg_mesh_cubed_sphere, else 0
+  double radius = 1.0, thickness = 0.0;
+  int64_t n_cells = 0, n_nodes = 0, n_edges = 0;
+  // host copies (0-based)
+  std::vector<int32_t> cell_nodes;     // [n_cells][4]
+  std::vector<int32_t> cell_to_chart;  // [n_cells] 0-based panel
+  std::vector<double> chart_coords;    // [n_cells][4][2]
+  std::vector<int32_t> cell_edges;     // [n_cells][4] edge ids by first encounter
+  std::vector<int8_t> cell_edge_flip;  // [n_cells][4]
+  std::vector<int32_t> edge_cells;     // [n_edges][2] cells around the edge in increasing id (-1 if none)
+  // device: per-cell axis-aligned chart box (SoA) and panel
+  gg::DevBuf<double> d_x0, d_y0, d_hx, d_hy;
+  gg::DevBuf<int32_t> d_chart;
+  bool topology_built = false;
+};
+
+struct gg_space {
+  gg_mesh* mesh = nullptr;
+  int kind = 0, order = 0, constraint = 0;
+  int ndofs_loc = 0;
+  int64_t n_free = 0, n_dirichlet = 0;
+  std::vector<int32_t> cell_dofs;  // [n_cells][ndofs_loc], 0-based, -1 = Dirichlet
+  std::vector<int8_t> cell_signs;  // [n_cells][ndofs_loc] (RT) or empty
+  gg::DevBuf<int32_t> d_cell_dofs; // same layout on the device
+  gg::DevBuf<int8_t> d_cell_signs;
+  // local dof -> tensor multi-index (Lagrangian): lex index ix + (order+1)*iy
+  std::vector<int32_t> loc2lex;
+  // DOF -> contributing (cell, local) lists for atomic-free vector assembly
+  gg::DevBuf<int32_t> d_vptr;  // [n_free+1]
+  gg::DevBuf<int32_t> d_vsrc;  // [n_entries] = local*n_cells + cell (entry-major element-vector buffer index)
+  bool vec_map_built = false;
+};
+
+struct gg_vec {
+  gg_ctx* ctx = nullptr;
+  gg::DevBuf<double> d;
+};
+
+struct gg_csr {
+  gg_ctx* ctx = nullptr;
+  gg_space* test = nullptr;
+  gg_space* trial = nullptr;
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  gg::DevBuf<int32_t> d_rowptr;  // [n_rows+1]
+  gg::DevBuf<int32_t> d_colind;  // [nnz]
+  gg::DevBuf<double> d_vals;     // [nnz]
+  // numeric-phase maps: slot -> sources in the element-matrix buffer
+  gg::DevBuf<int32_t> d_sptr;    // [nnz+1]
+  gg::DevBuf<int32_t> d_ssrc;    // [n_pairs_kept] raw pair id = cell*(mt*mu) + (i*mu+j)
+  int64_t n_pairs = 0;
+  // cache of ssrc re-encoded for a given element-buffer layout (symmetric packed / full, entry-major)
+  int cached_layout = -1;
+  gg::DevBuf<int32_t> d_ssrc_layout;
+};
+
+struct gg_solver {
+  gg_csr* A = nullptr;
+  double rtol = 1e-12;
+  int max_iter = 1000;
+  gg::DevBuf<double> dinv, r, z, p, Ap, partials;
+  gg::DevBuf<double> stats;  // [0] iterations of the last solve, [1] its relative residual
+  int grid = 0, block = 256;
+};
+
+namespace gg {
+// internal entry points shared between translation units
+void build_vec_map(gg_space* s);
+void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);
+void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int add);
+const double* element_matrices_device(gg_form form, const gg_form_args* args, int* layout);
+void spmv(gg_csr* A, double alpha, const double* x, double beta, double* y);
+void solver_update(gg_solver* s);
+void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x);
+}  // namespace gg

@@ -1,0 +1,696 @@
+// Numeric phase: cell-wise quadrature -> element matrices / vectors -> atomic-free gather into CSR / DOF vectors.
+//
+// Replaces Gridap's collect_cell_matrix / collect_cell_vector + assemble_* on the forms of the reference's
+// drivers (src/ODEs/ODEs.jl:33-39; forms: test/Laplacian/LaplaceBeltrami.jl:47,53, test/Laplacian/Helmholtz.jl:43,
+// test/AmbientModel/AmbientLaplaceBeltrami.jl:44, test/Transient/TransientWaveEquation.jl:63-66).
+// Two kernel families:
+//   * gg_lb_fast.cuh: the hot sum-factorised one-thread-per-cell kernels for scalar Q1/Q2 stiffness forms;
+//   * the generic kernels below (one thread per (cell, test dof), tabulated bases) for every other supported
+//     (space, order, degree, form) combination.  Both are CUDA; nothing falls back to the host.
+#include <cub/cub.cuh>
+#include <cstring>
+#include "gg_common.cuh"
+#include "gg_refel.cuh"
+#include "gg_geom.cuh"
+#include "gg_lb_fast.cuh"
+
+namespace gg {
+
+void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int add);
+void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- device tabulations ---------------------------------------------------------------------------------
+struct FormTab {
+  int kind, order, nq, Q, m;
+  DevBuf<double> xi, w;  // 1-D rule on [0,1]
+  DevBuf<double> val;    // scalar: [Q][m]      RT: [Q][m][2]
+  DevBuf<double> der;    // scalar: [Q][m][2]   RT: [Q][m] (divergence)
+};
+
+static std::shared_ptr<FormTab> get_tab(gg_ctx* ctx, int kind, int order, int nq) {
+  int k = kind == GG_SPACE_RT ? 1 : 0;
+  uint64_t key = ((uint64_t)k << 32) | ((uint64_t)order << 16) | (uint64_t)nq;
+  auto it = ctx->tabs.find(key);
+  if (it != ctx->tabs.end()) return it->second;
+  GG_REQUIRE(nq >= 1 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high (max 31)");
+  auto T = std::make_shared<FormTab>();
+  T->kind = k; T->order = order; T->nq = nq; T->Q = nq * nq;
+  std::vector<double> xi(nq), w(nq);
+  gauss_legendre_01(nq, xi.data(), w.data());
+  std::vector<double> val, der;
+  if (k == 0) {
+    int nb = order + 1, m = nb * nb;
+    T->m = m;
+    std::vector<int32_t> l2x = quad_local_to_lex(order);
+    val.resize((size_t)T->Q * m);
+    der.resize((size_t)T->Q * m * 2);
+    std::vector<double> N(nq * nb), D(nq * nb);
+    for (int q = 0; q < nq; ++q) lagrange_1d(order, xi[q], &N[q * nb], &D[q * nb]);
+    for (int q2 = 0; q2 < nq; ++q2)
+      for (int q1 = 0; q1 < nq; ++q1) {
+        int q = q1 + nq * q2;
+        for (int a = 0; a < m; ++a) {
+          int ix = l2x[a] % nb, iy = l2x[a] / nb;
+          val[(size_t)q * m + a] = N[q1 * nb + ix] * N[q2 * nb + iy];
+          der[((size_t)q * m + a) * 2 + 0] = D[q1 * nb + ix] * N[q2 * nb + iy];
+          der[((size_t)q * m + a) * 2 + 1] = N[q1 * nb + ix] * D[q2 * nb + iy];
+        }
+      }
+  } else {
+    RTRef R = build_rt_ref(order);
+    T->m = R.ndofs;
+    std::vector<double> pts((size_t)T->Q * 2);
+    for (int q2 = 0; q2 < nq; ++q2)
+      for (int q1 = 0; q1 < nq; ++q1) {
+        pts[2 * (q1 + nq * q2)] = xi[q1];
+        pts[2 * (q1 + nq * q2) + 1] = xi[q2];
+      }
+    R.tabulate(T->Q, pts.data(), val, der);
+  }
+  cudaStream_t st = ctx->stream;
+  T->xi.upload(xi, st); T->w.upload(w, st); T->val.upload(val, st); T->der.upload(der, st);
+  GG_CUDA(cudaStreamSynchronize(st));
+  ctx->tabs[key] = T;
+  return T;
+}
+
+struct Geo {
+  int64_t nc;
+  const double *x0, *y0, *hx, *hy;
+  const int32_t* chart;
+  double radius;
+};
+static Geo geo_of(gg_mesh* m) { return {m->n_cells, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->d_chart.p, m->radius}; }
+
+// ---- generic kernels: one thread per (cell, test dof) -----------------------------------------------------
+
+// Ke[I][J] = sum_q w hx hy [ cM * qcoef * v_I u_J sqrtg  +  cK * grad v_I . ginv grad u_J sqrtg ]
+template <int MU, bool EXTRINSIC>
+__global__ void __launch_bounds__(128)
+k_scalar_matrix(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w, int mt,
+                const double* __restrict__ tval, const double* __restrict__ tder, const double* __restrict__ uval,
+                const double* __restrict__ uder, double cM, double cK, const double* __restrict__ qcoef,
+                double* __restrict__ ebuf) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nc * mt) return;
+  int I = (int)(t / g.nc);
+  int64_t c = t - (int64_t)I * g.nc;
+  const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
+  const int panel = g.chart[c];
+  double acc[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) acc[j] = 0.0;
+  double ta[MAX_NQ];
+  for (int q = 0; q < nq; ++q) ta[q] = tan(fma(HX, xi[q], X0));
+  const int Q = nq * nq;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], Y0));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      const double a = ta[q1];
+      Metric2 m = EXTRINSIC ? extrinsic_metric_terms(panel, a, b, g.radius) : csphere_metric_terms(a, b, g.radius);
+      const double dV = w[q1] * w[q2] * HX * HY * m.sqrtg;
+      const double vI = tval[q * mt + I];
+      const double gx = tder[(q * mt + I) * 2] / HX, gy = tder[(q * mt + I) * 2 + 1] / HY;
+      const double fx = cK * dV * (m.i11 * gx + m.i12 * gy), fy = cK * dV * (m.i12 * gx + m.i22 * gy);
+      double fm = cM * dV * vI;
+      if (qcoef) fm *= qcoef[c * Q + q];
+#pragma unroll
+      for (int j = 0; j < MU; ++j) {
+        double v = acc[j];
+        v = fma(fm, uval[q * MU + j], v);
+        v = fma(fx / HX, uder[(q * MU + j) * 2], v);
+        v = fma(fy / HY, uder[(q * MU + j) * 2 + 1], v);
+        acc[j] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MU; ++j) ebuf[(int64_t)(I * MU + j) * g.nc + c] = acc[j];
+}
+
+// RT mass: Ke[I][J] = sum_q w hx hy (v_I . g u_J) / sqrtg, contravariant Piola u = (uhat_x/hy, uhat_y/hx) * sign
+template <int MU>
+__global__ void __launch_bounds__(128)
+k_rt_mass_matrix(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w,
+                 const double* __restrict__ val, const int8_t* __restrict__ signs, double* __restrict__ ebuf) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nc * MU) return;
+  int I = (int)(t / g.nc);
+  int64_t c = t - (int64_t)I * g.nc;
+  const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
+  double acc[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) acc[j] = 0.0;
+  double ta[MAX_NQ];
+  for (int q = 0; q < nq; ++q) ta[q] = tan(fma(HX, xi[q], X0));
+  const double sI = signs[c * MU + I];
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], Y0));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      Metric2 m = csphere_metric_terms(ta[q1], b, g.radius);
+      const double dV = w[q1] * w[q2] * HX * HY / m.sqrtg;
+      const double vx = sI * val[(q * MU + I) * 2] / HY, vy = sI * val[(q * MU + I) * 2 + 1] / HX;
+      const double fx = dV * (m.g11 * vx + m.g12 * vy) / HY, fy = dV * (m.g12 * vx + m.g22 * vy) / HX;
+#pragma unroll
+      for (int j = 0; j < MU; ++j)
+        acc[j] = fma(fx, val[(q * MU + j) * 2], fma(fy, val[(q * MU + j) * 2 + 1], acc[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MU; ++j) ebuf[(int64_t)(I * MU + j) * g.nc + c] = acc[j] * (double)signs[c * MU + j];
+}
+
+// div: Ke[I][J] = sum_q w q_I divhat(uhat_J) sign_J   (the Jacobian determinant cancels)
+template <int MU>
+__global__ void __launch_bounds__(128)
+k_div_matrix(int64_t nc, int nq, const double* __restrict__ w, int mt, const double* __restrict__ tval,
+             const double* __restrict__ udiv, const int8_t* __restrict__ signs, double* __restrict__ ebuf) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * mt) return;
+  int I = (int)(t / nc);
+  int64_t c = t - (int64_t)I * nc;
+  double acc[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) acc[j] = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2)
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      const double f = w[q1] * w[q2] * tval[q * mt + I];
+#pragma unroll
+      for (int j = 0; j < MU; ++j) acc[j] = fma(f, udiv[q * MU + j], acc[j]);
+    }
+#pragma unroll
+  for (int j = 0; j < MU; ++j) ebuf[(int64_t)(I * MU + j) * nc + c] = acc[j] * (double)signs[c * MU + j];
+}
+
+// fe[I] = sum_q w hx hy sqrtg f_q v_I
+__global__ void __launch_bounds__(128)
+k_source_vector(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w, int mt,
+                const double* __restrict__ tval, const double* __restrict__ qdata, double* __restrict__ vbuf) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nc * mt) return;
+  int I = (int)(t / g.nc);
+  int64_t c = t - (int64_t)I * g.nc;
+  const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
+  double ta[MAX_NQ];
+  for (int q = 0; q < nq; ++q) ta[q] = tan(fma(HX, xi[q], X0));
+  const int Q = nq * nq;
+  double acc = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], Y0));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      Metric2 m = csphere_metric_terms(ta[q1], b, g.radius);
+      acc = fma(w[q1] * w[q2] * HX * HY * m.sqrtg * qdata[c * Q + q], tval[q * mt + I], acc);
+    }
+  }
+  vbuf[(int64_t)I * g.nc + c] = acc;
+}
+
+// generic action of the scalar forms: fe[I] = sum_q dV [ cM v_I u_h + cK grad v_I . ginv grad u_h ]
+template <int MU, bool EXTRINSIC>
+__global__ void __launch_bounds__(128)
+k_scalar_action(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w, int mt,
+                const double* __restrict__ tval, const double* __restrict__ tder, const double* __restrict__ uval,
+                const double* __restrict__ uder, double cM, double cK, const int32_t* __restrict__ udofs,
+                const double* __restrict__ u, double dirichlet, double* __restrict__ vbuf) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nc * mt) return;
+  int I = (int)(t / g.nc);
+  int64_t c = t - (int64_t)I * g.nc;
+  const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
+  const int panel = g.chart[c];
+  double ue[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) {
+    int32_t d = udofs[c * MU + j];
+    ue[j] = d >= 0 ? u[d] : dirichlet;
+  }
+  double ta[MAX_NQ];
+  for (int q = 0; q < nq; ++q) ta[q] = tan(fma(HX, xi[q], X0));
+  double acc = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], Y0));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      Metric2 m = EXTRINSIC ? extrinsic_metric_terms(panel, ta[q1], b, g.radius) : csphere_metric_terms(ta[q1], b, g.radius);
+      double uh = 0.0, ux = 0.0, uy = 0.0;
+#pragma unroll
+      for (int j = 0; j < MU; ++j) {
+        uh = fma(uval[q * MU + j], ue[j], uh);
+        ux = fma(uder[(q * MU + j) * 2], ue[j], ux);
+        uy = fma(uder[(q * MU + j) * 2 + 1], ue[j], uy);
+      }
+      ux /= HX; uy /= HY;
+      const double dV = w[q1] * w[q2] * HX * HY * m.sqrtg;
+      const double gx = tder[(q * mt + I) * 2] / HX, gy = tder[(q * mt + I) * 2 + 1] / HY;
+      acc += dV * (cM * tval[q * mt + I] * uh + cK * (gx * (m.i11 * ux + m.i12 * uy) + gy * (m.i12 * ux + m.i22 * uy)));
+    }
+  }
+  vbuf[(int64_t)I * g.nc + c] = acc;
+}
+
+__global__ void k_qpoints(Geo g, int nq, const double* __restrict__ xi, double* __restrict__ chart_out, double* __restrict__ xyz_out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int Q = nq * nq;
+  if (t >= g.nc * Q) return;
+  int64_t c = t / Q;
+  int q = (int)(t - c * Q);
+  int q1 = q % nq, q2 = q / nq;
+  double x = fma(g.hx[c], xi[q1], g.x0[c]), y = fma(g.hy[c], xi[q2], g.y0[c]);
+  if (chart_out) { chart_out[2 * t] = x; chart_out[2 * t + 1] = y; }
+  if (xyz_out) csphere_point(g.chart[c], tan(x), tan(y), g.radius, &xyz_out[3 * t]);
+}
+
+__global__ void k_integrate_cells(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w,
+                                  const double* __restrict__ qdata, double* __restrict__ cell_sums) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.nc) return;
+  const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
+  int Q = nq * nq;
+  double acc = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], Y0));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      Metric2 m = csphere_metric_terms(tan(fma(HX, xi[q1], X0)), b, g.radius);
+      double f = qdata ? qdata[c * Q + q1 + nq * q2] : 1.0;
+      acc = fma(w[q1] * w[q2] * HX * HY * m.sqrtg, f, acc);
+    }
+  }
+  cell_sums[c] = acc;
+}
+
+__global__ void k_eval_geometry(int panel, double r, int64_t n, const double* __restrict__ pts, double* xyz, double* jac,
+                                double* metric, double* inv_metric, double* sqrtg) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double a = tan(pts[2 * t]), b = tan(pts[2 * t + 1]);
+  if (xyz) csphere_point(panel, a, b, r, &xyz[3 * t]);
+  if (jac) {
+    double J[2][3];
+    csphere_jacobian(panel, a, b, r, J);
+    for (int i = 0; i < 2; ++i)
+      for (int k = 0; k < 3; ++k) jac[6 * t + 3 * i + k] = J[i][k];
+  }
+  Metric2 m = csphere_metric_terms(a, b, r);
+  if (metric) { metric[3 * t] = m.g11; metric[3 * t + 1] = m.g12; metric[3 * t + 2] = m.g22; }
+  if (inv_metric) { inv_metric[3 * t] = m.i11; inv_metric[3 * t + 1] = m.i12; inv_metric[3 * t + 2] = m.i22; }
+  if (sqrtg) sqrtg[t] = m.sqrtg;
+}
+
+// ---- dispatch -------------------------------------------------------------------------------------------
+
+static bool is_scalar(const gg_space* s) { return s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG; }
+
+static void load_const_tables(gg_ctx* ctx, int order, int nq) {
+  if (ctx->const_order == order && ctx->const_nq == nq) return;
+  ScalarTables t;
+  build_scalar_tables(order, nq, &t);
+  int nb = order + 1, M = nb * nb;
+  std::vector<int32_t> l2x = quad_local_to_lex(order);
+  std::vector<int32_t> x2l(M);
+  for (int a = 0; a < M; ++a) x2l[l2x[a]] = a;
+  std::vector<int32_t> plane;
+  for (int I = 0; I < M; ++I)
+    for (int J = I; J < M; ++J) {
+      int a = std::min(x2l[I], x2l[J]), b = std::max(x2l[I], x2l[J]);
+      plane.push_back(a * M - (a * (a - 1)) / 2 + (b - a));
+    }
+  // synchronous w.r.t. the stream: earlier launches reading the old tables must have drained
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  GG_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+  GG_CUDA(cudaMemcpyToSymbol(c_plane, plane.data(), plane.size() * sizeof(int32_t)));
+  GG_CUDA(cudaMemcpyToSymbol(c_lex2loc, x2l.data(), x2l.size() * sizeof(int32_t)));
+  ctx->const_order = order;
+  ctx->const_nq = nq;
+}
+
+template <int NB, int NQ>
+static void launch_lb_fast(gg_ctx* ctx, const Geo& g, bool extrinsic, const int32_t* dofs, const double* u, double dir,
+                           double* ebuf, double* vbuf) {
+  unsigned nb = nblk(g.nc, 128);
+  if (extrinsic)
+    k_lb_fast<NB, NQ, true><<<nb, 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, g.chart, g.radius, dofs, u, dir, ebuf, vbuf);
+  else
+    k_lb_fast<NB, NQ, false><<<nb, 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, g.chart, g.radius, dofs, u, dir, ebuf, vbuf);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+// fast-path availability: scalar Q1/Q2, test == trial numbering family, the quadrature sizes the reference uses
+static bool fast_lb_available(int order, int nq) {
+  if (order == 1) return nq == 2 || nq == 3 || nq == 4 || nq == 7;
+  if (order == 2) return nq == 3 || nq == 4 || nq == 5 || nq == 7 || nq == 10;
+  return false;
+}
+
+static void run_lb_fast(gg_ctx* ctx, const Geo& g, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u,
+                        double dir, double* ebuf, double* vbuf) {
+  load_const_tables(ctx, order, nq);
+#define GG_CASE(NB_, NQ_) \
+  if (order + 1 == NB_ && nq == NQ_) { launch_lb_fast<NB_, NQ_>(ctx, g, extrinsic, dofs, u, dir, ebuf, vbuf); return; }
+  GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
+  GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
+#undef GG_CASE
+  throw Error(GG_ERR_UNSUPPORTED, "no fast Laplace-Beltrami kernel for this (order, degree)");
+}
+
+template <int NB, int NQ>
+static void launch_action_fast(gg_ctx* ctx, const Geo& g, const int32_t* dofs, const double* u, double dir, double* vbuf) {
+  k_lb_action_fast<NB, NQ><<<nblk(g.nc, 128), 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, dofs, u, dir, vbuf);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+static void run_action_fast(gg_ctx* ctx, const Geo& g, int order, int nq, const int32_t* dofs, const double* u, double dir,
+                            double* vbuf) {
+  load_const_tables(ctx, order, nq);
+#define GG_CASE(NB_, NQ_) \
+  if (order + 1 == NB_ && nq == NQ_) { launch_action_fast<NB_, NQ_>(ctx, g, dofs, u, dir, vbuf); return; }
+  GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
+  GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
+#undef GG_CASE
+  throw Error(GG_ERR_UNSUPPORTED, "no fast Laplace-Beltrami action kernel for this (order, degree)");
+}
+
+static double* scratch(DevBuf<double>& b, size_t n) {
+  if (b.n < n) b.alloc(n);
+  return b.p;
+}
+
+struct Plan {
+  gg_ctx* ctx;
+  gg_mesh* mesh;
+  gg_space *test, *trial;
+  int nq, mt, mu;
+  double scale;
+};
+
+static Plan make_plan(gg_form form, const gg_form_args* a, bool need_trial) {
+  GG_REQUIRE(a && a->test, GG_ERR_INVALID, "form args need a test space");
+  Plan P;
+  P.test = a->test;
+  P.trial = a->trial;
+  if (need_trial) GG_REQUIRE(P.trial, GG_ERR_INVALID, "this form needs a trial space");
+  if (P.trial) GG_REQUIRE(P.trial->mesh == P.test->mesh, GG_ERR_INVALID, "test and trial spaces live on different meshes");
+  P.mesh = P.test->mesh;
+  P.ctx = P.mesh->ctx;
+  GG_REQUIRE(a->degree >= 0, GG_ERR_INVALID, "negative quadrature degree");
+  P.nq = num_points_1d(a->degree);
+  GG_REQUIRE(P.nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high (max 31)");
+  P.mt = P.test->ndofs_loc;
+  P.mu = P.trial ? P.trial->ndofs_loc : 0;
+  P.scale = a->scale == 0.0 ? 1.0 : a->scale;
+  (void)form;
+  GG_CUDA(cudaSetDevice(P.ctx->device));
+  return P;
+}
+
+static void form_coefficients(gg_form form, double* cM, double* cK, bool* extrinsic) {
+  *extrinsic = false;
+  switch (form) {
+    case GG_FORM_LAPLACE_BELTRAMI: *cM = 0.0; *cK = 1.0; break;
+    case GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC: *cM = 0.0; *cK = 1.0; *extrinsic = true; break;
+    case GG_FORM_HELMHOLTZ: *cM = 1.0; *cK = -1.0; break;
+    case GG_FORM_MASS_SCALAR: *cM = 1.0; *cK = 0.0; break;
+    default: throw Error(GG_ERR_INVALID, "not a scalar bilinear form");
+  }
+}
+
+// element matrices into ctx->ebuf; returns the buffer layout (0 full entry-major, 1 symmetric packed entry-major)
+static int compute_element_matrices(gg_form form, const gg_form_args* a, const Plan& P, bool want_fused_vector, double** vbuf_out) {
+  gg_ctx* ctx = P.ctx;
+  Geo g = geo_of(P.mesh);
+  cudaStream_t st = ctx->stream;
+  int64_t nc = g.nc;
+  if (vbuf_out) *vbuf_out = nullptr;
+  if (nc == 0) return 0;
+  const bool stiffness = form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC;
+  if (form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC || form == GG_FORM_HELMHOLTZ ||
+      form == GG_FORM_MASS_SCALAR) {
+    GG_REQUIRE(is_scalar(P.test) && is_scalar(P.trial), GG_ERR_INVALID, "scalar form needs Lagrangian test/trial spaces");
+    double cM, cK; bool ext;
+    form_coefficients(form, &cM, &cK, &ext);
+    if (stiffness && !a->qdata && P.test->order == P.trial->order && fast_lb_available(P.test->order, P.nq)) {
+      size_t np = (size_t)P.mt * (P.mt + 1) / 2;
+      double* eb = scratch(ctx->ebuf, np * nc);
+      double* vb = nullptr;
+      if (want_fused_vector) {
+        GG_REQUIRE(a->u, GG_ERR_INVALID, "fused residual needs args->u");
+        GG_REQUIRE(gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u has the wrong length");
+        vb = scratch(ctx->vbuf, (size_t)P.mt * nc);
+        *vbuf_out = vb;
+      }
+      run_lb_fast(ctx, g, P.test->order, P.nq, ext, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb);
+      return 1;
+    }
+    GG_REQUIRE(!want_fused_vector, GG_ERR_UNSUPPORTED, "fused matrix+vector assembly needs the fast Q1/Q2 stiffness kernel");
+    if (a->qdata) GG_REQUIRE(gg_vec_size(a->qdata) == nc * P.nq * P.nq, GG_ERR_INVALID, "qdata has the wrong length");
+    auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
+    auto tu = get_tab(ctx, P.trial->kind, P.trial->order, P.nq);
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    const double* qc = a->qdata ? a->qdata->d.p : nullptr;
+    unsigned nb = nblk(nc * P.mt, 128);
+#define GG_CASE(MU_)                                                                                                      \
+  if (P.mu == MU_) {                                                                                                      \
+    if (ext) k_scalar_matrix<MU_, true><<<nb, 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, tt->der.p, tu->val.p, tu->der.p, cM, cK, qc, eb); \
+    else k_scalar_matrix<MU_, false><<<nb, 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, tt->der.p, tu->val.p, tu->der.p, cM, cK, qc, eb); \
+  } else
+    GG_CASE(1) GG_CASE(4) GG_CASE(9) GG_CASE(16) GG_CASE(25) throw Error(GG_ERR_UNSUPPORTED, "unsupported trial order");
+#undef GG_CASE
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  GG_REQUIRE(!want_fused_vector, GG_ERR_UNSUPPORTED, "fused matrix+vector assembly is only implemented for the stiffness forms");
+  if (form == GG_FORM_MASS_RT) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_RT && P.trial->kind == GG_SPACE_RT && P.test->order == P.trial->order, GG_ERR_INVALID,
+               "RT mass needs RT test and trial spaces of the same order");
+    auto tu = get_tab(ctx, GG_SPACE_RT, P.trial->order, P.nq);
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    unsigned nb = nblk(nc * P.mt, 128);
+#define GG_CASE(MU_) \
+  if (P.mu == MU_) k_rt_mass_matrix<MU_><<<nb, 128, 0, st>>>(g, P.nq, tu->xi.p, tu->w.p, tu->val.p, P.trial->d_cell_signs.p, eb); else
+    GG_CASE(4) GG_CASE(12) GG_CASE(24) throw Error(GG_ERR_UNSUPPORTED, "RT order must be <= 2 for matrix assembly");
+#undef GG_CASE
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (form == GG_FORM_DIV) {
+    GG_REQUIRE(is_scalar(P.test) && P.trial->kind == GG_SPACE_RT, GG_ERR_INVALID, "div form needs a scalar test and an RT trial space");
+    auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
+    auto tu = get_tab(ctx, GG_SPACE_RT, P.trial->order, P.nq);
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    unsigned nb = nblk(nc * P.mt, 128);
+#define GG_CASE(MU_) \
+  if (P.mu == MU_) k_div_matrix<MU_><<<nb, 128, 0, st>>>(nc, P.nq, tt->w.p, P.mt, tt->val.p, tu->der.p, P.trial->d_cell_signs.p, eb); else
+    GG_CASE(4) GG_CASE(12) GG_CASE(24) throw Error(GG_ERR_UNSUPPORTED, "RT order must be <= 2 for matrix assembly");
+#undef GG_CASE
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  throw Error(GG_ERR_INVALID, "not a bilinear form id");
+}
+
+// element vectors into ctx->vbuf (entry-major [I][cell])
+static double* compute_element_vectors(gg_form form, const gg_form_args* a, const Plan& P) {
+  gg_ctx* ctx = P.ctx;
+  Geo g = geo_of(P.mesh);
+  cudaStream_t st = ctx->stream;
+  int64_t nc = g.nc;
+  double* vb = scratch(ctx->vbuf, (size_t)P.mt * std::max<int64_t>(nc, 1));
+  if (nc == 0) return vb;
+  if (form == GG_FORM_SOURCE) {
+    GG_REQUIRE(is_scalar(P.test), GG_ERR_INVALID, "source form needs a Lagrangian test space");
+    GG_REQUIRE(a->qdata && gg_vec_size(a->qdata) == nc * P.nq * P.nq, GG_ERR_INVALID, "source form needs qdata of length n_cells*Q");
+    auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
+    k_source_vector<<<nblk(nc * P.mt, 128), 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, a->qdata->d.p, vb);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    return vb;
+  }
+  // action of a scalar bilinear form on u_h
+  GG_REQUIRE(P.trial, GG_ERR_INVALID, "the action of a bilinear form needs the trial space");
+  GG_REQUIRE(is_scalar(P.test) && is_scalar(P.trial), GG_ERR_INVALID, "scalar form needs Lagrangian test/trial spaces");
+  GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u missing or of the wrong length");
+  double cM, cK; bool ext;
+  form_coefficients(form, &cM, &cK, &ext);
+  if (form == GG_FORM_LAPLACE_BELTRAMI && P.test->order == P.trial->order && fast_lb_available(P.test->order, P.nq)) {
+    run_action_fast(ctx, g, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, vb);
+    return vb;
+  }
+  auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
+  auto tu = get_tab(ctx, P.trial->kind, P.trial->order, P.nq);
+  unsigned nb = nblk(nc * P.mt, 128);
+#define GG_CASE(MU_)                                                                                                       \
+  if (P.mu == MU_) {                                                                                                       \
+    if (ext) k_scalar_action<MU_, true><<<nb, 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, tt->der.p, tu->val.p, tu->der.p, cM, cK, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, vb); \
+    else k_scalar_action<MU_, false><<<nb, 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, tt->der.p, tu->val.p, tu->der.p, cM, cK, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, vb); \
+  } else
+  GG_CASE(1) GG_CASE(4) GG_CASE(9) GG_CASE(16) GG_CASE(25) throw Error(GG_ERR_UNSUPPORTED, "unsupported trial order");
+#undef GG_CASE
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  return vb;
+}
+
+// element matrices of `form` left on the device (ctx scratch), for other translation units
+const double* element_matrices_device(gg_form form, const gg_form_args* args, int* layout) {
+  Plan P = make_plan(form, args, true);
+  *layout = compute_element_matrices(form, args, P, false, nullptr);
+  return P.ctx->ebuf.p;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_assemble_matrix(gg_form form, const gg_form_args* args, gg_csr* A, int add) {
+  GG_API_BEGIN
+  GG_REQUIRE(A, GG_ERR_INVALID, "null matrix");
+  Plan P = make_plan(form, args, true);
+  GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
+  int layout = compute_element_matrices(form, args, P, false, nullptr);
+  gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, add);
+  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  GG_API_END
+}
+
+int gg_assemble_vector(gg_form form, const gg_form_args* args, gg_vec* b, int add) {
+  GG_API_BEGIN
+  GG_REQUIRE(b, GG_ERR_INVALID, "null vector");
+  Plan P = make_plan(form, args, false);
+  GG_REQUIRE(gg_vec_size(b) == P.test->n_free, GG_ERR_INVALID, "output vector has the wrong length");
+  double* vb = compute_element_vectors(form, args, P);
+  gather_vector(P.test, vb, b->d.p, P.scale, add);
+  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  GG_API_END
+}
+
+int gg_assemble_matrix_and_vector(gg_form form, const gg_form_args* args, gg_csr* A, gg_vec* b) {
+  GG_API_BEGIN
+  GG_REQUIRE(A && b, GG_ERR_INVALID, "null output");
+  Plan P = make_plan(form, args, true);
+  GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
+  GG_REQUIRE(gg_vec_size(b) == P.test->n_free, GG_ERR_INVALID, "output vector has the wrong length");
+  double* vb = nullptr;
+  int layout = compute_element_matrices(form, args, P, true, &vb);
+  gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, 0);
+  gather_vector(P.test, vb, b->d.p, P.scale, 0);
+  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  GG_API_END
+}
+
+int gg_element_matrices(gg_form form, const gg_form_args* args, int64_t first_cell, int64_t n, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(out, GG_ERR_INVALID, "null output");
+  Plan P = make_plan(form, args, true);
+  int64_t nc = P.mesh->n_cells;
+  GG_REQUIRE(first_cell >= 0 && n >= 0 && first_cell + n <= nc, GG_ERR_INVALID, "cell range out of bounds");
+  int layout = compute_element_matrices(form, args, P, false, nullptr);
+  size_t planes = layout == 1 ? (size_t)P.mt * (P.mt + 1) / 2 : (size_t)P.mt * P.mu;
+  std::vector<double> h(planes * nc);
+  if (nc) GG_CUDA(cudaMemcpyAsync(h.data(), P.ctx->ebuf.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, P.ctx->stream));
+  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  for (int64_t c = 0; c < n; ++c)
+    for (int i = 0; i < P.mt; ++i)
+      for (int j = 0; j < P.mu; ++j) {
+        size_t pl;
+        if (layout == 1) {
+          int a = std::min(i, j), b = std::max(i, j);
+          pl = (size_t)a * P.mu - (size_t)(a * (a - 1)) / 2 + (b - a);
+        } else {
+          pl = (size_t)i * P.mu + j;
+        }
+        out[((size_t)c * P.mt + i) * P.mu + j] = P.scale * h[pl * nc + first_cell + c];
+      }
+  GG_API_END
+}
+
+int gg_element_vectors(gg_form form, const gg_form_args* args, int64_t first_cell, int64_t n, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(out, GG_ERR_INVALID, "null output");
+  Plan P = make_plan(form, args, false);
+  int64_t nc = P.mesh->n_cells;
+  GG_REQUIRE(first_cell >= 0 && n >= 0 && first_cell + n <= nc, GG_ERR_INVALID, "cell range out of bounds");
+  double* vb = compute_element_vectors(form, args, P);
+  std::vector<double> h((size_t)P.mt * nc);
+  if (nc) GG_CUDA(cudaMemcpyAsync(h.data(), vb, h.size() * sizeof(double), cudaMemcpyDeviceToHost, P.ctx->stream));
+  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  for (int64_t c = 0; c < n; ++c)
+    for (int i = 0; i < P.mt; ++i) out[(size_t)c * P.mt + i] = P.scale * h[(size_t)i * nc + first_cell + c];
+  GG_API_END
+}
+
+int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* out_xyz) {
+  GG_API_BEGIN
+  GG_REQUIRE(m, GG_ERR_INVALID, "null mesh");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  int nq = num_points_1d(degree);
+  auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
+  int64_t n = m->n_cells * nq * nq;
+  if (n == 0) return GG_OK;
+  DevBuf<double> dc(out_chart ? 2 * n : 0), dx(out_xyz ? 3 * n : 0);
+  k_qpoints<<<nblk(n, 256), 256, 0, ctx->stream>>>(geo_of(m), nq, T->xi.p, dc.p, dx.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  if (out_chart) dc.download(out_chart, ctx->stream);
+  if (out_xyz) dx.download(out_xyz, ctx->stream);
+  GG_API_END
+}
+
+int gg_integrate(gg_mesh* m, int32_t degree, gg_vec* qdata, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  int nq = num_points_1d(degree);
+  auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
+  int64_t nc = m->n_cells;
+  if (qdata) GG_REQUIRE(gg_vec_size(qdata) == nc * nq * nq, GG_ERR_INVALID, "qdata has the wrong length");
+  *out = 0.0;
+  if (nc == 0) return GG_OK;
+  DevBuf<double> sums(nc), total(1);
+  k_integrate_cells<<<nblk(nc, 128), 128, 0, ctx->stream>>>(geo_of(m), nq, T->xi.p, T->w.p, qdata ? qdata->d.p : nullptr, sums.p);
+  size_t tb = 0;
+  GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, ctx->stream));
+  DevBuf<uint8_t> tmp(tb);
+  GG_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, sums.p, total.p, (int)nc, ctx->stream));
+  ctx->launches += 3;
+  total.download(out, ctx->stream);
+  GG_API_END
+}
+
+int gg_eval_geometry(gg_ctx* ctx, int panel, double radius, int64_t n, const double* pts, double* xyz, double* jac,
+                     double* metric, double* inv_metric, double* sqrtg) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx && pts, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(panel >= 1 && panel <= 6, GG_ERR_INVALID, "panel must be in 1..6");
+  GG_REQUIRE(n >= 0, GG_ERR_INVALID, "negative n");
+  GG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return GG_OK;
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dp; dp.upload(pts, 2 * n, st);
+  DevBuf<double> dx(xyz ? 3 * n : 0), dj(jac ? 6 * n : 0), dg(metric ? 3 * n : 0), di(inv_metric ? 3 * n : 0), ds(sqrtg ? n : 0);
+  k_eval_geometry<<<nblk(n, 128), 128, 0, st>>>(panel - 1, radius, n, dp.p, dx.p, dj.p, dg.p, di.p, ds.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  if (xyz) dx.download(xyz, st);
+  if (jac) dj.download(jac, st);
+  if (metric) dg.download(metric, st);
+  if (inv_metric) di.download(inv_metric, st);
+  if (sqrtg) ds.download(sqrtg, st);
+  GG_CUDA(cudaStreamSynchronize(st));
+  GG_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+// Atlas mesh of the cubed sphere, topology and FE-space numbering (host side, one-off set-up), uploaded
+// to the device in the layouts the kernels want.
+//
+// Reference behaviour reproduced (paths relative to the reference checkout):
+//   src/Geometry/CubedSphereMesh.jl:83-116  coarse cube: 8 nodes, cells [1,2,3,4],[3,4,5,6],[2,7,4,6],[8,5,7,6],[1,8,2,7],[1,3,8,5]
+//   src/Geometry/AtlasGrids.jl:227-304      refinement by n: parent-major cell order, x-fastest inside a panel,
+//                                           chart corners = bilinear panel map of the reference grid k/n
+//   src/Distributed/AtlasDistributedDiscreteModels.jl:31-49   linear partition, vertex-adjacent ghost layer
+// Gridap conventions restated (not verifiable without Gridap): edge ids by first
+// encounter over cells and local edges (1,2),(3,4),(1,3),(2,4); conforming DOFs = vertices, edges, interiors;
+// fine node ids = CG-Q_n numbering of the coarse cube; RT facet DOFs negated on the higher-id cell.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include "gg_common.cuh"
+#include "gg_refel.cuh"
+
+namespace gg {
+
+static const int QUAD_EDGE_V[4][2] = {{0, 1}, {2, 3}, {0, 2}, {1, 3}};
+
+struct EdgeTopo {
+  std::vector<int32_t> cell_edges;  // [nc][4]
+  std::vector<int8_t> flip;         // [nc][4]
+  std::vector<int32_t> edge_cells;  // [ne][2]
+  int64_t n_edges = 0;
+};
+
+static EdgeTopo build_edges(int64_t nc, const int32_t* cell_nodes) {
+  EdgeTopo T;
+  T.cell_edges.resize(nc * 4);
+  T.flip.resize(nc * 4);
+  struct Ref { uint64_t key; int64_t idx; };
+  std::vector<Ref> refs(nc * 4);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int e = 0; e < 4; ++e) {
+      uint32_t a = cell_nodes[c * 4 + QUAD_EDGE_V[e][0]], b = cell_nodes[c * 4 + QUAD_EDGE_V[e][1]];
+      uint64_t lo = std::min(a, b), hi = std::max(a, b);
+      refs[c * 4 + e] = {(lo << 32) | hi, c * 4 + e};
+    }
+  std::sort(refs.begin(), refs.end(), [](const Ref& x, const Ref& y) { return x.key != y.key ? x.key < y.key : x.idx < y.idx; });
+  // groups of equal key; first member (smallest idx) defines the encounter position
+  std::vector<int64_t> group_first;  // encounter position of each group
+  std::vector<int64_t> group_of(nc * 4);
+  for (size_t i = 0; i < refs.size(); ++i) {
+    if (i == 0 || refs[i].key != refs[i - 1].key) group_first.push_back(refs[i].idx);
+    group_of[refs[i].idx] = (int64_t)group_first.size() - 1;
+  }
+  int64_t ne = (int64_t)group_first.size();
+  std::vector<int64_t> order(ne);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return group_first[a] < group_first[b]; });
+  std::vector<int32_t> rank(ne);
+  for (int64_t r = 0; r < ne; ++r) rank[order[r]] = (int32_t)r;
+  T.n_edges = ne;
+  T.edge_cells.assign(ne * 2, -1);
+  std::vector<int32_t> edge_first_node(ne);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int e = 0; e < 4; ++e) {
+      int32_t id = rank[group_of[c * 4 + e]];
+      T.cell_edges[c * 4 + e] = id;
+      int32_t a = cell_nodes[c * 4 + QUAD_EDGE_V[e][0]];
+      if (T.edge_cells[id * 2] < 0) {
+        T.edge_cells[id * 2] = (int32_t)c;
+        edge_first_node[id] = a;
+        T.flip[c * 4 + e] = 0;
+      } else {
+        GG_REQUIRE(T.edge_cells[id * 2 + 1] < 0, GG_ERR_INVALID, "non-manifold mesh: an edge has more than two cells");
+        T.edge_cells[id * 2 + 1] = (int32_t)c;
+        T.flip[c * 4 + e] = (a != edge_first_node[id]);
+      }
+    }
+  return T;
+}
+
+// Conforming Q_p ids, Gridap local order (vertices, edge interiors edge by edge, cell interior)
+static void cg_numbering(int64_t nc, const int32_t* cell_nodes, int64_t n_nodes, const EdgeTopo& T, int p,
+                         std::vector<int32_t>& ids, int64_t& ndofs) {
+  int m = (p + 1) * (p + 1);
+  ids.resize(nc * m);
+  int64_t ne = T.n_edges;
+  int ni = (p - 1) * (p - 1);
+  ndofs = n_nodes + ne * (p - 1) + nc * ni;
+  GG_REQUIRE(ndofs < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "more than 2^31 DOFs in one space");
+  for (int64_t c = 0; c < nc; ++c) {
+    int32_t* o = &ids[c * m];
+    int k = 0;
+    for (int v = 0; v < 4; ++v) o[k++] = cell_nodes[c * 4 + v];
+    for (int e = 0; e < 4; ++e)
+      for (int t = 0; t < p - 1; ++t) {
+        int tt = T.flip[c * 4 + e] ? (p - 2 - t) : t;
+        o[k++] = (int32_t)(n_nodes + (int64_t)T.cell_edges[c * 4 + e] * (p - 1) + tt);
+      }
+    for (int t = 0; t < ni; ++t) o[k++] = (int32_t)(n_nodes + ne * (p - 1) + c * ni + t);
+  }
+}
+
+static void ensure_topology(gg_mesh* m) {
+  if (m->topology_built) return;
+  EdgeTopo T = build_edges(m->n_cells, m->cell_nodes.data());
+  m->cell_edges = std::move(T.cell_edges);
+  m->cell_edge_flip = std::move(T.flip);
+  m->edge_cells = std::move(T.edge_cells);
+  m->n_edges = T.n_edges;
+  m->topology_built = true;
+}
+
+static void upload_geometry(gg_mesh* m) {
+  int64_t nc = m->n_cells;
+  std::vector<double> x0(nc), y0(nc), hx(nc), hy(nc);
+  for (int64_t c = 0; c < nc; ++c) {
+    const double* q = &m->chart_coords[c * 8];  // BL, BR, TL, TR
+    double tol = 1e-13 * (std::fabs(q[0]) + std::fabs(q[6]) + 1.0);
+    bool ok = std::fabs(q[0] - q[4]) <= tol && std::fabs(q[2] - q[6]) <= tol &&   // x: BL==TL, BR==TR
+              std::fabs(q[1] - q[3]) <= tol && std::fabs(q[5] - q[7]) <= tol;     // y: BL==BR, TL==TR
+    GG_REQUIRE(ok, GG_ERR_UNSUPPORTED, "cell " + std::to_string(c) + " is not an axis-aligned rectangle in chart space");
+    x0[c] = q[0]; y0[c] = q[1];
+    hx[c] = q[2] - q[0]; hy[c] = q[5] - q[1];
+    GG_REQUIRE(hx[c] > 0 && hy[c] > 0, GG_ERR_UNSUPPORTED, "cell " + std::to_string(c) + " has non-positive extent");
+  }
+  cudaStream_t s = m->ctx->stream;
+  m->d_x0.upload(x0, s); m->d_y0.upload(y0, s); m->d_hx.upload(hx, s); m->d_hy.upload(hy, s);
+  m->d_chart.upload(m->cell_to_chart, s);
+  GG_CUDA(cudaStreamSynchronize(s));
+}
+
+static const int32_t COARSE_CELLS[6][4] = {{0, 1, 2, 3}, {2, 3, 4, 5}, {1, 6, 3, 5}, {7, 4, 6, 5}, {0, 7, 1, 6}, {0, 2, 7, 4}};
+
+static gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
+  std::unique_ptr<gg_mesh> m(new gg_mesh);
+  m->ctx = ctx; m->dim = 2; m->n = n; m->radius = radius;
+  int64_t nc = 6LL * n * n;
+  GG_REQUIRE(nc * 25 < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "mesh too large for Int32 ids");
+  m->n_cells = nc;
+  // fine nodes = CG-Q_n DOFs of the coarse cube
+  EdgeTopo CT = build_edges(6, &COARSE_CELLS[0][0]);
+  std::vector<int32_t> coarse_ids;
+  int64_t nn;
+  cg_numbering(6, &COARSE_CELLS[0][0], 8, CT, n, coarse_ids, nn);
+  m->n_nodes = nn;
+  std::vector<int32_t> l2x = quad_local_to_lex(n);
+  std::vector<int32_t> lut((n + 1) * (n + 1));
+  for (size_t k = 0; k < l2x.size(); ++k) lut[l2x[k]] = (int32_t)k;
+  int mloc = (n + 1) * (n + 1);
+  m->cell_nodes.resize(nc * 4);
+  m->cell_to_chart.resize(nc);
+  m->chart_coords.resize(nc * 8);
+  const double H = M_PI / 4;  // CUBE_HALF_EDGE, src/Geometry/CubedSphereMesh.jl:23
+  auto psi = [&](double xi) { return (1.0 - xi) * (-H) + xi * H; };
+  for (int p = 0; p < 6; ++p)
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) {
+        int64_t c = (int64_t)p * n * n + (int64_t)j * n + i;
+        const int32_t* cid = &coarse_ids[(size_t)p * mloc];
+        m->cell_nodes[c * 4 + 0] = cid[lut[i + (n + 1) * j]];
+        m->cell_nodes[c * 4 + 1] = cid[lut[i + 1 + (n + 1) * j]];
+        m->cell_nodes[c * 4 + 2] = cid[lut[i + (n + 1) * (j + 1)]];
+        m->cell_nodes[c * 4 + 3] = cid[lut[i + 1 + (n + 1) * (j + 1)]];
+        m->cell_to_chart[c] = p;
+        double xa = psi((double)i / n), xb = psi((double)(i + 1) / n);
+        double ya = psi((double)j / n), yb = psi((double)(j + 1) / n);
+        double* q = &m->chart_coords[c * 8];
+        q[0] = xa; q[1] = ya; q[2] = xb; q[3] = ya; q[4] = xa; q[5] = yb; q[6] = xb; q[7] = yb;
+      }
+  upload_geometry(m.get());
+  return m.release();
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_mesh_cubed_sphere(gg_ctx* ctx, int dim, int n, int n_layers, double radius, double thickness, int ordering,
+                         gg_mesh** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(dim == 2, GG_ERR_UNSUPPORTED, "only the 2-D cubed-sphere surface is implemented (dim=3 shell: not yet)");
+  GG_REQUIRE(n >= 1, GG_ERR_INVALID, "n must be >= 1");
+  GG_REQUIRE(radius > 0, GG_ERR_INVALID, "radius must be positive");
+  GG_REQUIRE(ordering == 0, GG_ERR_UNSUPPORTED, "only ordering 0 (one-shot, parent-major lexicographic) is implemented");
+  (void)n_layers; (void)thickness;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  *out = build_cubed_sphere(ctx, n, radius);
+  GG_API_END
+}
+
+int gg_mesh_from_arrays(gg_ctx* ctx, int dim, int64_t n_cells, int64_t n_nodes, const int32_t* cell_to_chart,
+                        const double* cell_chart_coords, const int32_t* cell_node_ids, double radius, double thickness,
+                        gg_mesh** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx && out && cell_to_chart && cell_chart_coords && cell_node_ids, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(dim == 2, GG_ERR_UNSUPPORTED, "only dim=2 is implemented");
+  GG_REQUIRE(n_cells >= 0 && n_nodes >= 0, GG_ERR_INVALID, "negative size");
+  GG_REQUIRE(radius > 0, GG_ERR_INVALID, "radius must be positive");
+  (void)thickness;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<gg_mesh> m(new gg_mesh);
+  m->ctx = ctx; m->dim = 2; m->n = 0; m->radius = radius;
+  m->n_cells = n_cells; m->n_nodes = n_nodes;
+  m->cell_nodes.resize(n_cells * 4);
+  m->cell_to_chart.resize(n_cells);
+  for (int64_t i = 0; i < n_cells * 4; ++i) {
+    GG_REQUIRE(cell_node_ids[i] >= 1 && cell_node_ids[i] <= n_nodes, GG_ERR_INVALID, "cell_node_ids out of range (1-based)");
+    m->cell_nodes[i] = cell_node_ids[i] - 1;
+  }
+  for (int64_t i = 0; i < n_cells; ++i) {
+    GG_REQUIRE(cell_to_chart[i] >= 1 && cell_to_chart[i] <= 6, GG_ERR_INVALID, "cell_to_chart must be in 1..6");
+    m->cell_to_chart[i] = cell_to_chart[i] - 1;
+  }
+  m->chart_coords.assign(cell_chart_coords, cell_chart_coords + n_cells * 8);
+  upload_geometry(m.get());
+  *out = m.release();
+  GG_API_END
+}
+
+int gg_mesh_info(gg_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* n_edges) {
+  GG_API_BEGIN
+  GG_REQUIRE(m, GG_ERR_INVALID, "null mesh");
+  if (n_cells) *n_cells = m->n_cells;
+  if (n_nodes) *n_nodes = m->n_nodes;
+  if (n_edges) { ensure_topology(m); *n_edges = m->n_edges; }
+  GG_API_END
+}
+
+int gg_mesh_get_cell_nodes(gg_mesh* m, int32_t* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < m->cell_nodes.size(); ++i) out[i] = m->cell_nodes[i] + 1;
+  GG_API_END
+}
+
+int gg_mesh_get_cell_to_chart(gg_mesh* m, int32_t* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < m->cell_to_chart.size(); ++i) out[i] = m->cell_to_chart[i] + 1;
+  GG_API_END
+}
+
+int gg_mesh_get_chart_coords(gg_mesh* m, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  std::copy(m->chart_coords.begin(), m->chart_coords.end(), out);
+  GG_API_END
+}
+
+void gg_mesh_destroy(gg_mesh* m) { delete m; }
+
+int gg_partition_range(int64_t n_cells, int nparts, int part, int64_t* first, int64_t* last) {
+  GG_API_BEGIN
+  GG_REQUIRE(first && last && nparts >= 1 && part >= 0 && part < nparts && n_cells >= 0, GG_ERR_INVALID, "bad partition request");
+  // part(i) = floor(i * P / Nc) (0-based i)  =>  first cell of part p = ceil(p * Nc / P)
+  auto lo = [&](int64_t p) { return (p * n_cells + nparts - 1) / nparts; };
+  *first = lo(part);
+  *last = lo(part + 1);
+  GG_API_END
+}
+
+int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out && (cells || n_sub == 0), GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(m->ctx->device));
+  std::unique_ptr<gg_mesh> s(new gg_mesh);
+  s->ctx = m->ctx; s->dim = m->dim; s->n = 0; s->radius = m->radius; s->thickness = m->thickness;
+  s->n_cells = n_sub; s->n_nodes = m->n_nodes;
+  s->cell_nodes.resize(n_sub * 4); s->cell_to_chart.resize(n_sub); s->chart_coords.resize(n_sub * 8);
+  for (int64_t i = 0; i < n_sub; ++i) {
+    int64_t c = cells[i];
+    GG_REQUIRE(c >= 0 && c < m->n_cells, GG_ERR_INVALID, "cell id out of range");
+    GG_REQUIRE(i == 0 || cells[i - 1] < c, GG_ERR_INVALID, "cells must be strictly ascending");
+    std::copy(&m->cell_nodes[c * 4], &m->cell_nodes[c * 4] + 4, &s->cell_nodes[i * 4]);
+    s->cell_to_chart[i] = m->cell_to_chart[c];
+    std::copy(&m->chart_coords[c * 8], &m->chart_coords[c * 8] + 8, &s->chart_coords[i * 8]);
+  }
+  upload_geometry(s.get());
+  *out = s.release();
+  GG_API_END
+}
+
+int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghost, int64_t* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && n_ghost, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(first >= 0 && first <= last && last <= m->n_cells, GG_ERR_INVALID, "bad owned range");
+  std::vector<uint8_t> touched(m->n_nodes, 0);
+  for (int64_t c = first; c < last; ++c)
+    for (int v = 0; v < 4; ++v) touched[m->cell_nodes[c * 4 + v]] = 1;
+  int64_t cnt = 0;
+  for (int64_t c = 0; c < m->n_cells; ++c) {
+    if (c >= first && c < last) continue;
+    bool near = false;
+    for (int v = 0; v < 4; ++v) near = near || touched[m->cell_nodes[c * 4 + v]];
+    if (near) {
+      if (out) out[cnt] = c;
+      ++cnt;
+    }
+  }
+  *n_ghost = cnt;
+  GG_API_END
+}
+
+// ---- spaces ---------------------------------------------------------------------------------------
+
+static void finish_space(gg_space* s) {
+  gg_mesh* m = s->mesh;
+  cudaStream_t st = m->ctx->stream;
+  s->d_cell_dofs.upload(s->cell_dofs, st);
+  if (!s->cell_signs.empty()) s->d_cell_signs.upload(s->cell_signs, st);
+  GG_CUDA(cudaStreamSynchronize(st));
+  if (s->kind != GG_SPACE_RT) s->loc2lex = quad_local_to_lex(s->order);
+}
+
+int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(m->ctx->device));
+  std::unique_ptr<gg_space> s(new gg_space);
+  s->mesh = m; s->kind = kind; s->order = order; s->constraint = constraint;
+  int64_t nc = m->n_cells;
+  if (kind == GG_SPACE_CG) {
+    GG_REQUIRE(order >= 1 && order <= 4, GG_ERR_UNSUPPORTED, "CG order must be in 1..4");
+    ensure_topology(m);
+    EdgeTopo T;
+    T.cell_edges = m->cell_edges; T.flip = m->cell_edge_flip; T.n_edges = m->n_edges;
+    int64_t nd;
+    cg_numbering(nc, m->cell_nodes.data(), m->n_nodes, T, order, s->cell_dofs, nd);
+    s->ndofs_loc = (order + 1) * (order + 1);
+    if (constraint == GG_CONSTRAINT_ZEROMEAN) {
+      for (auto& d : s->cell_dofs)
+        if (d == nd - 1) d = -1;
+      s->n_free = nd - 1; s->n_dirichlet = 1;
+    } else {
+      GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_INVALID, "unknown constraint");
+      s->n_free = nd;
+    }
+  } else if (kind == GG_SPACE_DG) {
+    GG_REQUIRE(order >= 0 && order <= 4, GG_ERR_UNSUPPORTED, "DG order must be in 0..4");
+    GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on DG spaces are not implemented");
+    int mloc = (order + 1) * (order + 1);
+    s->ndofs_loc = mloc;
+    s->n_free = nc * mloc;
+    GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
+    s->cell_dofs.resize(nc * mloc);
+    std::iota(s->cell_dofs.begin(), s->cell_dofs.end(), 0);
+  } else if (kind == GG_SPACE_RT) {
+    GG_REQUIRE(order >= 0 && order <= 3, GG_ERR_UNSUPPORTED, "RT order must be in 0..3");
+    GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on RT spaces are not implemented");
+    ensure_topology(m);
+    int nf = order + 1, ni = 2 * order * (order + 1);
+    int mloc = 4 * nf + ni;
+    s->ndofs_loc = mloc;
+    s->n_free = m->n_edges * nf + nc * ni;
+    GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
+    s->cell_dofs.resize(nc * mloc);
+    s->cell_signs.assign(nc * mloc, 1);
+    for (int64_t c = 0; c < nc; ++c) {
+      int k = 0;
+      for (int e = 0; e < 4; ++e) {
+        int32_t ed = m->cell_edges[c * 4 + e];
+        GG_REQUIRE(!m->cell_edge_flip[c * 4 + e], GG_ERR_UNSUPPORTED,
+                   "RT spaces need shared edges with the same vertex order in both cells");
+        bool slave = m->edge_cells[ed * 2 + 1] == (int32_t)c;
+        for (int t = 0; t < nf; ++t) {
+          s->cell_dofs[c * mloc + k] = ed * nf + t;
+          s->cell_signs[c * mloc + k] = slave ? -1 : 1;
+          ++k;
+        }
+      }
+      for (int t = 0; t < ni; ++t) s->cell_dofs[c * mloc + k++] = (int32_t)(m->n_edges * nf + c * ni + t);
+    }
+  } else {
+    throw Error(GG_ERR_INVALID, "unknown space kind");
+  }
+  finish_space(s.get());
+  *out = s.release();
+  GG_API_END
+}
+
+int gg_space_from_arrays(gg_mesh* m, int kind, int order, int64_t n_free, const int32_t* cell_dof_ids,
+                         const int8_t* cell_dof_signs, gg_space** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out && cell_dof_ids, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(n_free >= 0 && n_free < (int64_t)INT32_MAX, GG_ERR_INVALID, "bad n_free");
+  GG_CUDA(cudaSetDevice(m->ctx->device));
+  std::unique_ptr<gg_space> s(new gg_space);
+  s->mesh = m; s->kind = kind; s->order = order; s->constraint = 0;
+  if (kind == GG_SPACE_CG || kind == GG_SPACE_DG) {
+    GG_REQUIRE(order >= 0 && order <= 4, GG_ERR_UNSUPPORTED, "Lagrangian order must be in 0..4");
+    s->ndofs_loc = (order + 1) * (order + 1);
+  } else if (kind == GG_SPACE_RT) {
+    GG_REQUIRE(order >= 0 && order <= 3, GG_ERR_UNSUPPORTED, "RT order must be in 0..3");
+    s->ndofs_loc = 2 * (order + 1) * (order + 2);
+  } else {
+    throw Error(GG_ERR_INVALID, "unknown space kind");
+  }
+  size_t tot = (size_t)m->n_cells * s->ndofs_loc;
+  s->cell_dofs.resize(tot);
+  int64_t ndir = 0;
+  for (size_t i = 0; i < tot; ++i) {
+    int32_t d = cell_dof_ids[i];
+    GG_REQUIRE(d != 0 && d <= n_free, GG_ERR_INVALID, "cell_dof_ids must be 1-based (negative = Dirichlet) and <= n_free");
+    if (d < 0) { s->cell_dofs[i] = -1; ndir = std::max<int64_t>(ndir, -d); }
+    else s->cell_dofs[i] = d - 1;
+  }
+  s->n_free = n_free; s->n_dirichlet = ndir;
+  if (cell_dof_signs) {
+    s->cell_signs.assign(cell_dof_signs, cell_dof_signs + tot);
+  } else if (kind == GG_SPACE_RT) {
+    s->cell_signs.assign(tot, 1);
+  }
+  finish_space(s.get());
+  *out = s.release();
+  GG_API_END
+}
+
+int gg_space_info(gg_space* s, int64_t* n_free, int32_t* ndofs_loc, int64_t* n_dirichlet) {
+  GG_API_BEGIN
+  GG_REQUIRE(s, GG_ERR_INVALID, "null space");
+  if (n_free) *n_free = s->n_free;
+  if (ndofs_loc) *ndofs_loc = s->ndofs_loc;
+  if (n_dirichlet) *n_dirichlet = s->n_dirichlet;
+  GG_API_END
+}
+
+int gg_space_get_cell_dofs(gg_space* s, int32_t* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && out, GG_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < s->cell_dofs.size(); ++i) out[i] = s->cell_dofs[i] < 0 ? -1 : s->cell_dofs[i] + 1;
+  GG_API_END
+}
+
+int gg_space_get_cell_signs(gg_space* s, int8_t* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && out, GG_ERR_INVALID, "null argument");
+  if (s->cell_signs.empty()) std::fill(out, out + s->cell_dofs.size(), (int8_t)1);
+  else std::copy(s->cell_signs.begin(), s->cell_signs.end(), out);
+  GG_API_END
+}
+
+void gg_space_destroy(gg_space* s) { delete s; }
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// Explicit Runge-Kutta stepping of the linear wave equation on the device.
+//
+// Replaces, for RT_p x DG_p on the cubed sphere (test/Transient/TransientWaveEquation.jl:28-77), the stock
+// Gridap.ODEs `ode_march!` of EXRungeKutta with a constant mass matrix:
+//     for each stage i:  x_i = x_0 + dt sum_j A_ij k_j ;  M k_i = -res(x_i)
+//     x_F = x_0 + dt sum_i b_i k_i                         (same stage algebra as src/ODEs/RungeKuttaEX.jl:78-122)
+// with  mass((du,dp),(v,q)) = int v.(g du)/sqrtg + int q dp sqrtg   and   res((u,p),(v,q)) = int q div(u) - int p div(v).
+//
+// B200 design
+//   * state, slopes and all operators stay resident in HBM/L2; a step enqueues a fixed sequence of launches with no
+//     host synchronisation (the PCG iteration count is decided inside the persistent kernel);
+//   * the stage residual is matrix-free and owner-computes: ONE launch, one thread per global DOF, no scatter and
+//     no atomics.  For the contravariant Piola map on an axis-aligned cell the Jacobian determinant cancels in
+//     int q div(u), so the cell-wise quadrature collapses to the reference matrix Bhat[I][J] = sum_q w_q q_I divhat_J
+//     (same quadrature rule as the reference, evaluated once);
+//   * the DG mass block is block diagonal: its cell blocks are inverted once (batched Gauss-Jordan, one thread per
+//     cell) and applied as a dense mat-vec; the RT block is solved by the persistent Jacobi-PCG (gg_solver.cu).
+#include <cstring>
+#include "gg_common.cuh"
+#include "gg_refel.cuh"
+
+struct gg_rk {
+  gg_ctx* ctx = nullptr;
+  gg_mesh* mesh = nullptr;
+  gg_space *V = nullptr, *Q = nullptr;
+  gg_csr* Mu = nullptr;
+  gg_solver* solver = nullptr;
+  int order = 0, degree = 0, n_stages = 0, mq = 0, mu = 0;
+  std::vector<double> A, b, c;
+  double dt = 0.0;
+  int64_t nu = 0, np = 0;
+  gg::DevBuf<double> x, xi, r, MpInv, Bhat, signs_d;
+  std::vector<gg::DevBuf<double>> k;
+  gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
+};
+
+namespace gg {
+
+// one thread per cell: invert the m x m DG mass block held entry-major in ebuf[(i*m+j)*nc + c]
+template <int M>
+__global__ void k_invert_blocks(int64_t nc, const double* __restrict__ ebuf, double* __restrict__ inv) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double a[M][M], b[M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      a[i][j] = ebuf[(int64_t)(i * M + j) * nc + c];
+      b[i][j] = i == j ? 1.0 : 0.0;
+    }
+  // SPD block: Gauss-Jordan without pivoting is stable
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    double d = 1.0 / a[k][k];
+#pragma unroll
+    for (int j = 0; j < M; ++j) { a[k][j] *= d; b[k][j] *= d; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (i == k) continue;
+      double f = a[i][k];
+#pragma unroll
+      for (int j = 0; j < M; ++j) { a[i][j] = fma(-f, a[k][j], a[i][j]); b[i][j] = fma(-f, b[k][j], b[i][j]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) inv[(int64_t)(i * M + j) * nc + c] = b[i][j];
+}
+
+// matrix-free wave residual, one thread per global DOF of [u; p]
+//   u-dof d: r = - sum_{(c,J) touching d} s_cJ sum_I Bhat[I][J] p[c*mq+I]
+//   p-dof (c,I): r = sum_J Bhat[I][J] s_cJ u[dof(c,J)]
+__global__ void __launch_bounds__(128)
+k_wave_residual(int64_t nu, int64_t np, int64_t nc, int mq, int mu, const int32_t* __restrict__ vptr,
+                const int32_t* __restrict__ vsrc, const int32_t* __restrict__ udofs, const int8_t* __restrict__ signs,
+                const double* __restrict__ Bhat, const double* __restrict__ x, double* __restrict__ r) {
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nu + np) return;
+  if (d < nu) {
+    double acc = 0.0;
+    for (int32_t e = vptr[d]; e < vptr[d + 1]; ++e) {
+      int32_t src = vsrc[e];
+      int J = (int)(src / nc);
+      int64_t c = src - (int64_t)J * nc;
+      double s = 0.0;
+      for (int I = 0; I < mq; ++I) s = fma(Bhat[I * mu + J], x[nu + c * mq + I], s);
+      acc = fma(-(double)signs[c * mu + J], s, acc);
+    }
+    r[d] = acc;
+  } else {
+    int64_t e = d - nu;
+    int64_t c = e / mq;
+    int I = (int)(e - c * mq);
+    double acc = 0.0;
+    for (int J = 0; J < mu; ++J) acc = fma(Bhat[I * mu + J] * (double)signs[c * mu + J], x[udofs[c * mu + J]], acc);
+    r[d] = acc;
+  }
+}
+
+// k_p = -MpInv r_p (one thread per DG dof)
+__global__ void k_apply_dg_inverse(int64_t nc, int mq, const double* __restrict__ inv, const double* __restrict__ rp,
+                                   double* __restrict__ kp) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * mq) return;
+  int64_t c = t / mq;
+  int i = (int)(t - c * mq);
+  double acc = 0.0;
+  for (int j = 0; j < mq; ++j) acc = fma(inv[(int64_t)(i * mq + j) * nc + c], rp[c * mq + j], acc);
+  kp[t] = -acc;
+}
+
+// out = x0 + sum_j coef[j] * k_j  (up to 4 slopes)
+__global__ void k_combine(int64_t n, const double* x0, int ns, double c0, const double* __restrict__ k0,
+                          double c1, const double* __restrict__ k1, double c2, const double* __restrict__ k2, double c3,
+                          const double* __restrict__ k3, double* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x0[i];
+  if (ns > 0) v = fma(c0, k0[i], v);
+  if (ns > 1) v = fma(c1, k1[i], v);
+  if (ns > 2) v = fma(c2, k2[i], v);
+  if (ns > 3) v = fma(c3, k3[i], v);
+  out[i] = v;
+}
+
+__global__ void k_accumulate_stats(const double* __restrict__ solver_stats, double* __restrict__ accum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { accum[0] += solver_stats[0]; accum[1] += 1.0; }
+}
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
+  gg_ctx* ctx = rk->ctx;
+  int64_t n = rk->nu + rk->np;
+  if (n == 0) return;
+  k_wave_residual<<<nblk(n, 128), 128, 0, ctx->stream>>>(rk->nu, rk->np, rk->mesh->n_cells, rk->mq, rk->mu, rk->V->d_vptr.p,
+                                                        rk->V->d_vsrc.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p,
+                                                        rk->Bhat.p, x, r);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+static void rk_step_async(gg_rk* rk) {
+  gg_ctx* ctx = rk->ctx;
+  cudaStream_t st = ctx->stream;
+  int64_t n = rk->nu + rk->np;
+  int s = rk->n_stages;
+  auto kp = [&](int j) { return j < s ? rk->k[j].p : nullptr; };
+  for (int i = 0; i < s; ++i) {
+    const double* xs = rk->x.p;
+    if (i > 0) {
+      double co[4] = {0, 0, 0, 0};
+      for (int j = 0; j < i && j < 4; ++j) co[j] = rk->dt * rk->A[i * s + j];
+      k_combine<<<nblk(n, 256), 256, 0, st>>>(n, rk->x.p, std::min(i, 4), co[0], kp(0), co[1], kp(1), co[2], kp(2), co[3], kp(3), rk->xi.p);
+      ctx->launches++;
+      xs = rk->xi.p;
+    }
+    rk_residual_async(rk, xs, rk->r.p);
+    // slope: M k = -r
+    solver_solve_async(rk->solver, rk->r.p, -1.0, rk->k[i].p);
+    k_accumulate_stats<<<1, 32, 0, st>>>(rk->solver->stats.p, rk->iter_accum.p);
+    ctx->launches++;
+    if (rk->np) {
+      k_apply_dg_inverse<<<nblk(rk->np, 128), 128, 0, st>>>(rk->mesh->n_cells, rk->mq, rk->MpInv.p, rk->r.p + rk->nu, rk->k[i].p + rk->nu);
+      ctx->launches++;
+    }
+  }
+  double co[4] = {0, 0, 0, 0};
+  for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
+  k_combine<<<nblk(n, 256), 256, 0, st>>>(n, rk->x.p, std::min(s, 4), co[0], kp(0), co[1], kp(1), co[2], kp(2), co[3], kp(3), rk->x.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+void gg_rk_destroy(gg_rk* rk) {
+  if (!rk) return;
+  gg_solver_destroy(rk->solver);
+  gg_csr_destroy(rk->Mu);
+  gg_space_destroy(rk->V);
+  gg_space_destroy(rk->Q);
+  delete rk;
+}
+
+int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
+  gg_rk* raw = nullptr;
+  GG_API_BEGIN
+  GG_REQUIRE(m && a && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE, GG_ERR_UNSUPPORTED, "only GG_PROBLEM_WAVE is implemented");
+  GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
+  GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "wave stepper supports RT_p x DG_p with p <= 2");
+  GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  raw = new gg_rk;
+  gg_rk* rk = raw;
+  rk->ctx = ctx; rk->mesh = m; rk->order = a->order; rk->degree = a->degree; rk->n_stages = a->n_stages; rk->dt = a->dt;
+  int s = a->n_stages;
+  rk->A.assign(a->A, a->A + s * s); rk->b.assign(a->b, a->b + s); rk->c.assign(a->c, a->c + s);
+  for (int i = 0; i < s; ++i)
+    for (int j = i; j < s; ++j) GG_REQUIRE(rk->A[i * s + j] == 0.0, GG_ERR_INVALID, "tableau is not explicit");
+  auto chk = [](int code) { if (code != GG_OK) throw Error(code, gg_last_error(nullptr)); };
+  chk(gg_space_builtin(m, GG_SPACE_RT, a->order, GG_CONSTRAINT_NONE, &rk->V));
+  chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
+  rk->nu = rk->V->n_free; rk->np = rk->Q->n_free; rk->mq = rk->Q->ndofs_loc; rk->mu = rk->V->ndofs_loc;
+  int64_t nc = m->n_cells;
+  // RT mass matrix and its solver
+  chk(gg_pattern(rk->V, rk->V, &rk->Mu));
+  gg_form_args fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.test = rk->V; fa.trial = rk->V; fa.degree = a->degree;
+  chk(gg_assemble_matrix(GG_FORM_MASS_RT, &fa, rk->Mu, 0));
+  chk(gg_solver_pcg_create(rk->Mu, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver));
+  // DG mass blocks -> inverses
+  fa.test = rk->Q; fa.trial = rk->Q;
+  int layout = 0;
+  const double* mp = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
+  GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
+  rk->MpInv.alloc((size_t)rk->mq * rk->mq * nc);
+  if (nc) {
+    unsigned nb = nblk(nc, 64);
+    switch (rk->mq) {
+      case 1: k_invert_blocks<1><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      case 4: k_invert_blocks<4><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      case 9: k_invert_blocks<9><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      default: throw Error(GG_ERR_UNSUPPORTED, "DG order > 2 in the wave stepper");
+    }
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+  // reference div matrix Bhat[I][J] = sum_q w_q q_I(xi_q) divhat_J(xi_q), same rule as Measure(Omega, degree)
+  {
+    int nq = num_points_1d(a->degree);
+    GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
+    std::vector<double> xi(nq), w(nq);
+    gauss_legendre_01(nq, xi.data(), w.data());
+    RTRef R = build_rt_ref(a->order);
+    std::vector<double> pts((size_t)nq * nq * 2), val, div;
+    for (int q2 = 0; q2 < nq; ++q2)
+      for (int q1 = 0; q1 < nq; ++q1) { pts[2 * (q1 + nq * q2)] = xi[q1]; pts[2 * (q1 + nq * q2) + 1] = xi[q2]; }
+    R.tabulate(nq * nq, pts.data(), val, div);
+    int nb1 = a->order + 1;
+    std::vector<int32_t> l2x = quad_local_to_lex(a->order);
+    std::vector<double> N(nq * nb1), D(nq * nb1);
+    for (int q = 0; q < nq; ++q) lagrange_1d(a->order, xi[q], &N[q * nb1], &D[q * nb1]);
+    std::vector<double> B((size_t)rk->mq * rk->mu, 0.0);
+    for (int q2 = 0; q2 < nq; ++q2)
+      for (int q1 = 0; q1 < nq; ++q1) {
+        int q = q1 + nq * q2;
+        for (int I = 0; I < rk->mq; ++I) {
+          double qI = N[q1 * nb1 + l2x[I] % nb1] * N[q2 * nb1 + l2x[I] / nb1];
+          for (int J = 0; J < rk->mu; ++J) B[(size_t)I * rk->mu + J] += w[q1] * w[q2] * qI * div[(size_t)q * rk->mu + J];
+        }
+      }
+    rk->Bhat.upload(B, ctx->stream);
+  }
+  build_vec_map(rk->V);
+  int64_t n = rk->nu + rk->np;
+  rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
+  rk->k.resize(s);
+  for (int i = 0; i < s; ++i) rk->k[i].alloc(n);
+  rk->iter_accum.alloc(2);
+  GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
+  if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = raw;
+  raw = nullptr;
+  }
+  catch (...) {
+    gg_rk_destroy(raw);
+    try { throw; }
+    catch (const gg::Error& e) { gg::set_last_error(e.what()); return e.code; }
+    catch (const std::exception& e) { gg::set_last_error(e.what()); return GG_ERR_INVALID; }
+  }
+  return GG_OK;
+}
+
+int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
+  if (n_u) *n_u = rk->nu;
+  if (n_p) *n_p = rk->np;
+  GG_API_END
+}
+
+int gg_rk_set_state(gg_rk* rk, const double* x) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && x, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  int64_t n = rk->nu + rk->np;
+  if (n) GG_CUDA(cudaMemcpyAsync(rk->x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
+  GG_CUDA(cudaStreamSynchronize(rk->ctx->stream));
+  GG_API_END
+}
+
+int gg_rk_get_state(gg_rk* rk, double* x) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && x, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  rk->x.download(x, rk->ctx->stream);
+  GG_API_END
+}
+
+double* gg_rk_state_device_ptr(gg_rk* rk) { return rk ? rk->x.p : nullptr; }
+
+int gg_rk_step(gg_rk* rk, int32_t n_steps) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && n_steps >= 0, GG_ERR_INVALID, "bad argument");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  for (int32_t i = 0; i < n_steps; ++i) rk_step_async(rk);
+  GG_CUDA(cudaStreamSynchronize(rk->ctx->stream));
+  GG_API_END
+}
+
+int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && x && r, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  int64_t n = rk->nu + rk->np;
+  if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
+  rk_residual_async(rk, rk->xi.p, rk->r.p);
+  rk->r.download(r, rk->ctx->stream);
+  GG_API_END
+}
+
+int gg_rk_stats(gg_rk* rk, int64_t* pcg_iters_total, int64_t* solves_total) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  double h[2];
+  rk->iter_accum.download(h, rk->ctx->stream);
+  if (pcg_iters_total) *pcg_iters_total = (int64_t)h[0];
+  if (solves_total) *solves_total = (int64_t)h[1];
+  GG_API_END
+}
+
+}  // extern "C"

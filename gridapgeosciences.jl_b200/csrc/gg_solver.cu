@@ -1,0 +1,248 @@
+// CSR SpMV and a persistent, single-launch Jacobi-preconditioned conjugate-gradient solver.
+//
+// Stands in for `LUSolver()` / `CGSolver(JacobiLinearSolver(); rtol=1e-12)` at the
+// `Algebra.solve!(x, ::LinearSolver, op, cache)` seam of the reference (src/ODEs/StageOperators.jl:55-88,
+// src/ODEs/DAE.jl:241-274; the reference's own tutorial uses Jacobi-CG at rtol 1e-12,
+// test/Tutorials/ShallowWater.jl:175-176).
+//
+// B200 design: the mass matrices of the named configurations are small enough to live in the 126 MB L2, so a
+// solve is latency-bound, not bandwidth-bound.  The whole PCG iteration therefore runs inside ONE cooperative
+// kernel (one CTA per SM slot, grid-wide barriers between phases) instead of ~6 launches per iteration;
+// dot products are reduced through per-CTA partials that every CTA re-sums in the same fixed order, so the
+// result is deterministic and needs neither atomics nor host round trips.
+#include <cooperative_groups.h>
+#include "gg_common.cuh"
+
+namespace cg = cooperative_groups;
+
+
+namespace gg {
+
+__global__ void k_spmv(int64_t n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                       const double* __restrict__ vals, double alpha, const double* __restrict__ x, double beta,
+                       double* __restrict__ y) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  double acc = 0.0;
+  for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k) acc = fma(vals[k], x[colind[k]], acc);
+  y[r] = beta == 0.0 ? alpha * acc : fma(alpha, acc, beta * y[r]);
+}
+
+__global__ void k_diag_inv(int64_t n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                           const double* __restrict__ vals, double* __restrict__ dinv) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  double d = 0.0;
+  for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+    if (colind[k] == r) d = vals[k];
+  dinv[r] = d != 0.0 ? 1.0 / d : 1.0;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  // fixed-order reduction: warp shuffles then the first warp over the warp partials
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+__device__ __forceinline__ double grid_total(const double* partials, int nblocks, double* sh) {
+  // every CTA sums all partials in the same order -> identical value everywhere
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += partials[i];
+  v = block_sum(v, sh);
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = v;
+  __syncthreads();
+  return bc;
+}
+
+// x = A^-1 b by Jacobi-PCG starting from x = 0.  `scale_b`: solve A x = scale_b * b (the RK stages need -r).
+__global__ void __launch_bounds__(256)
+k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                 const double* __restrict__ vals, const double* __restrict__ dinv, const double* __restrict__ b,
+                 double scale_b, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                 double* __restrict__ p, double* __restrict__ Ap, double* __restrict__ partials, double rtol,
+                 int max_iter, double* __restrict__ stats) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  const int nb = gridDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  double* P0 = partials;           // [nb]
+  double* P1 = partials + nb;      // [nb]
+  double* P2 = partials + 2 * nb;  // [nb]
+
+  // r = b, z = Dinv r, p = z, x = 0; rz, bb
+  double lrz = 0.0, lbb = 0.0;
+  for (int64_t i = tid; i < n; i += nth) {
+    double bi = scale_b * b[i];
+    double zi = dinv[i] * bi;
+    x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
+    lrz = fma(bi, zi, lrz);
+    lbb = fma(bi, bi, lbb);
+  }
+  lrz = block_sum(lrz, sh);
+  lbb = block_sum(lbb, sh);
+  if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; }
+  grid.sync();
+  double rz = grid_total(P0, nb, sh);
+  const double bb = grid_total(P1, nb, sh);
+  int it = 0;
+  double rr = bb;
+  if (bb > 0.0) {
+    const double tol2 = rtol * rtol * bb;
+    for (it = 1; it <= max_iter; ++it) {
+      // Ap = A p ; pAp
+      double lpap = 0.0;
+      for (int64_t i = tid; i < n; i += nth) {
+        double acc = 0.0;
+        for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) acc = fma(vals[k], p[colind[k]], acc);
+        Ap[i] = acc;
+        lpap = fma(p[i], acc, lpap);
+      }
+      lpap = block_sum(lpap, sh);
+      if (threadIdx.x == 0) P2[blockIdx.x] = lpap;
+      grid.sync();
+      const double alpha = rz / grid_total(P2, nb, sh);
+      double lrz2 = 0.0, lrr = 0.0;
+      for (int64_t i = tid; i < n; i += nth) {
+        x[i] = fma(alpha, p[i], x[i]);
+        double ri = fma(-alpha, Ap[i], r[i]);
+        double zi = dinv[i] * ri;
+        r[i] = ri; z[i] = zi;
+        lrz2 = fma(ri, zi, lrz2);
+        lrr = fma(ri, ri, lrr);
+      }
+      lrz2 = block_sum(lrz2, sh);
+      lrr = block_sum(lrr, sh);
+      if (threadIdx.x == 0) { P0[blockIdx.x] = lrz2; P1[blockIdx.x] = lrr; }
+      grid.sync();
+      const double rz_new = grid_total(P0, nb, sh);
+      rr = grid_total(P1, nb, sh);
+      if (rr <= tol2) break;  // uniform across the grid: every CTA computed the same rr
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      for (int64_t i = tid; i < n; i += nth) p[i] = fma(beta, p[i], z[i]);
+      grid.sync();
+    }
+  }
+  if (tid == 0) {
+    stats[0] = (double)(it > max_iter ? max_iter : it);
+    stats[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  }
+}
+
+void spmv(gg_csr* A, double alpha, const double* x, double beta, double* y) {
+  if (A->n_rows == 0) return;
+  k_spmv<<<(unsigned)((A->n_rows + 127) / 128), 128, 0, A->ctx->stream>>>(A->n_rows, A->d_rowptr.p, A->d_colind.p,
+                                                                          A->d_vals.p, alpha, x, beta, y);
+  A->ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+void solver_update(gg_solver* s) {
+  gg_csr* A = s->A;
+  if (A->n_rows == 0) return;
+  k_diag_inv<<<(unsigned)((A->n_rows + 127) / 128), 128, 0, A->ctx->stream>>>(A->n_rows, A->d_rowptr.p, A->d_colind.p,
+                                                                              A->d_vals.p, s->dinv.p);
+  A->ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+// enqueue one solve A x = scale_b * b (x overwritten, starts from 0); no host synchronisation
+void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x) {
+  gg_csr* A = s->A;
+  int64_t n = A->n_rows;
+  if (n == 0) return;
+  const int32_t* rp = A->d_rowptr.p;
+  const int32_t* ci = A->d_colind.p;
+  const double* va = A->d_vals.p;
+  const double* di = s->dinv.p;
+  double *r = s->r.p, *z = s->z.p, *p = s->p.p, *Ap = s->Ap.p, *pa = s->partials.p, *stt = s->stats.p;
+  double rtol = s->rtol;
+  int mi = s->max_iter;
+  void* args[] = {&n, &rp, &ci, &va, &di, &b, &scale_b, &x, &r, &z, &p, &Ap, &pa, &rtol, &mi, &stt};
+  // do not launch more CTAs than there is work for (fewer CTAs = cheaper grid barriers)
+  int grid = s->grid;
+  int64_t want = (n + s->block - 1) / s->block;
+  if (want < grid) grid = (int)std::max<int64_t>(want, 1);
+  GG_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(grid), dim3(s->block), args, 0, A->ctx->stream));
+  A->ctx->launches++;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_csr_spmv(gg_csr* A, double alpha, gg_vec* x, double beta, gg_vec* y) {
+  GG_API_BEGIN
+  GG_REQUIRE(A && x && y, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(gg_vec_size(x) == A->n_cols && gg_vec_size(y) == A->n_rows, GG_ERR_INVALID, "vector sizes do not match the matrix");
+  GG_CUDA(cudaSetDevice(A->ctx->device));
+  spmv(A, alpha, x->d.p, beta, y->d.p);
+  GG_CUDA(cudaStreamSynchronize(A->ctx->stream));
+  GG_API_END
+}
+
+int gg_solver_pcg_create(gg_csr* A, double rtol, int max_iter, gg_solver** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(A && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(A->n_rows == A->n_cols, GG_ERR_INVALID, "PCG needs a square matrix");
+  GG_CUDA(cudaSetDevice(A->ctx->device));
+  std::unique_ptr<gg_solver> s(new gg_solver);
+  s->A = A;
+  s->rtol = rtol > 0 ? rtol : 1e-12;
+  s->max_iter = max_iter > 0 ? max_iter : 1000;
+  int64_t n = A->n_rows;
+  s->dinv.alloc(n); s->r.alloc(n); s->z.alloc(n); s->p.alloc(n); s->Ap.alloc(n);
+  int per_sm = 0;
+  GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, s->block, 0));
+  GG_REQUIRE(per_sm >= 1, GG_ERR_CUDA, "persistent PCG kernel does not fit on an SM");
+  s->grid = A->ctx->sm_count * std::min(per_sm, 2);
+  s->partials.alloc(3 * (size_t)s->grid);
+  s->stats.alloc(2);
+  solver_update(s.get());
+  GG_CUDA(cudaStreamSynchronize(A->ctx->stream));
+  *out = s.release();
+  GG_API_END
+}
+
+int gg_solver_update(gg_solver* s) {
+  GG_API_BEGIN
+  GG_REQUIRE(s, GG_ERR_INVALID, "null solver");
+  GG_CUDA(cudaSetDevice(s->A->ctx->device));
+  solver_update(s);
+  GG_CUDA(cudaStreamSynchronize(s->A->ctx->stream));
+  GG_API_END
+}
+
+int gg_solver_solve(gg_solver* s, gg_vec* b, gg_vec* x, int32_t* iters, double* rel_res) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && b && x, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(gg_vec_size(b) == s->A->n_rows && gg_vec_size(x) == s->A->n_rows, GG_ERR_INVALID, "vector sizes do not match the matrix");
+  GG_CUDA(cudaSetDevice(s->A->ctx->device));
+  solver_solve_async(s, b->d.p, 1.0, x->d.p);
+  double st[2] = {0, 0};
+  if (s->A->n_rows) s->stats.download(st, s->A->ctx->stream);
+  if (iters) *iters = (int32_t)st[0];
+  if (rel_res) *rel_res = st[1];
+  GG_REQUIRE(st[1] <= s->rtol * 1.0000001 || s->A->n_rows == 0, GG_ERR_NOCONV,
+             "PCG did not converge: relative residual " + std::to_string(st[1]) + " after " + std::to_string((int)st[0]) + " iterations");
+  GG_API_END
+}
+
+void gg_solver_destroy(gg_solver* s) { delete s; }
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+/*
+ * geosgpu.h -- C ABI of libgeosgpu.so: the B200 (sm_100a) drop-in for the data-parallel hot path of
+ * GridapGeosciences.jl v0.7.2: cell-wise quadrature -> element matrix/vector -> sparse assembly of
+ * manifold FE forms on the cubed sphere, and the explicit Runge-Kutta stage residual / mass solve.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative to the
+ * reference checkout).  The reference reaches that arithmetic through Gridap's `Assembler` and
+ * `LinearSolver` abstract types (src/ODEs/ODEs.jl:33-39 imports `collect_cell_vector,
+ * collect_cell_matrix, assemble_vector_add!, allocate_matrix, assemble_matrix_add!, assemble_matrix!,
+ * assemble_vector!`); INTEGRATION.md shows the Julia `ccall` shim that binds these symbols.
+ *
+ * Conventions
+ *   - plain C: opaque handles, pointers and sizes only.  No exceptions cross the boundary: every call
+ *     returns GG_OK (0) or a negative error code, with a message available from gg_last_error().
+ *   - the library owns all device memory behind the handles; host arrays passed IN are copied before
+ *     the call returns; outputs are written into caller-allocated HOST buffers unless the function
+ *     name says `_device`.
+ *   - ids crossing the ABI are 1-based Int32 (Gridap `Table{Int32}`), Dirichlet DOFs are negative;
+ *     CSR export is Int64 (SparseMatrixCSC{Float64,Int}), 0- or 1-based on request.
+ *   - all floating point data is FP64.
+ *   - one gg_ctx per process = one GPU (one process per GPU; multi-GPU runs exchange halos with NCCL
+ *     on the device pointers exposed by gg_vec_device_ptr()).  Calls on one context are serialised by
+ *     the caller; work is enqueued on the context's stream and the call returns after the stream
+ *     has been synchronised unless stated otherwise.
+ *   - there is NO CPU fallback: if no CUDA device is usable gg_init fails with GG_ERR_CUDA.
+ */
+#ifndef GEOSGPU_H
+#define GEOSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_OK 0
+#define GG_ERR_INVALID (-1)     /* bad argument */
+#define GG_ERR_CUDA (-2)        /* CUDA runtime error (message has the CUDA string) */
+#define GG_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels implement (never a silent fallback) */
+#define GG_ERR_NOMEM (-4)
+#define GG_ERR_NOCONV (-5)      /* iterative solver did not reach the requested tolerance */
+
+typedef struct gg_ctx gg_ctx;
+typedef struct gg_mesh gg_mesh;
+typedef struct gg_space gg_space;
+typedef struct gg_csr gg_csr;
+typedef struct gg_vec gg_vec;
+typedef struct gg_solver gg_solver;
+typedef struct gg_rk gg_rk;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int gg_init(int device_id, gg_ctx** out);
+void gg_finalize(gg_ctx* ctx);
+/* message of the last failing call on this thread (ctx may be NULL) */
+const char* gg_last_error(gg_ctx* ctx);
+/* cudaStream_t of the context (as void*), so that callers can order their own work / NCCL calls */
+void* gg_stream(gg_ctx* ctx);
+int gg_synchronize(gg_ctx* ctx);
+/* number of kernel launches issued by this context so far (bench.py's `gpu_launches`) */
+int64_t gg_launch_count(gg_ctx* ctx);
+
+/* ---- atlas mesh ------------------------------------------------------------------------------
+ * Replaces AtlasDiscreteModel(CubedSphereMesh(radius), nref) -- src/Geometry/AtlasDiscreteModels.jl:222-229,
+ * src/Geometry/AtlasGrids.jl:227-304, src/Geometry/CubedSphereMesh.jl:83-116.
+ *   dim        2 (surface).  3 (shell, src/Geometry/CubedSphereWithThicknessMesh.jl) -> GG_ERR_UNSUPPORTED for now.
+ *   n          cells per panel edge (the reference only offers n = 2^nref; any n >= 1 is accepted here)
+ *   ordering   0 = one-shot parent-major, x-fastest inside a panel (AtlasGrids.jl:254-280)
+ * Cells [first_cell, first_cell + n_local) of the global panel-major order are instantiated (pass 0 and
+ * -1 for all); a rank of the linear partition `div((i-1)*P, Nc)+1`
+ * (src/Distributed/AtlasDistributedDiscreteModels.jl:31) uses its own slice, see gg_partition_range(). */
+int gg_mesh_cubed_sphere(gg_ctx* ctx, int dim, int n, int n_layers, double radius, double thickness,
+                         int ordering, gg_mesh** out);
+/* Connectivity supplied by the caller (the Julia host owns model construction): replaces the
+ * AtlasGrid fields `cell_chart_coords` / `cell_to_chart` (AtlasGrids.jl:141-182) and
+ * get_cell_node_ids (AtlasGrids.jl:383-384).  cell_node_ids: [n_cells][4], 1-based.
+ * cell_chart_coords: [n_cells][4][2] in Gridap vertex order BL,BR,TL,TR.  Cells must be axis-aligned
+ * rectangles in chart space (true for every cubed-sphere atlas, serial or p4est). */
+int gg_mesh_from_arrays(gg_ctx* ctx, int dim, int64_t n_cells, int64_t n_nodes, const int32_t* cell_to_chart,
+                        const double* cell_chart_coords, const int32_t* cell_node_ids, double radius,
+                        double thickness, gg_mesh** out);
+int gg_mesh_info(gg_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* n_edges);
+int gg_mesh_get_cell_nodes(gg_mesh* m, int32_t* out /* [n_cells][4], 1-based */);
+int gg_mesh_get_cell_to_chart(gg_mesh* m, int32_t* out /* [n_cells], 1-based panel */);
+int gg_mesh_get_chart_coords(gg_mesh* m, double* out /* [n_cells][4][2] */);
+void gg_mesh_destroy(gg_mesh* m);
+/* Linear partition of the reference: [first,last) 0-based cell range owned by `part` (0-based) of `nparts`. */
+int gg_partition_range(int64_t n_cells, int nparts, int part, int64_t* first, int64_t* last);
+/* Sub-mesh of an existing mesh: cells listed in `cells` (0-based, ascending), e.g. owned + ghost cells of a rank
+ * (AtlasDistributedDiscreteModels.jl:34-66).  Node ids are kept global. */
+int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** out);
+/* ghost cells of the owned range [first,last): cells outside it sharing a vertex with a cell inside (:34-49).
+ * Pass out=NULL to query the count. */
+int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghost, int64_t* out);
+
+/* ---- FE spaces -------------------------------------------------------------------------------
+ * Replace TestFESpace(model, ReferenceFE(lagrangian|raviart_thomas, Float64, order); conformity, constraint)
+ * (call sites: test/Laplacian/LaplaceBeltrami.jl:34-35, test/Transient/TransientWaveEquation.jl:40-47). */
+#define GG_SPACE_CG 0 /* lagrangian, conformity=:H1 */
+#define GG_SPACE_DG 1 /* lagrangian, conformity=:L2 */
+#define GG_SPACE_RT 2 /* raviart_thomas, conformity=:HDiv */
+#define GG_CONSTRAINT_NONE 0
+#define GG_CONSTRAINT_ZEROMEAN 1 /* constraint=:zeromean: last free DOF fixed (Gridap ZeroMeanFESpace) */
+/* Built-in numbering = our restatement of Gridap's (parity unpinned). */
+int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space** out);
+/* Numbering owned by the caller (exact Gridap numbering when called from Julia):
+ * cell_dof_ids [n_cells][ndofs_loc] 1-based, negative = Dirichlet; cell_dof_signs (RT) may be NULL (= all +1). */
+int gg_space_from_arrays(gg_mesh* m, int kind, int order, int64_t n_free, const int32_t* cell_dof_ids,
+                         const int8_t* cell_dof_signs, gg_space** out);
+int gg_space_info(gg_space* s, int64_t* n_free, int32_t* ndofs_loc, int64_t* n_dirichlet);
+int gg_space_get_cell_dofs(gg_space* s, int32_t* out /* [n_cells][ndofs_loc], 1-based */);
+int gg_space_get_cell_signs(gg_space* s, int8_t* out /* [n_cells][ndofs_loc] */);
+void gg_space_destroy(gg_space* s);
+
+/* ---- device vectors --------------------------------------------------------------------------
+ * Stand in for the Julia `Vector{Float64}` of free DOF values (and for per-quadrature-point data). */
+int gg_vec_create(gg_ctx* ctx, int64_t n, gg_vec** out);
+int gg_vec_set(gg_vec* v, const double* host);  /* H2D */
+int gg_vec_get(gg_vec* v, double* host);        /* D2H */
+int gg_vec_fill(gg_vec* v, double value);
+int64_t gg_vec_size(gg_vec* v);
+double* gg_vec_device_ptr(gg_vec* v);
+void gg_vec_destroy(gg_vec* v);
+
+/* ---- sparsity pattern and CSR matrix ------------------------------------------------------------
+ * Replaces allocate_matrix / symbolic loop of SparseMatrixAssembler (call sites
+ * src/ODEs/ODEOpsFromTFEOps.jl:154-160,385-408; src/ODEs/DAE.jl:161-162).  Built ONCE on the device
+ * (radix sort + run-length of the (row, col) pairs of all cells); also builds the slot -> contributing
+ * (cell, local pair) lists used by the atomic-free numeric phase.  Columns are sorted inside each row. */
+int gg_pattern(gg_space* test, gg_space* trial, gg_csr** out);
+int gg_csr_info(gg_csr* A, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
+/* index_base 0 or 1.  Any of rowptr/colind/vals may be NULL to skip it. */
+int gg_csr_export(gg_csr* A, int64_t* rowptr, int64_t* colind, double* vals, int index_base);
+double* gg_csr_device_values(gg_csr* A);
+/* y = alpha * A x + beta * y on the device */
+int gg_csr_spmv(gg_csr* A, double alpha, gg_vec* x, double beta, gg_vec* y);
+void gg_csr_destroy(gg_csr* A);
+
+/* ---- forms -----------------------------------------------------------------------------------
+ * Gridap forms are Julia closures interpreted as lazy operation trees; the library implements the forms of
+ * the reference's drivers as hand-written kernels selected by id (the documented deviation). */
+typedef enum {
+  /* a(u,v) = int grad(v).(ginv.grad(u)) sqrtg   -- test/Laplacian/LaplaceBeltrami.jl:47 */
+  GG_FORM_LAPLACE_BELTRAMI = 1,
+  /* a(u,v) = int grad_G(v).grad_G(u) dG on the extrinsic model (2x3 Jacobian, pseudo-determinant,
+   * pseudo-inverse) -- test/AmbientModel/AmbientLaplaceBeltrami.jl:44, src/Geometry/AtlasGrids.jl:374-376 */
+  GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC = 2,
+  /* a(u,v) = int u v sqrtg - int grad(v).(ginv.grad(u)) sqrtg -- test/Laplacian/Helmholtz.jl:43 */
+  GG_FORM_HELMHOLTZ = 3,
+  /* m(p,q) = int q p sqrtg -- scalar block of test/Transient/TransientWaveEquation.jl:63 */
+  GG_FORM_MASS_SCALAR = 4,
+  /* m(u,v) = int (v.(g u)) / sqrtg -- RT block of test/Transient/TransientWaveEquation.jl:63 */
+  GG_FORM_MASS_RT = 5,
+  /* b(u,q) = int q div(u)  (rows: scalar test, cols: RT trial) -- test/Transient/TransientWaveEquation.jl:64 */
+  GG_FORM_DIV = 6,
+  /* l(v) = int f v sqrtg, f given at the quadrature points -- test/Laplacian/LaplaceBeltrami.jl:53 */
+  GG_FORM_SOURCE = 7
+} gg_form;
+
+typedef struct {
+  gg_space* test;
+  gg_space* trial;   /* NULL for linear forms */
+  int32_t degree;    /* Measure(Omega, degree): tensor Gauss-Legendre with ceil((degree+1)/2) points per direction */
+  gg_vec* u;         /* DOF vector of the trial space for residual / action forms (free values), or NULL */
+  gg_vec* qdata;     /* per-quadrature-point coefficient [n_cells][Q] (x-fastest inside the cell), or NULL */
+  double dirichlet;  /* value of the (single, zeromean) Dirichlet DOF when gathering u */
+  double scale;      /* result is multiplied by this (1.0 if 0 is passed) */
+} gg_form_args;
+
+/* assemble_matrix! / assemble_matrix_add! (src/ODEs/ODEs.jl:36-38): numeric phase into the pattern of A. */
+int gg_assemble_matrix(gg_form form, const gg_form_args* args, gg_csr* A, int add);
+/* assemble_vector! / assemble_vector_add! (src/ODEs/ODEs.jl:35,39): b (size n_free of the test space).
+ * For bilinear forms this is the residual / matrix-free action b_i = a(u_h, phi_i) with u_h = args->u. */
+int gg_assemble_vector(gg_form form, const gg_form_args* args, gg_vec* b, int add);
+/* Jacobian and residual in ONE pass over the cells (shared geometry): A = a(.,.), b_i = a(u_h, phi_i). */
+int gg_assemble_matrix_and_vector(gg_form form, const gg_form_args* args, gg_csr* A, gg_vec* b);
+/* parity hook: dense element matrices of cells [first, first+n) -> host out[n][m_test][m_trial] */
+int gg_element_matrices(gg_form form, const gg_form_args* args, int64_t first_cell, int64_t n, double* out);
+/* parity hook: element vectors of cells [first, first+n) -> host out[n][m_test] */
+int gg_element_vectors(gg_form form, const gg_form_args* args, int64_t first_cell, int64_t n, double* out);
+/* chart / ambient coordinates of the quadrature points: out_chart [n_cells][Q][2], out_xyz [n_cells][Q][3]
+ * (AmbientMapCellField, src/CellData/CellFields.jl:207-212); either may be NULL */
+int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* out_xyz);
+/* sum(int f sqrtg dOmega) with f at the quadrature points (NULL = 1: the surface area of
+ * test/Geometry/SurfaceArea.jl:19-24) */
+int gg_integrate(gg_mesh* m, int32_t degree, gg_vec* qdata, double* out);
+
+/* ---- geometry parity hooks (device evaluation of src/Fields/CubedSphere{Map,Metric,InvMetric}.jl) ---- */
+/* pts [n][2] chart points of panel `panel` (1-based); outputs (any may be NULL):
+ * xyz [n][3], jac [n][2][3] (J[i][k] = d phi_k / d x_i), metric [n][3] (g11,g12,g22), inv_metric [n][3], sqrtg [n] */
+int gg_eval_geometry(gg_ctx* ctx, int panel, double radius, int64_t n, const double* pts, double* xyz,
+                     double* jac, double* metric, double* inv_metric, double* sqrtg);
+
+/* ---- linear solver (mass solves of the RK stages) ------------------------------------------------
+ * Stands in for LUSolver() / CGSolver(JacobiLinearSolver(); rtol=1e-12) (test/Tutorials/ShallowWater.jl:175-176)
+ * at the `Algebra.solve!(x, ::LinearSolver, op, cache)` seam (src/ODEs/StageOperators.jl:55-88). */
+int gg_solver_pcg_create(gg_csr* A, double rtol, int max_iter, gg_solver** out);
+/* numerical_setup!: refresh the Jacobi preconditioner after A's values changed */
+int gg_solver_update(gg_solver* s);
+int gg_solver_solve(gg_solver* s, gg_vec* b, gg_vec* x, int32_t* iters, double* rel_res);
+void gg_solver_destroy(gg_solver* s);
+
+/* ---- explicit Runge-Kutta drivers ----------------------------------------------------------------
+ * Replace Gridap.ODEs `ode_march!` for EXRungeKutta on the linear-wave operator
+ * (test/Transient/TransientWaveEquation.jl:63-77; constant mass) -- the whole step runs on the device. */
+#define GG_PROBLEM_WAVE 1
+typedef struct {
+  int32_t problem;     /* GG_PROBLEM_* */
+  int32_t order;       /* p_fe: RT_p x DG_p */
+  int32_t degree;      /* quadrature degree */
+  int32_t n_stages;
+  const double* A;     /* [n_stages][n_stages] row-major, strictly lower triangular */
+  const double* b;     /* [n_stages] */
+  const double* c;     /* [n_stages] */
+  double dt;
+  double rtol;         /* PCG tolerance of the RT mass solve (1e-12 if 0) */
+} gg_rk_args;
+int gg_rk_create(gg_mesh* m, const gg_rk_args* args, gg_rk** out);
+int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p);
+int gg_rk_set_state(gg_rk* rk, const double* x /* [n_u + n_p] host */);
+int gg_rk_get_state(gg_rk* rk, double* x);
+double* gg_rk_state_device_ptr(gg_rk* rk);
+int gg_rk_step(gg_rk* rk, int32_t n_steps);
+/* matrix-free stage residual r = res(x) (parity hook), host in/out */
+int gg_rk_residual(gg_rk* rk, const double* x, double* r);
+int gg_rk_stats(gg_rk* rk, int64_t* pcg_iters_total, int64_t* solves_total);
+void gg_rk_destroy(gg_rk* rk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOSGPU_H */

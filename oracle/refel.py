@@ -171,7 +171,13 @@ class RaviartThomasQuad:
                         M[row, :] = (w2 * q) @ P[:, :, comp]
                         row += 1
         assert row == self.ndofs
-        self.C = np.linalg.inv(M)  # phi_j = sum_i C[i, j] psi_i
+        # phi_j = sum_i C[i, j] psi_i; the monomial moment matrix has cond ~1e4 for k = 2, so polish the
+        # inverse with two Newton-Schulz steps in extended precision
+        Ml = M.astype(np.longdouble)
+        Cl = np.linalg.inv(M).astype(np.longdouble)
+        for _ in range(2):
+            Cl = Cl + Cl @ (np.eye(self.ndofs, dtype=np.longdouble) - Ml @ Cl)
+        self.C = Cl.astype(np.float64)
 
     def _prebasis(self, pts):
         out = np.zeros((pts.shape[0], self.ndofs, 2))
