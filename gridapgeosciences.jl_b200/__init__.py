@@ -58,6 +58,22 @@ class Context:
     def launches(self):
         return int(self.lib.gg_launch_count(self.h))
 
+    def set_async(self, enabled=True):
+        _lib.check(self.lib.gg_set_async(self.h, 1 if enabled else 0))
+
+    def profile(self, enabled=True):
+        _lib.check(self.lib.gg_profile_enable(self.h, 1 if enabled else 0))
+
+    def profile_query(self, name):
+        n, ms = C.c_int64(), C.c_double()
+        _lib.check(self.lib.gg_profile_query(self.h, name.encode(), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def measure_fp64_peak(self):
+        out = C.c_double()
+        _lib.check(self.lib.gg_measure_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
     def close(self):
         if self.h:
             self.lib.gg_finalize(self.h)

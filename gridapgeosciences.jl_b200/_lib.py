@@ -57,6 +57,10 @@ SIGNATURES = {
     "gg_stream": (C.c_void_p, [_P]),
     "gg_synchronize": (C.c_int, [_P]),
     "gg_launch_count": (_I64, [_P]),
+    "gg_set_async": (C.c_int, [_P, C.c_int]),
+    "gg_profile_enable": (C.c_int, [_P, C.c_int]),
+    "gg_profile_query": (C.c_int, [_P, C.c_char_p, _PI64, _PD]),
+    "gg_measure_fp64_peak": (C.c_int, [_P, _PD]),
     "gg_mesh_cubed_sphere": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _PP]),
     "gg_mesh_from_arrays": (C.c_int, [_P, C.c_int, _I64, _I64, _PI32, _PD, _PI32, C.c_double, C.c_double, _PP]),
     "gg_mesh_info": (C.c_int, [_P, _PI64, _PI64, _PI64]),

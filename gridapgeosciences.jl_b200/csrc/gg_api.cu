@@ -5,6 +5,21 @@ namespace gg {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
 
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, 2 flops per FMA
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+
 __global__ void k_fill(int64_t n, double v, double* __restrict__ x) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = v;
@@ -67,6 +82,64 @@ int gg_synchronize(gg_ctx* ctx) {
 }
 
 int64_t gg_launch_count(gg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gg_set_async(gg_ctx* ctx, int enabled) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx, GG_ERR_INVALID, "null context");
+  ctx->async = enabled != 0;
+  GG_API_END
+}
+
+int gg_profile_enable(gg_ctx* ctx, int enabled) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx, GG_ERR_INVALID, "null context");
+  GG_CUDA(cudaSetDevice(ctx->device));
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  ctx->prof.clear();
+  ctx->profile = enabled != 0;
+  GG_API_END
+}
+
+int gg_profile_query(gg_ctx* ctx, const char* kernel_name, int64_t* count, double* total_ms) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx && kernel_name && count && total_ms, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(ctx->device));
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *count = 0; *total_ms = 0.0;
+  for (auto& e : ctx->prof)
+    if (e.name == kernel_name) {
+      float ms = 0.f;
+      GG_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+      *total_ms += ms; ++*count;
+    }
+  GG_API_END
+}
+
+int gg_measure_fp64_peak(gg_ctx* ctx, double* tflops) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx && tflops, GG_ERR_INVALID, "null argument");
+  GG_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<double> out(1);
+  const int iters = 4096, threads = 256, blocks = ctx->sm_count * 8;
+  cudaEvent_t a, b;
+  GG_CUDA(cudaEventCreate(&a)); GG_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    GG_CUDA(cudaEventRecord(a, ctx->stream));
+    k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(iters, 1.0 + rep, out.p);
+    GG_CUDA(cudaEventRecord(b, ctx->stream));
+    GG_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    GG_CUDA(cudaEventElapsedTime(&ms, a, b));
+    double fl = 2.0 * 64.0 * iters * (double)threads * blocks;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    ctx->launches++;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *tflops = best;
+  GG_API_END
+}
 
 int gg_vec_create(gg_ctx* ctx, int64_t n, gg_vec** out) {
   GG_API_BEGIN

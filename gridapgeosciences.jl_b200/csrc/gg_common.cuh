@@ -101,7 +101,32 @@ struct gg_ctx {
   gg::DevBuf<double> ebuf, vbuf;
   // (order, nq) currently resident in the __constant__ tables of the fast scalar kernels
   int const_order = -1, const_nq = -1;
+  // when set, assembly / solver entry points enqueue their work and return without synchronising the stream
+  bool async = false;
+  // optional per-kernel CUDA-event timing (gg_profile_*): name -> (events, count)
+  bool profile = false;
+  struct ProfEntry { std::string name; cudaEvent_t a, b; };
+  std::vector<ProfEntry> prof;
 };
+
+namespace gg {
+// RAII event pair around one launch when profiling is on
+struct ProfScope {
+  gg_ctx* ctx; cudaEvent_t a = nullptr, b = nullptr; const char* name;
+  ProfScope(gg_ctx* c, const char* n) : ctx(c), name(n) {
+    if (ctx->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEventRecord(b, ctx->stream); ctx->prof.push_back({name, a, b}); }
+  }
+};
+inline void finish_call(gg_ctx* ctx) {
+  if (!ctx->async) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) throw Error(GG_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+  }
+}
+}  // namespace gg
 
 // Reference-element tables for one (order, nq) pair, host copies; see gg_refel.cu
 struct gg_tables;
@@ -159,9 +184,14 @@ struct gg_csr {
   gg::DevBuf<int32_t> d_sptr;    // [nnz+1]
   gg::DevBuf<int32_t> d_ssrc;    // [n_pairs_kept] raw pair id = cell*(mt*mu) + (i*mu+j)
   int64_t n_pairs = 0;
-  // cache of ssrc re-encoded for a given element-buffer layout (symmetric packed / full, entry-major)
+  // chunked gather lists for one element-buffer layout (0 full / 1 symmetric packed, entry-major): sources of every
+  // 2048 consecutive slots sorted by (round, buffer address); see gg_pattern.cu
   int cached_layout = -1;
-  gg::DevBuf<int32_t> d_ssrc_layout;
+  int n_rounds = 0;
+  int64_t n_chunks = 0;
+  gg::DevBuf<int32_t> d_lsrc;      // [n_pairs] element-buffer index
+  gg::DevBuf<uint16_t> d_lslot;    // [n_pairs] slot index inside its chunk
+  gg::DevBuf<int32_t> d_roundptr;  // [n_chunks][n_rounds+1]
 };
 
 struct gg_solver {

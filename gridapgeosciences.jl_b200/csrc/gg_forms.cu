@@ -333,6 +333,7 @@ template <int NB, int NQ>
 static void launch_lb_fast(gg_ctx* ctx, const Geo& g, bool extrinsic, const int32_t* dofs, const double* u, double dir,
                            double* ebuf, double* vbuf) {
   unsigned nb = nblk(g.nc, 128);
+  ProfScope ps(ctx, "k_lb_fast");
   if (extrinsic)
     k_lb_fast<NB, NQ, true><<<nb, 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, g.chart, g.radius, dofs, u, dir, ebuf, vbuf);
   else
@@ -361,6 +362,7 @@ static void run_lb_fast(gg_ctx* ctx, const Geo& g, int order, int nq, bool extri
 
 template <int NB, int NQ>
 static void launch_action_fast(gg_ctx* ctx, const Geo& g, const int32_t* dofs, const double* u, double dir, double* vbuf) {
+  ProfScope ps(ctx, "k_lb_action_fast");
   k_lb_action_fast<NB, NQ><<<nblk(g.nc, 128), 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, dofs, u, dir, vbuf);
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
@@ -560,7 +562,7 @@ int gg_assemble_matrix(gg_form form, const gg_form_args* args, gg_csr* A, int ad
   GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
   int layout = compute_element_matrices(form, args, P, false, nullptr);
   gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, add);
-  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  finish_call(P.ctx);
   GG_API_END
 }
 
@@ -571,7 +573,7 @@ int gg_assemble_vector(gg_form form, const gg_form_args* args, gg_vec* b, int ad
   GG_REQUIRE(gg_vec_size(b) == P.test->n_free, GG_ERR_INVALID, "output vector has the wrong length");
   double* vb = compute_element_vectors(form, args, P);
   gather_vector(P.test, vb, b->d.p, P.scale, add);
-  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  finish_call(P.ctx);
   GG_API_END
 }
 
@@ -585,7 +587,7 @@ int gg_assemble_matrix_and_vector(gg_form form, const gg_form_args* args, gg_csr
   int layout = compute_element_matrices(form, args, P, true, &vb);
   gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, 0);
   gather_vector(P.test, vb, b->d.p, P.scale, 0);
-  GG_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  finish_call(P.ctx);
   GG_API_END
 }
 

@@ -12,7 +12,7 @@
 //   * all table operands are __constant__ with compile-time offsets (FMA constant-bank operands) for the unrolled
 //     y loop and warp-uniform LDC loads for the rolled x loop, so the instruction stream is almost pure DFMA;
 //   * the symmetric half (M(M+1)/2 entries) is written entry-major [pair][cell]: consecutive threads write
-//     consecutive addresses (fully coalesced FP64 stores); the atomic-free CSR fill is k_gather_slots.
+//     consecutive addresses (fully coalesced FP64 stores); the atomic-free CSR fill is k_gather_chunks (gg_pattern.cu).
 // The fused residual r_e = Ke u_e is formed from the registers that already hold Ke (LB is linear).
 #pragma once
 #include "gg_common.cuh"

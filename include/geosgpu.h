@@ -58,6 +58,15 @@ void* gg_stream(gg_ctx* ctx);
 int gg_synchronize(gg_ctx* ctx);
 /* number of kernel launches issued by this context so far (bench.py's `gpu_launches`) */
 int64_t gg_launch_count(gg_ctx* ctx);
+/* async != 0: assembly / SpMV entry points enqueue their kernels on gg_stream() and return without synchronising
+ * (the RK stage loop and bench.py's device-resident timing); results are complete after gg_synchronize(). */
+int gg_set_async(gg_ctx* ctx, int enabled);
+/* measurement hooks: per-kernel CUDA-event timing on the context's stream (names: "k_lb_fast",
+ * "k_lb_action_fast", "k_gather_chunks", "k_gather_dofs"), and an FP64-FMA throughput probe (the roofline
+ * denominator of the FP64-bound element kernels; MEASURED_PEAKS.json has no FP64 figure). */
+int gg_profile_enable(gg_ctx* ctx, int enabled);
+int gg_profile_query(gg_ctx* ctx, const char* kernel_name, int64_t* count, double* total_ms);
+int gg_measure_fp64_peak(gg_ctx* ctx, double* tflops);
 
 /* ---- atlas mesh ------------------------------------------------------------------------------
  * Replaces AtlasDiscreteModel(CubedSphereMesh(radius), nref) -- src/Geometry/AtlasDiscreteModels.jl:222-229,
