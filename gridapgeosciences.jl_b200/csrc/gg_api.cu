@@ -49,6 +49,9 @@ int gg_init(int device_id, gg_ctx** out) {
   ctx->device = device_id;
   ctx->sm_count = prop.multiProcessorCount;
   GG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  GG_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  for (auto& e : ctx->ev_batch) GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx.release();
   GG_API_END
 }
@@ -62,6 +65,9 @@ void gg_finalize(gg_ctx* ctx) {
   ctx->tabs.clear();
   ctx->ebuf.release();
   ctx->vbuf.release();
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  for (auto& e : ctx->ev_batch) if (e) cudaEventDestroy(e);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

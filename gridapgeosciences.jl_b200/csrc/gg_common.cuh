@@ -93,6 +93,9 @@ namespace gg { struct FormTab; }
 struct gg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // second stream + events for overlapping the HBM-bound CSR fill with the FP64-bound element kernel
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_batch[8] = {nullptr}, ev_join = nullptr;
   int sm_count = 148;
   int64_t launches = 0;
   // device tabulations of reference bases at quadrature points, keyed by (kind, order, nq)
@@ -147,6 +150,13 @@ struct gg_mesh {
   // device: per-cell axis-aligned chart box (SoA) and panel
   gg::DevBuf<double> d_x0, d_y0, d_hx, d_hy;
   gg::DevBuf<int32_t> d_chart;
+  // distinct chart intervals [lo, lo+h] of the cells in x and in y (cells of one mesh column / row share theirs),
+  // the interval id of every cell, and per quadrature size nq the tangents of the interval's abscissae
+  int64_t n_xint = 0, n_yint = 0;
+  gg::DevBuf<double> d_xlo, d_xh, d_ylo, d_yh;
+  gg::DevBuf<int32_t> d_ix, d_iy;
+  struct TanTab { gg::DevBuf<double> tx, ty; };
+  std::map<int, std::shared_ptr<TanTab>> tan_tabs;
   bool topology_built = false;
 };
 
@@ -192,6 +202,11 @@ struct gg_csr {
   gg::DevBuf<int32_t> d_lsrc;      // [n_pairs] element-buffer index
   gg::DevBuf<uint16_t> d_lslot;    // [n_pairs] slot index inside its chunk
   gg::DevBuf<int32_t> d_roundptr;  // [n_chunks][n_rounds+1]
+  // pipelining of the numeric phase: chunks ordered by the cell batch that completes them (all of a chunk's sources
+  // lie in batches <= its batch), so the CSR fill of batch b can run while the element kernel works on batch b+1
+  static constexpr int N_BATCH = 8;
+  gg::DevBuf<int32_t> d_chunk_order;       // [n_chunks] chunk ids sorted by completing batch
+  int64_t batch_chunk_ptr[N_BATCH + 1] = {0};
 };
 
 struct gg_solver {
@@ -208,6 +223,9 @@ namespace gg {
 void build_vec_map(gg_space* s);
 void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);
 void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int add);
+void prepare_gather(gg_csr* A, int layout);
+// CSR fill of the chunks completed by cell batch `batch`, enqueued on `st`
+void gather_matrix_batch(gg_csr* A, int batch, const double* ebuf, double scale, int add, cudaStream_t st);
 const double* element_matrices_device(gg_form form, const gg_form_args* args, int* layout);
 void spmv(gg_csr* A, double alpha, const double* x, double beta, double* y);
 void solver_update(gg_solver* s);

@@ -9,6 +9,7 @@
 //     (space, order, degree, form) combination.  Both are CUDA; nothing falls back to the host.
 #include <cub/cub.cuh>
 #include <cstring>
+#include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
@@ -320,27 +321,82 @@ static void load_const_tables(gg_ctx* ctx, int order, int nq) {
       int a = std::min(x2l[I], x2l[J]), b = std::max(x2l[I], x2l[J]);
       plane.push_back(a * M - (a * (a - 1)) / 2 + (b - a));
     }
+  // compact pair tables in use order: row q = [NN sym | DD sym | ND], quadrature weight folded in
+  int NS = nb * (nb + 1) / 2, ROW = 2 * NS + M;
+  std::vector<double> lb((size_t)nq * ROW);
+  for (int q = 0; q < nq; ++q) {
+    int k = 0;
+    for (int i = 0; i < nb; ++i)
+      for (int j = i; j < nb; ++j) {
+        lb[(size_t)q * ROW + k] = t.NN[i * nb + j][q];
+        lb[(size_t)q * ROW + NS + k] = t.DD[i * nb + j][q];
+        ++k;
+      }
+    for (int k2 = 0; k2 < M; ++k2) lb[(size_t)q * ROW + 2 * NS + k2] = t.ND[k2][q];
+  }
   // synchronous w.r.t. the stream: earlier launches reading the old tables must have drained
   GG_CUDA(cudaStreamSynchronize(ctx->stream));
   GG_CUDA(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+  GG_CUDA(cudaMemcpyToSymbol(c_lb, lb.data(), lb.size() * sizeof(double)));
   GG_CUDA(cudaMemcpyToSymbol(c_plane, plane.data(), plane.size() * sizeof(int32_t)));
   GG_CUDA(cudaMemcpyToSymbol(c_lex2loc, x2l.data(), x2l.size() * sizeof(int32_t)));
   ctx->const_order = order;
   ctx->const_nq = nq;
 }
 
+// per-(mesh, nq) tangent tables of the distinct chart intervals, built on the device at first use
+static CellGeo cell_geo(gg_mesh* m, int nq) {
+  gg_ctx* ctx = m->ctx;
+  auto it = m->tan_tabs.find(nq);
+  if (it == m->tan_tabs.end()) {
+    auto T = std::make_shared<gg_mesh::TanTab>();
+    auto tab = get_tab(ctx, GG_SPACE_DG, 0, nq);  // 1-D abscissae on the device
+    T->tx.alloc((size_t)m->n_xint * nq);
+    T->ty.alloc((size_t)m->n_yint * nq);
+    if (m->n_xint) k_tan_table<<<nblk(m->n_xint * nq, 128), 128, 0, ctx->stream>>>(m->n_xint, nq, m->d_xlo.p, m->d_xh.p, tab->xi.p, T->tx.p);
+    if (m->n_yint) k_tan_table<<<nblk(m->n_yint * nq, 128), 128, 0, ctx->stream>>>(m->n_yint, nq, m->d_ylo.p, m->d_yh.p, tab->xi.p, T->ty.p);
+    ctx->launches += 2;
+    GG_CUDA(cudaGetLastError());
+    it = m->tan_tabs.emplace(nq, T).first;
+  }
+  CellGeo g;
+  g.hx = m->d_hx.p; g.hy = m->d_hy.p; g.ix = m->d_ix.p; g.iy = m->d_iy.p;
+  g.tx = it->second->tx.p; g.ty = it->second->ty.p;
+  g.chart = m->d_chart.p; g.radius = m->radius;
+  return g;
+}
+
 template <int NB, int NQ>
-static void launch_lb_fast(gg_ctx* ctx, const Geo& g, bool extrinsic, const int32_t* dofs, const double* u, double dir,
-                           double* ebuf, double* vbuf) {
-  unsigned nb = nblk(g.nc, 128);
+static void launch_lb_fast(gg_ctx* ctx, int64_t nc, int64_t c0, int64_t c1, const CellGeo& g, bool extrinsic,
+                           const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf, bool leave_room) {
+  if (c1 <= c0) return;
+  unsigned nb = nblk(c1 - c0, 128);
+  // leave_room: cap residency at 2 CTAs per SM (an unused 80 KB dynamic shared-memory reservation), so that a third of the
+  // register file and 67 KB of shared memory stay free for the concurrently running CSR-fill CTAs of the second stream
+  size_t pad = leave_room ? 80 * 1024 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GG_CUDA(cudaFuncSetAttribute(k_lb_fast<NB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    GG_CUDA(cudaFuncSetAttribute(k_lb_fast<NB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
   ProfScope ps(ctx, "k_lb_fast");
   if (extrinsic)
-    k_lb_fast<NB, NQ, true><<<nb, 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, g.chart, g.radius, dofs, u, dir, ebuf, vbuf);
+    k_lb_fast<NB, NQ, true><<<nb, 128, pad, ctx->stream>>>(nc, c0, c1, g, dofs, u, dir, ebuf, vbuf);
   else
-    k_lb_fast<NB, NQ, false><<<nb, 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, g.chart, g.radius, dofs, u, dir, ebuf, vbuf);
+    k_lb_fast<NB, NQ, false><<<nb, 128, pad, ctx->stream>>>(nc, c0, c1, g, dofs, u, dir, ebuf, vbuf);
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
 }
+
+// When set, the CSR fill is pipelined behind the element kernel: the cells are cut into gg_csr::N_BATCH batches; as soon
+// as batch b has been computed (event on the main stream) the chunks it completes are gathered on the second stream
+// while the FP64-bound element kernel proceeds with batch b+1 (the two kernels use complementary resources).
+struct FillPipe {
+  gg_csr* A;
+  double scale;
+  int add;
+};
 
 // fast-path availability: scalar Q1/Q2, test == trial numbering family, the quadrature sizes the reference uses
 static bool fast_lb_available(int order, int nq) {
@@ -349,30 +405,65 @@ static bool fast_lb_available(int order, int nq) {
   return false;
 }
 
-static void run_lb_fast(gg_ctx* ctx, const Geo& g, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u,
-                        double dir, double* ebuf, double* vbuf) {
-  load_const_tables(ctx, order, nq);
+static void run_lb_fast_range(gg_mesh* m, int order, int nq, bool extrinsic, int64_t c0, int64_t c1, const CellGeo& g,
+                              const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf,
+                              bool leave_room = false) {
+  gg_ctx* ctx = m->ctx;
+  int64_t nc = m->n_cells;
 #define GG_CASE(NB_, NQ_) \
-  if (order + 1 == NB_ && nq == NQ_) { launch_lb_fast<NB_, NQ_>(ctx, g, extrinsic, dofs, u, dir, ebuf, vbuf); return; }
+  if (order + 1 == NB_ && nq == NQ_) { launch_lb_fast<NB_, NQ_>(ctx, nc, c0, c1, g, extrinsic, dofs, u, dir, ebuf, vbuf, leave_room); return; }
   GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
   GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
 #undef GG_CASE
   throw Error(GG_ERR_UNSUPPORTED, "no fast Laplace-Beltrami kernel for this (order, degree)");
 }
 
+static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u,
+                        double dir, double* ebuf, double* vbuf, const FillPipe* pipe) {
+  gg_ctx* ctx = m->ctx;
+  load_const_tables(ctx, order, nq);
+  CellGeo g = cell_geo(m, nq);
+  int64_t nc = m->n_cells;
+  const int NBt = gg_csr::N_BATCH;
+  // Measured on B200 (round 1, 393 216 cells): 0.287 ms sequential vs 0.306-0.348 ms pipelined -- the co-resident fill CTAs
+  // slow the FP64-bound element kernel more than the overlap gains and the 8 batches add partial waves, so the pipeline
+  // stays off unless GG_PIPELINE=1 is exported (kept for the next round's wave-aligned batching experiment).
+  static const bool want_pipeline = getenv("GG_PIPELINE") && getenv("GG_PIPELINE")[0] == '1';
+  if (!pipe || !want_pipeline || nc < 64 * 1024 || ctx->profile) {
+    // default, small meshes (launch-bound) and per-kernel profiling runs: one element launch, one fill launch
+    run_lb_fast_range(m, order, nq, extrinsic, 0, nc, g, dofs, u, dir, ebuf, vbuf);
+    if (pipe) gather_matrix(pipe->A, 1, ebuf, pipe->scale, pipe->add);
+    return;
+  }
+  prepare_gather(pipe->A, 1);
+  for (int b = 0; b < NBt; ++b) {
+    // batch boundaries rounded to whole CTAs; batch b owns cells with (cell * NBt) / nc == b
+    int64_t c0 = (b * nc + NBt - 1) / NBt, c1 = ((b + 1) * nc + NBt - 1) / NBt;
+    run_lb_fast_range(m, order, nq, extrinsic, c0, c1, g, dofs, u, dir, ebuf, vbuf, true);
+    GG_CUDA(cudaEventRecord(ctx->ev_batch[b], ctx->stream));
+    GG_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_batch[b], 0));
+    gather_matrix_batch(pipe->A, b, ebuf, pipe->scale, pipe->add, ctx->stream2);
+  }
+  GG_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  GG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+}
+
 template <int NB, int NQ>
-static void launch_action_fast(gg_ctx* ctx, const Geo& g, const int32_t* dofs, const double* u, double dir, double* vbuf) {
+static void launch_action_fast(gg_ctx* ctx, int64_t nc, const CellGeo& g, const int32_t* dofs, const double* u, double dir,
+                               double* vbuf) {
   ProfScope ps(ctx, "k_lb_action_fast");
-  k_lb_action_fast<NB, NQ><<<nblk(g.nc, 128), 128, 0, ctx->stream>>>(g.nc, g.x0, g.y0, g.hx, g.hy, dofs, u, dir, vbuf);
+  k_lb_action_fast<NB, NQ><<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, g, dofs, u, dir, vbuf);
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
 }
 
-static void run_action_fast(gg_ctx* ctx, const Geo& g, int order, int nq, const int32_t* dofs, const double* u, double dir,
-                            double* vbuf) {
+static void run_action_fast(gg_mesh* m, int order, int nq, const int32_t* dofs, const double* u, double dir, double* vbuf) {
+  gg_ctx* ctx = m->ctx;
   load_const_tables(ctx, order, nq);
+  CellGeo g = cell_geo(m, nq);
+  int64_t nc = m->n_cells;
 #define GG_CASE(NB_, NQ_) \
-  if (order + 1 == NB_ && nq == NQ_) { launch_action_fast<NB_, NQ_>(ctx, g, dofs, u, dir, vbuf); return; }
+  if (order + 1 == NB_ && nq == NQ_) { launch_action_fast<NB_, NQ_>(ctx, nc, g, dofs, u, dir, vbuf); return; }
   GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
   GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
 #undef GG_CASE
@@ -424,7 +515,8 @@ static void form_coefficients(gg_form form, double* cM, double* cK, bool* extrin
 }
 
 // element matrices into ctx->ebuf; returns the buffer layout (0 full entry-major, 1 symmetric packed entry-major)
-static int compute_element_matrices(gg_form form, const gg_form_args* a, const Plan& P, bool want_fused_vector, double** vbuf_out) {
+static int compute_element_matrices(gg_form form, const gg_form_args* a, const Plan& P, bool want_fused_vector, double** vbuf_out,
+                                    const FillPipe* pipe = nullptr) {
   gg_ctx* ctx = P.ctx;
   Geo g = geo_of(P.mesh);
   cudaStream_t st = ctx->stream;
@@ -447,8 +539,8 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
         vb = scratch(ctx->vbuf, (size_t)P.mt * nc);
         *vbuf_out = vb;
       }
-      run_lb_fast(ctx, g, P.test->order, P.nq, ext, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb);
-      return 1;
+      run_lb_fast(P.mesh, P.test->order, P.nq, ext, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb, pipe);
+      return pipe ? -1 : 1;  // -1: the CSR fill has already been enqueued
     }
     GG_REQUIRE(!want_fused_vector, GG_ERR_UNSUPPORTED, "fused matrix+vector assembly needs the fast Q1/Q2 stiffness kernel");
     if (a->qdata) GG_REQUIRE(gg_vec_size(a->qdata) == nc * P.nq * P.nq, GG_ERR_INVALID, "qdata has the wrong length");
@@ -524,7 +616,7 @@ static double* compute_element_vectors(gg_form form, const gg_form_args* a, cons
   double cM, cK; bool ext;
   form_coefficients(form, &cM, &cK, &ext);
   if (form == GG_FORM_LAPLACE_BELTRAMI && P.test->order == P.trial->order && fast_lb_available(P.test->order, P.nq)) {
-    run_action_fast(ctx, g, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, vb);
+    run_action_fast(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, vb);
     return vb;
   }
   auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
@@ -560,8 +652,9 @@ int gg_assemble_matrix(gg_form form, const gg_form_args* args, gg_csr* A, int ad
   GG_REQUIRE(A, GG_ERR_INVALID, "null matrix");
   Plan P = make_plan(form, args, true);
   GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
-  int layout = compute_element_matrices(form, args, P, false, nullptr);
-  gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, add);
+  FillPipe pipe{A, P.scale, add};
+  int layout = compute_element_matrices(form, args, P, false, nullptr, &pipe);
+  if (layout >= 0) gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, add);
   finish_call(P.ctx);
   GG_API_END
 }
@@ -584,8 +677,9 @@ int gg_assemble_matrix_and_vector(gg_form form, const gg_form_args* args, gg_csr
   GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
   GG_REQUIRE(gg_vec_size(b) == P.test->n_free, GG_ERR_INVALID, "output vector has the wrong length");
   double* vb = nullptr;
-  int layout = compute_element_matrices(form, args, P, true, &vb);
-  gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, 0);
+  FillPipe pipe{A, P.scale, 0};
+  int layout = compute_element_matrices(form, args, P, true, &vb, &pipe);
+  if (layout >= 0) gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, 0);
   gather_vector(P.test, vb, b->d.p, P.scale, 0);
   finish_call(P.ctx);
   GG_API_END

@@ -5,12 +5,15 @@
 // src/CellData/CellFields.jl:80-82):
 //     Ke[I,J] += w_q |det grad(cell_map)| grad(phi_I) . (ginv(x_q) grad(phi_J)) sqrtg(x_q)
 // B200 design: ONE THREAD PER CELL, everything in FP64 registers, no shared memory, no synchronisation.
-//   * geometry: ginv*sqrtg = (1/rho) [[sb, ab],[ab, sa]] (the radius cancels in 2-D); tan() is evaluated on the
-//     2*NQ one-dimensional abscissae of the cell instead of the NQ^2 points (tensor grid of an axis-aligned cell);
+//   * geometry: ginv*sqrtg = (1/rho) [[sb, ab],[ab, sa]] (the radius cancels in 2-D).  tan() is not evaluated in the
+//     kernel at all: an axis-aligned cell only needs the tangents of its 2*NQ one-dimensional abscissae, and cells
+//     of one mesh column/row share them, so they are tabulated once per (mesh, rule) for the distinct chart
+//     intervals (k_tan_table) and read back through L1 (a few KB for a structured panel);
+//   * 1/rho: MUFU.RSQ64H seed + one cubically convergent FP64 step, no range branches (rho^2 is in [1,3]);
 //   * sum factorisation: first contract the y-direction into T11/T12/T22 (NQ*(2*NS+NB^2) FMAs per x-abscissa), then
 //     the x-direction into the packed symmetric element matrix (4 FMAs per unique entry and abscissa);
-//   * all table operands are __constant__ with compile-time offsets (FMA constant-bank operands) for the unrolled
-//     y loop and warp-uniform LDC loads for the rolled x loop, so the instruction stream is almost pure DFMA;
+//   * table operands sit in a compact __constant__ block laid out in use order ([abscissa][NN.. DD.. ND..], 1.7 KB for
+//     Q2/degree 18, so it stays in the constant cache and adjacent operands can be fetched by one 128-bit uniform load);
 //   * the symmetric half (M(M+1)/2 entries) is written entry-major [pair][cell]: consecutive threads write
 //     consecutive addresses (fully coalesced FP64 stores); the atomic-free CSR fill is k_gather_chunks (gg_pattern.cu).
 // The fused residual r_e = Ke u_e is formed from the registers that already hold Ke (LB is linear).
@@ -20,8 +23,10 @@
 
 namespace gg {
 
-// 1-D tables of the resident (order, nq) pair; rewritten (stream-ordered) when the pair changes
+// generic 1-D tables of the resident (order, nq) pair (used by the action kernel); rewritten when the pair changes
 __constant__ ScalarTables c_tab;
+// compact pair tables of the resident (order, nq) pair: row q = [NN sym (NS) | DD sym (NS) | ND (NB*NB)], weights folded
+__constant__ double c_lb[MAX_NQ * (MAX_NB * (MAX_NB + 1) + MAX_NB * MAX_NB)];
 // packed-pair -> plane index of the symmetric entry-major buffer, and lexicographic -> Gridap local dof
 __constant__ int32_t c_plane[(MAX_NB * MAX_NB) * (MAX_NB * MAX_NB + 1) / 2];
 __constant__ int32_t c_lex2loc[MAX_NB * MAX_NB];
@@ -31,27 +36,56 @@ __host__ __device__ constexpr int sym_index(int i, int j) {  // i <= j
   return i * NB - (i * (i - 1)) / 2 + (j - i);
 }
 
+// 1/sqrt(x) for x in a benign range: hardware seed (rel. error ~2^-22) + one cubic Newton step -> < 1 ulp
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x, -(y * y), 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  return fma(p, y * e, y);
+}
+
+// tangents of the 1-D abscissae of every distinct chart interval: out[i*nq + q] = tan(lo[i] + h[i] * xi[q])
+__global__ void k_tan_table(int64_t n_int, int nq, const double* __restrict__ lo, const double* __restrict__ h,
+                            const double* __restrict__ xi, double* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_int * nq) return;
+  int64_t i = t / nq;
+  int q = (int)(t - i * nq);
+  out[t] = tan(fma(h[i], xi[q], lo[i]));
+}
+
+struct CellGeo {
+  const double *hx, *hy;      // cell extents in the chart
+  const int32_t *ix, *iy;     // interval ids of the cell in x and y
+  const double *tx, *ty;      // tangent tables [interval][NQ]
+  const int32_t* chart;       // 0-based panel (extrinsic form only)
+  double radius;
+};
+
 // EXTRINSIC: geometry from the 2x3 Jacobian of ambient o chart (pseudo-determinant path) instead of the analytic metric
 template <int NB, int NQ, bool EXTRINSIC>
-__global__ void __launch_bounds__(128)
-k_lb_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ y0, const double* __restrict__ hx,
-          const double* __restrict__ hy, const int32_t* __restrict__ chart, double radius,
-          const int32_t* __restrict__ cell_dofs, const double* __restrict__ u, double dirichlet,
-          double* __restrict__ ebuf, double* __restrict__ vbuf) {
+__global__ void __launch_bounds__(128, 3)
+k_lb_fast(int64_t nc, int64_t c0, int64_t c1, CellGeo g, const int32_t* __restrict__ cell_dofs,
+          const double* __restrict__ u, double dirichlet, double* __restrict__ ebuf, double* __restrict__ vbuf) {
   constexpr int M = NB * NB, NS = NB * (NB + 1) / 2, NP = M * (M + 1) / 2;
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  const double X0 = x0[c], Y0 = y0[c], HX = hx[c], HY = hy[c];
+  constexpr int ROW = 2 * NS + M;  // doubles per abscissa in c_lb
+  constexpr int ONN = 0, ODD = NS, OND = 2 * NS;
+  // cells [c0, c1) of the nc cells of the mesh (the numeric phase is pipelined over cell batches)
+  int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c1) return;
+  const double HX = g.hx[c], HY = g.hy[c];
   const double rx = HY / HX, ry = HX / HY;
+  const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * NQ;
+  const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * NQ;
   int panel = 0;
-  if (EXTRINSIC) panel = chart[c];
+  if (EXTRINSIC) panel = g.chart[c];
 
   double b[NQ], sb[NQ];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    double t = tan(fma(HY, c_tab.xi[j], Y0));
-    b[j] = t;
-    sb[j] = fma(t, t, 1.0);
+    b[j] = tb[j];
+    sb[j] = fma(b[j], b[j], 1.0);
   }
   double acc[NP];
 #pragma unroll
@@ -59,7 +93,7 @@ k_lb_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ 
 
 #pragma unroll 1
   for (int q1 = 0; q1 < NQ; ++q1) {
-    const double a = tan(fma(HX, c_tab.xi[q1], X0));
+    const double a = ta[q1];
     const double sa = fma(a, a, 1.0);
     double T11[NS], T22[NS], T12[M];
 #pragma unroll
@@ -70,37 +104,26 @@ k_lb_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ 
     for (int q2 = 0; q2 < NQ; ++q2) {
       double G11, G12, G22;
       if (!EXTRINSIC) {
-        const double rinv = rsqrt(fma(b[q2], b[q2], sa));
+        const double rinv = fast_rsqrt(fma(b[q2], b[q2], sa));
+        const double ar = a * rinv;
         G11 = sb[q2] * rinv;
-        G12 = a * b[q2] * rinv;
+        G12 = ar * b[q2];
         G22 = sa * rinv;
       } else {
         // chart-space factors of the reference-to-ambient Jacobian are applied through rx/ry below
-        Metric2 m = extrinsic_metric_terms(panel, a, b[q2], radius);
+        Metric2 m = extrinsic_metric_terms(panel, a, b[q2], g.radius);
         G11 = m.i11 * m.sqrtg; G12 = m.i12 * m.sqrtg; G22 = m.i22 * m.sqrtg;
       }
 #pragma unroll
-      for (int i2 = 0; i2 < NB; ++i2)
+      for (int k = 0; k < NS; ++k) T11[k] = fma(G11, c_lb[q2 * ROW + ONN + k], T11[k]);
 #pragma unroll
-        for (int j2 = i2; j2 < NB; ++j2) {
-          T11[sym_index<NB>(i2, j2)] = fma(G11, c_tab.NN[i2 * NB + j2][q2], T11[sym_index<NB>(i2, j2)]);
-          T22[sym_index<NB>(i2, j2)] = fma(G22, c_tab.DD[i2 * NB + j2][q2], T22[sym_index<NB>(i2, j2)]);
-        }
+      for (int k = 0; k < NS; ++k) T22[k] = fma(G22, c_lb[q2 * ROW + ODD + k], T22[k]);
 #pragma unroll
-      for (int k = 0; k < M; ++k) T12[k] = fma(G12, c_tab.ND[k][q2], T12[k]);
+      for (int k = 0; k < M; ++k) T12[k] = fma(G12, c_lb[q2 * ROW + OND + k], T12[k]);
     }
 #pragma unroll
     for (int k = 0; k < NS; ++k) { T11[k] *= rx; T22[k] *= ry; }
-    double dd[NS], nn[NS], nd[M];
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-#pragma unroll
-      for (int j = i; j < NB; ++j) {
-        dd[sym_index<NB>(i, j)] = c_tab.DD[i * NB + j][q1];
-        nn[sym_index<NB>(i, j)] = c_tab.NN[i * NB + j][q1];
-      }
-#pragma unroll
-    for (int k = 0; k < M; ++k) nd[k] = c_tab.ND[k][q1];
+    const double* __restrict__ row = c_lb + q1 * ROW;  // warp-uniform
     // second contraction into the packed upper triangle, I = i1 + NB*i2 <= J = j1 + NB*j2
     int p = 0;
 #pragma unroll
@@ -115,10 +138,10 @@ k_lb_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ 
             const int s1 = i1 <= j1 ? sym_index<NB>(i1, j1) : sym_index<NB>(j1, i1);
             const int s2 = sym_index<NB>(i2, j2);
             double v = acc[p];
-            v = fma(dd[s1], T11[s2], v);
-            v = fma(nd[j1 * NB + i1], T12[i2 * NB + j2], v);
-            v = fma(nd[i1 * NB + j1], T12[j2 * NB + i2], v);
-            v = fma(nn[s1], T22[s2], v);
+            v = fma(row[ODD + s1], T11[s2], v);
+            v = fma(row[OND + j1 * NB + i1], T12[i2 * NB + j2], v);
+            v = fma(row[OND + i1 * NB + j1], T12[j2 * NB + i2], v);
+            v = fma(row[ONN + s1], T22[s2], v);
             acc[p] = v;
             ++p;
           }
@@ -154,14 +177,15 @@ k_lb_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ 
 // Matrix-free action r_e = a(u_h, phi_I) by sum factorisation, never forming Ke (3 contractions per abscissa)
 template <int NB, int NQ>
 __global__ void __launch_bounds__(128)
-k_lb_action_fast(int64_t nc, const double* __restrict__ x0, const double* __restrict__ y0, const double* __restrict__ hx,
-                 const double* __restrict__ hy, const int32_t* __restrict__ cell_dofs, const double* __restrict__ u,
+k_lb_action_fast(int64_t nc, CellGeo g, const int32_t* __restrict__ cell_dofs, const double* __restrict__ u,
                  double dirichlet, double* __restrict__ vbuf) {
   constexpr int M = NB * NB;
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
-  const double X0 = x0[c], Y0 = y0[c], HX = hx[c], HY = hy[c];
+  const double HX = g.hx[c], HY = g.hy[c];
   const double rx = HY / HX, ry = HX / HY;
+  const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * NQ;
+  const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * NQ;
   double ue[M], re[M];
 #pragma unroll
   for (int I = 0; I < M; ++I) {
@@ -172,13 +196,12 @@ k_lb_action_fast(int64_t nc, const double* __restrict__ x0, const double* __rest
   double b[NQ], sb[NQ];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    double t = tan(fma(HY, c_tab.xi[j], Y0));
-    b[j] = t;
-    sb[j] = fma(t, t, 1.0);
+    b[j] = tb[j];
+    sb[j] = fma(b[j], b[j], 1.0);
   }
 #pragma unroll 1
   for (int q1 = 0; q1 < NQ; ++q1) {
-    const double a = tan(fma(HX, c_tab.xi[q1], X0));
+    const double a = ta[q1];
     const double sa = fma(a, a, 1.0);
     const double w1 = c_tab.w[q1];
     double n1[NB], d1[NB];
@@ -196,7 +219,7 @@ k_lb_action_fast(int64_t nc, const double* __restrict__ x0, const double* __rest
     }
 #pragma unroll
     for (int q2 = 0; q2 < NQ; ++q2) {
-      const double rinv = rsqrt(fma(b[q2], b[q2], sa));
+      const double rinv = fast_rsqrt(fma(b[q2], b[q2], sa));
       const double ww = w1 * c_tab.w[q2] * rinv;
       const double G11 = sb[q2] * ww * rx, G12 = a * b[q2] * ww, G22 = sa * ww * ry;
       double ux = 0.0, uy = 0.0;

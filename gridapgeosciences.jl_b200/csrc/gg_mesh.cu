@@ -121,6 +121,29 @@ static void upload_geometry(gg_mesh* m) {
   cudaStream_t s = m->ctx->stream;
   m->d_x0.upload(x0, s); m->d_y0.upload(y0, s); m->d_hx.upload(hx, s); m->d_hy.upload(hy, s);
   m->d_chart.upload(m->cell_to_chart, s);
+  // distinct (lo, h) intervals per direction (bitwise comparison: cells of one column are produced by the same
+  // expression; a caller-supplied mesh with last-bit differences just gets more intervals)
+  auto intervals = [&](const std::vector<double>& lo, const std::vector<double>& h, std::vector<int32_t>& id,
+                       std::vector<double>& ulo, std::vector<double>& uh) {
+    std::vector<int64_t> order(nc);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return lo[a] != lo[b] ? lo[a] < lo[b] : h[a] < h[b]; });
+    id.resize(nc);
+    ulo.clear(); uh.clear();
+    for (int64_t k = 0; k < nc; ++k) {
+      int64_t c = order[k];
+      if (k == 0 || lo[c] != ulo.back() || h[c] != uh.back()) { ulo.push_back(lo[c]); uh.push_back(h[c]); }
+      id[c] = (int32_t)ulo.size() - 1;
+    }
+  };
+  std::vector<int32_t> ix, iy;
+  std::vector<double> xlo, xh, ylo, yh;
+  intervals(x0, hx, ix, xlo, xh);
+  intervals(y0, hy, iy, ylo, yh);
+  m->n_xint = (int64_t)xlo.size(); m->n_yint = (int64_t)ylo.size();
+  m->d_ix.upload(ix, s); m->d_iy.upload(iy, s);
+  m->d_xlo.upload(xlo, s); m->d_xh.upload(xh, s); m->d_ylo.upload(ylo, s); m->d_yh.upload(yh, s);
+  m->tan_tabs.clear();
   GG_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -208,20 +208,50 @@ __global__ void k_max_sources(int64_t nnz, const int32_t* __restrict__ sptr, int
   if (s < nnz) atomicMax(out, sptr[s + 1] - sptr[s]);
 }
 
+// last cell (completion batch) any source of the chunk comes from; buffer index = plane * nc + cell
 __global__ void __launch_bounds__(256)
-k_gather_chunks(int64_t nnz, int R, const int32_t* __restrict__ roundptr, const int32_t* __restrict__ lsrc,
-                const uint16_t* __restrict__ lslot, const double* __restrict__ ebuf, double* __restrict__ vals,
-                double scale, int add) {
-  __shared__ double acc[GATHER_CHUNK];
+k_chunk_batch(int64_t nc, int R, int n_batch, const int32_t* __restrict__ roundptr, const int32_t* __restrict__ lsrc,
+              int32_t* __restrict__ chunk_batch) {
+  __shared__ int smax[8];
   const int64_t chunk = blockIdx.x;
+  const int32_t b = roundptr[chunk * (R + 1)], e = roundptr[chunk * (R + 1) + R];
+  int mx = 0;
+  for (int32_t k = b + threadIdx.x; k < e; k += blockDim.x) mx = max(mx, (int)(lsrc[k] % nc));
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = max(mx, smax[w]);
+    chunk_batch[chunk] = (int32_t)(((int64_t)mx * n_batch) / nc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_chunks(int64_t nnz, int R, const int32_t* __restrict__ chunk_order, const int32_t* __restrict__ roundptr,
+                const int32_t* __restrict__ lsrc, const uint16_t* __restrict__ lslot, const double* __restrict__ ebuf,
+                double* __restrict__ vals, double scale, int add) {
+  __shared__ double acc[GATHER_CHUNK];
+  const int64_t chunk = chunk_order[blockIdx.x];
   const int32_t* rp = roundptr + chunk * (R + 1);
   for (int r = 0; r < R; ++r) {
     const int32_t b = rp[r], e = rp[r + 1];
-    if (r == 0) {
-      for (int32_t k = b + threadIdx.x; k < e; k += blockDim.x) acc[lslot[k]] = ebuf[lsrc[k]];
-    } else {
-      if (b == e) break;  // uniform: rounds are nested (a slot has round r only if it has round r-1)
-      for (int32_t k = b + threadIdx.x; k < e; k += blockDim.x) acc[lslot[k]] += ebuf[lsrc[k]];
+    if (r > 0 && b == e) break;  // uniform: rounds are nested (a slot has round r only if it has round r-1)
+    // 4 independent index -> value load chains per thread in flight
+    for (int32_t k0 = b + threadIdx.x; k0 < e; k0 += 4 * blockDim.x) {
+      int32_t src[4];
+      uint16_t ls[4];
+      double v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int32_t k = k0 + j * blockDim.x;
+        src[j] = k < e ? lsrc[k] : -1;
+        ls[j] = k < e ? lslot[k] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = src[j] >= 0 ? ebuf[src[j]] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (src[j] >= 0) acc[ls[j]] = r == 0 ? v[j] : acc[ls[j]] + v[j];
     }
     __syncthreads();
   }
@@ -274,7 +304,28 @@ static void build_chunk_lists(gg_csr* A, int layout) {
   GG_CUDA(cudaStreamSynchronize(st));
   A->n_rounds = R;
   A->n_chunks = nchunks;
+  // order the chunks by the cell batch that completes them
+  {
+    const int NBt = gg_csr::N_BATCH;
+    DevBuf<int32_t> d_cb(nchunks);
+    k_chunk_batch<<<(unsigned)nchunks, 256, 0, st>>>(A->test->mesh->n_cells, R, NBt, A->d_roundptr.p, A->d_lsrc.p, d_cb.p);
+    ctx->launches++;
+    std::vector<int32_t> cb(nchunks), order(nchunks);
+    d_cb.download(cb.data(), st);
+    std::vector<int64_t> cnt(NBt + 1, 0);
+    for (int64_t i = 0; i < nchunks; ++i) cnt[cb[i] + 1]++;
+    for (int b2 = 0; b2 < NBt; ++b2) cnt[b2 + 1] += cnt[b2];
+    for (int b2 = 0; b2 <= NBt; ++b2) A->batch_chunk_ptr[b2] = cnt[b2];
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int64_t i = 0; i < nchunks; ++i) order[pos[cb[i]]++] = (int32_t)i;
+    A->d_chunk_order.upload(order, st);
+    GG_CUDA(cudaStreamSynchronize(st));
+  }
   A->cached_layout = layout;
+}
+
+void prepare_gather(gg_csr* A, int layout) {
+  if (A->nnz) build_chunk_lists(A, layout);
 }
 
 void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int add) {
@@ -282,8 +333,18 @@ void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int 
   if (A->nnz == 0) return;
   build_chunk_lists(A, layout);
   ProfScope ps(ctx, "k_gather_chunks");
-  k_gather_chunks<<<(unsigned)A->n_chunks, 256, 0, ctx->stream>>>(A->nnz, A->n_rounds, A->d_roundptr.p, A->d_lsrc.p,
-                                                                  A->d_lslot.p, ebuf, A->d_vals.p, scale, add);
+  k_gather_chunks<<<(unsigned)A->n_chunks, 256, 0, ctx->stream>>>(A->nnz, A->n_rounds, A->d_chunk_order.p, A->d_roundptr.p,
+                                                                  A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+void gather_matrix_batch(gg_csr* A, int batch, const double* ebuf, double scale, int add, cudaStream_t st) {
+  gg_ctx* ctx = A->ctx;
+  int64_t c0 = A->batch_chunk_ptr[batch], c1 = A->batch_chunk_ptr[batch + 1];
+  if (c1 == c0) return;
+  k_gather_chunks<<<(unsigned)(c1 - c0), 256, 0, st>>>(A->nnz, A->n_rounds, A->d_chunk_order.p + c0, A->d_roundptr.p,
+                                                       A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add);
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
 }
