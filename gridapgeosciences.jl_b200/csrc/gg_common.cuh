@@ -171,6 +171,10 @@ struct gg_space {
   gg::DevBuf<int8_t> d_cell_signs;
   // local dof -> tensor multi-index (Lagrangian): lex index ix + (order+1)*iy
   std::vector<int32_t> loc2lex;
+  // groups of consecutively numbered free DOFs owned by one mesh entity: (first dof, number of groups, dofs per group);
+  // empty for caller-numbered spaces (the preconditioner then degenerates to point Jacobi)
+  struct BlockClass { int64_t start, count; int size; };
+  std::vector<BlockClass> blocks;
   // DOF -> contributing (cell, local) lists for atomic-free vector assembly
   gg::DevBuf<int32_t> d_vptr;  // [n_free+1]
   gg::DevBuf<int32_t> d_vsrc;  // [n_entries] = local*n_cells + cell (entry-major element-vector buffer index)
@@ -213,7 +217,17 @@ struct gg_solver {
   gg_csr* A = nullptr;
   double rtol = 1e-12;
   int max_iter = 1000;
-  gg::DevBuf<double> dinv, r, z, p, Ap, partials;
+  // block-Jacobi preconditioner: the DOFs owned by one mesh entity (facet / edge / cell interior) form a block;
+  // per row: first row of its block, block size, offset of the row's slice of the block inverse
+  gg::DevBuf<int32_t> bstart, rowoff;
+  gg::DevBuf<uint8_t> bsize;
+  gg::DevBuf<double> binv;
+  int64_t n_blocks = 0;
+  std::vector<int32_t> h_blk_start;  // per block: first row
+  std::vector<uint8_t> h_blk_size;
+  gg::DevBuf<int32_t> d_blk_start, d_blk_off;
+  gg::DevBuf<uint8_t> d_blk_size;
+  gg::DevBuf<double> r, r2, z, p, Ap, partials;
   gg::DevBuf<double> stats;  // [0] iterations of the last solve, [1] its relative residual
   int grid = 0, block = 256;
 };

@@ -356,6 +356,11 @@ int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space**
       GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_INVALID, "unknown constraint");
       s->n_free = nd;
     }
+    s->blocks.push_back({0, m->n_nodes, 1});
+    if (order > 1) {
+      s->blocks.push_back({m->n_nodes, m->n_edges, order - 1});
+      s->blocks.push_back({m->n_nodes + m->n_edges * (order - 1), nc, (order - 1) * (order - 1)});
+    }
   } else if (kind == GG_SPACE_DG) {
     GG_REQUIRE(order >= 0 && order <= 4, GG_ERR_UNSUPPORTED, "DG order must be in 0..4");
     GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on DG spaces are not implemented");
@@ -365,6 +370,7 @@ int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space**
     GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
     s->cell_dofs.resize(nc * mloc);
     std::iota(s->cell_dofs.begin(), s->cell_dofs.end(), 0);
+    s->blocks.push_back({0, nc, mloc});
   } else if (kind == GG_SPACE_RT) {
     GG_REQUIRE(order >= 0 && order <= 3, GG_ERR_UNSUPPORTED, "RT order must be in 0..3");
     GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on RT spaces are not implemented");
@@ -376,6 +382,8 @@ int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space**
     GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
     s->cell_dofs.resize(nc * mloc);
     s->cell_signs.assign(nc * mloc, 1);
+    s->blocks.push_back({0, m->n_edges, nf});
+    if (ni > 0) s->blocks.push_back({m->n_edges * nf, nc, ni});
     for (int64_t c = 0; c < nc; ++c) {
       int k = 0;
       for (int e = 0; e < 4; ++e) {
