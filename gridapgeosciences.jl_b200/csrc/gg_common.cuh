@@ -233,6 +233,23 @@ struct gg_solver {
 };
 
 namespace gg {
+// device tabulation of a reference basis at the tensor quadrature points, cached per (kind, order, nq) on the context
+struct FormTab {
+  int kind, order, nq, Q, m;
+  DevBuf<double> xi, w;  // 1-D rule on [0,1]
+  DevBuf<double> val;    // scalar: [Q][m]      RT: [Q][m][2]
+  DevBuf<double> der;    // scalar: [Q][m][2]   RT: [Q][m] (divergence)
+};
+std::shared_ptr<FormTab> get_tab(gg_ctx* ctx, int kind, int order, int nq);
+// per-cell geometry handles for kernels that read the tangents of the 1-D abscissae from the per-(mesh, nq) tables
+struct CellGeo {
+  const double *hx, *hy;      // cell extents in the chart
+  const int32_t *ix, *iy;     // interval ids of the cell in x and y
+  const double *tx, *ty;      // tangent tables [interval][NQ]
+  const int32_t* chart;       // 0-based panel
+  double radius;
+};
+CellGeo cell_geo(gg_mesh* m, int nq);
 // internal entry points shared between translation units
 void build_vec_map(gg_space* s);
 void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);

@@ -23,14 +23,7 @@ void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, i
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // ---- device tabulations ---------------------------------------------------------------------------------
-struct FormTab {
-  int kind, order, nq, Q, m;
-  DevBuf<double> xi, w;  // 1-D rule on [0,1]
-  DevBuf<double> val;    // scalar: [Q][m]      RT: [Q][m][2]
-  DevBuf<double> der;    // scalar: [Q][m][2]   RT: [Q][m] (divergence)
-};
-
-static std::shared_ptr<FormTab> get_tab(gg_ctx* ctx, int kind, int order, int nq) {
+std::shared_ptr<FormTab> get_tab(gg_ctx* ctx, int kind, int order, int nq) {
   int k = kind == GG_SPACE_RT ? 1 : 0;
   uint64_t key = ((uint64_t)k << 32) | ((uint64_t)order << 16) | (uint64_t)nq;
   auto it = ctx->tabs.find(key);
@@ -345,7 +338,7 @@ static void load_const_tables(gg_ctx* ctx, int order, int nq) {
 }
 
 // per-(mesh, nq) tangent tables of the distinct chart intervals, built on the device at first use
-static CellGeo cell_geo(gg_mesh* m, int nq) {
+CellGeo cell_geo(gg_mesh* m, int nq) {
   gg_ctx* ctx = m->ctx;
   auto it = m->tan_tabs.find(nq);
   if (it == m->tan_tabs.end()) {

@@ -55,14 +55,6 @@ __global__ void k_tan_table(int64_t n_int, int nq, const double* __restrict__ lo
   out[t] = tan(fma(h[i], xi[q], lo[i]));
 }
 
-struct CellGeo {
-  const double *hx, *hy;      // cell extents in the chart
-  const int32_t *ix, *iy;     // interval ids of the cell in x and y
-  const double *tx, *ty;      // tangent tables [interval][NQ]
-  const int32_t* chart;       // 0-based panel (extrinsic form only)
-  double radius;
-};
-
 // EXTRINSIC: geometry from the 2x3 Jacobian of ambient o chart (pseudo-determinant path) instead of the analytic metric
 template <int NB, int NQ, bool EXTRINSIC>
 __global__ void __launch_bounds__(128, 3)
