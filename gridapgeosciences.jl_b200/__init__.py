@@ -535,6 +535,41 @@ class AffineFEOperator:
         return self.b
 
 
+# ---- interpolation / norms ---------------------------------------------------------------------------------
+
+def interpolation_points(V, chart=False, ambient=True):
+    """Points at which `interpolate` samples its function: (n_cells, n_pts, 2|3) chart / ambient coordinates."""
+    n = C.c_int32()
+    _lib.check(V.lib.gg_space_interp_points(V.h, C.byref(n), None, None))
+    nc = V.model.num_cells
+    ch = np.empty((nc, n.value, 2)) if chart else None
+    xyz = np.empty((nc, n.value, 3)) if ambient else None
+    _lib.check(V.lib.gg_space_interp_points(V.h, C.byref(n), _dp(ch) if chart else None, _dp(xyz) if ambient else None))
+    return ch, xyz
+
+
+def interpolate(fun, V, out=None):
+    """interpolate(fun∘ambient_map_cf, V).  Lagrangian V: `fun(xyz)` is scalar.  Raviart-Thomas V: `fun(xyz)` is an
+    ambient 3-vector field and the interpolated chart field is meas_cf*((pinvJ∘transpose∘∇(ambient_map_cf))⋅fun)
+    (test/Transient/TransientShallowWater.jl:88-95)."""
+    _, xyz = interpolation_points(V)
+    vals = np.asarray(fun(xyz), dtype=np.float64)
+    shape = xyz.shape if V.kind == _lib.SPACE_RT else xyz.shape[:2]
+    vals = np.ascontiguousarray(np.broadcast_to(vals, shape))
+    out = out if out is not None else DeviceVector(V.model.ctx, V.num_free_dofs)
+    _lib.check(V.lib.gg_space_interpolate(V.h, _dp(vals), out.h))
+    return out
+
+
+def norm(e, V, degree):
+    """sqrt(sum(∫(e*e*meas_cf)dΩ)) for Lagrangian V, sqrt(sum(∫(e⋅(metric_cf⋅e)*(1/meas_cf))dΩ)) for RT V."""
+    if not isinstance(e, DeviceVector):
+        e = DeviceVector.from_numpy(V.model.ctx, e)
+    out = C.c_double()
+    _lib.check(V.lib.gg_norm_sq(V.h, e.h, int(degree), C.byref(out)))
+    return math.sqrt(max(out.value, 0.0))
+
+
 # ---- linear solver ------------------------------------------------------------------------------------------
 
 class CGSolver:
@@ -600,7 +635,27 @@ class WaveOperator:
         self.degree = 5 * (p_fe + 1) if degree is None else degree
 
 
-class WaveStepper:
+class ShallowWaterOperator:
+    """DAEFEOperator(opT, opFE, ls_diag) for the rotating shallow-water forms of
+    test/Transient/TransientShallowWater.jl:113-145: prognostic (u, p) in RT_p x DG_p, diagnostic (q, F, Φ) in
+    CG_{p+1} x RT_p x DG_p.  `f` (Coriolis) and `b` (topography) are functions of the ambient coordinates
+    (`cor_cf = f∘ambient_map_cf`); `q0_mode` is "alias" (what the reference's stepper does) or
+    "start_of_step"."""
+
+    def __init__(self, model, p_fe, f, b=None, gravity=1.0, degree=None, q0_mode="alias", tau=None):
+        self.model, self.p_fe = model, p_fe
+        self.degree = 4 * (p_fe + 1) if degree is None else degree
+        self.gravity, self.q0_mode, self.tau = float(gravity), q0_mode, tau
+        dΩ = Measure(Triangulation(model), self.degree)
+        _, xyz = dΩ.quadrature_points(chart=False)
+        self.f_q = np.ascontiguousarray(np.broadcast_to(f(xyz), xyz.shape[:2]), dtype=np.float64)
+        self.b_q = None if b is None else np.ascontiguousarray(np.broadcast_to(b(xyz), xyz.shape[:2]), dtype=np.float64)
+
+
+class RKStepper:
+    """Device-resident explicit RK march (`gg_rk_*`): Gridap.ODEs `ode_march!` for the wave operator, the DAE-aware
+    `ode_march!` of src/ODEs/RungeKuttaEX.jl:48-134 for the shallow-water operator."""
+
     def __init__(self, solver, op):
         m = op.model
         self.lib, self.ctx = m.lib, m.ctx
@@ -610,10 +665,19 @@ class WaveStepper:
         self._b = (C.c_double * s)(*[float(v) for v in b])
         self._c = (C.c_double * s)(*[float(v) for v in c])
         a = _lib.RKArgs()
-        a.problem, a.order, a.degree, a.n_stages = _lib.PROBLEM_WAVE, op.p_fe, op.degree, s
+        a.order, a.degree, a.n_stages = op.p_fe, op.degree, s
         a.A, a.b, a.c = self._A, self._b, self._c
         a.dt = solver.dt
         a.rtol = getattr(solver.ls, "rtol", 1e-12) or 1e-12
+        if isinstance(op, ShallowWaterOperator):
+            a.problem = _lib.PROBLEM_SHALLOW_WATER
+            a.gravity = op.gravity
+            a.tau = -1.0 if op.tau is None else float(op.tau)
+            a.q0_mode = {"alias": _lib.Q0_ALIAS, "start_of_step": _lib.Q0_START_OF_STEP}[op.q0_mode]
+            a.coriolis = _dp(op.f_q)
+            a.topography = _dp(op.b_q) if op.b_q is not None else None
+        else:
+            a.problem = _lib.PROBLEM_WAVE
         h = C.c_void_p()
         _lib.check(self.lib.gg_rk_create(m.h, C.byref(a), C.byref(h)))
         self.h = h
@@ -621,6 +685,9 @@ class WaveStepper:
         nu, np_ = C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_rk_info(self.h, C.byref(nu), C.byref(np_)))
         self.nu, self.np_ = nu.value, np_.value
+        nq, nF, nP = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_rk_diag_info(self.h, C.byref(nq), C.byref(nF), C.byref(nP)))
+        self.nq, self.ny = nq.value, nq.value + nF.value + nP.value
         self.dt = solver.dt
 
     def set_state(self, x):
@@ -642,6 +709,28 @@ class WaveStepper:
         _lib.check(self.lib.gg_rk_residual(self.h, _dp(x), _dp(r)))
         return r
 
+    # -- shallow water only
+    def get_diagnostics(self):
+        y = np.empty(self.ny)
+        _lib.check(self.lib.gg_rk_get_diagnostics(self.h, _dp(y)))
+        return y
+
+    def diagnostics(self, x):
+        """y = (q, F, Φ) from the diagnostic solve at x (src/ODEs/DAE.jl:241-274)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty(self.ny)
+        _lib.check(self.lib.gg_rk_diagnostics(self.h, _dp(x), _dp(y)))
+        return y
+
+    def stage_residual(self, x, y, q0=None):
+        """res_x(t,(u,p),(q,F,Φ),(v,r),(q0,..)) + mass(0) as the vector [r_u; r_p]."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        q0 = np.ascontiguousarray(y[: self.nq] if q0 is None else q0, dtype=np.float64)
+        r = np.empty_like(x)
+        _lib.check(self.lib.gg_rk_swe_residual(self.h, _dp(x), _dp(y), _dp(q0), _dp(r)))
+        return r
+
     def stats(self):
         a, b = C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_rk_stats(self.h, C.byref(a), C.byref(b)))
@@ -659,6 +748,9 @@ class WaveStepper:
             pass
 
 
+WaveStepper = RKStepper
+
+
 def gridap_num_steps(t0, tF, dt):
     """Steps taken by Gridap's ODE-solution iterator: stop when t >= tF - 100 eps, t accumulated as t += dt."""
     eps = 100 * np.finfo(np.float64).eps
@@ -671,7 +763,7 @@ def gridap_num_steps(t0, tF, dt):
 
 def solve(solver, op, t0, tF, x0):
     """solve(RungeKutta(...), op, t0, tF, xh0): marches to tF on the device, returns (tF, x_F, stepper)."""
-    st = WaveStepper(solver, op)
+    st = RKStepper(solver, op)
     st.set_state(x0)
     n = gridap_num_steps(t0, tF, solver.dt)
     st.step(n)

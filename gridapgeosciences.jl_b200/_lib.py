@@ -22,6 +22,8 @@ FORM_MASS_RT = 5
 FORM_DIV = 6
 FORM_SOURCE = 7
 PROBLEM_WAVE = 1
+PROBLEM_SHALLOW_WATER = 2
+Q0_ALIAS, Q0_START_OF_STEP = 0, 1
 
 
 class GGError(RuntimeError):
@@ -38,7 +40,9 @@ class FormArgs(C.Structure):
 class RKArgs(C.Structure):
     _fields_ = [("problem", C.c_int32), ("order", C.c_int32), ("degree", C.c_int32), ("n_stages", C.c_int32),
                 ("A", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)), ("c", C.POINTER(C.c_double)),
-                ("dt", C.c_double), ("rtol", C.c_double)]
+                ("dt", C.c_double), ("rtol", C.c_double),
+                ("gravity", C.c_double), ("tau", C.c_double), ("q0_mode", C.c_int32),
+                ("coriolis", C.POINTER(C.c_double)), ("topography", C.POINTER(C.c_double))]
 
 
 _P = C.c_void_p
@@ -102,6 +106,9 @@ SIGNATURES = {
     "gg_solver_update": (C.c_int, [_P]),
     "gg_solver_solve": (C.c_int, [_P, _P, _P, _PI32, _PD]),
     "gg_solver_destroy": (None, [_P]),
+    "gg_space_interp_points": (C.c_int, [_P, _PI32, _PD, _PD]),
+    "gg_space_interpolate": (C.c_int, [_P, _PD, _P]),
+    "gg_norm_sq": (C.c_int, [_P, _P, C.c_int32, _PD]),
     "gg_rk_create": (C.c_int, [_P, C.POINTER(RKArgs), _PP]),
     "gg_rk_info": (C.c_int, [_P, _PI64, _PI64]),
     "gg_rk_set_state": (C.c_int, [_P, _PD]),
@@ -110,6 +117,10 @@ SIGNATURES = {
     "gg_rk_step": (C.c_int, [_P, C.c_int32]),
     "gg_rk_residual": (C.c_int, [_P, _PD, _PD]),
     "gg_rk_stats": (C.c_int, [_P, _PI64, _PI64]),
+    "gg_rk_diag_info": (C.c_int, [_P, _PI64, _PI64, _PI64]),
+    "gg_rk_get_diagnostics": (C.c_int, [_P, _PD]),
+    "gg_rk_diagnostics": (C.c_int, [_P, _PD, _PD]),
+    "gg_rk_swe_residual": (C.c_int, [_P, _PD, _PD, _PD, _PD]),
     "gg_rk_destroy": (None, [_P]),
 }
 

@@ -1,0 +1,232 @@
+// Interpolation of ambient functions into the FE spaces and the norms of the transient drivers' error measures.
+//
+// Replaces `interpolate(f o ambient_map_cf, P)` (Lagrangian) and
+// `interpolate(meas_cf*((pinvJ o transpose o grad(ambient_map_cf)) . (vX o ambient_map_cf)), U)` (Raviart-Thomas) of
+// test/Transient/TransientShallowWater.jl:88-95 (pinvJ: src/Helpers/Operators.jl:16-24), and the error integrals
+// sqrt(sum(int e.(g e)/sqrtg)) / sqrt(sum(int e e sqrtg)) of test/Transient/TransientWaveEquation.jl:112-117.
+// The caller only evaluates its own ambient function at the points handed out by gg_space_interp_points(); geometry,
+// pull-back, inverse Piola map and moments run on the device.
+#include <cub/cub.cuh>
+#include "gg_common.cuh"
+#include "gg_refel.cuh"
+#include "gg_geom.cuh"
+
+namespace gg {
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// reference interpolation points of the space (host)
+static std::vector<double> interp_ref_points(const gg_space* s, std::vector<double>* W) {
+  std::vector<double> pts;
+  if (s->kind == GG_SPACE_RT) {
+    std::vector<double> w;
+    rt_moment_functionals(s->order, pts, w);
+    if (W) *W = std::move(w);
+  } else {
+    int p = s->order, nb = p + 1;
+    std::vector<int32_t> l2x = quad_local_to_lex(p);
+    pts.resize((size_t)nb * nb * 2);
+    for (int a = 0; a < nb * nb; ++a) {
+      pts[2 * a] = p == 0 ? 0.5 : (double)(l2x[a] % nb) / p;
+      pts[2 * a + 1] = p == 0 ? 0.5 : (double)(l2x[a] / nb) / p;
+    }
+  }
+  return pts;
+}
+
+__global__ void k_interp_points(int64_t nc, int N, const double* __restrict__ ref, const double* __restrict__ x0,
+                                const double* __restrict__ y0, const double* __restrict__ hx, const double* __restrict__ hy,
+                                const int32_t* __restrict__ chart, double radius, double* __restrict__ out_chart,
+                                double* __restrict__ out_xyz) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * N) return;
+  int64_t c = t / N;
+  int n = (int)(t - c * N);
+  double x = fma(hx[c], ref[2 * n], x0[c]), y = fma(hy[c], ref[2 * n + 1], y0[c]);
+  if (out_chart) { out_chart[2 * t] = x; out_chart[2 * t + 1] = y; }
+  if (out_xyz) csphere_point(chart[c], tan(x), tan(y), radius, &out_xyz[3 * t]);
+}
+
+// RT: reference-space field uhat = det(Jc) Jc^-1 u at every moment point, u = sqrtg (J J^T)^-1 J v  (sqrtg * pinvJ . v)
+__global__ void k_rt_pullback(int64_t nc, int N, const double* __restrict__ ref, const double* __restrict__ x0,
+                              const double* __restrict__ y0, const double* __restrict__ hx, const double* __restrict__ hy,
+                              const int32_t* __restrict__ chart, double radius, const double* __restrict__ v,
+                              double* __restrict__ uhat) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * N) return;
+  int64_t c = t / N;
+  int n = (int)(t - c * N);
+  double a = tan(fma(hx[c], ref[2 * n], x0[c])), b = tan(fma(hy[c], ref[2 * n + 1], y0[c]));
+  double J[2][3];
+  csphere_jacobian(chart[c], a, b, radius, J);
+  Metric2 m = csphere_metric_terms(a, b, radius);
+  double Jv0 = J[0][0] * v[3 * t] + J[0][1] * v[3 * t + 1] + J[0][2] * v[3 * t + 2];
+  double Jv1 = J[1][0] * v[3 * t] + J[1][1] * v[3 * t + 1] + J[1][2] * v[3 * t + 2];
+  double ux = m.sqrtg * (m.i11 * Jv0 + m.i12 * Jv1), uy = m.sqrtg * (m.i12 * Jv0 + m.i22 * Jv1);
+  uhat[2 * t] = hy[c] * ux;
+  uhat[2 * t + 1] = hx[c] * uy;
+}
+
+// one thread per free DOF: take the value from the first (cell, local) pair that touches it
+__global__ void k_interp_pick_scalar(int64_t n_free, int64_t nc, int m, const int32_t* __restrict__ vptr,
+                                     const int32_t* __restrict__ vsrc, const double* __restrict__ vals,
+                                     double* __restrict__ out) {
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_free) return;
+  if (vptr[d + 1] == vptr[d]) { out[d] = 0.0; return; }
+  int32_t src = vsrc[vptr[d]];
+  int i = (int)(src / nc);
+  int64_t c = src - (int64_t)i * nc;
+  out[d] = vals[c * m + i];
+}
+
+__global__ void k_interp_pick_rt(int64_t n_free, int64_t nc, int m, int N, const int32_t* __restrict__ vptr,
+                                 const int32_t* __restrict__ vsrc, const int8_t* __restrict__ signs,
+                                 const double* __restrict__ W, const double* __restrict__ uhat, double* __restrict__ out) {
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_free) return;
+  if (vptr[d + 1] == vptr[d]) { out[d] = 0.0; return; }
+  int32_t src = vsrc[vptr[d]];
+  int i = (int)(src / nc);
+  int64_t c = src - (int64_t)i * nc;
+  const double* w = W + (size_t)i * N * 2;
+  const double* uh = uhat + (size_t)c * N * 2;
+  double acc = 0.0;
+  for (int n = 0; n < 2 * N; ++n) acc = fma(w[n], uh[n], acc);
+  out[d] = (double)signs[c * m + i] * acc;
+}
+
+// per-cell contribution to the squared norm
+__global__ void k_norm_cells(int64_t nc, int nq, int m, int is_rt, const double* __restrict__ x0, const double* __restrict__ y0,
+                             const double* __restrict__ hx, const double* __restrict__ hy, double radius,
+                             const double* __restrict__ xi, const double* __restrict__ w, const double* __restrict__ val,
+                             const int32_t* __restrict__ dofs, const int8_t* __restrict__ signs, const double* __restrict__ e,
+                             double* __restrict__ sums) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double HX = hx[c], HY = hy[c];
+  double acc = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], y0[c]));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      Metric2 mt = csphere_metric_terms(tan(fma(HX, xi[q1], x0[c])), b, radius);
+      const double wq = w[q1] * w[q2] * HX * HY;
+      if (is_rt) {
+        double Ux = 0.0, Uy = 0.0;
+        for (int j = 0; j < m; ++j) {
+          int32_t d = dofs[c * m + j];
+          double ej = d >= 0 ? (double)signs[c * m + j] * e[d] : 0.0;
+          Ux = fma(val[(q * m + j) * 2], ej, Ux);
+          Uy = fma(val[(q * m + j) * 2 + 1], ej, Uy);
+        }
+        const double ux = Ux / HY, uy = Uy / HX;
+        acc = fma(wq / mt.sqrtg, ux * (mt.g11 * ux + mt.g12 * uy) + uy * (mt.g12 * ux + mt.g22 * uy), acc);
+      } else {
+        double eh = 0.0;
+        for (int j = 0; j < m; ++j) {
+          int32_t d = dofs[c * m + j];
+          eh = fma(val[q * m + j], d >= 0 ? e[d] : 0.0, eh);
+        }
+        acc = fma(wq * mt.sqrtg, eh * eh, acc);
+      }
+    }
+  }
+  sums[c] = acc;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* xyz) {
+  GG_API_BEGIN
+  GG_REQUIRE(s, GG_ERR_INVALID, "null space");
+  gg_mesh* m = s->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  std::vector<double> ref = interp_ref_points(s, nullptr);
+  int N = (int)(ref.size() / 2);
+  if (n_pts) *n_pts = N;
+  int64_t tot = m->n_cells * N;
+  if ((!chart && !xyz) || tot == 0) return GG_OK;
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dref; dref.upload(ref, st);
+  DevBuf<double> dc(chart ? 2 * tot : 0), dx(xyz ? 3 * tot : 0);
+  k_interp_points<<<nblk(tot, 256), 256, 0, st>>>(m->n_cells, N, dref.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
+                                                  m->d_chart.p, m->radius, dc.p, dx.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  if (chart) dc.download(chart, st);
+  if (xyz) dx.download(xyz, st);
+  GG_CUDA(cudaStreamSynchronize(st));
+  GG_API_END
+}
+
+int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && vals && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(gg_vec_size(out) == s->n_free, GG_ERR_INVALID, "output vector has the wrong length");
+  gg_mesh* m = s->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int64_t nc = m->n_cells;
+  if (s->n_free == 0) return GG_OK;
+  build_vec_map(s);
+  std::vector<double> W;
+  std::vector<double> ref = interp_ref_points(s, &W);
+  int N = (int)(ref.size() / 2);
+  int ml = s->ndofs_loc;
+  if (s->kind == GG_SPACE_RT) {
+    DevBuf<double> dref, dW, dv, duh((size_t)nc * N * 2);
+    dref.upload(ref, st); dW.upload(W, st); dv.upload(vals, (size_t)nc * N * 3, st);
+    if (nc) k_rt_pullback<<<nblk(nc * N, 128), 128, 0, st>>>(nc, N, dref.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
+                                                             m->d_chart.p, m->radius, dv.p, duh.p);
+    k_interp_pick_rt<<<nblk(s->n_free, 128), 128, 0, st>>>(s->n_free, nc, ml, N, s->d_vptr.p, s->d_vsrc.p, s->d_cell_signs.p,
+                                                           dW.p, duh.p, out->d.p);
+    ctx->launches += 2;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
+  } else {
+    DevBuf<double> dv; dv.upload(vals, (size_t)nc * ml, st);
+    k_interp_pick_scalar<<<nblk(s->n_free, 256), 256, 0, st>>>(s->n_free, nc, ml, s->d_vptr.p, s->d_vsrc.p, dv.p, out->d.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
+  }
+  GG_API_END
+}
+
+int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && e && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(gg_vec_size(e) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  gg_mesh* m = s->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  int64_t nc = m->n_cells;
+  *out = 0.0;
+  if (nc == 0) return GG_OK;
+  auto T = get_tab(ctx, s->kind, s->order, nq);
+  DevBuf<double> sums(nc), total(1);
+  int is_rt = s->kind == GG_SPACE_RT ? 1 : 0;
+  k_norm_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, is_rt, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius,
+                                              T->xi.p, T->w.p, T->val.p, s->d_cell_dofs.p, is_rt ? s->d_cell_signs.p : nullptr,
+                                              e->d.p, sums.p);
+  size_t tb = 0;
+  GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
+  DevBuf<uint8_t> tmp(tb);
+  GG_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, sums.p, total.p, (int)nc, st));
+  ctx->launches += 3;
+  GG_CUDA(cudaGetLastError());
+  total.download(out, st);
+  GG_API_END
+}
+
+}  // extern "C"

@@ -218,6 +218,52 @@ RTRef build_rt_ref(int k) {
   return R;
 }
 
+// Points and weights of the RT_k moment functionals (same facet / interior rules as build_rt_ref):
+// dof_i(f) = sum_n W[(i*N + n)*2 + c] f_c(pts[n]) for a reference-space vector field f.
+void rt_moment_functionals(int k, std::vector<double>& pts, std::vector<double>& W) {
+  GG_REQUIRE(k >= 0 && k <= 3, GG_ERR_UNSUPPORTED, "Raviart-Thomas order must be in 0..3");
+  const double va[4][2] = {{0, 0}, {0, 1}, {0, 0}, {1, 0}};
+  const double vb[4][2] = {{1, 0}, {1, 1}, {0, 1}, {1, 1}};
+  const double nn[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
+  int nqf = k + 2, nqc = k > 0 ? num_points_1d(2 * (k + 1)) : 0;
+  int N = 4 * nqf + nqc * nqc;
+  int ndofs = 2 * (k + 1) * (k + 2);
+  double xq[MAX_NQ], wq[MAX_NQ], xc[MAX_NQ], wc[MAX_NQ];
+  gauss_legendre_01(nqf, xq, wq);
+  if (nqc) gauss_legendre_01(nqc, xc, wc);
+  pts.assign((size_t)N * 2, 0.0);
+  W.assign((size_t)ndofs * N * 2, 0.0);
+  for (int f = 0; f < 4; ++f)
+    for (int q = 0; q < nqf; ++q) {
+      pts[2 * (f * nqf + q)] = va[f][0] + xq[q] * (vb[f][0] - va[f][0]);
+      pts[2 * (f * nqf + q) + 1] = va[f][1] + xq[q] * (vb[f][1] - va[f][1]);
+    }
+  for (int qy = 0; qy < nqc; ++qy)
+    for (int qx = 0; qx < nqc; ++qx) {
+      pts[2 * (4 * nqf + qx + nqc * qy)] = xc[qx];
+      pts[2 * (4 * nqf + qx + nqc * qy) + 1] = xc[qy];
+    }
+  int row = 0;
+  for (int f = 0; f < 4; ++f)
+    for (int m = 0; m <= k; ++m) {
+      for (int q = 0; q < nqf; ++q)
+        for (int c = 0; c < 2; ++c) W[((size_t)row * N + f * nqf + q) * 2 + c] = wq[q] * ipow(xq[q], m) * nn[f][c];
+      ++row;
+    }
+  if (k > 0)
+    for (int comp = 0; comp < 2; ++comp) {
+      int imax = comp == 0 ? k - 1 : k, jmax = comp == 0 ? k : k - 1;
+      for (int j = 0; j <= jmax; ++j)
+        for (int i = 0; i <= imax; ++i) {
+          for (int qy = 0; qy < nqc; ++qy)
+            for (int qx = 0; qx < nqc; ++qx)
+              W[((size_t)row * N + 4 * nqf + qx + nqc * qy) * 2 + comp] = wc[qx] * wc[qy] * ipow(xc[qx], i) * ipow(xc[qy], j);
+          ++row;
+        }
+    }
+  GG_REQUIRE(row == ndofs, GG_ERR_INVALID, "RT moment count mismatch");
+}
+
 void RTRef::tabulate(int npts, const double* pts, std::vector<double>& val, std::vector<double>& div) const {
   int n = ndofs;
   val.assign((size_t)npts * n * 2, 0.0);

@@ -41,5 +41,7 @@ struct RTRef {
   void tabulate(int npts, const double* pts, std::vector<double>& val, std::vector<double>& div) const;
 };
 RTRef build_rt_ref(int k);
+// points [N][2] and weights [ndofs][N][2] of the moment functionals of RT_k (interpolation of a reference-space field)
+void rt_moment_functionals(int k, std::vector<double>& pts, std::vector<double>& W);
 
 }  // namespace gg

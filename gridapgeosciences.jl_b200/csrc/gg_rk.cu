@@ -19,22 +19,11 @@
 #include "gg_common.cuh"
 #include "gg_refel.cuh"
 
-struct gg_rk {
-  gg_ctx* ctx = nullptr;
-  gg_mesh* mesh = nullptr;
-  gg_space *V = nullptr, *Q = nullptr;
-  gg_csr* Mu = nullptr;
-  gg_solver* solver = nullptr;
-  int order = 0, degree = 0, n_stages = 0, mq = 0, mu = 0;
-  std::vector<double> A, b, c;
-  double dt = 0.0;
-  int64_t nu = 0, np = 0;
-  gg::DevBuf<double> x, xi, r, MpInv, Bhat, signs_d;
-  std::vector<gg::DevBuf<double>> k;
-  gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
-};
+#include "gg_rk.cuh"
 
 namespace gg {
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 // one thread per cell: invert the m x m DG mass block held entry-major in ebuf[(i*m+j)*nc + c]
 template <int M>
@@ -129,8 +118,6 @@ __global__ void k_accumulate_stats(const double* __restrict__ solver_stats, doub
   if (threadIdx.x == 0 && blockIdx.x == 0) { accum[0] += solver_stats[0]; accum[1] += 1.0; }
 }
 
-static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
-
 static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
   gg_ctx* ctx = rk->ctx;
   int64_t n = rk->nu + rk->np;
@@ -142,7 +129,70 @@ static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
   GG_CUDA(cudaGetLastError());
 }
 
+void rk_accumulate_stats(gg_rk* rk, gg_solver* s) {
+  k_accumulate_stats<<<1, 32, 0, rk->ctx->stream>>>(s->stats.p, rk->iter_accum.p);
+  rk->ctx->launches++;
+}
+
+void rk_combine(gg_rk* rk, int ns, const double* co, double* out) {
+  int64_t n = rk->nu + rk->np;
+  if (n == 0) return;
+  auto kp = [&](int j) { return j < (int)rk->k.size() ? rk->k[j].p : nullptr; };
+  k_combine<<<nblk(n, 256), 256, 0, rk->ctx->stream>>>(n, rk->x.p, ns, co[0], kp(0), co[1], kp(1), co[2], kp(2), co[3], kp(3), out);
+  rk->ctx->launches++;
+}
+
+std::vector<double> build_bhat(int order, int degree) {
+  int nq = num_points_1d(degree);
+  GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
+  std::vector<double> xi(nq), w(nq);
+  gauss_legendre_01(nq, xi.data(), w.data());
+  RTRef R = build_rt_ref(order);
+  std::vector<double> pts((size_t)nq * nq * 2), val, div;
+  for (int q2 = 0; q2 < nq; ++q2)
+    for (int q1 = 0; q1 < nq; ++q1) { pts[2 * (q1 + nq * q2)] = xi[q1]; pts[2 * (q1 + nq * q2) + 1] = xi[q2]; }
+  R.tabulate(nq * nq, pts.data(), val, div);
+  int nb1 = order + 1, mq = nb1 * nb1, mu = R.ndofs;
+  std::vector<int32_t> l2x = quad_local_to_lex(order);
+  std::vector<double> N(nq * nb1), D(nq * nb1);
+  for (int q = 0; q < nq; ++q) lagrange_1d(order, xi[q], &N[q * nb1], &D[q * nb1]);
+  std::vector<double> B((size_t)mq * mu, 0.0);
+  for (int q2 = 0; q2 < nq; ++q2)
+    for (int q1 = 0; q1 < nq; ++q1) {
+      int q = q1 + nq * q2;
+      for (int I = 0; I < mq; ++I) {
+        double qI = N[q1 * nb1 + l2x[I] % nb1] * N[q2 * nb1 + l2x[I] / nb1];
+        for (int J = 0; J < mu; ++J) B[(size_t)I * mu + J] += w[q1] * w[q2] * qI * div[(size_t)q * mu + J];
+      }
+    }
+  return B;
+}
+
+void build_dg_mass_inverse(gg_rk* rk) {
+  gg_ctx* ctx = rk->ctx;
+  int64_t nc = rk->mesh->n_cells;
+  gg_form_args fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.test = rk->Q; fa.trial = rk->Q; fa.degree = rk->degree;
+  int layout = 0;
+  const double* mp = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
+  GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
+  rk->MpInv.alloc((size_t)rk->mq * rk->mq * nc);
+  if (nc) {
+    unsigned nb = nblk(nc, 64);
+    switch (rk->mq) {
+      case 1: k_invert_blocks<1><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      case 4: k_invert_blocks<4><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      case 9: k_invert_blocks<9><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
+      default: throw Error(GG_ERR_UNSUPPORTED, "DG order > 2 in the RK steppers");
+    }
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+}
+
 static void rk_step_async(gg_rk* rk) {
+  if (rk->problem == GG_PROBLEM_SHALLOW_WATER) { swe_step_async(rk); return; }
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
   int64_t n = rk->nu + rk->np;
@@ -182,6 +232,7 @@ extern "C" {
 
 void gg_rk_destroy(gg_rk* rk) {
   if (!rk) return;
+  swe_destroy(rk);
   gg_solver_destroy(rk->solver);
   gg_csr_destroy(rk->Mu);
   gg_space_destroy(rk->V);
@@ -193,15 +244,17 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   gg_rk* raw = nullptr;
   GG_API_BEGIN
   GG_REQUIRE(m && a && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE, GG_ERR_UNSUPPORTED, "only GG_PROBLEM_WAVE is implemented");
+  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_UNSUPPORTED,
+             "unknown problem id (GG_PROBLEM_WAVE and GG_PROBLEM_SHALLOW_WATER are implemented)");
   GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
-  GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "wave stepper supports RT_p x DG_p with p <= 2");
+  GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "the RK steppers support RT_p x DG_p with p <= 2");
   GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   raw = new gg_rk;
   gg_rk* rk = raw;
-  rk->ctx = ctx; rk->mesh = m; rk->order = a->order; rk->degree = a->degree; rk->n_stages = a->n_stages; rk->dt = a->dt;
+  rk->ctx = ctx; rk->mesh = m; rk->problem = a->problem; rk->order = a->order; rk->degree = a->degree;
+  rk->n_stages = a->n_stages; rk->dt = a->dt;
   int s = a->n_stages;
   rk->A.assign(a->A, a->A + s * s); rk->b.assign(a->b, a->b + s); rk->c.assign(a->c, a->c + s);
   for (int i = 0; i < s; ++i)
@@ -210,7 +263,6 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   chk(gg_space_builtin(m, GG_SPACE_RT, a->order, GG_CONSTRAINT_NONE, &rk->V));
   chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
   rk->nu = rk->V->n_free; rk->np = rk->Q->n_free; rk->mq = rk->Q->ndofs_loc; rk->mu = rk->V->ndofs_loc;
-  int64_t nc = m->n_cells;
   // RT mass matrix and its solver
   chk(gg_pattern(rk->V, rk->V, &rk->Mu));
   gg_form_args fa;
@@ -219,48 +271,9 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   chk(gg_assemble_matrix(GG_FORM_MASS_RT, &fa, rk->Mu, 0));
   chk(gg_solver_pcg_create(rk->Mu, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver));
   // DG mass blocks -> inverses
-  fa.test = rk->Q; fa.trial = rk->Q;
-  int layout = 0;
-  const double* mp = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
-  GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
-  rk->MpInv.alloc((size_t)rk->mq * rk->mq * nc);
-  if (nc) {
-    unsigned nb = nblk(nc, 64);
-    switch (rk->mq) {
-      case 1: k_invert_blocks<1><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
-      case 4: k_invert_blocks<4><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
-      case 9: k_invert_blocks<9><<<nb, 64, 0, ctx->stream>>>(nc, mp, rk->MpInv.p); break;
-      default: throw Error(GG_ERR_UNSUPPORTED, "DG order > 2 in the wave stepper");
-    }
-    ctx->launches++;
-    GG_CUDA(cudaGetLastError());
-  }
-  // reference div matrix Bhat[I][J] = sum_q w_q q_I(xi_q) divhat_J(xi_q), same rule as Measure(Omega, degree)
-  {
-    int nq = num_points_1d(a->degree);
-    GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
-    std::vector<double> xi(nq), w(nq);
-    gauss_legendre_01(nq, xi.data(), w.data());
-    RTRef R = build_rt_ref(a->order);
-    std::vector<double> pts((size_t)nq * nq * 2), val, div;
-    for (int q2 = 0; q2 < nq; ++q2)
-      for (int q1 = 0; q1 < nq; ++q1) { pts[2 * (q1 + nq * q2)] = xi[q1]; pts[2 * (q1 + nq * q2) + 1] = xi[q2]; }
-    R.tabulate(nq * nq, pts.data(), val, div);
-    int nb1 = a->order + 1;
-    std::vector<int32_t> l2x = quad_local_to_lex(a->order);
-    std::vector<double> N(nq * nb1), D(nq * nb1);
-    for (int q = 0; q < nq; ++q) lagrange_1d(a->order, xi[q], &N[q * nb1], &D[q * nb1]);
-    std::vector<double> B((size_t)rk->mq * rk->mu, 0.0);
-    for (int q2 = 0; q2 < nq; ++q2)
-      for (int q1 = 0; q1 < nq; ++q1) {
-        int q = q1 + nq * q2;
-        for (int I = 0; I < rk->mq; ++I) {
-          double qI = N[q1 * nb1 + l2x[I] % nb1] * N[q2 * nb1 + l2x[I] / nb1];
-          for (int J = 0; J < rk->mu; ++J) B[(size_t)I * rk->mu + J] += w[q1] * w[q2] * qI * div[(size_t)q * rk->mu + J];
-        }
-      }
-    rk->Bhat.upload(B, ctx->stream);
-  }
+  build_dg_mass_inverse(rk);
+  // reference div matrix, same rule as Measure(Omega, degree)
+  rk->Bhat.upload(build_bhat(a->order, a->degree), ctx->stream);
   build_vec_map(rk->V);
   int64_t n = rk->nu + rk->np;
   rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
@@ -269,6 +282,7 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   rk->iter_accum.alloc(2);
   GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
   if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
+  if (a->problem == GG_PROBLEM_SHALLOW_WATER) swe_create(rk, a);
   GG_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = raw;
   raw = nullptr;
@@ -287,6 +301,16 @@ int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p) {
   GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
   if (n_u) *n_u = rk->nu;
   if (n_p) *n_p = rk->np;
+  GG_API_END
+}
+
+int gg_rk_diag_info(gg_rk* rk, int64_t* n_q, int64_t* n_F, int64_t* n_Phi) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
+  bool swe = rk->problem == GG_PROBLEM_SHALLOW_WATER;
+  if (n_q) *n_q = swe ? rk->nr : 0;
+  if (n_F) *n_F = swe ? rk->nu : 0;
+  if (n_Phi) *n_Phi = swe ? rk->np : 0;
   GG_API_END
 }
 
@@ -325,8 +349,49 @@ int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
   GG_CUDA(cudaSetDevice(rk->ctx->device));
   int64_t n = rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
-  rk_residual_async(rk, rk->xi.p, rk->r.p);
+  if (rk->problem == GG_PROBLEM_SHALLOW_WATER) {
+    swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
+    swe_residual_async(rk, rk->xi.p, rk->y.p, rk->y.p, rk->r.p, nullptr);
+  } else {
+    rk_residual_async(rk, rk->xi.p, rk->r.p);
+  }
   rk->r.download(r, rk->ctx->stream);
+  GG_API_END
+}
+
+int gg_rk_get_diagnostics(gg_rk* rk, double* y) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && y, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(rk->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_INVALID, "this stepper has no diagnostic variables");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  rk->y.download(y, rk->ctx->stream);
+  GG_API_END
+}
+
+int gg_rk_diagnostics(gg_rk* rk, const double* x, double* y) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && x && y, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(rk->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_INVALID, "this stepper has no diagnostic variables");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  int64_t n = rk->nu + rk->np;
+  if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
+  swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
+  rk->y.download(y, rk->ctx->stream);
+  GG_API_END
+}
+
+int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double* q0, double* r) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && x && y && q0 && r, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(rk->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_INVALID, "not a shallow-water stepper");
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  cudaStream_t st = rk->ctx->stream;
+  int64_t n = rk->nu + rk->np, ny = rk->nr + rk->nu + rk->np;
+  if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (ny) GG_CUDA(cudaMemcpyAsync(rk->y.p, y, ny * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (rk->nr) GG_CUDA(cudaMemcpyAsync(rk->q0.p, q0, rk->nr * sizeof(double), cudaMemcpyHostToDevice, st));
+  swe_residual_async(rk, rk->xi.p, rk->y.p, rk->q0.p, rk->r.p, nullptr);
+  rk->r.download(r, st);
   GG_API_END
 }
 

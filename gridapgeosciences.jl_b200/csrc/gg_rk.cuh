@@ -1,0 +1,49 @@
+// Explicit Runge-Kutta stepper state shared by the linear-wave (gg_rk.cu) and shallow-water (gg_swe.cu) drivers.
+#pragma once
+#include "gg_common.cuh"
+
+struct gg_rk {
+  gg_ctx* ctx = nullptr;
+  gg_mesh* mesh = nullptr;
+  int problem = 0;
+  gg_space *V = nullptr, *Q = nullptr;  // RT_k, DG_k (prognostic u, p)
+  gg_csr* Mu = nullptr;                 // RT mass matrix (constant)
+  gg_solver* solver = nullptr;          // block-Jacobi PCG on Mu
+  int order = 0, degree = 0, n_stages = 0, mq = 0, mu = 0;
+  std::vector<double> A, b, c;
+  double dt = 0.0;
+  int64_t nu = 0, np = 0;
+  gg::DevBuf<double> x, xi, r, MpInv, Bhat;
+  std::vector<gg::DevBuf<double>> k;
+  gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
+  // ---- shallow water (DAE) only -------------------------------------------------------------------
+  gg_space* R = nullptr;          // CG_{k+1} (potential vorticity)
+  gg_csr* Mq = nullptr;           // int q p w sqrtg, re-assembled for every diagnostic solve
+  gg_solver* solver_q = nullptr;
+  gg_vec* pq = nullptr;           // depth at the quadrature points [n_cells][Q] (coefficient of Mq)
+  int mr = 0, nq1 = 0;
+  int64_t nr = 0;
+  double gravity = 0.0, tau = 0.0;
+  int q0_mode = 0;
+  gg::DevBuf<double> y;           // diagnostics [q (nr); F (nu); Phi (np)]
+  gg::DevBuf<double> q0;          // potential vorticity at the start of the step (q0_mode 1)
+  gg::DevBuf<double> fq, bq;      // Coriolis parameter / topography at the quadrature points
+  gg::DevBuf<double> rhs_q, rhs_F;
+  gg::DevBuf<double> evec_q, evec_u;  // entry-major element-vector scratch
+  int64_t diag_solves = 0;
+};
+
+namespace gg {
+// reference divergence matrix Bhat[I][J] = sum_q w_q psi_I(xi_q) divhat(phihat_J)(xi_q)  (mq x mu, row-major)
+std::vector<double> build_bhat(int order, int degree);
+// inverses of the DG mass blocks int psi_i psi_j sqrtg, entry-major [(i*mq+j)][cell] -> rk->MpInv
+void build_dg_mass_inverse(gg_rk* rk);
+void rk_accumulate_stats(gg_rk* rk, gg_solver* s);
+void rk_combine(gg_rk* rk, int ns, const double* coef, double* out);  // out = x + sum_j coef[j] k_j
+// shallow water (gg_swe.cu)
+void swe_create(gg_rk* rk, const gg_rk_args* a);
+void swe_step_async(gg_rk* rk);
+void swe_diagnostics_async(gg_rk* rk, const double* x, double* y);
+void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp);
+void swe_destroy(gg_rk* rk);
+}  // namespace gg

@@ -1,0 +1,397 @@
+// Rotating shallow water as a DAE with explicit Runge-Kutta stepping, on the device.
+//
+// Replaces, for X = RT_k x DG_k (prognostic u, p) and Y = CG_{k+1} x RT_k x DG_k (diagnostic q, F, Phi) on the cubed
+// sphere, the reference's DAE-aware `ode_march!` (src/ODEs/RungeKuttaEX.jl:48-134) applied to the forms of
+// test/Transient/TransientShallowWater.jl:113-139:
+//   diagnostics (src/ODEs/DAE.jl:241-274: x = 0, b = res_y, A = jac_y, one linear solve A y = -b; jac_y is block
+//   diagonal, so the three blocks are solved separately):
+//     int q p w sqrtg            = int f w sqrtg + int ((R u).ginv).grad(w) sqrtg          (CG_{k+1}, matrix depends on p)
+//     int F.(g v)/sqrtg          = int p u.(g v)/sqrtg                                    (RT_k mass, constant)
+//     int Phi psi sqrtg          = int g_r (p + b) psi sqrtg + int 1/2 u.(g u) psi/sqrtg  (DG_k mass, block diagonal)
+//   stage slope (src/ODEs/StageOperators.jl:55-88: x = 0, b = res_x + mass(0), A = mass, M k = -b):
+//     r_u = int [q - tau (q - q0)/dt - tau (u.grad q)/sqrtg] (R F).v - int Phi div(v),   r_p = int r div(F)
+// `q0` follows SURVEY.md F11: GG_Q0_ALIAS reproduces the reference (q0 and q share one array, the (q - q0) term
+// vanishes), GG_Q0_START_OF_STEP keeps the potential vorticity of the beginning of the step.
+//
+// B200 design
+//   * state, slopes, diagnostics and every operator stay resident in HBM/L2; a step enqueues a fixed sequence of
+//     launches with no host synchronisation (PCG iteration counts are decided inside the persistent solver kernel);
+//   * the nonlinear cell integrals run one thread per cell with all accumulators in FP64 registers; tangents of the
+//     quadrature abscissae come from the per-mesh tables (no tan() in the kernels), basis tabulations are read
+//     warp-uniformly through L1;
+//   * terms that are linear with constant coefficients collapse to the reference matrix Bhat (the Jacobian determinant
+//     cancels in int q div(u) under the contravariant Piola map), so -int Phi div(v) and int r div(F) need no quadrature;
+//   * the Bernoulli potential and the depth slope are cell-local (DG): the inverse mass block is applied inside the
+//     kernel that computed the right-hand side; RT and CG right-hand sides go through the atomic-free DOF gather.
+#include <cstring>
+#include "gg_rk.cuh"
+#include "gg_refel.cuh"
+#include "gg_geom.cuh"
+
+namespace gg {
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+struct SweTabs {
+  const double* w;       // 1-D quadrature weights [nq]
+  const double* rt_val;  // [Q][MU][2] reference RT basis
+  const double* dg_val;  // [Q][MP]
+  const double* cg_val;  // [Q][MR]
+  const double* cg_der;  // [Q][MR][2] reference gradients
+};
+
+// sqrt(det g) = r^2 sa sb / rho^3 (src/CellData/CellFields.jl:80-82 evaluated in closed form)
+__device__ __forceinline__ double csphere_sqrtg(double a, double b, double r) {
+  const double sa = fma(a, a, 1.0), sb = fma(b, b, 1.0);
+  const double rho2 = sa + b * b;
+  return r * r * sa * sb / (rho2 * sqrt(rho2));
+}
+
+// Right-hand sides of the three diagnostic equations, one thread per cell.
+//   pq_out [c*Q+q]      depth at the quadrature points (coefficient of the q mass matrix)
+//   eq [MR][nc], eF [MU][nc]  entry-major element vectors of the q and F equations
+//   Phi [c*MP+i]        Bernoulli potential (DG mass block inverted in place)
+template <int K>
+__global__ void __launch_bounds__(64)
+k_swe_diag(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
+           const double* __restrict__ u, const double* __restrict__ p, const double* __restrict__ fq,
+           const double* __restrict__ bq, double gravity, const double* __restrict__ MpInv, double* __restrict__ pq_out,
+           double* __restrict__ eq, double* __restrict__ eF, double* __restrict__ Phi) {
+  constexpr int MU = 2 * (K + 1) * (K + 2), MP = (K + 1) * (K + 1), MR = (K + 2) * (K + 2);
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double HX = g.hx[c], HY = g.hy[c], iHX = 1.0 / HX, iHY = 1.0 / HY;
+  const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * nq;
+  const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * nq;
+  double ue[MU], pe[MP], aq[MR], aF[MU], aP[MP];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) { ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]]; aF[j] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < MP; ++i) { pe[i] = p[c * MP + i]; aP[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) aq[i] = 0.0;
+  const int Q = nq * nq;
+#pragma unroll 1
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tb[q2];
+#pragma unroll 1
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      const Metric2 m = csphere_metric_terms(ta[q1], b, g.radius);
+      const double* __restrict__ rv = T.rt_val + (size_t)q * MU * 2;
+      double Ux = 0.0, Uy = 0.0;
+#pragma unroll
+      for (int j = 0; j < MU; ++j) { Ux = fma(rv[2 * j], ue[j], Ux); Uy = fma(rv[2 * j + 1], ue[j], Uy); }
+      const double ux = Ux * iHY, uy = Uy * iHX;  // contravariant Piola on an axis-aligned cell
+      const double* __restrict__ dv = T.dg_val + (size_t)q * MP;
+      double ph = 0.0;
+#pragma unroll
+      for (int i = 0; i < MP; ++i) ph = fma(dv[i], pe[i], ph);
+      pq_out[c * Q + q] = ph;
+      const double wq = T.w[q1] * T.w[q2] * HX * HY;
+      // vorticity equation: f w + ((R u).ginv).grad(w), R u = (-u_y, u_x)
+      {
+        const double cq = wq * m.sqrtg;
+        const double f0 = cq * fq[c * Q + q];
+        const double fx = cq * (-uy * m.i11 + ux * m.i12) * iHX, fy = cq * (-uy * m.i12 + ux * m.i22) * iHY;
+        const double* __restrict__ cv = T.cg_val + (size_t)q * MR;
+        const double* __restrict__ cd = T.cg_der + (size_t)q * MR * 2;
+#pragma unroll
+        for (int i = 0; i < MR; ++i) aq[i] = fma(f0, cv[i], fma(fx, cd[2 * i], fma(fy, cd[2 * i + 1], aq[i])));
+      }
+      // mass flux: p u.(g v)/sqrtg
+      const double gux = m.g11 * ux + m.g12 * uy, guy = m.g12 * ux + m.g22 * uy;
+      {
+        const double cF = wq * ph / m.sqrtg;
+        const double fx = cF * gux * iHY, fy = cF * guy * iHX;
+#pragma unroll
+        for (int j = 0; j < MU; ++j) aF[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], aF[j]));
+      }
+      // Bernoulli potential: g_r (p + b) sqrtg + 1/2 u.(g u)/sqrtg
+      {
+        const double bt = bq ? bq[c * Q + q] : 0.0;
+        const double cP = wq * (gravity * (ph + bt) * m.sqrtg + 0.5 * (ux * gux + uy * guy) / m.sqrtg);
+#pragma unroll
+        for (int i = 0; i < MP; ++i) aP[i] = fma(cP, dv[i], aP[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MR; ++i) eq[(int64_t)i * nc + c] = aq[i];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) eF[(int64_t)j * nc + c] = (double)vsigns[c * MU + j] * aF[j];
+#pragma unroll
+  for (int i = 0; i < MP; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < MP; ++j) acc = fma(MpInv[(int64_t)(i * MP + j) * nc + c], aP[j], acc);
+    Phi[c * MP + i] = acc;
+  }
+}
+
+// Stage residual, one thread per cell.  eru [MU][nc] entry-major element vector of r_u; rp [c*MP+i] = r_p (DG, cell
+// local); kp (optional) = -Mp^-1 r_p, the depth slope.
+template <int K, bool ALIAS>
+__global__ void __launch_bounds__(64)
+k_swe_stage(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
+            const int32_t* __restrict__ rdofs, const double* __restrict__ u, const double* __restrict__ qv,
+            const double* __restrict__ q0v, const double* __restrict__ Fv, const double* __restrict__ Phi,
+            const double* __restrict__ Bhat, const double* __restrict__ MpInv, double tau, double tau_over_dt,
+            double* __restrict__ eru, double* __restrict__ rp, double* __restrict__ kp) {
+  constexpr int MU = 2 * (K + 1) * (K + 2), MP = (K + 1) * (K + 1), MR = (K + 2) * (K + 2);
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double HX = g.hx[c], HY = g.hy[c], iHX = 1.0 / HX, iHY = 1.0 / HY;
+  const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * nq;
+  const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * nq;
+  double Fe[MU], ru[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) Fe[j] = (double)vsigns[c * MU + j] * Fv[vdofs[c * MU + j]];
+  // linear, constant-coefficient parts through the reference divergence matrix
+  {
+    double pe[MP], r[MP];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) { pe[i] = Phi[c * MP + i]; r[i] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < MU; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < MP; ++i) {
+        const double bij = Bhat[i * MU + j];
+        acc = fma(bij, pe[i], acc);
+        r[i] = fma(bij, Fe[j], r[i]);
+      }
+      ru[j] = -acc;
+    }
+#pragma unroll
+    for (int i = 0; i < MP; ++i) rp[c * MP + i] = r[i];
+    if (kp) {
+#pragma unroll
+      for (int i = 0; i < MP; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < MP; ++j) acc = fma(MpInv[(int64_t)(i * MP + j) * nc + c], r[j], acc);
+        kp[c * MP + i] = -acc;
+      }
+    }
+  }
+  double ue[MU], qe[MR], qc[ALIAS ? 1 : MR];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]];
+#pragma unroll
+  for (int i = 0; i < MR; ++i) {
+    const int32_t d = rdofs[c * MR + i];
+    qe[i] = qv[d];
+    // q - tau (q - q0)/dt = (1 - tau/dt) q + (tau/dt) q0
+    if (!ALIAS) qc[i] = fma(tau_over_dt, q0v[d] - qe[i], qe[i]);
+  }
+#pragma unroll 1
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tb[q2];
+#pragma unroll 1
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      const double sqrtg = csphere_sqrtg(ta[q1], b, g.radius);
+      const double* __restrict__ rv = T.rt_val + (size_t)q * MU * 2;
+      double Ux = 0.0, Uy = 0.0, Fx = 0.0, Fy = 0.0;
+#pragma unroll
+      for (int j = 0; j < MU; ++j) {
+        Ux = fma(rv[2 * j], ue[j], Ux); Uy = fma(rv[2 * j + 1], ue[j], Uy);
+        Fx = fma(rv[2 * j], Fe[j], Fx); Fy = fma(rv[2 * j + 1], Fe[j], Fy);
+      }
+      const double* __restrict__ cv = T.cg_val + (size_t)q * MR;
+      const double* __restrict__ cd = T.cg_der + (size_t)q * MR * 2;
+      double qq = 0.0, qx = 0.0, qy = 0.0;
+#pragma unroll
+      for (int i = 0; i < MR; ++i) {
+        qq = fma(cv[i], ALIAS ? qe[i] : qc[i], qq);
+        qx = fma(cd[2 * i], qe[i], qx);
+        qy = fma(cd[2 * i + 1], qe[i], qy);
+      }
+      // u.grad(q) in chart coordinates: (Ux/HY)(qx/HX) + (Uy/HX)(qy/HY)
+      const double ugq = (Ux * qx + Uy * qy) * iHX * iHY;
+      const double coef = T.w[q1] * T.w[q2] * HX * HY * (qq - tau * ugq / sqrtg);
+      // (R F).v_I with F = (Fx/HY, Fy/HX), v_I = (vx/HY, vy/HX): (-Fy/HX)(vx/HY) + (Fx/HY)(vy/HX)
+      const double fx = -coef * Fy * iHX * iHY, fy = coef * Fx * iHX * iHY;
+#pragma unroll
+      for (int j = 0; j < MU; ++j) ru[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], ru[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MU; ++j) eru[(int64_t)j * nc + c] = (double)vsigns[c * MU + j] * ru[j];
+}
+
+__global__ void k_copy(int64_t n, const double* __restrict__ a, double* __restrict__ b) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = a[i];
+}
+
+static SweTabs swe_tabs(gg_rk* rk) {
+  gg_ctx* ctx = rk->ctx;
+  auto trt = get_tab(ctx, GG_SPACE_RT, rk->order, rk->nq1);
+  auto tdg = get_tab(ctx, GG_SPACE_DG, rk->order, rk->nq1);
+  auto tcg = get_tab(ctx, GG_SPACE_CG, rk->order + 1, rk->nq1);
+  SweTabs T;
+  T.w = tdg->w.p; T.rt_val = trt->val.p; T.dg_val = tdg->val.p; T.cg_val = tcg->val.p; T.cg_der = tcg->der.p;
+  return T;
+}
+
+// y = [q; F; Phi] from the state x = [u; p]
+void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
+  gg_ctx* ctx = rk->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t nc = rk->mesh->n_cells;
+  if (nc == 0) return;
+  CellGeo g = cell_geo(rk->mesh, rk->nq1);
+  SweTabs T = swe_tabs(rk);
+  double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
+  const double *u = x, *p = x + rk->nu;
+  unsigned nb = nblk(nc, 64);
+  {
+    ProfScope ps(ctx, "k_swe_diag");
+#define GG_ARGS nc, rk->nq1, g, T, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, u, p, rk->fq.p, rk->bq.n ? rk->bq.p : nullptr, \
+                rk->gravity, rk->MpInv.p, rk->pq->d.p, rk->evec_q.p, rk->evec_u.p, yP
+    switch (rk->order) {
+      case 0: k_swe_diag<0><<<nb, 64, 0, st>>>(GG_ARGS); break;
+      case 1: k_swe_diag<1><<<nb, 64, 0, st>>>(GG_ARGS); break;
+      case 2: k_swe_diag<2><<<nb, 64, 0, st>>>(GG_ARGS); break;
+      default: throw Error(GG_ERR_UNSUPPORTED, "shallow-water order must be <= 2");
+    }
+#undef GG_ARGS
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+  // potential vorticity: assemble int q p w sqrtg (the Jacobian block that depends on the state), refresh the
+  // preconditioner (numerical_setup!), solve
+  {
+    gg_form_args fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.test = rk->R; fa.trial = rk->R; fa.degree = rk->degree; fa.qdata = rk->pq;
+    int layout = 0;
+    const double* eb = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
+    gather_matrix(rk->Mq, layout, eb, 1.0, 0);
+    solver_update(rk->solver_q);
+    gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
+    solver_solve_async(rk->solver_q, rk->rhs_q.p, 1.0, yq);
+    rk_accumulate_stats(rk, rk->solver_q);
+  }
+  // mass flux
+  gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
+  solver_solve_async(rk->solver, rk->rhs_F.p, 1.0, yF);
+  rk_accumulate_stats(rk, rk->solver);
+  rk->diag_solves++;
+}
+
+// r = [r_u; r_p]; kp (optional) receives the depth slope -Mp^-1 r_p
+void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp) {
+  gg_ctx* ctx = rk->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t nc = rk->mesh->n_cells;
+  if (nc == 0) return;
+  CellGeo g = cell_geo(rk->mesh, rk->nq1);
+  SweTabs T = swe_tabs(rk);
+  const double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
+  const bool alias = (q0 == yq);
+  unsigned nb = nblk(nc, 64);
+  {
+    ProfScope ps(ctx, "k_swe_stage");
+#define GG_ARGS nc, rk->nq1, g, T, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, rk->R->d_cell_dofs.p, x, yq, q0, yF, yP, \
+                rk->Bhat.p, rk->MpInv.p, rk->tau, rk->tau / rk->dt, rk->evec_u.p, r + rk->nu, kp
+#define GG_CASE(K_)                                                    \
+  case K_:                                                             \
+    if (alias) k_swe_stage<K_, true><<<nb, 64, 0, st>>>(GG_ARGS);      \
+    else k_swe_stage<K_, false><<<nb, 64, 0, st>>>(GG_ARGS);           \
+    break;
+    switch (rk->order) {
+      GG_CASE(0) GG_CASE(1) GG_CASE(2)
+      default: throw Error(GG_ERR_UNSUPPORTED, "shallow-water order must be <= 2");
+    }
+#undef GG_CASE
+#undef GG_ARGS
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+  gather_vector(rk->V, rk->evec_u.p, r, 1.0, 0);
+}
+
+// one ode_march! (src/ODEs/RungeKuttaEX.jl:48-134)
+void swe_step_async(gg_rk* rk) {
+  gg_ctx* ctx = rk->ctx;
+  cudaStream_t st = ctx->stream;
+  const int s = rk->n_stages;
+  // :70-75 initial diagnostics of the step
+  swe_diagnostics_async(rk, rk->x.p, rk->y.p);
+  if (rk->q0_mode == GG_Q0_START_OF_STEP && rk->nr) {
+    k_copy<<<nblk(rk->nr, 256), 256, 0, st>>>(rk->nr, rk->y.p, rk->q0.p);
+    ctx->launches++;
+  }
+  for (int i = 0; i < s; ++i) {
+    const double* xs = rk->x.p;
+    if (i > 0) {
+      // :85-88 stage state
+      double co[4] = {0, 0, 0, 0};
+      for (int j = 0; j < i && j < 4; ++j) co[j] = rk->dt * rk->A[i * s + j];
+      rk_combine(rk, std::min(i, 4), co, rk->xi.p);
+      xs = rk->xi.p;
+    }
+    // :91-93 stage diagnostics
+    swe_diagnostics_async(rk, xs, rk->y.p);
+    // :100-117 slope: M k = -(res_x + mass(0))
+    const double* q0 = rk->q0_mode == GG_Q0_START_OF_STEP ? rk->q0.p : rk->y.p;
+    swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu);
+    solver_solve_async(rk->solver, rk->r.p, -1.0, rk->k[i].p);
+    rk_accumulate_stats(rk, rk->solver);
+  }
+  // :121-122 update, :125-127 final diagnostics
+  double co[4] = {0, 0, 0, 0};
+  for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
+  rk_combine(rk, std::min(s, 4), co, rk->x.p);
+  swe_diagnostics_async(rk, rk->x.p, rk->y.p);
+  GG_CUDA(cudaGetLastError());
+}
+
+void swe_create(gg_rk* rk, const gg_rk_args* a) {
+  gg_ctx* ctx = rk->ctx;
+  cudaStream_t st = ctx->stream;
+  auto chk = [](int code) { if (code != GG_OK) throw Error(code, gg_last_error(nullptr)); };
+  GG_REQUIRE(a->coriolis, GG_ERR_INVALID, "shallow water needs the Coriolis parameter at the quadrature points");
+  GG_REQUIRE(a->q0_mode == GG_Q0_ALIAS || a->q0_mode == GG_Q0_START_OF_STEP, GG_ERR_INVALID, "unknown q0_mode");
+  const int64_t nc = rk->mesh->n_cells;
+  rk->nq1 = num_points_1d(a->degree);
+  GG_REQUIRE(rk->nq1 <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
+  const int64_t Q = (int64_t)rk->nq1 * rk->nq1;
+  rk->gravity = a->gravity;
+  rk->tau = a->tau < 0 ? 0.5 * a->dt : a->tau;  // TransientShallowWater.jl:150
+  rk->q0_mode = a->q0_mode;
+  chk(gg_space_builtin(rk->mesh, GG_SPACE_CG, a->order + 1, GG_CONSTRAINT_NONE, &rk->R));
+  rk->nr = rk->R->n_free; rk->mr = rk->R->ndofs_loc;
+  chk(gg_pattern(rk->R, rk->R, &rk->Mq));
+  chk(gg_vec_create(ctx, nc * Q, &rk->pq));
+  chk(gg_vec_fill(rk->pq, 1.0));
+  // a first assembly with unit depth so that the solver is created on a positive definite matrix
+  gg_form_args fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.test = rk->R; fa.trial = rk->R; fa.degree = a->degree; fa.qdata = rk->pq;
+  chk(gg_assemble_matrix(GG_FORM_MASS_SCALAR, &fa, rk->Mq, 0));
+  chk(gg_solver_pcg_create(rk->Mq, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver_q));
+  build_vec_map(rk->R);
+  rk->fq.upload(a->coriolis, (size_t)(nc * Q), st);
+  if (a->topography) rk->bq.upload(a->topography, (size_t)(nc * Q), st);
+  rk->y.alloc(rk->nr + rk->nu + rk->np);
+  rk->q0.alloc(rk->nr);
+  rk->rhs_q.alloc(rk->nr); rk->rhs_F.alloc(rk->nu);
+  rk->evec_q.alloc((size_t)rk->mr * nc); rk->evec_u.alloc((size_t)rk->mu * nc);
+  if (rk->y.n) GG_CUDA(cudaMemsetAsync(rk->y.p, 0, rk->y.n * sizeof(double), st));
+  if (rk->q0.n) GG_CUDA(cudaMemsetAsync(rk->q0.p, 0, rk->q0.n * sizeof(double), st));
+  GG_CUDA(cudaStreamSynchronize(st));
+}
+
+void swe_destroy(gg_rk* rk) {
+  if (rk->solver_q) gg_solver_destroy(rk->solver_q);
+  if (rk->Mq) gg_csr_destroy(rk->Mq);
+  if (rk->pq) gg_vec_destroy(rk->pq);
+  if (rk->R) gg_space_destroy(rk->R);
+  rk->solver_q = nullptr; rk->Mq = nullptr; rk->pq = nullptr; rk->R = nullptr;
+}
+
+}  // namespace gg

@@ -208,10 +208,33 @@ int gg_solver_update(gg_solver* s);
 int gg_solver_solve(gg_solver* s, gg_vec* b, gg_vec* x, int32_t* iters, double* rel_res);
 void gg_solver_destroy(gg_solver* s);
 
+/* ---- interpolation and norms (initial conditions / error measures of the transient drivers) ---------
+ * Replace `interpolate(f o ambient_map_cf, P)` for Lagrangian spaces and, for Raviart-Thomas spaces,
+ * `interpolate(meas_cf*((pinvJ o transpose o grad(ambient_map_cf)) . (vX o ambient_map_cf)), U)`
+ * (test/Transient/TransientShallowWater.jl:88-95, src/Helpers/Operators.jl:16-24): the caller evaluates its
+ * ambient function at the points returned by gg_space_interp_points(); the pull-back sqrtg * pinvJ(J) . v,
+ * the inverse contravariant Piola map and the reference moments run on the device.
+ *   n_pts   points per cell (Lagrangian: the ndofs_loc nodes; RT_k: 4 (k+2) facet + (k+2)^2 interior moment points)
+ *   chart   [n_cells][n_pts][2] or NULL;  xyz [n_cells][n_pts][3] or NULL */
+int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* xyz);
+/* vals: Lagrangian [n_cells][n_pts] scalars; RT [n_cells][n_pts][3] ambient vectors.  out: free DOF values. */
+int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out);
+/* squared norms used by the drivers' error measures (test/Transient/TransientWaveEquation.jl:112-117):
+ * Lagrangian: sum(int e^2 sqrtg);  RT: sum(int e.(g e) / sqrtg), quadrature degree `degree`. */
+int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
+
 /* ---- explicit Runge-Kutta drivers ----------------------------------------------------------------
- * Replace Gridap.ODEs `ode_march!` for EXRungeKutta on the linear-wave operator
- * (test/Transient/TransientWaveEquation.jl:63-77; constant mass) -- the whole step runs on the device. */
+ * GG_PROBLEM_WAVE: replaces Gridap.ODEs `ode_march!` for EXRungeKutta on the linear-wave operator
+ * (test/Transient/TransientWaveEquation.jl:63-77; constant mass).
+ * GG_PROBLEM_SHALLOW_WATER: replaces the DAE-aware `ode_march!` of src/ODEs/RungeKuttaEX.jl:48-134 on the rotating
+ * shallow-water operator of test/Transient/TransientShallowWater.jl:113-154 (prognostic u in RT_k, p in DG_k;
+ * diagnostic q in CG_{k+1}, F in RT_k, Phi in DG_k): a diagnostic solve (src/ODEs/DAE.jl:241-274) before every
+ * stage and after the update, then slope_i = -M^-1 r (src/ODEs/StageOperators.jl:55-88).
+ * The whole step runs on the device without host synchronisation. */
 #define GG_PROBLEM_WAVE 1
+#define GG_PROBLEM_SHALLOW_WATER 2
+#define GG_Q0_ALIAS 0         /* q0 aliases q, as in the reference (RungeKuttaEX.jl:69-75 pass one array twice) */
+#define GG_Q0_START_OF_STEP 1 /* q0 = potential vorticity at the beginning of the step */
 typedef struct {
   int32_t problem;     /* GG_PROBLEM_* */
   int32_t order;       /* p_fe: RT_p x DG_p */
@@ -221,7 +244,13 @@ typedef struct {
   const double* b;     /* [n_stages] */
   const double* c;     /* [n_stages] */
   double dt;
-  double rtol;         /* PCG tolerance of the RT mass solve (1e-12 if 0) */
+  double rtol;         /* PCG tolerance of the mass solves (1e-12 if 0) */
+  /* shallow water only */
+  double gravity;           /* g_r of the Bernoulli potential */
+  double tau;               /* upwinding parameter of res_u; negative: dt/2 (TransientShallowWater.jl:150) */
+  int32_t q0_mode;          /* GG_Q0_* */
+  const double* coriolis;   /* host [n_cells][Q]: f at the quadrature points (cor_cf) */
+  const double* topography; /* host [n_cells][Q]: b at the quadrature points, or NULL (= 0) */
 } gg_rk_args;
 int gg_rk_create(gg_mesh* m, const gg_rk_args* args, gg_rk** out);
 int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p);
@@ -229,9 +258,18 @@ int gg_rk_set_state(gg_rk* rk, const double* x /* [n_u + n_p] host */);
 int gg_rk_get_state(gg_rk* rk, double* x);
 double* gg_rk_state_device_ptr(gg_rk* rk);
 int gg_rk_step(gg_rk* rk, int32_t n_steps);
-/* matrix-free stage residual r = res(x) (parity hook), host in/out */
+/* matrix-free stage residual r = res(x) (parity hook), host in/out.  Shallow water: the diagnostics are solved
+ * at x first and q0 aliases q. */
 int gg_rk_residual(gg_rk* rk, const double* x, double* r);
 int gg_rk_stats(gg_rk* rk, int64_t* pcg_iters_total, int64_t* solves_total);
+/* shallow water: sizes of the diagnostic blocks y = [q; F; Phi] */
+int gg_rk_diag_info(gg_rk* rk, int64_t* n_q, int64_t* n_F, int64_t* n_Phi);
+/* diagnostics of the last solve (after gg_rk_step: those of the final state), host out [n_q + n_F + n_Phi] */
+int gg_rk_get_diagnostics(gg_rk* rk, double* y);
+/* parity hooks: y = diagnostics(x) (src/ODEs/DAE.jl:241-274); r = res_x(x, y, q0) + mass(0) (StageOperators.jl:24-38),
+ * all host arrays; q0 has n_q entries */
+int gg_rk_diagnostics(gg_rk* rk, const double* x, double* y);
+int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double* q0, double* r);
 void gg_rk_destroy(gg_rk* rk);
 
 #ifdef __cplusplus

@@ -1,0 +1,121 @@
+"""GPU parity: rotating shallow water as a DAE with explicit RK (RT_p x DG_p prognostic, CG_{p+1} x RT_p x DG_p
+diagnostic) against the oracle (oracle/swe.py) and the reference's regression numbers
+(test/Transient/TransientShallowWater.jl:208-209); interpolation and norms of the transient drivers."""
+import numpy as np
+import pytest
+
+from __graft_entry__ import load_package
+from oracle import rk as ork
+from oracle import swe as oswe
+from oracle.mesh import CubedSphereMesh2D
+
+pytestmark = pytest.mark.gpu
+
+EU_REF, EP_REF = 0.0035085422284689785, 3.5206285360509003e-6
+
+
+@pytest.fixture(scope="module")
+def gg():
+    return load_package()
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def _stepper(gg, n, p, dt, q0_mode="alias", rtol=1e-14):
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
+    op = gg.ShallowWaterOperator(model, p, oswe.coriolis(), gravity=oswe._g, q0_mode=q0_mode)
+    return model, gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=rtol), None, dt, "EXRK_SSP_3_3"), op)
+
+
+@pytest.mark.parametrize("n,p", [(4, 0), (5, 1), (3, 2)])
+def test_interpolation_and_norms_match_oracle(gg, n, p):
+    mesh = CubedSphereMesh2D(n)
+    P = oswe.ShallowWaterProblem(mesh, p)
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+    R = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p + 1), conformity="H1")
+    vX = oswe.tangent_component(oswe.velocity())
+    u = gg.interpolate(vX, V).get()
+    uo = ork.interpolate_rt(P.V, mesh, vX)
+    assert _rel(u, uo) < 1e-12
+    h = gg.interpolate(oswe.depth(), Q).get()
+    assert _rel(h, ork.interpolate_scalar(P.Q, mesh, oswe.depth())) < 1e-13
+    f = gg.interpolate(oswe.coriolis(), R).get()
+    assert np.abs(f - ork.interpolate_scalar(P.R, mesh, oswe.coriolis())).max() < 1e-13 * np.abs(f).max()
+    # norms: e_u = sqrt(int e.(g e)/sqrtg), e_p = sqrt(int e^2 sqrtg) at the error quadrature degree
+    rng = np.random.default_rng(3)
+    e = np.concatenate([rng.standard_normal(P.nu), rng.standard_normal(P.np_)])
+    eu, ep = P.errors(e, np.zeros_like(e))
+    assert abs(gg.norm(e[: P.nu], V, 2 * P.degree) - eu) < 1e-12 * eu
+    assert abs(gg.norm(e[P.nu:], Q, 2 * P.degree) - ep) < 1e-12 * ep
+
+
+@pytest.mark.parametrize("n,p", [(4, 0), (4, 1), (3, 2)])
+def test_diagnostics_and_stage_residual_match_oracle(gg, n, p):
+    mesh = CubedSphereMesh2D(n)
+    P = oswe.ShallowWaterProblem(mesh, p)
+    dt = oswe.reference_dt(mesh, max(p, 1))
+    P.dt, P.tau = dt, dt / 2
+    model, st = _stepper(gg, n, p, dt)
+    assert (st.nu, st.np_, st.nq) == (P.nu, P.np_, P.nq)
+    rng = np.random.default_rng(11)
+    x = P.initial_state()
+    x = x * (1 + 0.05 * rng.standard_normal(x.size))   # perturbed Williamson-2 state (depth stays positive)
+    y, yo = st.diagnostics(x), P.diagnostics(x)
+    q, F, Phi = P.split_y(y)
+    qo, Fo, Phio = P.split_y(yo)
+    assert _rel(q, qo) < 1e-10 and _rel(F, Fo) < 1e-10 and _rel(Phi, Phio) < 1e-12
+    # stage residual with the oracle's diagnostics as input: alias (q0 = q) and a distinct q0
+    r, ro = st.stage_residual(x, yo), P.residual_x(x, yo, yo)
+    assert np.abs(r - ro).max() < 1e-12 * np.abs(ro).max()
+    y0 = yo * (1 + 0.1 * rng.standard_normal(yo.size))
+    r, ro = st.stage_residual(x, yo, y0[: P.nq]), P.residual_x(x, yo, y0)
+    assert np.abs(r - ro).max() < 1e-12 * np.abs(ro).max()
+    # gg_rk_residual = diagnostics + residual in one call
+    r = st.residual(x)
+    ro = P.residual_x(x, yo, yo)
+    assert np.abs(r - ro).max() < 1e-9 * np.abs(ro).max()
+
+
+@pytest.mark.parametrize("n,p,mode", [(4, 1, "alias"), (4, 1, "start_of_step"), (3, 2, "alias"), (4, 0, "alias")])
+def test_steps_match_oracle(gg, n, p, mode):
+    mesh = CubedSphereMesh2D(n)
+    P = oswe.ShallowWaterProblem(mesh, p, q0_mode=mode)
+    dt = oswe.reference_dt(mesh, max(p, 1))
+    model, st = _stepper(gg, n, p, dt, q0_mode=mode)
+    x0 = P.initial_state()
+    st.set_state(x0)
+    st.step(2)
+    x = x0.copy()
+    for _ in range(2):
+        x, y = P.step(x, dt)
+    xg = st.get_state()
+    assert _rel(xg[: P.nu], x[: P.nu]) < 1e-9 and _rel(xg[P.nu:], x[P.nu:]) < 1e-10
+    assert _rel(st.get_diagnostics(), y) < 1e-8
+    iters, solves = st.stats()
+    assert solves == 2 * (2 * 5 + 3) and iters > 0    # per step: 5 diagnostic solves (q and F) + 3 slope solves
+
+
+def test_williamson2_regression_numbers_on_gpu(gg):
+    # nref 3, p_fe 1, CFL 0.1, one day, SSPRK(3,3); everything (initial state, march, error norms) through the library
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), 3)
+    p = 1
+    degree = 4 * (p + 1)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+    u0 = gg.interpolate(oswe.tangent_component(oswe.velocity()), V).get()
+    h0 = gg.interpolate(oswe.depth(), Q).get()
+    x0 = np.concatenate([u0, h0])
+    _dt = gg.dx(model) * 0.1 / (p * np.sqrt(oswe._g * oswe._H_0))
+    dt = oswe._tF / np.floor(oswe._tF / _dt)
+    op = gg.ShallowWaterOperator(model, p, oswe.coriolis(), gravity=oswe._g)
+    tend, xF, st = gg.solve(gg.RungeKutta(gg.CGSolver(rtol=1e-13), None, dt, ":EXRK_SSP_3_3"), op, 0.0, oswe._tF, x0)
+    e = x0 - xF
+    eu, ep = gg.norm(e[: st.nu], V, 2 * degree), gg.norm(e[st.nu:], Q, 2 * degree)
+    # the reference's own tolerance, then the oracle's (pinned in tests/test_oracle_swe.py) at PCG accuracy
+    assert abs(eu - EU_REF) <= 1e-2 * EU_REF + 1e-3 and abs(ep - EP_REF) <= 1e-2 * EP_REF + 1e-3
+    assert abs(eu - EU_REF) < 2e-4 * EU_REF and abs(ep - EP_REF) < 3e-4 * EP_REF
+    assert abs(eu - 0.0035082599123392863) < 1e-7 * eu and abs(ep - 3.52011724075712e-06) < 1e-6 * ep
