@@ -736,6 +736,12 @@ class RKStepper:
         _lib.check(self.lib.gg_rk_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def solver_phase_ns(self, which=0):
+        """(cell phase, gather+dot phase, update+preconditioner phase, iterations) of the matrix-free PCG `which`."""
+        out = np.zeros(4)
+        _lib.check(self.lib.gg_rk_solver_phase_ns(self.h, int(which), _dp(out)))
+        return out
+
     @property
     def state_device_ptr(self):
         return self.lib.gg_rk_state_device_ptr(self.h)

@@ -117,6 +117,7 @@ SIGNATURES = {
     "gg_rk_step": (C.c_int, [_P, C.c_int32]),
     "gg_rk_residual": (C.c_int, [_P, _PD, _PD]),
     "gg_rk_stats": (C.c_int, [_P, _PI64, _PI64]),
+    "gg_rk_solver_phase_ns": (C.c_int, [_P, C.c_int, _PD]),
     "gg_rk_diag_info": (C.c_int, [_P, _PI64, _PI64, _PI64]),
     "gg_rk_get_diagnostics": (C.c_int, [_P, _PD]),
     "gg_rk_diagnostics": (C.c_int, [_P, _PD, _PD]),

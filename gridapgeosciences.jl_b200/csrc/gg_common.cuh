@@ -104,6 +104,8 @@ struct gg_ctx {
   gg::DevBuf<double> ebuf, vbuf;
   // (order, nq) currently resident in the __constant__ tables of the fast scalar kernels
   int const_order = -1, const_nq = -1;
+  // tables resident in the __constant__ blocks of the matrix-free PCG (gg_mf.cu): nq of the weights, (order, nq) keys
+  int64_t mf_key_w = -1, mf_key_rt = -1, mf_key_sc = -1;
   // when set, assembly / solver entry points enqueue their work and return without synchronising the stream
   bool async = false;
   // optional per-kernel CUDA-event timing (gg_profile_*): name -> (events, count)
@@ -230,6 +232,11 @@ struct gg_solver {
   gg::DevBuf<double> r, r2, z, p, Ap, partials;
   gg::DevBuf<double> stats;  // [0] iterations of the last solve, [1] its relative residual
   int grid = 0, block = 256;
+  // matrix-free operator (gg_mf.cu): when on, A only provides the space and the preconditioner blocks
+  bool mf_on = false;
+  int mf_nq = 0, mf_grid = 0;
+  const double* mf_qcoef = nullptr;  // coefficient at the quadrature points [n_cells][Q] (scalar mass), not owned
+  gg::DevBuf<double> mf_ev;          // [ndofs_loc][n_cells] element vectors of A p
 };
 
 namespace gg {
@@ -261,4 +268,7 @@ const double* element_matrices_device(gg_form form, const gg_form_args* args, in
 void spmv(gg_csr* A, double alpha, const double* x, double beta, double* y);
 void solver_update(gg_solver* s);
 void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x);
+bool mf_supported(int kind, int order, int nq);
+void solver_set_matrix_free(gg_solver* s, int degree, const double* qcoef);
+void solver_solve_mf_async(gg_solver* s, const double* b, double scale_b, double* x);
 }  // namespace gg

@@ -1,0 +1,535 @@
+// Statically condensed, element-by-element, persistent single-launch PCG for the mass solves of the RK stages.
+//
+// Stands in for `LUSolver()` / `CGSolver(JacobiLinearSolver(); rtol=1e-12)` at the
+// `Algebra.solve!(x, ::LinearSolver, op, cache)` seam (src/ODEs/StageOperators.jl:55-88, src/ODEs/DAE.jl:241-274) on the
+// symmetric positive definite mass matrices of the transient drivers (RT_k mass: test/Transient/TransientWaveEquation.jl:63;
+// potential-vorticity mass int q p w sqrtg: test/Transient/TransientShallowWater.jl:122).
+//
+// B200 design.  A CG iteration on the assembled RT_2 mass matrix of a 256x256-per-panel mesh streams 3.4 GB of CSR
+// (0.5 ms of HBM time) plus 0.5 GB of block-Jacobi inverses; re-integrating the form every iteration instead costs
+// 0.37 ms of FP64 pipe (measured, gg_mf.cu).  Both lose to linear algebra done once per matrix:
+//   * the interior DOFs of a cell (12 of the 24 RT_2 moments, 4 of the 16 Q_3 nodes) are private to the cell, so they
+//     are eliminated exactly, cell by cell:  S_c = M_ff - M_fi M_ii^-1 M_if.  CG then runs on the facet / vertex / edge
+//     DOFs only (3x fewer unknowns for RT_2) and needs 19 instead of 34 iterations for rtol 1e-12;
+//   * the condensed operator is never assembled: every iteration applies the packed symmetric S_c (78 doubles per cell for
+//     RT_2 / Q_3, stored entry-major so that consecutive threads read consecutive addresses) and sums the element vectors
+//     per DOF in fixed cell order (atomic-free, deterministic);
+//   * one cooperative launch per solve, 3 grid barriers per iteration (the direction update p = z + beta p is folded into
+//     the operator phase), dot products through per-CTA partials that every CTA re-sums in the same order;
+//   * block-Jacobi preconditioner over the DOFs of one facet / edge, built from the condensed element matrices.
+// The eliminated DOFs are recovered cell by cell after the iteration: x_i = M_ii^-1 b_i - (M_ii^-1 M_if) x_f.
+#include <cooperative_groups.h>
+#include "gg_common.cuh"
+#include "gg_ebe.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gg {
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+__host__ __device__ constexpr int ebe_sym(int MB, int i, int j) {  // packed upper triangle, i <= j
+  return i * MB - (i * (i - 1)) / 2 + (j - i);
+}
+
+// ---- condensation: one thread per cell, element matrix entry-major full layout ebuf[(i*m+j)*nc + c] ------------------
+template <int MB, int MI>
+__global__ void __launch_bounds__(64)
+k_ebe_condense(int64_t nc, const double* __restrict__ ebuf, double* __restrict__ S, double* __restrict__ T,
+               double* __restrict__ W) {
+  constexpr int M = MB + MI;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  auto E = [&](int i, int j) { return ebuf[(int64_t)(i * M + j) * nc + c]; };
+  if (MI == 0) {
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = i; j < MB; ++j) S[(int64_t)ebe_sym(MB, i, j) * nc + c] = E(i, j);
+    return;
+  }
+  constexpr int MIa = MI > 0 ? MI : 1;
+  // W = M_ii^-1 (Gauss-Jordan; SPD block)
+  double a[MIa][MIa], w[MIa][MIa];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < MI; ++j) { a[i][j] = E(MB + i, MB + j); w[i][j] = i == j ? 1.0 : 0.0; }
+#pragma unroll
+  for (int k = 0; k < MI; ++k) {
+    const double d = 1.0 / a[k][k];
+#pragma unroll
+    for (int j = 0; j < MI; ++j) { a[k][j] *= d; w[k][j] *= d; }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+#pragma unroll
+      for (int j = 0; j < MI; ++j) { a[i][j] = fma(-f, a[k][j], a[i][j]); w[i][j] = fma(-f, w[k][j], w[i][j]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = i; j < MI; ++j) W[(int64_t)ebe_sym(MI, i, j) * nc + c] = 0.5 * (w[i][j] + w[j][i]);
+  // T = W M_if, column by column; S = M_ff - M_fi T (upper triangle)
+  for (int j = 0; j < MB; ++j) {
+    double v[MIa], t[MIa];
+#pragma unroll
+    for (int s = 0; s < MI; ++s) v[s] = E(MB + s, j);
+#pragma unroll
+    for (int r = 0; r < MI; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < MI; ++s) acc = fma(w[r][s], v[s], acc);
+      t[r] = acc;
+      T[(int64_t)(r * MB + j) * nc + c] = acc;
+    }
+    for (int i = 0; i <= j; ++i) {
+      double acc = E(i, j);
+#pragma unroll
+      for (int r = 0; r < MI; ++r) acc = fma(-E(i, MB + r), t[r], acc);
+      S[(int64_t)ebe_sym(MB, i, j) * nc + c] = acc;
+    }
+  }
+}
+
+// ---- block-Jacobi of the (never assembled) condensed matrix -----------------------------------------------------------
+// one thread per boundary DOF row: bmat[rowoff[d] + b] = sum over the cells around d of S_c[local(d)][local(bstart + b)]
+__global__ void k_ebe_block_rows(int64_t nb, int64_t nc, int mloc, int MB, const int32_t* __restrict__ vptr,
+                                 const int32_t* __restrict__ vsrc, const int32_t* __restrict__ cell_dofs,
+                                 const int32_t* __restrict__ bstart, const uint8_t* __restrict__ bsize,
+                                 const int32_t* __restrict__ rowoff, const double* __restrict__ S, double* __restrict__ bmat) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nb) return;
+  const int s = bstart[d], m = bsize[d];
+  double* out = bmat + rowoff[d];
+  for (int b = 0; b < m; ++b) out[b] = 0.0;
+  for (int32_t k = vptr[d]; k < vptr[d + 1]; ++k) {
+    const int32_t src = vsrc[k];
+    const int ia = (int)(src / nc);
+    const int64_t c = src - (int64_t)ia * nc;
+    for (int b = 0; b < m; ++b) {
+      int ib = -1;
+      for (int l = 0; l < MB; ++l)
+        if (cell_dofs[c * mloc + l] == s + b) { ib = l; break; }
+      if (ib < 0) continue;
+      const int lo = ia < ib ? ia : ib, hi = ia < ib ? ib : ia;
+      out[b] += S[(int64_t)(lo * MB - (lo * (lo - 1)) / 2 + (hi - lo)) * nc + c];
+    }
+  }
+}
+
+constexpr int EBE_MAX_BLOCK = 8;
+__global__ void k_ebe_block_inverse(int64_t n_blocks, const int32_t* __restrict__ blk_off, const uint8_t* __restrict__ blk_size,
+                                    double* __restrict__ bmat) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const int m = blk_size[b];
+  double* A = bmat + blk_off[b];
+  double a[EBE_MAX_BLOCK][EBE_MAX_BLOCK], v[EBE_MAX_BLOCK][EBE_MAX_BLOCK];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) { a[i][j] = A[i * m + j]; v[i][j] = i == j ? 1.0 : 0.0; }
+  for (int i = 0; i < m; ++i)
+    if (a[i][i] == 0.0) a[i][i] = 1.0;  // DOF without cells (sub-mesh)
+  for (int k = 0; k < m; ++k) {
+    const double d = 1.0 / a[k][k];
+    for (int j = 0; j < m; ++j) { a[k][j] *= d; v[k][j] *= d; }
+    for (int i = 0; i < m; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      for (int j = 0; j < m; ++j) { a[i][j] = fma(-f, a[k][j], a[i][j]); v[i][j] = fma(-f, v[k][j], v[i][j]); }
+    }
+  }
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) A[i * m + j] = v[i][j];
+}
+
+// ---- the solve -------------------------------------------------------------------------------------------------------
+struct EbeArgs {
+  int64_t nb, nc;
+  int mloc;
+  const int32_t* cell_dofs;
+  const double *S, *T, *W;
+  double* ev;  // [MB][nc]
+  const int32_t *vptr, *vsrc;
+  const int32_t *bstart, *rowoff;
+  const uint8_t* bsize;
+  const double* binv;
+  const double* b;
+  double scale_b;
+  double *x, *ra, *rb, *z, *p, *Ap, *partials;
+  double rtol;
+  int max_iter;
+  double* stats;
+};
+
+__device__ __forceinline__ unsigned long long ebe_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ double ebe_block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+__device__ __forceinline__ double ebe_grid_total(const double* partials, int nblocks, double* sh) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v += partials[i];
+  v = ebe_block_sum(v, sh);
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = v;
+  __syncthreads();
+  return bc;
+}
+
+// sum of the element contributions of DOF row i (at most 2 sources on the fast path, more in the tail loop)
+__device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i) {
+  const int32_t lo = a.vptr[i], hi = a.vptr[i + 1];
+  double acc = lo < hi ? a.ev[a.vsrc[lo]] : 0.0;
+  for (int32_t k = lo + 1; k < hi; ++k) acc += a.ev[a.vsrc[k]];
+  return acc;
+}
+
+template <int MB, int MI>
+__global__ void __launch_bounds__(256, 2)
+k_pcg_ebe(const EbeArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  constexpr int MIa = MI > 0 ? MI : 1;
+  constexpr int UNR = 4;
+  const int nbk = gridDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n = a.nb, nc = a.nc;
+  double* P0 = a.partials;
+  double* P1 = a.partials + nbk;
+  double* P2 = a.partials + 2 * nbk;
+  double* r_old = a.ra;
+  double* r_new = a.rb;
+
+  // ---- condensed right-hand side: bt = s b_f - sum_c T_c^T (s b_i) ----
+  if (MI > 0) {
+    for (int64_t c = tid; c < nc; c += nth) {
+      double bi[MIa];
+#pragma unroll
+      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t];
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * nc + c], bi[t], acc);
+        a.ev[(int64_t)j * nc + c] = acc;
+      }
+    }
+    grid.sync();
+  }
+  for (int64_t i = tid; i < n; i += nth) {
+    double v = a.scale_b * a.b[i];
+    if (MI > 0) v -= ebe_gather_row(a, i);
+    r_old[i] = v;
+  }
+  grid.sync();
+  double lrz = 0.0, lbb = 0.0;
+  for (int64_t i = tid; i < n; i += nth) {
+    const int s = a.bstart[i], m = a.bsize[i];
+    const double* bi_row = a.binv + a.rowoff[i];
+    double zi = 0.0;
+    for (int j = 0; j < m; ++j) zi = fma(bi_row[j], r_old[s + j], zi);
+    const double ri = r_old[i];
+    a.x[i] = 0.0; a.z[i] = zi; a.p[i] = 0.0;
+    lrz = fma(ri, zi, lrz);
+    lbb = fma(ri, ri, lbb);
+  }
+  lrz = ebe_block_sum(lrz, sh);
+  lbb = ebe_block_sum(lbb, sh);
+  if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; }
+  grid.sync();
+  double rz = ebe_grid_total(P0, nbk, sh);
+  const double bb = ebe_grid_total(P1, nbk, sh);
+  int it = 0;
+  double rr = bb;
+  double beta = 0.0;
+  unsigned long long tA = 0, tB = 0, tC = 0;
+  if (bb > 0.0) {
+    const double tol2 = a.rtol * a.rtol * bb;
+    for (it = 1; it <= a.max_iter; ++it) {
+      // -- A: element vectors of S p with p = z + beta p_old formed on the fly
+      unsigned long long t0 = ebe_now();
+      for (int64_t c = tid; c < nc; c += nth) {
+        double pe[MB], acc[MB];
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+          const int32_t d = a.cell_dofs[c * a.mloc + j];
+          pe[j] = d >= 0 ? fma(beta, a.p[d], a.z[d]) : 0.0;
+          acc[j] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+          for (int j = i; j < MB; ++j) {
+            const double s = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
+            acc[i] = fma(s, pe[j], acc[i]);
+            if (j != i) acc[j] = fma(s, pe[i], acc[j]);
+          }
+#pragma unroll
+        for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
+      }
+      grid.sync();
+      unsigned long long t1 = ebe_now();
+      tA += t1 - t0;
+      // -- B: p = z + beta p ; Ap = gather ; pAp
+      double lpap = 0.0;
+      for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+        int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
+        double pv[UNR], acc[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int64_t i = i0 + u * nth;
+          const bool ok = i < n;
+          lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
+          pv[u] = ok ? fma(beta, a.p[i], a.z[i]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          acc[u] = s0[u] >= 0 ? a.ev[s0[u]] : 0.0;
+          if (s1[u] >= 0) acc[u] += a.ev[s1[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          for (int32_t k = lo[u] + 2; k < hi[u]; ++k) acc[u] += a.ev[a.vsrc[k]];
+          const int64_t i = i0 + u * nth;
+          if (i < n) { a.p[i] = pv[u]; a.Ap[i] = acc[u]; lpap = fma(pv[u], acc[u], lpap); }
+        }
+      }
+      lpap = ebe_block_sum(lpap, sh);
+      if (threadIdx.x == 0) P2[blockIdx.x] = lpap;
+      grid.sync();
+      t0 = ebe_now();
+      tB += t0 - t1;
+      const double alpha = rz / ebe_grid_total(P2, nbk, sh);
+      // -- C: x += alpha p ; r -= alpha Ap ; z = Binv r (block rows recomputed: no barrier) ; rz, rr
+      double lrz2 = 0.0, lrr = 0.0;
+      for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+        int sb[UNR], mb[UNR], ro[UNR];
+        double ri[UNR], zi[UNR], xi[UNR], pi[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int64_t i = i0 + u * nth;
+          const bool ok = i < n;
+          sb[u] = ok ? a.bstart[i] : 0; mb[u] = ok ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
+          ri[u] = ok ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
+          xi[u] = ok ? a.x[i] : 0.0; pi[u] = ok ? a.p[i] : 0.0;
+          zi[u] = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const double* bi_row = a.binv + ro[u];
+          const int s = sb[u];
+          for (int j = 0; j < mb[u]; ++j) zi[u] = fma(bi_row[j], fma(-alpha, a.Ap[s + j], r_old[s + j]), zi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int64_t i = i0 + u * nth;
+          if (i < n) {
+            a.x[i] = fma(alpha, pi[u], xi[u]);
+            r_new[i] = ri[u]; a.z[i] = zi[u];
+            lrz2 = fma(ri[u], zi[u], lrz2);
+            lrr = fma(ri[u], ri[u], lrr);
+          }
+        }
+      }
+      lrz2 = ebe_block_sum(lrz2, sh);
+      lrr = ebe_block_sum(lrr, sh);
+      if (threadIdx.x == 0) { P0[blockIdx.x] = lrz2; P1[blockIdx.x] = lrr; }
+      grid.sync();
+      t1 = ebe_now();
+      tC += t1 - t0;
+      { double* t = r_old; r_old = r_new; r_new = t; }
+      const double rz_new = ebe_grid_total(P0, nbk, sh);
+      rr = ebe_grid_total(P1, nbk, sh);
+      if (rr <= tol2) break;  // uniform across the grid
+      beta = rz_new / rz;
+      rz = rz_new;
+    }
+  }
+  // ---- eliminated DOFs: x_i = W (s b_i) - T x_f ----
+  if (MI > 0) {
+    for (int64_t c = tid; c < nc; c += nth) {
+      double bi[MIa], xf[MB];
+#pragma unroll
+      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t];
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        const int32_t d = a.cell_dofs[c * a.mloc + j];
+        xf[j] = d >= 0 ? a.x[d] : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < MI; ++t) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < MI; ++s) {
+          const int lo = t < s ? t : s, hi = t < s ? s : t;
+          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * nc + c], bi[s], acc);
+        }
+#pragma unroll
+        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * nc + c], xf[j], acc);
+        a.x[n + c * MI + t] = acc;
+      }
+    }
+  }
+  if (tid == 0) {
+    const int itc = it > a.max_iter ? a.max_iter : it;
+    a.stats[0] = (double)itc;
+    a.stats[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    a.stats[2] += (double)tA; a.stats[3] += (double)tB; a.stats[4] += (double)tC; a.stats[5] += (double)itc;
+  }
+}
+
+template <int MB, int MI>
+static void ebe_launch_condense(gg_ctx* ctx, int64_t nc, const double* ebuf, double* S, double* T, double* W) {
+  k_ebe_condense<MB, MI><<<nblk(nc, 64), 64, 0, ctx->stream>>>(nc, ebuf, S, T, W);
+}
+
+#define GG_EBE_CASES(X) X(4, 0) X(8, 4) X(12, 12) X(8, 1) X(12, 4)
+
+static void* ebe_kernel(int MB, int MI) {
+#define X(MB_, MI_) if (MB == MB_ && MI == MI_) return (void*)k_pcg_ebe<MB_, MI_>;
+  GG_EBE_CASES(X)
+#undef X
+  return nullptr;
+}
+
+// (boundary, interior) local DOF split of a builtin space, or false when the condensed solver does not apply
+bool ebe_supported(const gg_space* sp) {
+  if (sp->blocks.empty() || sp->constraint != GG_CONSTRAINT_NONE) return false;
+  int MB, MI;
+  if (sp->kind == GG_SPACE_RT) { MB = 4 * (sp->order + 1); MI = 2 * sp->order * (sp->order + 1); }
+  else if (sp->kind == GG_SPACE_CG) { MB = 4 * sp->order; MI = (sp->order - 1) * (sp->order - 1); }
+  else return false;
+  return ebe_kernel(MB, MI) != nullptr;
+}
+
+EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
+  GG_REQUIRE(ebe_supported(sp), GG_ERR_UNSUPPORTED, "the condensed element-by-element solver needs a builtin RT_0..2 / CG_1..3 space");
+  gg_ctx* ctx = sp->mesh->ctx;
+  cudaStream_t st = ctx->stream;
+  std::unique_ptr<EbeSolver> s(new EbeSolver);
+  s->ctx = ctx; s->sp = sp;
+  s->rtol = rtol > 0 ? rtol : 1e-12;
+  s->max_iter = max_iter > 0 ? max_iter : 1000;
+  if (sp->kind == GG_SPACE_RT) { s->MB = 4 * (sp->order + 1); s->MI = 2 * sp->order * (sp->order + 1); }
+  else { s->MB = 4 * sp->order; s->MI = (sp->order - 1) * (sp->order - 1); }
+  const int64_t nc = sp->mesh->n_cells;
+  s->nc = nc;
+  // boundary DOFs come first in the builtin numberings, the interior ones are numbered cell by cell after them
+  s->nb = sp->n_free - nc * s->MI;
+  if (s->MI > 0) {
+    const auto& last = sp->blocks.back();
+    GG_REQUIRE(last.start == s->nb && last.count == nc && last.size == s->MI, GG_ERR_INVALID, "unexpected interior DOF numbering");
+  }
+  const int64_t n = s->nb;
+  std::vector<int32_t> bstart(n), rowoff(n), blk_off;
+  std::vector<uint8_t> bsize(n), blk_size;
+  int64_t off = 0, covered = 0;
+  for (const auto& bc : sp->blocks) {
+    if (bc.start >= n) break;
+    GG_REQUIRE(bc.start == covered && bc.size <= EBE_MAX_BLOCK, GG_ERR_INVALID, "inconsistent DOF block classes");
+    for (int64_t g = 0; g < bc.count; ++g) {
+      blk_off.push_back((int32_t)off); blk_size.push_back((uint8_t)bc.size);
+      for (int i = 0; i < bc.size; ++i) {
+        bstart[covered + i] = (int32_t)covered; bsize[covered + i] = (uint8_t)bc.size;
+        rowoff[covered + i] = (int32_t)(off + (int64_t)i * bc.size);
+      }
+      off += (int64_t)bc.size * bc.size;
+      covered += bc.size;
+    }
+  }
+  GG_REQUIRE(covered == n, GG_ERR_INVALID, "DOF block classes do not cover the boundary DOFs");
+  GG_REQUIRE(off < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "block preconditioner too large");
+  s->n_blocks = (int64_t)blk_off.size();
+  s->bstart.upload(bstart, st); s->rowoff.upload(rowoff, st); s->bsize.upload(bsize, st);
+  s->blk_off.upload(blk_off, st); s->blk_size.upload(blk_size, st);
+  s->binv.alloc(off);
+  const int MB = s->MB, MI = s->MI;
+  s->S.alloc((size_t)(MB * (MB + 1) / 2) * nc);
+  s->T.alloc((size_t)MI * MB * nc);
+  s->W.alloc((size_t)(MI * (MI + 1) / 2) * nc);
+  s->ev.alloc((size_t)MB * std::max<int64_t>(nc, 1));
+  s->r.alloc(n); s->r2.alloc(n); s->z.alloc(n); s->p.alloc(n); s->Ap.alloc(n);
+  build_vec_map(sp);
+  void* fn = ebe_kernel(MB, MI);
+  int per_sm = 0;
+  GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
+  GG_REQUIRE(per_sm >= 1, GG_ERR_CUDA, "condensed PCG kernel does not fit on an SM");
+  s->grid = ctx->sm_count * per_sm;
+  s->partials.alloc(3 * (size_t)s->grid);
+  s->stats.alloc(8);
+  GG_CUDA(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(double), st));
+  GG_CUDA(cudaStreamSynchronize(st));
+  return s.release();
+}
+
+void ebe_destroy(EbeSolver* s) { delete s; }
+
+// numerical_setup!: condense the element matrices (entry-major full layout [(i*m+j)][cell]) and rebuild the preconditioner
+void ebe_set_matrix(EbeSolver* s, const double* ebuf) {
+  gg_ctx* ctx = s->ctx;
+  gg_space* sp = s->sp;
+  if (s->nc == 0) return;
+  {
+    ProfScope ps(ctx, "k_ebe_condense");
+#define X(MB_, MI_) if (s->MB == MB_ && s->MI == MI_) ebe_launch_condense<MB_, MI_>(ctx, s->nc, ebuf, s->S.p, s->T.p, s->W.p);
+    GG_EBE_CASES(X)
+#undef X
+    ctx->launches++;
+  }
+  if (s->nb) {
+    ProfScope ps(ctx, "k_ebe_precond");
+    k_ebe_block_rows<<<nblk(s->nb, 128), 128, 0, ctx->stream>>>(s->nb, s->nc, sp->ndofs_loc, s->MB, sp->d_vptr.p, sp->d_vsrc.p,
+                                                                sp->d_cell_dofs.p, s->bstart.p, s->bsize.p, s->rowoff.p, s->S.p,
+                                                                s->binv.p);
+    k_ebe_block_inverse<<<nblk(s->n_blocks, 128), 128, 0, ctx->stream>>>(s->n_blocks, s->blk_off.p, s->blk_size.p, s->binv.p);
+    ctx->launches += 2;
+  }
+  GG_CUDA(cudaGetLastError());
+}
+
+// enqueue x = A^-1 (scale_b b), x and b over ALL free DOFs of the space (boundary first, then interior); no host sync
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x) {
+  gg_ctx* ctx = s->ctx;
+  gg_space* sp = s->sp;
+  if (sp->n_free == 0) return;
+  EbeArgs a;
+  a.nb = s->nb; a.nc = s->nc; a.mloc = sp->ndofs_loc; a.cell_dofs = sp->d_cell_dofs.p;
+  a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p;
+  a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p;
+  a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
+  a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
+  a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;
+  void* fn = ebe_kernel(s->MB, s->MI);
+  int grid = s->grid;
+  const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;
+  if (want < grid) grid = (int)std::max<int64_t>(want, 1);
+  void* args[] = {&a};
+  ProfScope ps(ctx, "k_pcg_ebe");
+  GG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
+}
+
+}  // namespace gg

@@ -1,0 +1,30 @@
+// Statically condensed element-by-element PCG (gg_ebe.cu): internal interface used by the RK steppers.
+#pragma once
+#include "gg_common.cuh"
+
+namespace gg {
+
+struct EbeSolver {
+  gg_ctx* ctx = nullptr;
+  gg_space* sp = nullptr;
+  int MB = 0, MI = 0;        // boundary (shared) / interior (cell-private) local DOFs
+  int64_t nb = 0, nc = 0;    // boundary free DOFs (numbered first), cells
+  DevBuf<double> S, T, W;    // per cell, entry-major: packed S_c, T_c = M_ii^-1 M_if, packed M_ii^-1
+  DevBuf<int32_t> bstart, rowoff, blk_off;
+  DevBuf<uint8_t> bsize, blk_size;
+  DevBuf<double> binv;
+  int64_t n_blocks = 0;
+  DevBuf<double> r, r2, z, p, Ap, ev, partials;
+  DevBuf<double> stats;      // [0] iterations of the last solve, [1] its relative residual, [2..5] phase timers (ns) + iterations
+  double rtol = 1e-12;
+  int max_iter = 1000;
+  int grid = 0;
+};
+
+bool ebe_supported(const gg_space* sp);
+EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter);
+void ebe_set_matrix(EbeSolver* s, const double* ebuf_full);
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x);
+void ebe_destroy(EbeSolver* s);
+
+}  // namespace gg

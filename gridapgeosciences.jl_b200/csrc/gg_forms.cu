@@ -542,6 +542,7 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
     const double* qc = a->qdata ? a->qdata->d.p : nullptr;
     unsigned nb = nblk(nc * P.mt, 128);
+    ProfScope ps(ctx, "k_scalar_matrix");
 #define GG_CASE(MU_)                                                                                                      \
   if (P.mu == MU_) {                                                                                                      \
     if (ext) k_scalar_matrix<MU_, true><<<nb, 128, 0, st>>>(g, P.nq, tt->xi.p, tt->w.p, P.mt, tt->val.p, tt->der.p, tu->val.p, tu->der.p, cM, cK, qc, eb); \

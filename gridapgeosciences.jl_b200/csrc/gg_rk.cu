@@ -16,6 +16,7 @@
 //   * the DG mass block is block diagonal: its cell blocks are inverted once (batched Gauss-Jordan, one thread per
 //     cell) and applied as a dense mat-vec; the RT block is solved by the persistent Jacobi-PCG (gg_solver.cu).
 #include <cstring>
+#include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_refel.cuh"
 
@@ -129,9 +130,21 @@ static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
   GG_CUDA(cudaGetLastError());
 }
 
-void rk_accumulate_stats(gg_rk* rk, gg_solver* s) {
-  k_accumulate_stats<<<1, 32, 0, rk->ctx->stream>>>(s->stats.p, rk->iter_accum.p);
+void rk_accumulate_stats(gg_rk* rk, const double* solver_stats) {
+  k_accumulate_stats<<<1, 32, 0, rk->ctx->stream>>>(solver_stats, rk->iter_accum.p);
   rk->ctx->launches++;
+}
+
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x) {
+  EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
+  if (e) {
+    ebe_solve_async(e, b, scale, x);
+    rk_accumulate_stats(rk, e->stats.p);
+  } else {
+    gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
+    solver_solve_async(s, b, scale, x);
+    rk_accumulate_stats(rk, s->stats.p);
+  }
 }
 
 void rk_combine(gg_rk* rk, int ns, const double* co, double* out) {
@@ -209,9 +222,7 @@ static void rk_step_async(gg_rk* rk) {
     }
     rk_residual_async(rk, xs, rk->r.p);
     // slope: M k = -r
-    solver_solve_async(rk->solver, rk->r.p, -1.0, rk->k[i].p);
-    k_accumulate_stats<<<1, 32, 0, st>>>(rk->solver->stats.p, rk->iter_accum.p);
-    ctx->launches++;
+    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p);
     if (rk->np) {
       k_apply_dg_inverse<<<nblk(rk->np, 128), 128, 0, st>>>(rk->mesh->n_cells, rk->mq, rk->MpInv.p, rk->r.p + rk->nu, rk->k[i].p + rk->nu);
       ctx->launches++;
@@ -233,6 +244,7 @@ extern "C" {
 void gg_rk_destroy(gg_rk* rk) {
   if (!rk) return;
   swe_destroy(rk);
+  ebe_destroy(rk->ebe_u);
   gg_solver_destroy(rk->solver);
   gg_csr_destroy(rk->Mu);
   gg_space_destroy(rk->V);
@@ -270,6 +282,16 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   fa.test = rk->V; fa.trial = rk->V; fa.degree = a->degree;
   chk(gg_assemble_matrix(GG_FORM_MASS_RT, &fa, rk->Mu, 0));
   chk(gg_solver_pcg_create(rk->Mu, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver));
+  // mass solver: GG_PCG = ebe (default: statically condensed element-by-element), mf (matrix-free re-integration), csr
+  const char* mode_env = getenv("GG_PCG");
+  const std::string mode = mode_env ? mode_env : "ebe";
+  if (mode == "ebe" && ebe_supported(rk->V)) {
+    rk->ebe_u = ebe_create(rk->V, a->rtol > 0 ? a->rtol : 1e-12, 2000);
+    int layout = 0;
+    const double* eb = element_matrices_device(GG_FORM_MASS_RT, &fa, &layout);
+    GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
+    ebe_set_matrix(rk->ebe_u, eb);
+  }
   // DG mass blocks -> inverses
   build_dg_mass_inverse(rk);
   // reference div matrix, same rule as Measure(Omega, degree)
@@ -282,7 +304,11 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   rk->iter_accum.alloc(2);
   GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
   if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
-  if (a->problem == GG_PROBLEM_SHALLOW_WATER) swe_create(rk, a);
+  if (a->problem == GG_PROBLEM_SHALLOW_WATER) {
+    swe_create(rk, a);
+  } else if (mode == "mf" && mf_supported(GG_SPACE_RT, a->order, num_points_1d(a->degree))) {
+    solver_set_matrix_free(rk->solver, a->degree, nullptr);
+  }
   GG_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = raw;
   raw = nullptr;
@@ -392,6 +418,21 @@ int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double
   if (rk->nr) GG_CUDA(cudaMemcpyAsync(rk->q0.p, q0, rk->nr * sizeof(double), cudaMemcpyHostToDevice, st));
   swe_residual_async(rk, rk->xi.p, rk->y.p, rk->q0.p, rk->r.p, nullptr);
   rk->r.download(r, st);
+  GG_API_END
+}
+
+int gg_rk_solver_phase_ns(gg_rk* rk, int which, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(rk && out, GG_ERR_INVALID, "null argument");
+  gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
+  EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
+  for (int i = 0; i < 4; ++i) out[i] = 0.0;
+  if (!s && !e) return GG_OK;
+  GG_CUDA(cudaSetDevice(rk->ctx->device));
+  double h[8];
+  if (e) e->stats.download(h, rk->ctx->stream);
+  else s->stats.download(h, rk->ctx->stream);
+  for (int i = 0; i < 4; ++i) out[i] = h[2 + i];
   GG_API_END
 }
 

@@ -1,6 +1,7 @@
 // Explicit Runge-Kutta stepper state shared by the linear-wave (gg_rk.cu) and shallow-water (gg_swe.cu) drivers.
 #pragma once
 #include "gg_common.cuh"
+#include "gg_ebe.cuh"
 
 struct gg_rk {
   gg_ctx* ctx = nullptr;
@@ -8,7 +9,9 @@ struct gg_rk {
   int problem = 0;
   gg_space *V = nullptr, *Q = nullptr;  // RT_k, DG_k (prognostic u, p)
   gg_csr* Mu = nullptr;                 // RT mass matrix (constant)
-  gg_solver* solver = nullptr;          // block-Jacobi PCG on Mu
+  gg_solver* solver = nullptr;          // block-Jacobi PCG on Mu (assembled or matrix-free operator)
+  gg::EbeSolver* ebe_u = nullptr;       // default: statically condensed element-by-element PCG on the RT mass
+  gg::EbeSolver* ebe_q = nullptr;       // ... and on the potential-vorticity mass (shallow water)
   int order = 0, degree = 0, n_stages = 0, mq = 0, mu = 0;
   std::vector<double> A, b, c;
   double dt = 0.0;
@@ -38,7 +41,9 @@ namespace gg {
 std::vector<double> build_bhat(int order, int degree);
 // inverses of the DG mass blocks int psi_i psi_j sqrtg, entry-major [(i*mq+j)][cell] -> rk->MpInv
 void build_dg_mass_inverse(gg_rk* rk);
-void rk_accumulate_stats(gg_rk* rk, gg_solver* s);
+void rk_accumulate_stats(gg_rk* rk, const double* solver_stats);
+// k = A^-1 (scale b) with the RT mass (which = 0) or the potential-vorticity mass (which = 1), whichever solver is active
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x);
 void rk_combine(gg_rk* rk, int ns, const double* coef, double* out);  // out = x + sum_j coef[j] k_j
 // shallow water (gg_swe.cu)
 void swe_create(gg_rk* rk, const gg_rk_args* a);

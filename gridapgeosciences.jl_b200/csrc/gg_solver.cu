@@ -192,6 +192,7 @@ void spmv(gg_csr* A, double alpha, const double* x, double beta, double* y) {
 void solver_update(gg_solver* s) {
   gg_csr* A = s->A;
   if (s->n_blocks == 0) return;
+  ProfScope ps(A->ctx, "k_block_inverse");
   k_block_inverse<<<(unsigned)((s->n_blocks + 63) / 64), 64, 0, A->ctx->stream>>>(
       s->n_blocks, s->d_blk_start.p, s->d_blk_size.p, s->d_blk_off.p, A->d_rowptr.p, A->d_colind.p, A->d_vals.p, s->binv.p);
   A->ctx->launches++;
@@ -203,6 +204,7 @@ void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x
   gg_csr* A = s->A;
   int64_t n = A->n_rows;
   if (n == 0) return;
+  if (s->mf_on) { solver_solve_mf_async(s, b, scale_b, x); return; }
   const int32_t* rp = A->d_rowptr.p;
   const int32_t* ci = A->d_colind.p;
   const double* va = A->d_vals.p;
@@ -218,6 +220,7 @@ void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x
   int grid = s->grid;
   int64_t want = (n + s->block - 1) / s->block;
   if (want < grid) grid = (int)std::max<int64_t>(want, 1);
+  ProfScope ps(A->ctx, "k_pcg_persistent");
   GG_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(grid), dim3(s->block), args, 0, A->ctx->stream));
   A->ctx->launches++;
 }
@@ -285,7 +288,8 @@ int gg_solver_pcg_create(gg_csr* A, double rtol, int max_iter, gg_solver** out) 
   GG_REQUIRE(per_sm >= 1, GG_ERR_CUDA, "persistent PCG kernel does not fit on an SM");
   s->grid = ctx->sm_count * std::min(per_sm, 2);
   s->partials.alloc(3 * (size_t)s->grid);
-  s->stats.alloc(2);
+  s->stats.alloc(8);
+  GG_CUDA(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(double), st));
   solver_update(s.get());
   GG_CUDA(cudaStreamSynchronize(st));
   *out = s.release();
@@ -307,7 +311,7 @@ int gg_solver_solve(gg_solver* s, gg_vec* b, gg_vec* x, int32_t* iters, double* 
   GG_REQUIRE(gg_vec_size(b) == s->A->n_rows && gg_vec_size(x) == s->A->n_rows, GG_ERR_INVALID, "vector sizes do not match the matrix");
   GG_CUDA(cudaSetDevice(s->A->ctx->device));
   solver_solve_async(s, b->d.p, 1.0, x->d.p);
-  double st[2] = {0, 0};
+  double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (s->A->n_rows) s->stats.download(st, s->A->ctx->stream);
   if (iters) *iters = (int32_t)st[0];
   if (rel_res) *rel_res = st[1];

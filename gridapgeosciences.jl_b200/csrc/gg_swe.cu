@@ -24,6 +24,7 @@
 //   * the Bernoulli potential and the depth slope are cell-local (DG): the inverse mass block is applied inside the
 //     kernel that computed the right-hand side; RT and CG right-hand sides go through the atomic-free DOF gather.
 #include <cstring>
+#include <cstdlib>
 #include "gg_rk.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
@@ -264,21 +265,28 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   // potential vorticity: assemble int q p w sqrtg (the Jacobian block that depends on the state), refresh the
   // preconditioner (numerical_setup!), solve
   {
-    gg_form_args fa;
-    std::memset(&fa, 0, sizeof(fa));
-    fa.test = rk->R; fa.trial = rk->R; fa.degree = rk->degree; fa.qdata = rk->pq;
-    int layout = 0;
-    const double* eb = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
-    gather_matrix(rk->Mq, layout, eb, 1.0, 0);
-    solver_update(rk->solver_q);
+    if (rk->ebe_q || !rk->solver_q->mf_on) {
+      // the Jacobian block that depends on the state: element matrices of int q p w sqrtg, then numerical_setup!
+      // (condensation + preconditioner for the element-by-element solver, CSR fill + block inverses for the assembled one)
+      gg_form_args fa;
+      std::memset(&fa, 0, sizeof(fa));
+      fa.test = rk->R; fa.trial = rk->R; fa.degree = rk->degree; fa.qdata = rk->pq;
+      int layout = 0;
+      const double* eb = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
+      if (rk->ebe_q) {
+        GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
+        ebe_set_matrix(rk->ebe_q, eb);
+      } else {
+        gather_matrix(rk->Mq, layout, eb, 1.0, 0);
+        solver_update(rk->solver_q);
+      }
+    }
     gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
-    solver_solve_async(rk->solver_q, rk->rhs_q.p, 1.0, yq);
-    rk_accumulate_stats(rk, rk->solver_q);
+    rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq);
   }
   // mass flux
   gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
-  solver_solve_async(rk->solver, rk->rhs_F.p, 1.0, yF);
-  rk_accumulate_stats(rk, rk->solver);
+  rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF);
   rk->diag_solves++;
 }
 
@@ -339,8 +347,7 @@ void swe_step_async(gg_rk* rk) {
     // :100-117 slope: M k = -(res_x + mass(0))
     const double* q0 = rk->q0_mode == GG_Q0_START_OF_STEP ? rk->q0.p : rk->y.p;
     swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu);
-    solver_solve_async(rk->solver, rk->r.p, -1.0, rk->k[i].p);
-    rk_accumulate_stats(rk, rk->solver);
+    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p);
   }
   // :121-122 update, :125-127 final diagnostics
   double co[4] = {0, 0, 0, 0};
@@ -375,6 +382,15 @@ void swe_create(gg_rk* rk, const gg_rk_args* a) {
   chk(gg_assemble_matrix(GG_FORM_MASS_SCALAR, &fa, rk->Mq, 0));
   chk(gg_solver_pcg_create(rk->Mq, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver_q));
   build_vec_map(rk->R);
+  // matrix-free mass solves unless GG_PCG=csr is exported (the assembled path stays available for comparison)
+  const char* mode_env = getenv("GG_PCG");
+  const std::string mode = mode_env ? mode_env : "ebe";
+  if (mode == "ebe" && rk->ebe_u && ebe_supported(rk->R)) {
+    rk->ebe_q = ebe_create(rk->R, a->rtol > 0 ? a->rtol : 1e-12, 2000);
+  } else if (mode == "mf" && mf_supported(GG_SPACE_RT, a->order, rk->nq1) && mf_supported(GG_SPACE_CG, a->order + 1, rk->nq1)) {
+    solver_set_matrix_free(rk->solver, a->degree, nullptr);
+    solver_set_matrix_free(rk->solver_q, a->degree, rk->pq->d.p);
+  }
   rk->fq.upload(a->coriolis, (size_t)(nc * Q), st);
   if (a->topography) rk->bq.upload(a->topography, (size_t)(nc * Q), st);
   rk->y.alloc(rk->nr + rk->nu + rk->np);
@@ -387,6 +403,8 @@ void swe_create(gg_rk* rk, const gg_rk_args* a) {
 }
 
 void swe_destroy(gg_rk* rk) {
+  ebe_destroy(rk->ebe_q);
+  rk->ebe_q = nullptr;
   if (rk->solver_q) gg_solver_destroy(rk->solver_q);
   if (rk->Mq) gg_csr_destroy(rk->Mq);
   if (rk->pq) gg_vec_destroy(rk->pq);

@@ -262,6 +262,11 @@ int gg_rk_step(gg_rk* rk, int32_t n_steps);
  * at x first and q0 aliases q. */
 int gg_rk_residual(gg_rk* rk, const double* x, double* r);
 int gg_rk_stats(gg_rk* rk, int64_t* pcg_iters_total, int64_t* solves_total);
+/* measurement hook: time (ns, summed over all solves so far) the matrix-free PCG of mass solver `which` (0: RT mass,
+ * 1: potential-vorticity mass) spent in its three phases -- out[0] cell-wise operator application, out[1] DOF gather +
+ * dot product, out[2] vector updates + block preconditioner -- and out[3] the iterations they cover (read with
+ * %globaltimer inside the persistent kernel).  Zeros when that solver runs on the assembled matrix. */
+int gg_rk_solver_phase_ns(gg_rk* rk, int which, double* out);
 /* shallow water: sizes of the diagnostic blocks y = [q; F; Phi] */
 int gg_rk_diag_info(gg_rk* rk, int64_t* n_q, int64_t* n_F, int64_t* n_Phi);
 /* diagnostics of the last solve (after gg_rk_step: those of the final state), host out [n_q + n_F + n_Phi] */
