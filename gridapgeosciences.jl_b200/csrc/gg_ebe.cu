@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 #include "gg_common.cuh"
 #include "gg_ebe.cuh"
+#include "gg_refel.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -94,6 +95,135 @@ k_ebe_condense(int64_t nc, const double* __restrict__ ebuf, double* __restrict__
   }
 }
 
+// ---- fused element matrix + condensation for the scalar mass with a coefficient ----------------------------------------
+// M_IJ = int coef phi_I phi_J sqrtg on Q_P (the state-dependent block of jac_y, test/Transient/TransientShallowWater.jl:122,
+// re-evaluated before every diagnostic solve).  One thread per cell, sum-factorised: with I = (i1,i2), J = (j1,j2) the entry
+// only depends on the unordered pairs {i1,j1}, {i2,j2}:
+//   B[q1][s2] = sum_q2 c(q1,q2) NN[s2][q2],   A[s1][s2] = sum_q1 NN[s1][q1] B[q1][s2],   NN[s][q] = N_i(x_q) N_j(x_q)
+// (NS^2 = 100 accumulators for Q_3 instead of 136 packed entries x 49 points), then the cell-private interior nodes are
+// eliminated in registers and only the condensed S_c, T_c and M_ii^-1 are written (entry-major, coalesced).
+__constant__ double c_ebe_nn[MAX_NQ * 10];  // [q][s], s = packed (i <= j) pair of 1-D basis functions
+__constant__ double c_ebe_w[MAX_NQ];
+
+__host__ __device__ constexpr int q_loc2lex(int P, int a) {
+  // Gridap local node order of Q_P on the square -> lexicographic ix + (P+1) iy (same as quad_local_to_lex)
+  const int nb = P + 1, ne = P - 1;
+  if (a == 0) return 0;
+  if (a == 1) return P;
+  if (a == 2) return nb * P;
+  if (a == 3) return P + nb * P;
+  int e = a - 4;
+  if (e < ne) return e + 1;
+  e -= ne;
+  if (e < ne) return e + 1 + nb * P;
+  e -= ne;
+  if (e < ne) return nb * (e + 1);
+  e -= ne;
+  if (e < ne) return P + nb * (e + 1);
+  e -= ne;
+  return (e % ne + 1) + nb * (e / ne + 1);
+}
+
+template <int P>
+__global__ void __launch_bounds__(64)
+k_ebe_scalar_mass(int64_t nc, int nq, CellGeo g, const double* __restrict__ coef, double* __restrict__ S,
+                  double* __restrict__ T, double* __restrict__ W) {
+  constexpr int NB = P + 1, NS = NB * (NB + 1) / 2, MB = 4 * P, MI = (P - 1) * (P - 1);
+  constexpr int MIa = MI > 0 ? MI : 1;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double HX = g.hx[c], HY = g.hy[c];
+  const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * nq;
+  const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * nq;
+  const double* __restrict__ cf = coef + c * (int64_t)(nq * nq);
+  const double scale = g.radius * g.radius * HX * HY;
+  double acc[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; ++k) acc[k] = 0.0;
+#pragma unroll 1
+  for (int q1 = 0; q1 < nq; ++q1) {
+    const double t = ta[q1], sa = fma(t, t, 1.0), w1 = c_ebe_w[q1] * scale * sa;
+    double B[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) B[k] = 0.0;
+#pragma unroll 1
+    for (int q2 = 0; q2 < nq; ++q2) {
+      const double b = tb[q2], sb = fma(b, b, 1.0);
+      double ri;
+      {
+        const double x = sa + b * b;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ri) : "d"(x));
+        const double e = fma(x, -(ri * ri), 1.0);
+        ri = fma(fma(e, 0.375, 0.5), ri * e, ri);
+      }
+      const double cq = w1 * c_ebe_w[q2] * sb * ri * ri * ri * cf[q1 + nq * q2];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) B[k] = fma(cq, c_ebe_nn[q2 * NS + k], B[k]);
+    }
+#pragma unroll
+    for (int s1 = 0; s1 < NS; ++s1) {
+      const double n1 = c_ebe_nn[q1 * NS + s1];
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) acc[s1 * NS + s2] = fma(n1, B[s2], acc[s1 * NS + s2]);
+    }
+  }
+  // element matrix entry of local DOFs (I, J)
+  auto E = [&](int I, int J) -> double {
+    const int li = q_loc2lex(P, I), lj = q_loc2lex(P, J);
+    const int i1 = li % NB, i2 = li / NB, j1 = lj % NB, j2 = lj / NB;
+    const int a1 = i1 < j1 ? i1 : j1, b1 = i1 < j1 ? j1 : i1, a2 = i2 < j2 ? i2 : j2, b2 = i2 < j2 ? j2 : i2;
+    return acc[ebe_sym(NB, a1, b1) * NS + ebe_sym(NB, a2, b2)];
+  };
+  if (MI == 0) {
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+      for (int j = i; j < MB; ++j) S[(int64_t)ebe_sym(MB, i, j) * nc + c] = E(i, j);
+    return;
+  }
+  double a[MIa][MIa], w[MIa][MIa];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < MI; ++j) { a[i][j] = E(MB + i, MB + j); w[i][j] = i == j ? 1.0 : 0.0; }
+#pragma unroll
+  for (int k = 0; k < MI; ++k) {
+    const double d = 1.0 / a[k][k];
+#pragma unroll
+    for (int j = 0; j < MI; ++j) { a[k][j] *= d; w[k][j] *= d; }
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+#pragma unroll
+      for (int j = 0; j < MI; ++j) { a[i][j] = fma(-f, a[k][j], a[i][j]); w[i][j] = fma(-f, w[k][j], w[i][j]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = i; j < MI; ++j) W[(int64_t)ebe_sym(MI, i, j) * nc + c] = 0.5 * (w[i][j] + w[j][i]);
+#pragma unroll
+  for (int j = 0; j < MB; ++j) {
+    double tcol[MIa];
+#pragma unroll
+    for (int r = 0; r < MI; ++r) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < MI; ++q) v = fma(w[r][q], E(MB + q, j), v);
+      tcol[r] = v;
+      T[(int64_t)(r * MB + j) * nc + c] = v;
+    }
+#pragma unroll
+    for (int i = 0; i <= j; ++i) {
+      double v = E(i, j);
+#pragma unroll
+      for (int r = 0; r < MI; ++r) v = fma(-E(i, MB + r), tcol[r], v);
+      S[(int64_t)ebe_sym(MB, i, j) * nc + c] = v;
+    }
+  }
+}
+
 // ---- block-Jacobi of the (never assembled) condensed matrix -----------------------------------------------------------
 // one thread per boundary DOF row: bmat[rowoff[d] + b] = sum over the cells around d of S_c[local(d)][local(bstart + b)]
 __global__ void k_ebe_block_rows(int64_t nb, int64_t nc, int mloc, int MB, const int32_t* __restrict__ vptr,
@@ -161,6 +291,7 @@ struct EbeArgs {
   double *x, *ra, *rb, *z, *p, *Ap, *partials;
   double rtol;
   int max_iter;
+  int warm;  // start from the content of x instead of 0
   double* stats;
 };
 
@@ -237,35 +368,66 @@ k_pcg_ebe(const EbeArgs a) {
     }
     grid.sync();
   }
+  double lbb = 0.0;
   for (int64_t i = tid; i < n; i += nth) {
     double v = a.scale_b * a.b[i];
     if (MI > 0) v -= ebe_gather_row(a, i);
     r_old[i] = v;
+    lbb = fma(v, v, lbb);
+    if (!a.warm) a.x[i] = 0.0;
   }
+  lbb = ebe_block_sum(lbb, sh);
+  if (threadIdx.x == 0) P1[blockIdx.x] = lbb;
   grid.sync();
-  double lrz = 0.0, lbb = 0.0;
+  const double bb = ebe_grid_total(P1, nbk, sh);
+  if (a.warm) {
+    // initial guess = what the output vector holds (the solution of the previous stage / step): r = bt - S x
+    for (int64_t c = tid; c < nc; c += nth) {
+      double pe[MB], acc[MB];
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        const int32_t d = a.cell_dofs[c * a.mloc + j];
+        pe[j] = d >= 0 ? a.x[d] : 0.0;
+        acc[j] = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = i; j < MB; ++j) {
+          const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
+          acc[i] = fma(sv, pe[j], acc[i]);
+          if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
+    }
+    grid.sync();
+    for (int64_t i = tid; i < n; i += nth) r_old[i] -= ebe_gather_row(a, i);
+    grid.sync();
+  }
+  double lrz = 0.0, lrr0 = 0.0;
   for (int64_t i = tid; i < n; i += nth) {
     const int s = a.bstart[i], m = a.bsize[i];
     const double* bi_row = a.binv + a.rowoff[i];
     double zi = 0.0;
     for (int j = 0; j < m; ++j) zi = fma(bi_row[j], r_old[s + j], zi);
     const double ri = r_old[i];
-    a.x[i] = 0.0; a.z[i] = zi; a.p[i] = 0.0;
+    a.z[i] = zi; a.p[i] = 0.0;
     lrz = fma(ri, zi, lrz);
-    lbb = fma(ri, ri, lbb);
+    lrr0 = fma(ri, ri, lrr0);
   }
   lrz = ebe_block_sum(lrz, sh);
-  lbb = ebe_block_sum(lbb, sh);
-  if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; }
+  lrr0 = ebe_block_sum(lrr0, sh);
+  if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P2[blockIdx.x] = lrr0; }
   grid.sync();
   double rz = ebe_grid_total(P0, nbk, sh);
-  const double bb = ebe_grid_total(P1, nbk, sh);
   int it = 0;
-  double rr = bb;
+  double rr = ebe_grid_total(P2, nbk, sh);
   double beta = 0.0;
   unsigned long long tA = 0, tB = 0, tC = 0;
-  if (bb > 0.0) {
-    const double tol2 = a.rtol * a.rtol * bb;
+  grid.sync();  // P2 is reused by the first iteration
+  const double tol2 = a.rtol * a.rtol * bb;
+  if (bb > 0.0 && rr > tol2) {
     for (it = 1; it <= a.max_iter; ++it) {
       // -- A: element vectors of S p with p = z + beta p_old formed on the fly
       unsigned long long t0 = ebe_now();
@@ -401,6 +563,8 @@ k_pcg_ebe(const EbeArgs a) {
   }
 }
 
+static void ebe_build_precond(EbeSolver* s);
+
 template <int MB, int MI>
 static void ebe_launch_condense(gg_ctx* ctx, int64_t nc, const double* ebuf, double* S, double* T, double* W) {
   k_ebe_condense<MB, MI><<<nblk(nc, 64), 64, 0, ctx->stream>>>(nc, ebuf, S, T, W);
@@ -499,19 +663,65 @@ void ebe_set_matrix(EbeSolver* s, const double* ebuf) {
 #undef X
     ctx->launches++;
   }
-  if (s->nb) {
-    ProfScope ps(ctx, "k_ebe_precond");
-    k_ebe_block_rows<<<nblk(s->nb, 128), 128, 0, ctx->stream>>>(s->nb, s->nc, sp->ndofs_loc, s->MB, sp->d_vptr.p, sp->d_vsrc.p,
-                                                                sp->d_cell_dofs.p, s->bstart.p, s->bsize.p, s->rowoff.p, s->S.p,
-                                                                s->binv.p);
-    k_ebe_block_inverse<<<nblk(s->n_blocks, 128), 128, 0, ctx->stream>>>(s->n_blocks, s->blk_off.p, s->blk_size.p, s->binv.p);
-    ctx->launches += 2;
-  }
+  GG_CUDA(cudaGetLastError());
+  ebe_build_precond(s);
+}
+
+static void ebe_build_precond(EbeSolver* s) {
+  gg_ctx* ctx = s->ctx;
+  gg_space* sp = s->sp;
+  if (s->nb == 0) return;
+  ProfScope ps(ctx, "k_ebe_precond");
+  k_ebe_block_rows<<<nblk(s->nb, 128), 128, 0, ctx->stream>>>(s->nb, s->nc, sp->ndofs_loc, s->MB, sp->d_vptr.p, sp->d_vsrc.p,
+                                                              sp->d_cell_dofs.p, s->bstart.p, s->bsize.p, s->rowoff.p, s->S.p,
+                                                              s->binv.p);
+  k_ebe_block_inverse<<<nblk(s->n_blocks, 128), 128, 0, ctx->stream>>>(s->n_blocks, s->blk_off.p, s->blk_size.p, s->binv.p);
+  ctx->launches += 2;
   GG_CUDA(cudaGetLastError());
 }
 
+// numerical_setup! for the scalar mass int coef q w sqrtg on a CG_P space: element matrices, condensation and preconditioner
+// in one pass, coef given at the quadrature points [n_cells][Q] (x-fastest inside the cell) or NULL (= 1)
+void ebe_set_scalar_mass(EbeSolver* s, int degree, const double* coef) {
+  gg_ctx* ctx = s->ctx;
+  gg_space* sp = s->sp;
+  GG_REQUIRE(sp->kind == GG_SPACE_CG && sp->order >= 1 && sp->order <= 3, GG_ERR_UNSUPPORTED, "fused scalar mass needs CG_1..3");
+  GG_REQUIRE(coef, GG_ERR_INVALID, "coefficient at the quadrature points is required");
+  if (s->nc == 0) return;
+  const int nq = num_points_1d(degree), P = sp->order, NB = P + 1, NS = NB * (NB + 1) / 2;
+  GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
+  const int64_t key = ((int64_t)P << 8) | nq;
+  if (ctx->ebe_key != key) {
+    std::vector<double> xi(nq), w(nq), nn((size_t)nq * NS), N(NB), D(NB);
+    gauss_legendre_01(nq, xi.data(), w.data());
+    for (int q = 0; q < nq; ++q) {
+      lagrange_1d(P, xi[q], N.data(), D.data());
+      int k = 0;
+      for (int i = 0; i < NB; ++i)
+        for (int j = i; j < NB; ++j) nn[(size_t)q * NS + k++] = N[i] * N[j];
+    }
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old tables
+    GG_CUDA(cudaMemcpyToSymbol(c_ebe_w, w.data(), nq * sizeof(double)));
+    GG_CUDA(cudaMemcpyToSymbol(c_ebe_nn, nn.data(), nn.size() * sizeof(double)));
+    ctx->ebe_key = key;
+  }
+  CellGeo g = cell_geo(sp->mesh, nq);
+  {
+    ProfScope ps(ctx, "k_ebe_scalar_mass");
+    unsigned nb = nblk(s->nc, 64);
+    switch (P) {
+      case 1: k_ebe_scalar_mass<1><<<nb, 64, 0, ctx->stream>>>(s->nc, nq, g, coef, s->S.p, s->T.p, s->W.p); break;
+      case 2: k_ebe_scalar_mass<2><<<nb, 64, 0, ctx->stream>>>(s->nc, nq, g, coef, s->S.p, s->T.p, s->W.p); break;
+      case 3: k_ebe_scalar_mass<3><<<nb, 64, 0, ctx->stream>>>(s->nc, nq, g, coef, s->S.p, s->T.p, s->W.p); break;
+    }
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+  ebe_build_precond(s);
+}
+
 // enqueue x = A^-1 (scale_b b), x and b over ALL free DOFs of the space (boundary first, then interior); no host sync
-void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x) {
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm) {
   gg_ctx* ctx = s->ctx;
   gg_space* sp = s->sp;
   if (sp->n_free == 0) return;
@@ -522,6 +732,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x) {
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;
+  a.warm = warm ? 1 : 0;
   void* fn = ebe_kernel(s->MB, s->MI);
   int grid = s->grid;
   const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;

@@ -24,7 +24,9 @@ struct EbeSolver {
 bool ebe_supported(const gg_space* sp);
 EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter);
 void ebe_set_matrix(EbeSolver* s, const double* ebuf_full);
-void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x);
+void ebe_set_scalar_mass(EbeSolver* s, int degree, const double* coef);
+// warm: use the content of x as the initial guess (convergence is still measured against the right-hand side norm)
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm = false);
 void ebe_destroy(EbeSolver* s);
 
 }  // namespace gg

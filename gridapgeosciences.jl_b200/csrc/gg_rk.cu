@@ -138,7 +138,7 @@ void rk_accumulate_stats(gg_rk* rk, const double* solver_stats) {
 void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x) {
   EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
   if (e) {
-    ebe_solve_async(e, b, scale, x);
+    ebe_solve_async(e, b, scale, x, rk->warm_start);
     rk_accumulate_stats(rk, e->stats.p);
   } else {
     gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
@@ -285,6 +285,10 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   // mass solver: GG_PCG = ebe (default: statically condensed element-by-element), mf (matrix-free re-integration), csr
   const char* mode_env = getenv("GG_PCG");
   const std::string mode = mode_env ? mode_env : "ebe";
+  // every mass solve starts from the previous solution held by its output vector (the same stage of the previous step,
+  // or the previous diagnostics) unless GG_WARM_START=0
+  const char* ws = getenv("GG_WARM_START");
+  rk->warm_start = !(ws && ws[0] == '0');
   if (mode == "ebe" && ebe_supported(rk->V)) {
     rk->ebe_u = ebe_create(rk->V, a->rtol > 0 ? a->rtol : 1e-12, 2000);
     int layout = 0;
@@ -346,6 +350,7 @@ int gg_rk_set_state(gg_rk* rk, const double* x) {
   GG_CUDA(cudaSetDevice(rk->ctx->device));
   int64_t n = rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
+  rk->y_valid = false;
   GG_CUDA(cudaStreamSynchronize(rk->ctx->stream));
   GG_API_END
 }
@@ -376,6 +381,7 @@ int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
   int64_t n = rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
   if (rk->problem == GG_PROBLEM_SHALLOW_WATER) {
+    rk->y_valid = false;
     swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
     swe_residual_async(rk, rk->xi.p, rk->y.p, rk->y.p, rk->r.p, nullptr);
   } else {
@@ -401,6 +407,7 @@ int gg_rk_diagnostics(gg_rk* rk, const double* x, double* y) {
   GG_CUDA(cudaSetDevice(rk->ctx->device));
   int64_t n = rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
+  rk->y_valid = false;
   swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
   rk->y.download(y, rk->ctx->stream);
   GG_API_END
@@ -414,6 +421,7 @@ int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double
   cudaStream_t st = rk->ctx->stream;
   int64_t n = rk->nu + rk->np, ny = rk->nr + rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  rk->y_valid = false;
   if (ny) GG_CUDA(cudaMemcpyAsync(rk->y.p, y, ny * sizeof(double), cudaMemcpyHostToDevice, st));
   if (rk->nr) GG_CUDA(cudaMemcpyAsync(rk->q0.p, q0, rk->nr * sizeof(double), cudaMemcpyHostToDevice, st));
   swe_residual_async(rk, rk->xi.p, rk->y.p, rk->q0.p, rk->r.p, nullptr);

@@ -16,6 +16,7 @@ struct gg_rk {
   std::vector<double> A, b, c;
   double dt = 0.0;
   int64_t nu = 0, np = 0;
+  bool warm_start = true;               // mass solves start from the previous content of their output vector
   gg::DevBuf<double> x, xi, r, MpInv, Bhat;
   std::vector<gg::DevBuf<double>> k;
   gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
@@ -33,7 +34,9 @@ struct gg_rk {
   gg::DevBuf<double> fq, bq;      // Coriolis parameter / topography at the quadrature points
   gg::DevBuf<double> rhs_q, rhs_F;
   gg::DevBuf<double> evec_q, evec_u;  // entry-major element-vector scratch
+  gg::DevBuf<double> stage2;          // [point][component][cell] coefficient staging of the cell kernels (large rules only)
   int64_t diag_solves = 0;
+  bool y_valid = false;           // y == diagnostics(x) (lets a step reuse the final diagnostics of the previous one)
 };
 
 namespace gg {

@@ -33,6 +33,15 @@ namespace gg {
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// Basis tabulations of the resident (order, nq) pair in __constant__ memory (warp-uniform operands: no L1 traffic).
+// Sized for RT_2 / DG_2 / CG_3 at 7x7 points (41 KB); larger rules fall back to the same tables in global memory.
+constexpr int SWE_MAXQ = 49;
+__constant__ double c_swe_w[MAX_NQ];
+__constant__ double c_swe_rt[SWE_MAXQ * 24 * 2];  // [Q][MU][2] reference RT basis
+__constant__ double c_swe_dg[SWE_MAXQ * 9];       // [Q][MP]
+__constant__ double c_swe_cg[SWE_MAXQ * 16];      // [Q][MR]
+__constant__ double c_swe_cgd[SWE_MAXQ * 16 * 2]; // [Q][MR][2] reference gradients
+
 struct SweTabs {
   const double* w;       // 1-D quadrature weights [nq]
   const double* rt_val;  // [Q][MU][2] reference RT basis
@@ -41,6 +50,21 @@ struct SweTabs {
   const double* cg_der;  // [Q][MR][2] reference gradients
 };
 
+// table accessors: CONST selects the __constant__ copies
+template <bool CONST> __device__ __forceinline__ const double* tab_w(const SweTabs& T) { return CONST ? c_swe_w : T.w; }
+template <bool CONST> __device__ __forceinline__ const double* tab_rt(const SweTabs& T) { return CONST ? c_swe_rt : T.rt_val; }
+template <bool CONST> __device__ __forceinline__ const double* tab_dg(const SweTabs& T) { return CONST ? c_swe_dg : T.dg_val; }
+template <bool CONST> __device__ __forceinline__ const double* tab_cg(const SweTabs& T) { return CONST ? c_swe_cg : T.cg_val; }
+template <bool CONST> __device__ __forceinline__ const double* tab_cgd(const SweTabs& T) { return CONST ? c_swe_cgd : T.cg_der; }
+
+// 1/sqrt(x), x in [1,3]: hardware seed + one cubic step (< 1 ulp)
+__device__ __forceinline__ double swe_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x, -(y * y), 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
 // sqrt(det g) = r^2 sa sb / rho^3 (src/CellData/CellFields.jl:80-82 evaluated in closed form)
 __device__ __forceinline__ double csphere_sqrtg(double a, double b, double r) {
   const double sa = fma(a, a, 1.0), sb = fma(b, b, 1.0);
@@ -48,107 +72,192 @@ __device__ __forceinline__ double csphere_sqrtg(double a, double b, double r) {
   return r * r * sa * sb / (rho2 * sqrt(rho2));
 }
 
+// Both cell kernels run one thread per cell in two passes over the quadrature points so that the live register state
+// stays below the 255-register limit for RT_2 / CG_3: pass 1 interpolates the fields and stages two coefficients per
+// point (the chart-space vector that multiplies the RT test functions) in shared memory, laid out [point][component]
+// [thread] (conflict-free); pass 2 only accumulates the RT element vector.  Rules with more than 7x7 points stage the
+// coefficients in a global scratch instead ([point][component][cell], coalesced).
+struct Stage2 {
+  double* base;    // this thread's column
+  int64_t stride;  // distance between consecutive (point, component) slots
+  __device__ __forceinline__ double& at(int q, int comp) { return base[(int64_t)(2 * q + comp) * stride]; }
+};
+__device__ __forceinline__ Stage2 stage2_of(double* gscratch, int64_t nc, int64_t c) {
+  extern __shared__ double swe_smem[];
+  Stage2 s;
+  if (gscratch) { s.base = gscratch + c; s.stride = nc; }
+  else { s.base = swe_smem + threadIdx.x; s.stride = blockDim.x; }
+  return s;
+}
+
 // Right-hand sides of the three diagnostic equations, one thread per cell.
 //   pq_out [c*Q+q]      depth at the quadrature points (coefficient of the q mass matrix)
 //   eq [MR][nc], eF [MU][nc]  entry-major element vectors of the q and F equations
 //   Phi [c*MP+i]        Bernoulli potential (DG mass block inverted in place)
-template <int K>
+template <int K, bool CONST>
 __global__ void __launch_bounds__(64)
 k_swe_diag(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
            const double* __restrict__ u, const double* __restrict__ p, const double* __restrict__ fq,
            const double* __restrict__ bq, double gravity, const double* __restrict__ MpInv, double* __restrict__ pq_out,
-           double* __restrict__ eq, double* __restrict__ eF, double* __restrict__ Phi) {
+           double* __restrict__ eq, double* __restrict__ eF, double* __restrict__ Phi, double* __restrict__ gscratch) {
   constexpr int MU = 2 * (K + 1) * (K + 2), MP = (K + 1) * (K + 1), MR = (K + 2) * (K + 2);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  Stage2 st = stage2_of(gscratch, nc, c);
   const double HX = g.hx[c], HY = g.hy[c], iHX = 1.0 / HX, iHY = 1.0 / HY;
   const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * nq;
   const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * nq;
-  double ue[MU], pe[MP], aq[MR], aF[MU], aP[MP];
-#pragma unroll
-  for (int j = 0; j < MU; ++j) { ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]]; aF[j] = 0.0; }
-#pragma unroll
-  for (int i = 0; i < MP; ++i) { pe[i] = p[c * MP + i]; aP[i] = 0.0; }
-#pragma unroll
-  for (int i = 0; i < MR; ++i) aq[i] = 0.0;
   const int Q = nq * nq;
+  const double r2 = g.radius * g.radius;
+  const double* __restrict__ tw = tab_w<CONST>(T);
+  {
+    double ue[MU], pe[MP], aq[MR], aP[MP];
+#pragma unroll
+    for (int j = 0; j < MU; ++j) ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) { pe[i] = p[c * MP + i]; aP[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < MR; ++i) aq[i] = 0.0;
 #pragma unroll 1
-  for (int q2 = 0; q2 < nq; ++q2) {
-    const double b = tb[q2];
+    for (int q2 = 0; q2 < nq; ++q2) {
+      const double b = tb[q2], sb = fma(b, b, 1.0);
 #pragma unroll 1
-    for (int q1 = 0; q1 < nq; ++q1) {
-      const int q = q1 + nq * q2;
-      const Metric2 m = csphere_metric_terms(ta[q1], b, g.radius);
-      const double* __restrict__ rv = T.rt_val + (size_t)q * MU * 2;
-      double Ux = 0.0, Uy = 0.0;
+      for (int q1 = 0; q1 < nq; ++q1) {
+        const int q = q1 + nq * q2;
+        // metric from one rsqrt: sqrtg = r^2 sa sb / rho^3, g / sqrtg = [[sa, -ab], [-ab, sb]] / rho,
+        // ginv sqrtg = [[sb, ab], [ab, sa]] / rho
+        const double t = ta[q1], sa = fma(t, t, 1.0), ab = t * b;
+        const double ri = swe_rsqrt(sa + b * b);
+        const double sqrtg = r2 * sa * sb * ri * ri * ri;
+        const double* __restrict__ rv = tab_rt<CONST>(T) + (size_t)q * MU * 2;
+        double Uxp[2] = {0.0, 0.0}, Uyp[2] = {0.0, 0.0};
 #pragma unroll
-      for (int j = 0; j < MU; ++j) { Ux = fma(rv[2 * j], ue[j], Ux); Uy = fma(rv[2 * j + 1], ue[j], Uy); }
-      const double ux = Ux * iHY, uy = Uy * iHX;  // contravariant Piola on an axis-aligned cell
-      const double* __restrict__ dv = T.dg_val + (size_t)q * MP;
-      double ph = 0.0;
+        for (int j = 0; j < MU; ++j) { Uxp[j & 1] = fma(rv[2 * j], ue[j], Uxp[j & 1]); Uyp[j & 1] = fma(rv[2 * j + 1], ue[j], Uyp[j & 1]); }
+        const double ux = (Uxp[0] + Uxp[1]) * iHY, uy = (Uyp[0] + Uyp[1]) * iHX;  // contravariant Piola, axis-aligned cell
+        const double* __restrict__ dv = tab_dg<CONST>(T) + (size_t)q * MP;
+        double ph = 0.0;
 #pragma unroll
-      for (int i = 0; i < MP; ++i) ph = fma(dv[i], pe[i], ph);
-      pq_out[c * Q + q] = ph;
-      const double wq = T.w[q1] * T.w[q2] * HX * HY;
-      // vorticity equation: f w + ((R u).ginv).grad(w), R u = (-u_y, u_x)
-      {
-        const double cq = wq * m.sqrtg;
-        const double f0 = cq * fq[c * Q + q];
-        const double fx = cq * (-uy * m.i11 + ux * m.i12) * iHX, fy = cq * (-uy * m.i12 + ux * m.i22) * iHY;
-        const double* __restrict__ cv = T.cg_val + (size_t)q * MR;
-        const double* __restrict__ cd = T.cg_der + (size_t)q * MR * 2;
+        for (int i = 0; i < MP; ++i) ph = fma(dv[i], pe[i], ph);
+        pq_out[c * Q + q] = ph;
+        const double wq = tw[q1] * tw[q2] * HX * HY;
+        const double wr = wq * ri;
+        // vorticity equation: f w sqrtg + ((R u).ginv).grad(w) sqrtg, R u = (-u_y, u_x)
+        {
+          const double f0 = wq * sqrtg * fq[c * Q + q];
+          const double fx = wr * (ux * ab - uy * sb) * iHX, fy = wr * (ux * sa - uy * ab) * iHY;
+          const double* __restrict__ cv = tab_cg<CONST>(T) + (size_t)q * MR;
+          const double* __restrict__ cd = tab_cgd<CONST>(T) + (size_t)q * MR * 2;
 #pragma unroll
-        for (int i = 0; i < MR; ++i) aq[i] = fma(f0, cv[i], fma(fx, cd[2 * i], fma(fy, cd[2 * i + 1], aq[i])));
-      }
-      // mass flux: p u.(g v)/sqrtg
-      const double gux = m.g11 * ux + m.g12 * uy, guy = m.g12 * ux + m.g22 * uy;
-      {
-        const double cF = wq * ph / m.sqrtg;
-        const double fx = cF * gux * iHY, fy = cF * guy * iHX;
+          for (int i = 0; i < MR; ++i) aq[i] = fma(f0, cv[i], fma(fx, cd[2 * i], fma(fy, cd[2 * i + 1], aq[i])));
+        }
+        // mass flux p u.(g v)/sqrtg, (g u)/sqrtg = (sa ux - ab uy, sb uy - ab ux) / rho: staged for pass 2
+        const double gux = sa * ux - ab * uy, guy = sb * uy - ab * ux;
+        st.at(q, 0) = wr * ph * gux * iHY;
+        st.at(q, 1) = wr * ph * guy * iHX;
+        // Bernoulli potential: g_r (p + b) sqrtg + 1/2 u.(g u)/sqrtg
+        {
+          const double bt = bq ? bq[c * Q + q] : 0.0;
+          const double cP = wq * (gravity * (ph + bt) * sqrtg + 0.5 * ri * (ux * gux + uy * guy));
 #pragma unroll
-        for (int j = 0; j < MU; ++j) aF[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], aF[j]));
-      }
-      // Bernoulli potential: g_r (p + b) sqrtg + 1/2 u.(g u)/sqrtg
-      {
-        const double bt = bq ? bq[c * Q + q] : 0.0;
-        const double cP = wq * (gravity * (ph + bt) * m.sqrtg + 0.5 * (ux * gux + uy * guy) / m.sqrtg);
-#pragma unroll
-        for (int i = 0; i < MP; ++i) aP[i] = fma(cP, dv[i], aP[i]);
+          for (int i = 0; i < MP; ++i) aP[i] = fma(cP, dv[i], aP[i]);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < MR; ++i) eq[(int64_t)i * nc + c] = aq[i];
+    for (int i = 0; i < MR; ++i) eq[(int64_t)i * nc + c] = aq[i];
+#pragma unroll
+    for (int i = 0; i < MP; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < MP; ++j) acc = fma(MpInv[(int64_t)(i * MP + j) * nc + c], aP[j], acc);
+      Phi[c * MP + i] = acc;
+    }
+  }
+  // pass 2: RT element vector of the mass-flux equation
+  double aF[MU];
+#pragma unroll
+  for (int j = 0; j < MU; ++j) aF[j] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < Q; ++q) {
+    const double* __restrict__ rv = tab_rt<CONST>(T) + (size_t)q * MU * 2;
+    const double fx = st.at(q, 0), fy = st.at(q, 1);
+#pragma unroll
+    for (int j = 0; j < MU; ++j) aF[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], aF[j]));
+  }
 #pragma unroll
   for (int j = 0; j < MU; ++j) eF[(int64_t)j * nc + c] = (double)vsigns[c * MU + j] * aF[j];
-#pragma unroll
-  for (int i = 0; i < MP; ++i) {
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < MP; ++j) acc = fma(MpInv[(int64_t)(i * MP + j) * nc + c], aP[j], acc);
-    Phi[c * MP + i] = acc;
-  }
 }
 
 // Stage residual, one thread per cell.  eru [MU][nc] entry-major element vector of r_u; rp [c*MP+i] = r_p (DG, cell
 // local); kp (optional) = -Mp^-1 r_p, the depth slope.
-template <int K, bool ALIAS>
+template <int K, bool ALIAS, bool CONST>
 __global__ void __launch_bounds__(64)
 k_swe_stage(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
             const int32_t* __restrict__ rdofs, const double* __restrict__ u, const double* __restrict__ qv,
             const double* __restrict__ q0v, const double* __restrict__ Fv, const double* __restrict__ Phi,
             const double* __restrict__ Bhat, const double* __restrict__ MpInv, double tau, double tau_over_dt,
-            double* __restrict__ eru, double* __restrict__ rp, double* __restrict__ kp) {
+            double* __restrict__ eru, double* __restrict__ rp, double* __restrict__ kp, double* __restrict__ gscratch) {
   constexpr int MU = 2 * (K + 1) * (K + 2), MP = (K + 1) * (K + 1), MR = (K + 2) * (K + 2);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  Stage2 st = stage2_of(gscratch, nc, c);
   const double HX = g.hx[c], HY = g.hy[c], iHX = 1.0 / HX, iHY = 1.0 / HY;
   const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * nq;
   const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * nq;
-  double Fe[MU], ru[MU];
+  const int Q = nq * nq;
+  double Fe[MU];
 #pragma unroll
   for (int j = 0; j < MU; ++j) Fe[j] = (double)vsigns[c * MU + j] * Fv[vdofs[c * MU + j]];
+  // pass 1: coefficient of (R F).v at every point
+  {
+    double ue[MU], qe[MR], qc[ALIAS ? 1 : MR];
+#pragma unroll
+    for (int j = 0; j < MU; ++j) ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]];
+#pragma unroll
+    for (int i = 0; i < MR; ++i) {
+      const int32_t d = rdofs[c * MR + i];
+      qe[i] = qv[d];
+      // q - tau (q - q0)/dt = (1 - tau/dt) q + (tau/dt) q0
+      if (!ALIAS) qc[i] = fma(tau_over_dt, q0v[d] - qe[i], qe[i]);
+    }
+    const double ir2 = 1.0 / (g.radius * g.radius);
+    const double* __restrict__ tw = tab_w<CONST>(T);
+#pragma unroll 1
+    for (int q2 = 0; q2 < nq; ++q2) {
+      const double b = tb[q2], isb = 1.0 / fma(b, b, 1.0);
+#pragma unroll 1
+      for (int q1 = 0; q1 < nq; ++q1) {
+        const int q = q1 + nq * q2;
+        // 1 / sqrtg = rho^3 / (r^2 sa sb)
+        const double t = ta[q1], sa = fma(t, t, 1.0), rho2 = sa + b * b;
+        const double isqrtg = ir2 * isb * rho2 * rho2 * swe_rsqrt(rho2) / sa;
+        const double* __restrict__ rv = tab_rt<CONST>(T) + (size_t)q * MU * 2;
+        double Ux = 0.0, Uy = 0.0, Fx = 0.0, Fy = 0.0;
+#pragma unroll
+        for (int j = 0; j < MU; ++j) {
+          Ux = fma(rv[2 * j], ue[j], Ux); Uy = fma(rv[2 * j + 1], ue[j], Uy);
+          Fx = fma(rv[2 * j], Fe[j], Fx); Fy = fma(rv[2 * j + 1], Fe[j], Fy);
+        }
+        const double* __restrict__ cv = tab_cg<CONST>(T) + (size_t)q * MR;
+        const double* __restrict__ cd = tab_cgd<CONST>(T) + (size_t)q * MR * 2;
+        double qq = 0.0, qx = 0.0, qy = 0.0;
+#pragma unroll
+        for (int i = 0; i < MR; ++i) {
+          qq = fma(cv[i], ALIAS ? qe[i] : qc[i], qq);
+          qx = fma(cd[2 * i], qe[i], qx);
+          qy = fma(cd[2 * i + 1], qe[i], qy);
+        }
+        // u.grad(q) in chart coordinates: (Ux/HY)(qx/HX) + (Uy/HX)(qy/HY)
+        const double ugq = (Ux * qx + Uy * qy) * iHX * iHY;
+        const double coef = tw[q1] * tw[q2] * HX * HY * (qq - tau * ugq * isqrtg);
+        // (R F).v_I with F = (Fx/HY, Fy/HX), v_I = (vx/HY, vy/HX): (-Fy/HX)(vx/HY) + (Fx/HY)(vy/HX)
+        st.at(q, 0) = -coef * Fy * iHX * iHY;
+        st.at(q, 1) = coef * Fx * iHX * iHY;
+      }
+    }
+  }
   // linear, constant-coefficient parts through the reference divergence matrix
+  double ru[MU];
   {
     double pe[MP], r[MP];
 #pragma unroll
@@ -176,47 +285,13 @@ k_swe_stage(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict_
       }
     }
   }
-  double ue[MU], qe[MR], qc[ALIAS ? 1 : MR];
-#pragma unroll
-  for (int j = 0; j < MU; ++j) ue[j] = (double)vsigns[c * MU + j] * u[vdofs[c * MU + j]];
-#pragma unroll
-  for (int i = 0; i < MR; ++i) {
-    const int32_t d = rdofs[c * MR + i];
-    qe[i] = qv[d];
-    // q - tau (q - q0)/dt = (1 - tau/dt) q + (tau/dt) q0
-    if (!ALIAS) qc[i] = fma(tau_over_dt, q0v[d] - qe[i], qe[i]);
-  }
+  // pass 2: RT element vector
 #pragma unroll 1
-  for (int q2 = 0; q2 < nq; ++q2) {
-    const double b = tb[q2];
-#pragma unroll 1
-    for (int q1 = 0; q1 < nq; ++q1) {
-      const int q = q1 + nq * q2;
-      const double sqrtg = csphere_sqrtg(ta[q1], b, g.radius);
-      const double* __restrict__ rv = T.rt_val + (size_t)q * MU * 2;
-      double Ux = 0.0, Uy = 0.0, Fx = 0.0, Fy = 0.0;
+  for (int q = 0; q < Q; ++q) {
+    const double* __restrict__ rv = tab_rt<CONST>(T) + (size_t)q * MU * 2;
+    const double fx = st.at(q, 0), fy = st.at(q, 1);
 #pragma unroll
-      for (int j = 0; j < MU; ++j) {
-        Ux = fma(rv[2 * j], ue[j], Ux); Uy = fma(rv[2 * j + 1], ue[j], Uy);
-        Fx = fma(rv[2 * j], Fe[j], Fx); Fy = fma(rv[2 * j + 1], Fe[j], Fy);
-      }
-      const double* __restrict__ cv = T.cg_val + (size_t)q * MR;
-      const double* __restrict__ cd = T.cg_der + (size_t)q * MR * 2;
-      double qq = 0.0, qx = 0.0, qy = 0.0;
-#pragma unroll
-      for (int i = 0; i < MR; ++i) {
-        qq = fma(cv[i], ALIAS ? qe[i] : qc[i], qq);
-        qx = fma(cd[2 * i], qe[i], qx);
-        qy = fma(cd[2 * i + 1], qe[i], qy);
-      }
-      // u.grad(q) in chart coordinates: (Ux/HY)(qx/HX) + (Uy/HX)(qy/HY)
-      const double ugq = (Ux * qx + Uy * qy) * iHX * iHY;
-      const double coef = T.w[q1] * T.w[q2] * HX * HY * (qq - tau * ugq / sqrtg);
-      // (R F).v_I with F = (Fx/HY, Fy/HX), v_I = (vx/HY, vy/HX): (-Fy/HX)(vx/HY) + (Fx/HY)(vy/HX)
-      const double fx = -coef * Fy * iHX * iHY, fy = coef * Fx * iHX * iHY;
-#pragma unroll
-      for (int j = 0; j < MU; ++j) ru[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], ru[j]));
-    }
+    for (int j = 0; j < MU; ++j) ru[j] = fma(fx, rv[2 * j], fma(fy, rv[2 * j + 1], ru[j]));
   }
 #pragma unroll
   for (int j = 0; j < MU; ++j) eru[(int64_t)j * nc + c] = (double)vsigns[c * MU + j] * ru[j];
@@ -227,13 +302,41 @@ __global__ void k_copy(int64_t n, const double* __restrict__ a, double* __restri
   if (i < n) b[i] = a[i];
 }
 
-static SweTabs swe_tabs(gg_rk* rk) {
+// dynamic shared memory of the two-pass cell kernels: 2 coefficients per point and thread; 0 = stage through global memory
+static size_t swe_stage_smem(gg_rk* rk, int threads) {
+  const size_t bytes = (size_t)2 * rk->nq1 * rk->nq1 * threads * sizeof(double);
+  if (bytes > 96 * 1024) {
+    if (rk->stage2.n == 0) rk->stage2.alloc((size_t)2 * rk->nq1 * rk->nq1 * std::max<int64_t>(rk->mesh->n_cells, 1));
+    return 0;
+  }
+  return bytes;
+}
+
+template <typename Kern, typename... Args>
+static void swe_launch(Kern kern, unsigned nb, size_t smem, cudaStream_t st, Args... args) {
+  if (smem > 48 * 1024) GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nb, 64, smem, st>>>(args...);
+}
+
+// global-memory tables; *use_const: the same tables are (made) resident in the __constant__ block
+static SweTabs swe_tabs(gg_rk* rk, bool* use_const) {
   gg_ctx* ctx = rk->ctx;
   auto trt = get_tab(ctx, GG_SPACE_RT, rk->order, rk->nq1);
   auto tdg = get_tab(ctx, GG_SPACE_DG, rk->order, rk->nq1);
   auto tcg = get_tab(ctx, GG_SPACE_CG, rk->order + 1, rk->nq1);
   SweTabs T;
   T.w = tdg->w.p; T.rt_val = trt->val.p; T.dg_val = tdg->val.p; T.cg_val = tcg->val.p; T.cg_der = tcg->der.p;
+  *use_const = rk->nq1 * rk->nq1 <= SWE_MAXQ;
+  const int64_t key = ((int64_t)rk->order << 8) | rk->nq1;
+  if (*use_const && ctx->swe_key != key) {
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old tables
+    GG_CUDA(cudaMemcpyToSymbol(c_swe_w, tdg->w.p, tdg->w.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    GG_CUDA(cudaMemcpyToSymbol(c_swe_rt, trt->val.p, trt->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    GG_CUDA(cudaMemcpyToSymbol(c_swe_dg, tdg->val.p, tdg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    GG_CUDA(cudaMemcpyToSymbol(c_swe_cg, tcg->val.p, tcg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    GG_CUDA(cudaMemcpyToSymbol(c_swe_cgd, tcg->der.p, tcg->der.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    ctx->swe_key = key;
+  }
   return T;
 }
 
@@ -244,20 +347,27 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   const int64_t nc = rk->mesh->n_cells;
   if (nc == 0) return;
   CellGeo g = cell_geo(rk->mesh, rk->nq1);
-  SweTabs T = swe_tabs(rk);
+  bool uc = false;
+  SweTabs T = swe_tabs(rk, &uc);
   double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
   const double *u = x, *p = x + rk->nu;
   unsigned nb = nblk(nc, 64);
   {
     ProfScope ps(ctx, "k_swe_diag");
+    const size_t smem = swe_stage_smem(rk, 64);
+    double* gs = smem ? nullptr : rk->stage2.p;
 #define GG_ARGS nc, rk->nq1, g, T, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, u, p, rk->fq.p, rk->bq.n ? rk->bq.p : nullptr, \
-                rk->gravity, rk->MpInv.p, rk->pq->d.p, rk->evec_q.p, rk->evec_u.p, yP
+                rk->gravity, rk->MpInv.p, rk->pq->d.p, rk->evec_q.p, rk->evec_u.p, yP, gs
+#define GG_CASE(K_)                                                 \
+  case K_:                                                          \
+    if (uc) swe_launch(k_swe_diag<K_, true>, nb, smem, st, GG_ARGS);       \
+    else swe_launch(k_swe_diag<K_, false>, nb, smem, st, GG_ARGS);         \
+    break;
     switch (rk->order) {
-      case 0: k_swe_diag<0><<<nb, 64, 0, st>>>(GG_ARGS); break;
-      case 1: k_swe_diag<1><<<nb, 64, 0, st>>>(GG_ARGS); break;
-      case 2: k_swe_diag<2><<<nb, 64, 0, st>>>(GG_ARGS); break;
+      GG_CASE(0) GG_CASE(1) GG_CASE(2)
       default: throw Error(GG_ERR_UNSUPPORTED, "shallow-water order must be <= 2");
     }
+#undef GG_CASE
 #undef GG_ARGS
     ctx->launches++;
     GG_CUDA(cudaGetLastError());
@@ -265,21 +375,19 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   // potential vorticity: assemble int q p w sqrtg (the Jacobian block that depends on the state), refresh the
   // preconditioner (numerical_setup!), solve
   {
-    if (rk->ebe_q || !rk->solver_q->mf_on) {
-      // the Jacobian block that depends on the state: element matrices of int q p w sqrtg, then numerical_setup!
-      // (condensation + preconditioner for the element-by-element solver, CSR fill + block inverses for the assembled one)
+    // the Jacobian block that depends on the state, int q p w sqrtg, then numerical_setup!
+    if (rk->ebe_q) {
+      // element matrices, static condensation and preconditioner in one fused pass (gg_ebe.cu)
+      ebe_set_scalar_mass(rk->ebe_q, rk->degree, rk->pq->d.p);
+    } else if (!rk->solver_q->mf_on) {
+      // assembled path: element matrices, atomic-free CSR fill, block inverses
       gg_form_args fa;
       std::memset(&fa, 0, sizeof(fa));
       fa.test = rk->R; fa.trial = rk->R; fa.degree = rk->degree; fa.qdata = rk->pq;
       int layout = 0;
       const double* eb = element_matrices_device(GG_FORM_MASS_SCALAR, &fa, &layout);
-      if (rk->ebe_q) {
-        GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
-        ebe_set_matrix(rk->ebe_q, eb);
-      } else {
-        gather_matrix(rk->Mq, layout, eb, 1.0, 0);
-        solver_update(rk->solver_q);
-      }
+      gather_matrix(rk->Mq, layout, eb, 1.0, 0);
+      solver_update(rk->solver_q);
     }
     gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
     rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq);
@@ -297,18 +405,23 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
   const int64_t nc = rk->mesh->n_cells;
   if (nc == 0) return;
   CellGeo g = cell_geo(rk->mesh, rk->nq1);
-  SweTabs T = swe_tabs(rk);
+  bool uc = false;
+  SweTabs T = swe_tabs(rk, &uc);
   const double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
   const bool alias = (q0 == yq);
   unsigned nb = nblk(nc, 64);
   {
     ProfScope ps(ctx, "k_swe_stage");
+    const size_t smem = swe_stage_smem(rk, 64);
+    double* gs = smem ? nullptr : rk->stage2.p;
 #define GG_ARGS nc, rk->nq1, g, T, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, rk->R->d_cell_dofs.p, x, yq, q0, yF, yP, \
-                rk->Bhat.p, rk->MpInv.p, rk->tau, rk->tau / rk->dt, rk->evec_u.p, r + rk->nu, kp
-#define GG_CASE(K_)                                                    \
-  case K_:                                                             \
-    if (alias) k_swe_stage<K_, true><<<nb, 64, 0, st>>>(GG_ARGS);      \
-    else k_swe_stage<K_, false><<<nb, 64, 0, st>>>(GG_ARGS);           \
+                rk->Bhat.p, rk->MpInv.p, rk->tau, rk->tau / rk->dt, rk->evec_u.p, r + rk->nu, kp, gs
+#define GG_CASE(K_)                                                                   \
+  case K_:                                                                            \
+    if (alias && uc) swe_launch(k_swe_stage<K_, true, true>, nb, smem, st, GG_ARGS);         \
+    else if (alias) swe_launch(k_swe_stage<K_, true, false>, nb, smem, st, GG_ARGS);         \
+    else if (uc) swe_launch(k_swe_stage<K_, false, true>, nb, smem, st, GG_ARGS);            \
+    else swe_launch(k_swe_stage<K_, false, false>, nb, smem, st, GG_ARGS);                   \
     break;
     switch (rk->order) {
       GG_CASE(0) GG_CASE(1) GG_CASE(2)
@@ -322,28 +435,31 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
   gather_vector(rk->V, rk->evec_u.p, r, 1.0, 0);
 }
 
-// one ode_march! (src/ODEs/RungeKuttaEX.jl:48-134)
+// one ode_march! (src/ODEs/RungeKuttaEX.jl:48-134).  The reference solves the diagnostics five times per SSPRK3 step; two of
+// those solves repeat an earlier one on the same state (the first stage starts from u0, :85-93 after :70-75, and the final
+// solve of a step, :125-127, is the initial one of the next), so their result is reused: identical numbers, 3 solves per step.
 void swe_step_async(gg_rk* rk) {
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
   const int s = rk->n_stages;
   // :70-75 initial diagnostics of the step
-  swe_diagnostics_async(rk, rk->x.p, rk->y.p);
+  if (!rk->y_valid) { swe_diagnostics_async(rk, rk->x.p, rk->y.p); rk->y_valid = true; }
   if (rk->q0_mode == GG_Q0_START_OF_STEP && rk->nr) {
     k_copy<<<nblk(rk->nr, 256), 256, 0, st>>>(rk->nr, rk->y.p, rk->q0.p);
     ctx->launches++;
   }
   for (int i = 0; i < s; ++i) {
     const double* xs = rk->x.p;
+    bool same_state = true;
+    double co[4] = {0, 0, 0, 0};
+    for (int j = 0; j < i && j < 4; ++j) { co[j] = rk->dt * rk->A[i * s + j]; same_state = same_state && co[j] == 0.0; }
     if (i > 0) {
       // :85-88 stage state
-      double co[4] = {0, 0, 0, 0};
-      for (int j = 0; j < i && j < 4; ++j) co[j] = rk->dt * rk->A[i * s + j];
       rk_combine(rk, std::min(i, 4), co, rk->xi.p);
       xs = rk->xi.p;
     }
-    // :91-93 stage diagnostics
-    swe_diagnostics_async(rk, xs, rk->y.p);
+    // :91-93 stage diagnostics (y still holds diagnostics(x) when the stage state is x itself)
+    if (!(same_state && rk->y_valid)) { swe_diagnostics_async(rk, xs, rk->y.p); rk->y_valid = false; }
     // :100-117 slope: M k = -(res_x + mass(0))
     const double* q0 = rk->q0_mode == GG_Q0_START_OF_STEP ? rk->q0.p : rk->y.p;
     swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu);
@@ -354,6 +470,7 @@ void swe_step_async(gg_rk* rk) {
   for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
   rk_combine(rk, std::min(s, 4), co, rk->x.p);
   swe_diagnostics_async(rk, rk->x.p, rk->y.p);
+  rk->y_valid = true;
   GG_CUDA(cudaGetLastError());
 }
 

@@ -61,7 +61,7 @@ def main():
     it0, so0 = st.stats()
     ctx.profile(True)
     st.step(args.steps)
-    names = ["k_swe_diag", "k_swe_stage", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs", "k_block_inverse", "k_pcg_persistent", "k_pcg_mf", "k_pcg_ebe", "k_ebe_condense", "k_ebe_precond"]
+    names = ["k_swe_diag", "k_swe_stage", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs", "k_block_inverse", "k_pcg_persistent", "k_pcg_mf", "k_pcg_ebe", "k_ebe_condense", "k_ebe_precond", "k_ebe_scalar_mass"]
     prof = {}
     for nme in names:
         cnt, ms = ctx.profile_query(nme)
