@@ -182,6 +182,127 @@ class AtlasDiscreteModel:
             pass
 
 
+class PartitionPlan:
+    """Partition of AtlasDiscreteModel(CubedSphereMesh(r), n) over `nparts` ranks as seen by rank `part`
+    (src/Distributed/AtlasDistributedDiscreteModels.jl:20-73): owned cell range, ghost layer, and per FE space the
+    local -> global DOF map, DOF owners and exchange lists.  Pure host computation (no GPU, no communication)."""
+
+    def __init__(self, n, nparts, part, radius=1.0):
+        self.lib = _lib.load()
+        self.n, self.nparts, self.part, self.radius = int(n), int(nparts), int(part), float(radius)
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_plan_create(self.n, self.radius, self.nparts, self.part, C.byref(h)))
+        self.h = h
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.gg_plan_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        self.num_cells_global, self.first_owned, self.last_owned, self.num_local_cells = a.value, b.value, c.value, d.value
+
+    def local_cells(self):
+        out = np.empty(self.num_local_cells, dtype=np.int64)
+        _lib.check(self.lib.gg_plan_local_cells(self.h, _ip64(out)))
+        return out
+
+    def space(self, kind, order):
+        """dict with n_global, n_local, n_owned, slot_capacity, l2g, owner and the neighbour lists of space (kind, order)."""
+        ng, nl, no, nn, cap = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_int64()
+        _lib.check(self.lib.gg_plan_space_info(self.h, kind, order, C.byref(ng), C.byref(nl), C.byref(no), C.byref(nn), C.byref(cap)))
+        l2g, owner = np.empty(nl.value, dtype=np.int64), np.empty(nl.value, dtype=np.int32)
+        _lib.check(self.lib.gg_plan_space_maps(self.h, kind, order, _ip64(l2g), _ip32(owner)))
+        nbrs = {}
+        for k in range(nn.value):
+            peer, ns, nr = C.c_int32(), C.c_int64(), C.c_int64()
+            _lib.check(self.lib.gg_plan_space_neighbor(self.h, kind, order, k, C.byref(peer), C.byref(ns), C.byref(nr), None, None, None))
+            send, remote, recv = (np.empty(ns.value, dtype=np.int32), np.empty(ns.value, dtype=np.int32),
+                                  np.empty(nr.value, dtype=np.int32))
+            _lib.check(self.lib.gg_plan_space_neighbor(self.h, kind, order, k, C.byref(peer), C.byref(ns), C.byref(nr),
+                                                       _ip32(send), _ip32(remote), _ip32(recv)))
+            nbrs[peer.value] = {"send": send, "send_remote": remote, "recv": recv}
+        return {"n_global": ng.value, "n_local": nl.value, "n_owned": no.value, "slot_capacity": cap.value,
+                "l2g": l2g, "owner": owner, "neighbors": nbrs}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.gg_plan_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PeerWindow:
+    """This rank's peer-visible window (flags, reduction operands, one exchange slot) and the IPC mappings of the other
+    ranks' windows.  `connect()` exchanges the 64-byte CUDA-IPC handles with torch.distributed (the only set-up
+    communication of the multi-GPU path)."""
+
+    def __init__(self, ctx, rank, world, slot_doubles):
+        self.ctx, self.lib, self.rank, self.world = ctx, ctx.lib, int(rank), int(world)
+        h = C.c_void_p()
+        _lib.check(self.lib.gg_comm_create(ctx.h, self.rank, self.world, int(slot_doubles), C.byref(h)))
+        self.h = h
+
+    def handle(self):
+        buf = (C.c_uint8 * 64)()
+        _lib.check(self.lib.gg_comm_handle(self.h, buf))
+        return bytes(buf)
+
+    def connect(self, handles=None):
+        if self.world == 1:
+            return
+        if handles is None:
+            import torch
+            import torch.distributed as dist
+            mine = torch.tensor(list(self.handle()), dtype=torch.uint8)
+            dev = torch.device("cuda", self.ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            mine = mine.to(dev)
+            allh = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allh, mine)
+            handles = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        buf = (C.c_uint8 * (64 * self.world)).from_buffer_copy(handles)
+        _lib.check(self.lib.gg_comm_connect(self.h, buf))
+
+    def error_epoch(self):
+        out = C.c_int64()
+        _lib.check(self.lib.gg_comm_error(self.h, C.byref(out)))
+        return out.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                self.lib.gg_comm_destroy(self.h)
+        except Exception:
+            pass
+
+
+def window_doubles(plan, p_fe):
+    """Exchange-slot size that fits every space of the RT_p x DG_p / CG_{p+1} steppers on this plan."""
+    cap = 0
+    for kind, order in ((_lib.SPACE_RT, p_fe), (_lib.SPACE_DG, p_fe), (_lib.SPACE_CG, p_fe + 1)):
+        cap = max(cap, plan.space(kind, order)["slot_capacity"])
+    return cap
+
+
+def partitioned_model(mesh, plan, comm=None, ctx=None, manifold_style=None):
+    """AtlasDiscreteModel(ranks, mesh, nref): this rank's sub-model (owned + ghost cells) on the device."""
+    ctx = ctx or get_context()
+    h = C.c_void_p()
+    _lib.check(ctx.lib.gg_mesh_partitioned(ctx.h, plan.h, comm.h if comm is not None else None, C.byref(h)))
+    m = AtlasDiscreteModel(mesh, ctx=ctx, manifold_style=manifold_style, _handle=h)
+    m.plan, m.comm = plan, comm
+    return m
+
+
+def consistent(v, V):
+    """consistent!(v): owner -> ghost update of a DOF vector of the partitioned space V (collective)."""
+    _lib.check(V.lib.gg_vec_consistent(V.h, v.h))
+    return v
+
+
+def global_dof_ids(V):
+    """(1-based global DOF id, owner rank) of every local DOF of a partitioned space."""
+    l2g, owner = np.empty(V.num_free_dofs, dtype=np.int64), np.empty(V.num_free_dofs, dtype=np.int32)
+    _lib.check(V.lib.gg_space_global_dofs(V.h, _ip64(l2g), _ip32(owner)))
+    return l2g, owner
+
+
 def partition_range(num_cells, nparts, part):
     """Owned cell range of the reference's linear partition (AtlasDistributedDiscreteModels.jl:31), 0-based [first,last)."""
     lib = _lib.load()

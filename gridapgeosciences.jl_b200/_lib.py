@@ -75,6 +75,21 @@ SIGNATURES = {
     "gg_partition_range": (C.c_int, [_I64, C.c_int, C.c_int, _PI64, _PI64]),
     "gg_mesh_restrict": (C.c_int, [_P, _I64, _PI64, _PP]),
     "gg_mesh_ghost_cells": (C.c_int, [_P, _I64, _I64, _PI64, _PI64]),
+    "gg_plan_create": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, _PP]),
+    "gg_plan_destroy": (None, [_P]),
+    "gg_plan_info": (C.c_int, [_P, _PI64, _PI64, _PI64, _PI64]),
+    "gg_plan_local_cells": (C.c_int, [_P, _PI64]),
+    "gg_plan_space_info": (C.c_int, [_P, C.c_int, C.c_int, _PI64, _PI64, _PI64, _PI32, _PI64]),
+    "gg_plan_space_maps": (C.c_int, [_P, C.c_int, C.c_int, _PI64, _PI32]),
+    "gg_plan_space_neighbor": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _PI32, _PI64, _PI64, _PI32, _PI32, _PI32]),
+    "gg_comm_create": (C.c_int, [_P, C.c_int, C.c_int, _I64, _PP]),
+    "gg_comm_handle": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "gg_comm_connect": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "gg_comm_error": (C.c_int, [_P, _PI64]),
+    "gg_comm_destroy": (None, [_P]),
+    "gg_mesh_partitioned": (C.c_int, [_P, _P, _P, _PP]),
+    "gg_space_global_dofs": (C.c_int, [_P, _PI64, _PI32]),
+    "gg_vec_consistent": (C.c_int, [_P, _P]),
     "gg_space_builtin": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _PP]),
     "gg_space_from_arrays": (C.c_int, [_P, C.c_int, C.c_int, _I64, _PI32, _PI8, _PP]),
     "gg_space_info": (C.c_int, [_P, _PI64, _PI32, _PI64]),

@@ -137,6 +137,8 @@ inline void finish_call(gg_ctx* ctx) {
 
 // Reference-element tables for one (order, nq) pair, host copies; see gg_refel.cu
 struct gg_tables;
+struct gg_plan;
+struct gg_comm;
 
 struct gg_mesh {
   gg_ctx* ctx = nullptr;
@@ -162,6 +164,12 @@ struct gg_mesh {
   struct TanTab { gg::DevBuf<double> tx, ty; };
   std::map<int, std::shared_ptr<TanTab>> tan_tabs;
   bool topology_built = false;
+  // partitioned models (gg_dist.cu): the plan this rank-local sub-mesh (owned + ghost cells) was cut from, the peer window
+  // used for halo exchanges, and the owned-cell mask (norms and integrals count owned cells only)
+  gg_plan* plan = nullptr;
+  gg_comm* comm = nullptr;
+  std::vector<uint8_t> cell_owned;
+  gg::DevBuf<uint8_t> d_cell_owned;
 };
 
 struct gg_space {
@@ -183,6 +191,17 @@ struct gg_space {
   gg::DevBuf<int32_t> d_vptr;  // [n_free+1]
   gg::DevBuf<int32_t> d_vsrc;  // [n_entries] = local*n_cells + cell (entry-major element-vector buffer index)
   bool vec_map_built = false;
+  // partitioned spaces (gg_dist.cu): local -> global DOF ids, owner rank of every local DOF, exchange lists grouped by
+  // neighbour rank (ascending global id on both sides); send_remote = the receiver's local id of every sent DOF
+  struct Dist {
+    int64_t n_global = 0, n_owned = 0, slot_capacity = 0;
+    std::vector<int64_t> l2g;
+    std::vector<int32_t> owner;
+    std::vector<int32_t> peers, send_ptr, send_idx, send_remote, recv_ptr, recv_idx;
+    gg::DevBuf<uint8_t> d_owned;  // [n_free] 1 = owned by this rank
+    gg::DevBuf<int32_t> d_peers, d_send_ptr, d_send_idx, d_send_remote, d_send_peer, d_recv_ptr, d_recv_idx;
+  };
+  std::unique_ptr<Dist> dist;
 };
 
 struct gg_vec {
@@ -259,6 +278,12 @@ struct CellGeo {
   double radius;
 };
 CellGeo cell_geo(gg_mesh* m, int nq);
+// host-side construction shared with the partition plans (gg_dist.cu); ctx == nullptr gives a host-only mesh
+gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius);
+void upload_geometry(gg_mesh* m);  // per-cell chart boxes, interval tables and the owned-cell mask -> device
+void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s);
+void space_from_plan(gg_mesh* m, int kind, int order, gg_space* s);
+void space_upload_dist(gg_space* s);
 // internal entry points shared between translation units
 void build_vec_map(gg_space* s);
 void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);

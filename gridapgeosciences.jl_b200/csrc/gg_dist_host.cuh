@@ -1,0 +1,44 @@
+// Host-side structures of the partitioned-model path (gg_dist.cu).
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+#include "gg_common.cuh"
+#include "gg_dist.cuh"
+
+namespace gg {
+struct SpacePlan {
+  int kind = 0, order = 0, mloc = 0;
+  int64_t n_global = 0, n_owned = 0, slot_capacity = 0;
+  std::vector<int64_t> l2g;         // local -> global DOF (0-based, ascending)
+  std::vector<int32_t> owner;       // owner rank of every local DOF
+  std::vector<int32_t> cell_dofs;   // [n_local_cells][mloc] local ids
+  std::vector<int8_t> signs;        // RT: signs of the GLOBAL numbering
+  struct Block { int64_t start, count; int size; };
+  std::vector<Block> blocks;
+  std::vector<int32_t> peers, send_ptr, send_idx, send_remote, recv_ptr, recv_idx;
+};
+SpacePlan& plan_space(gg_plan* P, int kind, int order);
+DistDev dist_dev(gg_space* s);
+void vec_consistent_async(gg_space* s, double* vec);
+}  // namespace gg
+
+struct gg_plan {
+  int n = 0, nparts = 1, part = 0;
+  double radius = 1.0;
+  std::unique_ptr<gg_mesh> gmesh;              // global mesh, host arrays only
+  std::vector<int64_t> first, last;            // owned range of every rank
+  std::vector<std::vector<int64_t>> cells;     // local cells (owned + ghost, ascending global id) of every rank
+  std::map<int, std::unique_ptr<gg::SpacePlan>> spaces;
+};
+
+struct gg_comm {
+  gg_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  int64_t slot_doubles = 0;
+  size_t bytes = 0;
+  void* window = nullptr;           // this rank's window: WinHeader + exchange slot
+  std::vector<void*> peer;          // [world] device pointers (IPC mappings for the other ranks)
+  gg::DevBuf<void*> d_win, d_slot;  // the same pointers on the device
+  bool connected = false;
+};

@@ -22,6 +22,8 @@
 #include "gg_common.cuh"
 #include "gg_ebe.cuh"
 #include "gg_refel.cuh"
+#include "gg_dist.cuh"
+#include "gg_dist_host.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -293,6 +295,7 @@ struct EbeArgs {
   int max_iter;
   int warm;  // start from the content of x instead of 0
   double* stats;
+  DistDev dist;  // world == 1: single GPU
 };
 
 __device__ __forceinline__ unsigned long long ebe_now() {
@@ -335,6 +338,32 @@ __device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i) {
   return acc;
 }
 
+// S_c p_c for one cell, p gathered through `load`
+template <int MB, typename Load>
+__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load load) {
+  const int64_t nc = a.nc;
+  double pe[MB], acc[MB];
+#pragma unroll
+  for (int j = 0; j < MB; ++j) {
+    const int32_t d = a.cell_dofs[c * a.mloc + j];
+    pe[j] = d >= 0 ? load(d) : 0.0;
+    acc[j] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < MB; ++i)
+#pragma unroll
+    for (int j = i; j < MB; ++j) {
+      const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
+      acc[i] = fma(sv, pe[j], acc[i]);
+      if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
+    }
+#pragma unroll
+  for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
+}
+
+// Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; after every
+// preconditioner application the owners store z straight into the neighbours' vectors (z lives in the peer-visible exchange
+// slot) and the dot products are summed over the ranks in rank order (gg_dist.cuh) -- 2 rounds per iteration, no host.
 template <int MB, int MI>
 __global__ void __launch_bounds__(256, 2)
 k_pcg_ebe(const EbeArgs a) {
@@ -346,6 +375,9 @@ k_pcg_ebe(const EbeArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t n = a.nb, nc = a.nc;
+  const bool multi = a.dist.world > 1;
+  const uint8_t* __restrict__ owned = multi ? a.dist.owned : nullptr;
+  unsigned long long epoch = multi ? a.dist.win[a.dist.rank]->epoch : 0ull;
   double* P0 = a.partials;
   double* P1 = a.partials + nbk;
   double* P2 = a.partials + 2 * nbk;
@@ -373,46 +405,35 @@ k_pcg_ebe(const EbeArgs a) {
     double v = a.scale_b * a.b[i];
     if (MI > 0) v -= ebe_gather_row(a, i);
     r_old[i] = v;
-    lbb = fma(v, v, lbb);
+    if (!owned || owned[i]) lbb = fma(v, v, lbb);
     if (!a.warm) a.x[i] = 0.0;
   }
   lbb = ebe_block_sum(lbb, sh);
   if (threadIdx.x == 0) P1[blockIdx.x] = lbb;
   grid.sync();
-  const double bb = ebe_grid_total(P1, nbk, sh);
+  double bb = ebe_grid_total(P1, nbk, sh);
+  if (multi) {
+    double v[1] = {bb};
+    dist_allreduce<1>(grid, a.dist, epoch, v);
+    bb = v[0];
+  }
   if (a.warm) {
     // initial guess = what the output vector holds (the solution of the previous stage / step): r = bt - S x
-    for (int64_t c = tid; c < nc; c += nth) {
-      double pe[MB], acc[MB];
-#pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        const int32_t d = a.cell_dofs[c * a.mloc + j];
-        pe[j] = d >= 0 ? a.x[d] : 0.0;
-        acc[j] = 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < MB; ++i)
-#pragma unroll
-        for (int j = i; j < MB; ++j) {
-          const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
-          acc[i] = fma(sv, pe[j], acc[i]);
-          if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
-        }
-#pragma unroll
-      for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
-    }
+    for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB>(a, c, [&](int32_t d) { return a.x[d]; });
     grid.sync();
     for (int64_t i = tid; i < n; i += nth) r_old[i] -= ebe_gather_row(a, i);
     grid.sync();
   }
   double lrz = 0.0, lrr0 = 0.0;
   for (int64_t i = tid; i < n; i += nth) {
+    a.p[i] = 0.0;
+    if (owned && !owned[i]) continue;
     const int s = a.bstart[i], m = a.bsize[i];
     const double* bi_row = a.binv + a.rowoff[i];
     double zi = 0.0;
     for (int j = 0; j < m; ++j) zi = fma(bi_row[j], r_old[s + j], zi);
     const double ri = r_old[i];
-    a.z[i] = zi; a.p[i] = 0.0;
+    a.z[i] = zi;
     lrz = fma(ri, zi, lrz);
     lrr0 = fma(ri, ri, lrr0);
   }
@@ -420,36 +441,24 @@ k_pcg_ebe(const EbeArgs a) {
   lrr0 = ebe_block_sum(lrr0, sh);
   if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P2[blockIdx.x] = lrr0; }
   grid.sync();
+  if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
   double rz = ebe_grid_total(P0, nbk, sh);
   int it = 0;
   double rr = ebe_grid_total(P2, nbk, sh);
+  if (multi) {
+    double v[2] = {rz, rr};
+    dist_allreduce<2>(grid, a.dist, epoch, v);
+    rz = v[0]; rr = v[1];
+  }
   double beta = 0.0;
   unsigned long long tA = 0, tB = 0, tC = 0;
   grid.sync();  // P2 is reused by the first iteration
   const double tol2 = a.rtol * a.rtol * bb;
   if (bb > 0.0 && rr > tol2) {
     for (it = 1; it <= a.max_iter; ++it) {
-      // -- A: element vectors of S p with p = z + beta p_old formed on the fly
+      // -- A: element vectors of S p with p = z + beta p_old formed on the fly (z may have been written by a peer: L2 loads)
       unsigned long long t0 = ebe_now();
-      for (int64_t c = tid; c < nc; c += nth) {
-        double pe[MB], acc[MB];
-#pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          const int32_t d = a.cell_dofs[c * a.mloc + j];
-          pe[j] = d >= 0 ? fma(beta, a.p[d], a.z[d]) : 0.0;
-          acc[j] = 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < MB; ++i)
-#pragma unroll
-          for (int j = i; j < MB; ++j) {
-            const double s = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
-            acc[i] = fma(s, pe[j], acc[i]);
-            if (j != i) acc[j] = fma(s, pe[i], acc[j]);
-          }
-#pragma unroll
-        for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
-      }
+      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB>(a, c, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
       grid.sync();
       unsigned long long t1 = ebe_now();
       tA += t1 - t0;
@@ -458,12 +467,14 @@ k_pcg_ebe(const EbeArgs a) {
       for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
         int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
         double pv[UNR], acc[UNR];
+        bool own[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
           const bool ok = i < n;
-          lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
-          pv[u] = ok ? fma(beta, a.p[i], a.z[i]) : 0.0;
+          own[u] = ok && (!owned || owned[i]);
+          lo[u] = own[u] ? a.vptr[i] : 0; hi[u] = own[u] ? a.vptr[i + 1] : 0;
+          pv[u] = ok ? fma(beta, a.p[i], __ldcg(a.z + i)) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
@@ -476,7 +487,8 @@ k_pcg_ebe(const EbeArgs a) {
         for (int u = 0; u < UNR; ++u) {
           for (int32_t k = lo[u] + 2; k < hi[u]; ++k) acc[u] += a.ev[a.vsrc[k]];
           const int64_t i = i0 + u * nth;
-          if (i < n) { a.p[i] = pv[u]; a.Ap[i] = acc[u]; lpap = fma(pv[u], acc[u], lpap); }
+          if (i < n) a.p[i] = pv[u];
+          if (own[u]) { a.Ap[i] = acc[u]; lpap = fma(pv[u], acc[u], lpap); }
         }
       }
       lpap = ebe_block_sum(lpap, sh);
@@ -484,19 +496,26 @@ k_pcg_ebe(const EbeArgs a) {
       grid.sync();
       t0 = ebe_now();
       tB += t0 - t1;
-      const double alpha = rz / ebe_grid_total(P2, nbk, sh);
-      // -- C: x += alpha p ; r -= alpha Ap ; z = Binv r (block rows recomputed: no barrier) ; rz, rr
+      double pap = ebe_grid_total(P2, nbk, sh);
+      if (multi) {
+        double v[1] = {pap};
+        dist_allreduce<1>(grid, a.dist, epoch, v);
+        pap = v[0];
+      }
+      const double alpha = rz / pap;
+      // -- C: x += alpha p ; r -= alpha Ap ; z = Binv r (block rows recomputed: no barrier) ; rz, rr  (owned rows only)
       double lrz2 = 0.0, lrr = 0.0;
       for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
         int sb[UNR], mb[UNR], ro[UNR];
         double ri[UNR], zi[UNR], xi[UNR], pi[UNR];
+        bool own[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
-          const bool ok = i < n;
-          sb[u] = ok ? a.bstart[i] : 0; mb[u] = ok ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
-          ri[u] = ok ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
-          xi[u] = ok ? a.x[i] : 0.0; pi[u] = ok ? a.p[i] : 0.0;
+          own[u] = i < n && (!owned || owned[i]);
+          sb[u] = own[u] ? a.bstart[i] : 0; mb[u] = own[u] ? a.bsize[i] : 0; ro[u] = own[u] ? a.rowoff[i] : 0;
+          ri[u] = own[u] ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
+          xi[u] = own[u] ? a.x[i] : 0.0; pi[u] = own[u] ? a.p[i] : 0.0;
           zi[u] = 0.0;
         }
 #pragma unroll
@@ -508,7 +527,7 @@ k_pcg_ebe(const EbeArgs a) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
-          if (i < n) {
+          if (own[u]) {
             a.x[i] = fma(alpha, pi[u], xi[u]);
             r_new[i] = ri[u]; a.z[i] = zi[u];
             lrz2 = fma(ri[u], zi[u], lrz2);
@@ -520,15 +539,32 @@ k_pcg_ebe(const EbeArgs a) {
       lrr = ebe_block_sum(lrr, sh);
       if (threadIdx.x == 0) { P0[blockIdx.x] = lrz2; P1[blockIdx.x] = lrr; }
       grid.sync();
+      if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
       t1 = ebe_now();
       tC += t1 - t0;
       { double* t = r_old; r_old = r_new; r_new = t; }
-      const double rz_new = ebe_grid_total(P0, nbk, sh);
+      double rz_new = ebe_grid_total(P0, nbk, sh);
       rr = ebe_grid_total(P1, nbk, sh);
-      if (rr <= tol2) break;  // uniform across the grid
+      if (multi) {
+        double v[2] = {rz_new, rr};
+        dist_allreduce<2>(grid, a.dist, epoch, v);
+        rz_new = v[0]; rr = v[1];
+      }
+      if (rr <= tol2) break;  // uniform across the grid and across the ranks
       beta = rz_new / rz;
       rz = rz_new;
     }
+  }
+  if (multi) {
+    // owner -> ghost update of the solution (the exchange slot is free again: z is dead)
+    grid.sync();
+    dist_push(a.dist, a.x, tid, nth, n);
+    grid.sync();
+    double v[1] = {0.0};
+    dist_allreduce<1>(grid, a.dist, epoch, v);
+    dist_unpack(a.dist, a.x, tid, nth, n);
+    grid.sync();
+    if (tid == 0) a.dist.win[a.dist.rank]->epoch = epoch;
   }
   // ---- eliminated DOFs: x_i = W (s b_i) - T x_f ----
   if (MI > 0) {
@@ -733,6 +769,8 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;
   a.warm = warm ? 1 : 0;
+  a.dist = dist_dev(sp);
+  if (a.dist.world > 1) a.z = (double*)((char*)sp->mesh->comm->window + sizeof(WinHeader));  // peers store ghost z here
   void* fn = ebe_kernel(s->MB, s->MI);
   int grid = s->grid;
   const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;

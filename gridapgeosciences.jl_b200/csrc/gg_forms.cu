@@ -261,9 +261,11 @@ __global__ void k_qpoints(Geo g, int nq, const double* __restrict__ xi, double* 
 }
 
 __global__ void k_integrate_cells(Geo g, int nq, const double* __restrict__ xi, const double* __restrict__ w,
-                                  const double* __restrict__ qdata, double* __restrict__ cell_sums) {
+                                  const double* __restrict__ qdata, const uint8_t* __restrict__ cell_owned,
+                                  double* __restrict__ cell_sums) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= g.nc) return;
+  if (cell_owned && !cell_owned[c]) { cell_sums[c] = 0.0; return; }  // partitioned model: counted by the owner
   const double X0 = g.x0[c], Y0 = g.y0[c], HX = g.hx[c], HY = g.hy[c];
   int Q = nq * nq;
   double acc = 0.0;
@@ -750,7 +752,8 @@ int gg_integrate(gg_mesh* m, int32_t degree, gg_vec* qdata, double* out) {
   *out = 0.0;
   if (nc == 0) return GG_OK;
   DevBuf<double> sums(nc), total(1);
-  k_integrate_cells<<<nblk(nc, 128), 128, 0, ctx->stream>>>(geo_of(m), nq, T->xi.p, T->w.p, qdata ? qdata->d.p : nullptr, sums.p);
+  k_integrate_cells<<<nblk(nc, 128), 128, 0, ctx->stream>>>(geo_of(m), nq, T->xi.p, T->w.p, qdata ? qdata->d.p : nullptr,
+                                                            m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;
   GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, ctx->stream));
   DevBuf<uint8_t> tmp(tb);

@@ -101,9 +101,10 @@ __global__ void k_norm_cells(int64_t nc, int nq, int m, int is_rt, const double*
                              const double* __restrict__ hx, const double* __restrict__ hy, double radius,
                              const double* __restrict__ xi, const double* __restrict__ w, const double* __restrict__ val,
                              const int32_t* __restrict__ dofs, const int8_t* __restrict__ signs, const double* __restrict__ e,
-                             double* __restrict__ sums) {
+                             const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  if (cell_owned && !cell_owned[c]) { sums[c] = 0.0; return; }  // partitioned model: ghost cells are counted by their owner
   const double HX = hx[c], HY = hy[c];
   double acc = 0.0;
   for (int q2 = 0; q2 < nq; ++q2) {
@@ -218,7 +219,7 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   int is_rt = s->kind == GG_SPACE_RT ? 1 : 0;
   k_norm_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, is_rt, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius,
                                               T->xi.p, T->w.p, T->val.p, s->d_cell_dofs.p, is_rt ? s->d_cell_signs.p : nullptr,
-                                              e->d.p, sums.p);
+                                              e->d.p, m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;
   GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
   DevBuf<uint8_t> tmp(tb);

@@ -105,7 +105,8 @@ static void ensure_topology(gg_mesh* m) {
   m->topology_built = true;
 }
 
-static void upload_geometry(gg_mesh* m) {
+void upload_geometry(gg_mesh* m) {
+  if (!m->ctx) return;  // host-only mesh (partition plans)
   int64_t nc = m->n_cells;
   std::vector<double> x0(nc), y0(nc), hx(nc), hy(nc);
   for (int64_t c = 0; c < nc; ++c) {
@@ -144,12 +145,13 @@ static void upload_geometry(gg_mesh* m) {
   m->d_ix.upload(ix, s); m->d_iy.upload(iy, s);
   m->d_xlo.upload(xlo, s); m->d_xh.upload(xh, s); m->d_ylo.upload(ylo, s); m->d_yh.upload(yh, s);
   m->tan_tabs.clear();
+  if (!m->cell_owned.empty()) m->d_cell_owned.upload(m->cell_owned, s);
   GG_CUDA(cudaStreamSynchronize(s));
 }
 
 static const int32_t COARSE_CELLS[6][4] = {{0, 1, 2, 3}, {2, 3, 4, 5}, {1, 6, 3, 5}, {7, 4, 6, 5}, {0, 7, 1, 6}, {0, 2, 7, 4}};
 
-static gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
+gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
   std::unique_ptr<gg_mesh> m(new gg_mesh);
   m->ctx = ctx; m->dim = 2; m->n = n; m->radius = radius;
   int64_t nc = 6LL * n * n;
@@ -326,6 +328,8 @@ int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghos
 
 static void finish_space(gg_space* s) {
   gg_mesh* m = s->mesh;
+  if (s->kind != GG_SPACE_RT) s->loc2lex = quad_local_to_lex(s->order);
+  if (!m->ctx) return;  // host-only space (partition plans)
   cudaStream_t st = m->ctx->stream;
   s->d_cell_dofs.upload(s->cell_dofs, st);
   if (!s->cell_signs.empty()) s->d_cell_signs.upload(s->cell_signs, st);
@@ -333,11 +337,11 @@ static void finish_space(gg_space* s) {
   if (s->kind != GG_SPACE_RT) s->loc2lex = quad_local_to_lex(s->order);
 }
 
-int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space** out) {
-  GG_API_BEGIN
-  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
-  GG_CUDA(cudaSetDevice(m->ctx->device));
-  std::unique_ptr<gg_space> s(new gg_space);
+}  // extern "C"
+
+namespace gg {
+// Builtin numbering (our restatement of Gridap's) on the host arrays of `m`
+void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s) {
   s->mesh = m; s->kind = kind; s->order = order; s->constraint = constraint;
   int64_t nc = m->n_cells;
   if (kind == GG_SPACE_CG) {
@@ -402,7 +406,25 @@ int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space**
   } else {
     throw Error(GG_ERR_INVALID, "unknown space kind");
   }
+}
+}  // namespace gg
+
+extern "C" {
+
+int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  if (m->ctx) GG_CUDA(cudaSetDevice(m->ctx->device));
+  std::unique_ptr<gg_space> s(new gg_space);
+  if (m->plan) {
+    // rank-local sub-mesh of a partitioned model: the global builtin numbering restricted to the local cells (gg_dist.cu)
+    GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on partitioned spaces are not implemented");
+    space_from_plan(m, kind, order, s.get());
+  } else {
+    space_builtin_host(m, kind, order, constraint, s.get());
+  }
   finish_space(s.get());
+  if (m->plan && m->ctx) space_upload_dist(s.get());
   *out = s.release();
   GG_API_END
 }

@@ -275,13 +275,6 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   chk(gg_space_builtin(m, GG_SPACE_RT, a->order, GG_CONSTRAINT_NONE, &rk->V));
   chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
   rk->nu = rk->V->n_free; rk->np = rk->Q->n_free; rk->mq = rk->Q->ndofs_loc; rk->mu = rk->V->ndofs_loc;
-  // RT mass matrix and its solver
-  chk(gg_pattern(rk->V, rk->V, &rk->Mu));
-  gg_form_args fa;
-  std::memset(&fa, 0, sizeof(fa));
-  fa.test = rk->V; fa.trial = rk->V; fa.degree = a->degree;
-  chk(gg_assemble_matrix(GG_FORM_MASS_RT, &fa, rk->Mu, 0));
-  chk(gg_solver_pcg_create(rk->Mu, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver));
   // mass solver: GG_PCG = ebe (default: statically condensed element-by-element), mf (matrix-free re-integration), csr
   const char* mode_env = getenv("GG_PCG");
   const std::string mode = mode_env ? mode_env : "ebe";
@@ -289,12 +282,23 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   // or the previous diagnostics) unless GG_WARM_START=0
   const char* ws = getenv("GG_WARM_START");
   rk->warm_start = !(ws && ws[0] == '0');
+  gg_form_args fa;
+  std::memset(&fa, 0, sizeof(fa));
+  fa.test = rk->V; fa.trial = rk->V; fa.degree = a->degree;
+  const bool partitioned = m->plan != nullptr;
   if (mode == "ebe" && ebe_supported(rk->V)) {
+    // RT mass: element matrices once, condensed and kept per cell (never assembled)
     rk->ebe_u = ebe_create(rk->V, a->rtol > 0 ? a->rtol : 1e-12, 2000);
     int layout = 0;
     const double* eb = element_matrices_device(GG_FORM_MASS_RT, &fa, &layout);
     GG_REQUIRE(layout == 0, GG_ERR_INVALID, "unexpected element buffer layout");
     ebe_set_matrix(rk->ebe_u, eb);
+  } else {
+    GG_REQUIRE(!partitioned, GG_ERR_UNSUPPORTED, "partitioned models need the element-by-element mass solver (GG_PCG=ebe)");
+    // assembled RT mass matrix and block-Jacobi PCG on it
+    chk(gg_pattern(rk->V, rk->V, &rk->Mu));
+    chk(gg_assemble_matrix(GG_FORM_MASS_RT, &fa, rk->Mu, 0));
+    chk(gg_solver_pcg_create(rk->Mu, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver));
   }
   // DG mass blocks -> inverses
   build_dg_mass_inverse(rk);
@@ -304,7 +308,15 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   int64_t n = rk->nu + rk->np;
   rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
   rk->k.resize(s);
-  for (int i = 0; i < s; ++i) rk->k[i].alloc(n);
+  for (int i = 0; i < s; ++i) {
+    rk->k[i].alloc(n);
+    // the slopes double as initial guesses of the warm-started mass solves: they must start out consistent across ranks
+    if (n) GG_CUDA(cudaMemsetAsync(rk->k[i].p, 0, n * sizeof(double), ctx->stream));
+  }
+  if (n) {
+    GG_CUDA(cudaMemsetAsync(rk->xi.p, 0, n * sizeof(double), ctx->stream));
+    GG_CUDA(cudaMemsetAsync(rk->r.p, 0, n * sizeof(double), ctx->stream));
+  }
   rk->iter_accum.alloc(2);
   GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
   if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));

@@ -489,24 +489,27 @@ void swe_create(gg_rk* rk, const gg_rk_args* a) {
   rk->q0_mode = a->q0_mode;
   chk(gg_space_builtin(rk->mesh, GG_SPACE_CG, a->order + 1, GG_CONSTRAINT_NONE, &rk->R));
   rk->nr = rk->R->n_free; rk->mr = rk->R->ndofs_loc;
-  chk(gg_pattern(rk->R, rk->R, &rk->Mq));
   chk(gg_vec_create(ctx, nc * Q, &rk->pq));
   chk(gg_vec_fill(rk->pq, 1.0));
-  // a first assembly with unit depth so that the solver is created on a positive definite matrix
-  gg_form_args fa;
-  std::memset(&fa, 0, sizeof(fa));
-  fa.test = rk->R; fa.trial = rk->R; fa.degree = a->degree; fa.qdata = rk->pq;
-  chk(gg_assemble_matrix(GG_FORM_MASS_SCALAR, &fa, rk->Mq, 0));
-  chk(gg_solver_pcg_create(rk->Mq, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver_q));
   build_vec_map(rk->R);
-  // matrix-free mass solves unless GG_PCG=csr is exported (the assembled path stays available for comparison)
   const char* mode_env = getenv("GG_PCG");
   const std::string mode = mode_env ? mode_env : "ebe";
-  if (mode == "ebe" && rk->ebe_u && ebe_supported(rk->R)) {
+  if (rk->ebe_u && ebe_supported(rk->R)) {
     rk->ebe_q = ebe_create(rk->R, a->rtol > 0 ? a->rtol : 1e-12, 2000);
-  } else if (mode == "mf" && mf_supported(GG_SPACE_RT, a->order, rk->nq1) && mf_supported(GG_SPACE_CG, a->order + 1, rk->nq1)) {
-    solver_set_matrix_free(rk->solver, a->degree, nullptr);
-    solver_set_matrix_free(rk->solver_q, a->degree, rk->pq->d.p);
+  } else {
+    GG_REQUIRE(!rk->mesh->plan, GG_ERR_UNSUPPORTED, "partitioned models need the element-by-element mass solver (GG_PCG=ebe)");
+    GG_REQUIRE(rk->solver, GG_ERR_INVALID, "no RT mass solver");
+    chk(gg_pattern(rk->R, rk->R, &rk->Mq));
+    // a first assembly with unit depth so that the solver is created on a positive definite matrix
+    gg_form_args fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.test = rk->R; fa.trial = rk->R; fa.degree = a->degree; fa.qdata = rk->pq;
+    chk(gg_assemble_matrix(GG_FORM_MASS_SCALAR, &fa, rk->Mq, 0));
+    chk(gg_solver_pcg_create(rk->Mq, a->rtol > 0 ? a->rtol : 1e-12, 2000, &rk->solver_q));
+    if (mode == "mf" && mf_supported(GG_SPACE_RT, a->order, rk->nq1) && mf_supported(GG_SPACE_CG, a->order + 1, rk->nq1)) {
+      solver_set_matrix_free(rk->solver, a->degree, nullptr);
+      solver_set_matrix_free(rk->solver_q, a->degree, rk->pq->d.p);
+    }
   }
   rk->fq.upload(a->coriolis, (size_t)(nc * Q), st);
   if (a->topography) rk->bq.upload(a->topography, (size_t)(nc * Q), st);

@@ -47,6 +47,8 @@ typedef struct gg_csr gg_csr;
 typedef struct gg_vec gg_vec;
 typedef struct gg_solver gg_solver;
 typedef struct gg_rk gg_rk;
+typedef struct gg_plan gg_plan;
+typedef struct gg_comm gg_comm;
 
 /* ---- context ------------------------------------------------------------------------------- */
 int gg_init(int device_id, gg_ctx** out);
@@ -100,6 +102,41 @@ int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** 
 /* ghost cells of the owned range [first,last): cells outside it sharing a vertex with a cell inside (:34-49).
  * Pass out=NULL to query the count. */
 int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghost, int64_t* out);
+
+/* ---- partitioned models (multi-GPU) ------------------------------------------------------------------
+ * Replace AtlasDiscreteModel(ranks, mesh, nref) (src/Distributed/AtlasDistributedDiscreteModels.jl:20-113): linear cell
+ * partition `div((i-1)*P, Nc)+1` (:31), ghost layer = cells sharing a vertex with an owned cell (:32-49), and
+ * PartitionedArrays' PRange / `consistent!` on DOF vectors (src/ODEs/StageOperators.jl:109,134; src/ODEs/DAE.jl:291,314).
+ * One process per GPU.  The plan is a pure function of (n, nparts) computed redundantly by every rank ON THE HOST (no GPU
+ * and no communication needed); the only thing ranks exchange at set-up are the 64-byte CUDA-IPC handles of their peer
+ * windows.  At run time halo values and dot-product operands are stored straight into the peers' HBM over NVLink by the
+ * solver kernels (no NCCL call inside a step).  DOF ownership: the rank owning the lowest-numbered cell around the DOF. */
+int gg_plan_create(int n, double radius, int nparts, int part, gg_plan** out);
+void gg_plan_destroy(gg_plan* p);
+int gg_plan_info(gg_plan* p, int64_t* n_cells_global, int64_t* first_owned, int64_t* last_owned, int64_t* n_local);
+int gg_plan_local_cells(gg_plan* p, int64_t* out /* [n_local] global cell ids (0-based), ascending: owned + ghost */);
+/* spaces are identified by (kind, order) of gg_space_builtin; slot_capacity = max local DOFs over the ranks */
+int gg_plan_space_info(gg_plan* p, int kind, int order, int64_t* n_global, int64_t* n_local, int64_t* n_owned,
+                       int32_t* n_neighbors, int64_t* slot_capacity);
+int gg_plan_space_maps(gg_plan* p, int kind, int order, int64_t* l2g /* [n_local] 0-based global DOF */,
+                       int32_t* owner /* [n_local] owner rank */);
+/* k-th neighbour: DOFs sent to it (local ids, and the ids they have over there) and received from it, ascending global id */
+int gg_plan_space_neighbor(gg_plan* p, int kind, int order, int k, int32_t* peer, int64_t* n_send, int64_t* n_recv,
+                           int32_t* send_idx, int32_t* send_remote_idx, int32_t* recv_idx);
+/* peer window of this rank: header (flags, reduction operands) + an exchange slot of slot_doubles doubles */
+int gg_comm_create(gg_ctx* ctx, int rank, int world, int64_t slot_doubles, gg_comm** out);
+int gg_comm_handle(gg_comm* c, uint8_t* out64 /* cudaIpcMemHandle_t */);
+int gg_comm_connect(gg_comm* c, const uint8_t* handles /* [world][64], rank order */);
+/* epoch of the first timed-out wait (0 = none): a lost peer is an error code, not a hung GPU */
+int gg_comm_error(gg_comm* c, int64_t* error_epoch);
+void gg_comm_destroy(gg_comm* c);
+/* the rank's sub-model (owned + ghost cells).  Spaces, vectors and RK steppers built on it are partitioned: local
+ * numbering = the global builtin numbering restricted to the local cells; gg_norm_sq / gg_integrate count owned cells only
+ * (sum the results over the ranks).  The plan (and comm) must outlive the mesh. */
+int gg_mesh_partitioned(gg_ctx* ctx, gg_plan* p, gg_comm* comm, gg_mesh** out);
+int gg_space_global_dofs(gg_space* s, int64_t* l2g /* 1-based global DOF ids */, int32_t* owner);
+/* consistent!(v): owner -> ghost update through the peer windows (collective: every rank must call it) */
+int gg_vec_consistent(gg_space* s, gg_vec* v);
 
 /* ---- FE spaces -------------------------------------------------------------------------------
  * Replace TestFESpace(model, ReferenceFE(lagrangian|raviart_thomas, Float64, order); conformity, constraint)

@@ -1,0 +1,123 @@
+"""Worker of tests/test_gpu_dist.py (launched with torch.distributed.run, one rank per GPU): the partitioned RK steppers --
+halo exchange and dot products through peer memory inside the solver kernels -- against the single-GPU run of the same
+problem on the same mesh."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+OM, G = 1.0, 9.8 * (1 / 7.29e-5) ** 2 / 6.37e6
+H0, U0 = 2.94e4 / 9.8 / 6.37e6, 2 * np.pi / (12 * 24 * 3600 * 7.29e-5)
+
+
+def coriolis(X):
+    return 2.0 * OM * X[..., 2] / np.linalg.norm(X, axis=-1)
+
+
+def depth(X):
+    s = X[..., 2] / np.linalg.norm(X, axis=-1)
+    return H0 - (OM * U0 + 0.5 * U0 * U0) * s * s / G + 1e-5 * np.cos(3 * X[..., 0]) * X[..., 1]
+
+
+def velocity(X):
+    n = X / np.linalg.norm(X, axis=-1, keepdims=True)
+    return U0 * np.stack([-n[..., 1], n[..., 0], 0.3 * n[..., 0] * n[..., 1]], -1)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gg = load_package()
+    ctx = gg.get_context(local)
+    n, p = int(sys.argv[1]) if len(sys.argv) > 1 else 6, int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    mesh = gg.CubedSphereMesh(1.0)
+    plan = gg.PartitionPlan(n, world, rank)
+    comm = gg.PeerWindow(ctx, rank, world, gg.window_doubles(plan, p))
+    comm.connect()
+    local_model = gg.partitioned_model(mesh, plan, comm, ctx=ctx)
+    full_model = gg.AtlasDiscreteModel(mesh, n=n, ctx=ctx)
+    assert local_model.num_cells == plan.num_local_cells
+
+    def spaces(model):
+        V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+        Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+        return V, Q
+
+    V, Q = spaces(local_model)
+    Vf, Qf = spaces(full_model)
+    lv, ov = gg.global_dof_ids(V)
+    lq, oq = gg.global_dof_ids(Q)
+    lv, lq = lv - 1, lq - 1
+
+    # -- consistent!: ghosts unknown -> owner values
+    for S_, l2g, own in ((V, lv, ov), (Q, lq, oq)) if 'cons' not in os.environ.get('GG_DEBUG_SKIP', '') else ():
+        g = np.sin(0.1 * np.arange(l2g.max() + 1)) + 2.0
+        v = gg.DeviceVector.from_numpy(ctx, np.where(own == rank, g[l2g], -777.0))
+        gg.consistent(v, S_)
+        assert (v.get() == g[l2g]).all(), "consistent! did not reproduce the owner values"
+
+    # -- interpolation on the sub-model = restriction of the global interpolant; norms add up over the ranks
+    u0, h0 = gg.interpolate(velocity, V).get(), gg.interpolate(depth, Q).get()
+    u0f, h0f = gg.interpolate(velocity, Vf).get(), gg.interpolate(depth, Qf).get()
+    assert rel(u0, u0f[lv]) < 1e-13 and rel(h0, h0f[lq]) < 1e-13
+    nsq = torch.tensor([gg.norm(u0, V, 8) ** 2, gg.norm(h0, Q, 8) ** 2], device="cuda", dtype=torch.float64)
+    dist.all_reduce(nsq)
+    assert abs(nsq[0].item() - gg.norm(u0f, Vf, 8) ** 2) < 1e-12 * nsq[0].item()
+    assert abs(nsq[1].item() - gg.norm(h0f, Qf, 8) ** 2) < 1e-12 * nsq[1].item()
+
+    x0, x0f = np.concatenate([u0, h0]), np.concatenate([u0f, h0f])
+    nsteps = 3
+    # -- linear wave
+    skip = os.environ.get('GG_DEBUG_SKIP', '')
+    dt = gg.dx(full_model) * 0.1
+    rk = gg.RungeKutta(gg.CGSolver(rtol=1e-13), None, dt, "EXRK_SSP_3_3")
+    st, stf = gg.RKStepper(rk, gg.WaveOperator(local_model, p)), gg.RKStepper(rk, gg.WaveOperator(full_model, p))
+    st.set_state(x0); stf.set_state(x0f)
+    if 'wave' not in skip:
+        st.step(nsteps); stf.step(nsteps)
+    x, xf = st.get_state(), stf.get_state()
+    e_w = max(rel(x[: st.nu], xf[: stf.nu][lv]), rel(x[st.nu:], xf[stf.nu:][lq]))
+    assert e_w < 1e-10, f"wave: partitioned and single-GPU states differ by {e_w}"
+    assert comm.error_epoch() == 0
+    del st, stf
+
+    # -- rotating shallow water (diagnostic + slope solves, all of them partitioned)
+    dt = gg.dx(full_model) * 0.1 / (max(p, 1) * np.sqrt(G * H0))
+    rk = gg.RungeKutta(gg.CGSolver(rtol=1e-13), None, dt, "EXRK_SSP_3_3")
+    st = gg.RKStepper(rk, gg.ShallowWaterOperator(local_model, p, coriolis, gravity=G))
+    stf = gg.RKStepper(rk, gg.ShallowWaterOperator(full_model, p, coriolis, gravity=G))
+    st.set_state(x0); stf.set_state(x0f)
+    st.step(nsteps); stf.step(nsteps)
+    x, xf = st.get_state(), stf.get_state()
+    e_s = max(rel(x[: st.nu], xf[: stf.nu][lv]), rel(x[st.nu:], xf[stf.nu:][lq]))
+    assert e_s < 1e-9, f"shallow water: partitioned and single-GPU states differ by {e_s}"
+    R = gg.TestFESpace(local_model, gg.ReferenceFE(gg.lagrangian, float, p + 1), conformity="H1")
+    lr, _ = gg.global_dof_ids(R)
+    y, yf = st.get_diagnostics(), stf.get_diagnostics()
+    e_q = rel(y[: st.nq], yf[: stf.nq][lr - 1])
+    assert e_q < 1e-8, f"shallow water: potential vorticity differs by {e_q}"
+    assert comm.error_epoch() == 0
+    its, sol = st.stats()
+    itf, solf = stf.stats()
+    assert sol == solf
+    dist.barrier()
+    if rank == 0:
+        print(f"DIST_OK world={world} n={n} p={p} wave_err={e_w:.2e} swe_err={e_s:.2e} pv_err={e_q:.2e} "
+              f"pcg_iters={its} (single GPU {itf}) solves={sol}")
+    del st, stf
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
