@@ -105,35 +105,62 @@ def _w2_velocity(X):
     return _U0 * np.stack([-n[..., 1], n[..., 0], 0 * n[..., 0]], -1)
 
 
-def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10):
+def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10, dist=None, rank=0, world=1):
+    """RK steps/s of the shallow-water DAE stepper.  world > 1: the n x n-per-panel model is partitioned over the ranks
+    (linear partition + ghost layer of the reference); halo exchange and dot products go through peer memory inside the
+    solver kernels, the time is the max over ranks."""
     ctx.set_async(False)
-    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n, ctx=ctx)
+    mesh = gg.CubedSphereMesh(1.0)
+    keep = []
+    if world > 1:
+        plan = gg.PartitionPlan(n, world, rank)
+        comm = gg.PeerWindow(ctx, rank, world, gg.window_doubles(plan, p))
+        comm.connect()
+        model = gg.partitioned_model(mesh, plan, comm, ctx=ctx)
+        ncells = plan.num_cells_global
+        keep = [plan, comm]
+    else:
+        model = gg.AtlasDiscreteModel(mesh, n=n, ctx=ctx)
+        ncells = model.num_cells
     V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
     Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
     x0 = np.concatenate([gg.interpolate(_w2_velocity, V).get(), gg.interpolate(_w2_depth, Q).get()])
-    dt = gg.dx(model) * 0.1 / (p * math.sqrt(_G * _H0))          # TransientShallowWater.jl:147
+    dt = math.sqrt(4 * math.pi / ncells) * 0.1 / (p * math.sqrt(_G * _H0))          # TransientShallowWater.jl:147
     op = gg.ShallowWaterOperator(model, p, _w2_coriolis, gravity=_G)
     st = gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=1e-12), None, dt, "EXRK_SSP_3_3"), op)
     st.set_state(x0)
     st.step(3)
     it0, so0 = st.stats()
     l0 = ctx.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     e0.record(stream)
     st.step(steps)
     e1.record(stream)
     torch.cuda.synchronize()
-    it1, so1 = st.stats()
     ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        assert keep[1].error_epoch() == 0, "a peer-memory wait timed out"
+    it1, so1 = st.stats()
     ph = {name: st.solver_phase_ns(w) for w, name in ((0, "rt_mass"), (1, "pv_mass"))}
-    return {"workload": f"rotating shallow water (Williamson 2), {n}x{n} per panel, RT{p} x DG{p} + CG{p + 1} diagnostics, "
-                        f"degree {4 * (p + 1)}, SSPRK(3,3), dt = 0.1 dx / (p sqrt(g H0))",
-            "cells": model.num_cells, "dofs_prognostic": st.nu + st.np_, "dofs_diagnostic": st.ny,
-            "steps_per_s": 1e3 / ms, "ms_per_step": ms, "cell_stage_evaluations_per_s": 6 * model.num_cells / (ms * 1e-3),
-            "mass_solves_per_step": (so1 - so0) / steps, "pcg_iters_per_solve": (it1 - it0) / max(so1 - so0, 1),
-            "launches_per_step": (ctx.launches - l0) / steps,
-            "pcg_us_per_iter": {k: {"cells": v[0] / max(v[3], 1) / 1e3, "gather_dot": v[1] / max(v[3], 1) / 1e3,
-                                    "update_precond": v[2] / max(v[3], 1) / 1e3} for k, v in ph.items()},
-            "solver": "statically condensed element-by-element block-Jacobi PCG, rtol 1e-12, warm-started from the previous solution"}
+    drift = float(np.abs(st.get_state() - x0).max() / np.abs(x0).max())
+    out = {"workload": f"rotating shallow water (Williamson 2), {n}x{n} per panel, RT{p} x DG{p} + CG{p + 1} diagnostics, "
+                       f"degree {4 * (p + 1)}, SSPRK(3,3), dt = 0.1 dx / (p sqrt(g H0))",
+           "n_gpus": world, "cells": ncells, "cells_local_incl_ghosts": model.num_cells,
+           "dofs_prognostic_local": st.nu + st.np_, "dofs_diagnostic_local": st.ny,
+           "steps_per_s": 1e3 / ms, "ms_per_step": ms, "cell_stage_evaluations_per_s": 6 * ncells / (ms * 1e-3),
+           "mass_solves_per_step": (so1 - so0) / steps, "pcg_iters_per_solve": (it1 - it0) / max(so1 - so0, 1),
+           "launches_per_step": (ctx.launches - l0) / steps, "state_drift_after_steps": drift,
+           "pcg_us_per_iter": {k: {"cells": v[0] / max(v[3], 1) / 1e3, "gather_dot": v[1] / max(v[3], 1) / 1e3,
+                                   "update_precond": v[2] / max(v[3], 1) / 1e3} for k, v in ph.items()},
+           "solver": "statically condensed element-by-element block-Jacobi PCG, rtol 1e-12, warm-started from the previous "
+                     "solution" + ("; halo + all-reduce through CUDA-IPC peer memory inside the kernel" if world > 1 else "")}
+    del st
+    return out
 
 
 def cpu_baseline_run(nthreads, target_seconds=12.0):
@@ -394,10 +421,19 @@ def main():
             line["rk"] = {"error": str(ex)}
         # nonlinear rotating shallow water (DAE: 3 diagnostic solves + 3 slope solves per SSPRK3 step), BASELINE configs[3]:
         # 256x256 per panel, order 2 (RT2 x DG2 prognostic, CG3 x RT2 x DG2 diagnostic), degree 12, Williamson-2 state
+        if world == 1:
+            try:
+                line["rk"]["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1)
+            except Exception as ex:
+                line["rk"]["shallow_water"] = {"error": str(ex)}
+
+    # ---- RK steps/s on N GPUs: the partitioned shallow-water stepper, weak scaling (every rank takes part) -------------
+    if not args.no_extras and world > 1:
         try:
-            line["rk"]["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1)
+            sw = swe_leg(gg, ctx, torch, stream, e0, e1, n=n, dist=dist, rank=rank, world=world)
         except Exception as ex:
-            line["rk"]["shallow_water"] = {"error": str(ex)}
+            sw = {"error": str(ex)}
+        line.setdefault("rk", {})["shallow_water"] = sw
 
     # ---- CPU baseline beside it (rank 0, N=1) -------------------------------------------------------------------
     if not args.no_extras and rank == 0 and world == 1:

@@ -198,8 +198,8 @@ struct gg_space {
     std::vector<int64_t> l2g;
     std::vector<int32_t> owner;
     std::vector<int32_t> peers, send_ptr, send_idx, send_remote, recv_ptr, recv_idx;
-    gg::DevBuf<uint8_t> d_owned;  // [n_free] 1 = owned by this rank
-    gg::DevBuf<int32_t> d_peers, d_send_ptr, d_send_idx, d_send_remote, d_send_peer, d_recv_ptr, d_recv_idx;
+    gg::DevBuf<uint8_t> d_owned;  // [n_free] 0 ghost, 1 owned, 2 owned and a ghost of some neighbour (device send lists are sorted by row)
+    gg::DevBuf<int32_t> d_peers, d_send_ptr, d_send_idx, d_send_remote, d_send_peer, d_push_first, d_recv_ptr, d_recv_idx;
   };
   std::unique_ptr<Dist> dist;
 };

@@ -15,6 +15,7 @@
 // numbering restricted to the local cells (boundary DOFs first, cell-private interior DOFs after them in local cell order),
 // which keeps the statically condensed solver applicable.  All run-time exchanges go through peer memory (gg_dist.cuh).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -147,15 +148,25 @@ void space_upload_dist(gg_space* s) {
   auto& d = *s->dist;
   cudaStream_t st = s->mesh->ctx->stream;
   const int me = s->mesh->plan->part;
-  std::vector<uint8_t> owned(d.owner.size());
-  for (size_t i = 0; i < owned.size(); ++i) owned[i] = d.owner[i] == me;
-  std::vector<int32_t> send_peer(d.send_idx.size());
+  // device copies of the send entries sorted by local row, so that the solver can push a row's value to its ghosts the
+  // moment it is computed: owned[i] = 2 marks rows with entries, push_first[i] is the first of them
+  const size_t ns = d.send_idx.size();
+  std::vector<int32_t> peer_of(ns);
   for (size_t k = 0; k + 1 < d.send_ptr.size(); ++k)
-    for (int32_t e = d.send_ptr[k]; e < d.send_ptr[k + 1]; ++e) send_peer[e] = d.peers[k];
+    for (int32_t e = d.send_ptr[k]; e < d.send_ptr[k + 1]; ++e) peer_of[e] = d.peers[k];
+  std::vector<int32_t> order(ns);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return d.send_idx[a] < d.send_idx[b]; });
+  std::vector<int32_t> e_row(ns), e_peer(ns), e_remote(ns);
+  for (size_t k = 0; k < ns; ++k) { e_row[k] = d.send_idx[order[k]]; e_peer[k] = peer_of[order[k]]; e_remote[k] = d.send_remote[order[k]]; }
+  std::vector<uint8_t> owned(d.owner.size());
+  std::vector<int32_t> push_first(d.owner.size(), -1);
+  for (size_t i = 0; i < owned.size(); ++i) owned[i] = d.owner[i] == me;
+  for (size_t k = ns; k-- > 0;) { push_first[e_row[k]] = (int32_t)k; owned[e_row[k]] = 2; }
   d.d_owned.upload(owned, st);
   d.d_peers.upload(d.peers, st);
-  d.d_send_ptr.upload(d.send_ptr, st); d.d_send_idx.upload(d.send_idx, st); d.d_send_remote.upload(d.send_remote, st);
-  d.d_send_peer.upload(send_peer, st);
+  d.d_send_ptr.upload(d.send_ptr, st); d.d_send_idx.upload(e_row, st); d.d_send_remote.upload(e_remote, st);
+  d.d_send_peer.upload(e_peer, st); d.d_push_first.upload(push_first, st);
   d.d_recv_ptr.upload(d.recv_ptr, st); d.d_recv_idx.upload(d.recv_idx, st);
   GG_CUDA(cudaStreamSynchronize(st));
 }
@@ -170,9 +181,11 @@ DistDev dist_dev(gg_space* s) {
              "peer window too small: needs " + std::to_string(s->dist->slot_capacity) + " doubles per slot");
   auto& x = *s->dist;
   d.rank = c->rank; d.world = c->world;
+  d.timing = getenv("GG_COMM_STATS") ? 1 : 0;
   d.win = (WinHeader* const*)c->d_win.p; d.slot = (double* const*)c->d_slot.p;
   d.owned = x.d_owned.p;
   d.send_idx = x.d_send_idx.p; d.send_remote = x.d_send_remote.p; d.send_peer = x.d_send_peer.p;
+  d.push_first = x.d_push_first.p;
   d.n_send = (int64_t)x.send_idx.size();
   d.recv_idx = x.d_recv_idx.p; d.n_recv = (int64_t)x.recv_idx.size();
   return d;
@@ -353,6 +366,9 @@ int gg_comm_error(gg_comm* c, int64_t* error_epoch) {
   WinHeader h;
   GG_CUDA(cudaMemcpy(&h, c->window, sizeof(h), cudaMemcpyDeviceToHost));
   *error_epoch = (int64_t)h.error;
+  if (getenv("GG_COMM_STATS"))
+    fprintf(stderr, "[gg_comm rank %d] rounds %llu  wait %.2f us/round  post %.2f us/round\n", c->rank, h.rounds,
+            h.rounds ? 1e-3 * h.wait_ns / h.rounds : 0.0, h.rounds ? 1e-3 * h.post_ns / h.rounds : 0.0);
   GG_API_END
 }
 

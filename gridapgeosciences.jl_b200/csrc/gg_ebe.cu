@@ -19,6 +19,7 @@
 //   * block-Jacobi preconditioner over the DOFs of one facet / edge, built from the condensed element matrices.
 // The eliminated DOFs are recovered cell by cell after the iteration: x_i = M_ii^-1 b_i - (M_ii^-1 M_if) x_f.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_ebe.cuh"
 #include "gg_refel.cuh"
@@ -361,9 +362,11 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load
   for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
 }
 
-// Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; after every
-// preconditioner application the owners store z straight into the neighbours' vectors (z lives in the peer-visible exchange
-// slot) and the dot products are summed over the ranks in rank order (gg_dist.cuh) -- 2 rounds per iteration, no host.
+// Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; the owner of a
+// row stores its new z straight into the neighbours' exchange slots the moment it is computed (NVLink stores from inside
+// phase C), the dot products are summed over the ranks in rank order (gg_dist.cuh), and the ghost values are copied from
+// the slot into z after the round -- 2 rounds per iteration, no host, no NCCL.  (z itself stays in ordinary device memory:
+// writing the whole vector into the IPC-exported window made phase C 2x slower on B200.)
 template <int MB, int MI>
 __global__ void __launch_bounds__(256, 2)
 k_pcg_ebe(const EbeArgs a) {
@@ -375,7 +378,7 @@ k_pcg_ebe(const EbeArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t n = a.nb, nc = a.nc;
-  const bool multi = a.dist.world > 1;
+  const bool multi = a.dist.world > 1 || a.dist.force_multi;
   const uint8_t* __restrict__ owned = multi ? a.dist.owned : nullptr;
   unsigned long long epoch = multi ? a.dist.win[a.dist.rank]->epoch : 0ull;
   double* P0 = a.partials;
@@ -449,9 +452,10 @@ k_pcg_ebe(const EbeArgs a) {
     double v[2] = {rz, rr};
     dist_allreduce<2>(grid, a.dist, epoch, v);
     rz = v[0]; rr = v[1];
+    dist_unpack(a.dist, a.z, tid, nth, n);  // ghost z: from the exchange slot into the vector (the barrier below orders it)
   }
   double beta = 0.0;
-  unsigned long long tA = 0, tB = 0, tC = 0;
+  unsigned long long tA = 0, tB = 0, tC = 0, tR = 0, tP = 0;
   grid.sync();  // P2 is reused by the first iteration
   const double tol2 = a.rtol * a.rtol * bb;
   if (bb > 0.0 && rr > tol2) {
@@ -472,8 +476,10 @@ k_pcg_ebe(const EbeArgs a) {
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
           const bool ok = i < n;
+          // the ownership byte is loaded alongside the row data, not ahead of it (no extra dependent-load level);
+          // ghost rows gather too (harmless, few) but are not stored
           own[u] = ok && (!owned || owned[i]);
-          lo[u] = own[u] ? a.vptr[i] : 0; hi[u] = own[u] ? a.vptr[i + 1] : 0;
+          lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
           pv[u] = ok ? fma(beta, a.p[i], __ldcg(a.z + i)) : 0.0;
         }
 #pragma unroll
@@ -501,21 +507,25 @@ k_pcg_ebe(const EbeArgs a) {
         double v[1] = {pap};
         dist_allreduce<1>(grid, a.dist, epoch, v);
         pap = v[0];
+        const unsigned long long tr = ebe_now();
+        tR += tr - t0;
       }
       const double alpha = rz / pap;
+      const unsigned long long tc0 = ebe_now();
       // -- C: x += alpha p ; r -= alpha Ap ; z = Binv r (block rows recomputed: no barrier) ; rz, rr  (owned rows only)
       double lrz2 = 0.0, lrr = 0.0;
       for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
         int sb[UNR], mb[UNR], ro[UNR];
         double ri[UNR], zi[UNR], xi[UNR], pi[UNR];
-        bool own[UNR];
+        uint8_t ob[UNR];  // 0 ghost row, 1 owned, 2 owned and pushed to neighbours
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
-          own[u] = i < n && (!owned || owned[i]);
-          sb[u] = own[u] ? a.bstart[i] : 0; mb[u] = own[u] ? a.bsize[i] : 0; ro[u] = own[u] ? a.rowoff[i] : 0;
-          ri[u] = own[u] ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
-          xi[u] = own[u] ? a.x[i] : 0.0; pi[u] = own[u] ? a.p[i] : 0.0;
+          const bool ok = i < n;
+          ob[u] = ok ? (owned ? owned[i] : (uint8_t)1) : (uint8_t)0;
+          sb[u] = ok ? a.bstart[i] : 0; mb[u] = ok ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
+          ri[u] = ok ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
+          xi[u] = ok ? a.x[i] : 0.0; pi[u] = ok ? a.p[i] : 0.0;
           zi[u] = 0.0;
         }
 #pragma unroll
@@ -527,21 +537,27 @@ k_pcg_ebe(const EbeArgs a) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           const int64_t i = i0 + u * nth;
-          if (own[u]) {
+          if (ob[u]) {
             a.x[i] = fma(alpha, pi[u], xi[u]);
             r_new[i] = ri[u]; a.z[i] = zi[u];
             lrz2 = fma(ri[u], zi[u], lrz2);
             lrr = fma(ri[u], ri[u], lrr);
           }
         }
+        // halo: the owner stores z straight into the neighbours' exchange slots (ordered before the flag by the grid
+        // barrier and the cumulative system-scope fence of the posting thread, gg_dist.cuh)
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+          if (ob[u] == 2) dist_push_row(a.dist, i0 + u * nth, zi[u]);
       }
       lrz2 = ebe_block_sum(lrz2, sh);
       lrr = ebe_block_sum(lrr, sh);
       if (threadIdx.x == 0) { P0[blockIdx.x] = lrz2; P1[blockIdx.x] = lrr; }
+      const unsigned long long tc1 = ebe_now();
       grid.sync();
-      if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
       t1 = ebe_now();
       tC += t1 - t0;
+      tP += tc1 - tc0;
       { double* t = r_old; r_old = r_new; r_new = t; }
       double rz_new = ebe_grid_total(P0, nbk, sh);
       rr = ebe_grid_total(P1, nbk, sh);
@@ -549,6 +565,8 @@ k_pcg_ebe(const EbeArgs a) {
         double v[2] = {rz_new, rr};
         dist_allreduce<2>(grid, a.dist, epoch, v);
         rz_new = v[0]; rr = v[1];
+        if (rr > tol2) { dist_unpack(a.dist, a.z, tid, nth, n); grid.sync(); }
+        tR += ebe_now() - t1;
       }
       if (rr <= tol2) break;  // uniform across the grid and across the ranks
       beta = rz_new / rz;
@@ -596,6 +614,7 @@ k_pcg_ebe(const EbeArgs a) {
     a.stats[0] = (double)itc;
     a.stats[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
     a.stats[2] += (double)tA; a.stats[3] += (double)tB; a.stats[4] += (double)tC; a.stats[5] += (double)itc;
+    a.stats[6] += (double)tR; a.stats[7] += (double)tP;
   }
 }
 
@@ -770,7 +789,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;
   a.warm = warm ? 1 : 0;
   a.dist = dist_dev(sp);
-  if (a.dist.world > 1) a.z = (double*)((char*)sp->mesh->comm->window + sizeof(WinHeader));  // peers store ghost z here
+  if (getenv("GG_FORCE_MULTI") && a.dist.win) a.dist.force_multi = 1;  // measurement: run the partitioned code path on one rank
   void* fn = ebe_kernel(s->MB, s->MI);
   int grid = s->grid;
   const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;

@@ -453,6 +453,10 @@ int gg_rk_solver_phase_ns(gg_rk* rk, int which, double* out) {
   if (e) e->stats.download(h, rk->ctx->stream);
   else s->stats.download(h, rk->ctx->stream);
   for (int i = 0; i < 4; ++i) out[i] = h[2 + i];
+  if (getenv("GG_COMM_STATS") && h[5] > 0)
+    fprintf(stderr, "[gg_rk solver %d] per iteration: cells %.1f  gather+dot %.1f  update+precond %.1f us, of which all-reduce rounds %.1f "
+                    "and thread 0's own phase-C loop %.1f us\n", which, 1e-3 * h[2] / h[5], 1e-3 * h[3] / h[5], 1e-3 * h[4] / h[5], 1e-3 * h[6] / h[5],
+            1e-3 * h[7] / h[5]);
   GG_API_END
 }
 
