@@ -109,16 +109,25 @@ class CubedSphereMesh:
         self.radius = float(radius)
 
 
+class CubedSphereWithThicknessMesh:
+    """CubedSphereWithThicknessMesh(radius, thickness) -- src/Geometry/CubedSphereWithThicknessMesh.jl:11-16: the 3-D shell
+    between the spheres of radius `radius` and `radius + thickness`, chart coordinates (γ, α, β)."""
+
+    def __init__(self, radius=1.0, thickness=0.1):
+        self.radius, self.thickness = float(radius), float(thickness)
+
+
 class AtlasDiscreteModel:
     """AtlasDiscreteModel(CubedSphereMesh(r), nref; manifold_style) -- src/Geometry/AtlasDiscreteModels.jl:222-229.
 
     `n` (cells per panel edge) may be given instead of `nref` (n = 2**nref); the reference only offers powers of two."""
 
-    def __init__(self, mesh, nref=None, *, n=None, manifold_style=None, ctx=None, _handle=None):
+    def __init__(self, mesh, nref=None, *, n=None, n_layers=None, manifold_style=None, ctx=None, _handle=None):
         self.ctx = ctx or get_context()
         self.lib = self.ctx.lib
         self.mesh = mesh
         self.manifold_style = manifold_style or IntrinsicManifold()
+        self.dim = 3 if isinstance(mesh, CubedSphereWithThicknessMesh) else 2
         if _handle is not None:
             self.h = _handle
             self.n = 0
@@ -129,7 +138,12 @@ class AtlasDiscreteModel:
                 n = 2 ** int(nref)
             self.n = int(n)
             h = C.c_void_p()
-            _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, 0, C.byref(h)))
+            if self.dim == 3:
+                # the reference refines the 6 coarse hexahedra isotropically: n cells through the shell unless n_layers is given
+                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 3, self.n, int(n_layers or 0), mesh.radius, mesh.thickness, 0, C.byref(h)))
+                self.n_layers = int(n_layers or self.n)
+            else:
+                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, 0, C.byref(h)))
             self.h = h
         nc, nn, ne = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_mesh_info(self.h, C.byref(nc), C.byref(nn), C.byref(ne)))
@@ -160,7 +174,7 @@ class AtlasDiscreteModel:
         return out
 
     def get_cell_node_ids(self):
-        out = np.empty((self.num_cells, 4), dtype=np.int32)
+        out = np.empty((self.num_cells, 2 ** self.dim), dtype=np.int32)
         _lib.check(self.lib.gg_mesh_get_cell_nodes(self.h, _ip32(out)))
         return out
 
@@ -170,7 +184,7 @@ class AtlasDiscreteModel:
         return out
 
     def get_cell_coordinates(self):
-        out = np.empty((self.num_cells, 4, 2))
+        out = np.empty((self.num_cells, 2 ** self.dim, self.dim))
         _lib.check(self.lib.gg_mesh_get_chart_coords(self.h, _dp(out)))
         return out
 
@@ -337,7 +351,7 @@ class Measure:
         self.model = trian.model
         self.degree = int(degree)
         self.nq1 = (self.degree + 2) // 2
-        self.num_points = self.nq1 ** 2
+        self.num_points = self.nq1 ** self.model.dim
 
     def quadrature_points(self, chart=True, ambient=True):
         m = self.model

@@ -106,6 +106,7 @@ struct gg_ctx {
   int const_order = -1, const_nq = -1;
   // tables resident in the __constant__ blocks of the matrix-free PCG (gg_mf.cu): nq of the weights, (order, nq) keys
   int64_t mf_key_w = -1, mf_key_rt = -1, mf_key_sc = -1;
+  int hex_order = -1;    // order of the hexahedral index tables resident in gg_forms.cu's __constant__ block
   int64_t swe_key = -1;  // (order, nq) of the shallow-water tabulations resident in gg_swe.cu's __constant__ block
   int64_t ebe_key = -1;  // (order, nq) of the pair tables resident in gg_ebe.cu's __constant__ block
   // when set, assembly / solver entry points enqueue their work and return without synchronising the stream
@@ -164,6 +165,18 @@ struct gg_mesh {
   struct TanTab { gg::DevBuf<double> tx, ty; };
   std::map<int, std::shared_ptr<TanTab>> tan_tabs;
   bool topology_built = false;
+  // 3-D shell (dim == 3, src/Geometry/CubedSphereWithThicknessMesh.jl): hexahedra ordered gamma-fastest inside a panel; the
+  // (alpha, beta) geometry of a cell is that of its column, a cell of the 2-D surface mesh `surface`
+  int n_layers = 0;
+  std::vector<int32_t> cell_nodes8;    // [n_cells][8], Gridap hex vertex order (x = gamma fastest)
+  std::vector<int32_t> cell_col, cell_layer;
+  std::vector<int32_t> cell_edges12, cell_faces6;  // hex topology by first encounter (built on demand)
+  int64_t n_faces = 0;
+  std::unique_ptr<gg_mesh> surface;
+  gg::DevBuf<int32_t> d_col, d_layer;
+  // per layer: int N'_i N'_j s^2 / h and int N_i N_j h; per column: scratch for the surface matrices (keyed by order, nq)
+  struct GammaTab { gg::DevBuf<double> Dg, Ng, K2, M2; };
+  std::map<int, std::shared_ptr<GammaTab>> gamma_tabs;
   // partitioned models (gg_dist.cu): the plan this rank-local sub-mesh (owned + ghost cells) was cut from, the peer window
   // used for halo exchanges, and the owned-cell mask (norms and integrals count owned cells only)
   gg_plan* plan = nullptr;
@@ -280,7 +293,9 @@ struct CellGeo {
 CellGeo cell_geo(gg_mesh* m, int nq);
 // host-side construction shared with the partition plans (gg_dist.cu); ctx == nullptr gives a host-only mesh
 gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius);
-void upload_geometry(gg_mesh* m);  // per-cell chart boxes, interval tables and the owned-cell mask -> device
+void upload_geometry(gg_mesh* m);
+gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int n_layers, double radius, double thickness);
+std::vector<int32_t> hex_local_to_lex(int p);  // per-cell chart boxes, interval tables and the owned-cell mask -> device
 void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s);
 void space_from_plan(gg_mesh* m, int kind, int order, gg_space* s);
 void space_upload_dist(gg_space* s);

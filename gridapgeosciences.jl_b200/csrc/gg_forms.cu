@@ -14,6 +14,7 @@
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
 #include "gg_lb_fast.cuh"
+#include "gg_hex.cuh"
 
 namespace gg {
 
@@ -509,6 +510,108 @@ static void form_coefficients(gg_form form, double* cM, double* cK, bool* extrin
   }
 }
 
+// ---- 3-D shell: Kronecker path (gg_hex.cuh) ----------------------------------------------------------------------------------
+struct HexWork {
+  const double *K2, *M2, *Dg, *Ng;
+  int64_t ncol;
+};
+
+static void load_hex_tables(gg_ctx* ctx, int order) {
+  if (ctx->hex_order == order) return;
+  const int nb = order + 1, m2 = nb * nb, m3 = m2 * nb, G = nb * nb;
+  std::vector<int32_t> l2 = quad_local_to_lex(order), l3 = hex_local_to_lex(order);
+  std::vector<int32_t> loc3(m3);
+  for (int I = 0; I < m3; ++I) loc3[l3[I]] = I;
+  std::vector<int32_t> t3(3 * 9, 0), plane(45 * 9, -1);
+  for (int i0 = 0; i0 < nb; ++i0)
+    for (int A = 0; A < m2; ++A) t3[i0 * m2 + A] = loc3[i0 + nb * l2[A]];
+  int p2 = 0;
+  for (int a = 0; a < m2; ++a)
+    for (int b = a; b < m2; ++b) {
+      for (int i0 = 0; i0 < nb; ++i0)
+        for (int j0 = 0; j0 < nb; ++j0) {
+          if (a == b && i0 > j0) continue;  // the unordered pair is produced by (j0, i0)
+          int I = t3[i0 * m2 + a], J = t3[j0 * m2 + b];
+          int lo = std::min(I, J), hi = std::max(I, J);
+          plane[p2 * G + i0 * nb + j0] = lo * m3 - (lo * (lo - 1)) / 2 + (hi - lo);
+        }
+      ++p2;
+    }
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old tables
+  GG_CUDA(cudaMemcpyToSymbol(c_hex_t3, t3.data(), t3.size() * sizeof(int32_t)));
+  GG_CUDA(cudaMemcpyToSymbol(c_hex_plane, plane.data(), plane.size() * sizeof(int32_t)));
+  ctx->hex_order = order;
+}
+
+// per-column surface matrices (re-integrated on every call) and per-layer radial matrices (cached) of a shell mesh
+static HexWork hex_prepare(gg_mesh* m, int order, int nq) {
+  gg_ctx* ctx = m->ctx;
+  gg_mesh* ms = m->surface.get();
+  GG_REQUIRE(order == 1 || order == 2, GG_ERR_UNSUPPORTED, "the 3-D shell path implements hexahedral Q1 / Q2");
+  GG_REQUIRE(fast_lb_available(order, nq), GG_ERR_UNSUPPORTED, "no surface kernel for this (order, quadrature degree) on the shell");
+  const int nb = order + 1, m2 = nb * nb, G = nb * nb;
+  const int64_t ncol = ms->n_cells;
+  const int key = order * 64 + nq;
+  auto it = m->gamma_tabs.find(key);
+  if (it == m->gamma_tabs.end()) {
+    std::vector<double> xi(nq), w(nq), N(nb), D(nb), Dg((size_t)m->n_layers * G, 0.0), Ng((size_t)m->n_layers * G, 0.0);
+    gauss_legendre_01(nq, xi.data(), w.data());
+    const double hg = 1.0 / m->n_layers;
+    for (int l = 0; l < m->n_layers; ++l)
+      for (int q = 0; q < nq; ++q) {
+        lagrange_1d(order, xi[q], N.data(), D.data());
+        const double s = 1.0 + m->thickness * (l + xi[q]) * hg / m->radius;
+        for (int i = 0; i < nb; ++i)
+          for (int j = 0; j < nb; ++j) {
+            Dg[(size_t)l * G + i * nb + j] += w[q] * D[i] * D[j] * s * s / hg;
+            Ng[(size_t)l * G + i * nb + j] += w[q] * N[i] * N[j] * hg;
+          }
+      }
+    auto T = std::make_shared<gg_mesh::GammaTab>();
+    T->Dg.upload(Dg, ctx->stream); T->Ng.upload(Ng, ctx->stream);
+    T->K2.alloc((size_t)(m2 * (m2 + 1) / 2) * ncol); T->M2.alloc((size_t)m2 * m2 * ncol);
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = m->gamma_tabs.emplace(key, T).first;
+  }
+  auto& T = *it->second;
+  // K2: the 2-D hot kernel on the surface mesh (packed symmetric, entry-major)
+  load_const_tables(ctx, order, nq);
+  CellGeo g2 = cell_geo(ms, nq);
+  run_lb_fast_range(ms, order, nq, false, 0, ncol, g2, nullptr, nullptr, 0.0, T.K2.p, nullptr);
+  // M2: scalar mass with sqrtg_surf (full, entry-major)
+  {
+    auto tt = get_tab(ctx, GG_SPACE_CG, order, nq);
+    Geo g = geo_of(ms);
+    unsigned nbk = nblk(ncol * m2, 128);
+    if (m2 == 4) k_scalar_matrix<4, false><<<nbk, 128, 0, ctx->stream>>>(g, nq, tt->xi.p, tt->w.p, m2, tt->val.p, tt->der.p, tt->val.p, tt->der.p, 1.0, 0.0, nullptr, T.M2.p);
+    else k_scalar_matrix<9, false><<<nbk, 128, 0, ctx->stream>>>(g, nq, tt->xi.p, tt->w.p, m2, tt->val.p, tt->der.p, tt->val.p, tt->der.p, 1.0, 0.0, nullptr, T.M2.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
+  load_hex_tables(ctx, order);
+  return {T.K2.p, T.M2.p, T.Dg.p, T.Ng.p, ncol};
+}
+
+static void run_hex_lb(gg_mesh* m, int order, int nq, const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf) {
+  gg_ctx* ctx = m->ctx;
+  HexWork W = hex_prepare(m, order, nq);
+  const int64_t nc = m->n_cells;
+  unsigned nbk = nblk(nc, 128);
+  if (ebuf) {
+    ProfScope ps(ctx, "k_hex_kron");
+    if (order == 1) k_hex_kron<2><<<nbk, 128, 0, ctx->stream>>>(nc, W.ncol, m->d_col.p, m->d_layer.p, W.K2, W.M2, W.Dg, W.Ng, m->thickness, ebuf);
+    else k_hex_kron<3><<<nbk, 128, 0, ctx->stream>>>(nc, W.ncol, m->d_col.p, m->d_layer.p, W.K2, W.M2, W.Dg, W.Ng, m->thickness, ebuf);
+    ctx->launches++;
+  }
+  if (vbuf) {
+    ProfScope ps(ctx, "k_hex_residual");
+    if (order == 1) k_hex_residual<2><<<nbk, 128, 0, ctx->stream>>>(nc, W.ncol, m->d_col.p, m->d_layer.p, W.K2, W.M2, W.Dg, W.Ng, m->thickness, dofs, u, dir, vbuf);
+    else k_hex_residual<3><<<nbk, 128, 0, ctx->stream>>>(nc, W.ncol, m->d_col.p, m->d_layer.p, W.K2, W.M2, W.Dg, W.Ng, m->thickness, dofs, u, dir, vbuf);
+    ctx->launches++;
+  }
+  GG_CUDA(cudaGetLastError());
+}
+
 // element matrices into ctx->ebuf; returns the buffer layout (0 full entry-major, 1 symmetric packed entry-major)
 static int compute_element_matrices(gg_form form, const gg_form_args* a, const Plan& P, bool want_fused_vector, double** vbuf_out,
                                     const FillPipe* pipe = nullptr) {
@@ -518,6 +621,21 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
   int64_t nc = g.nc;
   if (vbuf_out) *vbuf_out = nullptr;
   if (nc == 0) return 0;
+  if (P.mesh->dim == 3) {
+    GG_REQUIRE(form == GG_FORM_LAPLACE_BELTRAMI && !a->qdata, GG_ERR_UNSUPPORTED, "on the 3-D shell only the Laplace-Beltrami form is implemented");
+    GG_REQUIRE(P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG && P.test->order == P.trial->order, GG_ERR_INVALID,
+               "the shell Laplace-Beltrami form needs CG test/trial spaces of the same order");
+    size_t np = (size_t)P.mt * (P.mt + 1) / 2;
+    double* eb = scratch(ctx->ebuf, np * nc);
+    double* vb = nullptr;
+    if (want_fused_vector) {
+      GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "fused residual needs args->u of the trial size");
+      vb = scratch(ctx->vbuf, (size_t)P.mt * nc);
+      *vbuf_out = vb;
+    }
+    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb);
+    return 1;
+  }
   const bool stiffness = form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC;
   if (form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC || form == GG_FORM_HELMHOLTZ ||
       form == GG_FORM_MASS_SCALAR) {
@@ -596,6 +714,13 @@ static double* compute_element_vectors(gg_form form, const gg_form_args* a, cons
   int64_t nc = g.nc;
   double* vb = scratch(ctx->vbuf, (size_t)P.mt * std::max<int64_t>(nc, 1));
   if (nc == 0) return vb;
+  if (P.mesh->dim == 3) {
+    GG_REQUIRE(form == GG_FORM_LAPLACE_BELTRAMI && P.trial && P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG &&
+                   P.test->order == P.trial->order, GG_ERR_UNSUPPORTED, "on the 3-D shell only the Laplace-Beltrami action is implemented");
+    GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u missing or of the wrong length");
+    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb);
+    return vb;
+  }
   if (form == GG_FORM_SOURCE) {
     GG_REQUIRE(is_scalar(P.test), GG_ERR_INVALID, "source form needs a Lagrangian test space");
     GG_REQUIRE(a->qdata && gg_vec_size(a->qdata) == nc * P.nq * P.nq, GG_ERR_INVALID, "source form needs qdata of length n_cells*Q");
@@ -725,6 +850,7 @@ int gg_element_vectors(gg_form form, const gg_form_args* args, int64_t first_cel
 int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* out_xyz) {
   GG_API_BEGIN
   GG_REQUIRE(m, GG_ERR_INVALID, "null mesh");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "quadrature points of the 3-D shell are not exported");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   int nq = num_points_1d(degree);
@@ -748,10 +874,15 @@ int gg_integrate(gg_mesh* m, int32_t degree, gg_vec* qdata, double* out) {
   int nq = num_points_1d(degree);
   auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
   int64_t nc = m->n_cells;
-  if (qdata) GG_REQUIRE(gg_vec_size(qdata) == nc * nq * nq, GG_ERR_INVALID, "qdata has the wrong length");
+  if (qdata && m->dim == 2) GG_REQUIRE(gg_vec_size(qdata) == nc * nq * nq, GG_ERR_INVALID, "qdata has the wrong length");
   *out = 0.0;
   if (nc == 0) return GG_OK;
   DevBuf<double> sums(nc), total(1);
+  if (m->dim == 3) {
+    if (qdata) GG_REQUIRE(gg_vec_size(qdata) == nc * nq * nq * nq, GG_ERR_INVALID, "qdata has the wrong length");
+    k_integrate_shell<<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, m->n, m->n_layers, m->radius, m->thickness, nq, T->xi.p, T->w.p,
+                                                             m->d_col.p, m->d_layer.p, qdata ? qdata->d.p : nullptr, sums.p);
+  } else
   k_integrate_cells<<<nblk(nc, 128), 128, 0, ctx->stream>>>(geo_of(m), nq, T->xi.p, T->w.p, qdata ? qdata->d.p : nullptr,
                                                             m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;

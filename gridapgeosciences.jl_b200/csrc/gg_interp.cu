@@ -146,6 +146,7 @@ int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* x
   GG_API_BEGIN
   GG_REQUIRE(s, GG_ERR_INVALID, "null space");
   gg_mesh* m = s->mesh;
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "interpolation on the 3-D shell is not implemented");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   std::vector<double> ref = interp_ref_points(s, nullptr);
@@ -170,6 +171,7 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && vals && out, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(gg_vec_size(out) == s->n_free, GG_ERR_INVALID, "output vector has the wrong length");
+  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "interpolation on the 3-D shell is not implemented");
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
@@ -205,6 +207,7 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && e && out, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(gg_vec_size(e) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "norms on the 3-D shell are not implemented");
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <unordered_map>
 #include "gg_common.cuh"
 #include "gg_refel.cuh"
 
@@ -191,6 +192,140 @@ gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
   return m.release();
 }
 
+// ---- 3-D shell ------------------------------------------------------------------------------------------------------------
+// local vertices of the 12 edges and 6 faces of the hexahedron, Gridap order
+static const int HEX_EDGE_V[12][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {0, 2}, {1, 3}, {4, 6}, {5, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+static const int HEX_FACE_V[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}, {0, 2, 4, 6}, {1, 3, 5, 7}};
+// panel permutation table of the gnomonic map (src/Fields/CubedSphereMap.jl:19-26), 0-based component, sign
+static const int PERM_J[6][3] = {{0, 1, 2}, {2, 1, 0}, {1, 0, 2}, {0, 2, 1}, {1, 2, 0}, {2, 0, 1}};
+static const int PERM_S[6][3] = {{1, 1, 1}, {-1, 1, 1}, {-1, 1, 1}, {-1, 1, 1}, {-1, 1, -1}, {-1, -1, 1}};
+
+// ids of entities given by up to 4 vertex ids each, numbered by first encounter (same scheme as build_edges)
+static int64_t number_entities(int64_t n_refs, int nv, const std::vector<int32_t>& verts, std::vector<int32_t>& ids) {
+  struct Ref { int32_t v[4]; int64_t idx; };
+  std::vector<Ref> refs(n_refs);
+  for (int64_t i = 0; i < n_refs; ++i) {
+    int32_t tmp[4] = {-1, -1, -1, -1};
+    for (int k = 0; k < nv; ++k) tmp[k] = verts[i * nv + k];
+    std::sort(tmp, tmp + nv);
+    for (int k = 0; k < 4; ++k) refs[i].v[k] = tmp[k];
+    refs[i].idx = i;
+  }
+  auto less = [](const Ref& a, const Ref& b) {
+    for (int k = 0; k < 4; ++k) if (a.v[k] != b.v[k]) return a.v[k] < b.v[k];
+    return a.idx < b.idx;
+  };
+  std::sort(refs.begin(), refs.end(), less);
+  std::vector<int64_t> group_first, group_of(n_refs);
+  for (int64_t i = 0; i < n_refs; ++i) {
+    bool fresh = i == 0;
+    if (!fresh) for (int k = 0; k < 4; ++k) fresh = fresh || refs[i].v[k] != refs[i - 1].v[k];
+    if (fresh) group_first.push_back(refs[i].idx);
+    group_of[refs[i].idx] = (int64_t)group_first.size() - 1;
+  }
+  int64_t ne = (int64_t)group_first.size();
+  std::vector<int64_t> order(ne);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return group_first[a] < group_first[b]; });
+  std::vector<int32_t> rank(ne);
+  for (int64_t r = 0; r < ne; ++r) rank[order[r]] = (int32_t)r;
+  ids.resize(n_refs);
+  for (int64_t i = 0; i < n_refs; ++i) ids[i] = rank[group_of[i]];
+  return ne;
+}
+
+static void ensure_hex_topology(gg_mesh* m) {
+  if (m->topology_built) return;
+  int64_t nc = m->n_cells;
+  std::vector<int32_t> ev(nc * 12 * 2), fv(nc * 6 * 4);
+  for (int64_t c = 0; c < nc; ++c) {
+    for (int e = 0; e < 12; ++e)
+      for (int k = 0; k < 2; ++k) ev[(c * 12 + e) * 2 + k] = m->cell_nodes8[c * 8 + HEX_EDGE_V[e][k]];
+    for (int f = 0; f < 6; ++f)
+      for (int k = 0; k < 4; ++k) fv[(c * 6 + f) * 4 + k] = m->cell_nodes8[c * 8 + HEX_FACE_V[f][k]];
+  }
+  m->n_edges = number_entities(nc * 12, 2, ev, m->cell_edges12);
+  m->n_faces = number_entities(nc * 6, 4, fv, m->cell_faces6);
+  m->topology_built = true;
+}
+
+// AtlasDiscreteModel(CubedSphereWithThicknessMesh(radius, thickness), l): n x n cells per panel, L cells through the shell
+// (src/Geometry/CubedSphereWithThicknessMesh.jl:33-124, AtlasGrids.jl:227-304; the reference refines isotropically, L = n).
+// Nodes are identified through their integer position on the cube-surface lattice and numbered by first encounter.
+gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, double thickness) {
+  std::unique_ptr<gg_mesh> m(new gg_mesh);
+  m->ctx = ctx; m->dim = 3; m->n = n; m->n_layers = L; m->radius = radius; m->thickness = thickness;
+  int64_t nc = 6LL * n * n * L;
+  GG_REQUIRE(nc * 27 < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "shell mesh too large for Int32 ids");
+  m->n_cells = nc;
+  m->cell_nodes8.resize(nc * 8); m->cell_to_chart.resize(nc); m->cell_col.resize(nc); m->cell_layer.resize(nc);
+  std::unordered_map<uint64_t, int32_t> nodes;
+  nodes.reserve((size_t)(6LL * n * n + 2) * (L + 1) * 2);
+  int64_t c = 0;
+  for (int p = 0; p < 6; ++p)
+    for (int jb = 0; jb < n; ++jb)
+      for (int ia = 0; ia < n; ++ia)
+        for (int kg = 0; kg < L; ++kg) {
+          for (int v = 0; v < 8; ++v) {
+            int dg = v & 1, da = (v >> 1) & 1, db = (v >> 2) & 1;
+            int h[3] = {n, 2 * (ia + da) - n, 2 * (jb + db) - n};
+            uint64_t key = 0;
+            for (int k = 0; k < 3; ++k) key = key * (uint64_t)(2 * n + 1) + (uint64_t)(PERM_S[p][k] * h[PERM_J[p][k]] + n);
+            key = key * (uint64_t)(L + 1) + (uint64_t)(kg + dg);
+            auto it = nodes.find(key);
+            if (it == nodes.end()) it = nodes.emplace(key, (int32_t)nodes.size()).first;
+            m->cell_nodes8[c * 8 + v] = it->second;
+          }
+          m->cell_to_chart[c] = p;
+          m->cell_col[c] = (int32_t)((int64_t)p * n * n + (int64_t)jb * n + ia);
+          m->cell_layer[c] = kg;
+          ++c;
+        }
+  m->n_nodes = (int64_t)nodes.size();
+  m->surface.reset(build_cubed_sphere(ctx, n, radius));
+  if (ctx) {
+    m->d_col.upload(m->cell_col, ctx->stream); m->d_layer.upload(m->cell_layer, ctx->stream);
+    m->d_chart.upload(m->cell_to_chart, ctx->stream);
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return m.release();
+}
+
+// Gridap local node of Q_p on the hexahedron (vertices, edges, faces, interior) -> lexicographic i0 + nb (i1 + nb i2)
+std::vector<int32_t> hex_local_to_lex(int p) {
+  int nb = p + 1;
+  if (p == 0) return {0};
+  std::vector<int32_t> out;
+  auto lex = [&](int i0, int i1, int i2) { return i0 + nb * (i1 + nb * i2); };
+  for (int v = 0; v < 8; ++v) out.push_back(lex((v & 1) * p, ((v >> 1) & 1) * p, ((v >> 2) & 1) * p));
+  // edges: spanning axis S, the fixed axes take the end-point values (first fixed axis fastest)
+  for (int S = 0; S < 3; ++S)
+    for (int bits = 0; bits < 4; ++bits) {
+      int fa[2], k = 0;
+      for (int a = 0; a < 3; ++a) if (a != S) fa[k++] = a;
+      for (int t = 1; t < p; ++t) {
+        int mi[3];
+        mi[S] = t; mi[fa[0]] = (bits & 1) * p; mi[fa[1]] = ((bits >> 1) & 1) * p;
+        out.push_back(lex(mi[0], mi[1], mi[2]));
+      }
+    }
+  // faces: spanning axes (0,1) z fixed, (0,2) y fixed, (1,2) x fixed; first spanning axis fastest
+  const int SP[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+  const int FX[3] = {2, 1, 0};
+  for (int f = 0; f < 3; ++f)
+    for (int bit = 0; bit < 2; ++bit)
+      for (int t1 = 1; t1 < p; ++t1)
+        for (int t0 = 1; t0 < p; ++t0) {
+          int mi[3];
+          mi[SP[f][0]] = t0; mi[SP[f][1]] = t1; mi[FX[f]] = bit * p;
+          out.push_back(lex(mi[0], mi[1], mi[2]));
+        }
+  for (int t2 = 1; t2 < p; ++t2)
+    for (int t1 = 1; t1 < p; ++t1)
+      for (int t0 = 1; t0 < p; ++t0) out.push_back(lex(t0, t1, t2));
+  return out;
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -201,13 +336,18 @@ int gg_mesh_cubed_sphere(gg_ctx* ctx, int dim, int n, int n_layers, double radiu
                          gg_mesh** out) {
   GG_API_BEGIN
   GG_REQUIRE(ctx && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(dim == 2, GG_ERR_UNSUPPORTED, "only the 2-D cubed-sphere surface is implemented (dim=3 shell: not yet)");
+  GG_REQUIRE(dim == 2 || dim == 3, GG_ERR_INVALID, "dim must be 2 (surface) or 3 (shell)");
   GG_REQUIRE(n >= 1, GG_ERR_INVALID, "n must be >= 1");
   GG_REQUIRE(radius > 0, GG_ERR_INVALID, "radius must be positive");
   GG_REQUIRE(ordering == 0, GG_ERR_UNSUPPORTED, "only ordering 0 (one-shot, parent-major lexicographic) is implemented");
-  (void)n_layers; (void)thickness;
   GG_CUDA(cudaSetDevice(ctx->device));
-  *out = build_cubed_sphere(ctx, n, radius);
+  if (dim == 3) {
+    GG_REQUIRE(thickness > 0, GG_ERR_INVALID, "shell thickness must be positive");
+    GG_REQUIRE(n_layers >= 0, GG_ERR_INVALID, "n_layers must be >= 0 (0: isotropic refinement, n layers)");
+    *out = build_cubed_sphere_shell(ctx, n, n_layers > 0 ? n_layers : n, radius, thickness);
+  } else {
+    *out = build_cubed_sphere(ctx, n, radius);
+  }
   GG_API_END
 }
 
@@ -245,13 +385,17 @@ int gg_mesh_info(gg_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* n_edge
   GG_REQUIRE(m, GG_ERR_INVALID, "null mesh");
   if (n_cells) *n_cells = m->n_cells;
   if (n_nodes) *n_nodes = m->n_nodes;
-  if (n_edges) { ensure_topology(m); *n_edges = m->n_edges; }
+  if (n_edges) { if (m->dim == 3) ensure_hex_topology(m); else ensure_topology(m); *n_edges = m->n_edges; }
   GG_API_END
 }
 
 int gg_mesh_get_cell_nodes(gg_mesh* m, int32_t* out) {
   GG_API_BEGIN
   GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  if (m->dim == 3) {
+    for (size_t i = 0; i < m->cell_nodes8.size(); ++i) out[i] = m->cell_nodes8[i] + 1;
+    return GG_OK;
+  }
   for (size_t i = 0; i < m->cell_nodes.size(); ++i) out[i] = m->cell_nodes[i] + 1;
   GG_API_END
 }
@@ -266,6 +410,19 @@ int gg_mesh_get_cell_to_chart(gg_mesh* m, int32_t* out) {
 int gg_mesh_get_chart_coords(gg_mesh* m, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(m && out, GG_ERR_INVALID, "null argument");
+  if (m->dim == 3) {
+    // [n_cells][8][3], coordinates (gamma, alpha, beta)
+    const double H = M_PI / 4;
+    for (int64_t c = 0; c < m->n_cells; ++c) {
+      int col = m->cell_col[c] % (m->n * m->n), ia = col % m->n, jb = col / m->n, kg = m->cell_layer[c];
+      for (int v = 0; v < 8; ++v) {
+        out[(c * 8 + v) * 3 + 0] = (double)(kg + (v & 1)) / m->n_layers;
+        out[(c * 8 + v) * 3 + 1] = -H + (ia + ((v >> 1) & 1)) * 2 * H / m->n;
+        out[(c * 8 + v) * 3 + 2] = -H + (jb + ((v >> 2) & 1)) * 2 * H / m->n;
+      }
+    }
+    return GG_OK;
+  }
   std::copy(m->chart_coords.begin(), m->chart_coords.end(), out);
   GG_API_END
 }
@@ -285,6 +442,7 @@ int gg_partition_range(int64_t n_cells, int nparts, int part, int64_t* first, in
 int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** out) {
   GG_API_BEGIN
   GG_REQUIRE(m && out && (cells || n_sub == 0), GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "sub-meshes of the 3-D shell are not implemented");
   GG_CUDA(cudaSetDevice(m->ctx->device));
   std::unique_ptr<gg_mesh> s(new gg_mesh);
   s->ctx = m->ctx; s->dim = m->dim; s->n = 0; s->radius = m->radius; s->thickness = m->thickness;
@@ -306,6 +464,7 @@ int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** 
 int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghost, int64_t* out) {
   GG_API_BEGIN
   GG_REQUIRE(m && n_ghost, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "ghost layers of the 3-D shell are not implemented");
   GG_REQUIRE(first >= 0 && first <= last && last <= m->n_cells, GG_ERR_INVALID, "bad owned range");
   std::vector<uint8_t> touched(m->n_nodes, 0);
   for (int64_t c = first; c < last; ++c)
@@ -328,13 +487,12 @@ int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghos
 
 static void finish_space(gg_space* s) {
   gg_mesh* m = s->mesh;
-  if (s->kind != GG_SPACE_RT) s->loc2lex = quad_local_to_lex(s->order);
+  if (s->kind != GG_SPACE_RT) s->loc2lex = m->dim == 3 ? hex_local_to_lex(s->order) : quad_local_to_lex(s->order);
   if (!m->ctx) return;  // host-only space (partition plans)
   cudaStream_t st = m->ctx->stream;
   s->d_cell_dofs.upload(s->cell_dofs, st);
   if (!s->cell_signs.empty()) s->d_cell_signs.upload(s->cell_signs, st);
   GG_CUDA(cudaStreamSynchronize(st));
-  if (s->kind != GG_SPACE_RT) s->loc2lex = quad_local_to_lex(s->order);
 }
 
 }  // extern "C"
@@ -344,6 +502,43 @@ namespace gg {
 void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s) {
   s->mesh = m; s->kind = kind; s->order = order; s->constraint = constraint;
   int64_t nc = m->n_cells;
+  if (m->dim == 3) {
+    // hexahedral Q_p: vertices, edges, faces, interior (one DOF per entity for p = 2)
+    if (kind == GG_SPACE_DG) {
+      GG_REQUIRE(order >= 0 && order <= 2 && constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "hex DG order must be in 0..2");
+      int mloc = (order + 1) * (order + 1) * (order + 1);
+      s->ndofs_loc = mloc; s->n_free = nc * mloc;
+      s->cell_dofs.resize(nc * mloc);
+      std::iota(s->cell_dofs.begin(), s->cell_dofs.end(), 0);
+      return;
+    }
+    GG_REQUIRE(kind == GG_SPACE_CG && (order == 1 || order == 2), GG_ERR_UNSUPPORTED, "on the 3-D shell only CG Q1/Q2 and DG spaces are implemented");
+    int mloc = (order + 1) * (order + 1) * (order + 1);
+    s->ndofs_loc = mloc;
+    s->cell_dofs.resize(nc * mloc);
+    int64_t nd = m->n_nodes;
+    if (order == 2) { ensure_hex_topology(m); nd += m->n_edges + m->n_faces + nc; }
+    GG_REQUIRE(nd < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
+    for (int64_t c = 0; c < nc; ++c) {
+      int32_t* o = &s->cell_dofs[c * mloc];
+      int k = 0;
+      for (int v = 0; v < 8; ++v) o[k++] = m->cell_nodes8[c * 8 + v];
+      if (order == 2) {
+        for (int e = 0; e < 12; ++e) o[k++] = (int32_t)(m->n_nodes + m->cell_edges12[c * 12 + e]);
+        for (int f = 0; f < 6; ++f) o[k++] = (int32_t)(m->n_nodes + m->n_edges + m->cell_faces6[c * 6 + f]);
+        o[k++] = (int32_t)(m->n_nodes + m->n_edges + m->n_faces + c);
+      }
+    }
+    if (constraint == GG_CONSTRAINT_ZEROMEAN) {
+      for (auto& d : s->cell_dofs)
+        if (d == nd - 1) d = -1;
+      s->n_free = nd - 1; s->n_dirichlet = 1;
+    } else {
+      GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_INVALID, "unknown constraint");
+      s->n_free = nd;
+    }
+    return;
+  }
   if (kind == GG_SPACE_CG) {
     GG_REQUIRE(order >= 1 && order <= 4, GG_ERR_UNSUPPORTED, "CG order must be in 1..4");
     ensure_topology(m);

@@ -261,6 +261,7 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
   GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "the RK steppers support RT_p x DG_p with p <= 2");
   GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "the RK steppers run on the 2-D cubed sphere");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   raw = new gg_rk;

@@ -1,0 +1,146 @@
+"""Oracle (test infrastructure): the 3-D cubed-sphere shell -- mesh, hexahedral Q_p numbering, Laplace-Beltrami forms.
+
+Restates
+  /root/reference/src/Geometry/CubedSphereWithThicknessMesh.jl:33-124  16-node / 6-hex coarse shell, chart box
+                                                                       [0,1] x [-pi/4,pi/4]^2, coordinate order (gamma, alpha, beta)
+  /root/reference/src/Geometry/AtlasGrids.jl:227-304                   one-shot refinement by n in every direction, parent-major
+                                                                       cell order, reference-grid (x = gamma fastest) order inside
+  /root/reference/src/Fields/CubedSphereWithThickness{Map,Metric,InvMetric}.jl  (geometry: oracle/geometry.py csphere3d_*)
+  /root/reference/test/Laplacian/LaplaceBeltrami.jl:47                 a(u,v) = int grad(v).(ginv.grad(u)) sqrtg, here in 3-D
+PARITY UNPINNED (Gridap internals): local order of hex nodes = vertices (x fastest), edges (4 x-dir,
+4 y-dir, 4 z-dir), faces (z=0, z=1, y=0, y=1, x=0, x=1), interior; edge / face ids by first encounter over cells and local
+entities.  Fine-mesh NODE ids are numbered by first encounter too (cells in order, local vertices in order), with nodes
+identified exactly through their integer position on the cube surface lattice; the 2-D mesh uses the Q_n numbering of the
+coarse cube instead -- both are restatement choices the reference tests do not pin.
+Written as brute-force tensor quadrature over all nq^3 points (the GPU path factorises the integrals instead).
+"""
+import numpy as np
+
+from . import geometry as geo
+from .refel import LagrangeQ, lagrange_node_multi_indices, ncube_faces, tensor_quadrature
+
+H = geo.CUBE_HALF_EDGE
+
+
+def _cube_lattice_point(panel, i, j, n):
+    """Integer position on the cube surface of the panel lattice point (i, j): perm_p(n, 2i - n, 2j - n) (App. A.1)."""
+    h = (n, 2 * i - n, 2 * j - n)
+    jj, ss = geo._perm(panel + 1)
+    return tuple(int(ss[k]) * h[jj[k]] for k in range(3))
+
+
+class CubedSphereShellMesh3D:
+    """AtlasDiscreteModel(CubedSphereWithThicknessMesh(radius, thickness), l): n x n cells per panel, L cells through the shell
+    (the reference refines isotropically: L = n)."""
+
+    def __init__(self, n, radius=1.0, thickness=0.1, n_layers=None):
+        L = n if n_layers is None else n_layers
+        self.n, self.L, self.radius, self.thickness, self.D = n, L, radius, thickness, 3
+        self.num_cells = 6 * n * n * L
+        nodes = {}
+        cn = np.empty((self.num_cells, 8), dtype=np.int64)
+        cc = np.empty((self.num_cells, 8, 3))
+        c2c = np.empty(self.num_cells, dtype=np.int64)
+        col = np.empty(self.num_cells, dtype=np.int64)
+        lay = np.empty(self.num_cells, dtype=np.int64)
+        c = 0
+        # cell order inside a panel: gamma fastest, then alpha, then beta
+        for p in range(6):
+            for jb in range(n):
+                for ia in range(n):
+                    for kg in range(L):
+                        for v in range(8):
+                            dg, da, db = v & 1, (v >> 1) & 1, (v >> 2) & 1
+                            key = _cube_lattice_point(p, ia + da, jb + db, n) + (kg + dg,)
+                            if key not in nodes:
+                                nodes[key] = len(nodes)
+                            cn[c, v] = nodes[key]
+                            cc[c, v] = ((kg + dg) / L, -H + (ia + da) * 2 * H / n, -H + (jb + db) * 2 * H / n)
+                        c2c[c] = p
+                        col[c] = p * n * n + jb * n + ia
+                        lay[c] = kg
+                        c += 1
+        self.cell_nodes, self.cell_chart_coords, self.cell_to_chart = cn, cc, c2c
+        self.cell_column, self.cell_layer = col, lay
+        self.num_nodes = len(nodes)
+
+
+def entity_ids(cell_verts, D, d):
+    """ids of the d-dimensional entities (edges d=1, faces d=2) by first encounter; returns (Nc, n_local) ids and the count."""
+    faces = ncube_faces(D)[d]
+    keys = {}
+    out = np.empty((cell_verts.shape[0], len(faces)), dtype=np.int64)
+    for c in range(cell_verts.shape[0]):
+        for f, (S, fixed) in enumerate(faces):
+            vs = []
+            for v in range(1 << D):
+                if all(((v >> a) & 1) == b for a, b in fixed.items()):
+                    vs.append(cell_verts[c, v])
+            k = tuple(sorted(vs))
+            if k not in keys:
+                keys[k] = len(keys)
+            out[c, f] = keys[k]
+    return out, len(keys)
+
+
+class HexCGSpace:
+    """H1-conforming Q_p (p = 1, 2) on the hexahedral shell mesh; `zeromean=True` fixes the last DOF."""
+    kind = "CG"
+
+    def __init__(self, mesh, p, zeromean=False):
+        assert mesh.D == 3 and p in (1, 2)
+        self.mesh, self.p = mesh, p
+        self.ref = LagrangeQ(3, p)
+        Nc = mesh.num_cells
+        ids = [mesh.cell_nodes]
+        n = mesh.num_nodes
+        if p == 2:
+            e, ne = entity_ids(mesh.cell_nodes, 3, 1)
+            f, nf = entity_ids(mesh.cell_nodes, 3, 2)
+            ids += [n + e, n + ne + f, (n + ne + nf + np.arange(Nc))[:, None]]
+            n = n + ne + nf + Nc
+            self.num_edges, self.num_faces = ne, nf
+        ids = np.concatenate(ids, axis=1)
+        self.num_dofs_total = n
+        if zeromean:
+            ids = np.where(ids == n - 1, -1, ids)
+            n -= 1
+        self.cell_dofs, self.num_free, self.ndofs_loc, self.signs = ids, n, ids.shape[1], None
+
+
+class ShellQuadrature:
+    """Measure(Omega, degree) on the shell: tensor Gauss-Legendre with nq^3 points per hexahedron, geometry at the points."""
+
+    def __init__(self, mesh, degree):
+        self.mesh, self.degree = mesh, degree
+        self.pts, self.w = tensor_quadrature(3, degree)           # reference points, first coordinate (gamma) fastest
+        c = mesh.cell_chart_coords
+        lo, hi = c[:, 0, :], c[:, 7, :]
+        self.h = hi - lo                                           # (Nc, 3)
+        self.x = lo[:, None, :] + self.pts[None, :, :] * self.h[:, None, :]
+        self.dV = self.w[None, :] * np.prod(self.h, axis=1)[:, None]
+        self.ginv = geo.csphere3d_inv_metric(mesh.radius, mesh.thickness, self.x)
+        self.sqrtg = geo.csphere3d_sqrtg(mesh.radius, mesh.thickness, self.x)
+
+    def ambient(self):
+        out = np.empty(self.x.shape)
+        for p in range(6):
+            sel = self.mesh.cell_to_chart == p
+            out[sel] = geo.csphere3d_eval(p + 1, self.mesh.radius, self.mesh.thickness, self.x[sel])
+        return out
+
+
+def lb_element_matrices(space, quad):
+    """Ke[c, I, J] = sum_q dV grad(phi_I).(ginv grad(phi_J)) sqrtg (test/Laplacian/LaplaceBeltrami.jl:47 with the shell metric)."""
+    _, gref = space.ref.tabulate(quad.pts)                        # (Q, m, 3)
+    out = np.empty((space.mesh.num_cells, space.ndofs_loc, space.ndofs_loc))
+    for c in range(space.mesh.num_cells):                         # cell by cell: (Q, m, m) temporaries stay small
+        g = gref / quad.h[c][None, None, :]
+        flux = np.einsum("qij,qmj->qmi", quad.ginv[c], g)
+        out[c] = np.einsum("q,qai,qbi->ab", quad.dV[c] * quad.sqrtg[c], g, flux)
+    return out
+
+
+def shell_volume(mesh, degree):
+    q = ShellQuadrature(mesh, degree)
+    return float((q.dV * q.sqrtg).sum())

@@ -1,0 +1,83 @@
+"""GPU parity on the 3-D cubed-sphere shell (BASELINE config 5): hexahedral mesh and Q1/Q2 numbering bit-exact against the
+oracle, Laplace-Beltrami element matrices / assembled matrix / residual (Kronecker-factorised on the GPU, brute-force
+nq^3-point quadrature in the oracle) to 1e-12, and the shell volume of test/Distributed/DistributedSurfaceAreaTests.jl:120-134."""
+import numpy as np
+import pytest
+
+from __graft_entry__ import load_package
+from oracle import forms, shell
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gg():
+    return load_package()
+
+
+def _models(gg, n, L, r, t):
+    return (gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=n, n_layers=L),
+            shell.CubedSphereShellMesh3D(n, r, t, n_layers=L))
+
+
+@pytest.mark.parametrize("n,L", [(1, 1), (2, 2), (3, 2)])
+def test_shell_mesh_and_numbering_bit_exact(gg, n, L):
+    model, mesh = _models(gg, n, L, 1.0, 0.19)
+    assert (model.num_cells, model.num_nodes) == (mesh.num_cells, mesh.num_nodes)
+    assert (model.get_cell_node_ids() - 1 == mesh.cell_nodes).all()
+    assert np.abs(model.get_cell_coordinates() - mesh.cell_chart_coords).max() < 1e-15
+    for p in (1, 2):
+        V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+        Vo = shell.HexCGSpace(mesh, p)
+        assert V.num_free_dofs == Vo.num_free and (V.get_cell_dof_ids() - 1 == Vo.cell_dofs).all()
+    Vz = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 2), conformity="H1", constraint="zeromean")
+    Vzo = shell.HexCGSpace(mesh, 2, zeromean=True)
+    ids = Vz.get_cell_dof_ids()
+    assert Vz.num_free_dofs == Vzo.num_free and (np.where(ids < 0, -1, ids - 1) == Vzo.cell_dofs).all()
+
+
+@pytest.mark.parametrize("n,L,p,degree", [(2, 2, 2, 18), (2, 3, 2, 8), (3, 2, 1, 12), (2, 1, 1, 6)])
+def test_shell_laplace_beltrami_matches_oracle(gg, n, L, p, degree):
+    r, t = 1.3, 0.19
+    model, mesh = _models(gg, n, L, r, t)
+    dΩ = gg.Measure(gg.Triangulation(model), degree)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+    Vo = shell.HexCGSpace(mesh, p)
+    Keo = shell.lb_element_matrices(Vo, shell.ShellQuadrature(mesh, degree))
+    Ke = gg.element_matrices(gg.LaplaceBeltrami(dΩ), V, V)
+    assert np.abs(Ke - Keo).max() < 1e-12 * np.abs(Keo).max()
+    assem = gg.SparseMatrixAssembler(V, V)
+    u = np.random.default_rng(20261019).standard_normal(V.num_free_dofs)
+    A, b = gg.assemble_matrix_and_vector(gg.LaplaceBeltrami(dΩ, u=u), assem)
+    A, b = A.to_scipy(), b.get()
+    Ao = forms.assemble_matrix(Vo, Vo, Keo)
+    assert (A.indptr == Ao.indptr).all() and (A.indices == Ao.indices).all()
+    assert np.abs(A.data - Ao.data).max() < 1e-12 * np.abs(Ao.data).max()
+    assert np.abs(b - Ao @ u).max() < 1e-12 * np.abs(Ao @ u).max()
+    # residual alone (matrix-free action) and the null space: constants
+    b2 = gg.assemble_vector(gg.LaplaceBeltrami(dΩ, u=u), V).get()
+    assert np.abs(b2 - b).max() < 1e-13 * np.abs(b).max()
+    assert np.abs(A @ np.ones(V.num_free_dofs)).max() < 1e-11 * np.abs(A.data).max()
+
+
+def test_shell_volume(gg):
+    # int sqrtg = 4/3 pi ((r + t)^3 - r^3), rel 1e-2 in the reference (coarse meshes, low degrees)
+    r, t = 2.0, 0.25
+    exact = 4.0 / 3.0 * np.pi * ((r + t) ** 3 - r ** 3)
+    for n, degree, tol in ((2, 2, 1e-2), (4, 4, 1e-4), (8, 8, 1e-9)):
+        model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=n)
+        vol = gg.Measure(gg.Triangulation(model), degree).integrate()
+        assert abs(vol - exact) < tol * exact, (n, degree, vol, exact)
+    mesh = shell.CubedSphereShellMesh3D(2, r, t)
+    model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=2)
+    assert abs(gg.Measure(gg.Triangulation(model), 4).integrate() - shell.shell_volume(mesh, 4)) < 1e-13 * exact
+
+
+def test_unsupported_requests_on_the_shell_fail_loudly(gg):
+    model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.1), n=2)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="H1")
+    dΩ = gg.Measure(gg.Triangulation(model), 4)
+    with pytest.raises(gg.GGError):
+        gg.assemble_matrix(gg.Helmholtz(dΩ), V, V)
+    with pytest.raises(gg.GGError):
+        gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, 0), conformity="HDiv")
