@@ -17,6 +17,7 @@ import math
 import numpy as np
 
 from . import _lib
+from . import initial_conditions  # noqa: F401
 from ._lib import GGError  # noqa: F401
 
 lagrangian = "lagrangian"
@@ -122,7 +123,7 @@ class AtlasDiscreteModel:
 
     `n` (cells per panel edge) may be given instead of `nref` (n = 2**nref); the reference only offers powers of two."""
 
-    def __init__(self, mesh, nref=None, *, n=None, n_layers=None, manifold_style=None, ctx=None, _handle=None):
+    def __init__(self, mesh, nref=None, *, n=None, n_layers=None, ordering=0, manifold_style=None, ctx=None, _handle=None):
         self.ctx = ctx or get_context()
         self.lib = self.ctx.lib
         self.mesh = mesh
@@ -143,7 +144,7 @@ class AtlasDiscreteModel:
                 _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 3, self.n, int(n_layers or 0), mesh.radius, mesh.thickness, 0, C.byref(h)))
                 self.n_layers = int(n_layers or self.n)
             else:
-                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, 0, C.byref(h)))
+                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, int(ordering), C.byref(h)))
             self.h = h
         nc, nn, ne = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_mesh_info(self.h, C.byref(nc), C.byref(nn), C.byref(ne)))

@@ -292,7 +292,7 @@ struct CellGeo {
 };
 CellGeo cell_geo(gg_mesh* m, int nq);
 // host-side construction shared with the partition plans (gg_dist.cu); ctx == nullptr gives a host-only mesh
-gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius);
+gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius, int ordering = 0);
 void upload_geometry(gg_mesh* m);
 gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int n_layers, double radius, double thickness);
 std::vector<int32_t> hex_local_to_lex(int p);  // per-cell chart boxes, interval tables and the owned-cell mask -> device

@@ -152,7 +152,7 @@ void upload_geometry(gg_mesh* m) {
 
 static const int32_t COARSE_CELLS[6][4] = {{0, 1, 2, 3}, {2, 3, 4, 5}, {1, 6, 3, 5}, {7, 4, 6, 5}, {0, 7, 1, 6}, {0, 2, 7, 4}};
 
-gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
+gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius, int ordering) {
   std::unique_ptr<gg_mesh> m(new gg_mesh);
   m->ctx = ctx; m->dim = 2; m->n = n; m->radius = radius;
   int64_t nc = 6LL * n * n;
@@ -173,10 +173,19 @@ gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius) {
   m->chart_coords.resize(nc * 8);
   const double H = M_PI / 4;  // CUBE_HALF_EDGE, src/Geometry/CubedSphereMesh.jl:23
   auto psi = [&](double xi) { return (1.0 - xi) * (-H) + xi * H; };
+  // ordering 0: x-fastest inside a panel (one-shot refinement, AtlasGrids.jl:254-280).  ordering 1 / 2: Morton (z-order, x bit
+  // lowest) inside a panel = the cell order of successive `refine` calls (children BL, BR, TL, TR of each parent stay
+  // together, test/AtlasDiscreteModels/seq/RefinementOrderingTests.jl:93-100) and of a uniformly refined p4est tree
+  // (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208); needs n = 2^l.
+  auto morton = [&](int i, int j) {
+    int64_t k = 0;
+    for (int b = 0; (1 << b) < n; ++b) k |= ((int64_t)((i >> b) & 1) << (2 * b)) | ((int64_t)((j >> b) & 1) << (2 * b + 1));
+    return k;
+  };
   for (int p = 0; p < 6; ++p)
     for (int j = 0; j < n; ++j)
       for (int i = 0; i < n; ++i) {
-        int64_t c = (int64_t)p * n * n + (int64_t)j * n + i;
+        int64_t c = (int64_t)p * n * n + (ordering == 0 ? (int64_t)j * n + i : morton(i, j));
         const int32_t* cid = &coarse_ids[(size_t)p * mloc];
         m->cell_nodes[c * 4 + 0] = cid[lut[i + (n + 1) * j]];
         m->cell_nodes[c * 4 + 1] = cid[lut[i + 1 + (n + 1) * j]];
@@ -282,7 +291,7 @@ gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, doub
           ++c;
         }
   m->n_nodes = (int64_t)nodes.size();
-  m->surface.reset(build_cubed_sphere(ctx, n, radius));
+  m->surface.reset(build_cubed_sphere(ctx, n, radius, 0));
   if (ctx) {
     m->d_col.upload(m->cell_col, ctx->stream); m->d_layer.upload(m->cell_layer, ctx->stream);
     m->d_chart.upload(m->cell_to_chart, ctx->stream);
@@ -339,14 +348,18 @@ int gg_mesh_cubed_sphere(gg_ctx* ctx, int dim, int n, int n_layers, double radiu
   GG_REQUIRE(dim == 2 || dim == 3, GG_ERR_INVALID, "dim must be 2 (surface) or 3 (shell)");
   GG_REQUIRE(n >= 1, GG_ERR_INVALID, "n must be >= 1");
   GG_REQUIRE(radius > 0, GG_ERR_INVALID, "radius must be positive");
-  GG_REQUIRE(ordering == 0, GG_ERR_UNSUPPORTED, "only ordering 0 (one-shot, parent-major lexicographic) is implemented");
+  GG_REQUIRE(ordering >= 0 && ordering <= 2, GG_ERR_INVALID, "ordering must be 0 (one-shot), 1 (recursive refinement) or 2 (Morton / p4est)");
+  if (ordering != 0) {
+    GG_REQUIRE(dim == 2, GG_ERR_UNSUPPORTED, "Morton ordering is implemented for the 2-D surface");
+    GG_REQUIRE((n & (n - 1)) == 0, GG_ERR_INVALID, "recursive / Morton ordering needs n = 2^l cells per panel edge");
+  }
   GG_CUDA(cudaSetDevice(ctx->device));
   if (dim == 3) {
     GG_REQUIRE(thickness > 0, GG_ERR_INVALID, "shell thickness must be positive");
     GG_REQUIRE(n_layers >= 0, GG_ERR_INVALID, "n_layers must be >= 0 (0: isotropic refinement, n layers)");
     *out = build_cubed_sphere_shell(ctx, n, n_layers > 0 ? n_layers : n, radius, thickness);
   } else {
-    *out = build_cubed_sphere(ctx, n, radius);
+    *out = build_cubed_sphere(ctx, n, radius, ordering);
   }
   GG_API_END
 }

@@ -73,9 +73,15 @@ int gg_measure_fp64_peak(gg_ctx* ctx, double* tflops);
 /* ---- atlas mesh ------------------------------------------------------------------------------
  * Replaces AtlasDiscreteModel(CubedSphereMesh(radius), nref) -- src/Geometry/AtlasDiscreteModels.jl:222-229,
  * src/Geometry/AtlasGrids.jl:227-304, src/Geometry/CubedSphereMesh.jl:83-116.
- *   dim        2 (surface).  3 (shell, src/Geometry/CubedSphereWithThicknessMesh.jl) -> GG_ERR_UNSUPPORTED for now.
+ *   dim        2 (surface) or 3 (shell, src/Geometry/CubedSphereWithThicknessMesh.jl: n x n cells per panel, n_layers cells
+ *              through the shell, 0 = n as the reference's isotropic refinement; hexahedra ordered gamma-fastest; CG Q1/Q2 and DG
+ *              spaces and the Laplace-Beltrami form are implemented on it)
  *   n          cells per panel edge (the reference only offers n = 2^nref; any n >= 1 is accepted here)
  *   ordering   0 = one-shot parent-major, x-fastest inside a panel (AtlasGrids.jl:254-280)
+ *              1 = successive `refine` calls (src/Geometry/AtlasDiscreteModels.jl:248-262,286-344): recursive, the 4 children
+ *                  of a parent stay together in Gridap order BL,BR,TL,TR  (n = 2^l)
+ *              2 = uniformly refined p4est forest (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208): Morton
+ *                  order inside each of the 6 trees -- the same cell order as 1  (n = 2^l)
  * Cells [first_cell, first_cell + n_local) of the global panel-major order are instantiated (pass 0 and
  * -1 for all); a rank of the linear partition `div((i-1)*P, Nc)+1`
  * (src/Distributed/AtlasDistributedDiscreteModels.jl:31) uses its own slice, see gg_partition_range(). */

@@ -252,3 +252,36 @@ def test_error_behaviour(gg):
     xy[0, 3, 0] += 0.01
     with pytest.raises(gg.GGError):
         gg.AtlasDiscreteModel.from_arrays(gg.CubedSphereMesh(1.0), model.get_cell_to_chart(), xy, model.get_cell_node_ids(), model.num_nodes)
+
+
+@pytest.mark.parametrize("ordering", [1, 2])
+def test_recursive_and_morton_cell_orderings(gg, ordering):
+    """ordering 1 (successive `refine`) and 2 (p4est Morton): children of a parent stay together in Gridap order BL,BR,TL,TR
+    (test/AtlasDiscreteModels/seq/RefinementOrderingTests.jl:42-48,93-100); the mesh is the one-shot mesh with its cells
+    permuted, so every assembled quantity is the same up to a symmetric permutation."""
+    n = 8
+    m0 = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
+    m1 = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n, ordering=ordering)
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    mort = np.zeros_like(i)
+    for b in range(3):
+        mort |= (((i >> b) & 1) << (2 * b)) | (((j >> b) & 1) << (2 * b + 1))
+    perm = np.concatenate([p * n * n + mort.reshape(-1) for p in range(6)])       # lexicographic cell -> its Morton position
+    assert (m1.get_cell_node_ids()[perm] == m0.get_cell_node_ids()).all()
+    assert np.abs(m1.get_cell_coordinates()[perm] - m0.get_cell_coordinates()).max() == 0
+    assert (m1.get_cell_to_chart()[perm] == m0.get_cell_to_chart()).all()
+    # parent-major recursion: cells 4k..4k+3 are the BL, BR, TL, TR children of one parent
+    xy = m1.get_cell_coordinates().reshape(-1, 4, 4, 2)
+    h = xy[:, 0, 1, 0] - xy[:, 0, 0, 0]
+    assert np.abs(xy[:, 1, 0] - (xy[:, 0, 0] + np.stack([h, 0 * h], 1))).max() < 1e-14
+    assert np.abs(xy[:, 2, 0] - (xy[:, 0, 0] + np.stack([0 * h, h], 1))).max() < 1e-14
+    assert np.abs(xy[:, 3, 0] - (xy[:, 0, 0] + np.stack([h, h], 1))).max() < 1e-14
+    # same operator up to the permutation
+    dΩ0, dΩ1 = gg.Measure(gg.Triangulation(m0), 6), gg.Measure(gg.Triangulation(m1), 6)
+    V0 = gg.TestFESpace(m0, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="H1")
+    V1 = gg.TestFESpace(m1, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="H1")
+    A0 = gg.assemble_matrix(gg.LaplaceBeltrami(dΩ0), V0, V0).to_scipy()
+    A1 = gg.assemble_matrix(gg.LaplaceBeltrami(dΩ1), V1, V1).to_scipy()
+    assert np.abs((A0 - A1).data).max() < 1e-13 * np.abs(A0.data).max()          # Q1 DOFs are the nodes: identical numbering
+    with pytest.raises(gg.GGError):
+        gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=6, ordering=ordering)

@@ -121,3 +121,46 @@ def test_williamson2_regression_numbers_on_gpu(gg):
     assert abs(eu - EU_REF) <= 1e-2 * EU_REF + 1e-3 and abs(ep - EP_REF) <= 1e-2 * EP_REF + 1e-3
     assert abs(eu - EU_REF) < 2e-4 * EU_REF and abs(ep - EP_REF) < 3e-4 * EP_REF
     assert abs(eu - 0.0035082599123392863) < 1e-7 * eu and abs(ep - 3.52011724075712e-06) < 1e-6 * ep
+
+
+def test_galewsky_jet_runs_and_conserves_mass(gg):
+    """BASELINE config 4 names the Galewsky jet; it is not in the reference, so only invariants are checked:
+    the discrete mass int p sqrtg is conserved to round-off (res_p = int r div(F) sums to zero over a closed surface) and the
+    balanced jet without perturbation stays nearly steady."""
+    ic = gg.initial_conditions
+    n, p = 16, 1
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+    dΩ = gg.Measure(gg.Triangulation(model), 4 * (p + 1))
+    dt = gg.dx(model) * 0.1 / (p * np.sqrt(ic.GRAVITY * 1.0e4 / ic.A_E))
+    op = gg.ShallowWaterOperator(model, p, ic.coriolis, gravity=ic.GRAVITY)
+
+    def mass(x, nu):
+        # int p sqrtg = sum over cells of the DG interpolant against the measure: use the scalar mass matrix row sums
+        M = gg.assemble_matrix(gg.ScalarMass(dΩ), Q, Q).to_scipy()
+        return float(np.ones(Q.num_free_dofs) @ (M @ x[nu:]))
+
+    out = {}
+    for perturbed in (False, True):
+        u0 = gg.interpolate(ic.galewsky_velocity, V).get()
+        h0 = gg.interpolate(lambda X: ic.galewsky_depth(X, perturbed=perturbed), Q).get()
+        x0 = np.concatenate([u0, h0])
+        st = gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=1e-13), None, dt, "EXRK_SSP_3_3"), op)
+        st.set_state(x0)
+        st.step(20)
+        x = st.get_state()
+        assert np.isfinite(x).all()
+        m0, m1 = mass(x0, st.nu), mass(x, st.nu)
+        assert abs(m1 - m0) < 1e-12 * abs(m0)
+        out[perturbed] = np.abs(x[st.nu:] - x0[st.nu:]).max() / np.abs(x0[st.nu:]).max()
+    print("galewsky depth drift after 20 steps (balanced, perturbed):", out)
+    assert out[False] < 1e-2          # balanced jet: depth changes only by discretisation error (coarse 16x16 panels)
+    assert out[True] < 2e-2
+    # sanity of the restated profile: 80 m/s jet, depth between 9 and 10.2 km
+    X = np.random.default_rng(1).standard_normal((4000, 3))
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Xc = np.array([[np.cos(np.pi / 4), 0.0, np.sin(np.pi / 4)]])                 # centre of the jet, latitude pi/4
+    assert abs(np.linalg.norm(ic.galewsky_velocity(Xc)) * ic.A_E / ic.T_SCALE - 80.0) < 1e-9
+    h = ic.galewsky_depth(X) * ic.A_E
+    assert 9000 < h.min() < 9200 and 10100 < h.max() < 10200
