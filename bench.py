@@ -457,6 +457,25 @@ def main():
             line["rk"] = {"error": str(ex)}
         # nonlinear rotating shallow water (DAE: 3 diagnostic solves + 3 slope solves per SSPRK3 step), BASELINE configs[3]:
         # 256x256 per panel, order 2 (RT2 x DG2 prognostic, CG3 x RT2 x DG2 diagnostic), degree 12, Williamson-2 state
+        # DG upwind advection, BASELINE configs[2]: 128x128 per panel, DG-Q2, solid-body wind, SSPRK(3,3)
+        try:
+            am = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=128, ctx=ctx)
+            wind = lambda X: np.stack([-X[..., 1], X[..., 0], 0 * X[..., 0]], -1)   # noqa: E731  AdvectionUpwinding.jl:100-102
+            ast = gg.RKStepper(gg.RungeKutta(None, None, 2 * math.pi / 20000, "EXRK_SSP_3_3"), gg.AdvectionOperator(am, 2, wind))
+            aq = gg.TestFESpace(am, gg.ReferenceFE(gg.lagrangian, float, 2), conformity="L2")
+            ast.set_state(gg.interpolate(lambda X: np.exp(-(X[..., 1] ** 2 + X[..., 2] ** 2)), aq).get())
+            ast.step(20)
+            e0.record(stream)
+            ast.step(200)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ams = e0.elapsed_time(e1) / 200
+            line["rk"]["advection"] = {"workload": "DG-Q2 upwind advection (volume + skeleton terms), 128x128 per panel, degree 8, SSPRK(3,3)",
+                                       "cells": am.num_cells, "dofs": ast.np_, "steps_per_s": 1e3 / ams, "ms_per_step": ams,
+                                       "cell_stage_evaluations_per_s": 3 * am.num_cells / (ams * 1e-3)}
+            del ast, am, aq
+        except Exception as ex:
+            line["rk"]["advection"] = {"error": str(ex)}
         if world == 1:
             try:
                 line["rk"]["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1)

@@ -788,6 +788,23 @@ class ShallowWaterOperator:
         self.b_q = None if b is None else np.ascontiguousarray(np.broadcast_to(b(xyz), xyz.shape[:2]), dtype=np.float64)
 
 
+class AdvectionOperator:
+    """TransientSemilinearFEOperator(mass, res, (jac, jac_t), P, Q) of the DG upwind advection tutorial
+    (test/Tutorials/AdvectionUpwinding.jl:107-137): Q = DG-Q_order, wind `beta(xyz)` given in ambient components."""
+
+    def __init__(self, model, order, beta, degree=None):
+        self.model, self.p_fe = model, order
+        self.degree = 4 * order if degree is None else degree
+        dΩ = Measure(Triangulation(model), self.degree)
+        _, xyz = dΩ.quadrature_points(chart=False)
+        self.beta_cells = np.ascontiguousarray(np.broadcast_to(beta(xyz), xyz.shape), dtype=np.float64)
+        n = C.c_int32()
+        _lib.check(model.lib.gg_skeleton_points(model.h, self.degree, C.byref(n), None))
+        fx = np.empty((model.num_cells, 4, n.value, 3))
+        _lib.check(model.lib.gg_skeleton_points(model.h, self.degree, C.byref(n), _dp(fx)))
+        self.beta_facets = np.ascontiguousarray(np.broadcast_to(beta(fx), fx.shape), dtype=np.float64)
+
+
 class RKStepper:
     """Device-resident explicit RK march (`gg_rk_*`): Gridap.ODEs `ode_march!` for the wave operator, the DAE-aware
     `ode_march!` of src/ODEs/RungeKuttaEX.jl:48-134 for the shallow-water operator."""
@@ -812,6 +829,9 @@ class RKStepper:
             a.q0_mode = {"alias": _lib.Q0_ALIAS, "start_of_step": _lib.Q0_START_OF_STEP}[op.q0_mode]
             a.coriolis = _dp(op.f_q)
             a.topography = _dp(op.b_q) if op.b_q is not None else None
+        elif isinstance(op, AdvectionOperator):
+            a.problem = _lib.PROBLEM_ADVECTION
+            a.velocity_cells, a.velocity_facets = _dp(op.beta_cells), _dp(op.beta_facets)
         else:
             a.problem = _lib.PROBLEM_WAVE
         h = C.c_void_p()

@@ -23,6 +23,7 @@ FORM_DIV = 6
 FORM_SOURCE = 7
 PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
+PROBLEM_ADVECTION = 3
 Q0_ALIAS, Q0_START_OF_STEP = 0, 1
 
 
@@ -42,7 +43,8 @@ class RKArgs(C.Structure):
                 ("A", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)), ("c", C.POINTER(C.c_double)),
                 ("dt", C.c_double), ("rtol", C.c_double),
                 ("gravity", C.c_double), ("tau", C.c_double), ("q0_mode", C.c_int32),
-                ("coriolis", C.POINTER(C.c_double)), ("topography", C.POINTER(C.c_double))]
+                ("coriolis", C.POINTER(C.c_double)), ("topography", C.POINTER(C.c_double)),
+                ("velocity_cells", C.POINTER(C.c_double)), ("velocity_facets", C.POINTER(C.c_double))]
 
 
 _P = C.c_void_p
@@ -115,6 +117,7 @@ SIGNATURES = {
     "gg_element_matrices": (C.c_int, [C.c_int, C.POINTER(FormArgs), _I64, _I64, _PD]),
     "gg_element_vectors": (C.c_int, [C.c_int, C.POINTER(FormArgs), _I64, _I64, _PD]),
     "gg_quadrature_points": (C.c_int, [_P, C.c_int32, _PD, _PD]),
+    "gg_skeleton_points": (C.c_int, [_P, C.c_int32, _PI32, _PD]),
     "gg_integrate": (C.c_int, [_P, C.c_int32, _P, _PD]),
     "gg_eval_geometry": (C.c_int, [_P, C.c_int, C.c_double, _I64, _PD, _PD, _PD, _PD, _PD, _PD]),
     "gg_solver_pcg_create": (C.c_int, [_P, C.c_double, C.c_int, _PP]),

@@ -206,6 +206,7 @@ void build_dg_mass_inverse(gg_rk* rk) {
 
 static void rk_step_async(gg_rk* rk) {
   if (rk->problem == GG_PROBLEM_SHALLOW_WATER) { swe_step_async(rk); return; }
+  if (rk->problem == GG_PROBLEM_ADVECTION) { adv_step_async(rk); return; }
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
   int64_t n = rk->nu + rk->np;
@@ -256,8 +257,8 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   gg_rk* raw = nullptr;
   GG_API_BEGIN
   GG_REQUIRE(m && a && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_UNSUPPORTED,
-             "unknown problem id (GG_PROBLEM_WAVE and GG_PROBLEM_SHALLOW_WATER are implemented)");
+  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER || a->problem == GG_PROBLEM_ADVECTION,
+             GG_ERR_UNSUPPORTED, "unknown problem id (GG_PROBLEM_WAVE, GG_PROBLEM_SHALLOW_WATER and GG_PROBLEM_ADVECTION are implemented)");
   GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
   GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "the RK steppers support RT_p x DG_p with p <= 2");
   GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
@@ -273,6 +274,23 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   for (int i = 0; i < s; ++i)
     for (int j = i; j < s; ++j) GG_REQUIRE(rk->A[i * s + j] == 0.0, GG_ERR_INVALID, "tableau is not explicit");
   auto chk = [](int code) { if (code != GG_OK) throw Error(code, gg_last_error(nullptr)); };
+  if (a->problem == GG_PROBLEM_ADVECTION) {
+    // scalar DG state only: no RT space, no global solve
+    chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
+    rk->nu = 0; rk->np = rk->Q->n_free; rk->mq = rk->Q->ndofs_loc; rk->mu = 0;
+    build_dg_mass_inverse(rk);
+    int64_t n = rk->np;
+    rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
+    rk->k.resize(s);
+    for (int i = 0; i < s; ++i) rk->k[i].alloc(n);
+    rk->iter_accum.alloc(2);
+    GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
+    if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
+    adv_create(rk, a);
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = raw;
+    return GG_OK;
+  }
   chk(gg_space_builtin(m, GG_SPACE_RT, a->order, GG_CONSTRAINT_NONE, &rk->V));
   chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
   rk->nu = rk->V->n_free; rk->np = rk->Q->n_free; rk->mq = rk->Q->ndofs_loc; rk->mu = rk->V->ndofs_loc;
@@ -397,6 +415,8 @@ int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
     rk->y_valid = false;
     swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
     swe_residual_async(rk, rk->xi.p, rk->y.p, rk->y.p, rk->r.p, nullptr);
+  } else if (rk->problem == GG_PROBLEM_ADVECTION) {
+    adv_slope_async(rk, rk->xi.p, nullptr, rk->r.p);
   } else {
     rk_residual_async(rk, rk->xi.p, rk->r.p);
   }

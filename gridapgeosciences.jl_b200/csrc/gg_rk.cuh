@@ -35,6 +35,12 @@ struct gg_rk {
   gg::DevBuf<double> rhs_q, rhs_F;
   gg::DevBuf<double> evec_q, evec_u;  // entry-major element-vector scratch
   gg::DevBuf<double> stage2;          // [point][component][cell] coefficient staging of the cell kernels (large rules only)
+  // ---- DG advection only (gg_adv.cu) ------------------------------------------------------------------
+  gg::DevBuf<int32_t> adv_nbr_cell;            // [n_cells][4] cell across each local edge
+  gg::DevBuf<int8_t> adv_nbr_edge, adv_is_plus;  // its local edge there; whether this cell is the facet's plus side
+  gg::DevBuf<double> adv_bq;                   // [Q][2][n_cells] w dV sqrtg times the contravariant wind / (hx, hy)
+  gg::DevBuf<double> adv_bn, adv_wsg;          // [4][nqf][n_cells] beta.n and w dL sqrtg at the facet points of each side
+  gg::DevBuf<double> adv_fval;                 // [4][nqf][m] basis at the facet points
   int64_t diag_solves = 0;
   bool y_valid = false;           // y == diagnostics(x) (lets a step reuse the final diagnostics of the previous one)
 };
@@ -54,4 +60,8 @@ void swe_step_async(gg_rk* rk);
 void swe_diagnostics_async(gg_rk* rk, const double* x, double* y);
 void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp);
 void swe_destroy(gg_rk* rk);
+// DG advection (gg_adv.cu)
+void adv_create(gg_rk* rk, const gg_rk_args* a);
+void adv_step_async(gg_rk* rk);
+void adv_slope_async(gg_rk* rk, const double* u, double* kout, double* rout);
 }  // namespace gg

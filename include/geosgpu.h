@@ -232,6 +232,10 @@ int gg_element_vectors(gg_form form, const gg_form_args* args, int64_t first_cel
 /* chart / ambient coordinates of the quadrature points: out_chart [n_cells][Q][2], out_xyz [n_cells][Q][3]
  * (AmbientMapCellField, src/CellData/CellFields.jl:207-212); either may be NULL */
 int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* out_xyz);
+/* ambient coordinates of the facet quadrature points (Gauss-Legendre, nq = ceil((degree+1)/2) per facet) of the four sides
+ * of every cell, xyz [n_cells][4][nq][3] (local edges in Gridap order, points from the first to the second vertex):
+ * AmbientMapCellField on SkeletonTriangulation(model) (src/CellData/CellFields.jl:207-260) */
+int gg_skeleton_points(gg_mesh* m, int32_t degree, int32_t* n_pts, double* xyz);
 /* sum(int f sqrtg dOmega) with f at the quadrature points (NULL = 1: the surface area of
  * test/Geometry/SurfaceArea.jl:19-24) */
 int gg_integrate(gg_mesh* m, int32_t degree, gg_vec* qdata, double* out);
@@ -276,6 +280,9 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
  * The whole step runs on the device without host synchronisation. */
 #define GG_PROBLEM_WAVE 1
 #define GG_PROBLEM_SHALLOW_WATER 2
+/* DG upwind advection of a scalar, volume + skeleton terms (test/Tutorials/AdvectionUpwinding.jl:107-137), Q = DG-Q_order,
+ * marched with the explicit tableau (BASELINE configs[2]); the state is [p] alone (n_u = 0) */
+#define GG_PROBLEM_ADVECTION 3
 #define GG_Q0_ALIAS 0         /* q0 aliases q, as in the reference (RungeKuttaEX.jl:69-75 pass one array twice) */
 #define GG_Q0_START_OF_STEP 1 /* q0 = potential vorticity at the beginning of the step */
 typedef struct {
@@ -294,6 +301,10 @@ typedef struct {
   int32_t q0_mode;          /* GG_Q0_* */
   const double* coriolis;   /* host [n_cells][Q]: f at the quadrature points (cor_cf) */
   const double* topography; /* host [n_cells][Q]: b at the quadrature points, or NULL (= 0) */
+  /* DG advection only: the ambient wind beta_x (3 components) at the cell quadrature points [n_cells][Q][3]
+   * (gg_quadrature_points) and at the facet quadrature points of every cell side [n_cells][4][nq][3] (gg_skeleton_points) */
+  const double* velocity_cells;
+  const double* velocity_facets;
 } gg_rk_args;
 int gg_rk_create(gg_mesh* m, const gg_rk_args* args, gg_rk** out);
 int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p);
