@@ -165,7 +165,9 @@ class AtlasDiscreteModel:
         cells = np.ascontiguousarray(cells, dtype=np.int64)
         h = C.c_void_p()
         _lib.check(self.lib.gg_mesh_restrict(self.h, len(cells), _ip64(cells), C.byref(h)))
-        return AtlasDiscreteModel(self.mesh, ctx=self.ctx, manifold_style=self.manifold_style, _handle=h)
+        sub = AtlasDiscreteModel(self.mesh, ctx=self.ctx, manifold_style=self.manifold_style, _handle=h)
+        sub.n, sub.n_layers = self.n, getattr(self, "n_layers", 0)
+        return sub
 
     def ghost_cells(self, first, last):
         n = C.c_int64()

@@ -455,7 +455,27 @@ int gg_partition_range(int64_t n_cells, int nparts, int part, int64_t* first, in
 int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** out) {
   GG_API_BEGIN
   GG_REQUIRE(m && out && (cells || n_sub == 0), GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "sub-meshes of the 3-D shell are not implemented");
+  if (m->dim == 3) {
+    // sub-mesh of the shell: the listed hexahedra with global node ids; the column geometry stays that of the full surface
+    GG_CUDA(cudaSetDevice(m->ctx->device));
+    std::unique_ptr<gg_mesh> s3(new gg_mesh);
+    s3->ctx = m->ctx; s3->dim = 3; s3->n = m->n; s3->n_layers = m->n_layers; s3->radius = m->radius; s3->thickness = m->thickness;
+    s3->n_cells = n_sub; s3->n_nodes = m->n_nodes;
+    s3->cell_nodes8.resize(n_sub * 8); s3->cell_to_chart.resize(n_sub); s3->cell_col.resize(n_sub); s3->cell_layer.resize(n_sub);
+    for (int64_t i = 0; i < n_sub; ++i) {
+      int64_t c = cells[i];
+      GG_REQUIRE(c >= 0 && c < m->n_cells, GG_ERR_INVALID, "cell id out of range");
+      GG_REQUIRE(i == 0 || cells[i - 1] < c, GG_ERR_INVALID, "cells must be strictly ascending");
+      std::copy(&m->cell_nodes8[c * 8], &m->cell_nodes8[c * 8] + 8, &s3->cell_nodes8[i * 8]);
+      s3->cell_to_chart[i] = m->cell_to_chart[c]; s3->cell_col[i] = m->cell_col[c]; s3->cell_layer[i] = m->cell_layer[c];
+    }
+    s3->surface.reset(build_cubed_sphere(m->ctx, m->n, m->radius, 0));
+    s3->d_col.upload(s3->cell_col, m->ctx->stream); s3->d_layer.upload(s3->cell_layer, m->ctx->stream);
+    s3->d_chart.upload(s3->cell_to_chart, m->ctx->stream);
+    GG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    *out = s3.release();
+    return GG_OK;
+  }
   GG_CUDA(cudaSetDevice(m->ctx->device));
   std::unique_ptr<gg_mesh> s(new gg_mesh);
   s->ctx = m->ctx; s->dim = m->dim; s->n = 0; s->radius = m->radius; s->thickness = m->thickness;
@@ -477,16 +497,17 @@ int gg_mesh_restrict(gg_mesh* m, int64_t n_sub, const int64_t* cells, gg_mesh** 
 int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghost, int64_t* out) {
   GG_API_BEGIN
   GG_REQUIRE(m && n_ghost, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "ghost layers of the 3-D shell are not implemented");
   GG_REQUIRE(first >= 0 && first <= last && last <= m->n_cells, GG_ERR_INVALID, "bad owned range");
+  const int nv = m->dim == 3 ? 8 : 4;
+  const std::vector<int32_t>& cn = m->dim == 3 ? m->cell_nodes8 : m->cell_nodes;
   std::vector<uint8_t> touched(m->n_nodes, 0);
   for (int64_t c = first; c < last; ++c)
-    for (int v = 0; v < 4; ++v) touched[m->cell_nodes[c * 4 + v]] = 1;
+    for (int v = 0; v < nv; ++v) touched[cn[c * nv + v]] = 1;
   int64_t cnt = 0;
   for (int64_t c = 0; c < m->n_cells; ++c) {
     if (c >= first && c < last) continue;
     bool near = false;
-    for (int v = 0; v < 4; ++v) near = near || touched[m->cell_nodes[c * 4 + v]];
+    for (int v = 0; v < nv; ++v) near = near || touched[cn[c * nv + v]];
     if (near) {
       if (out) out[cnt] = c;
       ++cnt;

@@ -81,3 +81,22 @@ def test_unsupported_requests_on_the_shell_fail_loudly(gg):
         gg.assemble_matrix(gg.Helmholtz(dΩ), V, V)
     with pytest.raises(gg.GGError):
         gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, 0), conformity="HDiv")
+
+
+def test_shell_slices_assemble_the_owned_rows(gg):
+    """Sharding as in bench.py: a rank assembles its slice of the linear partition plus the vertex-adjacent ghost layer; the
+    element matrices of the sub-mesh are those of the same cells of the full mesh (global node ids are kept)."""
+    n, L, p, degree = 3, 2, 2, 8
+    model, mesh = _models(gg, n, L, 1.0, 0.19)
+    a, b = gg.partition_range(model.num_cells, 3, 1)
+    ghosts = model.ghost_cells(a, b)
+    assert len(ghosts) > 0 and not ((ghosts >= a) & (ghosts < b)).any()
+    cells = np.sort(np.concatenate([np.arange(a, b), ghosts]))
+    sub = model.restrict(cells)
+    assert sub.num_cells == len(cells) and (sub.get_cell_node_ids() == model.get_cell_node_ids()[cells]).all()
+    V, Vs = (gg.TestFESpace(m, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1") for m in (model, sub))
+    Ke = gg.element_matrices(gg.LaplaceBeltrami(gg.Measure(gg.Triangulation(model), degree)), V, V)
+    Ks = gg.element_matrices(gg.LaplaceBeltrami(gg.Measure(gg.Triangulation(sub), degree)), Vs, Vs)
+    assert np.abs(Ks - Ke[cells]).max() < 1e-15 * np.abs(Ke).max()
+    A = gg.assemble_matrix(gg.LaplaceBeltrami(gg.Measure(gg.Triangulation(sub), degree)), Vs, Vs).to_scipy()
+    assert A.nnz > 0 and np.isfinite(A.data).all()
