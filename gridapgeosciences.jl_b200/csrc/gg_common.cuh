@@ -222,8 +222,11 @@ struct gg_vec {
   gg::DevBuf<double> d;
 };
 
+namespace gg { struct HexTensor; }
 struct gg_csr {
   gg_ctx* ctx = nullptr;
+  // 3-D shell matrices: maps of the tensor-structured numeric phase (gg_forms.cu), built at first use
+  std::shared_ptr<gg::HexTensor> tensor;
   gg_space* test = nullptr;
   gg_space* trial = nullptr;
   int64_t n_rows = 0, n_cols = 0, nnz = 0;

@@ -592,9 +592,107 @@ static HexWork hex_prepare(gg_mesh* m, int order, int nq) {
   return {T.K2.p, T.M2.p, T.Dg.p, T.Ng.p, ncol};
 }
 
-static void run_hex_lb(gg_mesh* m, int order, int nq, const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf) {
+struct HexTensor {
+  gg_space* Vs = nullptr;          // surface CG-Q_p space
+  gg_csr *AK = nullptr, *AM = nullptr;  // assembled surface stiffness / mass (same pattern)
+  int NR = 0;
+  DevBuf<int32_t> slot2d;          // [nnz] slot of the surface pattern
+  DevBuf<uint16_t> rr;             // [nnz] radial pair rho_i * NR + rho_j
+  DevBuf<double2> KM;              // [nnz of the surface pattern] (mass, stiffness) interleaved
+  std::map<int, std::shared_ptr<DevBuf<double2>>> radial;  // (order, nq) -> (DG / t, t NG) interleaved
+  ~HexTensor() { gg_csr_destroy(AK); gg_csr_destroy(AM); gg_space_destroy(Vs); }
+};
+
+// whether the matrix can take the tensor-structured numeric phase: a complete shell (every column with all its layers)
+static bool hex_tensor_applicable(gg_csr* A) {
+  static const bool off = getenv("GG_SHELL_ASSEMBLY") && std::string(getenv("GG_SHELL_ASSEMBLY")) == "cellwise";
+  gg_mesh* m = A->test->mesh;
+  return !off && A->test == A->trial && m->dim == 3 && m->n_cells == 6LL * m->n * m->n * m->n_layers &&
+         A->test->constraint == GG_CONSTRAINT_NONE && (int64_t)(A->test->order * m->n_layers + 1) * (A->test->order * m->n_layers + 1) <= 65535;
+}
+
+static HexWork hex_tensor_fill(gg_csr* A, int order, int nq, double scale, int add) {
+  gg_space* V = A->test;
+  gg_mesh* m = V->mesh;
   gg_ctx* ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  auto chk = [](int code) { if (code != GG_OK) throw Error(code, gg_last_error(nullptr)); };
+  const int nb = order + 1, m2 = nb * nb, m3 = m2 * nb, G = nb * nb;
+  const int NR = order * m->n_layers + 1;
+  if (!A->tensor) {
+    auto T = std::make_shared<HexTensor>();
+    T->NR = NR;
+    chk(gg_space_builtin(m->surface.get(), GG_SPACE_CG, order, GG_CONSTRAINT_NONE, &T->Vs));
+    chk(gg_pattern(T->Vs, T->Vs, &T->AK));
+    chk(gg_pattern(T->Vs, T->Vs, &T->AM));
+    // (radial node, surface DOF) of every shell DOF
+    std::vector<int32_t> l2 = quad_local_to_lex(order), l3 = hex_local_to_lex(order), loc3(m3);
+    for (int I = 0; I < m3; ++I) loc3[l3[I]] = I;
+    std::vector<int32_t> rho(V->n_free, 0), sig(V->n_free, 0);
+    for (int64_t c = 0; c < m->n_cells; ++c)
+      for (int i0 = 0; i0 < nb; ++i0)
+        for (int a2 = 0; a2 < m2; ++a2) {
+          const int32_t d = V->cell_dofs[c * m3 + loc3[i0 + nb * l2[a2]]];
+          if (d < 0) continue;
+          rho[d] = order * m->cell_layer[c] + i0;
+          sig[d] = T->Vs->cell_dofs[(int64_t)m->cell_col[c] * m2 + a2];
+        }
+    DevBuf<int32_t> drho, dsig;
+    drho.upload(rho, st); dsig.upload(sig, st);
+    T->slot2d.alloc(A->nnz); T->rr.alloc(A->nnz);
+    DevBuf<int> bad(1);
+    GG_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    k_hex_tensor_maps<<<nblk(A->n_rows, 128), 128, 0, st>>>(A->n_rows, NR, A->d_rowptr.p, A->d_colind.p, drho.p, dsig.p,
+                                                           T->AK->d_rowptr.p, T->AK->d_colind.p, T->slot2d.p, T->rr.p, bad.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    int nbad = 0;
+    bad.download(&nbad, st);
+    GG_REQUIRE(nbad == 0, GG_ERR_INVALID, "shell matrix pattern does not have the surface x radial tensor structure");
+    A->tensor = T;
+  }
+  HexTensor& T = *A->tensor;
+  // surface matrices: cell-wise quadrature on the columns + atomic-free CSR fill, every call
   HexWork W = hex_prepare(m, order, nq);
+  gather_matrix(T.AK, 1, W.K2, 1.0, 0);
+  gather_matrix(T.AM, 0, W.M2, 1.0, 0);
+  // assembled radial matrices (constant per mesh and rule)
+  const int key = order * 64 + nq;
+  auto it = T.radial.find(key);
+  if (it == T.radial.end()) {
+    std::vector<double> Dg((size_t)m->n_layers * G), Ng((size_t)m->n_layers * G), DG((size_t)NR * NR, 0.0), NG((size_t)NR * NR, 0.0);
+    GG_CUDA(cudaMemcpyAsync(Dg.data(), W.Dg, Dg.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaMemcpyAsync(Ng.data(), W.Ng, Ng.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    for (int l = 0; l < m->n_layers; ++l)
+      for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < nb; ++j) {
+          DG[(size_t)(order * l + i) * NR + order * l + j] += Dg[(size_t)l * G + i * nb + j];
+          NG[(size_t)(order * l + i) * NR + order * l + j] += Ng[(size_t)l * G + i * nb + j];
+        }
+    std::vector<double2> DN((size_t)NR * NR);
+    for (size_t k = 0; k < DN.size(); ++k) DN[k] = make_double2(DG[k] / m->thickness, m->thickness * NG[k]);
+    // (a row only addresses DN[rho_i * NR + rho_j] with |rho_j - rho_i| <= order and both inside 0 .. NR-1)
+    auto dDN = std::make_shared<DevBuf<double2>>();
+    dDN->upload(DN, st);
+    GG_CUDA(cudaStreamSynchronize(st));
+    it = T.radial.emplace(key, dDN).first;
+  }
+  {
+    if (T.KM.n != (size_t)T.AK->nnz) T.KM.alloc(T.AK->nnz);
+    k_hex_interleave<<<nblk(T.AK->nnz, 256), 256, 0, st>>>(T.AK->nnz, T.AM->d_vals.p, T.AK->d_vals.p, T.KM.p);
+    ProfScope ps(ctx, "k_hex_tensor_fill");
+    k_hex_tensor_fill<<<nblk(A->nnz, 256), 256, 0, st>>>(A->nnz, T.slot2d.p, T.rr.p, it->second->p, T.KM.p, scale, add, A->d_vals.p);
+    ctx->launches += 2;
+    GG_CUDA(cudaGetLastError());
+  }
+  return W;
+}
+
+static void run_hex_lb(gg_mesh* m, int order, int nq, const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf,
+                       const HexWork* prepared = nullptr) {
+  gg_ctx* ctx = m->ctx;
+  HexWork W = prepared ? *prepared : hex_prepare(m, order, nq);
   const int64_t nc = m->n_cells;
   unsigned nbk = nblk(nc, 128);
   if (ebuf) {
@@ -625,14 +723,20 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     GG_REQUIRE(form == GG_FORM_LAPLACE_BELTRAMI && !a->qdata, GG_ERR_UNSUPPORTED, "on the 3-D shell only the Laplace-Beltrami form is implemented");
     GG_REQUIRE(P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG && P.test->order == P.trial->order, GG_ERR_INVALID,
                "the shell Laplace-Beltrami form needs CG test/trial spaces of the same order");
-    size_t np = (size_t)P.mt * (P.mt + 1) / 2;
-    double* eb = scratch(ctx->ebuf, np * nc);
     double* vb = nullptr;
     if (want_fused_vector) {
       GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "fused residual needs args->u of the trial size");
       vb = scratch(ctx->vbuf, (size_t)P.mt * nc);
       *vbuf_out = vb;
     }
+    if (pipe && hex_tensor_applicable(pipe->A)) {
+      // assembled matrix straight from the tensor structure (no element matrices); the residual stays cell-wise
+      HexWork W = hex_tensor_fill(pipe->A, P.test->order, P.nq, pipe->scale, pipe->add);
+      if (vb) run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb, &W);
+      return -1;
+    }
+    size_t np = (size_t)P.mt * (P.mt + 1) / 2;
+    double* eb = scratch(ctx->ebuf, np * nc);
     run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb);
     return 1;
   }

@@ -48,6 +48,8 @@ def test_shell_laplace_beltrami_matches_oracle(gg, n, L, p, degree):
     assert np.abs(Ke - Keo).max() < 1e-12 * np.abs(Keo).max()
     assem = gg.SparseMatrixAssembler(V, V)
     u = np.random.default_rng(20261019).standard_normal(V.num_free_dofs)
+    # on a complete shell the CSR values come from the tensor-structured numeric phase (assembled surface x radial factors);
+    # the element matrices above and the sub-mesh test below cover the cell-wise path
     A, b = gg.assemble_matrix_and_vector(gg.LaplaceBeltrami(dΩ, u=u), assem)
     A, b = A.to_scipy(), b.get()
     Ao = forms.assemble_matrix(Vo, Vo, Keo)
@@ -100,3 +102,12 @@ def test_shell_slices_assemble_the_owned_rows(gg):
     assert np.abs(Ks - Ke[cells]).max() < 1e-15 * np.abs(Ke).max()
     A = gg.assemble_matrix(gg.LaplaceBeltrami(gg.Measure(gg.Triangulation(sub), degree)), Vs, Vs).to_scipy()
     assert A.nnz > 0 and np.isfinite(A.data).all()
+    # cell-wise CSR fill of the sub-mesh against scipy's COO assembly of the same element matrices
+    import scipy.sparse as sp
+    ids = Vs.get_cell_dof_ids() - 1
+    m = ids.shape[1]
+    Ao = sp.coo_matrix((Ks.reshape(-1), (np.repeat(ids, m, axis=1).reshape(-1), np.tile(ids, (1, m)).reshape(-1))),
+                       shape=A.shape).tocsr()
+    Ao.sort_indices()
+    assert (A.indptr == Ao.indptr).all() and (A.indices == Ao.indices).all()
+    assert np.abs(A.data - Ao.data).max() < 1e-13 * np.abs(Ao.data).max()

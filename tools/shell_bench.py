@@ -56,7 +56,7 @@ def main():
     for _ in range(args.steps):
         gg.assemble_matrix_and_vector(form, assem, b)
     ctx.synchronize()
-    prof = {k: ctx.profile_query(k)[1] / args.steps for k in ("k_hex_kron", "k_hex_residual", "k_lb_fast", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs")}
+    prof = {k: ctx.profile_query(k)[1] / args.steps for k in ("k_hex_tensor_fill", "k_hex_kron", "k_hex_residual", "k_lb_fast", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs")}
     ctx.profile(False)
     nq = (args.degree + 2) // 2
     m = (args.order + 1) ** 3
