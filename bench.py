@@ -399,6 +399,7 @@ def main():
         "achieved_is": "ALGORITHMIC FLOPs of SURVEY.md §8(d) (45 600 + 14 000 per cell) / measured kernel time; the kernel is "
                        "sum-factorised and executes ~13 kFLOP per cell, so frac can exceed 1",
         "executed_tflops": (2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60) * ncell_local / (k_ms * 1e-3) / 1e12,
+        "frac_executed": ((2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60) * ncell_local / (k_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
         # command (profiles/ncu_lb_assembly_r01_final.txt: 151.3 MB for 393 216 cells = 384.8 B/cell), scaled to this launch

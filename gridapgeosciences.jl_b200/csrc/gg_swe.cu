@@ -36,6 +36,9 @@ static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) 
 // Basis tabulations of the resident (order, nq) pair in __constant__ memory (warp-uniform operands: no L1 traffic).
 // Sized for RT_2 / DG_2 / CG_3 at 7x7 points (41 KB); larger rules fall back to the same tables in global memory.
 constexpr int SWE_MAXQ = 49;
+#ifndef SWE_MIN_BLOCKS
+#define SWE_MIN_BLOCKS 6
+#endif
 __constant__ double c_swe_w[MAX_NQ];
 __constant__ double c_swe_rt[SWE_MAXQ * 24 * 2];  // [Q][MU][2] reference RT basis
 __constant__ double c_swe_dg[SWE_MAXQ * 9];       // [Q][MP]
@@ -95,7 +98,7 @@ __device__ __forceinline__ Stage2 stage2_of(double* gscratch, int64_t nc, int64_
 //   eq [MR][nc], eF [MU][nc]  entry-major element vectors of the q and F equations
 //   Phi [c*MP+i]        Bernoulli potential (DG mass block inverted in place)
 template <int K, bool CONST>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, SWE_MIN_BLOCKS)
 k_swe_diag(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
            const double* __restrict__ u, const double* __restrict__ p, const double* __restrict__ fq,
            const double* __restrict__ bq, double gravity, const double* __restrict__ MpInv, double* __restrict__ pq_out,
@@ -191,7 +194,7 @@ k_swe_diag(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__
 // Stage residual, one thread per cell.  eru [MU][nc] entry-major element vector of r_u; rp [c*MP+i] = r_p (DG, cell
 // local); kp (optional) = -Mp^-1 r_p, the depth slope.
 template <int K, bool ALIAS, bool CONST>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, SWE_MIN_BLOCKS)
 k_swe_stage(int64_t nc, int nq, CellGeo g, SweTabs T, const int32_t* __restrict__ vdofs, const int8_t* __restrict__ vsigns,
             const int32_t* __restrict__ rdofs, const double* __restrict__ u, const double* __restrict__ qv,
             const double* __restrict__ q0v, const double* __restrict__ Fv, const double* __restrict__ Phi,
