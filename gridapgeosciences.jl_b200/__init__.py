@@ -367,7 +367,9 @@ class Measure:
         """sum(∫(f * meas_cf)dΩ) with f given at the quadrature points (None = 1)."""
         m = self.model
         out = C.c_double()
-        v = DeviceVector.from_numpy(m.ctx, np.ascontiguousarray(fq, dtype=np.float64).reshape(-1)) if fq is not None else None
+        v = fq
+        if fq is not None and not isinstance(fq, DeviceVector):
+            v = DeviceVector.from_numpy(m.ctx, np.ascontiguousarray(fq, dtype=np.float64).reshape(-1))
         _lib.check(m.lib.gg_integrate(m.h, self.degree, v.h if v is not None else None, C.byref(out)))
         return out.value
 
@@ -585,7 +587,9 @@ class Source(Form):
     bilinear = False
 
     def __init__(self, dΩ, fq, **kw):
-        super().__init__(dΩ, qdata=np.ascontiguousarray(fq, dtype=np.float64).reshape(-1), **kw)
+        if not isinstance(fq, DeviceVector):
+            fq = np.ascontiguousarray(fq, dtype=np.float64).reshape(-1)
+        super().__init__(dΩ, qdata=fq, **kw)
 
 
 # ---- assembly ---------------------------------------------------------------------------------------------
@@ -706,6 +710,56 @@ def norm(e, V, degree):
     out = C.c_double()
     _lib.check(V.lib.gg_norm_sq(V.h, e.h, int(degree), C.byref(out)))
     return math.sqrt(max(out.value, 0.0))
+
+
+def surface_laplacian(dΩ, grad_f, hess_f):
+    """Δs(f, Ω) evaluated at the quadrature points of dΩ for an ambient function f given by its ambient gradient and Hessian
+    (closed form of src/CellData/SurfaceDiffOps.jl:26-65).  Returns a DeviceVector usable as `fq` of Source."""
+    m = dΩ.model
+    _, xyz = dΩ.quadrature_points(chart=False)
+    g = np.ascontiguousarray(np.broadcast_to(grad_f(xyz), xyz.shape), dtype=np.float64)
+    h = np.ascontiguousarray(np.broadcast_to(hess_f(xyz), xyz.shape + (3,)), dtype=np.float64)
+    out = DeviceVector(m.ctx, m.num_cells * dΩ.num_points)
+    _lib.check(m.lib.gg_surface_laplacian(m.h, dΩ.degree, _dp(g), _dp(h), out.h))
+    return out
+
+
+def l2_error(uh, V, dΩ, fq=None, dirichlet=0.0):
+    """sqrt(sum(∫((f - uh)*(f - uh)*meas_cf)dΩ)) with f at the quadrature points of dΩ (test/Laplacian/LaplaceBeltrami.jl:82-83)."""
+    ctx = V.model.ctx
+    if not isinstance(uh, DeviceVector):
+        uh = DeviceVector.from_numpy(ctx, uh)
+    if fq is not None and not isinstance(fq, DeviceVector):
+        fq = DeviceVector.from_numpy(ctx, np.ascontiguousarray(fq, dtype=np.float64).reshape(-1))
+    out = C.c_double()
+    _lib.check(V.lib.gg_l2_error_sq(V.h, uh.h, float(dirichlet), fq.h if fq is not None else None, dΩ.degree, C.byref(out)))
+    return math.sqrt(max(out.value, 0.0))
+
+
+def chart_mean(uh, V, dirichlet=0.0):
+    """(∫uh dξ)/(∫dξ): the constant Gridap's ZeroMeanFESpace removes from a solution (FEFunction of a zeromean space)."""
+    if not isinstance(uh, DeviceVector):
+        uh = DeviceVector.from_numpy(V.model.ctx, uh)
+    out = C.c_double()
+    _lib.check(V.lib.gg_chart_mean(V.h, uh.h, float(dirichlet), C.byref(out)))
+    return out.value
+
+
+def laplace_beltrami_solver(model, order, f, grad_f, hess_f, degree=None, ls=None):
+    """The driver of test/Laplacian/LaplaceBeltrami.jl:19-98 on the device: zero-mean Q_order space, a = LaplaceBeltrami,
+    l = Source(-Δs f), Jacobi-PCG solve, zero-mean shift, L2 error with a degree-2*degree rule.  Returns (error, uh, V, numerical setup)."""
+    degree = 6 * (order + 1) if degree is None else degree
+    Ω = Triangulation(model)
+    dΩ, dΩe = Measure(Ω, degree), Measure(Ω, min(2 * degree, 31))  # device rules stop at 16 points per direction
+    V = TestFESpace(model, ReferenceFE(lagrangian, float, order), conformity="H1", constraint="zeromean")
+    rhs = surface_laplacian(dΩ, grad_f, hess_f)
+    op = AffineFEOperator(LaplaceBeltrami(dΩ), Source(dΩ, rhs, scale=-1.0), V, V)
+    ns = (ls or CGSolver(rtol=1e-13, maxiter=20000)).numerical_setup(op.get_matrix())
+    uh = ns.solve(op.get_vector())
+    mean = chart_mean(uh, V)
+    _, xyz = dΩe.quadrature_points(chart=False)
+    err = l2_error(uh, V, dΩe, fq=np.asarray(f(xyz), dtype=np.float64) + mean)
+    return err, uh, V, ns
 
 
 # ---- linear solver ------------------------------------------------------------------------------------------

@@ -73,4 +73,41 @@ __device__ __forceinline__ Metric2 extrinsic_metric_terms(int panel, double a, d
   return m;
 }
 
+
+// Second derivatives of the panel map: H[l][i][k] = d^2 phi_k / (d x_i d x_l)  (src/Fields/CubedSphereMap.jl:97-123)
+__device__ __forceinline__ void csphere_hessian(int panel, double a, double b, double r, double H[2][2][3]) {
+  const double sa = 1.0 + a * a, sb = 1.0 + b * b, rho2 = 1.0 + a * a + b * b;
+  const double rho5 = rho2 * rho2 * sqrt(rho2);
+  const double D = rho2 + 3.0 * a * a * b * b, E = 3.0 * a * b * sa * sb;
+  const double F = a * sa * sb * (2.0 * b * b - sa), G = b * sa * sb * (2.0 * a * a - sb);
+  const double n[3][4] = {{-sa * D, E, E, -sb * D}, {F, G, G, -a * sb * D}, {-b * sa * D, F, F, G}};
+  const double fac = r / rho5;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int j = c_perm_j[panel][k];
+    const double s = fac * c_perm_s[panel][k];
+    H[0][0][k] = s * n[j][0]; H[1][0][k] = s * n[j][1]; H[0][1][k] = s * n[j][2]; H[1][1][k] = s * n[j][3];
+  }
+}
+
+// dg[k] = (d g11, d g12, d g22) / d x_k  (src/Fields/CubedSphereMetric.jl:52-71) and
+// dgi[k] = (d ginv11, d ginv12, d ginv22) / d x_k  (src/Fields/CubedSphereInvMetric.jl:37-56)
+__device__ __forceinline__ void csphere_metric_gradients(double a, double b, double r, double dg[2][3], double dgi[2][3]) {
+  const double sa = 1.0 + a * a, sb = 1.0 + b * b, rho2 = 1.0 + a * a + b * b;
+  const double c6 = r * r / (rho2 * rho2 * rho2);
+  dg[0][0] = 4.0 * c6 * a * sa * sa * sb * b * b;
+  dg[1][0] = 2.0 * c6 * b * sa * sa * sb * (a * a - sb);
+  dg[0][1] = -c6 * b * sa * sb * (rho2 + a * a * (3.0 * b * b - sa));
+  dg[1][1] = -c6 * a * sa * sb * (rho2 + b * b * (3.0 * a * a - sb));
+  dg[0][2] = 2.0 * c6 * a * sa * sb * sb * (b * b - sa);
+  dg[1][2] = 4.0 * c6 * b * sa * sb * sb * a * a;
+  const double ci = 1.0 / (r * r * sa * sb);
+  dgi[0][0] = -2.0 * ci * a * b * b * sb;
+  dgi[1][0] = 2.0 * ci * b * sb * sb;
+  dgi[0][1] = ci * b * (sa * rho2 - 2.0 * a * a * b * b);
+  dgi[1][1] = ci * a * (sb * rho2 - 2.0 * a * a * b * b);
+  dgi[0][2] = 2.0 * ci * a * sa * sa;
+  dgi[1][2] = -2.0 * ci * b * a * a * sa;
+}
+
 }  // namespace gg

@@ -136,6 +136,94 @@ __global__ void k_norm_cells(int64_t nc, int nq, int m, int is_rt, const double*
   sums[c] = acc;
 }
 
+// Closed-form Laplace-Beltrami operator of an ambient function at the quadrature points (src/CellData/SurfaceDiffOps.jl:26-65):
+//   Delta_s f = 1/sqrtg [ grad(sqrtg).(ginv grad_f) + sqrtg div(ginv).grad_f + sqrtg ginv : hess_f ],
+//   grad_f = J grad_X f,   hess_f = J (hess_X f) J^T + grad_X f . d2phi,   grad(sqrtg)_k = cof(g) : d_k g / (2 sqrtg)
+__global__ void k_surface_laplacian(int64_t nc, int nq, const double* __restrict__ xi, const double* __restrict__ x0,
+                                    const double* __restrict__ y0, const double* __restrict__ hx, const double* __restrict__ hy,
+                                    const int32_t* __restrict__ chart, double radius, const double* __restrict__ gf,
+                                    const double* __restrict__ hf, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Q = nq * nq;
+  if (t >= nc * Q) return;
+  const int64_t c = t / Q;
+  const int q = (int)(t - c * Q), q1 = q % nq, q2 = q / nq;
+  const double a = tan(fma(hx[c], xi[q1], x0[c])), b = tan(fma(hy[c], xi[q2], y0[c]));
+  const int panel = chart[c];
+  double J[2][3], H[2][2][3], dg[2][3], dgi[2][3];
+  csphere_jacobian(panel, a, b, radius, J);
+  csphere_hessian(panel, a, b, radius, H);
+  csphere_metric_gradients(a, b, radius, dg, dgi);
+  const Metric2 m = csphere_metric_terms(a, b, radius);
+  const double* g1 = gf + 3 * t;
+  const double* h2 = hf + 9 * t;
+  double gradf[2], hess[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) gradf[i] = J[i][0] * g1[0] + J[i][1] * g1[1] + J[i][2] * g1[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) v = fma(J[i][k] * h2[3 * k + l], J[j][l], v);
+        v = fma(g1[k], H[i][j][k], v);
+      }
+      hess[i][j] = v;
+    }
+  const double gi[2][2] = {{m.i11, m.i12}, {m.i12, m.i22}};
+  // cof(g) : d_k g = g22 d g11 - 2 g12 d g12 + g11 d g22
+  double gm[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) gm[k] = 0.5 / m.sqrtg * (m.g22 * dg[k][0] - 2.0 * m.g12 * dg[k][1] + m.g11 * dg[k][2]);
+  // (div ginv)_j = d_i ginv_ij
+  const double dv[2] = {dgi[0][0] + dgi[1][1], dgi[0][1] + dgi[1][2]};
+  double t1 = 0.0, t3 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { t1 = fma(gm[i] * gi[i][j], gradf[j], t1); t3 = fma(gi[i][j], hess[i][j], t3); }
+  const double t2 = dv[0] * gradf[0] + dv[1] * gradf[1];
+  out[t] = t1 / m.sqrtg + t2 + t3;
+}
+
+// per-cell functionals of u_h.  MODE 0: int (u_h - f)^2 sqrtg with f given at the quadrature points (f may be NULL);
+// MODE 1: int u_h in the CHART measure (no sqrtg); MODE 2: chart area of the cell
+template <int MODE>
+__global__ void k_l2_error_cells(int64_t nc, int nq, int m, const double* __restrict__ x0, const double* __restrict__ y0,
+                                 const double* __restrict__ hx, const double* __restrict__ hy, double radius,
+                                 const double* __restrict__ xi, const double* __restrict__ w, const double* __restrict__ val,
+                                 const int32_t* __restrict__ dofs, const double* __restrict__ u, double dirichlet,
+                                 const double* __restrict__ fq, const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  if (cell_owned && !cell_owned[c]) { sums[c] = 0.0; return; }
+  const double HX = hx[c], HY = hy[c];
+  const int Q = nq * nq;
+  double acc = 0.0;
+  for (int q2 = 0; q2 < nq; ++q2) {
+    const double b = tan(fma(HY, xi[q2], y0[c]));
+    for (int q1 = 0; q1 < nq; ++q1) {
+      const int q = q1 + nq * q2;
+      const Metric2 mt = csphere_metric_terms(tan(fma(HX, xi[q1], x0[c])), b, radius);
+      double uh = 0.0;
+      for (int j = 0; j < m; ++j) {
+        const int32_t d = dofs[c * m + j];
+        uh = fma(val[q * m + j], d >= 0 ? u[d] : dirichlet, uh);
+      }
+      if (MODE == 0) {
+        const double e = uh - (fq ? fq[c * Q + q] : 0.0);
+        acc = fma(w[q1] * w[q2] * HX * HY * mt.sqrtg, e * e, acc);
+      } else {
+        acc = fma(w[q1] * w[q2] * HX * HY, MODE == 1 ? uh : 1.0, acc);
+      }
+    }
+  }
+  sums[c] = acc;
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -230,6 +318,92 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   ctx->launches += 3;
   GG_CUDA(cudaGetLastError());
   total.download(out, st);
+  GG_API_END
+}
+
+int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const double* hess_f, gg_vec* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && grad_f && hess_f && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "the surface Laplacian of an ambient function is implemented on the 2-D surface");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  const int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  const int64_t n = m->n_cells * nq * nq;
+  GG_REQUIRE(gg_vec_size(out) == n, GG_ERR_INVALID, "output vector must have n_cells * Q entries");
+  if (n == 0) return GG_OK;
+  cudaStream_t st = ctx->stream;
+  auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
+  DevBuf<double> dg, dh;
+  dg.upload(grad_f, (size_t)3 * n, st); dh.upload(hess_f, (size_t)9 * n, st);
+  k_surface_laplacian<<<nblk(n, 128), 128, 0, st>>>(m->n_cells, nq, T->xi.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->d_chart.p,
+                                                   m->radius, dg.p, dh.p, out->d.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  GG_CUDA(cudaStreamSynchronize(st));
+  GG_API_END
+}
+
+int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && u && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(s->kind != GG_SPACE_RT && s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "L2 errors are implemented for Lagrangian spaces on the 2-D surface");
+  GG_REQUIRE(gg_vec_size(u) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  gg_mesh* m = s->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  const int64_t nc = m->n_cells;
+  if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq, GG_ERR_INVALID, "f must be given at the n_cells * Q quadrature points");
+  *out = 0.0;
+  if (nc == 0) return GG_OK;
+  auto T = get_tab(ctx, s->kind, s->order, nq);
+  DevBuf<double> sums(nc), total(1);
+  k_l2_error_cells<0><<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius, T->xi.p,
+                                                  T->w.p, T->val.p, s->d_cell_dofs.p, u->d.p, dirichlet, fq ? fq->d.p : nullptr,
+                                                  m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
+  size_t tb = 0;
+  GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
+  DevBuf<uint8_t> tmp(tb);
+  GG_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, sums.p, total.p, (int)nc, st));
+  ctx->launches += 3;
+  GG_CUDA(cudaGetLastError());
+  total.download(out, st);
+  GG_API_END
+}
+
+int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out) {
+  GG_API_BEGIN
+  GG_REQUIRE(s && u && out, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(s->kind != GG_SPACE_RT && s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "chart means are implemented for Lagrangian spaces on the 2-D surface");
+  GG_REQUIRE(gg_vec_size(u) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  gg_mesh* m = s->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nq = num_points_1d(2 * (s->order > 0 ? s->order : 1));
+  const int64_t nc = m->n_cells;
+  *out = 0.0;
+  if (nc == 0) return GG_OK;
+  auto T = get_tab(ctx, s->kind, s->order, nq);
+  DevBuf<double> sums(2 * nc), total(2);
+  const uint8_t* own = m->d_cell_owned.n ? m->d_cell_owned.p : nullptr;
+  k_l2_error_cells<1><<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius, T->xi.p,
+                                                     T->w.p, T->val.p, s->d_cell_dofs.p, u->d.p, dirichlet, nullptr, own, sums.p);
+  k_l2_error_cells<2><<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius, T->xi.p,
+                                                     T->w.p, T->val.p, s->d_cell_dofs.p, u->d.p, dirichlet, nullptr, own, sums.p + nc);
+  size_t tb = 0;
+  GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
+  DevBuf<uint8_t> tmp(tb);
+  GG_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, sums.p, total.p, (int)nc, st));
+  GG_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, sums.p + nc, total.p + 1, (int)nc, st));
+  ctx->launches += 6;
+  GG_CUDA(cudaGetLastError());
+  double h[2];
+  total.download(h, st);
+  *out = h[0] / h[1];
   GG_API_END
 }
 

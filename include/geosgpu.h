@@ -270,6 +270,19 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out);
  * Lagrangian: sum(int e^2 sqrtg);  RT: sum(int e.(g e) / sqrtg), quadrature degree `degree`. */
 int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
 
+/* Delta_s f of an AMBIENT function f at the quadrature points, closed form (use_automatic_differentiation=false branch of
+ * Δs(f, Ω), src/CellData/SurfaceDiffOps.jl:26-65,78-82; Hessian of the map src/Fields/CubedSphereMap.jl:97-123, metric
+ * derivatives CubedSphereMetric.jl:52-71, CubedSphereInvMetric.jl:37-56).  The caller evaluates grad_X f [n_cells][Q][3] and
+ * hess_X f [n_cells][Q][3][3] at the ambient points of gg_quadrature_points; out has n_cells * Q entries and can be passed
+ * as `qdata` of GG_FORM_SOURCE (the manufactured right-hand side of test/Laplacian/LaplaceBeltrami.jl:41-53). */
+int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const double* hess_f, gg_vec* out);
+/* sum(int (u_h - f)^2 sqrtg) with f at the quadrature points (NULL = 0): the error measure of
+ * test/Laplacian/LaplaceBeltrami.jl:82-83; `dirichlet` is the value of the constrained DOF of a zeromean space */
+int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out);
+/* (int u_h d xi) / (int d xi) in the CHART measure: the shift Gridap's ZeroMeanFESpace subtracts after a solve
+ * (FEFunction(::ZeroMeanFESpace, ...): c = -(vol_i . x) / vol), used by test/Laplacian/LaplaceBeltrami.jl:71 */
+int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out);
+
 /* ---- explicit Runge-Kutta drivers ----------------------------------------------------------------
  * GG_PROBLEM_WAVE: replaces Gridap.ODEs `ode_march!` for EXRungeKutta on the linear-wave operator
  * (test/Transient/TransientWaveEquation.jl:63-77; constant mass).
