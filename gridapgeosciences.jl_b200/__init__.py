@@ -724,6 +724,27 @@ def surface_laplacian(dΩ, grad_f, hess_f):
     return out
 
 
+def surface_gradient(dΩ, grad_f):
+    """∇s(f, Ω): contravariant components (n_cells, Q, 2) at the quadrature points (src/CellData/SurfaceDiffOps.jl:107-133)."""
+    m = dΩ.model
+    _, xyz = dΩ.quadrature_points(chart=False)
+    g = np.ascontiguousarray(np.broadcast_to(grad_f(xyz), xyz.shape), dtype=np.float64)
+    out = DeviceVector(m.ctx, 2 * m.num_cells * dΩ.num_points)
+    _lib.check(m.lib.gg_surface_gradient(m.h, dΩ.degree, _dp(g), out.h))
+    return out
+
+
+def surface_divergence(dΩ, F, grad_F):
+    """divs(F, Ω) of an ambient vector field at the quadrature points (src/CellData/SurfaceDiffOps.jl:228-259)."""
+    m = dΩ.model
+    _, xyz = dΩ.quadrature_points(chart=False)
+    f = np.ascontiguousarray(np.broadcast_to(F(xyz), xyz.shape), dtype=np.float64)
+    g = np.ascontiguousarray(np.broadcast_to(grad_F(xyz), xyz.shape + (3,)), dtype=np.float64)
+    out = DeviceVector(m.ctx, m.num_cells * dΩ.num_points)
+    _lib.check(m.lib.gg_surface_divergence(m.h, dΩ.degree, _dp(f), _dp(g), out.h))
+    return out
+
+
 def l2_error(uh, V, dΩ, fq=None, dirichlet=0.0):
     """sqrt(sum(∫((f - uh)*(f - uh)*meas_cf)dΩ)) with f at the quadrature points of dΩ (test/Laplacian/LaplaceBeltrami.jl:82-83)."""
     ctx = V.model.ctx

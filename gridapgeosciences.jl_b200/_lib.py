@@ -129,6 +129,8 @@ SIGNATURES = {
     "gg_norm_sq": (C.c_int, [_P, _P, C.c_int32, _PD]),
     "gg_surface_laplacian": (C.c_int, [_P, C.c_int32, _PD, _PD, _P]),
     "gg_l2_error_sq": (C.c_int, [_P, _P, C.c_double, _P, C.c_int32, _PD]),
+    "gg_surface_gradient": (C.c_int, [_P, C.c_int32, _PD, _P]),
+    "gg_surface_divergence": (C.c_int, [_P, C.c_int32, _PD, _PD, _P]),
     "gg_chart_mean": (C.c_int, [_P, _P, C.c_double, _PD]),
     "gg_rk_create": (C.c_int, [_P, C.POINTER(RKArgs), _PP]),
     "gg_rk_info": (C.c_int, [_P, _PI64, _PI64]),

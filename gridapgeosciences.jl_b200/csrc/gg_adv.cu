@@ -18,6 +18,7 @@
 #include "gg_rk.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
+#include "gg_dist_host.cuh"
 
 namespace gg {
 
@@ -98,12 +99,21 @@ template <int P>
 __global__ void __launch_bounds__(128)
 k_adv_slope(int64_t nc, int nq, int nqf, AdvTabs T, const double* __restrict__ bq, const double* __restrict__ bn,
             const double* __restrict__ wsg, const int32_t* __restrict__ nbr_cell, const int8_t* __restrict__ nbr_edge,
-            const int8_t* __restrict__ is_plus, const double* __restrict__ MInv, const double* __restrict__ u,
-            double* __restrict__ kout, double* __restrict__ rout) {
+            const int8_t* __restrict__ is_plus, const double* __restrict__ MInv, const uint8_t* __restrict__ cell_owned,
+            const double* __restrict__ u, double* __restrict__ kout, double* __restrict__ rout) {
   constexpr int M = (P + 1) * (P + 1);
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   double ue[M], r[M];
+  if (cell_owned && !cell_owned[c]) {
+    // ghost cell of a partitioned model: its slope belongs to another rank (the stage states are made consistent instead)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      if (rout) rout[c * M + j] = 0.0;
+      if (kout) kout[c * M + j] = 0.0;
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < M; ++j) { ue[j] = u[c * M + j]; r[j] = 0.0; }
   const int Q = nq * nq;
@@ -169,7 +179,7 @@ void adv_slope_async(gg_rk* rk, const double* u, double* kout, double* rout) {
   unsigned nb = nblk(nc, 128);
   ProfScope ps(ctx, "k_adv_slope");
 #define GG_ARGS nc, rk->nq1, rk->nq1, T, rk->adv_bq.p, rk->adv_bn.p, rk->adv_wsg.p, rk->adv_nbr_cell.p, rk->adv_nbr_edge.p, \
-                rk->adv_is_plus.p, rk->MpInv.p, u, kout, rout
+                rk->adv_is_plus.p, rk->MpInv.p, rk->mesh->d_cell_owned.n ? rk->mesh->d_cell_owned.p : nullptr, u, kout, rout
   switch (rk->order) {
     case 0: k_adv_slope<0><<<nb, 128, 0, ctx->stream>>>(GG_ARGS); break;
     case 1: k_adv_slope<1><<<nb, 128, 0, ctx->stream>>>(GG_ARGS); break;
@@ -189,6 +199,7 @@ void adv_step_async(gg_rk* rk) {
       double co[4] = {0, 0, 0, 0};
       for (int j = 0; j < i && j < 4; ++j) co[j] = rk->dt * rk->A[i * s + j];
       rk_combine(rk, std::min(i, 4), co, rk->xi.p);
+      vec_consistent_async(rk->Q, rk->xi.p);   // partitioned models: owner -> ghost cells, through peer memory
       xs = rk->xi.p;
     }
     adv_slope_async(rk, xs, rk->k[i].p, nullptr);
@@ -196,6 +207,7 @@ void adv_step_async(gg_rk* rk) {
   double co[4] = {0, 0, 0, 0};
   for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
   rk_combine(rk, std::min(s, 4), co, rk->x.p);
+  vec_consistent_async(rk->Q, rk->x.p);
 }
 
 void adv_create(gg_rk* rk, const gg_rk_args* a) {
@@ -204,7 +216,6 @@ void adv_create(gg_rk* rk, const gg_rk_args* a) {
   cudaStream_t st = ctx->stream;
   GG_REQUIRE(a->velocity_cells && a->velocity_facets, GG_ERR_INVALID,
              "DG advection needs the ambient wind at the cell and facet quadrature points");
-  GG_REQUIRE(!m->plan, GG_ERR_UNSUPPORTED, "DG advection on partitioned models is not implemented");
   const int64_t nc = m->n_cells;
   const int nq = num_points_1d(a->degree), Q = nq * nq, M = rk->mq;
   rk->nq1 = nq;
@@ -220,6 +231,12 @@ void adv_create(gg_rk* rk, const gg_rk_args* a) {
       const int32_t ed = m->cell_edges[c * 4 + e];
       GG_REQUIRE(!m->cell_edge_flip[c * 4 + e], GG_ERR_UNSUPPORTED, "skeleton terms need shared edges with the same vertex order in both cells");
       const int32_t c0 = m->edge_cells[ed * 2], c1 = m->edge_cells[ed * 2 + 1];
+      const bool owned = m->cell_owned.empty() || m->cell_owned[c];
+      if (c1 < 0 && !owned) {
+        // outer edge of the ghost layer of a partitioned model: never integrated (ghost cells are skipped)
+        nbr_cell[c * 4 + e] = (int32_t)c; nbr_edge[c * 4 + e] = (int8_t)e; is_plus[c * 4 + e] = 1;
+        continue;
+      }
       GG_REQUIRE(c1 >= 0, GG_ERR_UNSUPPORTED, "boundary facets are not supported (the cubed sphere is closed)");
       const int32_t other = c0 == (int32_t)c ? c1 : c0;
       int eo = -1;

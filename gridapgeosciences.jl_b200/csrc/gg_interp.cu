@@ -224,6 +224,58 @@ __global__ void k_l2_error_cells(int64_t nc, int nq, int m, const double* __rest
   sums[c] = acc;
 }
 
+// MODE 0: contravariant surface gradient ginv (J grad_X f) -> out[t][2]           (src/CellData/SurfaceDiffOps.jl:107-115)
+// MODE 1: surface divergence 1/sqrtg div(sqrtg ginv J F) of an ambient field -> out[t]   (:228-259)
+template <int MODE>
+__global__ void k_surface_grad_div(int64_t nc, int nq, const double* __restrict__ xi, const double* __restrict__ x0,
+                                   const double* __restrict__ y0, const double* __restrict__ hx, const double* __restrict__ hy,
+                                   const int32_t* __restrict__ chart, double radius, const double* __restrict__ F,
+                                   const double* __restrict__ dF, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Q = nq * nq;
+  if (t >= nc * Q) return;
+  const int64_t c = t / Q;
+  const int q = (int)(t - c * Q), q1 = q % nq, q2 = q / nq;
+  const double a = tan(fma(hx[c], xi[q1], x0[c])), b = tan(fma(hy[c], xi[q2], y0[c]));
+  const int panel = chart[c];
+  double J[2][3];
+  csphere_jacobian(panel, a, b, radius, J);
+  const Metric2 m = csphere_metric_terms(a, b, radius);
+  const double gi[2][2] = {{m.i11, m.i12}, {m.i12, m.i22}};
+  const double* f = F + 3 * t;
+  double JF[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) JF[i] = J[i][0] * f[0] + J[i][1] * f[1] + J[i][2] * f[2];
+  if (MODE == 0) {
+    out[2 * t] = gi[0][0] * JF[0] + gi[0][1] * JF[1];
+    out[2 * t + 1] = gi[1][0] * JF[0] + gi[1][1] * JF[1];
+    return;
+  }
+  double H[2][2][3], dg[2][3], dgi[2][3];
+  csphere_hessian(panel, a, b, radius, H);
+  csphere_metric_gradients(a, b, radius, dg, dgi);
+  const double* d = dF + 9 * t;
+  double gm[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) gm[k] = 0.5 / m.sqrtg * (m.g22 * dg[k][0] - 2.0 * m.g12 * dg[k][1] + m.g11 * dg[k][2]);
+  const double dv[2] = {dgi[0][0] + dgi[1][1], dgi[0][1] + dgi[1][2]};
+  double acc = dv[0] * JF[0] + dv[1] * JF[1];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v = fma(H[i][j][k], f[k], v);                                                   // (d_i J_jk) F_k
+        v = fma(J[j][k], J[i][0] * d[k] + J[i][1] * d[3 + k] + J[i][2] * d[6 + k], v);  // J_jk J_il dF_lk
+      }
+      acc = fma(gi[i][j], v, acc);
+      acc = fma(gm[i] * gi[i][j], JF[j] / m.sqrtg, acc);
+    }
+  out[t] = acc;
+}
+
 }  // namespace gg
 
 using namespace gg;
@@ -405,6 +457,46 @@ int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out) {
   total.download(h, st);
   *out = h[0] / h[1];
   GG_API_END
+}
+
+}  // extern "C"
+
+static int surface_grad_div(gg_mesh* m, int32_t degree, const double* F, const double* dF, gg_vec* out, int mode) {
+  GG_API_BEGIN
+  GG_REQUIRE(m && F && out && (mode == 0 || dF), GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "surface differential operators of ambient functions are implemented on the 2-D surface");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  const int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  const int64_t n = m->n_cells * nq * nq;
+  GG_REQUIRE(gg_vec_size(out) == (mode == 0 ? 2 * n : n), GG_ERR_INVALID, "output vector has the wrong length");
+  if (n == 0) return GG_OK;
+  cudaStream_t st = ctx->stream;
+  auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
+  DevBuf<double> dg, dh;
+  dg.upload(F, (size_t)3 * n, st);
+  if (mode == 1) dh.upload(dF, (size_t)9 * n, st);
+  if (mode == 0)
+    k_surface_grad_div<0><<<nblk(n, 128), 128, 0, st>>>(m->n_cells, nq, T->xi.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->d_chart.p,
+                                                        m->radius, dg.p, nullptr, out->d.p);
+  else
+    k_surface_grad_div<1><<<nblk(n, 128), 128, 0, st>>>(m->n_cells, nq, T->xi.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->d_chart.p,
+                                                        m->radius, dg.p, dh.p, out->d.p);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  GG_CUDA(cudaStreamSynchronize(st));
+  GG_API_END
+}
+
+extern "C" {
+
+int gg_surface_gradient(gg_mesh* m, int32_t degree, const double* grad_f, gg_vec* out) {
+  return surface_grad_div(m, degree, grad_f, nullptr, out, 0);
+}
+
+int gg_surface_divergence(gg_mesh* m, int32_t degree, const double* F, const double* grad_F, gg_vec* out) {
+  return surface_grad_div(m, degree, F, grad_F, out, 1);
 }
 
 }  // extern "C"

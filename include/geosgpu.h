@@ -276,6 +276,13 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
  * hess_X f [n_cells][Q][3][3] at the ambient points of gg_quadrature_points; out has n_cells * Q entries and can be passed
  * as `qdata` of GG_FORM_SOURCE (the manufactured right-hand side of test/Laplacian/LaplaceBeltrami.jl:41-53). */
 int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const double* hess_f, gg_vec* out);
+/* Contravariant components of the surface gradient, ginv . (J grad_X f): out [n_cells][Q][2]
+ * (∇s(f, Ω), src/CellData/SurfaceDiffOps.jl:107-115,127-133) */
+int gg_surface_gradient(gg_mesh* m, int32_t degree, const double* grad_f, gg_vec* out);
+/* Surface divergence of an ambient vector field, 1/sqrtg div(sqrtg ginv J F): F [n_cells][Q][3],
+ * grad_F [n_cells][Q][3][3] with grad_F[l][k] = dF_k/dX_l (Gridap's convention); out [n_cells][Q]
+ * (divs(f, Ω), src/CellData/SurfaceDiffOps.jl:228-259) */
+int gg_surface_divergence(gg_mesh* m, int32_t degree, const double* F, const double* grad_F, gg_vec* out);
 /* sum(int (u_h - f)^2 sqrtg) with f at the quadrature points (NULL = 0): the error measure of
  * test/Laplacian/LaplaceBeltrami.jl:82-83; `dirichlet` is the value of the constrained DOF of a zeromean space */
 int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out);

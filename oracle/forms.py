@@ -208,3 +208,46 @@ def surface_laplacian(f, gradf, hessf, mesh, x, cell_to_chart):
         t3 = meas * np.einsum("...ij,...ij->...", gi, gg)
         out[sel] = (t1 + t2 + t3) / meas
     return out
+
+
+def surface_gradient(gradf, mesh, x, cell_to_chart):
+    """Contravariant components of the surface gradient, ginv . (J grad_X f) -- src/CellData/SurfaceDiffOps.jl:107-115 (_∇s_no_ad)."""
+    out = np.empty(x.shape[:2] + (2,))
+    for p in range(6):
+        sel = cell_to_chart == p
+        xs = x[sel]
+        X = geo.csphere_eval(p + 1, mesh.radius, xs)
+        J = geo.csphere_jac(p + 1, mesh.radius, xs)
+        gi = geo.csphere_inv_metric(mesh.radius, xs)
+        out[sel] = np.einsum("...ij,...jk,...k->...i", gi, J, gradf(X))
+    return out
+
+
+def surface_divergence(F, gradF, mesh, x, cell_to_chart):
+    """divs F = 1/sqrtg div(sqrtg Jdag (F o phi)), Jdag = ginv J -- src/CellData/SurfaceDiffOps.jl:228-259 (_divs_no_ad).
+
+    F: xyz -> (..,3); gradF: xyz -> (..,3,3) with Gridap's convention gradF[l,k] = d F_k / d X_l."""
+    r = mesh.radius
+    out = np.empty(x.shape[:2])
+    for p in range(6):
+        sel = cell_to_chart == p
+        xs = x[sel]
+        X = geo.csphere_eval(p + 1, r, xs)
+        J = geo.csphere_jac(p + 1, r, xs)                  # [i,k]
+        H = geo.csphere_hess(p + 1, r, xs)                 # [l,i,k] = d_l J[i,k]
+        g = geo.csphere_metric(r, xs)
+        gi = geo.csphere_inv_metric(r, xs)
+        dg = geo.csphere_metric_grad(r, xs)                # [k,i,j]
+        dgi = geo.csphere_inv_metric_grad(r, xs)           # [k,i,j]
+        meas = np.sqrt(g[..., 0, 0] * g[..., 1, 1] - g[..., 0, 1] ** 2)
+        cof = np.empty_like(g)
+        cof[..., 0, 0], cof[..., 1, 1] = g[..., 1, 1], g[..., 0, 0]
+        cof[..., 0, 1], cof[..., 1, 0] = -g[..., 1, 0], -g[..., 0, 1]
+        grad_meas = (0.5 / meas)[..., None] * np.einsum("...ij,...kij->...k", cof, dg)
+        Fv, dF = F(X), gradF(X)
+        JF = np.einsum("...jk,...k->...j", J, Fv)
+        tr1 = np.einsum("...iij,...j->...", dgi, JF)                         # (d_i ginv_ij) (J F)_j
+        tr2 = np.einsum("...ij,...ijk,...k->...", gi, H, Fv)                 # ginv_ij (d_i J_jk) F_k
+        tr3 = np.einsum("...ij,...jk,...il,...lk->...", gi, J, J, dF)        # ginv_ij J_jk d_i (F_k o phi)
+        out[sel] = tr1 + tr2 + tr3 + np.einsum("...i,...ij,...j->...", grad_meas, gi, JF) / meas
+    return out

@@ -82,3 +82,21 @@ def test_laplace_beltrami_driver_convergence(gg):
             assert abs(e - e_ref) <= 1e-6 * e_ref   # different error rule (degree 31 instead of 36) and an iterative solve
     slope = np.polyfit(np.log10(dxs), np.log10(errs), 1)[0]
     assert slope >= 2
+
+
+def test_surface_gradient_and_divergence_match_oracle(gg):
+    # the fields of test/Autodiff/seq/SurfDiffOperatorTests.jl:25-33
+    from oracle import forms
+    from oracle.mesh import CubedSphereMesh2D
+    from test_oracle_forms import _ambient_vecX, _grad_ambient_fX, _grad_ambient_vecX
+    r = 1.7
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(r), n=3)
+    dΩ = gg.Measure(gg.Triangulation(model), 5)
+    mesh = CubedSphereMesh2D(3, r)
+    q = forms.CellQuadrature(mesh, 5)
+    sg = gg.surface_gradient(dΩ, _grad_ambient_fX).get().reshape(model.num_cells, -1, 2)
+    ref = forms.surface_gradient(_grad_ambient_fX, mesh, q.x, mesh.cell_to_chart)
+    assert np.abs(sg - ref).max() <= 1e-12 * np.abs(ref).max()
+    sd = gg.surface_divergence(dΩ, _ambient_vecX, _grad_ambient_vecX).get().reshape(model.num_cells, -1)
+    ref = forms.surface_divergence(_ambient_vecX, _grad_ambient_vecX, mesh, q.x, mesh.cell_to_chart)
+    assert np.abs(sd - ref).max() <= 1e-12 * np.abs(ref).max()

@@ -154,3 +154,51 @@ def test_rt_interpolation_reproduces_rt_fields():
         ue = geo.csphere_sqrtg(1.0, q.x[sel])[..., None] * np.einsum("...ik,...k->...i", P, vfun(X))
         err = max(err, np.abs(ue - uh[sel]).max())
     assert err < 2e-2
+
+
+def _ambient_fX(X):           # test/Autodiff/seq/SurfDiffOperatorTests.jl:25-28
+    return X[..., 0] ** 2 + X[..., 1] ** 2 * X[..., 2]
+
+
+def _grad_ambient_fX(X):
+    x, y, z = X[..., 0], X[..., 1], X[..., 2]
+    return np.stack([2 * x, 2 * y * z, y * y], axis=-1)
+
+
+def _ambient_vecX(X):         # :30-33
+    x, y = X[..., 0], X[..., 1]
+    return np.stack([y * y, -x * x, np.zeros_like(x)], axis=-1)
+
+
+def _grad_ambient_vecX(X):    # [l,k] = d F_k / d X_l
+    x, y = X[..., 0], X[..., 1]
+    G = np.zeros(X.shape + (3,))
+    G[..., 1, 0] = 2 * y
+    G[..., 0, 1] = -2 * x
+    return G
+
+
+def test_surface_gradient_and_divergence_equal_their_ambient_forms():
+    # test/Autodiff/seq/SurfDiffOperatorTests.jl:43-62: intrinsic == extrinsic pointwise, 1e-12
+    from oracle import geometry as geo
+    r = 1.0
+    mesh = CubedSphereMesh2D(2, r)
+    q = forms.CellQuadrature(mesh, 4)
+    X = q.ambient()
+    n = X / r
+    P = np.eye(3) - n[..., :, None] * n[..., None, :]
+    sg = forms.surface_gradient(_grad_ambient_fX, mesh, q.x, mesh.cell_to_chart)
+    push = np.empty(X.shape)
+    for p in range(6):
+        sel = mesh.cell_to_chart == p
+        J = geo.csphere_jac(p + 1, r, q.x[sel])
+        push[sel] = np.einsum("...ik,...i->...k", J, sg[sel])                # covariant basis . contravariant components
+    assert np.abs(push - np.einsum("...kl,...l->...k", P, _grad_ambient_fX(X))).max() < 1e-12
+    sd = forms.surface_divergence(_ambient_vecX, _grad_ambient_vecX, mesh, q.x, mesh.cell_to_chart)
+    F, dF = _ambient_vecX(X), _grad_ambient_vecX(X)
+    amb = np.einsum("...lk,...lk->...", P, dF) - 2.0 / r * np.einsum("...k,...k->...", F, n)
+    assert np.abs(sd - amb).max() < 1e-12
+    # divs(grad f) = Delta_s f for any ambient f (the normal part of grad f drops out)
+    lap = forms.surface_laplacian(fX, grad_fX, hess_fX, mesh, q.x, mesh.cell_to_chart)
+    sd2 = forms.surface_divergence(grad_fX, hess_fX, mesh, q.x, mesh.cell_to_chart)
+    assert np.abs(sd2 - lap).max() < 1e-12
