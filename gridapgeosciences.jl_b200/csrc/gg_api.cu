@@ -49,7 +49,12 @@ int gg_init(int device_id, gg_ctx** out) {
   ctx->device = device_id;
   ctx->sm_count = prop.multiProcessorCount;
   GG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  GG_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  {
+    // the fill stream outranks the main stream: its CTAs must get onto the SMs while the element kernel still has CTAs queued
+    int lo = 0, hi = 0;
+    GG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GG_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+  }
   for (auto& e : ctx->ev_batch) GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx.release();

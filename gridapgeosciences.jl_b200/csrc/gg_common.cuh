@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -223,6 +224,16 @@ struct gg_vec {
 };
 
 namespace gg { struct HexTensor; }
+// number of cell batches of the pipelined CSR fill (GG_PIPELINE_BATCHES, 1..8)
+inline int pipeline_batches() {
+  static const int n = [] {
+    const char* e = getenv("GG_PIPELINE_BATCHES");
+    int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  return n;
+}
+
 struct gg_csr {
   gg_ctx* ctx = nullptr;
   // 3-D shell matrices: maps of the tensor-structured numeric phase (gg_forms.cu), built at first use
@@ -247,7 +258,7 @@ struct gg_csr {
   gg::DevBuf<int32_t> d_roundptr;  // [n_chunks][n_rounds+1]
   // pipelining of the numeric phase: chunks ordered by the cell batch that completes them (all of a chunk's sources
   // lie in batches <= its batch), so the CSR fill of batch b can run while the element kernel works on batch b+1
-  static constexpr int N_BATCH = 8;
+  static constexpr int N_BATCH = 8;   // upper bound; pipeline_batches() gives the count in use
   gg::DevBuf<int32_t> d_chunk_order;       // [n_chunks] chunk ids sorted by completing batch
   int64_t batch_chunk_ptr[N_BATCH + 1] = {0};
 };

@@ -420,10 +420,11 @@ static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int
   load_const_tables(ctx, order, nq);
   CellGeo g = cell_geo(m, nq);
   int64_t nc = m->n_cells;
-  const int NBt = gg_csr::N_BATCH;
-  // Measured on B200 (round 1, 393 216 cells): 0.287 ms sequential vs 0.306-0.348 ms pipelined -- the co-resident fill CTAs
-  // slow the FP64-bound element kernel more than the overlap gains and the 8 batches add partial waves, so the pipeline
-  // stays off unless GG_PIPELINE=1 is exported (kept for the next round's wave-aligned batching experiment).
+  const int NBt = pipeline_batches();
+  // Measured on B200 (round 1, 393 216 cells, tools/pipeline_sweep.sh): 0.282 ms sequential vs 0.306-0.41 ms pipelined for
+  // 2, 3, 4 and 8 batches, with and without the shared-memory reservation that leaves room for the fill CTAs, fill stream at
+  // the highest priority -- the co-resident fill CTAs slow the FP64-bound element kernel more than the overlap gains, so the
+  // pipeline stays off unless GG_PIPELINE=1 is exported (GG_PIPELINE_BATCHES, GG_PIPELINE_ROOM select the variant).
   static const bool want_pipeline = getenv("GG_PIPELINE") && getenv("GG_PIPELINE")[0] == '1';
   if (!pipe || !want_pipeline || nc < 64 * 1024 || ctx->profile) {
     // default, small meshes (launch-bound) and per-kernel profiling runs: one element launch, one fill launch
@@ -435,7 +436,8 @@ static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int
   for (int b = 0; b < NBt; ++b) {
     // batch boundaries rounded to whole CTAs; batch b owns cells with (cell * NBt) / nc == b
     int64_t c0 = (b * nc + NBt - 1) / NBt, c1 = ((b + 1) * nc + NBt - 1) / NBt;
-    run_lb_fast_range(m, order, nq, extrinsic, c0, c1, g, dofs, u, dir, ebuf, vbuf, true);
+    static const bool room = !(getenv("GG_PIPELINE_ROOM") && getenv("GG_PIPELINE_ROOM")[0] == '0');
+    run_lb_fast_range(m, order, nq, extrinsic, c0, c1, g, dofs, u, dir, ebuf, vbuf, room);
     GG_CUDA(cudaEventRecord(ctx->ev_batch[b], ctx->stream));
     GG_CUDA(cudaStreamWaitEvent(ctx->stream2, ctx->ev_batch[b], 0));
     gather_matrix_batch(pipe->A, b, ebuf, pipe->scale, pipe->add, ctx->stream2);

@@ -306,7 +306,7 @@ static void build_chunk_lists(gg_csr* A, int layout) {
   A->n_chunks = nchunks;
   // order the chunks by the cell batch that completes them
   {
-    const int NBt = gg_csr::N_BATCH;
+    const int NBt = pipeline_batches();
     DevBuf<int32_t> d_cb(nchunks);
     k_chunk_batch<<<(unsigned)nchunks, 256, 0, st>>>(A->test->mesh->n_cells, R, NBt, A->d_roundptr.p, A->d_lsrc.p, d_cb.p);
     ctx->launches++;
