@@ -101,7 +101,7 @@ __global__ void k_norm_cells(int64_t nc, int nq, int m, int is_rt, const double*
                              const double* __restrict__ hx, const double* __restrict__ hy, double radius,
                              const double* __restrict__ xi, const double* __restrict__ w, const double* __restrict__ val,
                              const int32_t* __restrict__ dofs, const int8_t* __restrict__ signs, const double* __restrict__ e,
-                             const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
+                             const double* __restrict__ fq, const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   if (cell_owned && !cell_owned[c]) { sums[c] = 0.0; return; }  // partitioned model: ghost cells are counted by their owner
@@ -121,8 +121,10 @@ __global__ void k_norm_cells(int64_t nc, int nq, int m, int is_rt, const double*
           Ux = fma(val[(q * m + j) * 2], ej, Ux);
           Uy = fma(val[(q * m + j) * 2 + 1], ej, Uy);
         }
-        const double ux = Ux / HY, uy = Uy / HX;
-        acc = fma(wq / mt.sqrtg, ux * (mt.g11 * ux + mt.g12 * uy) + uy * (mt.g12 * ux + mt.g22 * uy), acc);
+        // contravariant components u_h / sqrtg, minus the exact contravariant field when one is given
+        double ux = Ux / (HY * mt.sqrtg), uy = Uy / (HX * mt.sqrtg);
+        if (fq) { ux -= fq[(c * nq * nq + q) * 2]; uy -= fq[(c * nq * nq + q) * 2 + 1]; }
+        acc = fma(wq * mt.sqrtg, ux * (mt.g11 * ux + mt.g12 * uy) + uy * (mt.g12 * ux + mt.g22 * uy), acc);
       } else {
         double eh = 0.0;
         for (int j = 0; j < m; ++j) {
@@ -362,7 +364,7 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   int is_rt = s->kind == GG_SPACE_RT ? 1 : 0;
   k_norm_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, is_rt, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius,
                                               T->xi.p, T->w.p, T->val.p, s->d_cell_dofs.p, is_rt ? s->d_cell_signs.p : nullptr,
-                                              e->d.p, m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
+                                              e->d.p, nullptr, m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;
   GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
   DevBuf<uint8_t> tmp(tb);
@@ -399,7 +401,7 @@ int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const
 int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && u && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(s->kind != GG_SPACE_RT && s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "L2 errors are implemented for Lagrangian spaces on the 2-D surface");
+  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "L2 errors are implemented on the 2-D surface");
   GG_REQUIRE(gg_vec_size(u) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
@@ -408,11 +410,18 @@ int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t
   const int nq = num_points_1d(degree);
   GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   const int64_t nc = m->n_cells;
-  if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq, GG_ERR_INVALID, "f must be given at the n_cells * Q quadrature points");
+  const bool is_rt = s->kind == GG_SPACE_RT;
+  if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq * (is_rt ? 2 : 1), GG_ERR_INVALID,
+                     "f must be given at the n_cells * Q quadrature points (two contravariant components for Raviart-Thomas)");
   *out = 0.0;
   if (nc == 0) return GG_OK;
   auto T = get_tab(ctx, s->kind, s->order, nq);
   DevBuf<double> sums(nc), total(1);
+  if (is_rt)
+    k_norm_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, 1, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius, T->xi.p,
+                                                T->w.p, T->val.p, s->d_cell_dofs.p, s->d_cell_signs.p, u->d.p, fq ? fq->d.p : nullptr,
+                                                m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
+  else
   k_l2_error_cells<0><<<nblk(nc, 128), 128, 0, st>>>(nc, nq, s->ndofs_loc, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->radius, T->xi.p,
                                                   T->w.p, T->val.p, s->d_cell_dofs.p, u->d.p, dirichlet, fq ? fq->d.p : nullptr,
                                                   m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);

@@ -596,14 +596,22 @@ void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_spac
     }
   } else if (kind == GG_SPACE_DG) {
     GG_REQUIRE(order >= 0 && order <= 4, GG_ERR_UNSUPPORTED, "DG order must be in 0..4");
-    GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on DG spaces are not implemented");
     int mloc = (order + 1) * (order + 1);
     s->ndofs_loc = mloc;
     s->n_free = nc * mloc;
     GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
     s->cell_dofs.resize(nc * mloc);
     std::iota(s->cell_dofs.begin(), s->cell_dofs.end(), 0);
-    s->blocks.push_back({0, nc, mloc});
+    if (constraint == GG_CONSTRAINT_ZEROMEAN && nc > 0) {
+      // the last DOF is fixed (test/Laplacian/HodgeLaplacian_scalar.jl:44: pressure space with constraint=:zeromean)
+      s->cell_dofs.back() = -1;
+      s->n_free -= 1; s->n_dirichlet = 1;
+      if (nc > 1) s->blocks.push_back({0, nc - 1, mloc});
+      if (mloc > 1) s->blocks.push_back({(nc - 1) * mloc, 1, mloc - 1});
+    } else {
+      GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_INVALID, "unknown constraint");
+      s->blocks.push_back({0, nc, mloc});
+    }
   } else if (kind == GG_SPACE_RT) {
     GG_REQUIRE(order >= 0 && order <= 3, GG_ERR_UNSUPPORTED, "RT order must be in 0..3");
     GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on RT spaces are not implemented");

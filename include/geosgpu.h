@@ -284,7 +284,9 @@ int gg_surface_gradient(gg_mesh* m, int32_t degree, const double* grad_f, gg_vec
  * (divs(f, Ω), src/CellData/SurfaceDiffOps.jl:228-259) */
 int gg_surface_divergence(gg_mesh* m, int32_t degree, const double* F, const double* grad_F, gg_vec* out);
 /* sum(int (u_h - f)^2 sqrtg) with f at the quadrature points (NULL = 0): the error measure of
- * test/Laplacian/LaplaceBeltrami.jl:82-83; `dirichlet` is the value of the constrained DOF of a zeromean space */
+ * test/Laplacian/LaplaceBeltrami.jl:82-83; `dirichlet` is the value of the constrained DOF of a zeromean space.
+ * Raviart-Thomas spaces: f holds the two CONTRAVARIANT components of the exact field per point and the measure is
+ * sum(int (u_h/sqrtg - f).g.(u_h/sqrtg - f) sqrtg), the velocity error of test/Laplacian/HodgeLaplacian_scalar.jl:104-105 */
 int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out);
 /* (int u_h d xi) / (int d xi) in the CHART measure: the shift Gridap's ZeroMeanFESpace subtracts after a solve
  * (FEFunction(::ZeroMeanFESpace, ...): c = -(vol_i . x) / vol), used by test/Laplacian/LaplaceBeltrami.jl:71 */

@@ -100,3 +100,62 @@ def test_surface_gradient_and_divergence_match_oracle(gg):
     sd = gg.surface_divergence(dΩ, _ambient_vecX, _grad_ambient_vecX).get().reshape(model.num_cells, -1)
     ref = forms.surface_divergence(_ambient_vecX, _grad_ambient_vecX, mesh, q.x, mesh.cell_to_chart)
     assert np.abs(sd - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_helmholtz_driver_convergence(gg):
+    """test/Laplacian/Helmholtz.jl:19-86 with the blocks assembled on the device; the indefinite system goes to the caller's LU
+    (LUSolver() in the reference), the manufactured right-hand side and the error norm stay on the device."""
+    import scipy.sparse.linalg as spla
+    from test_oracle_forms import solve_helmholtz
+    from oracle.mesh import CubedSphereMesh2D
+    errs = []
+    for lvl in (1, 2, 3, 4):
+        model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=2**lvl)
+        Ω = gg.Triangulation(model)
+        dΩ, dΩe = gg.Measure(Ω, 18), gg.Measure(Ω, 31)
+        V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 2), conformity="H1")
+        A = gg.assemble_matrix(gg.Helmholtz(dΩ), V, V).to_scipy()
+        _, xyz = dΩ.quadrature_points(chart=False)
+        rhs = fX(xyz).reshape(-1) + gg.surface_laplacian(dΩ, grad_fX, hess_fX).get()
+        b = gg.assemble_vector(gg.Source(dΩ, rhs), V).get()
+        x = spla.spsolve(A.tocsc(), b)
+        _, xe = dΩe.quadrature_points(chart=False)
+        errs.append(gg.l2_error(x, V, dΩe, fq=fX(xe)))
+        if lvl == 2:
+            e_ref = solve_helmholtz(CubedSphereMesh2D(4), 2)
+            assert abs(errs[-1] - e_ref) <= 1e-6 * e_ref
+    slope = np.polyfit(np.log10([1 / 2.0**lvl for lvl in (1, 2, 3, 4)]), np.log10(errs), 1)[0]
+    assert slope >= 2
+
+
+def test_hodge_laplacian_scalar_driver_convergence(gg):
+    """test/Laplacian/HodgeLaplacian_scalar.jl:23-121: mixed RT_2 x DG_2 system from device-assembled blocks (RT mass, div,
+    manufactured source), caller's LU, device error norms for the pressure and for the contravariant velocity."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from test_oracle_forms import grad_sinlat, hess_sinlat, sinlat, solve_hodge_scalar
+    from oracle.mesh import CubedSphereMesh2D
+    p, degree = 2, 12
+    eu, ep = [], []
+    for lvl in (1, 2, 3):
+        model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=2**lvl)
+        Ω = gg.Triangulation(model)
+        dΩ, dΩe = gg.Measure(Ω, degree), gg.Measure(Ω, 2 * degree)
+        V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+        Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2", constraint="zeromean")
+        M = gg.assemble_matrix(gg.RTMass(dΩ), V, V).to_scipy()
+        B = gg.assemble_matrix(gg.Div(dΩ), V, Q).to_scipy()                  # rows: test Q, columns: trial V
+        bq = gg.assemble_vector(gg.Source(dΩ, gg.surface_laplacian(dΩ, grad_sinlat, hess_sinlat), scale=-1.0), Q).get()
+        A = sp.bmat([[M, -B.T], [B, None]]).tocsc()
+        x = spla.spsolve(A, np.concatenate([np.zeros(V.num_free_dofs), bq]))
+        u, ph = x[: V.num_free_dofs], x[V.num_free_dofs:]
+        mean = gg.chart_mean(ph, Q)
+        _, xe = dΩe.quadrature_points(chart=False)
+        ep.append(gg.l2_error(ph, Q, dΩe, fq=sinlat(xe) + mean))
+        minus_sigma = -gg.surface_gradient(dΩe, grad_sinlat).get()
+        eu.append(gg.l2_error(u, V, dΩe, fq=minus_sigma))
+        if lvl == 2:
+            eu_ref, ep_ref = solve_hodge_scalar(CubedSphereMesh2D(4), p)
+            assert abs(eu[-1] - eu_ref) <= 1e-8 * eu_ref and abs(ep[-1] - ep_ref) <= 1e-8 * ep_ref
+    lv = np.log10([1 / 2.0**lvl for lvl in (1, 2, 3)])
+    assert np.polyfit(lv, np.log10(eu), 1)[0] >= 2 and np.polyfit(lv, np.log10(ep), 1)[0] >= 2

@@ -202,3 +202,78 @@ def test_surface_gradient_and_divergence_equal_their_ambient_forms():
     lap = forms.surface_laplacian(fX, grad_fX, hess_fX, mesh, q.x, mesh.cell_to_chart)
     sd2 = forms.surface_divergence(grad_fX, hess_fX, mesh, q.x, mesh.cell_to_chart)
     assert np.abs(sd2 - lap).max() < 1e-12
+
+
+def solve_helmholtz(mesh, p):
+    """helmholtz_solver of test/Laplacian/Helmholtz.jl:19-86: (M - K) u = int (f + Delta_s f) v sqrtg, LU solve."""
+    degree = 6 * (p + 1)
+    V = CGSpace(mesh, p)
+    q = forms.CellQuadrature(mesh, degree)
+    Ke = forms.scalar_mass_element_matrices(V, V, q) - forms.lb_element_matrices(V, q)
+    A = forms.assemble_matrix(V, V, Ke)
+    rhs = fX(q.ambient()) + forms.surface_laplacian(fX, grad_fX, hess_fX, mesh, q.x, mesh.cell_to_chart)
+    b = forms.assemble_vector(V, forms.source_element_vectors(V, q, rhs))
+    x = spla.spsolve(A.tocsc(), b)
+    qe = forms.CellQuadrature(mesh, 2 * degree)
+    return np.sqrt(((fX(qe.ambient()) - forms.eval_scalar(V, qe, x)) ** 2 * qe.dV * qe.sqrtg).sum())
+
+
+def test_helmholtz_convergence_p2():
+    # test/Laplacian/seq/HelmholtzTests.jl + src/ConvergenceTools/Tools.jl:4-35
+    errs = [solve_helmholtz(CubedSphereMesh2D(2**lvl), 2) for lvl in (1, 2, 3, 4)]
+    slope = np.polyfit(np.log10([1 / 2.0**lvl for lvl in (1, 2, 3, 4)]), np.log10(errs), 1)[0]
+    assert slope >= 2
+
+
+def sinlat(X):                # test/Laplacian/HodgeLaplacian_scalar.jl:18-21: sin of the latitude
+    return X[..., 2] / np.linalg.norm(X, axis=-1)
+
+
+def grad_sinlat(X):
+    r = np.linalg.norm(X, axis=-1)[..., None]
+    ez = np.zeros_like(X)
+    ez[..., 2] = 1.0
+    return ez / r - X[..., 2:3] * X / r**3
+
+
+def hess_sinlat(X):
+    r = np.linalg.norm(X, axis=-1)[..., None, None]
+    z = X[..., 2][..., None, None]
+    ez = np.zeros_like(X)
+    ez[..., 2] = 1.0
+    XX = X[..., :, None] * X[..., None, :]
+    eX = ez[..., :, None] * X[..., None, :]
+    return -(eX + np.swapaxes(eX, -1, -2)) / r**3 - z * np.eye(3) / r**3 + 3 * z * XX / r**5
+
+
+def solve_hodge_scalar(mesh, p):
+    """hodge_laplacian_scalar of test/Laplacian/HodgeLaplacian_scalar.jl:23-121: u + grad_s(phi) = 0, div_s u = -Delta_s f in
+    mixed form on RT_p x DG_p (zero-mean pressure), LU solve; returns (velocity error, pressure error)."""
+    import scipy.sparse as sp
+    degree = 4 * (p + 1) if p > 0 else 10
+    V, Q = RTSpace(mesh, p), DGSpace(mesh, p)
+    q = forms.CellQuadrature(mesh, degree)
+    M = forms.assemble_matrix(V, V, forms.rt_mass_element_matrices(V, q))
+    B = forms.assemble_matrix(Q, V, forms.div_element_matrices(Q, V, q))
+    lap = forms.surface_laplacian(sinlat, grad_sinlat, hess_sinlat, mesh, q.x, mesh.cell_to_chart)
+    bq = forms.assemble_vector(Q, forms.source_element_vectors(Q, q, -lap))
+    nq = Q.num_free - 1                                              # zeromean: the last DOF is fixed to zero
+    A = sp.bmat([[M, -B.T[:, :nq]], [B[:nq], None]]).tocsc()
+    x = spla.spsolve(A, np.concatenate([np.zeros(V.num_free), bq[:nq]]))
+    u, ph = x[: V.num_free], np.append(x[V.num_free:], 0.0)
+    vol_i = forms.assemble_vector(Q, np.einsum("cq,qa->ca", q.dV, Q.ref.tabulate(q.pts)[0]))
+    ph = ph - (vol_i @ ph) / vol_i.sum()
+    qe = forms.CellQuadrature(mesh, 2 * degree)
+    e_p = np.sqrt(((sinlat(qe.ambient()) - forms.eval_scalar(Q, qe, ph)) ** 2 * qe.dV * qe.sqrtg).sum())
+    sigma = forms.surface_gradient(grad_sinlat, mesh, qe.x, mesh.cell_to_chart)
+    e = forms.eval_rt(V, qe, u)[0] / qe.sqrtg[..., None] + sigma
+    e_u = np.sqrt((np.einsum("cqi,cqij,cqj->cq", e, qe.g, e) * qe.dV * qe.sqrtg).sum())
+    return e_u, e_p
+
+
+def test_hodge_laplacian_scalar_convergence_p2():
+    # test/Laplacian/seq/HodgeLaplacianScalarTests.jl (nref 1..4, p = 2): slope of the velocity error >= p
+    errs = [solve_hodge_scalar(CubedSphereMesh2D(2**lvl), 2) for lvl in (1, 2, 3)]
+    lv = np.log10([1 / 2.0**lvl for lvl in (1, 2, 3)])
+    assert np.polyfit(lv, np.log10([e[0] for e in errs]), 1)[0] >= 2
+    assert np.polyfit(lv, np.log10([e[1] for e in errs]), 1)[0] >= 2
