@@ -546,17 +546,23 @@ static void load_hex_tables(gg_ctx* ctx, int order) {
 }
 
 // per-column surface matrices (re-integrated on every call) and per-layer radial matrices (cached) of a shell mesh
-static HexWork hex_prepare(gg_mesh* m, int order, int nq) {
+// The form cM * int phi_I phi_J sqrtg + cK * int grad(phi_I).(ginv grad(phi_J)) sqrtg keeps the Kronecker structure: with
+// sqrtg = t s^2 sqrtg_surf the mass term is t NSg (x) M2, NSg = int N_i0 N_j0 s^2 h_gamma, so the kernels run unchanged on the
+// per-layer tables Dg' = cK Dg + cM t^2 NSg (coefficient of M2 after the division by t) and Ng' = cK Ng.
+static int hex_form_code(double cM, double cK) { return cM == 0.0 ? 0 : (cK == 0.0 ? 2 : 1); }
+
+static HexWork hex_prepare(gg_mesh* m, int order, int nq, double cM = 0.0, double cK = 1.0) {
   gg_ctx* ctx = m->ctx;
   gg_mesh* ms = m->surface.get();
   GG_REQUIRE(order == 1 || order == 2, GG_ERR_UNSUPPORTED, "the 3-D shell path implements hexahedral Q1 / Q2");
   GG_REQUIRE(fast_lb_available(order, nq), GG_ERR_UNSUPPORTED, "no surface kernel for this (order, quadrature degree) on the shell");
   const int nb = order + 1, m2 = nb * nb, G = nb * nb;
   const int64_t ncol = ms->n_cells;
-  const int key = order * 64 + nq;
+  const int key = (hex_form_code(cM, cK) * 8 + order) * 64 + nq;
   auto it = m->gamma_tabs.find(key);
   if (it == m->gamma_tabs.end()) {
     std::vector<double> xi(nq), w(nq), N(nb), D(nb), Dg((size_t)m->n_layers * G, 0.0), Ng((size_t)m->n_layers * G, 0.0);
+    const double t2 = m->thickness * m->thickness;
     gauss_legendre_01(nq, xi.data(), w.data());
     const double hg = 1.0 / m->n_layers;
     for (int l = 0; l < m->n_layers; ++l)
@@ -565,8 +571,8 @@ static HexWork hex_prepare(gg_mesh* m, int order, int nq) {
         const double s = 1.0 + m->thickness * (l + xi[q]) * hg / m->radius;
         for (int i = 0; i < nb; ++i)
           for (int j = 0; j < nb; ++j) {
-            Dg[(size_t)l * G + i * nb + j] += w[q] * D[i] * D[j] * s * s / hg;
-            Ng[(size_t)l * G + i * nb + j] += w[q] * N[i] * N[j] * hg;
+            Dg[(size_t)l * G + i * nb + j] += cK * w[q] * D[i] * D[j] * s * s / hg + cM * t2 * w[q] * N[i] * N[j] * s * s * hg;
+            Ng[(size_t)l * G + i * nb + j] += cK * w[q] * N[i] * N[j] * hg;
           }
       }
     auto T = std::make_shared<gg_mesh::GammaTab>();
@@ -613,7 +619,7 @@ static bool hex_tensor_applicable(gg_csr* A) {
          A->test->constraint == GG_CONSTRAINT_NONE && (int64_t)(A->test->order * m->n_layers + 1) * (A->test->order * m->n_layers + 1) <= 65535;
 }
 
-static HexWork hex_tensor_fill(gg_csr* A, int order, int nq, double scale, int add) {
+static HexWork hex_tensor_fill(gg_csr* A, int order, int nq, double scale, int add, double cM = 0.0, double cK = 1.0) {
   gg_space* V = A->test;
   gg_mesh* m = V->mesh;
   gg_ctx* ctx = m->ctx;
@@ -655,11 +661,11 @@ static HexWork hex_tensor_fill(gg_csr* A, int order, int nq, double scale, int a
   }
   HexTensor& T = *A->tensor;
   // surface matrices: cell-wise quadrature on the columns + atomic-free CSR fill, every call
-  HexWork W = hex_prepare(m, order, nq);
+  HexWork W = hex_prepare(m, order, nq, cM, cK);
   gather_matrix(T.AK, 1, W.K2, 1.0, 0);
   gather_matrix(T.AM, 0, W.M2, 1.0, 0);
-  // assembled radial matrices (constant per mesh and rule)
-  const int key = order * 64 + nq;
+  // assembled radial matrices (constant per mesh, rule and form)
+  const int key = (hex_form_code(cM, cK) * 8 + order) * 64 + nq;
   auto it = T.radial.find(key);
   if (it == T.radial.end()) {
     std::vector<double> Dg((size_t)m->n_layers * G), Ng((size_t)m->n_layers * G), DG((size_t)NR * NR, 0.0), NG((size_t)NR * NR, 0.0);
@@ -692,9 +698,9 @@ static HexWork hex_tensor_fill(gg_csr* A, int order, int nq, double scale, int a
 }
 
 static void run_hex_lb(gg_mesh* m, int order, int nq, const int32_t* dofs, const double* u, double dir, double* ebuf, double* vbuf,
-                       const HexWork* prepared = nullptr) {
+                       const HexWork* prepared = nullptr, double cM = 0.0, double cK = 1.0) {
   gg_ctx* ctx = m->ctx;
-  HexWork W = prepared ? *prepared : hex_prepare(m, order, nq);
+  HexWork W = prepared ? *prepared : hex_prepare(m, order, nq, cM, cK);
   const int64_t nc = m->n_cells;
   unsigned nbk = nblk(nc, 128);
   if (ebuf) {
@@ -722,9 +728,12 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
   if (vbuf_out) *vbuf_out = nullptr;
   if (nc == 0) return 0;
   if (P.mesh->dim == 3) {
-    GG_REQUIRE(form == GG_FORM_LAPLACE_BELTRAMI && !a->qdata, GG_ERR_UNSUPPORTED, "on the 3-D shell only the Laplace-Beltrami form is implemented");
+    GG_REQUIRE((form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_HELMHOLTZ || form == GG_FORM_MASS_SCALAR) && !a->qdata,
+               GG_ERR_UNSUPPORTED, "on the 3-D shell the Laplace-Beltrami, Helmholtz and scalar mass forms (without coefficient) are implemented");
     GG_REQUIRE(P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG && P.test->order == P.trial->order, GG_ERR_INVALID,
-               "the shell Laplace-Beltrami form needs CG test/trial spaces of the same order");
+               "the shell forms need CG test/trial spaces of the same order");
+    double cM3, cK3; bool ext3;
+    form_coefficients(form, &cM3, &cK3, &ext3);
     double* vb = nullptr;
     if (want_fused_vector) {
       GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "fused residual needs args->u of the trial size");
@@ -733,13 +742,13 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     }
     if (pipe && hex_tensor_applicable(pipe->A)) {
       // assembled matrix straight from the tensor structure (no element matrices); the residual stays cell-wise
-      HexWork W = hex_tensor_fill(pipe->A, P.test->order, P.nq, pipe->scale, pipe->add);
+      HexWork W = hex_tensor_fill(pipe->A, P.test->order, P.nq, pipe->scale, pipe->add, cM3, cK3);
       if (vb) run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb, &W);
       return -1;
     }
     size_t np = (size_t)P.mt * (P.mt + 1) / 2;
     double* eb = scratch(ctx->ebuf, np * nc);
-    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb);
+    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, eb, vb, nullptr, cM3, cK3);
     return 1;
   }
   const bool stiffness = form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_LAPLACE_BELTRAMI_EXTRINSIC;
@@ -821,10 +830,13 @@ static double* compute_element_vectors(gg_form form, const gg_form_args* a, cons
   double* vb = scratch(ctx->vbuf, (size_t)P.mt * std::max<int64_t>(nc, 1));
   if (nc == 0) return vb;
   if (P.mesh->dim == 3) {
-    GG_REQUIRE(form == GG_FORM_LAPLACE_BELTRAMI && P.trial && P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG &&
-                   P.test->order == P.trial->order, GG_ERR_UNSUPPORTED, "on the 3-D shell only the Laplace-Beltrami action is implemented");
+    GG_REQUIRE((form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_HELMHOLTZ || form == GG_FORM_MASS_SCALAR) && !a->qdata && P.trial &&
+                   P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG && P.test->order == P.trial->order, GG_ERR_UNSUPPORTED,
+               "on the 3-D shell the actions of the Laplace-Beltrami, Helmholtz and scalar mass forms are implemented");
     GG_REQUIRE(a->u && gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u missing or of the wrong length");
-    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb);
+    double cM3, cK3; bool ext3;
+    form_coefficients(form, &cM3, &cK3, &ext3);
+    run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb, nullptr, cM3, cK3);
     return vb;
   }
   if (form == GG_FORM_SOURCE) {

@@ -141,6 +141,17 @@ def lb_element_matrices(space, quad):
     return out
 
 
+def mass_element_matrices(space, quad):
+    """Me[c, I, J] = sum_q dV phi_I phi_J sqrtg (the u*v*meas_cf term of test/Laplacian/Helmholtz.jl:43 with the shell measure)."""
+    val, _ = space.ref.tabulate(quad.pts)                         # (Q, m)
+    return np.einsum("cq,qa,qb->cab", quad.dV * quad.sqrtg, val, val)
+
+
+def helmholtz_element_matrices(space, quad):
+    """int u v sqrtg - int grad(v).(ginv grad(u)) sqrtg -- test/Laplacian/Helmholtz.jl:43."""
+    return mass_element_matrices(space, quad) - lb_element_matrices(space, quad)
+
+
 def shell_volume(mesh, degree):
     q = ShellQuadrature(mesh, degree)
     return float((q.dV * q.sqrtg).sum())

@@ -80,7 +80,7 @@ def test_unsupported_requests_on_the_shell_fail_loudly(gg):
     V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="H1")
     dΩ = gg.Measure(gg.Triangulation(model), 4)
     with pytest.raises(gg.GGError):
-        gg.assemble_matrix(gg.Helmholtz(dΩ), V, V)
+        gg.assemble_matrix(gg.ScalarMass(dΩ, qdata=np.ones(model.num_cells * dΩ.num_points)), V, V)
     with pytest.raises(gg.GGError):
         gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, 0), conformity="HDiv")
 
@@ -111,3 +111,28 @@ def test_shell_slices_assemble_the_owned_rows(gg):
     Ao.sort_indices()
     assert (A.indptr == Ao.indptr).all() and (A.indices == Ao.indices).all()
     assert np.abs(A.data - Ao.data).max() < 1e-13 * np.abs(Ao.data).max()
+
+
+@pytest.mark.parametrize("form", ["helmholtz", "mass"])
+@pytest.mark.parametrize("n,L,p,degree", [(2, 2, 2, 8), (2, 3, 1, 6)])
+def test_shell_helmholtz_and_mass_match_oracle(gg, form, n, L, p, degree):
+    """test/Laplacian/Helmholtz.jl:43 on the shell: the mass term keeps the Kronecker structure (sqrtg = t s^2 sqrtg_surf)."""
+    model, mesh = _models(gg, n, L, 1.3, 0.25)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+    dΩ = gg.Measure(gg.Triangulation(model), degree)
+    Vo = shell.HexCGSpace(mesh, p)
+    q = shell.ShellQuadrature(mesh, degree)
+    Ko = shell.helmholtz_element_matrices(Vo, q) if form == "helmholtz" else shell.mass_element_matrices(Vo, q)
+    F = gg.Helmholtz if form == "helmholtz" else gg.ScalarMass
+    Ke = gg.element_matrices(F(dΩ), V, V)
+    assert np.abs(Ke - Ko).max() <= 1e-12 * np.abs(Ko).max()
+    # assembled (tensor-structured fill) and action
+    import scipy.sparse as sp
+    rows = np.repeat(Vo.cell_dofs, Vo.ndofs_loc, axis=1).reshape(-1)
+    cols = np.tile(Vo.cell_dofs, (1, Vo.ndofs_loc)).reshape(-1)
+    Ao = sp.coo_matrix((Ko.reshape(-1), (rows, cols)), shape=(Vo.num_free,) * 2).tocsr()
+    A = gg.assemble_matrix(F(dΩ), V, V).to_scipy()
+    assert np.abs((A - Ao).data).max() <= 1e-12 * np.abs(Ao.data).max()
+    u = np.random.default_rng(3).standard_normal(V.num_free_dofs)
+    r = gg.assemble_vector(F(dΩ, u=u), V).get()
+    assert np.abs(r - Ao @ u).max() <= 1e-12 * np.abs(Ao @ u).max()

@@ -32,3 +32,14 @@ def test_laplace_beltrami_matrix_properties():
     assert np.abs(A @ np.ones(V.num_free)).max() < 1e-12 * np.abs(A.data).max()
     w = np.linalg.eigvalsh(A.toarray())
     assert w[0] > -1e-10 * w[-1] and w[1] > 1e-6 * w[-1]             # one zero eigenvalue (constants), the rest positive
+
+
+def test_shell_mass_sums_to_the_volume_and_helmholtz_splits():
+    mesh = shell.CubedSphereShellMesh3D(2, 1.3, 0.25, n_layers=2)
+    V = shell.HexCGSpace(mesh, 1)
+    q = shell.ShellQuadrature(mesh, 8)
+    M = shell.mass_element_matrices(V, q)
+    vol = 4.0 / 3.0 * np.pi * ((1.3 + 0.25) ** 3 - 1.3**3)
+    assert abs(M.sum() - vol) < 1e-6 * vol
+    H = shell.helmholtz_element_matrices(V, q)
+    assert np.abs(H.sum(axis=(1, 2)) - M.sum(axis=(1, 2))).max() < 1e-12     # the stiffness part annihilates constants
