@@ -135,11 +135,52 @@ void rk_accumulate_stats(gg_rk* rk, const double* solver_stats) {
   rk->ctx->launches++;
 }
 
-void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x) {
+// x = polynomial extrapolation of the last L solutions of this solve to the current step (the same-stage solutions of
+// consecutive steps are equally spaced in time): sum_j (-1)^(j+1) C(L, j) h_j, i.e. h1, 2 h1 - h2, 3 h1 - 3 h2 + h3, ...
+struct HistPtrs {
+  const double* h[GG_HIST_LEVELS];
+  double c[GG_HIST_LEVELS];
+};
+
+__global__ void k_extrapolate(int64_t n, int levels, HistPtrs H, double* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = 0.0;
+  for (int j = levels - 1; j >= 0; --j) v = fma(H.c[j], H.h[j][i], v);
+  x[i] = v;
+}
+
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot) {
   EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
   if (e) {
+    gg_rk_hist* H = nullptr;
+    const int64_t n = which == 0 ? rk->nu : rk->nr;
+    cudaStream_t st = rk->ctx->stream;
+    if (slot >= 0 && rk->warm_start && rk->extrap_order > 0 && n > 0) {
+      H = &rk->hist[slot];
+      const int levels = std::min(H->count, rk->extrap_order);
+      if (levels >= 1) {
+        HistPtrs P;
+        double binom = 1.0;
+        for (int j = 0; j < levels; ++j) {
+          binom = binom * (levels - j) / (j + 1);                                   // C(levels, j + 1)
+          P.h[j] = H->h[(H->head + GG_HIST_LEVELS - j) % GG_HIST_LEVELS].p;
+          P.c[j] = (j % 2 == 0 ? 1.0 : -1.0) * binom;
+        }
+        k_extrapolate<<<nblk(n, 256), 256, 0, st>>>(n, levels, P, x);
+        rk->ctx->launches++;
+      }
+    }
     ebe_solve_async(e, b, scale, x, rk->warm_start);
     rk_accumulate_stats(rk, e->stats.p);
+    if (H) {
+      // newest slot moves forward; the oldest level is overwritten
+      H->head = (H->head + 1) % GG_HIST_LEVELS;
+      auto& dst = H->h[H->head];
+      if ((int64_t)dst.n != n) dst.alloc(n);
+      GG_CUDA(cudaMemcpyAsync(dst.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if (H->count < GG_HIST_LEVELS) H->count++;
+    }
   } else {
     gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
     solver_solve_async(s, b, scale, x);
@@ -223,7 +264,7 @@ static void rk_step_async(gg_rk* rk) {
     }
     rk_residual_async(rk, xs, rk->r.p);
     // slope: M k = -r
-    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p);
+    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p, i);
     if (rk->np) {
       k_apply_dg_inverse<<<nblk(rk->np, 128), 128, 0, st>>>(rk->mesh->n_cells, rk->mq, rk->MpInv.p, rk->r.p + rk->nu, rk->k[i].p + rk->nu);
       ctx->launches++;
@@ -301,6 +342,7 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   // or the previous diagnostics) unless GG_WARM_START=0
   const char* ws = getenv("GG_WARM_START");
   rk->warm_start = !(ws && ws[0] == '0');
+  if (const char* ex = getenv("GG_EXTRAPOLATE")) rk->extrap_order = std::max(0, std::min(GG_HIST_LEVELS, atoi(ex)));
   gg_form_args fa;
   std::memset(&fa, 0, sizeof(fa));
   fa.test = rk->V; fa.trial = rk->V; fa.degree = a->degree;
@@ -382,6 +424,7 @@ int gg_rk_set_state(gg_rk* rk, const double* x) {
   int64_t n = rk->nu + rk->np;
   if (n) GG_CUDA(cudaMemcpyAsync(rk->x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
   rk->y_valid = false;
+  for (auto& h : rk->hist) h.second.count = 0;   // a new state: the solution histories no longer extrapolate to it
   GG_CUDA(cudaStreamSynchronize(rk->ctx->stream));
   GG_API_END
 }

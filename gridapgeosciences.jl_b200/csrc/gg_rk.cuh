@@ -3,6 +3,13 @@
 #include "gg_common.cuh"
 #include "gg_ebe.cuh"
 
+// solutions of the same solve (same stage, same unknown) in the previous steps: extrapolated initial guesses
+constexpr int GG_HIST_LEVELS = 6;
+struct gg_rk_hist {
+  gg::DevBuf<double> h[GG_HIST_LEVELS];
+  int head = 0, count = 0;   // h[head] is the newest
+};
+
 struct gg_rk {
   gg_ctx* ctx = nullptr;
   gg_mesh* mesh = nullptr;
@@ -17,6 +24,9 @@ struct gg_rk {
   double dt = 0.0;
   int64_t nu = 0, np = 0;
   bool warm_start = true;               // mass solves start from the previous content of their output vector
+  int extrap_order = 4;                 // ... or from a polynomial extrapolation of the last 1..6 solutions of the same solve
+  std::map<int, gg_rk_hist> hist;       // (GG_EXTRAPOLATE=0..6: history levels; 0 = plain warm start)
+  int diag_slot = -1;                   // history slot of the diagnostic solves in flight (-1: none)
   gg::DevBuf<double> x, xi, r, MpInv, Bhat;
   std::vector<gg::DevBuf<double>> k;
   gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
@@ -52,7 +62,8 @@ std::vector<double> build_bhat(int order, int degree);
 void build_dg_mass_inverse(gg_rk* rk);
 void rk_accumulate_stats(gg_rk* rk, const double* solver_stats);
 // k = A^-1 (scale b) with the RT mass (which = 0) or the potential-vorticity mass (which = 1), whichever solver is active
-void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x);
+// slot >= 0 names the solve across steps (stage / unknown) for the extrapolated initial guess
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot = -1);
 void rk_combine(gg_rk* rk, int ns, const double* coef, double* out);  // out = x + sum_j coef[j] k_j
 // shallow water (gg_swe.cu)
 void swe_create(gg_rk* rk, const gg_rk_args* a);

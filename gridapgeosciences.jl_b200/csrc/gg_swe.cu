@@ -393,11 +393,11 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
       solver_update(rk->solver_q);
     }
     gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
-    rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq);
+    rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq, rk->diag_slot >= 0 ? 100 + rk->diag_slot : -1);
   }
   // mass flux
   gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
-  rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF);
+  rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF, rk->diag_slot >= 0 ? 200 + rk->diag_slot : -1);
   rk->diag_solves++;
 }
 
@@ -462,17 +462,24 @@ void swe_step_async(gg_rk* rk) {
       xs = rk->xi.p;
     }
     // :91-93 stage diagnostics (y still holds diagnostics(x) when the stage state is x itself)
-    if (!(same_state && rk->y_valid)) { swe_diagnostics_async(rk, xs, rk->y.p); rk->y_valid = false; }
+    if (!(same_state && rk->y_valid)) {
+      rk->diag_slot = i;
+      swe_diagnostics_async(rk, xs, rk->y.p);
+      rk->diag_slot = -1;
+      rk->y_valid = false;
+    }
     // :100-117 slope: M k = -(res_x + mass(0))
     const double* q0 = rk->q0_mode == GG_Q0_START_OF_STEP ? rk->q0.p : rk->y.p;
     swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu);
-    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p);
+    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p, i);
   }
   // :121-122 update, :125-127 final diagnostics
   double co[4] = {0, 0, 0, 0};
   for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
   rk_combine(rk, std::min(s, 4), co, rk->x.p);
+  rk->diag_slot = s;
   swe_diagnostics_async(rk, rk->x.p, rk->y.p);
+  rk->diag_slot = -1;
   rk->y_valid = true;
   GG_CUDA(cudaGetLastError());
 }
