@@ -865,6 +865,15 @@ class ShallowWaterOperator:
         self.b_q = None if b is None else np.ascontiguousarray(np.broadcast_to(b(xyz), xyz.shape[:2]), dtype=np.float64)
 
 
+class ThermalShallowWaterOperator(ShallowWaterOperator):
+    """DAEFEOperator(opT, opFE, ls_diag) of test/Tutorials/ThermalShallowWater.jl:170-252: prognostic (u, p, B) in
+    RT_p x DG_p x DG_p, diagnostic (q, F, Φ, b) in CG_{p+1} x RT_p x DG_p x DG_p; Measure(Ω, 4*order) and Measure(Λ, 4*order)."""
+
+    def __init__(self, model, p_fe, f, degree=None, q0_mode="alias", tau=None):
+        degree = (4 * p_fe if p_fe > 0 else 2) if degree is None else degree
+        super().__init__(model, p_fe, f, gravity=0.0, degree=degree, q0_mode=q0_mode, tau=tau)
+
+
 class AdvectionOperator:
     """TransientSemilinearFEOperator(mass, res, (jac, jac_t), P, Q) of the DG upwind advection tutorial
     (test/Tutorials/AdvectionUpwinding.jl:107-137): Q = DG-Q_order, wind `beta(xyz)` given in ambient components."""
@@ -900,7 +909,7 @@ class RKStepper:
         a.dt = solver.dt
         a.rtol = getattr(solver.ls, "rtol", 1e-12) or 1e-12
         if isinstance(op, ShallowWaterOperator):
-            a.problem = _lib.PROBLEM_SHALLOW_WATER
+            a.problem = _lib.PROBLEM_THERMAL_SHALLOW_WATER if isinstance(op, ThermalShallowWaterOperator) else _lib.PROBLEM_SHALLOW_WATER
             a.gravity = op.gravity
             a.tau = -1.0 if op.tau is None else float(op.tau)
             a.q0_mode = {"alias": _lib.Q0_ALIAS, "start_of_step": _lib.Q0_START_OF_STEP}[op.q0_mode]

@@ -24,6 +24,7 @@ FORM_SOURCE = 7
 PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
 PROBLEM_ADVECTION = 3
+PROBLEM_THERMAL_SHALLOW_WATER = 4
 Q0_ALIAS, Q0_START_OF_STEP = 0, 1
 
 

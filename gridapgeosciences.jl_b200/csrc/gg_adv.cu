@@ -210,17 +210,14 @@ void adv_step_async(gg_rk* rk) {
   vec_consistent_async(rk->Q, rk->x.p);
 }
 
-void adv_create(gg_rk* rk, const gg_rk_args* a) {
+// Facet connectivity and DG traces shared by the skeleton terms of the DG advection and thermal shallow-water steppers:
+// every edge of the closed sphere has two cells, plus = the lower-numbered one; basis at the facet points of the 4 local edges.
+void facet_tables(gg_rk* rk, int nq) {
   gg_ctx* ctx = rk->ctx;
   gg_mesh* m = rk->mesh;
   cudaStream_t st = ctx->stream;
-  GG_REQUIRE(a->velocity_cells && a->velocity_facets, GG_ERR_INVALID,
-             "DG advection needs the ambient wind at the cell and facet quadrature points");
   const int64_t nc = m->n_cells;
-  const int nq = num_points_1d(a->degree), Q = nq * nq, M = rk->mq;
-  rk->nq1 = nq;
-  GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
-  // facet connectivity: every edge of the closed sphere has two cells, plus = the lower-numbered one
+  const int M = rk->mq;
   gg_mesh_info(m, nullptr, nullptr, nullptr);
   int64_t ne = 0;
   gg_mesh_info(m, nullptr, nullptr, &ne);   // builds the edge topology
@@ -260,6 +257,21 @@ void adv_create(gg_rk* rk, const gg_rk_args* a) {
     }
   (void)QNORM;
   rk->adv_fval.upload(fval, st);
+}
+
+void adv_create(gg_rk* rk, const gg_rk_args* a) {
+  gg_ctx* ctx = rk->ctx;
+  gg_mesh* m = rk->mesh;
+  cudaStream_t st = ctx->stream;
+  GG_REQUIRE(a->velocity_cells && a->velocity_facets, GG_ERR_INVALID,
+             "DG advection needs the ambient wind at the cell and facet quadrature points");
+  const int64_t nc = m->n_cells;
+  const int nq = num_points_1d(a->degree), Q = nq * nq, M = rk->mq;
+  rk->nq1 = nq;
+  GG_REQUIRE(nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
+  facet_tables(rk, nq);
+  std::vector<double> s(nq), wf(nq);
+  gauss_legendre_01(nq, s.data(), wf.data());
   // wind tabulations
   auto tab = get_tab(ctx, GG_SPACE_DG, rk->order, nq);
   DevBuf<double> dbc, dbf, ds, dw;

@@ -121,7 +121,7 @@ __global__ void k_accumulate_stats(const double* __restrict__ solver_stats, doub
 
 static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
   gg_ctx* ctx = rk->ctx;
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   if (n == 0) return;
   k_wave_residual<<<nblk(n, 128), 128, 0, ctx->stream>>>(rk->nu, rk->np, rk->mesh->n_cells, rk->mq, rk->mu, rk->V->d_vptr.p,
                                                         rk->V->d_vsrc.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p,
@@ -189,7 +189,7 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
 }
 
 void rk_combine(gg_rk* rk, int ns, const double* co, double* out) {
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   if (n == 0) return;
   auto kp = [&](int j) { return j < (int)rk->k.size() ? rk->k[j].p : nullptr; };
   k_combine<<<nblk(n, 256), 256, 0, rk->ctx->stream>>>(n, rk->x.p, ns, co[0], kp(0), co[1], kp(1), co[2], kp(2), co[3], kp(3), out);
@@ -250,7 +250,7 @@ static void rk_step_async(gg_rk* rk) {
   if (rk->problem == GG_PROBLEM_ADVECTION) { adv_step_async(rk); return; }
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   int s = rk->n_stages;
   auto kp = [&](int j) { return j < s ? rk->k[j].p : nullptr; };
   for (int i = 0; i < s; ++i) {
@@ -298,8 +298,9 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   gg_rk* raw = nullptr;
   GG_API_BEGIN
   GG_REQUIRE(m && a && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER || a->problem == GG_PROBLEM_ADVECTION,
-             GG_ERR_UNSUPPORTED, "unknown problem id (GG_PROBLEM_WAVE, GG_PROBLEM_SHALLOW_WATER and GG_PROBLEM_ADVECTION are implemented)");
+  GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER || a->problem == GG_PROBLEM_ADVECTION ||
+                 a->problem == GG_PROBLEM_THERMAL_SHALLOW_WATER, GG_ERR_UNSUPPORTED,
+             "unknown problem id (GG_PROBLEM_WAVE, GG_PROBLEM_SHALLOW_WATER, GG_PROBLEM_ADVECTION and GG_PROBLEM_THERMAL_SHALLOW_WATER are implemented)");
   GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
   GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "the RK steppers support RT_p x DG_p with p <= 2");
   GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
@@ -366,7 +367,9 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   // reference div matrix, same rule as Measure(Omega, degree)
   rk->Bhat.upload(build_bhat(a->order, a->degree), ctx->stream);
   build_vec_map(rk->V);
-  int64_t n = rk->nu + rk->np;
+  const bool thermal = a->problem == GG_PROBLEM_THERMAL_SHALLOW_WATER;
+  if (thermal) { rk->problem = GG_PROBLEM_SHALLOW_WATER; rk->thermal = true; rk->nB = rk->np; }
+  int64_t n = rk_nx(rk);
   rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
   rk->k.resize(s);
   for (int i = 0; i < s; ++i) {
@@ -381,8 +384,9 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   rk->iter_accum.alloc(2);
   GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
   if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
-  if (a->problem == GG_PROBLEM_SHALLOW_WATER) {
+  if (a->problem == GG_PROBLEM_SHALLOW_WATER || thermal) {
     swe_create(rk, a);
+    if (thermal) tswe_create(rk);
   } else if (mode == "mf" && mf_supported(GG_SPACE_RT, a->order, num_points_1d(a->degree))) {
     solver_set_matrix_free(rk->solver, a->degree, nullptr);
   }
@@ -403,7 +407,7 @@ int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p) {
   GG_API_BEGIN
   GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
   if (n_u) *n_u = rk->nu;
-  if (n_p) *n_p = rk->np;
+  if (n_p) *n_p = rk->np + rk->nB;   // thermal shallow water: [p; B]
   GG_API_END
 }
 
@@ -413,7 +417,7 @@ int gg_rk_diag_info(gg_rk* rk, int64_t* n_q, int64_t* n_F, int64_t* n_Phi) {
   bool swe = rk->problem == GG_PROBLEM_SHALLOW_WATER;
   if (n_q) *n_q = swe ? rk->nr : 0;
   if (n_F) *n_F = swe ? rk->nu : 0;
-  if (n_Phi) *n_Phi = swe ? rk->np : 0;
+  if (n_Phi) *n_Phi = swe ? rk->np + rk->nB : 0;   // thermal shallow water: [Phi; b]
   GG_API_END
 }
 
@@ -421,7 +425,7 @@ int gg_rk_set_state(gg_rk* rk, const double* x) {
   GG_API_BEGIN
   GG_REQUIRE(rk && x, GG_ERR_INVALID, "null argument");
   GG_CUDA(cudaSetDevice(rk->ctx->device));
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   if (n) GG_CUDA(cudaMemcpyAsync(rk->x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
   rk->y_valid = false;
   for (auto& h : rk->hist) h.second.count = 0;   // a new state: the solution histories no longer extrapolate to it
@@ -452,7 +456,7 @@ int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
   GG_API_BEGIN
   GG_REQUIRE(rk && x && r, GG_ERR_INVALID, "null argument");
   GG_CUDA(cudaSetDevice(rk->ctx->device));
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
   if (rk->problem == GG_PROBLEM_SHALLOW_WATER) {
     rk->y_valid = false;
@@ -481,7 +485,7 @@ int gg_rk_diagnostics(gg_rk* rk, const double* x, double* y) {
   GG_REQUIRE(rk && x && y, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(rk->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_INVALID, "this stepper has no diagnostic variables");
   GG_CUDA(cudaSetDevice(rk->ctx->device));
-  int64_t n = rk->nu + rk->np;
+  int64_t n = rk_nx(rk);
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, rk->ctx->stream));
   rk->y_valid = false;
   swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
@@ -495,7 +499,7 @@ int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double
   GG_REQUIRE(rk->problem == GG_PROBLEM_SHALLOW_WATER, GG_ERR_INVALID, "not a shallow-water stepper");
   GG_CUDA(cudaSetDevice(rk->ctx->device));
   cudaStream_t st = rk->ctx->stream;
-  int64_t n = rk->nu + rk->np, ny = rk->nr + rk->nu + rk->np;
+  int64_t n = rk_nx(rk), ny = rk->nr + rk_nx(rk);
   if (n) GG_CUDA(cudaMemcpyAsync(rk->xi.p, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
   rk->y_valid = false;
   if (ny) GG_CUDA(cudaMemcpyAsync(rk->y.p, y, ny * sizeof(double), cudaMemcpyHostToDevice, st));

@@ -23,6 +23,8 @@ struct gg_rk {
   std::vector<double> A, b, c;
   double dt = 0.0;
   int64_t nu = 0, np = 0;
+  int64_t nB = 0;                       // thermal shallow water: the second DG prognostic field B (= np), else 0
+  bool thermal = false;                 // shallow water with the buoyancy fields of test/Tutorials/ThermalShallowWater.jl
   bool warm_start = true;               // mass solves start from the previous content of their output vector
   int extrap_order = 4;                 // ... or from a polynomial extrapolation of the last 1..6 solutions of the same solve
   std::map<int, gg_rk_hist> hist;       // (GG_EXTRAPOLATE=0..6: history levels; 0 = plain warm start)
@@ -51,11 +53,19 @@ struct gg_rk {
   gg::DevBuf<double> adv_bq;                   // [Q][2][n_cells] w dV sqrtg times the contravariant wind / (hx, hy)
   gg::DevBuf<double> adv_bn, adv_wsg;          // [4][nqf][n_cells] beta.n and w dL sqrtg at the facet points of each side
   gg::DevBuf<double> adv_fval;                 // [4][nqf][m] basis at the facet points
+  // ---- thermal shallow water only (gg_tswe.cu) -----------------------------------------------------------
+  gg::DevBuf<double> tsw_fvn, tsw_wf;          // [4][nqf][mu] reference RT normal component at the facet points; [nqf] weights
   int64_t diag_solves = 0;
   bool y_valid = false;           // y == diagnostics(x) (lets a step reuse the final diagnostics of the previous one)
 };
 
+inline int64_t rk_nx(const gg_rk* rk) { return rk->nu + rk->np + rk->nB; }   // prognostic state [u; p; (B)]
+
 namespace gg {
+// thermal shallow water (gg_tswe.cu)
+void tswe_create(gg_rk* rk);
+void tswe_diagnostics_async(gg_rk* rk, const double* x, double* y);
+void tswe_residual_async(gg_rk* rk, const double* x, const double* y, double* rB, double* kB);
 // reference divergence matrix Bhat[I][J] = sum_q w_q psi_I(xi_q) divhat(phihat_J)(xi_q)  (mq x mu, row-major)
 std::vector<double> build_bhat(int order, int degree);
 // inverses of the DG mass blocks int psi_i psi_j sqrtg, entry-major [(i*mq+j)][cell] -> rk->MpInv
@@ -73,6 +83,7 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
 void swe_destroy(gg_rk* rk);
 // DG advection (gg_adv.cu)
 void adv_create(gg_rk* rk, const gg_rk_args* a);
+void facet_tables(gg_rk* rk, int nqf);  // adv_nbr_cell / adv_nbr_edge / adv_is_plus / adv_fval
 void adv_step_async(gg_rk* rk);
 void adv_slope_async(gg_rk* rk, const double* u, double* kout, double* rout);
 }  // namespace gg

@@ -398,6 +398,7 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   // mass flux
   gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
   rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF, rk->diag_slot >= 0 ? 200 + rk->diag_slot : -1);
+  if (rk->thermal) tswe_diagnostics_async(rk, x, y);   // Phi += 0.5 B, b
   rk->diag_solves++;
 }
 
@@ -435,6 +436,7 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
     ctx->launches++;
     GG_CUDA(cudaGetLastError());
   }
+  if (rk->thermal) tswe_residual_async(rk, x, y, r + rk->nu + rk->np, kp ? kp + rk->np : nullptr);
   gather_vector(rk->V, rk->evec_u.p, r, 1.0, 0);
 }
 
@@ -494,7 +496,7 @@ void swe_create(gg_rk* rk, const gg_rk_args* a) {
   rk->nq1 = num_points_1d(a->degree);
   GG_REQUIRE(rk->nq1 <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high");
   const int64_t Q = (int64_t)rk->nq1 * rk->nq1;
-  rk->gravity = a->gravity;
+  rk->gravity = rk->thermal ? 0.0 : a->gravity;   // thermal: the potential term is 0.5 B, added by gg_tswe.cu
   rk->tau = a->tau < 0 ? 0.5 * a->dt : a->tau;  // TransientShallowWater.jl:150
   rk->q0_mode = a->q0_mode;
   chk(gg_space_builtin(rk->mesh, GG_SPACE_CG, a->order + 1, GG_CONSTRAINT_NONE, &rk->R));
@@ -522,8 +524,8 @@ void swe_create(gg_rk* rk, const gg_rk_args* a) {
     }
   }
   rk->fq.upload(a->coriolis, (size_t)(nc * Q), st);
-  if (a->topography) rk->bq.upload(a->topography, (size_t)(nc * Q), st);
-  rk->y.alloc(rk->nr + rk->nu + rk->np);
+  if (a->topography && !rk->thermal) rk->bq.upload(a->topography, (size_t)(nc * Q), st);
+  rk->y.alloc(rk->nr + rk->nu + rk->np + rk->nB);
   rk->q0.alloc(rk->nr);
   rk->rhs_q.alloc(rk->nr); rk->rhs_F.alloc(rk->nu);
   rk->evec_q.alloc((size_t)rk->mr * nc); rk->evec_u.alloc((size_t)rk->mu * nc);

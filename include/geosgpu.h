@@ -305,6 +305,11 @@ int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out);
 /* DG upwind advection of a scalar, volume + skeleton terms (test/Tutorials/AdvectionUpwinding.jl:107-137), Q = DG-Q_order,
  * marched with the explicit tableau (BASELINE configs[2]); the state is [p] alone (n_u = 0) */
 #define GG_PROBLEM_ADVECTION 3
+/* Thermal shallow water (test/Tutorials/ThermalShallowWater.jl:170-252): state [u; p; B] with B in DG_k (gg_rk_info reports
+ * n_p = 2 x the DG size), diagnostics [q; F; Phi; b] (gg_rk_diag_info reports n_Phi = 2 x the DG size); same DAE stepper and
+ * q0 handling as GG_PROBLEM_SHALLOW_WATER, plus the buoyancy cell terms and the skeleton terms u_s1, u_s2, B_s1, B_s2
+ * (upwinding_sign threshold 1e-4).  `gravity` and `topography` are not used (B carries gravity). */
+#define GG_PROBLEM_THERMAL_SHALLOW_WATER 4
 #define GG_Q0_ALIAS 0         /* q0 aliases q, as in the reference (RungeKuttaEX.jl:69-75 pass one array twice) */
 #define GG_Q0_START_OF_STEP 1 /* q0 = potential vorticity at the beginning of the step */
 typedef struct {
