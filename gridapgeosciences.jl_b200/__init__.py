@@ -374,7 +374,13 @@ class Measure:
         return out.value
 
 
+class VectorValue:
+    """Marker for ReferenceFE(lagrangian, VectorValue, p): the vector-valued Lagrangian element (VectorValue{2,Float64})."""
+
+
 def ReferenceFE(name, T, order):
+    if T is VectorValue:
+        return (name, int(order), "vector")
     return (name, int(order))
 
 
@@ -421,9 +427,13 @@ class FESpace:
 
 def TestFESpace(model_or_trian, reffe, conformity="H1", constraint=None):
     model = model_or_trian.model if isinstance(model_or_trian, Triangulation) else model_or_trian
-    name, order = reffe
+    name, order = reffe[0], reffe[1]
     conformity = conformity.lstrip(":")
-    if name == lagrangian:
+    if name == lagrangian and len(reffe) > 2:
+        if conformity != "H1":
+            raise ValueError("vector-valued Lagrangian spaces are implemented for conformity=:H1")
+        kind = _lib.SPACE_CGV
+    elif name == lagrangian:
         kind = {"H1": _lib.SPACE_CG, "L2": _lib.SPACE_DG}[conformity]
     elif name == raviart_thomas:
         kind = _lib.SPACE_RT
@@ -581,6 +591,23 @@ class Div(Form):
     form_id = _lib.FORM_DIV
 
 
+class VectorMass(Form):
+    """a(u,v) = ∫( (u⋅(metric_cf⋅v))*meas_cf )dΩ on a vector H1 space -- test/Projection/L2_projection_Lagrangian_vector.jl:41."""
+    form_id = _lib.FORM_MASS_VECTOR
+
+
+class VectorSource(Form):
+    """l(v) = ∫( (f⋅(metric_cf⋅v))*meas_cf )dΩ, f = contravariant components (n_cells, Q, 2) at the quadrature points
+    -- test/Projection/L2_projection_Lagrangian_vector.jl:42."""
+    form_id = _lib.FORM_SOURCE_VECTOR
+    bilinear = False
+
+    def __init__(self, dΩ, fq, **kw):
+        if not isinstance(fq, DeviceVector):
+            fq = np.ascontiguousarray(fq, dtype=np.float64).reshape(-1)
+        super().__init__(dΩ, qdata=fq, **kw)
+
+
 class Source(Form):
     """l(v) = ∫( (f*v)*meas_cf )dΩ with f at the quadrature points -- test/Laplacian/LaplaceBeltrami.jl:53."""
     form_id = _lib.FORM_SOURCE
@@ -696,7 +723,7 @@ def interpolate(fun, V, out=None):
     (test/Transient/TransientShallowWater.jl:88-95)."""
     _, xyz = interpolation_points(V)
     vals = np.asarray(fun(xyz), dtype=np.float64)
-    shape = xyz.shape if V.kind == _lib.SPACE_RT else xyz.shape[:2]
+    shape = xyz.shape if V.kind in (_lib.SPACE_RT, _lib.SPACE_CGV) else xyz.shape[:2]
     vals = np.ascontiguousarray(np.broadcast_to(vals, shape))
     out = out if out is not None else DeviceVector(V.model.ctx, V.num_free_dofs)
     _lib.check(V.lib.gg_space_interpolate(V.h, _dp(vals), out.h))
@@ -742,6 +769,24 @@ def surface_divergence(dΩ, F, grad_F):
     g = np.ascontiguousarray(np.broadcast_to(grad_F(xyz), xyz.shape + (3,)), dtype=np.float64)
     out = DeviceVector(m.ctx, m.num_cells * dΩ.num_points)
     _lib.check(m.lib.gg_surface_divergence(m.h, dΩ.degree, _dp(f), _dp(g), out.h))
+    return out
+
+
+def contravariant_components(dΩ, vecX):
+    """(pinvJ∘transpose∘∇(ambient_map_cf))⋅(vecX∘ambient_map_cf) at the quadrature points: (n_cells, Q, 2) DeviceVector
+    (the contravariant surface gradient operator applied to the ambient vector itself, src/Helpers/Operators.jl:16-24)."""
+    m = dΩ.model
+    _, xyz = dΩ.quadrature_points(chart=False)
+    v = np.ascontiguousarray(np.broadcast_to(vecX(xyz), xyz.shape), dtype=np.float64)
+    out = DeviceVector(m.ctx, 2 * m.num_cells * dΩ.num_points)
+    _lib.check(m.lib.gg_surface_gradient(m.h, dΩ.degree, _dp(v), out.h))   # ginv . (J v) = pinvJ . v
+    return out
+
+
+def change_of_basis(V):
+    """(n_cells, n_nodes, 2, 2) blocks of a vector H1 space (src/FESpaces/GradConformingFESpaces.jl:60-113)."""
+    out = np.empty((V.model.num_cells, V.ndofs_loc // 2, 2, 2))
+    _lib.check(V.lib.gg_space_change_of_basis(V.h, _dp(out)))
     return out
 
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libgeosgpu.so")
 GG_OK = 0
 ERRORS = {-1: "GG_ERR_INVALID", -2: "GG_ERR_CUDA", -3: "GG_ERR_UNSUPPORTED", -4: "GG_ERR_NOMEM", -5: "GG_ERR_NOCONV"}
 
-SPACE_CG, SPACE_DG, SPACE_RT = 0, 1, 2
+SPACE_CG, SPACE_DG, SPACE_RT, SPACE_CGV = 0, 1, 2, 3
 CONSTRAINT_NONE, CONSTRAINT_ZEROMEAN = 0, 1
 FORM_LAPLACE_BELTRAMI = 1
 FORM_LAPLACE_BELTRAMI_EXTRINSIC = 2
@@ -21,6 +21,7 @@ FORM_MASS_SCALAR = 4
 FORM_MASS_RT = 5
 FORM_DIV = 6
 FORM_SOURCE = 7
+FORM_MASS_VECTOR, FORM_SOURCE_VECTOR = 8, 9
 PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
 PROBLEM_ADVECTION = 3
@@ -98,6 +99,7 @@ SIGNATURES = {
     "gg_space_info": (C.c_int, [_P, _PI64, _PI32, _PI64]),
     "gg_space_get_cell_dofs": (C.c_int, [_P, _PI32]),
     "gg_space_get_cell_signs": (C.c_int, [_P, _PI8]),
+    "gg_space_change_of_basis": (C.c_int, [_P, _PD]),
     "gg_space_destroy": (None, [_P]),
     "gg_vec_create": (C.c_int, [_P, _I64, _PP]),
     "gg_vec_set": (C.c_int, [_P, _PD]),

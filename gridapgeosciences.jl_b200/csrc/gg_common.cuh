@@ -197,6 +197,11 @@ struct gg_space {
   gg::DevBuf<int8_t> d_cell_signs;
   // local dof -> tensor multi-index (Lagrangian): lex index ix + (order+1)*iy
   std::vector<int32_t> loc2lex;
+  // vector H1 (GG_SPACE_CGV): per (cell, node) the master (cell, local node) across a panel interface (-1: none) and the
+  // 2x2 change-of-basis blocks [n_cells][n_nodes][2][2] (gg_vec.cu)
+  std::vector<int32_t> cob_master_cell;
+  std::vector<int8_t> cob_master_node;
+  gg::DevBuf<double> d_cob;
   // groups of consecutively numbered free DOFs owned by one mesh entity: (first dof, number of groups, dofs per group);
   // empty for caller-numbered spaces (the preconditioner then degenerates to point Jacobi)
   struct BlockClass { int64_t start, count; int size; };

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "gg_common.cuh"
+#include "gg_vec.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
 #include "gg_lb_fast.cuh"
@@ -804,6 +805,12 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     GG_CUDA(cudaGetLastError());
     return 0;
   }
+  if (form == GG_FORM_MASS_VECTOR) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_CGV && P.trial == P.test, GG_ERR_INVALID, "the vector mass form needs one vector H1 space as test and trial");
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    vec_mass_element_matrices(P.test, P.nq, eb);
+    return 0;
+  }
   if (form == GG_FORM_DIV) {
     GG_REQUIRE(is_scalar(P.test) && P.trial->kind == GG_SPACE_RT, GG_ERR_INVALID, "div form needs a scalar test and an RT trial space");
     auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);
@@ -837,6 +844,12 @@ static double* compute_element_vectors(gg_form form, const gg_form_args* a, cons
     double cM3, cK3; bool ext3;
     form_coefficients(form, &cM3, &cK3, &ext3);
     run_hex_lb(P.mesh, P.test->order, P.nq, P.trial->d_cell_dofs.p, a->u->d.p, a->dirichlet, nullptr, vb, nullptr, cM3, cK3);
+    return vb;
+  }
+  if (form == GG_FORM_SOURCE_VECTOR) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_CGV, GG_ERR_INVALID, "the vector source form needs a vector H1 test space");
+    GG_REQUIRE(a->qdata && gg_vec_size(a->qdata) == 2 * nc * P.nq * P.nq, GG_ERR_INVALID, "vector source form needs qdata of length n_cells*Q*2");
+    vec_source_element_vectors(P.test, P.nq, a->qdata->d.p, vb);
     return vb;
   }
   if (form == GG_FORM_SOURCE) {

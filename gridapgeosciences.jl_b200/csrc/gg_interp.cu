@@ -10,6 +10,7 @@
 #include "gg_common.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
+#include "gg_vec.cuh"
 
 namespace gg {
 
@@ -23,6 +24,7 @@ static std::vector<double> interp_ref_points(const gg_space* s, std::vector<doub
     rt_moment_functionals(s->order, pts, w);
     if (W) *W = std::move(w);
   } else {
+    // Lagrangian nodes (the vector H1 space has one point per node, both components)
     int p = s->order, nb = p + 1;
     std::vector<int32_t> l2x = quad_local_to_lex(p);
     pts.resize((size_t)nb * nb * 2);
@@ -335,6 +337,15 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
     ctx->launches += 2;
     GG_CUDA(cudaGetLastError());
     GG_CUDA(cudaStreamSynchronize(st));
+  } else if (s->kind == GG_SPACE_CGV) {
+    // ambient 3-vectors at the nodes -> contravariant components in the cell's chart -> master frame (C^-1) -> DOFs
+    DevBuf<double> dref, dv, dl((size_t)nc * ml);
+    dref.upload(ref, st); dv.upload(vals, (size_t)nc * N * 3, st);
+    if (nc) vec_interp_values(s, dref.p, dv.p, dl.p);
+    k_interp_pick_scalar<<<nblk(s->n_free, 256), 256, 0, st>>>(s->n_free, nc, ml, s->d_vptr.p, s->d_vsrc.p, dl.p, out->d.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
   } else {
     DevBuf<double> dv; dv.upload(vals, (size_t)nc * ml, st);
     k_interp_pick_scalar<<<nblk(s->n_free, 256), 256, 0, st>>>(s->n_free, nc, ml, s->d_vptr.p, s->d_vsrc.p, dv.p, out->d.p);
@@ -359,6 +370,7 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   int64_t nc = m->n_cells;
   *out = 0.0;
   if (nc == 0) return GG_OK;
+  if (s->kind == GG_SPACE_CGV) { *out = vec_error_sq(s, e->d.p, nullptr, nq); return GG_OK; }
   auto T = get_tab(ctx, s->kind, s->order, nq);
   DevBuf<double> sums(nc), total(1);
   int is_rt = s->kind == GG_SPACE_RT ? 1 : 0;
@@ -410,11 +422,12 @@ int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t
   const int nq = num_points_1d(degree);
   GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   const int64_t nc = m->n_cells;
-  const bool is_rt = s->kind == GG_SPACE_RT;
-  if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq * (is_rt ? 2 : 1), GG_ERR_INVALID,
-                     "f must be given at the n_cells * Q quadrature points (two contravariant components for Raviart-Thomas)");
+  const bool is_rt = s->kind == GG_SPACE_RT, is_vec = s->kind == GG_SPACE_CGV;
+  if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq * (is_rt || is_vec ? 2 : 1), GG_ERR_INVALID,
+                     "f must be given at the n_cells * Q quadrature points (two contravariant components for vector-valued spaces)");
   *out = 0.0;
   if (nc == 0) return GG_OK;
+  if (is_vec) { *out = vec_error_sq(s, u->d.p, fq ? fq->d.p : nullptr, nq); return GG_OK; }
   auto T = get_tab(ctx, s->kind, s->order, nq);
   DevBuf<double> sums(nc), total(1);
   if (is_rt)

@@ -14,6 +14,7 @@
 #include <numeric>
 #include <unordered_map>
 #include "gg_common.cuh"
+#include "gg_vec.cuh"
 #include "gg_refel.cuh"
 
 namespace gg {
@@ -527,6 +528,7 @@ static void finish_space(gg_space* s) {
   s->d_cell_dofs.upload(s->cell_dofs, st);
   if (!s->cell_signs.empty()) s->d_cell_signs.upload(s->cell_signs, st);
   GG_CUDA(cudaStreamSynchronize(st));
+  gg::vec_space_finish(s);
 }
 
 }  // extern "C"
@@ -593,6 +595,63 @@ void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_spac
     if (order > 1) {
       s->blocks.push_back({m->n_nodes, m->n_edges, order - 1});
       s->blocks.push_back({m->n_nodes + m->n_edges * (order - 1), nc, (order - 1) * (order - 1)});
+    }
+  } else if (kind == GG_SPACE_CGV) {
+    // vector-valued H1 Lagrangian (ReferenceFE(lagrangian, VectorValue{2,Float64}, p), conformity=:H1) with the panel-interface
+    // change of basis of src/FESpaces/GradConformingFESpaces.jl:1-113.  Local DOF = node + n_nodes * component; global ids
+    // entity by entity (scalar Q_p order), component-major inside an entity (App. B hypothesis, unpinned).
+    GG_REQUIRE(order >= 1 && order <= 2, GG_ERR_UNSUPPORTED, "vector H1 order must be 1 or 2");
+    GG_REQUIRE(constraint == GG_CONSTRAINT_NONE, GG_ERR_UNSUPPORTED, "constraints on vector H1 spaces are not implemented");
+    ensure_topology(m);
+    EdgeTopo T;
+    T.cell_edges = m->cell_edges; T.flip = m->cell_edge_flip; T.n_edges = m->n_edges;
+    std::vector<int32_t> sid;
+    int64_t nds;
+    cg_numbering(nc, m->cell_nodes.data(), m->n_nodes, T, order, sid, nds);
+    const int nn = (order + 1) * (order + 1), ne1 = order - 1, ni = ne1 * ne1;
+    const int64_t Nv = m->n_nodes, Ne = m->n_edges;
+    GG_REQUIRE(2 * nds < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
+    s->ndofs_loc = 2 * nn; s->n_free = 2 * nds;
+    s->cell_dofs.resize((size_t)nc * 2 * nn);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int a = 0; a < nn; ++a) {
+        const int64_t d = sid[c * nn + a];
+        for (int comp = 0; comp < 2; ++comp) {
+          int64_t g;
+          if (d < Nv) g = 2 * d + comp;
+          else if (d < Nv + Ne * ne1) { const int64_t e = (d - Nv) / ne1, k = (d - Nv) % ne1; g = 2 * Nv + e * 2 * ne1 + comp * ne1 + k; }
+          else { const int64_t cc = (d - Nv - Ne * ne1) / ni, k = (d - Nv - Ne * ne1) % ni; g = 2 * Nv + 2 * Ne * ne1 + cc * 2 * ni + comp * ni + k; }
+          s->cell_dofs[(size_t)c * 2 * nn + a + nn * comp] = (int32_t)g;
+        }
+      }
+    // master (cell, local node) of every (cell, node) whose owning vertex / edge has its master cell -- the surrounding cell
+    // with the largest id -- on another panel; -1 elsewhere
+    std::vector<int32_t> vmaster(Nv, -1), emaster(Ne, -1);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int k = 0; k < 4; ++k) {
+        GG_REQUIRE(!m->cell_edge_flip[c * 4 + k], GG_ERR_UNSUPPORTED, "the change of basis needs shared edges with the same vertex order in both cells");
+        vmaster[m->cell_nodes[c * 4 + k]] = std::max(vmaster[m->cell_nodes[c * 4 + k]], (int32_t)c);
+        emaster[m->cell_edges[c * 4 + k]] = std::max(emaster[m->cell_edges[c * 4 + k]], (int32_t)c);
+      }
+    s->cob_master_cell.assign((size_t)nc * nn, -1);
+    s->cob_master_node.assign((size_t)nc * nn, 0);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int a = 0; a < 4 + 4 * ne1; ++a) {
+        const bool vert = a < 4;
+        const int f = vert ? a : (a - 4) / ne1, k = vert ? 0 : (a - 4) % ne1;
+        const int32_t ent = vert ? m->cell_nodes[c * 4 + f] : m->cell_edges[c * 4 + f];
+        const int32_t mc = vert ? vmaster[ent] : emaster[ent];
+        if (m->cell_to_chart[mc] == m->cell_to_chart[c]) continue;
+        int fm = -1;
+        for (int j = 0; j < 4; ++j) if ((vert ? m->cell_nodes[mc * 4 + j] : m->cell_edges[mc * 4 + j]) == ent) fm = j;
+        GG_REQUIRE(fm >= 0, GG_ERR_INVALID, "inconsistent topology");
+        s->cob_master_cell[c * nn + a] = mc;
+        s->cob_master_node[c * nn + a] = (int8_t)(vert ? fm : 4 + fm * ne1 + k);
+      }
+    s->blocks.push_back({0, Nv, 2});
+    if (order > 1) {
+      s->blocks.push_back({2 * Nv, Ne, 2 * ne1});
+      s->blocks.push_back({2 * Nv + 2 * Ne * ne1, nc, 2 * ni});
     }
   } else if (kind == GG_SPACE_DG) {
     GG_REQUIRE(order >= 0 && order <= 4, GG_ERR_UNSUPPORTED, "DG order must be in 0..4");

@@ -150,6 +150,10 @@ int gg_vec_consistent(gg_space* s, gg_vec* v);
 #define GG_SPACE_CG 0 /* lagrangian, conformity=:H1 */
 #define GG_SPACE_DG 1 /* lagrangian, conformity=:L2 */
 #define GG_SPACE_RT 2 /* raviart_thomas, conformity=:HDiv */
+/* ReferenceFE(lagrangian, VectorValue{2,Float64}, p), conformity=:H1 on the intrinsic model: DOFs are contravariant components
+ * in the chart of the entity's master cell; cells on the other side of a panel interface see them through the 2x2
+ * change-of-basis blocks of src/FESpaces/GradConformingFESpaces.jl:60-113 (gg_space_change_of_basis) */
+#define GG_SPACE_CGV 3
 #define GG_CONSTRAINT_NONE 0
 #define GG_CONSTRAINT_ZEROMEAN 1 /* constraint=:zeromean: last free DOF fixed (Gridap ZeroMeanFESpace) */
 /* Built-in numbering = our restatement of Gridap's (parity unpinned). */
@@ -161,6 +165,9 @@ int gg_space_from_arrays(gg_mesh* m, int kind, int order, int64_t n_free, const 
 int gg_space_info(gg_space* s, int64_t* n_free, int32_t* ndofs_loc, int64_t* n_dirichlet);
 int gg_space_get_cell_dofs(gg_space* s, int32_t* out /* [n_cells][ndofs_loc], 1-based */);
 int gg_space_get_cell_signs(gg_space* s, int8_t* out /* [n_cells][ndofs_loc] */);
+/* GG_SPACE_CGV: the 2x2 blocks coeffs = pinvJ(J_slave) . J_master^T of every (cell, node), identity away from panel interfaces
+ * (GenerateChangeOfBasisMatrixMap, src/FESpaces/GradConformingFESpaces.jl:60-113) */
+int gg_space_change_of_basis(gg_space* s, double* out /* [n_cells][n_nodes][2][2] */);
 void gg_space_destroy(gg_space* s);
 
 /* ---- device vectors --------------------------------------------------------------------------
@@ -205,7 +212,11 @@ typedef enum {
   /* b(u,q) = int q div(u)  (rows: scalar test, cols: RT trial) -- test/Transient/TransientWaveEquation.jl:64 */
   GG_FORM_DIV = 6,
   /* l(v) = int f v sqrtg, f given at the quadrature points -- test/Laplacian/LaplaceBeltrami.jl:53 */
-  GG_FORM_SOURCE = 7
+  GG_FORM_SOURCE = 7,
+  /* vector H1: a(u,v) = int (u.(g v)) sqrtg and l(v) = int (f.(g v)) sqrtg with the contravariant field f given at the
+   * quadrature points, qdata [n_cells][Q][2] (test/Projection/L2_projection_Lagrangian_vector.jl:41-42) */
+  GG_FORM_MASS_VECTOR = 8,
+  GG_FORM_SOURCE_VECTOR = 9
 } gg_form;
 
 typedef struct {
