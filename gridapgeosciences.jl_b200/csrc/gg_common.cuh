@@ -163,6 +163,7 @@ struct gg_mesh {
   int64_t n_xint = 0, n_yint = 0;
   gg::DevBuf<double> d_xlo, d_xh, d_ylo, d_yh;
   gg::DevBuf<int32_t> d_ix, d_iy;
+  std::vector<int32_t> h_ix, h_iy;     // host copies (geometry classes of the condensed mass operators, gg_ebe.cu)
   struct TanTab { gg::DevBuf<double> tx, ty; };
   std::map<int, std::shared_ptr<TanTab>> tan_tabs;
   bool topology_built = false;

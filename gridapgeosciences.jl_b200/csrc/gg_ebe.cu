@@ -20,6 +20,7 @@
 // The eliminated DOFs are recovered cell by cell after the iteration: x_i = M_ii^-1 b_i - (M_ii^-1 M_if) x_f.
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <unordered_map>
 #include "gg_common.cuh"
 #include "gg_ebe.cuh"
 #include "gg_refel.cuh"
@@ -284,6 +285,9 @@ struct EbeArgs {
   int mloc;
   const int32_t* cell_dofs;
   const double *S, *T, *W;
+  int64_t ns;             // stride of S, T, W: cells, or geometry classes when cls != nullptr
+  const int32_t* cls;     // cell -> geometry class (nullptr: one operator per cell, DOF signs folded in)
+  const int8_t* sg;       // [nc][mloc] DOF signs applied around the class operators (nullptr: none)
   double* ev;  // [MB][nc]
   const int32_t *vptr, *vsrc;
   const int32_t *bstart, *rowoff;
@@ -342,24 +346,27 @@ __device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i) {
 // S_c p_c for one cell, p gathered through `load`
 template <int MB, typename Load>
 __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load load) {
-  const int64_t nc = a.nc;
+  const int64_t nc = a.nc, ns = a.ns;
+  const int64_t k = a.cls ? a.cls[c] : c;
+  const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
   double pe[MB], acc[MB];
 #pragma unroll
   for (int j = 0; j < MB; ++j) {
     const int32_t d = a.cell_dofs[c * a.mloc + j];
     pe[j] = d >= 0 ? load(d) : 0.0;
+    if (sg) pe[j] *= (double)sg[j];
     acc[j] = 0.0;
   }
 #pragma unroll
   for (int i = 0; i < MB; ++i)
 #pragma unroll
     for (int j = i; j < MB; ++j) {
-      const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * nc + c];
+      const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * ns + k];
       acc[i] = fma(sv, pe[j], acc[i]);
       if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
     }
 #pragma unroll
-  for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = acc[j];
+  for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = sg ? acc[j] * (double)sg[j] : acc[j];
 }
 
 // Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; the owner of a
@@ -391,14 +398,16 @@ k_pcg_ebe(const EbeArgs a) {
   if (MI > 0) {
     for (int64_t c = tid; c < nc; c += nth) {
       double bi[MIa];
+      const int64_t k = a.cls ? a.cls[c] : c;
+      const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t];
+      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         double acc = 0.0;
 #pragma unroll
-        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * nc + c], bi[t], acc);
-        a.ev[(int64_t)j * nc + c] = acc;
+        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * a.ns + k], bi[t], acc);
+        a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
       }
     }
     grid.sync();
@@ -588,12 +597,15 @@ k_pcg_ebe(const EbeArgs a) {
   if (MI > 0) {
     for (int64_t c = tid; c < nc; c += nth) {
       double bi[MIa], xf[MB];
+      const int64_t k = a.cls ? a.cls[c] : c;
+      const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t];
+      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         const int32_t d = a.cell_dofs[c * a.mloc + j];
         xf[j] = d >= 0 ? a.x[d] : 0.0;
+        if (sg) xf[j] *= (double)sg[j];
       }
 #pragma unroll
       for (int t = 0; t < MI; ++t) {
@@ -601,11 +613,11 @@ k_pcg_ebe(const EbeArgs a) {
 #pragma unroll
         for (int s = 0; s < MI; ++s) {
           const int lo = t < s ? t : s, hi = t < s ? s : t;
-          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * nc + c], bi[s], acc);
+          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * a.ns + k], bi[s], acc);
         }
 #pragma unroll
-        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * nc + c], xf[j], acc);
-        a.x[n + c * MI + t] = acc;
+        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * a.ns + k], xf[j], acc);
+        a.x[n + c * MI + t] = sg ? acc * (double)sg[MB + t] : acc;
       }
     }
   }
@@ -619,6 +631,20 @@ k_pcg_ebe(const EbeArgs a) {
 }
 
 static void ebe_build_precond(EbeSolver* s);
+static void ebe_compress(EbeSolver* s);
+
+// per-class copies of the per-cell operators of the representative cells, with the DOF signs taken out again
+// (planes [n_planes][nc] -> [n_planes][ns]; sign_a, sign_b: local DOF of the row / column of every plane)
+__global__ void k_ebe_compact(int64_t ns, int64_t nc, int n_planes, int mloc, const int32_t* __restrict__ rep,
+                              const int8_t* __restrict__ sg, const uint8_t* __restrict__ plane_a, const uint8_t* __restrict__ plane_b,
+                              const double* __restrict__ in, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns * n_planes) return;
+  const int64_t k = t % ns;
+  const int pl = (int)(t / ns);
+  const int64_t c = rep[k];
+  out[(int64_t)pl * ns + k] = in[(int64_t)pl * nc + c] * (double)(sg[c * mloc + plane_a[pl]] * sg[c * mloc + plane_b[pl]]);
+}
 
 template <int MB, int MI>
 static void ebe_launch_condense(gg_ctx* ctx, int64_t nc, const double* ebuf, double* S, double* T, double* W) {
@@ -711,6 +737,14 @@ void ebe_set_matrix(EbeSolver* s, const double* ebuf) {
   gg_ctx* ctx = s->ctx;
   gg_space* sp = s->sp;
   if (s->nc == 0) return;
+  if (s->compressed) {
+    // back to one operator per cell before condensing again
+    const int MB = s->MB, MI = s->MI;
+    s->S.alloc((size_t)(MB * (MB + 1) / 2) * s->nc);
+    s->T.alloc((size_t)MI * MB * s->nc);
+    s->W.alloc((size_t)(MI * (MI + 1) / 2) * s->nc);
+    s->compressed = false; s->ns = s->nc;
+  }
   {
     ProfScope ps(ctx, "k_ebe_condense");
 #define X(MB_, MI_) if (s->MB == MB_ && s->MI == MI_) ebe_launch_condense<MB_, MI_>(ctx, s->nc, ebuf, s->S.p, s->T.p, s->W.p);
@@ -719,7 +753,63 @@ void ebe_set_matrix(EbeSolver* s, const double* ebuf) {
     ctx->launches++;
   }
   GG_CUDA(cudaGetLastError());
+  s->ns = s->nc; s->compressed = false;
   ebe_build_precond(s);
+  ebe_compress(s);
+}
+
+// Constant operators on a mesh whose cells repeat chart boxes (every (x-interval, y-interval) pair of the cubed sphere occurs on
+// all 6 panels): the metric depends on the chart point only, so cells of one geometry class share S_c, T_c, M_ii^-1 up to the
+// DOF signs.  Keep one copy per class (6x less operator traffic per PCG iteration; the class operators of a 256^2 panel stay in
+// L2) and apply the signs on the fly.  Bitwise identical results: the copies are the representative cell's own numbers.
+static void ebe_compress(EbeSolver* s) {
+  static const bool off = getenv("GG_EBE_CLASSES") && getenv("GG_EBE_CLASSES")[0] == '0';
+  gg_space* sp = s->sp;
+  gg_mesh* m = sp->mesh;
+  gg_ctx* ctx = s->ctx;
+  const int64_t nc = s->nc;
+  if (off || sp->kind != GG_SPACE_RT || m->dim != 2 || (int64_t)m->h_ix.size() != nc || nc == 0) return;
+  std::vector<int32_t> cls(nc), rep;
+  {
+    std::unordered_map<int64_t, int32_t> seen;
+    seen.reserve((size_t)nc);
+    for (int64_t c = 0; c < nc; ++c) {
+      const int64_t key = (int64_t)m->h_iy[c] * m->n_xint + m->h_ix[c];
+      auto it = seen.find(key);
+      if (it == seen.end()) { it = seen.emplace(key, (int32_t)rep.size()).first; rep.push_back((int32_t)c); }
+      cls[c] = it->second;
+    }
+  }
+  const int64_t ns = (int64_t)rep.size();
+  if (2 * ns > nc) return;   // nothing to gain
+  cudaStream_t st = ctx->stream;
+  const int MB = s->MB, MI = s->MI, mloc = sp->ndofs_loc;
+  DevBuf<int32_t> drep;
+  drep.upload(rep, st);
+  auto compact = [&](DevBuf<double>& buf, const std::vector<uint8_t>& pa, const std::vector<uint8_t>& pb) {
+    const int np = (int)pa.size();
+    if (np == 0) return;
+    DevBuf<uint8_t> da, db;
+    da.upload(pa, st); db.upload(pb, st);
+    DevBuf<double> out((size_t)np * ns);
+    k_ebe_compact<<<nblk(ns * np, 256), 256, 0, st>>>(ns, nc, np, mloc, drep.p, sp->d_cell_signs.p, da.p, db.p, buf.p, out.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
+    buf = std::move(out);
+  };
+  std::vector<uint8_t> pa, pb;
+  for (int i = 0; i < MB; ++i) for (int j = i; j < MB; ++j) { pa.push_back((uint8_t)i); pb.push_back((uint8_t)j); }
+  compact(s->S, pa, pb);
+  pa.clear(); pb.clear();
+  for (int t = 0; t < MI; ++t) for (int j = 0; j < MB; ++j) { pa.push_back((uint8_t)(MB + t)); pb.push_back((uint8_t)j); }
+  compact(s->T, pa, pb);
+  pa.clear(); pb.clear();
+  for (int i = 0; i < MI; ++i) for (int j = i; j < MI; ++j) { pa.push_back((uint8_t)(MB + i)); pb.push_back((uint8_t)(MB + j)); }
+  compact(s->W, pa, pb);
+  s->cls.upload(cls, st);
+  GG_CUDA(cudaStreamSynchronize(st));
+  s->ns = ns; s->compressed = true;
 }
 
 static void ebe_build_precond(EbeSolver* s) {
@@ -783,6 +873,9 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   EbeArgs a;
   a.nb = s->nb; a.nc = s->nc; a.mloc = sp->ndofs_loc; a.cell_dofs = sp->d_cell_dofs.p;
   a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p;
+  a.ns = s->compressed ? s->ns : s->nc;
+  a.cls = s->compressed ? s->cls.p : nullptr;
+  a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p;
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;

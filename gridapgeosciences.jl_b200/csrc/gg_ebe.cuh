@@ -9,7 +9,12 @@ struct EbeSolver {
   gg_space* sp = nullptr;
   int MB = 0, MI = 0;        // boundary (shared) / interior (cell-private) local DOFs
   int64_t nb = 0, nc = 0;    // boundary free DOFs (numbered first), cells
-  DevBuf<double> S, T, W;    // per cell, entry-major: packed S_c, T_c = M_ii^-1 M_if, packed M_ii^-1
+  DevBuf<double> S, T, W;    // per cell (or geometry class), entry-major: packed S_c, T_c = M_ii^-1 M_if, packed M_ii^-1
+  // geometry classes (constant operators on meshes whose cells repeat chart boxes, e.g. the 6 congruent panels of the cubed
+  // sphere): S, T, W are stored once per class for the UNSIGNED reference basis; cls[c] = class of cell c, ns = classes
+  DevBuf<int32_t> cls;
+  int64_t ns = 0;            // stride of S, T, W (= nc when not compressed)
+  bool compressed = false;
   DevBuf<int32_t> bstart, rowoff, blk_off;
   DevBuf<uint8_t> bsize, blk_size;
   DevBuf<double> binv;

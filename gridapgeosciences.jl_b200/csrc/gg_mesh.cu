@@ -145,6 +145,7 @@ void upload_geometry(gg_mesh* m) {
   intervals(y0, hy, iy, ylo, yh);
   m->n_xint = (int64_t)xlo.size(); m->n_yint = (int64_t)ylo.size();
   m->d_ix.upload(ix, s); m->d_iy.upload(iy, s);
+  m->h_ix = ix; m->h_iy = iy;
   m->d_xlo.upload(xlo, s); m->d_xh.upload(xh, s); m->d_ylo.upload(ylo, s); m->d_yh.upload(yh, s);
   m->tan_tabs.clear();
   if (!m->cell_owned.empty()) m->d_cell_owned.upload(m->cell_owned, s);
