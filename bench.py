@@ -197,6 +197,38 @@ def adv_leg(gg, ctx, torch, stream, e0, e1, n=128, p=2, steps=200, dist=None, ra
     return out
 
 
+def tswe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=1, steps=10):
+    """RK steps/s of the thermal shallow-water stepper (test/Tutorials/ThermalShallowWater.jl: order 1, thermogeostrophic balance,
+    Measure(., 4*order); next-row caller of the same kernels)."""
+    ctx.set_async(False)
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n, ctx=ctx)
+    ic = gg.initial_conditions
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, p), conformity="HDiv")
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+    x0 = np.concatenate([gg.interpolate(ic.williamson2_velocity, V).get(), gg.interpolate(ic.williamson2_depth, Q).get(),
+                         gg.interpolate(ic.thermogeostrophic_weighted_buoyancy, Q).get()])
+    dt = math.sqrt(4 * math.pi / model.num_cells) * 0.1 / (p * math.sqrt(ic.GRAVITY * ic.H0_W2))
+    st = gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=1e-12), None, dt, "EXRK_SSP_3_3"),
+                      gg.ThermalShallowWaterOperator(model, p, ic.coriolis))
+    st.set_state(x0)
+    st.step(5)
+    it0, so0 = st.stats()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    st.step(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    it1, so1 = st.stats()
+    drift = float(np.abs(st.get_state() - x0).max() / np.abs(x0).max())
+    out = {"workload": f"thermal shallow water (thermogeostrophic balance), {n}x{n} per panel, RT{p} x DG{p} x DG{p} + CG{p + 1} "
+                       f"diagnostics, degree {4 * p}, SSPRK(3,3)", "cells": model.num_cells, "dofs_prognostic": st.nu + st.np_,
+           "steps_per_s": 1e3 / ms, "ms_per_step": ms, "pcg_iters_per_solve": (it1 - it0) / max(so1 - so0, 1),
+           "state_drift_after_steps": drift}
+    del st
+    return out
+
+
 def shell_leg(gg, ctx, torch, stream, e0, e1, n=48, order=2, degree=18, steps=10, dist=None, rank=0, world=1):
     """cells/s of the Laplace-Beltrami residual + Jacobian assembly on the 3-D shell (hexahedral Q2, 10^3 points per cell in the
     reference; here the tensor Gauss rule is factorised exactly into surface x radial integrals, gg_hex.cuh)."""
@@ -496,7 +528,32 @@ def main():
             ms2 = float(t.item())
         line["e2e"] = {"value": total_owned / (ms2 / Ke2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": 8 * V.num_free_dofs,
                        "d2h_bytes_per_step": 8 * (A.nnz + V.num_free_dofs), "ms_per_step": ms2 / Ke2e,
-                       "api": "DeviceVector.set(host u) + assemble_matrix_and_vector + CSRMatrix.values(host) + DeviceVector.get(host)"}
+                       "api": "DeviceVector.set(host u) + assemble_matrix_and_vector + CSRMatrix.values(host) + DeviceVector.get(host)",
+                       "bound": "PCIe: the 201 MB of CSR values dominate (the kernels are 0.28 ms of the step)"}
+
+        # the same call when the Jacobian stays on the device for a device-side solver (GPULinearSolver in INTEGRATION.md):
+        # only the state goes in and the residual comes out
+        def e2e_resident_step():
+            u.set(u_host.numpy())
+            gg.assemble_matrix_and_vector(form, assem, b)
+            b.get(out=b_host.numpy())
+
+        for _ in range(3):
+            e2e_resident_step()
+        barrier()
+        e0.record(stream)
+        for _ in range(Ke2e):
+            e2e_resident_step()
+        e1.record(stream)
+        barrier()
+        ms3 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms3 = float(t.item())
+        line["e2e"]["matrix_resident"] = {"value": total_owned / (ms3 / Ke2e * 1e-3), "unit": "cells/s", "ms_per_step": ms3 / Ke2e,
+                                          "h2d_bytes_per_step": 8 * V.num_free_dofs, "d2h_bytes_per_step": 8 * V.num_free_dofs,
+                                          "note": "Jacobian left in HBM for a device-side linear solver; state in, residual out"}
 
     # ---- RK steps/s (second half of BASELINE.json's metric): linear wave, 48x48 per panel, RT1 x DG1 -------------
     if not args.no_extras and rank == 0:
@@ -533,6 +590,10 @@ def main():
                 line["rk"]["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1)
             except Exception as ex:
                 line["rk"]["shallow_water"] = {"error": str(ex)}
+            try:
+                line["rk"]["thermal_shallow_water"] = tswe_leg(gg, ctx, torch, stream, e0, e1)
+            except Exception as ex:
+                line["rk"]["thermal_shallow_water"] = {"error": str(ex)}
 
     # ---- 3-D shell (BASELINE configs[4]): hexahedral Q2 Laplace-Beltrami residual + Jacobian, 48^3 cells per panel ---------
     if not args.no_extras and rank == 0 and world == 1:

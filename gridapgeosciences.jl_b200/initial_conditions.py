@@ -44,6 +44,17 @@ def williamson2_depth(X):
 
 
 # ---- Galewsky et al. (2004), eqs. (2)-(4) -------------------------------------------------------------------------------------
+def thermogeostrophic_buoyancy(X, c=0.05):
+    """b0 of test/Tutorials/ThermalShallowWater.jl:121-125: g (1 + c H0^2 / h^2) on the Williamson-2 depth."""
+    h = williamson2_depth(X)
+    return GRAVITY * (1.0 + c * H0_W2 ** 2 / h ** 2)
+
+
+def thermogeostrophic_weighted_buoyancy(X, c=0.05):
+    """B0 = b0 h0 (test/Tutorials/ThermalShallowWater.jl:127-131)."""
+    return thermogeostrophic_buoyancy(X, c) * williamson2_depth(X)
+
+
 _UMAX = 80.0 / A_E * T_SCALE
 _PHI0, _PHI1 = np.pi / 7, np.pi / 2 - np.pi / 7
 _EN = np.exp(-4.0 / (_PHI1 - _PHI0) ** 2)
