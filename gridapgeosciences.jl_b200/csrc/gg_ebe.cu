@@ -344,11 +344,11 @@ __device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i) {
 }
 
 // S_c p_c for one cell, p gathered through `load`
-template <int MB, typename Load>
+template <int MB, bool CLS, typename Load>
 __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load load) {
-  const int64_t nc = a.nc, ns = a.ns;
-  const int64_t k = a.cls ? a.cls[c] : c;
-  const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
+  const int64_t nc = a.nc, ns = CLS ? a.ns : a.nc;
+  const int64_t k = CLS ? a.cls[c] : c;
+  const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
   double pe[MB], acc[MB];
 #pragma unroll
   for (int j = 0; j < MB; ++j) {
@@ -374,7 +374,7 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load
 // phase C), the dot products are summed over the ranks in rank order (gg_dist.cuh), and the ghost values are copied from
 // the slot into z after the round -- 2 rounds per iteration, no host, no NCCL.  (z itself stays in ordinary device memory:
 // writing the whole vector into the IPC-exported window made phase C 2x slower on B200.)
-template <int MB, int MI>
+template <int MB, int MI, bool CLS>
 __global__ void __launch_bounds__(256, 2)
 k_pcg_ebe(const EbeArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -398,15 +398,15 @@ k_pcg_ebe(const EbeArgs a) {
   if (MI > 0) {
     for (int64_t c = tid; c < nc; c += nth) {
       double bi[MIa];
-      const int64_t k = a.cls ? a.cls[c] : c;
-      const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
+      const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
+      const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
       for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         double acc = 0.0;
 #pragma unroll
-        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * a.ns + k], bi[t], acc);
+        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * ns + k], bi[t], acc);
         a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
       }
     }
@@ -431,7 +431,7 @@ k_pcg_ebe(const EbeArgs a) {
   }
   if (a.warm) {
     // initial guess = what the output vector holds (the solution of the previous stage / step): r = bt - S x
-    for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB>(a, c, [&](int32_t d) { return a.x[d]; });
+    for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, [&](int32_t d) { return a.x[d]; });
     grid.sync();
     for (int64_t i = tid; i < n; i += nth) r_old[i] -= ebe_gather_row(a, i);
     grid.sync();
@@ -471,7 +471,7 @@ k_pcg_ebe(const EbeArgs a) {
     for (it = 1; it <= a.max_iter; ++it) {
       // -- A: element vectors of S p with p = z + beta p_old formed on the fly (z may have been written by a peer: L2 loads)
       unsigned long long t0 = ebe_now();
-      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB>(a, c, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
+      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
       grid.sync();
       unsigned long long t1 = ebe_now();
       tA += t1 - t0;
@@ -597,8 +597,8 @@ k_pcg_ebe(const EbeArgs a) {
   if (MI > 0) {
     for (int64_t c = tid; c < nc; c += nth) {
       double bi[MIa], xf[MB];
-      const int64_t k = a.cls ? a.cls[c] : c;
-      const int8_t* __restrict__ sg = a.sg ? a.sg + c * a.mloc : nullptr;
+      const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
+      const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
       for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
@@ -613,10 +613,10 @@ k_pcg_ebe(const EbeArgs a) {
 #pragma unroll
         for (int s = 0; s < MI; ++s) {
           const int lo = t < s ? t : s, hi = t < s ? s : t;
-          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * a.ns + k], bi[s], acc);
+          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * ns + k], bi[s], acc);
         }
 #pragma unroll
-        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * a.ns + k], xf[j], acc);
+        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * ns + k], xf[j], acc);
         a.x[n + c * MI + t] = sg ? acc * (double)sg[MB + t] : acc;
       }
     }
@@ -653,8 +653,8 @@ static void ebe_launch_condense(gg_ctx* ctx, int64_t nc, const double* ebuf, dou
 
 #define GG_EBE_CASES(X) X(4, 0) X(8, 4) X(12, 12) X(8, 1) X(12, 4)
 
-static void* ebe_kernel(int MB, int MI) {
-#define X(MB_, MI_) if (MB == MB_ && MI == MI_) return (void*)k_pcg_ebe<MB_, MI_>;
+static void* ebe_kernel(int MB, int MI, bool classes = false) {
+#define X(MB_, MI_) if (MB == MB_ && MI == MI_) return classes ? (void*)k_pcg_ebe<MB_, MI_, true> : (void*)k_pcg_ebe<MB_, MI_, false>;
   GG_EBE_CASES(X)
 #undef X
   return nullptr;
@@ -883,7 +883,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.warm = warm ? 1 : 0;
   a.dist = dist_dev(sp);
   if (getenv("GG_FORCE_MULTI") && a.dist.win) a.dist.force_multi = 1;  // measurement: run the partitioned code path on one rank
-  void* fn = ebe_kernel(s->MB, s->MI);
+  void* fn = ebe_kernel(s->MB, s->MI, s->compressed);
   int grid = s->grid;
   const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;
   if (want < grid) grid = (int)std::max<int64_t>(want, 1);
