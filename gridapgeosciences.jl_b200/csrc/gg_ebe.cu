@@ -288,7 +288,8 @@ struct EbeArgs {
   int64_t ns;             // stride of S, T, W: cells, or geometry classes when cls != nullptr
   const int32_t* cls;     // cell -> geometry class (nullptr: one operator per cell, DOF signs folded in)
   const int8_t* sg;       // [nc][mloc] DOF signs applied around the class operators (nullptr: none)
-  double* ev;  // [MB][nc]
+  double* ev;   // [MB][nc]
+  double* ev2;  // [MB][nc] second element-vector buffer (S x of the warm start, next to the condensed right-hand side)
   const int32_t *vptr, *vsrc;
   const int32_t *bstart, *rowoff;
   const uint8_t* bsize;
@@ -336,16 +337,16 @@ __device__ __forceinline__ double ebe_grid_total(const double* partials, int nbl
 }
 
 // sum of the element contributions of DOF row i (at most 2 sources on the fast path, more in the tail loop)
-__device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i) {
+__device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i, const double* __restrict__ ev) {
   const int32_t lo = a.vptr[i], hi = a.vptr[i + 1];
-  double acc = lo < hi ? a.ev[a.vsrc[lo]] : 0.0;
-  for (int32_t k = lo + 1; k < hi; ++k) acc += a.ev[a.vsrc[k]];
+  double acc = lo < hi ? ev[a.vsrc[lo]] : 0.0;
+  for (int32_t k = lo + 1; k < hi; ++k) acc += ev[a.vsrc[k]];
   return acc;
 }
 
 // S_c p_c for one cell, p gathered through `load`
 template <int MB, bool CLS, typename Load>
-__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load load) {
+__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, double* __restrict__ out, Load load) {
   const int64_t nc = a.nc, ns = CLS ? a.ns : a.nc;
   const int64_t k = CLS ? a.cls[c] : c;
   const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
@@ -366,7 +367,7 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, Load
       if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
     }
 #pragma unroll
-  for (int j = 0; j < MB; ++j) a.ev[(int64_t)j * nc + c] = sg ? acc[j] * (double)sg[j] : acc[j];
+  for (int j = 0; j < MB; ++j) out[(int64_t)j * nc + c] = sg ? acc[j] * (double)sg[j] : acc[j];
 }
 
 // Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; the owner of a
@@ -394,31 +395,68 @@ k_pcg_ebe(const EbeArgs a) {
   double* r_old = a.ra;
   double* r_new = a.rb;
 
-  // ---- condensed right-hand side: bt = s b_f - sum_c T_c^T (s b_i) ----
-  if (MI > 0) {
+  const unsigned long long tp0 = ebe_now();
+  // ---- one pass over the cells: condensed right-hand side  ev = T_c^T (s b_i)  and, for a warm start, ev2 = S_c x_c ----
+  if (MI > 0 || a.warm) {
     for (int64_t c = tid; c < nc; c += nth) {
-      double bi[MIa];
-      const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
-      const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
+      if (MI > 0) {
+        double bi[MIa];
+        const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
+        const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
+        for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        double acc = 0.0;
+        for (int j = 0; j < MB; ++j) {
+          double acc = 0.0;
 #pragma unroll
-        for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * ns + k], bi[t], acc);
-        a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
+          for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * ns + k], bi[t], acc);
+          a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
+        }
       }
+      // initial guess = what the output vector holds (the solution of the previous stage / step)
+      if (a.warm) ebe_apply_cell<MB, CLS>(a, c, a.ev2, [&](int32_t d) { return a.x[d]; });
     }
     grid.sync();
   }
+  const unsigned long long tp1 = ebe_now();
+  // ---- one pass over the rows: bt = s b_f - gather(ev), |bt|^2, r = bt - gather(ev2)  (4 rows in flight per thread) ----
   double lbb = 0.0;
-  for (int64_t i = tid; i < n; i += nth) {
-    double v = a.scale_b * a.b[i];
-    if (MI > 0) v -= ebe_gather_row(a, i);
-    r_old[i] = v;
-    if (!owned || owned[i]) lbb = fma(v, v, lbb);
-    if (!a.warm) a.x[i] = 0.0;
+  for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+    int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
+    double bt[UNR], rw[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t i = i0 + u * nth;
+      const bool ok = i < n;
+      lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
+      bt[u] = ok ? a.scale_b * a.b[i] : 0.0;
+      rw[u] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (MI > 0) {
+        if (s0[u] >= 0) bt[u] -= a.ev[s0[u]];
+        if (s1[u] >= 0) bt[u] -= a.ev[s1[u]];
+      }
+      if (a.warm) {
+        if (s0[u] >= 0) rw[u] = a.ev2[s0[u]];
+        if (s1[u] >= 0) rw[u] += a.ev2[s1[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t i = i0 + u * nth;
+      if (i >= n) continue;
+      for (int32_t k = lo[u] + 2; k < hi[u]; ++k) {
+        if (MI > 0) bt[u] -= a.ev[a.vsrc[k]];
+        if (a.warm) rw[u] += a.ev2[a.vsrc[k]];
+      }
+      r_old[i] = bt[u] - rw[u];
+      if (!owned || owned[i]) lbb = fma(bt[u], bt[u], lbb);
+      if (!a.warm) a.x[i] = 0.0;
+    }
   }
   lbb = ebe_block_sum(lbb, sh);
   if (threadIdx.x == 0) P1[blockIdx.x] = lbb;
@@ -429,25 +467,34 @@ k_pcg_ebe(const EbeArgs a) {
     dist_allreduce<1>(grid, a.dist, epoch, v);
     bb = v[0];
   }
-  if (a.warm) {
-    // initial guess = what the output vector holds (the solution of the previous stage / step): r = bt - S x
-    for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, [&](int32_t d) { return a.x[d]; });
-    grid.sync();
-    for (int64_t i = tid; i < n; i += nth) r_old[i] -= ebe_gather_row(a, i);
-    grid.sync();
-  }
+  const unsigned long long tp2 = ebe_now();
   double lrz = 0.0, lrr0 = 0.0;
-  for (int64_t i = tid; i < n; i += nth) {
-    a.p[i] = 0.0;
-    if (owned && !owned[i]) continue;
-    const int s = a.bstart[i], m = a.bsize[i];
-    const double* bi_row = a.binv + a.rowoff[i];
-    double zi = 0.0;
-    for (int j = 0; j < m; ++j) zi = fma(bi_row[j], r_old[s + j], zi);
-    const double ri = r_old[i];
-    a.z[i] = zi;
-    lrz = fma(ri, zi, lrz);
-    lrr0 = fma(ri, ri, lrr0);
+  for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+    int sb[UNR], mb[UNR], ro[UNR];
+    double zi[UNR], ri[UNR];
+    bool own[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t i = i0 + u * nth;
+      const bool ok = i < n;
+      own[u] = ok && (!owned || owned[i]);
+      sb[u] = ok ? a.bstart[i] : 0; mb[u] = own[u] ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
+      ri[u] = ok ? r_old[i] : 0.0;
+      zi[u] = 0.0;
+      if (ok) a.p[i] = 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const double* bi_row = a.binv + ro[u];
+      for (int j = 0; j < mb[u]; ++j) zi[u] = fma(bi_row[j], r_old[sb[u] + j], zi[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (!own[u]) continue;
+      a.z[i0 + u * nth] = zi[u];
+      lrz = fma(ri[u], zi[u], lrz);
+      lrr0 = fma(ri[u], ri[u], lrr0);
+    }
   }
   lrz = ebe_block_sum(lrz, sh);
   lrr0 = ebe_block_sum(lrr0, sh);
@@ -466,12 +513,13 @@ k_pcg_ebe(const EbeArgs a) {
   double beta = 0.0;
   unsigned long long tA = 0, tB = 0, tC = 0, tR = 0, tP = 0;
   grid.sync();  // P2 is reused by the first iteration
+  const unsigned long long tp3 = ebe_now();
   const double tol2 = a.rtol * a.rtol * bb;
   if (bb > 0.0 && rr > tol2) {
     for (it = 1; it <= a.max_iter; ++it) {
       // -- A: element vectors of S p with p = z + beta p_old formed on the fly (z may have been written by a peer: L2 loads)
       unsigned long long t0 = ebe_now();
-      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
+      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, a.ev, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
       grid.sync();
       unsigned long long t1 = ebe_now();
       tA += t1 - t0;
@@ -593,6 +641,7 @@ k_pcg_ebe(const EbeArgs a) {
     grid.sync();
     if (tid == 0) a.dist.win[a.dist.rank]->epoch = epoch;
   }
+  const unsigned long long tp4 = ebe_now();
   // ---- eliminated DOFs: x_i = W (s b_i) - T x_f ----
   if (MI > 0) {
     for (int64_t c = tid; c < nc; c += nth) {
@@ -627,6 +676,9 @@ k_pcg_ebe(const EbeArgs a) {
     a.stats[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
     a.stats[2] += (double)tA; a.stats[3] += (double)tB; a.stats[4] += (double)tC; a.stats[5] += (double)itc;
     a.stats[6] += (double)tR; a.stats[7] += (double)tP;
+    // set-up and tear-down phases of the solve: cell pre-pass, row pass, first preconditioner pass, interior recovery; solves
+    a.stats[8] += (double)(tp1 - tp0); a.stats[9] += (double)(tp2 - tp1); a.stats[10] += (double)(tp3 - tp2);
+    a.stats[11] += (double)(ebe_now() - tp4); a.stats[12] += 1.0;
   }
 }
 
@@ -716,6 +768,7 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   s->T.alloc((size_t)MI * MB * nc);
   s->W.alloc((size_t)(MI * (MI + 1) / 2) * nc);
   s->ev.alloc((size_t)MB * std::max<int64_t>(nc, 1));
+  s->ev2.alloc((size_t)MB * std::max<int64_t>(nc, 1));
   s->r.alloc(n); s->r2.alloc(n); s->z.alloc(n); s->p.alloc(n); s->Ap.alloc(n);
   build_vec_map(sp);
   void* fn = ebe_kernel(MB, MI);
@@ -724,8 +777,8 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   GG_REQUIRE(per_sm >= 1, GG_ERR_CUDA, "condensed PCG kernel does not fit on an SM");
   s->grid = ctx->sm_count * per_sm;
   s->partials.alloc(3 * (size_t)s->grid);
-  s->stats.alloc(8);
-  GG_CUDA(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(double), st));
+  s->stats.alloc(16);
+  GG_CUDA(cudaMemsetAsync(s->stats.p, 0, 16 * sizeof(double), st));
   GG_CUDA(cudaStreamSynchronize(st));
   return s.release();
 }
@@ -872,7 +925,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   if (sp->n_free == 0) return;
   EbeArgs a;
   a.nb = s->nb; a.nc = s->nc; a.mloc = sp->ndofs_loc; a.cell_dofs = sp->d_cell_dofs.p;
-  a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p;
+  a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p; a.ev2 = s->ev2.p;
   a.ns = s->compressed ? s->ns : s->nc;
   a.cls = s->compressed ? s->cls.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;

@@ -19,7 +19,7 @@ struct EbeSolver {
   DevBuf<uint8_t> bsize, blk_size;
   DevBuf<double> binv;
   int64_t n_blocks = 0;
-  DevBuf<double> r, r2, z, p, Ap, ev, partials;
+  DevBuf<double> r, r2, z, p, Ap, ev, ev2, partials;
   DevBuf<double> stats;      // [0] iterations of the last solve, [1] its relative residual, [2..5] phase timers (ns) + iterations
   double rtol = 1e-12;
   int max_iter = 1000;

@@ -512,14 +512,23 @@ int gg_rk_swe_residual(gg_rk* rk, const double* x, const double* y, const double
 int gg_rk_solver_phase_ns(gg_rk* rk, int which, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(rk && out, GG_ERR_INVALID, "null argument");
+  // which = 0 / 1: iteration phases of the RT / potential-vorticity solver; which = 10 / 11: set-up phases of the condensed
+  // solver (cell pre-pass, row pass, first preconditioner pass, interior recovery), each followed by the count in out[3] / ...
+  const bool setup = which >= 10;
+  if (setup) which -= 10;
   gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
   EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
   for (int i = 0; i < 4; ++i) out[i] = 0.0;
   if (!s && !e) return GG_OK;
   GG_CUDA(cudaSetDevice(rk->ctx->device));
-  double h[8];
+  double h[16] = {0};
   if (e) e->stats.download(h, rk->ctx->stream);
-  else s->stats.download(h, rk->ctx->stream);
+  else { double h8[8]; s->stats.download(h8, rk->ctx->stream); for (int i = 0; i < 8; ++i) h[i] = h8[i]; }
+  if (setup) {
+    const double ns = h[12] > 0 ? h[12] : 1.0;
+    for (int i = 0; i < 4; ++i) out[i] = h[8 + i] / ns;   // ns per solve
+    return GG_OK;
+  }
   for (int i = 0; i < 4; ++i) out[i] = h[2 + i];
   if (getenv("GG_COMM_STATS") && h[5] > 0)
     fprintf(stderr, "[gg_rk solver %d] per iteration: cells %.1f  gather+dot %.1f  update+precond %.1f us, of which all-reduce rounds %.1f "

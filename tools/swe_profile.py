@@ -74,7 +74,8 @@ def main():
         a = st.solver_phase_ns(which)
         if a[3] > 0:
             phases[name] = {"iters": a[3], "us_per_iter": {"cells": a[0] / a[3] / 1e3, "gather_dot": a[1] / a[3] / 1e3, "update_precond": a[2] / a[3] / 1e3}}
-    out = {"n": args.n, "order": p, "cells": model.num_cells, "dofs_prognostic": st.nu + st.np_, "dofs_diagnostic": st.ny,
+    setup = {name: [round(v / 1e3, 1) for v in st.solver_phase_ns(10 + which)] for which, name in ((0, "rt_mass"), (1, "q_mass"))}
+    out = {"pcg_setup_us_per_solve(cell pre-pass, rows, first precond, interior recovery)": setup, "n": args.n, "order": p, "cells": model.num_cells, "dofs_prognostic": st.nu + st.np_, "dofs_diagnostic": st.ny,
            "setup_s": setup_s, "ms_per_step": wall * 1e3, "steps_per_s": 1.0 / wall,
            "pcg_iters_per_solve": (it1 - it0) / max(so1 - so0, 1), "solves_per_step": (so1 - so0) / args.steps,
            "kernels": prof, "pcg_phases": phases, "profiled_ms_per_step": sum(v["ms_per_step"] for v in prof.values()),
