@@ -495,11 +495,16 @@ class DeviceVector:
 class CSRMatrix:
     """Device CSR matrix with a fixed pattern (`gg_pattern`); `to_scipy()` exports it."""
 
-    def __init__(self, test, trial):
+    def __init__(self, test, trial, skeleton=False):
         self.test, self.trial = test, trial
         self.ctx, self.lib = test.model.ctx, test.lib
         h = C.c_void_p()
-        _lib.check(self.lib.gg_pattern(test.h, trial.h, C.byref(h)))
+        if skeleton:
+            # SparseMatrixAssembler on a form with SkeletonTriangulation terms: facet-neighbour coupling (DG)
+            assert test is trial
+            _lib.check(self.lib.gg_pattern_skeleton(test.h, C.byref(h)))
+        else:
+            _lib.check(self.lib.gg_pattern(test.h, trial.h, C.byref(h)))
         self.h = h
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_csr_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
@@ -934,6 +939,14 @@ class AdvectionOperator:
         fx = np.empty((model.num_cells, 4, n.value, 3))
         _lib.check(model.lib.gg_skeleton_points(model.h, self.degree, C.byref(n), _dp(fx)))
         self.beta_facets = np.ascontiguousarray(np.broadcast_to(beta(fx), fx.shape), dtype=np.float64)
+
+
+def assemble_advection_matrix(op, Q, A=None):
+    """jac(t,u,du,v) = a_Ω(du,v) + b_Ω(du,v) + s_Ω(du,v) of test/Tutorials/AdvectionUpwinding.jl:124-131 as a device CSR matrix
+    (volume + skeleton terms; the tutorial hands it to SDIRK + LU)."""
+    A = A if A is not None else CSRMatrix(Q, Q, skeleton=True)
+    _lib.check(Q.lib.gg_assemble_advection(Q.h, op.degree, _dp(op.beta_cells), _dp(op.beta_facets), A.h))
+    return A
 
 
 class RKStepper:

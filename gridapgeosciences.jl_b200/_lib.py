@@ -109,6 +109,8 @@ SIGNATURES = {
     "gg_vec_device_ptr": (C.c_void_p, [_P]),
     "gg_vec_destroy": (None, [_P]),
     "gg_pattern": (C.c_int, [_P, _P, _PP]),
+    "gg_pattern_skeleton": (C.c_int, [_P, _PP]),
+    "gg_assemble_advection": (C.c_int, [_P, C.c_int32, _PD, _PD, _P]),
     "gg_csr_info": (C.c_int, [_P, _PI64, _PI64, _PI64]),
     "gg_csr_export": (C.c_int, [_P, _PI64, _PI64, _PD, C.c_int]),
     "gg_csr_device_values": (C.c_void_p, [_P]),

@@ -259,6 +259,32 @@ void facet_tables(gg_rk* rk, int nq) {
   rk->adv_fval.upload(fval, st);
 }
 
+// wind tabulations: contravariant wind times the cell weights, beta.n and the facet weights per cell side
+static void adv_wind_tables(gg_mesh* m, int order, int nq, const double* velocity_cells, const double* velocity_facets,
+                            DevBuf<double>& bq, DevBuf<double>& bn, DevBuf<double>& wsg) {
+  gg_ctx* ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t nc = m->n_cells;
+  const int Q = nq * nq;
+  std::vector<double> s(nq), wf(nq);
+  gauss_legendre_01(nq, s.data(), wf.data());
+  auto tab = get_tab(ctx, GG_SPACE_DG, order, nq);
+  DevBuf<double> dbc, dbf, ds, dw;
+  dbc.upload(velocity_cells, (size_t)nc * Q * 3, st);
+  dbf.upload(velocity_facets, (size_t)nc * 4 * nq * 3, st);
+  ds.upload(s, st); dw.upload(wf, st);
+  bq.alloc((size_t)2 * Q * nc); bn.alloc((size_t)4 * nq * nc); wsg.alloc((size_t)4 * nq * nc);
+  if (nc) {
+    k_adv_cell_wind<<<nblk(nc * Q, 128), 128, 0, st>>>(nc, nq, tab->xi.p, tab->w.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
+                                                      m->d_chart.p, m->radius, dbc.p, bq.p);
+    k_adv_facet_wind<<<nblk(nc * 4 * nq, 128), 128, 0, st>>>(nc, nq, ds.p, dw.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
+                                                            m->d_chart.p, m->radius, dbf.p, bn.p, wsg.p);
+    ctx->launches += 2;
+    GG_CUDA(cudaGetLastError());
+  }
+  GG_CUDA(cudaStreamSynchronize(st));
+}
+
 void adv_create(gg_rk* rk, const gg_rk_args* a) {
   gg_ctx* ctx = rk->ctx;
   gg_mesh* m = rk->mesh;
@@ -272,22 +298,89 @@ void adv_create(gg_rk* rk, const gg_rk_args* a) {
   facet_tables(rk, nq);
   std::vector<double> s(nq), wf(nq);
   gauss_legendre_01(nq, s.data(), wf.data());
-  // wind tabulations
-  auto tab = get_tab(ctx, GG_SPACE_DG, rk->order, nq);
-  DevBuf<double> dbc, dbf, ds, dw;
-  dbc.upload(a->velocity_cells, (size_t)nc * Q * 3, st);
-  dbf.upload(a->velocity_facets, (size_t)nc * 4 * nq * 3, st);
-  ds.upload(s, st); dw.upload(wf, st);
-  rk->adv_bq.alloc((size_t)2 * Q * nc); rk->adv_bn.alloc((size_t)4 * nq * nc); rk->adv_wsg.alloc((size_t)4 * nq * nc);
-  if (nc) {
-    k_adv_cell_wind<<<nblk(nc * Q, 128), 128, 0, st>>>(nc, nq, tab->xi.p, tab->w.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
-                                                      m->d_chart.p, m->radius, dbc.p, rk->adv_bq.p);
-    k_adv_facet_wind<<<nblk(nc * 4 * nq, 128), 128, 0, st>>>(nc, nq, ds.p, dw.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
-                                                            m->d_chart.p, m->radius, dbf.p, rk->adv_bn.p, rk->adv_wsg.p);
-    ctx->launches += 2;
-    GG_CUDA(cudaGetLastError());
+  adv_wind_tables(m, rk->order, nq, a->velocity_cells, a->velocity_facets, rk->adv_bq, rk->adv_bn, rk->adv_wsg);
+  (void)Q; (void)s; (void)wf; (void)st; (void)nc;
+}
+
+// ---- assembled operator (the tutorial marches implicitly: jac = a + b + s, test/Tutorials/AdvectionUpwinding.jl:124-131) ----
+// DG pattern with facet coupling: row (c, i) holds the 5 blocks of c and its four facet neighbours, ordered by cell id;
+// every row has exactly 5 M entries, so rowptr is a multiplication and a slot is (rank of the block) * M + j.
+__device__ __forceinline__ void adv_block_ranks(int64_t c, const int32_t* __restrict__ nb, int rank_own_and_nbr[5]) {
+  const int64_t ids[5] = {c, nb[0], nb[1], nb[2], nb[3]};
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    int r = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) r += ids[b] < ids[a];
+    rank_own_and_nbr[a] = r;
   }
-  GG_CUDA(cudaStreamSynchronize(st));
+}
+
+__global__ void k_adv_pattern(int64_t nc, int M, const int32_t* __restrict__ nbr_cell, int32_t* __restrict__ rowptr,
+                              int32_t* __restrict__ colind) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nc * M) return;
+  rowptr[t] = (int32_t)(t * 5 * M);
+  if (t == nc * M) return;
+  const int64_t c = t / M;
+  int rk[5];
+  adv_block_ranks(c, nbr_cell + c * 4, rk);
+  const int64_t ids[5] = {c, nbr_cell[c * 4], nbr_cell[c * 4 + 1], nbr_cell[c * 4 + 2], nbr_cell[c * 4 + 3]};
+  for (int a = 0; a < 5; ++a)
+    for (int j = 0; j < M; ++j) colind[t * 5 * M + rk[a] * M + j] = (int32_t)(ids[a] * M + j);
+}
+
+// one thread per (cell, test function): row of the volume block and of the four facet couplings
+template <int P>
+__global__ void __launch_bounds__(128)
+k_adv_matrix(int64_t nc, int nq, AdvTabs T, const double* __restrict__ bq, const double* __restrict__ bn,
+             const double* __restrict__ wsg, const int32_t* __restrict__ nbr_cell, const int8_t* __restrict__ nbr_edge,
+             const int8_t* __restrict__ is_plus, double* __restrict__ vals) {
+  constexpr int M = (P + 1) * (P + 1);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * M) return;
+  const int64_t c = t / M;
+  const int i = (int)(t - c * M);
+  double own[M], nbr[4][M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) { own[j] = 0.0; nbr[0][j] = 0.0; nbr[1][j] = 0.0; nbr[2][j] = 0.0; nbr[3][j] = 0.0; }
+  const int Q = nq * nq;
+#pragma unroll 1
+  for (int q = 0; q < Q; ++q) {
+    const double* __restrict__ v = T.val + q * M;
+    const double* __restrict__ d = T.der + q * M * 2;
+    const double g = -(bq[(int64_t)(q * 2) * nc + c] * d[2 * i] + bq[(int64_t)(q * 2 + 1) * nc + c] * d[2 * i + 1]);
+#pragma unroll
+    for (int j = 0; j < M; ++j) own[j] = fma(g, v[j], own[j]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t cn = nbr_cell[c * 4 + e];
+    const int en = nbr_edge[c * 4 + e];
+    const bool plus = is_plus[c * 4 + e];
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+      const double* __restrict__ vh = T.fval + (e * nq + q) * M;
+      const double* __restrict__ vn = T.fval + (en * nq + q) * M;
+      const int64_t oh = (int64_t)(e * nq + q) * nc + c, on = (int64_t)(en * nq + q) * nc + cn;
+      const double bh = bn[oh], bt = bn[on];
+      const double bp = plus ? bh : bt, bm = plus ? bt : bh;
+      const double cp = 0.5 * bp + 0.5 * fabs(bp), cm = -0.5 * bm - 0.5 * fabs(bp);      // d flux / d u_plus, d flux / d u_minus
+      const double f = (plus ? wsg[oh] : -wsg[on]) * vh[i];
+      const double co = f * (plus ? cp : cm), cnb = f * (plus ? cm : cp);
+#pragma unroll
+      for (int j = 0; j < M; ++j) { own[j] = fma(co, vh[j], own[j]); nbr[e][j] = fma(cnb, vn[j], nbr[e][j]); }
+    }
+  }
+  int rk[5];
+  adv_block_ranks(c, nbr_cell + c * 4, rk);
+  double* row = vals + t * 5 * M;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    row[rk[0] * M + j] = own[j];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) row[rk[1 + e] * M + j] = nbr[e][j];
+  }
 }
 
 }  // namespace gg
@@ -295,6 +388,77 @@ void adv_create(gg_rk* rk, const gg_rk_args* a) {
 using namespace gg;
 
 extern "C" {
+
+int gg_pattern_skeleton(gg_space* Q, gg_csr** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(Q && out, GG_ERR_INVALID, "null argument");
+  gg_mesh* m = Q->mesh;
+  GG_REQUIRE(Q->kind == GG_SPACE_DG && m->dim == 2 && Q->constraint == GG_CONSTRAINT_NONE && !m->plan && Q->order <= 2, GG_ERR_UNSUPPORTED,
+             "skeleton patterns are implemented for unconstrained DG-Q0..Q2 spaces on the (unpartitioned) 2-D surface");
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nc = m->n_cells;
+  const int M = Q->ndofs_loc;
+  GG_REQUIRE(nc * M * 5 * M < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "skeleton pattern too large for Int32 offsets");
+  gg_rk tmp;   // only to reuse facet_tables()
+  tmp.ctx = ctx; tmp.mesh = m; tmp.order = Q->order; tmp.mq = M;
+  facet_tables(&tmp, 1);
+  std::vector<int32_t> nb(nc * 4);
+  tmp.adv_nbr_cell.download(nb.data(), ctx->stream);
+  for (int64_t c = 0; c < nc; ++c)
+    for (int a = 0; a < 4; ++a) {
+      GG_REQUIRE(nb[c * 4 + a] != c, GG_ERR_UNSUPPORTED, "a cell is its own facet neighbour");
+      for (int b = a + 1; b < 4; ++b) GG_REQUIRE(nb[c * 4 + a] != nb[c * 4 + b], GG_ERR_UNSUPPORTED, "two facets of a cell lead to the same neighbour");
+    }
+  std::unique_ptr<gg_csr> A(new gg_csr);
+  A->ctx = ctx; A->test = Q; A->trial = Q; A->skeleton = true;
+  A->n_rows = A->n_cols = Q->n_free; A->nnz = nc * M * 5 * M;
+  A->d_rowptr.alloc(A->n_rows + 1); A->d_colind.alloc(A->nnz); A->d_vals.alloc(A->nnz);
+  if (nc) {
+    k_adv_pattern<<<nblk(nc * M + 1, 128), 128, 0, ctx->stream>>>(nc, M, tmp.adv_nbr_cell.p, A->d_rowptr.p, A->d_colind.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaMemsetAsync(A->d_vals.p, 0, A->nnz * sizeof(double), ctx->stream));
+  } else {
+    GG_CUDA(cudaMemsetAsync(A->d_rowptr.p, 0, sizeof(int32_t), ctx->stream));
+  }
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = A.release();
+  GG_API_END
+}
+
+int gg_assemble_advection(gg_space* Q, int32_t degree, const double* velocity_cells, const double* velocity_facets, gg_csr* A) {
+  GG_API_BEGIN
+  GG_REQUIRE(Q && velocity_cells && velocity_facets && A, GG_ERR_INVALID, "null argument");
+  GG_REQUIRE(A->skeleton && A->test == Q, GG_ERR_INVALID, "the matrix must come from gg_pattern_skeleton on the same space");
+  gg_mesh* m = Q->mesh;
+  gg_ctx* ctx = m->ctx;
+  GG_CUDA(cudaSetDevice(ctx->device));
+  const int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  const int64_t nc = m->n_cells;
+  if (nc == 0) return GG_OK;
+  gg_rk tmp;
+  tmp.ctx = ctx; tmp.mesh = m; tmp.order = Q->order; tmp.mq = Q->ndofs_loc;
+  facet_tables(&tmp, nq);
+  adv_wind_tables(m, Q->order, nq, velocity_cells, velocity_facets, tmp.adv_bq, tmp.adv_bn, tmp.adv_wsg);
+  auto tab = get_tab(ctx, GG_SPACE_DG, Q->order, nq);
+  AdvTabs T{tab->val.p, tab->der.p, tmp.adv_fval.p};
+  const unsigned nb = nblk(nc * Q->ndofs_loc, 128);
+  ProfScope ps(ctx, "k_adv_matrix");
+#define GG_ARGS nc, nq, T, tmp.adv_bq.p, tmp.adv_bn.p, tmp.adv_wsg.p, tmp.adv_nbr_cell.p, tmp.adv_nbr_edge.p, tmp.adv_is_plus.p, A->d_vals.p
+  switch (Q->order) {
+    case 0: k_adv_matrix<0><<<nb, 128, 0, ctx->stream>>>(GG_ARGS); break;
+    case 1: k_adv_matrix<1><<<nb, 128, 0, ctx->stream>>>(GG_ARGS); break;
+    case 2: k_adv_matrix<2><<<nb, 128, 0, ctx->stream>>>(GG_ARGS); break;
+    default: throw Error(GG_ERR_UNSUPPORTED, "DG advection order must be <= 2");
+  }
+#undef GG_ARGS
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+  GG_API_END
+}
 
 int gg_skeleton_points(gg_mesh* m, int32_t degree, int32_t* n_pts, double* xyz) {
   GG_API_BEGIN

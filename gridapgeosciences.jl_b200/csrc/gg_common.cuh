@@ -247,6 +247,7 @@ struct gg_csr {
   gg_space* test = nullptr;
   gg_space* trial = nullptr;
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  bool skeleton = false;         // DG pattern with facet-neighbour coupling (gg_pattern_skeleton): filled by gg_assemble_advection only
   gg::DevBuf<int32_t> d_rowptr;  // [n_rows+1]
   gg::DevBuf<int32_t> d_colind;  // [nnz]
   gg::DevBuf<double> d_vals;     // [nnz]

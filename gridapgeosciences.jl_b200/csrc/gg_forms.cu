@@ -904,6 +904,7 @@ int gg_assemble_matrix(gg_form form, const gg_form_args* args, gg_csr* A, int ad
   GG_REQUIRE(A, GG_ERR_INVALID, "null matrix");
   Plan P = make_plan(form, args, true);
   GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
+  GG_REQUIRE(!A->skeleton, GG_ERR_INVALID, "skeleton patterns are filled by gg_assemble_advection");
   FillPipe pipe{A, P.scale, add};
   int layout = compute_element_matrices(form, args, P, false, nullptr, &pipe);
   if (layout >= 0) gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, add);

@@ -186,6 +186,12 @@ void gg_vec_destroy(gg_vec* v);
  * (radix sort + run-length of the (row, col) pairs of all cells); also builds the slot -> contributing
  * (cell, local pair) lists used by the atomic-free numeric phase.  Columns are sorted inside each row. */
 int gg_pattern(gg_space* test, gg_space* trial, gg_csr** out);
+/* DG pattern with facet-neighbour coupling (SkeletonTriangulation terms): every row couples its cell with the four cells across
+ * its facets (test/Tutorials/AdvectionUpwinding.jl:124-131 assembles jac = a + b + s on it for the implicit march) */
+int gg_pattern_skeleton(gg_space* dg_space, gg_csr** out);
+/* values of jac(u, du, v) = a(du,v) + b(du,v) + s(du,v), the DG upwind advection operator (volume + skeleton terms), for the
+ * ambient wind given at gg_quadrature_points [n_cells][Q][3] and gg_skeleton_points [n_cells][4][nqf][3] */
+int gg_assemble_advection(gg_space* dg_space, int32_t degree, const double* velocity_cells, const double* velocity_facets, gg_csr* A);
 int gg_csr_info(gg_csr* A, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
 /* index_base 0 or 1.  Any of rowptr/colind/vals may be NULL to skip it. */
 int gg_csr_export(gg_csr* A, int64_t* rowptr, int64_t* colind, double* vals, int index_base);

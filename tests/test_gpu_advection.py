@@ -65,3 +65,32 @@ def test_solid_body_rotation_returns_the_initial_bump(gg):
     st.step(nsteps)
     e = gg.norm(st.get_state() - x0, Q, 8) / gg.norm(x0, Q, 8)
     assert e < 2e-3, e
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (3, 2), (4, 0)])
+def test_assembled_operator_with_skeleton_pattern_matches_oracle(gg, n, p):
+    """jac = a + b + s (test/Tutorials/AdvectionUpwinding.jl:124-131) on the facet-coupled DG pattern; the matrix-free residual of
+    the explicit stepper is the product with it."""
+    from oracle import advection as oadv
+    from oracle.mesh import CubedSphereMesh2D
+    degree = 4 * max(p, 1)
+    wind = lambda X: np.stack([-X[..., 1], X[..., 0] + 0.2 * X[..., 2], 0.1 * X[..., 0]], -1)   # noqa: E731
+    mesh = CubedSphereMesh2D(n)
+    P = oadv.AdvectionProblem(mesh, p, wind, degree=degree)
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="L2")
+    op = gg.AdvectionOperator(model, p, wind, degree=degree)
+    A = gg.assemble_advection_matrix(op, Q)
+    M = (p + 1) ** 2
+    assert A.nnz == model.num_cells * M * 5 * M
+    S = A.to_scipy()
+    S.sort_indices()
+    Ao = P.A.tocsr()
+    # the oracle's pattern is the set of structurally coupled pairs too; compare as dense-free sparse difference
+    D = (S - Ao).tocsr()
+    assert (np.abs(D.data).max() if D.nnz else 0.0) <= 1e-12 * np.abs(Ao.data).max()
+    rp, ci = A.pattern()
+    assert (np.diff(rp) == 5 * M).all() and all((np.diff(ci[rp[r]:rp[r + 1]]) > 0).all() for r in range(0, len(rp) - 1, 7))
+    u = np.random.default_rng(4).standard_normal(Q.num_free_dofs)
+    st = gg.RKStepper(gg.RungeKutta(None, None, 1e-3, "EXRK_SSP_3_3"), op)
+    assert np.abs(st.residual(u) - S @ u).max() <= 1e-12 * np.abs(S @ u).max()
