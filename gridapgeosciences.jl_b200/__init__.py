@@ -59,6 +59,10 @@ class Context:
     def launches(self):
         return int(self.lib.gg_launch_count(self.h))
 
+    def set_geometry_classes(self, enabled=True):
+        """One Laplace-Beltrami element matrix per geometry class instead of per cell (same numbers; see geosgpu.h)."""
+        _lib.check(self.lib.gg_set_geometry_classes(self.h, 1 if enabled else 0))
+
     def set_async(self, enabled=True):
         _lib.check(self.lib.gg_set_async(self.h, 1 if enabled else 0))
 

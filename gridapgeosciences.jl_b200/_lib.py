@@ -65,6 +65,7 @@ SIGNATURES = {
     "gg_stream": (C.c_void_p, [_P]),
     "gg_synchronize": (C.c_int, [_P]),
     "gg_launch_count": (_I64, [_P]),
+    "gg_set_geometry_classes": (C.c_int, [_P, C.c_int]),
     "gg_set_async": (C.c_int, [_P, C.c_int]),
     "gg_profile_enable": (C.c_int, [_P, C.c_int]),
     "gg_profile_query": (C.c_int, [_P, C.c_char_p, _PI64, _PD]),

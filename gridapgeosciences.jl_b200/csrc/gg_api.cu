@@ -56,6 +56,7 @@ int gg_init(int device_id, gg_ctx** out) {
     GG_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
   }
   for (auto& e : ctx->ev_batch) GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  ctx->geometry_classes = getenv("GG_LB_CLASSES") && getenv("GG_LB_CLASSES")[0] == '1';
   GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   *out = ctx.release();
   GG_API_END
@@ -98,6 +99,13 @@ int gg_set_async(gg_ctx* ctx, int enabled) {
   GG_API_BEGIN
   GG_REQUIRE(ctx, GG_ERR_INVALID, "null context");
   ctx->async = enabled != 0;
+  GG_API_END
+}
+
+int gg_set_geometry_classes(gg_ctx* ctx, int enabled) {
+  GG_API_BEGIN
+  GG_REQUIRE(ctx, GG_ERR_INVALID, "null context");
+  ctx->geometry_classes = enabled != 0;
   GG_API_END
 }
 

@@ -112,6 +112,7 @@ struct gg_ctx {
   int64_t ebe_key = -1;  // (order, nq) of the pair tables resident in gg_ebe.cu's __constant__ block
   // when set, assembly / solver entry points enqueue their work and return without synchronising the stream
   bool async = false;
+  bool geometry_classes = false;   // Laplace-Beltrami assembly computes one element matrix per geometry class (gg_set_geometry_classes)
   // optional per-kernel CUDA-event timing (gg_profile_*): name -> (events, count)
   bool profile = false;
   struct ProfEntry { std::string name; cudaEvent_t a, b; };
@@ -164,6 +165,12 @@ struct gg_mesh {
   gg::DevBuf<double> d_xlo, d_xh, d_ylo, d_yh;
   gg::DevBuf<int32_t> d_ix, d_iy;
   std::vector<int32_t> h_ix, h_iy;     // host copies (geometry classes of the condensed mass operators, gg_ebe.cu)
+  // geometry classes: cells with the same (x-interval, y-interval) pair have the same chart box, hence the same intrinsic
+  // element matrices (the metric depends on the chart point only; on the cubed sphere every class occurs on all 6 panels)
+  bool classes_built = false;
+  int64_t n_classes = 0;
+  std::vector<int32_t> cls, cls_rep;   // cell -> class (numbered by first occurrence), class -> representative cell
+  gg::DevBuf<int32_t> d_cls, d_cls_rep;
   struct TanTab { gg::DevBuf<double> tx, ty; };
   std::map<int, std::shared_ptr<TanTab>> tan_tabs;
   bool topology_built = false;
@@ -312,6 +319,7 @@ struct CellGeo {
   double radius;
 };
 CellGeo cell_geo(gg_mesh* m, int nq);
+void mesh_geometry_classes(gg_mesh* m);   // fills cls / cls_rep / n_classes (2-D meshes with a device)
 // host-side construction shared with the partition plans (gg_dist.cu); ctx == nullptr gives a host-only mesh
 gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius, int ordering = 0);
 void upload_geometry(gg_mesh* m);

@@ -822,17 +822,8 @@ static void ebe_compress(EbeSolver* s) {
   gg_ctx* ctx = s->ctx;
   const int64_t nc = s->nc;
   if (off || sp->kind != GG_SPACE_RT || m->dim != 2 || (int64_t)m->h_ix.size() != nc || nc == 0) return;
-  std::vector<int32_t> cls(nc), rep;
-  {
-    std::unordered_map<int64_t, int32_t> seen;
-    seen.reserve((size_t)nc);
-    for (int64_t c = 0; c < nc; ++c) {
-      const int64_t key = (int64_t)m->h_iy[c] * m->n_xint + m->h_ix[c];
-      auto it = seen.find(key);
-      if (it == seen.end()) { it = seen.emplace(key, (int32_t)rep.size()).first; rep.push_back((int32_t)c); }
-      cls[c] = it->second;
-    }
-  }
+  mesh_geometry_classes(m);
+  const std::vector<int32_t>&cls = m->cls, &rep = m->cls_rep;
   const int64_t ns = (int64_t)rep.size();
   if (2 * ns > nc) return;   // nothing to gain
   cudaStream_t st = ctx->stream;

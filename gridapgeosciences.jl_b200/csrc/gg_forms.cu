@@ -386,6 +386,25 @@ static void launch_lb_fast(gg_ctx* ctx, int64_t nc, int64_t c0, int64_t c1, cons
   GG_CUDA(cudaGetLastError());
 }
 
+// geometry-class mode: one element matrix per class (representative cells), residual from the class matrices
+template <int NB, int NQ>
+static void launch_lb_classes(gg_ctx* ctx, gg_mesh* m, const CellGeo& g, const int32_t* dofs, const double* u, double dir,
+                              double* ebuf, double* vbuf) {
+  const int64_t ncls = m->n_classes, nc = m->n_cells;
+  {
+    ProfScope ps(ctx, "k_lb_fast");
+    k_lb_fast<NB, NQ, false, true><<<nblk(ncls, 128), 128, 0, ctx->stream>>>(ncls, 0, ncls, g, nullptr, nullptr, 0.0, ebuf, nullptr,
+                                                                            m->d_cls_rep.p);
+    ctx->launches++;
+  }
+  if (vbuf) {
+    ProfScope ps(ctx, "k_lb_residual_classes");
+    k_lb_residual_classes<NB><<<nblk(nc, 128), 128, 0, ctx->stream>>>(nc, ncls, m->d_cls.p, ebuf, dofs, u, dir, vbuf);
+    ctx->launches++;
+  }
+  GG_CUDA(cudaGetLastError());
+}
+
 // When set, the CSR fill is pipelined behind the element kernel: the cells are cut into gg_csr::N_BATCH batches; as soon
 // as batch b has been computed (event on the main stream) the chunks it completes are gathered on the second stream
 // while the FP64-bound element kernel proceeds with batch b+1 (the two kernels use complementary resources).
@@ -427,6 +446,22 @@ static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int
   // the highest priority -- the co-resident fill CTAs slow the FP64-bound element kernel more than the overlap gains, so the
   // pipeline stays off unless GG_PIPELINE=1 is exported (GG_PIPELINE_BATCHES, GG_PIPELINE_ROOM select the variant).
   static const bool want_pipeline = getenv("GG_PIPELINE") && getenv("GG_PIPELINE")[0] == '1';
+  if (pipe && ctx->geometry_classes && !extrinsic) {
+    // Opt-in (gg_set_geometry_classes): cells with the same chart box share their intrinsic element matrix -- on the cubed
+    // sphere every (column, row) pair occurs on all 6 panels -- so the FP64-bound element kernel runs on one representative per
+    // class and the CSR fill reads the (L2-resident) class matrices.  Same numbers bit for bit, recomputed on every call.
+    mesh_geometry_classes(m);
+    if (2 * m->n_classes <= nc) {
+#define GG_CASE(NB_, NQ_) \
+  if (order + 1 == NB_ && nq == NQ_) { launch_lb_classes<NB_, NQ_>(ctx, m, g, dofs, u, dir, ebuf, vbuf); } else
+      GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
+      GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
+      throw Error(GG_ERR_UNSUPPORTED, "no fast Laplace-Beltrami kernel for this (order, degree)");
+#undef GG_CASE
+      gather_matrix(pipe->A, 2, ebuf, pipe->scale, pipe->add);
+      return;
+    }
+  }
   if (!pipe || !want_pipeline || nc < 64 * 1024 || ctx->profile) {
     // default, small meshes (launch-bound) and per-kernel profiling runs: one element launch, one fill launch
     run_lb_fast_range(m, order, nq, extrinsic, 0, nc, g, dofs, u, dir, ebuf, vbuf);

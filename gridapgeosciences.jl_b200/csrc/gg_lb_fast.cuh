@@ -56,16 +56,20 @@ __global__ void k_tan_table(int64_t n_int, int nq, const double* __restrict__ lo
 }
 
 // EXTRINSIC: geometry from the 2x3 Jacobian of ambient o chart (pseudo-determinant path) instead of the analytic metric
-template <int NB, int NQ, bool EXTRINSIC>
+// CLS: geometry-class mode -- thread t computes the element matrix of the representative cell cell_list[t] of class t and
+// stores it in slot t of a buffer with `nc` = number of classes planes stride (no residual in this mode)
+template <int NB, int NQ, bool EXTRINSIC, bool CLS = false>
 __global__ void __launch_bounds__(128, 3)
 k_lb_fast(int64_t nc, int64_t c0, int64_t c1, CellGeo g, const int32_t* __restrict__ cell_dofs,
-          const double* __restrict__ u, double dirichlet, double* __restrict__ ebuf, double* __restrict__ vbuf) {
+          const double* __restrict__ u, double dirichlet, double* __restrict__ ebuf, double* __restrict__ vbuf,
+          const int32_t* __restrict__ cell_list = nullptr) {
   constexpr int M = NB * NB, NS = NB * (NB + 1) / 2, NP = M * (M + 1) / 2;
   constexpr int ROW = 2 * NS + M;  // doubles per abscissa in c_lb
   constexpr int ONN = 0, ODD = NS, OND = 2 * NS;
   // cells [c0, c1) of the nc cells of the mesh (the numeric phase is pipelined over cell batches)
-  int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= c1) return;
+  const int64_t slot = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= c1) return;
+  const int64_t c = CLS ? (int64_t)cell_list[slot] : slot;
   const double HX = g.hx[c], HY = g.hy[c];
   const double rx = HY / HX, ry = HX / HY;
   const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * NQ;
@@ -141,9 +145,9 @@ k_lb_fast(int64_t nc, int64_t c0, int64_t c1, CellGeo g, const int32_t* __restri
   // coalesced entry-major store of the packed element matrix
   if (ebuf) {
 #pragma unroll
-    for (int p = 0; p < NP; ++p) ebuf[(int64_t)c_plane[p] * nc + c] = acc[p];
+    for (int p = 0; p < NP; ++p) ebuf[(int64_t)c_plane[p] * nc + slot] = acc[p];
   }
-  if (vbuf) {
+  if (!CLS && vbuf) {
     // fused residual r_e = Ke u_e (u gathered through the cell DOF ids; lexicographic <-> Gridap local order)
     double ue[M], re[M];
 #pragma unroll
@@ -164,6 +168,37 @@ k_lb_fast(int64_t nc, int64_t c0, int64_t c1, CellGeo g, const int32_t* __restri
 #pragma unroll
     for (int I = 0; I < M; ++I) vbuf[(int64_t)c_lex2loc[I] * nc + c] = re[I];
   }
+}
+
+// Residual r_e = Ke u_e from the element matrices stored once per geometry class (symmetric packed, entry-major [plane][class])
+template <int NB>
+__global__ void __launch_bounds__(128)
+k_lb_residual_classes(int64_t nc, int64_t ncls, const int32_t* __restrict__ cls, const double* __restrict__ ebuf,
+                      const int32_t* __restrict__ cell_dofs, const double* __restrict__ u, double dirichlet,
+                      double* __restrict__ vbuf) {
+  constexpr int M = NB * NB;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int64_t k = cls[c];
+  double ue[M], re[M];
+#pragma unroll
+  for (int I = 0; I < M; ++I) {
+    const int32_t d = cell_dofs[c * M + c_lex2loc[I]];
+    ue[I] = d >= 0 ? u[d] : dirichlet;
+    re[I] = 0.0;
+  }
+  int p = 0;
+#pragma unroll
+  for (int I = 0; I < M; ++I)
+#pragma unroll
+    for (int J = I; J < M; ++J) {
+      const double v = ebuf[(int64_t)c_plane[p] * ncls + k];
+      re[I] = fma(v, ue[J], re[I]);
+      if (J != I) re[J] = fma(v, ue[I], re[J]);
+      ++p;
+    }
+#pragma unroll
+  for (int I = 0; I < M; ++I) vbuf[(int64_t)c_lex2loc[I] * nc + c] = re[I];
 }
 
 // Matrix-free action r_e = a(u_h, phi_I) by sum factorisation, never forming Ke (3 contractions per abscissa)

@@ -535,6 +535,31 @@ static void finish_space(gg_space* s) {
 }  // extern "C"
 
 namespace gg {
+void mesh_geometry_classes(gg_mesh* m) {
+  if (m->classes_built) return;
+  const int64_t nc = m->n_cells;
+  m->cls.assign(nc, 0); m->cls_rep.clear();
+  if ((int64_t)m->h_ix.size() == nc && m->dim == 2) {
+    std::unordered_map<int64_t, int32_t> seen;
+    seen.reserve((size_t)nc);
+    for (int64_t c = 0; c < nc; ++c) {
+      const int64_t key = (int64_t)m->h_iy[c] * m->n_xint + m->h_ix[c];
+      auto it = seen.find(key);
+      if (it == seen.end()) { it = seen.emplace(key, (int32_t)m->cls_rep.size()).first; m->cls_rep.push_back((int32_t)c); }
+      m->cls[c] = it->second;
+    }
+  } else {
+    m->cls_rep.resize(nc);
+    for (int64_t c = 0; c < nc; ++c) { m->cls[c] = (int32_t)c; m->cls_rep[c] = (int32_t)c; }
+  }
+  m->n_classes = (int64_t)m->cls_rep.size();
+  if (m->ctx) {
+    m->d_cls.upload(m->cls, m->ctx->stream); m->d_cls_rep.upload(m->cls_rep, m->ctx->stream);
+    GG_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  }
+  m->classes_built = true;
+}
+
 // Builtin numbering (our restatement of Gridap's) on the host arrays of `m`
 void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s) {
   s->mesh = m; s->kind = kind; s->order = order; s->constraint = constraint;

@@ -156,8 +156,10 @@ void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, i
 // is still summed in the same fixed order: deterministic and atomic-free.
 constexpr int GATHER_CHUNK = 2048;
 
+// layout 2: symmetric packed planes with one column per geometry CLASS (stride ncls, column cls[cell]) instead of per cell
 __global__ void k_chunk_keys(int64_t n, int64_t nnz, int64_t nc, int mt, int mu, int layout, const int32_t* __restrict__ sptr,
-                             const int32_t* __restrict__ raw, uint64_t* __restrict__ keys, uint16_t* __restrict__ lslot) {
+                             const int32_t* __restrict__ raw, uint64_t* __restrict__ keys, uint16_t* __restrict__ lslot,
+                             int64_t ncls, const int32_t* __restrict__ cls) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   // slot of source position t: last slot with sptr[slot] <= t
@@ -172,12 +174,12 @@ __global__ void k_chunk_keys(int64_t n, int64_t nnz, int64_t nc, int mt, int mu,
   int mm = mt * mu;
   int64_t c = p / mm;
   int ij = (int)(p - c * mm);
-  if (layout == 1) {
+  if (layout >= 1) {
     int i = ij / mu, j = ij - i * mu;
     int a = min(i, j), b = max(i, j);
     ij = a * mu - (a * (a - 1)) / 2 + (b - a);
   }
-  uint64_t src = (uint64_t)((int64_t)ij * nc + c);
+  uint64_t src = layout == 2 ? (uint64_t)((int64_t)ij * ncls + cls[c]) : (uint64_t)((int64_t)ij * nc + c);
   uint64_t chunk = (uint64_t)(slot / GATHER_CHUNK);
   keys[t] = (chunk << 35) | ((uint64_t)min(round, 15) << 31) | src;
   lslot[t] = (uint16_t)(slot - (int64_t)chunk * GATHER_CHUNK);
@@ -282,8 +284,11 @@ static void build_chunk_lists(gg_csr* A, int layout) {
   GG_REQUIRE(R >= 1 && R <= 15, GG_ERR_UNSUPPORTED, "a matrix entry has more than 15 cell contributions");
   DevBuf<uint64_t> k0(n), k1(n);
   DevBuf<uint16_t> v0(n), v1(n);
-  k_chunk_keys<<<nblk(n, 256), 256, 0, st>>>(n, nnz, A->test->mesh->n_cells, A->test->ndofs_loc, A->trial->ndofs_loc, layout,
-                                             A->d_sptr.p, A->d_ssrc.p, k0.p, v0.p);
+  gg_mesh* mesh = A->test->mesh;
+  if (layout == 2) mesh_geometry_classes(mesh);
+  k_chunk_keys<<<nblk(n, 256), 256, 0, st>>>(n, nnz, mesh->n_cells, A->test->ndofs_loc, A->trial->ndofs_loc, layout,
+                                             A->d_sptr.p, A->d_ssrc.p, k0.p, v0.p, layout == 2 ? mesh->n_classes : 0,
+                                             layout == 2 ? mesh->d_cls.p : nullptr);
   cub::DoubleBuffer<uint64_t> dk(k0.p, k1.p);
   cub::DoubleBuffer<uint16_t> dv(v0.p, v1.p);
   size_t tmp_bytes = 0;
@@ -312,6 +317,7 @@ static void build_chunk_lists(gg_csr* A, int layout) {
     ctx->launches++;
     std::vector<int32_t> cb(nchunks), order(nchunks);
     d_cb.download(cb.data(), st);
+    if (layout == 2) std::fill(cb.begin(), cb.end(), 0);   // class-indexed sources: no cell batches
     std::vector<int64_t> cnt(NBt + 1, 0);
     for (int64_t i = 0; i < nchunks; ++i) cnt[cb[i] + 1]++;
     for (int b2 = 0; b2 < NBt; ++b2) cnt[b2 + 1] += cnt[b2];

@@ -63,6 +63,11 @@ int64_t gg_launch_count(gg_ctx* ctx);
 /* async != 0: assembly / SpMV entry points enqueue their kernels on gg_stream() and return without synchronising
  * (the RK stage loop and bench.py's device-resident timing); results are complete after gg_synchronize(). */
 int gg_set_async(gg_ctx* ctx, int enabled);
+/* Opt-in: the fused Laplace-Beltrami assembly (gg_assemble_matrix / gg_assemble_matrix_and_vector, intrinsic form, Q1 / Q2)
+ * computes one element matrix per GEOMETRY CLASS -- cells with the same chart box; every (column, row) pair of the cubed sphere
+ * occurs on all 6 panels -- instead of one per cell; the CSR fill and the residual read the class matrices.  Results are bit
+ * for bit those of the per-cell path and are recomputed on every call.  Off by default (also GG_LB_CLASSES=1). */
+int gg_set_geometry_classes(gg_ctx* ctx, int enabled);
 /* measurement hooks: per-kernel CUDA-event timing on the context's stream (names: "k_lb_fast",
  * "k_lb_action_fast", "k_gather_chunks", "k_gather_dofs"), and an FP64-FMA throughput probe (the roofline
  * denominator of the FP64-bound element kernels; MEASURED_PEAKS.json has no FP64 figure). */

@@ -285,3 +285,29 @@ def test_recursive_and_morton_cell_orderings(gg, ordering):
     assert np.abs((A0 - A1).data).max() < 1e-13 * np.abs(A0.data).max()          # Q1 DOFs are the nodes: identical numbering
     with pytest.raises(gg.GGError):
         gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=6, ordering=ordering)
+
+
+@pytest.mark.parametrize("n,p,degree", [(4, 2, 18), (6, 1, 12), (5, 2, 8)])
+def test_geometry_class_assembly_is_bitwise_the_per_cell_assembly(gg, n, p, degree):
+    """gg_set_geometry_classes: one element matrix per (column, row) class of the 6 congruent panels; values and residual are
+    bit for bit those of the per-cell path, for repeated calls with different states."""
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.3), n=n)
+    V = gpu_spaces(gg, model, "CG", p, constraint="zeromean")
+    dΩ = gg.Measure(gg.Triangulation(model), degree)
+    assem = gg.SparseMatrixAssembler(V, V)
+    rng = np.random.default_rng(7)
+    ctx = model.ctx
+    try:
+        for _ in range(2):
+            u = rng.standard_normal(V.num_free_dofs)
+            ctx.set_geometry_classes(False)
+            A, b = gg.assemble_matrix_and_vector(gg.LaplaceBeltrami(dΩ, u=u, dirichlet=0.4), assem)
+            v0, b0 = A.values().copy(), b.get().copy()
+            ctx.set_geometry_classes(True)
+            A, b = gg.assemble_matrix_and_vector(gg.LaplaceBeltrami(dΩ, u=u, dirichlet=0.4), assem)
+            assert (A.values() == v0).all()
+            assert np.abs(b.get() - b0).max() <= 1e-15 * np.abs(b0).max()
+            A2 = gg.assemble_matrix(gg.LaplaceBeltrami(dΩ), assem)
+            assert (A2.values() == v0).all()
+    finally:
+        ctx.set_geometry_classes(False)
