@@ -479,14 +479,14 @@ def main():
         "frac_executed": ((2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60) * ncell_local / (k_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-        # command (profiles/ncu_lb_assembly_r01_final.txt: 151.3 MB for 393 216 cells = 384.8 B/cell), scaled to this launch
-        "traffic": 384.8 * ncell_local, "traffic_unit": "bytes per launch (ncu, round 1 capture)",
-        "fp64_pipe_active_pct_ncu": 81.2,
+        # command (profiles/ncu_lb_assembly_r01_final.txt: 148.8 MB for 393 216 cells = 378.4 B/cell), scaled to this launch
+        "traffic": 378.4 * ncell_local, "traffic_unit": "bytes per launch (ncu, round 1 capture)",
+        "fp64_pipe_active_pct_ncu": 81.3,
         "csr_fill": {"kernel": "k_gather_chunks", "bound": "hbm", "unit": "GB/s", "kernel_ms": g_ms,
                      "achieved": gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None, "peak": hbm_peak,
                      "frac": gather_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "traffic": 1332.9 * ncell_local, "traffic_note": "ncu: 524 MB per launch at 393 216 cells, of which 190 MB gather lists"},
+                     "traffic": 1462.8 * ncell_local, "traffic_note": "ncu: 575 MB per launch at 393 216 cells (5.06 TB/s = 78 % of the measured copy bandwidth), of which 190 MB gather lists"},
     }
 
     line = {
