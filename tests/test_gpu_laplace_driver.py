@@ -159,3 +159,37 @@ def test_hodge_laplacian_scalar_driver_convergence(gg):
             assert abs(eu[-1] - eu_ref) <= 1e-8 * eu_ref and abs(ep[-1] - ep_ref) <= 1e-8 * ep_ref
     lv = np.log10([1 / 2.0**lvl for lvl in (1, 2, 3)])
     assert np.polyfit(lv, np.log10(eu), 1)[0] >= 2 and np.polyfit(lv, np.log10(ep), 1)[0] >= 2
+
+
+def test_error_behaviour_of_the_driver_hooks(gg):
+    """Wrong sizes / unsupported requests return error codes (GGError), never garbage."""
+    model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=2)
+    dΩ = gg.Measure(gg.Triangulation(model), 6)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="H1")
+    W = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, 1), conformity="H1")
+    Q = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="L2")
+    u = np.zeros(V.num_free_dofs)
+    with pytest.raises(gg.GGError):
+        gg.l2_error(u, V, dΩ, fq=np.zeros(7))                               # f at the wrong number of points
+    with pytest.raises(gg.GGError):
+        gg.l2_error(np.zeros(3), V, dΩ)                                     # DOF vector of the wrong length
+    with pytest.raises(gg.GGError):
+        gg.assemble_vector(gg.VectorSource(dΩ, np.zeros(model.num_cells * dΩ.num_points)), W)   # one component only
+    with pytest.raises(gg.GGError):
+        gg.assemble_matrix(gg.VectorMass(dΩ), V, V)                         # scalar space under the vector form
+    with pytest.raises(gg.GGError):
+        gg.change_of_basis(V)                                               # only vector H1 spaces carry one
+    with pytest.raises(ValueError):
+        gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, 1), conformity="L2")
+    with pytest.raises(gg.GGError):
+        gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, 3), conformity="H1")  # order 3 not built
+    with pytest.raises(gg.GGError):
+        gg.CSRMatrix(V, V, skeleton=True)                                   # skeleton patterns are for DG spaces
+    A = gg.CSRMatrix(Q, Q, skeleton=True)
+    with pytest.raises(gg.GGError):
+        gg.lib_check_skeleton_misuse(A, dΩ, Q)                              # generic numeric phase on a skeleton pattern
+    shell = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.1), n=2)
+    with pytest.raises(gg.GGError):
+        gg.surface_laplacian(gg.Measure(gg.Triangulation(shell), 4), grad_fX, hess_fX)      # 2-D surfaces only
+    with pytest.raises(gg.GGError):
+        gg.RKStepper(gg.RungeKutta(None, None, 1e-3, "EXRK_SSP_3_3"), gg.ThermalShallowWaterOperator(model, 3, lambda X: X[..., 2]))
