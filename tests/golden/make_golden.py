@@ -14,7 +14,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle import advection, forms, shell, swe  # noqa: E402
+from oracle import advection, forms, shell, swe, tswe  # noqa: E402
+from oracle import vector_h1  # noqa: E402
 from oracle import rk as ork  # noqa: E402
 from oracle.mesh import CubedSphereMesh2D  # noqa: E402
 from oracle.spaces import CGSpace, DGSpace, RTSpace  # noqa: E402
@@ -76,6 +77,41 @@ def main():
     u = rng.standard_normal(Pa.Q.num_free)
     out["adv_u"], out["adv_res"] = u, Pa.residual(u)
     np.savez_compressed(os.path.join(HERE, "shell_advection.npz"), **out)
+    # 4. next-row callers: thermal shallow water, vector H1 space, closed-form surface operators, assembled advection operator
+    out = {}
+    mesh = CubedSphereMesh2D(3, 1.0)
+    T = tswe.ThermalShallowWaterProblem(mesh, 1)
+    x0 = T.initial_state() * (1 + 1e-2 * np.cos(np.arange(T.nu + 2 * T.np_)))
+    dt = 0.01
+    T.dt, T.tau = dt, dt / 2
+    y0 = T.diagnostics(x0)
+    out["tswe_x0"], out["tswe_y0"], out["tswe_res0"], out["tswe_dt"] = x0, y0, T.residual_x(x0, y0, y0), dt
+    out["tswe_x_after_1_step"] = T.step(x0, dt)[0]
+    wX = lambda X: np.stack([X[..., 2] * X[..., 1], -X[..., 0] ** 2, X[..., 0] + 0.3], -1)   # noqa: E731
+    Vv = vector_h1.VectorCGSpace(mesh, 2)
+    q = forms.CellQuadrature(mesh, 12)
+    out["vh1_cell_dofs"], out["vh1_cob"] = Vv.cell_dofs, Vv.cob
+    Av = forms.assemble_matrix(Vv, Vv, vector_h1.mass_element_matrices(Vv, q))
+    out["vh1_mass_indptr"], out["vh1_mass_indices"], out["vh1_mass_data"] = Av.indptr, Av.indices, Av.data
+    out["vh1_interp"] = vector_h1.interpolate(Vv, wX)
+    fX = lambda X: X[..., 0] ** 2 + X[..., 1] ** 2 * X[..., 2]                                 # noqa: E731
+    gfX = lambda X: np.stack([2 * X[..., 0], 2 * X[..., 1] * X[..., 2], X[..., 1] ** 2], -1)    # noqa: E731
+
+    def hfX(X):
+        H = np.zeros(X.shape + (3,))
+        H[..., 0, 0] = 2.0
+        H[..., 1, 1] = 2 * X[..., 2]
+        H[..., 1, 2] = H[..., 2, 1] = 2 * X[..., 1]
+        return H
+    q6 = forms.CellQuadrature(mesh, 6)
+    out["surf_lap"] = forms.surface_laplacian(fX, gfX, hfX, mesh, q6.x, mesh.cell_to_chart)
+    out["surf_grad"] = forms.surface_gradient(gfX, mesh, q6.x, mesh.cell_to_chart)
+    out["surf_div_of_grad"] = forms.surface_divergence(gfX, hfX, mesh, q6.x, mesh.cell_to_chart)
+    Pa = advection.AdvectionProblem(mesh, 1, beta, degree=4)
+    Aa = Pa.A.tocsr()
+    Aa.sort_indices()
+    out["adv_matrix_dense_n3_p1"] = Aa.toarray()
+    np.savez_compressed(os.path.join(HERE, "next_rows_n3.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

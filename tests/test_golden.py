@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from __graft_entry__ import load_package
-from oracle import advection, forms, shell, swe
+from oracle import advection, forms, shell, swe, tswe, vector_h1
 from oracle import rk as ork
 from oracle.mesh import CubedSphereMesh2D
 from oracle.spaces import CGSpace
@@ -27,6 +27,59 @@ def test_oracle_reproduces_the_golden_fixtures():
     assert np.abs(W.residual(t["wave_x"]) - t["wave_res"]).max() < 1e-13 * np.abs(t["wave_res"]).max()
     P = swe.ShallowWaterProblem(CubedSphereMesh2D(3, 1.0), 1)
     assert np.abs(P.diagnostics(t["swe_x0"]) - t["swe_y0"]).max() < 1e-11 * np.abs(t["swe_y0"]).max()
+
+
+def test_oracle_reproduces_the_next_row_fixtures():
+    g = np.load(os.path.join(G, "next_rows_n3.npz"))
+    mesh = CubedSphereMesh2D(3, 1.0)
+    T = tswe.ThermalShallowWaterProblem(mesh, 1)
+    T.dt, T.tau = float(g["tswe_dt"]), float(g["tswe_dt"]) / 2
+    assert np.abs(T.diagnostics(g["tswe_x0"]) - g["tswe_y0"]).max() < 1e-11 * np.abs(g["tswe_y0"]).max()
+    r = T.residual_x(g["tswe_x0"], g["tswe_y0"], g["tswe_y0"])
+    assert np.abs(r - g["tswe_res0"]).max() < 1e-12 * np.abs(g["tswe_res0"]).max()
+    Vv = vector_h1.VectorCGSpace(mesh, 2)
+    assert (Vv.cell_dofs == g["vh1_cell_dofs"]).all() and np.abs(Vv.cob - g["vh1_cob"]).max() < 1e-14
+
+
+_wX = lambda X: np.stack([X[..., 2] * X[..., 1], -X[..., 0] ** 2, X[..., 0] + 0.3], -1)   # noqa: E731
+_gfX = lambda X: np.stack([2 * X[..., 0], 2 * X[..., 1] * X[..., 2], X[..., 1] ** 2], -1)    # noqa: E731
+
+
+def _hfX(X):
+    H = np.zeros(X.shape + (3,))
+    H[..., 0, 0] = 2.0
+    H[..., 1, 1] = 2 * X[..., 2]
+    H[..., 1, 2] = H[..., 2, 1] = 2 * X[..., 1]
+    return H
+
+
+@pytest.mark.gpu
+def test_gpu_against_the_next_row_fixtures():
+    gg = load_package()
+    g = np.load(os.path.join(G, "next_rows_n3.npz"))
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()   # noqa: E731
+    m3 = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=3)
+    st = gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=1e-14), None, float(g["tswe_dt"]), "EXRK_SSP_3_3"),
+                      gg.ThermalShallowWaterOperator(m3, 1, swe.coriolis()))
+    assert rel(st.diagnostics(g["tswe_x0"]), g["tswe_y0"]) < 1e-10
+    assert rel(st.stage_residual(g["tswe_x0"], g["tswe_y0"]), g["tswe_res0"]) < 1e-11
+    st.set_state(g["tswe_x0"])
+    st.step(1)
+    assert rel(st.get_state(), g["tswe_x_after_1_step"]) < 1e-9
+    V = gg.TestFESpace(m3, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, 2), conformity="H1")
+    assert (V.get_cell_dof_ids() - 1 == g["vh1_cell_dofs"]).all() and np.abs(gg.change_of_basis(V) - g["vh1_cob"]).max() < 1e-13
+    A = gg.assemble_matrix(gg.VectorMass(gg.Measure(gg.Triangulation(m3), 12)), V, V).to_scipy()
+    assert (A.indptr == g["vh1_mass_indptr"]).all() and (A.indices == g["vh1_mass_indices"]).all()
+    assert rel(A.data, g["vh1_mass_data"]) < 1e-12
+    assert rel(gg.interpolate(_wX, V).get(), g["vh1_interp"]) < 1e-12
+    d6 = gg.Measure(gg.Triangulation(m3), 6)
+    assert rel(gg.surface_laplacian(d6, _gfX, _hfX).get(), g["surf_lap"].reshape(-1)) < 1e-12
+    assert rel(gg.surface_gradient(d6, _gfX).get(), g["surf_grad"].reshape(-1)) < 1e-12
+    assert rel(gg.surface_divergence(d6, _gfX, _hfX).get(), g["surf_div_of_grad"].reshape(-1)) < 1e-12
+    wind = lambda X: np.stack([-X[..., 1], X[..., 0], 0 * X[..., 0]], -1)   # noqa: E731
+    Q = gg.TestFESpace(m3, gg.ReferenceFE(gg.lagrangian, float, 1), conformity="L2")
+    Aa = gg.assemble_advection_matrix(gg.AdvectionOperator(m3, 1, wind, degree=4), Q).to_scipy().toarray()
+    assert np.abs(Aa - g["adv_matrix_dense_n3_p1"]).max() < 1e-12 * np.abs(g["adv_matrix_dense_n3_p1"]).max()
 
 
 @pytest.mark.gpu
