@@ -308,7 +308,12 @@ __global__ void k_copy(int64_t n, const double* __restrict__ a, double* __restri
 // dynamic shared memory of the two-pass cell kernels: 2 coefficients per point and thread; 0 = stage through global memory
 static size_t swe_stage_smem(gg_rk* rk, int threads) {
   const size_t bytes = (size_t)2 * rk->nq1 * rk->nq1 * threads * sizeof(double);
-  if (bytes > 96 * 1024) {
+  // Staging through shared memory only below GG_SWE_STAGE_KB per CTA (default 36): at 7x7 points the buffer is 50 KB per
+  // 64-thread CTA, which caps the residency at 4 CTAs per SM while the registers allow 6; staging through a global scratch
+  // ([point][component][cell], coalesced, 1.5 KB more traffic per cell on kernels that use 17 % of the bandwidth) measured
+  // 2.35 -> 2.14 ms (k_swe_diag) and 2.47 -> 2.09 ms (k_swe_stage) per step at 256^2, order 2.
+  static const size_t limit = [] { const char* e = getenv("GG_SWE_STAGE_KB"); return (size_t)(e ? atoi(e) : 36) * 1024; }();
+  if (bytes > limit) {
     if (rk->stage2.n == 0) rk->stage2.alloc((size_t)2 * rk->nq1 * rk->nq1 * std::max<int64_t>(rk->mesh->n_cells, 1));
     return 0;
   }
