@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeosgpu.so")
+LIB_PATH = os.environ.get("GG_LIB_PATH") or os.path.join(_HERE, "libgeosgpu.so")   # GG_LIB_PATH: development builds
 
 GG_OK = 0
 ERRORS = {-1: "GG_ERR_INVALID", -2: "GG_ERR_CUDA", -3: "GG_ERR_UNSUPPORTED", -4: "GG_ERR_NOMEM", -5: "GG_ERR_NOCONV"}

@@ -375,13 +375,20 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, doub
 // phase C), the dot products are summed over the ranks in rank order (gg_dist.cuh), and the ghost values are copied from
 // the slot into z after the round -- 2 rounds per iteration, no host, no NCCL.  (z itself stays in ordinary device memory:
 // writing the whole vector into the IPC-exported window made phase C 2x slower on B200.)
+#ifndef GG_EBE_MIN_BLOCKS
+#define GG_EBE_MIN_BLOCKS 2
+#endif
 template <int MB, int MI, bool CLS>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, GG_EBE_MIN_BLOCKS)
 k_pcg_ebe(const EbeArgs a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
   constexpr int MIa = MI > 0 ? MI : 1;
   constexpr int UNR = 4;
+#ifndef GG_EBE_UNRB
+#define GG_EBE_UNRB 4
+#endif
+  constexpr int UNRB = GG_EBE_UNRB;   // rows in flight per thread in the gather phase (latency-bound at 16 warps per SM)
   const int nbk = gridDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
@@ -525,12 +532,12 @@ k_pcg_ebe(const EbeArgs a) {
       tA += t1 - t0;
       // -- B: p = z + beta p ; Ap = gather ; pAp
       double lpap = 0.0;
-      for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
-        int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
-        double pv[UNR], acc[UNR];
-        bool own[UNR];
+      for (int64_t i0 = tid; i0 < n; i0 += UNRB * nth) {
+        int32_t lo[UNRB], hi[UNRB], s0[UNRB], s1[UNRB];
+        double pv[UNRB], acc[UNRB];
+        bool own[UNRB];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNRB; ++u) {
           const int64_t i = i0 + u * nth;
           const bool ok = i < n;
           // the ownership byte is loaded alongside the row data, not ahead of it (no extra dependent-load level);
@@ -540,14 +547,14 @@ k_pcg_ebe(const EbeArgs a) {
           pv[u] = ok ? fma(beta, a.p[i], __ldcg(a.z + i)) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
+        for (int u = 0; u < UNRB; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNRB; ++u) {
           acc[u] = s0[u] >= 0 ? a.ev[s0[u]] : 0.0;
           if (s1[u] >= 0) acc[u] += a.ev[s1[u]];
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < UNRB; ++u) {
           for (int32_t k = lo[u] + 2; k < hi[u]; ++k) acc[u] += a.ev[a.vsrc[k]];
           const int64_t i = i0 + u * nth;
           if (i < n) a.p[i] = pv[u];
