@@ -28,6 +28,7 @@
 #include "gg_rk.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
+#include "gg_dist_host.cuh"
 
 namespace gg {
 
@@ -466,6 +467,7 @@ void swe_step_async(gg_rk* rk) {
     if (i > 0) {
       // :85-88 stage state
       rk_combine(rk, std::min(i, 4), co, rk->xi.p);
+      if (rk->thermal) vec_consistent_async(rk->Q, rk->xi.p + rk->nu + rk->np);   // B on the ghost cells (partitioned models)
       xs = rk->xi.p;
     }
     // :91-93 stage diagnostics (y still holds diagnostics(x) when the stage state is x itself)
@@ -484,6 +486,7 @@ void swe_step_async(gg_rk* rk) {
   double co[4] = {0, 0, 0, 0};
   for (int j = 0; j < s && j < 4; ++j) co[j] = rk->dt * rk->b[j];
   rk_combine(rk, std::min(s, 4), co, rk->x.p);
+  if (rk->thermal) vec_consistent_async(rk->Q, rk->x.p + rk->nu + rk->np);
   rk->diag_slot = s;
   swe_diagnostics_async(rk, rk->x.p, rk->y.p);
   rk->diag_slot = -1;

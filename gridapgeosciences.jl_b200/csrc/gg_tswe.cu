@@ -217,7 +217,9 @@ k_tswe_stage(int64_t nc, int nq, TsweTabs T, const double* __restrict__ hx, cons
 
 void tswe_create(gg_rk* rk) {
   gg_ctx* ctx = rk->ctx;
-  GG_REQUIRE(!rk->mesh->plan, GG_ERR_UNSUPPORTED, "thermal shallow water on partitioned models is not implemented");
+  // Partitioned models: everything is cell-local on consistent data except r_B of a ghost cell (its far neighbours are not
+  // local), so the B block of every stage state is made consistent through the peer windows (swe_step_async); the facet
+  // tables give outer edges of the ghost layer the cell itself as neighbour (their rows are never used).
   const int nq = rk->nq1;
   facet_tables(rk, nq);
   // reference RT normal component at the facet points of the four local edges

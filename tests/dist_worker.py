@@ -113,6 +113,26 @@ def main():
     assert sol == solf
     del st, stf
 
+    # -- thermal shallow water: shallow water + buoyancy skeleton terms; the B block of the stage states goes through the halo
+    if p >= 1:
+        def wb(X):
+            return G * (1.0 + 0.05 * H0 ** 2 / depth(X) ** 2) * depth(X)
+
+        dt = gg.dx(full_model) * 0.05 / np.sqrt(G * H0)
+        rk = gg.RungeKutta(gg.CGSolver(rtol=1e-13), None, dt, "EXRK_SSP_3_3")
+        stt = gg.RKStepper(rk, gg.ThermalShallowWaterOperator(local_model, p, coriolis))
+        sttf = gg.RKStepper(rk, gg.ThermalShallowWaterOperator(full_model, p, coriolis))
+        B0, B0f = gg.interpolate(wb, Q).get(), gg.interpolate(wb, Qf).get()
+        stt.set_state(np.concatenate([x0, B0])); sttf.set_state(np.concatenate([x0f, B0f]))
+        stt.step(nsteps); sttf.step(nsteps)
+        xt, xtf = stt.get_state(), sttf.get_state()
+        nq_ = Q.num_free_dofs
+        e_t = max(rel(xt[: stt.nu], xtf[: sttf.nu][lv]), rel(xt[stt.nu: stt.nu + nq_], xtf[sttf.nu: sttf.nu + Qf.num_free_dofs][lq]),
+                  rel(xt[stt.nu + nq_:], xtf[sttf.nu + Qf.num_free_dofs:][lq]))
+        assert e_t < 1e-9, f"thermal shallow water: partitioned and single-GPU states differ by {e_t}"
+        assert comm.error_epoch() == 0
+        del stt, sttf
+
     # -- DG upwind advection: ghost cells of every stage state filled through peer memory
     def wind(X):
         return np.stack([-X[..., 1], X[..., 0], 0.2 * X[..., 0]], -1)
