@@ -362,7 +362,7 @@ class Measure:
 
     def quadrature_points(self, chart=True, ambient=True):
         m = self.model
-        ch = np.empty((m.num_cells, self.num_points, 2)) if chart else None
+        ch = np.empty((m.num_cells, self.num_points, m.dim)) if chart else None
         xyz = np.empty((m.num_cells, self.num_points, 3)) if ambient else None
         _lib.check(m.lib.gg_quadrature_points(m.h, self.degree, _dp(ch) if chart else None, _dp(xyz) if ambient else None))
         return ch, xyz
@@ -617,6 +617,13 @@ class VectorSource(Form):
         super().__init__(dΩ, qdata=fq, **kw)
 
 
+class ShellBoundaryFlux(Form):
+    """boundary(v) = ∫( ((inv_metric_cf⋅∇(f_int))⋅nΓ)*v*meas_cf )dΓ over the bottom and top boundaries of the shell, f_int = `u`
+    -- the 3-D branch of test/Laplacian/LaplaceBeltrami.jl:58-64."""
+    form_id = _lib.FORM_SHELL_BOUNDARY_FLUX
+    bilinear = False
+
+
 class Source(Form):
     """l(v) = ∫( (f*v)*meas_cf )dΩ with f at the quadrature points -- test/Laplacian/LaplaceBeltrami.jl:53."""
     form_id = _lib.FORM_SOURCE
@@ -720,7 +727,7 @@ def interpolation_points(V, chart=False, ambient=True):
     n = C.c_int32()
     _lib.check(V.lib.gg_space_interp_points(V.h, C.byref(n), None, None))
     nc = V.model.num_cells
-    ch = np.empty((nc, n.value, 2)) if chart else None
+    ch = np.empty((nc, n.value, V.model.dim)) if chart else None
     xyz = np.empty((nc, n.value, 3)) if ambient else None
     _lib.check(V.lib.gg_space_interp_points(V.h, C.byref(n), _dp(ch) if chart else None, _dp(xyz) if ambient else None))
     return ch, xyz
@@ -822,13 +829,23 @@ def chart_mean(uh, V, dirichlet=0.0):
 
 def laplace_beltrami_solver(model, order, f, grad_f, hess_f, degree=None, ls=None):
     """The driver of test/Laplacian/LaplaceBeltrami.jl:19-98 on the device: zero-mean Q_order space, a = LaplaceBeltrami,
-    l = Source(-Δs f), Jacobi-PCG solve, zero-mean shift, L2 error with a degree-2*degree rule.  Returns (error, uh, V, numerical setup)."""
+    l = Source(-Δs f) (+ the boundary term on the 3-D shell), Jacobi-PCG solve, zero-mean shift, L2 error with a
+    degree-2*degree rule.  Returns (error, uh, V, numerical setup)."""
     degree = 6 * (order + 1) if degree is None else degree
     Ω = Triangulation(model)
     dΩ, dΩe = Measure(Ω, degree), Measure(Ω, min(2 * degree, 31))  # device rules stop at 16 points per direction
     V = TestFESpace(model, ReferenceFE(lagrangian, float, order), conformity="H1", constraint="zeromean")
-    rhs = surface_laplacian(dΩ, grad_f, hess_f)
-    op = AffineFEOperator(LaplaceBeltrami(dΩ), Source(dΩ, rhs, scale=-1.0), V, V)
+    if model.dim == 3:
+        # the shell is a flat 3-D domain in curvilinear coordinates: Δs f is the Euclidean Laplacian of f
+        _, xyz = dΩ.quadrature_points(chart=False)
+        rhs = -np.trace(np.broadcast_to(hess_f(xyz), xyz.shape + (3,)), axis1=-2, axis2=-1)
+        op = AffineFEOperator(LaplaceBeltrami(dΩ), Source(dΩ, rhs), V, V)
+        # f_int = interpolate(f, U): only its gradient enters, so the nodal value at the DOF fixed by the zero-mean space is kept
+        Uf = interpolate(f, TestFESpace(model, ReferenceFE(lagrangian, float, order), conformity="H1")).get()
+        assemble_vector(ShellBoundaryFlux(dΩ, u=Uf[:-1], dirichlet=float(Uf[-1])), V, out=op.get_vector(), add=True)
+    else:
+        rhs = surface_laplacian(dΩ, grad_f, hess_f)
+        op = AffineFEOperator(LaplaceBeltrami(dΩ), Source(dΩ, rhs, scale=-1.0), V, V)
     ns = (ls or CGSolver(rtol=1e-13, maxiter=20000)).numerical_setup(op.get_matrix())
     uh = ns.solve(op.get_vector())
     mean = chart_mean(uh, V)

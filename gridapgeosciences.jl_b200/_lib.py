@@ -22,6 +22,7 @@ FORM_MASS_RT = 5
 FORM_DIV = 6
 FORM_SOURCE = 7
 FORM_MASS_VECTOR, FORM_SOURCE_VECTOR = 8, 9
+FORM_SHELL_BOUNDARY_FLUX = 10
 PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
 PROBLEM_ADVECTION = 3

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include "gg_common.cuh"
 #include "gg_vec.cuh"
+#include "gg_hex_ops.cuh"
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
 #include "gg_lb_fast.cuh"
@@ -871,6 +872,19 @@ static double* compute_element_vectors(gg_form form, const gg_form_args* a, cons
   int64_t nc = g.nc;
   double* vb = scratch(ctx->vbuf, (size_t)P.mt * std::max<int64_t>(nc, 1));
   if (nc == 0) return vb;
+  if (P.mesh->dim == 3 && form == GG_FORM_SOURCE) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "the shell source form needs a CG test space");
+    GG_REQUIRE(a->qdata && gg_vec_size(a->qdata) == nc * P.nq * P.nq * P.nq, GG_ERR_INVALID, "source form needs qdata of length n_cells*nq^3");
+    hex_source_vectors(P.test, P.nq, a->qdata->d.p, vb);
+    return vb;
+  }
+  if (P.mesh->dim == 3 && form == GG_FORM_SHELL_BOUNDARY_FLUX) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "the shell boundary form needs a CG test space");
+    GG_REQUIRE(a->u && gg_vec_size(a->u) == P.test->n_free, GG_ERR_INVALID, "args->u missing or of the wrong length");
+    hex_boundary_flux_vectors(P.test, P.nq, a->u->d.p, a->dirichlet, vb);
+    return vb;
+  }
+  GG_REQUIRE(form != GG_FORM_SHELL_BOUNDARY_FLUX, GG_ERR_UNSUPPORTED, "the boundary-flux form exists on the 3-D shell only");
   if (P.mesh->dim == 3) {
     GG_REQUIRE((form == GG_FORM_LAPLACE_BELTRAMI || form == GG_FORM_HELMHOLTZ || form == GG_FORM_MASS_SCALAR) && !a->qdata && P.trial &&
                    P.test->kind == GG_SPACE_CG && P.trial->kind == GG_SPACE_CG && P.test->order == P.trial->order, GG_ERR_UNSUPPORTED,
@@ -1017,10 +1031,15 @@ int gg_element_vectors(gg_form form, const gg_form_args* args, int64_t first_cel
 int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* out_xyz) {
   GG_API_BEGIN
   GG_REQUIRE(m, GG_ERR_INVALID, "null mesh");
-  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "quadrature points of the 3-D shell are not exported");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   int nq = num_points_1d(degree);
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  if (m->dim == 3) {
+    // [n_cells][nq^3][3]: chart (gamma, alpha, beta) / ambient, gamma index fastest
+    hex_points(m, -1, nq, out_chart, out_xyz);
+    return GG_OK;
+  }
   auto T = get_tab(ctx, GG_SPACE_DG, 0, nq);
   int64_t n = m->n_cells * nq * nq;
   if (n == 0) return GG_OK;

@@ -11,6 +11,7 @@
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
 #include "gg_vec.cuh"
+#include "gg_hex_ops.cuh"
 
 namespace gg {
 
@@ -290,9 +291,26 @@ int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* x
   GG_API_BEGIN
   GG_REQUIRE(s, GG_ERR_INVALID, "null space");
   gg_mesh* m = s->mesh;
-  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "interpolation on the 3-D shell is not implemented");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
+  if (m->dim == 3) {
+    // Lagrange nodes of the hexahedra in the LOCAL DOF order of the space
+    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian space");
+    const int ml = s->ndofs_loc;
+    if (n_pts) *n_pts = ml;
+    const int64_t tot = m->n_cells * ml;
+    if ((!chart && !xyz) || tot == 0) return GG_OK;
+    std::vector<double> cl(chart ? 3 * tot : 0), xl(xyz ? 3 * tot : 0);
+    hex_points(m, s->order, 0, chart ? cl.data() : nullptr, xyz ? xl.data() : nullptr);
+    for (int64_t c = 0; c < m->n_cells; ++c)
+      for (int a = 0; a < ml; ++a)
+        for (int d = 0; d < 3; ++d) {
+          const size_t src = ((size_t)c * ml + s->loc2lex[a]) * 3 + d, dst = ((size_t)c * ml + a) * 3 + d;
+          if (chart) chart[dst] = cl[src];
+          if (xyz) xyz[dst] = xl[src];
+        }
+    return GG_OK;
+  }
   std::vector<double> ref = interp_ref_points(s, nullptr);
   int N = (int)(ref.size() / 2);
   if (n_pts) *n_pts = N;
@@ -315,7 +333,6 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && vals && out, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(gg_vec_size(out) == s->n_free, GG_ERR_INVALID, "output vector has the wrong length");
-  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "interpolation on the 3-D shell is not implemented");
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
@@ -323,6 +340,15 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
   int64_t nc = m->n_cells;
   if (s->n_free == 0) return GG_OK;
   build_vec_map(s);
+  if (m->dim == 3) {
+    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian space");
+    DevBuf<double> dv; dv.upload(vals, (size_t)nc * s->ndofs_loc, st);
+    k_interp_pick_scalar<<<nblk(s->n_free, 256), 256, 0, st>>>(s->n_free, nc, s->ndofs_loc, s->d_vptr.p, s->d_vsrc.p, dv.p, out->d.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(st));
+    return GG_OK;
+  }
   std::vector<double> W;
   std::vector<double> ref = interp_ref_points(s, &W);
   int N = (int)(ref.size() / 2);
@@ -360,13 +386,17 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && e && out, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(gg_vec_size(e) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
-  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "norms on the 3-D shell are not implemented");
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   int nq = num_points_1d(degree);
   GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  if (m->dim == 3) {
+    GG_REQUIRE(s->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "norms on the shell are implemented for CG spaces");
+    *out = hex_cell_functional(s, 0, nq, e->d.p, 0.0, nullptr);
+    return GG_OK;
+  }
   int64_t nc = m->n_cells;
   *out = 0.0;
   if (nc == 0) return GG_OK;
@@ -413,8 +443,16 @@ int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const
 int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t degree, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && u && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "L2 errors are implemented on the 2-D surface");
   GG_REQUIRE(gg_vec_size(u) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  if (s->mesh->dim == 3) {
+    GG_REQUIRE(s->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "L2 errors on the shell are implemented for CG spaces");
+    const int nq3 = num_points_1d(degree);
+    GG_REQUIRE(degree >= 0 && nq3 <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+    if (fq) GG_REQUIRE(gg_vec_size(fq) == s->mesh->n_cells * nq3 * nq3 * nq3, GG_ERR_INVALID, "f must be given at the n_cells * nq^3 quadrature points");
+    GG_CUDA(cudaSetDevice(s->mesh->ctx->device));
+    *out = hex_cell_functional(s, 0, nq3, u->d.p, dirichlet, fq ? fq->d.p : nullptr);
+    return GG_OK;
+  }
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
@@ -451,8 +489,15 @@ int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t
 int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out) {
   GG_API_BEGIN
   GG_REQUIRE(s && u && out, GG_ERR_INVALID, "null argument");
-  GG_REQUIRE(s->kind != GG_SPACE_RT && s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "chart means are implemented for Lagrangian spaces on the 2-D surface");
+  GG_REQUIRE(s->kind != GG_SPACE_RT && s->kind != GG_SPACE_CGV, GG_ERR_UNSUPPORTED, "chart means are implemented for scalar Lagrangian spaces");
   GG_REQUIRE(gg_vec_size(u) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
+  if (s->mesh->dim == 3) {
+    GG_REQUIRE(s->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "chart means on the shell are implemented for CG spaces");
+    GG_CUDA(cudaSetDevice(s->mesh->ctx->device));
+    const int nq3 = num_points_1d(2 * s->order);
+    *out = hex_cell_functional(s, 1, nq3, u->d.p, dirichlet, nullptr) / hex_cell_functional(s, 2, nq3, u->d.p, dirichlet, nullptr);
+    return GG_OK;
+  }
   gg_mesh* m = s->mesh;
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));

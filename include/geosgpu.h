@@ -227,7 +227,10 @@ typedef enum {
   /* vector H1: a(u,v) = int (u.(g v)) sqrtg and l(v) = int (f.(g v)) sqrtg with the contravariant field f given at the
    * quadrature points, qdata [n_cells][Q][2] (test/Projection/L2_projection_Lagrangian_vector.jl:41-42) */
   GG_FORM_MASS_VECTOR = 8,
-  GG_FORM_SOURCE_VECTOR = 9
+  GG_FORM_SOURCE_VECTOR = 9,
+  /* 3-D shell: l(v) = int_G ((ginv grad(u_h)).n_G) v sqrtg dG over the bottom and top boundaries, u_h = args->u -- the boundary
+   * term of the integration by parts in the 3-D run of test/Laplacian/LaplaceBeltrami.jl:58-64 (u_h = interpolate(f, U)) */
+  GG_FORM_SHELL_BOUNDARY_FLUX = 10
 } gg_form;
 
 typedef struct {

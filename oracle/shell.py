@@ -152,6 +152,90 @@ def helmholtz_element_matrices(space, quad):
     return mass_element_matrices(space, quad) - lb_element_matrices(space, quad)
 
 
+def source_element_vectors(space, quad, fq):
+    """int f v sqrtg with f at the nq^3 points (Nc, Q) -- test/Laplacian/LaplaceBeltrami.jl:53."""
+    val, _ = space.ref.tabulate(quad.pts)
+    return np.einsum("cq,qa->ca", quad.dV * quad.sqrtg * fq, val)
+
+
+def interpolate(space, fun):
+    """Nodal interpolation of an ambient function (interpolate(f o ambient_map_cf, U), LaplaceBeltrami.jl:62)."""
+    mesh = space.mesh
+    cc = mesh.cell_chart_coords
+    lo, hi = cc[:, 0, :], cc[:, 7, :]
+    x = lo[:, None, :] + space.ref.nodes[None, :, :] * (hi - lo)[:, None, :]               # (Nc, m, 3) chart nodes
+    U = np.zeros(space.num_dofs_total)
+    for p in range(6):
+        sel = mesh.cell_to_chart == p
+        vals = fun(geo.csphere3d_eval(p + 1, mesh.radius, mesh.thickness, x[sel]))
+        ids = space.cell_dofs[sel]
+        U[np.where(ids >= 0, ids, space.num_dofs_total - 1)] = vals          # the fixed DOF of a zeromean space is the last one
+    return U
+
+
+def boundary_flux_element_vectors(space, degree, U):
+    """int_G ((ginv grad(u_h)).n_G) v sqrtg dG over the bottom (gamma = 0) and top (gamma = 1) faces of the shell, u_h given by its
+    values U on ALL dofs -- the boundary term of the 3-D driver, test/Laplacian/LaplaceBeltrami.jl:58-64.  n_G is the outward unit
+    normal in chart space (-/+ e_gamma), dG the chart measure of the face; ginv_gg = 1/t^2, sqrtg = t s^2 sqrtg_surf."""
+    mesh = space.mesh
+    pts2, w2 = tensor_quadrature(2, degree)
+    out = np.zeros((mesh.num_cells, space.ndofs_loc))
+    cc = mesh.cell_chart_coords
+    lo, hi = cc[:, 0, :], cc[:, 7, :]
+    h = hi - lo
+    for side, gref, sign in ((0, 0.0, -1.0), (mesh.L - 1, 1.0, 1.0)):
+        cells = np.where(mesh.cell_layer == side)[0]
+        ref = np.concatenate([np.full((len(pts2), 1), gref), pts2], axis=1)              # (Q2, 3) reference points on the face
+        val, grad = space.ref.tabulate(ref)                                             # (Q2, m), (Q2, m, 3)
+        x = lo[cells, None, :] + ref[None, :, :] * h[cells, None, :]
+        sq = geo.csphere3d_sqrtg(mesh.radius, mesh.thickness, x)
+        gi = geo.csphere3d_inv_metric(mesh.radius, mesh.thickness, x)
+        Ue = U[np.where(space.cell_dofs[cells] >= 0, space.cell_dofs[cells], len(U) - 1)]
+        gu = np.einsum("qmi,cm->cqi", grad, Ue) / h[cells, None, :]                      # chart gradient of u_h
+        flux = sign * np.einsum("cqj,cqj->cq", gi[..., 0, :], gu)                        # (ginv grad u) . (+-e_gamma)
+        dG = w2[None, :] * (h[cells, 1] * h[cells, 2])[:, None]
+        out[cells] += np.einsum("cq,qa->ca", flux * sq * dG, val)
+    return out
+
+
+def eval_scalar(space, quad, U):
+    val, _ = space.ref.tabulate(quad.pts)
+    ids = space.cell_dofs
+    return np.einsum("qa,ca->cq", val, U[np.where(ids >= 0, ids, len(U) - 1)])
+
+
+def solve_lb(mesh, p, f, lap_f, degree=None):
+    """laplace_beltrami_solver on the shell (test/Laplacian/LaplaceBeltrami.jl:19-98 with Dc = 3): returns the L2 error."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    degree = 6 * (p + 1) if degree is None else degree
+    V = HexCGSpace(mesh, p, zeromean=True)
+    q = ShellQuadrature(mesh, degree)
+    m = V.ndofs_loc
+    ids = V.cell_dofs
+    Ke = lb_element_matrices(V, q)
+    keep = (ids[:, :, None] >= 0) & (ids[:, None, :] >= 0)
+    rows = np.broadcast_to(ids[:, :, None], Ke.shape)[keep]
+    cols = np.broadcast_to(ids[:, None, :], Ke.shape)[keep]
+    A = sp.coo_matrix((Ke[keep], (rows, cols)), shape=(V.num_free,) * 2).tocsc()
+    X = q.ambient()
+    fe = source_element_vectors(V, q, -lap_f(X))
+    Uint = interpolate(V, f)
+    fe = fe + boundary_flux_element_vectors(V, degree, Uint)
+    b = np.zeros(V.num_free)
+    np.add.at(b, ids[ids >= 0], fe[ids >= 0])
+    x = spla.spsolve(A, b)
+    xf = np.append(x, 0.0)
+    # zero-mean shift in the CHART measure (Gridap ZeroMeanFESpace)
+    val, _ = V.ref.tabulate(q.pts)
+    vol_i = np.zeros(V.num_dofs_total)
+    np.add.at(vol_i, np.where(ids >= 0, ids, V.num_dofs_total - 1), np.einsum("cq,qa->ca", q.dV, val))
+    xf = xf - (vol_i @ xf) / vol_i.sum()
+    qe = ShellQuadrature(mesh, min(2 * degree, 24))
+    e = f(qe.ambient()) - eval_scalar(V, qe, xf)
+    return float(np.sqrt((e * e * qe.dV * qe.sqrtg).sum()))
+
+
 def shell_volume(mesh, degree):
     q = ShellQuadrature(mesh, degree)
     return float((q.dV * q.sqrtg).sum())

@@ -136,3 +136,64 @@ def test_shell_helmholtz_and_mass_match_oracle(gg, form, n, L, p, degree):
     u = np.random.default_rng(3).standard_normal(V.num_free_dofs)
     r = gg.assemble_vector(F(dΩ, u=u), V).get()
     assert np.abs(r - Ao @ u).max() <= 1e-12 * np.abs(Ao @ u).max()
+
+
+def _fX(X):
+    return X[..., 0] * X[..., 1] * X[..., 2]
+
+
+def _hfX(X):
+    x, y, z = X[..., 0], X[..., 1], X[..., 2]
+    H = np.zeros(X.shape + (3,))
+    H[..., 0, 1] = H[..., 1, 0] = z
+    H[..., 0, 2] = H[..., 2, 0] = y
+    H[..., 1, 2] = H[..., 2, 1] = x
+    return H
+
+
+def test_shell_driver_pieces_match_oracle(gg):
+    """points, source vector, boundary term, interpolation, error norm and zero-mean shift of the 3-D Laplace-Beltrami driver."""
+    n, L, r, t, p, degree = 2, 3, 1.3, 0.25, 2, 6
+    model, mesh = _models(gg, n, L, r, t)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1", constraint="zeromean")
+    Vo = shell.HexCGSpace(mesh, p, zeromean=True)
+    dΩ = gg.Measure(gg.Triangulation(model), degree)
+    q = shell.ShellQuadrature(mesh, degree)
+    chart, xyz = dΩ.quadrature_points()
+    assert np.abs(chart - q.x).max() < 1e-14 and np.abs(xyz - q.ambient()).max() < 1e-13
+    fq = np.cos(xyz[..., 0]) + xyz[..., 1] * xyz[..., 2]
+    b = gg.assemble_vector(gg.Source(dΩ, fq), V).get()
+    fe = shell.source_element_vectors(Vo, q, fq)
+    bo = np.zeros(Vo.num_free)
+    np.add.at(bo, Vo.cell_dofs[Vo.cell_dofs >= 0], fe[Vo.cell_dofs >= 0])
+    assert np.abs(b - bo).max() <= 1e-12 * np.abs(bo).max()
+    Uo = shell.interpolate(Vo, _fX)
+    U = gg.interpolate(_fX, V)
+    assert np.abs(U.get() - Uo[:-1]).max() <= 1e-13 * np.abs(Uo).max()
+    # the fixed (last) DOF of the interpolant enters the boundary term with its own value
+    g = gg.assemble_vector(gg.ShellBoundaryFlux(dΩ, u=U, dirichlet=float(Uo[-1])), V).get()
+    fe = shell.boundary_flux_element_vectors(Vo, degree, Uo)
+    go = np.zeros(Vo.num_free)
+    np.add.at(go, Vo.cell_dofs[Vo.cell_dofs >= 0], fe[Vo.cell_dofs >= 0])
+    assert np.abs(g - go).max() <= 1e-12 * np.abs(go).max()
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal(V.num_free_dofs)
+    uq = shell.eval_scalar(Vo, q, np.append(u, 0.3))
+    e_ref = np.sqrt((((uq - fq) ** 2) * q.dV * q.sqrtg).sum())
+    assert abs(gg.l2_error(u, V, dΩ, fq=fq, dirichlet=0.3) - e_ref) <= 1e-12 * e_ref
+    mean_ref = (uq * q.dV).sum() / q.dV.sum()
+    assert abs(gg.chart_mean(u, V, dirichlet=0.3) - mean_ref) <= 1e-12 * abs(mean_ref)
+
+
+def test_shell_laplace_beltrami_driver_converges(gg):
+    """3-D run of test/Laplacian/LaplaceBeltrami.jl (test/Laplacian/mpi/LaplaceBeltramiTests.jl:23-28): slope >= p - 0.1, and the
+    errors of the device driver equal the oracle's."""
+    errs = []
+    for n in (2, 4):
+        model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.19), n=n)
+        e, uh, V, ns = gg.laplace_beltrami_solver(model, 2, _fX, None, _hfX, degree=8)
+        assert ns.rel_res < 1e-12
+        errs.append(e)
+    e_ref = shell.solve_lb(shell.CubedSphereShellMesh3D(2, 1.0, 0.19), 2, _fX, lambda X: np.zeros(X.shape[:-1]), degree=8)
+    assert abs(errs[0] - e_ref) <= 1e-5 * e_ref        # error rule of degree 16 here, 16 in the oracle; iterative solve
+    assert np.log(errs[0] / errs[1]) / np.log(2.0) >= 2 - 0.1

@@ -43,3 +43,17 @@ def test_shell_mass_sums_to_the_volume_and_helmholtz_splits():
     assert abs(M.sum() - vol) < 1e-6 * vol
     H = shell.helmholtz_element_matrices(V, q)
     assert np.abs(H.sum(axis=(1, 2)) - M.sum(axis=(1, 2))).max() < 1e-12     # the stiffness part annihilates constants
+
+
+def test_shell_laplace_beltrami_driver_converges():
+    """3-D run of test/Laplacian/LaplaceBeltrami.jl (test/Laplacian/mpi/LaplaceBeltramiTests.jl:23-28: two refinement levels,
+    p = 2, u = xyz): the shell is a flat 3-D domain in curvilinear coordinates, so Delta u = 0 for u = xyz and the data enter
+    through the boundary term alone; slope >= p - 0.1 (src/ConvergenceTools/Tools.jl:4-13)."""
+    f = lambda X: X[..., 0] * X[..., 1] * X[..., 2]          # noqa: E731
+    lap = lambda X: np.zeros(X.shape[:-1])                   # noqa: E731
+    errs = []
+    for n in (1, 2):
+        mesh = shell.CubedSphereShellMesh3D(n, 1.0, 0.19)
+        errs.append(shell.solve_lb(mesh, 2, f, lap, degree=8))
+    slope = np.log(errs[0] / errs[1]) / np.log(2.0)
+    assert slope >= 2 - 0.1, (errs, slope)
