@@ -94,6 +94,10 @@ __device__ __forceinline__ Stage2 stage2_of(double* gscratch, int64_t nc, int64_
   return s;
 }
 
+}  // namespace gg
+#include "gg_swe_sf.cuh"
+namespace gg {
+
 // Right-hand sides of the three diagnostic equations, one thread per cell.
 //   pq_out [c*Q+q]      depth at the quadrature points (coefficient of the q mass matrix)
 //   eq [MR][nc], eF [MU][nc]  entry-major element vectors of the q and F equations
@@ -349,6 +353,47 @@ static SweTabs swe_tabs(gg_rk* rk, bool* use_const) {
   return T;
 }
 
+// tables of the sum-factorised kernels: node values of the reference RT basis, 1-D Lagrange bases of orders K+1 and K
+static void swe_sf_tabs(gg_rk* rk) {
+  gg_ctx* ctx = rk->ctx;
+  const int K = rk->order, nq = rk->nq1;
+  const int64_t key = ((int64_t)K << 8) | nq;
+  if (ctx->swe_sf_key == key) return;
+  GG_REQUIRE(nq <= SF_MAXNQ && K <= 2, GG_ERR_UNSUPPORTED, "sum-factorised shallow-water kernels: order <= 2, at most 16 points per direction");
+  const int NA = K + 2, NB = K + 1, NX = NA * NB;
+  RTRef R = build_rt_ref(K);
+  const int MU = R.ndofs;
+  auto node = [](int p, int i) { return p > 0 ? (double)i / p : 0.5; };
+  std::vector<double> pts, val, div, phix((size_t)NX * MU), phiy((size_t)NX * MU);
+  // component x: nodes (x_a of order K+1, y_b of order K), index b * NA + a;  component y: (x_a of order K, y_b of order K+1), b * NB + a
+  for (int b = 0; b < NB; ++b) for (int a = 0; a < NA; ++a) { pts.push_back(node(K + 1, a)); pts.push_back(node(K, b)); }
+  for (int b = 0; b < NA; ++b) for (int a = 0; a < NB; ++a) { pts.push_back(node(K, a)); pts.push_back(node(K + 1, b)); }
+  R.tabulate(2 * NX, pts.data(), val, div);
+  for (int i = 0; i < NX; ++i)
+    for (int j = 0; j < MU; ++j) {
+      phix[(size_t)i * MU + j] = val[((size_t)i * MU + j) * 2 + 0];
+      phiy[(size_t)i * MU + j] = val[((size_t)(NX + i) * MU + j) * 2 + 1];
+    }
+  std::vector<double> xi(nq), w(nq), la((size_t)nq * NA), da((size_t)nq * NA), lb((size_t)nq * NB), db((size_t)nq * NB);
+  gauss_legendre_01(nq, xi.data(), w.data());
+  for (int q = 0; q < nq; ++q) {
+    lagrange_1d(K + 1, xi[q], &la[(size_t)q * NA], &da[(size_t)q * NA]);
+    lagrange_1d(K, xi[q], &lb[(size_t)q * NB], &db[(size_t)q * NB]);
+  }
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old tables
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_phix, phix.data(), phix.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_phiy, phiy.data(), phiy.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_la, la.data(), la.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_da, da.data(), da.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_lb, lb.data(), lb.size() * sizeof(double)));
+  ctx->swe_sf_key = key;
+}
+
+static bool swe_sf_enabled() {
+  static const bool on = !(getenv("GG_SWE_SF") && getenv("GG_SWE_SF")[0] == '0');
+  return on;
+}
+
 // y = [q; F; Phi] from the state x = [u; p]
 void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   gg_ctx* ctx = rk->ctx;
@@ -420,7 +465,33 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
   const double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
   const bool alias = (q0 == yq);
   unsigned nb = nblk(nc, 64);
-  {
+  if (swe_sf_enabled()) {
+    ProfScope ps(ctx, "k_swe_stage");
+    swe_sf_tabs(rk);
+    // the sum-factorised kernels are register-limited to 4 CTAs per SM, so the 50 KB staging buffer fits in shared memory
+    const size_t bytes = (size_t)2 * rk->nq1 * rk->nq1 * 64 * sizeof(double);
+    const size_t smem = bytes <= 56 * 1024 ? bytes : 0;
+    if (!smem && rk->stage2.n == 0) rk->stage2.alloc((size_t)2 * rk->nq1 * rk->nq1 * nc);
+    double* gs = smem ? nullptr : rk->stage2.p;
+    auto tdg = get_tab(ctx, GG_SPACE_DG, rk->order, rk->nq1);
+#define GG_ARGS nc, rk->nq1, g, tdg->w.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, rk->R->d_cell_dofs.p, x, yq, q0, yF, yP, \
+                rk->Bhat.p, rk->MpInv.p, rk->tau, rk->tau / rk->dt, rk->evec_u.p, r + rk->nu, kp, gs
+// (compile-time rule sizes with unrolled x-loops were measured too: 1.79 against 1.74 ms per step -- more spills, no gain)
+#define GG_NQ(K_, A_) swe_launch(k_swe_stage_sf<K_, A_, 0>, nb, smem, st, GG_ARGS);
+#define GG_CASE(K_)                                                                          \
+  case K_:                                                                                   \
+    if (alias) { GG_NQ(K_, true) } else { GG_NQ(K_, false) }                                 \
+    break;
+    switch (rk->order) {
+      GG_CASE(0) GG_CASE(1) GG_CASE(2)
+      default: throw Error(GG_ERR_UNSUPPORTED, "shallow-water order must be <= 2");
+    }
+#undef GG_CASE
+#undef GG_NQ
+#undef GG_ARGS
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  } else {
     ProfScope ps(ctx, "k_swe_stage");
     const size_t smem = swe_stage_smem(rk, 64);
     double* gs = smem ? nullptr : rk->stage2.p;
