@@ -962,13 +962,6 @@ class AdvectionOperator:
         self.beta_facets = np.ascontiguousarray(np.broadcast_to(beta(fx), fx.shape), dtype=np.float64)
 
 
-def lib_check_skeleton_misuse(A, dΩ, Q):
-    """(test helper) the generic numeric phase must refuse a skeleton pattern."""
-    form = ScalarMass(dΩ)
-    args = form.args(Q, Q)
-    _lib.check(Q.lib.gg_assemble_matrix(form.form_id, C.byref(args), A.h, 0))
-
-
 def assemble_advection_matrix(op, Q, A=None):
     """jac(t,u,du,v) = a_Ω(du,v) + b_Ω(du,v) + s_Ω(du,v) of test/Tutorials/AdvectionUpwinding.jl:124-131 as a device CSR matrix
     (volume + skeleton terms; the tutorial hands it to SDIRK + LU)."""

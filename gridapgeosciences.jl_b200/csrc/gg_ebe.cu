@@ -822,6 +822,9 @@ void ebe_set_matrix(EbeSolver* s, const double* ebuf) {
 // all 6 panels): the metric depends on the chart point only, so cells of one geometry class share S_c, T_c, M_ii^-1 up to the
 // DOF signs.  Keep one copy per class (6x less operator traffic per PCG iteration; the class operators of a 256^2 panel stay in
 // L2) and apply the signs on the fly.  Bitwise identical results: the copies are the representative cell's own numbers.
+// (Tried and slower on B200: staging the S of 42 classes per CTA in shared memory so that the 6 cells of a class read it from
+// there -- the load / barrier / compute sequence per class block loses the latency hiding of the free-running loop: cell phase
+// 93 us against 49 us per iteration, with either thread mapping.)
 static void ebe_compress(EbeSolver* s) {
   static const bool off = getenv("GG_EBE_CLASSES") && getenv("GG_EBE_CLASSES")[0] == '0';
   gg_space* sp = s->sp;

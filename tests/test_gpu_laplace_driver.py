@@ -187,7 +187,10 @@ def test_error_behaviour_of_the_driver_hooks(gg):
         gg.CSRMatrix(V, V, skeleton=True)                                   # skeleton patterns are for DG spaces
     A = gg.CSRMatrix(Q, Q, skeleton=True)
     with pytest.raises(gg.GGError):
-        gg.lib_check_skeleton_misuse(A, dΩ, Q)                              # generic numeric phase on a skeleton pattern
+        form = gg.ScalarMass(dΩ)                                            # generic numeric phase on a skeleton pattern
+        args = form.args(Q, Q)
+        import ctypes
+        gg._lib.check(Q.lib.gg_assemble_matrix(form.form_id, ctypes.byref(args), A.h, 0))
     shell = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.1), n=2)
     with pytest.raises(gg.GGError):
         gg.surface_laplacian(gg.Measure(gg.Triangulation(shell), 4), grad_fX, hess_fX)      # 2-D surfaces only
