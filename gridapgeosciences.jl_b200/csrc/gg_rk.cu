@@ -158,13 +158,18 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
     cudaStream_t st = rk->ctx->stream;
     if (slot >= 0 && rk->warm_start && rk->extrap_order > 0 && n > 0) {
       H = &rk->hist[slot];
-      const int levels = std::min(H->count, rk->extrap_order);
+      // all levels of a slot are allocated at its first solve: no cudaMalloc (a device-wide synchronisation of unpredictable
+      // cost) ever happens in the steady state of a march
+      const int R = rk->extrap_order;   // ring size = levels in use
+      if ((int64_t)H->h[0].n != n)
+        for (int l = 0; l < R; ++l) H->h[l].alloc(n);
+      const int levels = std::min(H->count, R);
       if (levels >= 1) {
         HistPtrs P;
         double binom = 1.0;
         for (int j = 0; j < levels; ++j) {
           binom = binom * (levels - j) / (j + 1);                                   // C(levels, j + 1)
-          P.h[j] = H->h[(H->head + GG_HIST_LEVELS - j) % GG_HIST_LEVELS].p;
+          P.h[j] = H->h[(H->head + R - j) % R].p;
           P.c[j] = (j % 2 == 0 ? 1.0 : -1.0) * binom;
         }
         k_extrapolate<<<nblk(n, 256), 256, 0, st>>>(n, levels, P, x);
@@ -175,11 +180,10 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
     rk_accumulate_stats(rk, e->stats.p);
     if (H) {
       // newest slot moves forward; the oldest level is overwritten
-      H->head = (H->head + 1) % GG_HIST_LEVELS;
-      auto& dst = H->h[H->head];
-      if ((int64_t)dst.n != n) dst.alloc(n);
-      GG_CUDA(cudaMemcpyAsync(dst.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      if (H->count < GG_HIST_LEVELS) H->count++;
+      const int R = rk->extrap_order;
+      H->head = (H->head + 1) % R;
+      GG_CUDA(cudaMemcpyAsync(H->h[H->head].p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if (H->count < R) H->count++;
     }
   } else {
     gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
