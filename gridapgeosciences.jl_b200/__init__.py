@@ -605,6 +605,17 @@ class VectorMass(Form):
     form_id = _lib.FORM_MASS_VECTOR
 
 
+class VectorLaplacian(Form):
+    """a(u,v) = ∫( (divg_product_rule(u)*divg_product_rule(v))*(1/meas_cf) )dΩ + ∫( -1.0*(divergenceRgu(u)*divergenceRgu(v))*(1/meas_cf) )dΩ
+    on a vector H1 space -- test/SurfaceStokes/VectorLaplacian2D.jl:71-73 (ν of the Stokes driver through `scale`)."""
+    form_id = _lib.FORM_VECTOR_LAPLACIAN
+
+
+class VectorDiv(Form):
+    """b(u,q) = ∫( q*divg_product_rule(u) )dΩ, Lagrangian test x vector H1 trial -- test/SurfaceStokes/SurfaceStokes_TaylorHood.jl:106."""
+    form_id = _lib.FORM_VECTOR_DIV
+
+
 class VectorSource(Form):
     """l(v) = ∫( (f⋅(metric_cf⋅v))*meas_cf )dΩ, f = contravariant components (n_cells, Q, 2) at the quadrature points
     -- test/Projection/L2_projection_Lagrangian_vector.jl:42."""
@@ -752,6 +763,16 @@ def norm(e, V, degree):
         e = DeviceVector.from_numpy(V.model.ctx, e)
     out = C.c_double()
     _lib.check(V.lib.gg_norm_sq(V.h, e.h, int(degree), C.byref(out)))
+    return math.sqrt(max(out.value, 0.0))
+
+
+def h1_seminorm(e, V, degree):
+    """sqrt(sum(∫( (gradient(e)⊙(inv_metric_cf⋅gradient(e)))*meas_cf )dΩ)) of a vector H1 FE function
+    (test/SurfaceStokes/SurfaceStokes_TaylorHood.jl:122)."""
+    if not isinstance(e, DeviceVector):
+        e = DeviceVector.from_numpy(V.model.ctx, e)
+    out = C.c_double()
+    _lib.check(V.lib.gg_h1_seminorm_sq(V.h, e.h, int(degree), C.byref(out)))
     return math.sqrt(max(out.value, 0.0))
 
 

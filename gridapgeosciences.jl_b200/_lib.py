@@ -23,6 +23,7 @@ FORM_DIV = 6
 FORM_SOURCE = 7
 FORM_MASS_VECTOR, FORM_SOURCE_VECTOR = 8, 9
 FORM_SHELL_BOUNDARY_FLUX = 10
+FORM_VECTOR_LAPLACIAN, FORM_VECTOR_DIV = 11, 12
 PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
 PROBLEM_ADVECTION = 3
@@ -134,6 +135,7 @@ SIGNATURES = {
     "gg_space_interp_points": (C.c_int, [_P, _PI32, _PD, _PD]),
     "gg_space_interpolate": (C.c_int, [_P, _PD, _P]),
     "gg_norm_sq": (C.c_int, [_P, _P, C.c_int32, _PD]),
+    "gg_h1_seminorm_sq": (C.c_int, [_P, _P, C.c_int32, _PD]),
     "gg_surface_laplacian": (C.c_int, [_P, C.c_int32, _PD, _PD, _P]),
     "gg_l2_error_sq": (C.c_int, [_P, _P, C.c_double, _P, C.c_int32, _PD]),
     "gg_surface_gradient": (C.c_int, [_P, C.c_int32, _PD, _P]),

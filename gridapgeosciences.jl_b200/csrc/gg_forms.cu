@@ -847,6 +847,18 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     vec_mass_element_matrices(P.test, P.nq, eb);
     return 0;
   }
+  if (form == GG_FORM_VECTOR_LAPLACIAN) {
+    GG_REQUIRE(P.test->kind == GG_SPACE_CGV && P.trial == P.test, GG_ERR_INVALID, "the vector Laplacian form needs one vector H1 space as test and trial");
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    vec_laplacian_element_matrices(P.test, P.nq, eb);
+    return 0;
+  }
+  if (form == GG_FORM_VECTOR_DIV) {
+    GG_REQUIRE(is_scalar(P.test) && P.trial->kind == GG_SPACE_CGV, GG_ERR_INVALID, "the vector divergence form needs a Lagrangian test and a vector H1 trial space");
+    double* eb = scratch(ctx->ebuf, (size_t)P.mt * P.mu * nc);
+    vec_div_element_matrices(P.test, P.trial, P.nq, eb);
+    return 0;
+  }
   if (form == GG_FORM_DIV) {
     GG_REQUIRE(is_scalar(P.test) && P.trial->kind == GG_SPACE_RT, GG_ERR_INVALID, "div form needs a scalar test and an RT trial space");
     auto tt = get_tab(ctx, P.test->kind, P.test->order, P.nq);

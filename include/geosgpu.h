@@ -230,7 +230,14 @@ typedef enum {
   GG_FORM_SOURCE_VECTOR = 9,
   /* 3-D shell: l(v) = int_G ((ginv grad(u_h)).n_G) v sqrtg dG over the bottom and top boundaries, u_h = args->u -- the boundary
    * term of the integration by parts in the 3-D run of test/Laplacian/LaplaceBeltrami.jl:58-64 (u_h = interpolate(f, U)) */
-  GG_FORM_SHELL_BOUNDARY_FLUX = 10
+  GG_FORM_SHELL_BOUNDARY_FLUX = 10,
+  /* vector H1: a(u,v) = int (D1(u) D1(v) - D2(u) D2(v)) / sqrtg with D1(u) = div(sqrtg u) ("divg_product_rule") and
+   * D2(u) = div(R g u) = -curl(g u) ("divergenceRgu") -- test/SurfaceStokes/VectorLaplacian2D.jl:38-50,71-73 and the viscous
+   * block biform_curl of test/SurfaceStokes/SurfaceStokes_TaylorHood.jl:100-102 (nu through args->scale) */
+  GG_FORM_VECTOR_LAPLACIAN = 11,
+  /* b(u,q) = int q D1(u) (rows: Lagrangian test, columns: vector H1 trial) -- biform_p of
+   * test/SurfaceStokes/SurfaceStokes_TaylorHood.jl:106; biform_u's pressure term is minus its transpose (:104) */
+  GG_FORM_VECTOR_DIV = 12
 } gg_form;
 
 typedef struct {
@@ -294,6 +301,9 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out);
 /* squared norms used by the drivers' error measures (test/Transient/TransientWaveEquation.jl:112-117):
  * Lagrangian: sum(int e^2 sqrtg);  RT: sum(int e.(g e) / sqrtg), quadrature degree `degree`. */
 int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
+/* vector H1 spaces: sum(int grad(e) : (ginv . grad(e)) sqrtg), the gradient part of eu_h1
+ * (test/SurfaceStokes/SurfaceStokes_TaylorHood.jl:122, VectorLaplacian2D.jl:91) */
+int gg_h1_seminorm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out);
 
 /* Delta_s f of an AMBIENT function f at the quadrature points, closed form (use_automatic_differentiation=false branch of
  * Δs(f, Ω), src/CellData/SurfaceDiffOps.jl:26-65,78-82; Hessian of the map src/Fields/CubedSphereMap.jl:97-123, metric

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import advection, forms, shell, swe, tswe  # noqa: E402
-from oracle import vector_h1  # noqa: E402
+from oracle import surface_stokes, vector_h1  # noqa: E402
 from oracle import rk as ork  # noqa: E402
 from oracle.mesh import CubedSphereMesh2D  # noqa: E402
 from oracle.spaces import CGSpace, DGSpace, RTSpace  # noqa: E402
@@ -112,6 +112,23 @@ def main():
     Aa.sort_indices()
     out["adv_matrix_dense_n3_p1"] = Aa.toarray()
     np.savez_compressed(os.path.join(HERE, "next_rows_n3.npz"), **out)
+    # 5. vector Laplacian / Stokes blocks on the vector H1 space (n = 3, Q2 x Q1): element matrices of the first cells (cell 0
+    #    touches a panel corner), assembled matrices, the H1 seminorm of an interpolant
+    out = {}
+    mesh = CubedSphereMesh2D(3, 1.0)
+    Vv, Qs = vector_h1.VectorCGSpace(mesh, 2), CGSpace(mesh, 1, zeromean=True)
+    q = forms.CellQuadrature(mesh, 18)
+    K = surface_stokes.vector_laplacian_element_matrices(Vv, q)
+    B = surface_stokes.div_element_matrices(Qs, Vv, q)
+    out["K_first4"], out["B_first4"] = K[:4], B[:4]
+    A = forms.assemble_matrix(Vv, Vv, K)
+    out["A_indptr"], out["A_indices"], out["A_data"] = A.indptr, A.indices, A.data
+    Bm = forms.assemble_matrix(Qs, Vv, B)
+    out["B_indptr"], out["B_indices"], out["B_data"] = Bm.indptr, Bm.indices, Bm.data
+    wX = lambda X: np.stack([X[..., 2] * X[..., 1], -X[..., 0] ** 2, X[..., 0] + 0.3], -1)   # noqa: E731
+    U = vector_h1.interpolate(Vv, wX)
+    out["h1_of_interp"] = surface_stokes.h1_error(Vv, q, U, 0 * U) ** 2 - surface_stokes.fe_l2_error(Vv, q, U, 0 * U) ** 2
+    np.savez_compressed(os.path.join(HERE, "surface_stokes_n3.npz"), **out)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from __graft_entry__ import load_package
-from oracle import advection, forms, shell, swe, tswe, vector_h1
+from oracle import advection, forms, shell, surface_stokes, swe, tswe, vector_h1
 from oracle import rk as ork
 from oracle.mesh import CubedSphereMesh2D
 from oracle.spaces import CGSpace
@@ -39,6 +39,20 @@ def test_oracle_reproduces_the_next_row_fixtures():
     assert np.abs(r - g["tswe_res0"]).max() < 1e-12 * np.abs(g["tswe_res0"]).max()
     Vv = vector_h1.VectorCGSpace(mesh, 2)
     assert (Vv.cell_dofs == g["vh1_cell_dofs"]).all() and np.abs(Vv.cob - g["vh1_cob"]).max() < 1e-14
+
+
+def test_oracle_reproduces_the_surface_stokes_fixture():
+    g = np.load(os.path.join(G, "surface_stokes_n3.npz"))
+    mesh = CubedSphereMesh2D(3, 1.0)
+    Vv, Qs = vector_h1.VectorCGSpace(mesh, 2), CGSpace(mesh, 1, zeromean=True)
+    q = forms.CellQuadrature(mesh, 18)
+    K = surface_stokes.vector_laplacian_element_matrices(Vv, q)
+    B = surface_stokes.div_element_matrices(Qs, Vv, q)
+    assert np.abs(K[:4] - g["K_first4"]).max() < 1e-13 * np.abs(g["K_first4"]).max()
+    assert np.abs(B[:4] - g["B_first4"]).max() < 1e-13 * np.abs(g["B_first4"]).max()
+    A = forms.assemble_matrix(Vv, Vv, K)
+    assert (A.indptr == g["A_indptr"]).all() and (A.indices == g["A_indices"]).all()
+    assert np.abs(A.data - g["A_data"]).max() < 1e-13 * np.abs(g["A_data"]).max()
 
 
 _wX = lambda X: np.stack([X[..., 2] * X[..., 1], -X[..., 0] ** 2, X[..., 0] + 0.3], -1)   # noqa: E731
