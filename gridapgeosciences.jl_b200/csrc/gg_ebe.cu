@@ -279,11 +279,25 @@ __global__ void k_ebe_block_inverse(int64_t n_blocks, const int32_t* __restrict_
     for (int j = 0; j < m; ++j) A[i * m + j] = v[i][j];
 }
 
+// transposed, sign-tagged boundary DOF table of the solver kernel (EbeArgs::dofT)
+__global__ void k_ebe_dof_table(int64_t nc, int mloc, int MB, const int32_t* __restrict__ cell_dofs, const int8_t* __restrict__ sg,
+                                int32_t* __restrict__ dofT) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nc * MB) return;
+  const int64_t c = t % nc;
+  const int j = (int)(t / nc);
+  const int32_t d = cell_dofs[c * mloc + j];
+  dofT[t] = d < 0 ? -1 : ((d << 1) | ((sg && sg[c * mloc + j] < 0) ? 1 : 0));
+}
+
 // ---- the solve -------------------------------------------------------------------------------------------------------
 struct EbeArgs {
   int64_t nb, nc;
   int mloc;
   const int32_t* cell_dofs;
+  // boundary DOF ids of the cells, transposed [MB][nc] so that a warp's 32 cells load 128 consecutive bytes per local DOF (the
+  // cell-major table costs 24 L1 wavefronts per load, and phase A is L1-wavefront bound); entry = (dof << 1) | (sign < 0), -1: none
+  const int32_t* dofT;
   const double *S, *T, *W;
   int64_t ns;             // stride of S, T, W: cells, or geometry classes when cls != nullptr
   const int32_t* cls;     // cell -> geometry class (nullptr: one operator per cell, DOF signs folded in)
@@ -291,8 +305,12 @@ struct EbeArgs {
   double* ev;   // [MB][nc]
   double* ev2;  // [MB][nc] second element-vector buffer (S x of the warm start, next to the condensed right-hand side)
   const int32_t *vptr, *vsrc;
+  int uni2;               // every boundary row has exactly two sources, vsrc[2 i] and vsrc[2 i + 1] (closed surface, one rank): vptr is not read
   const int32_t *bstart, *rowoff;
   const uint8_t* bsize;
+  // block classes of the builtin numberings (runs of equally sized blocks: RT_k one class, CG_p vertices + edges): block start,
+  // size and offset into binv by arithmetic instead of 9 bytes of index arrays per row; n == 0: read the arrays
+  struct { int n; int start[3], size[3], off[3]; } bc;
   const double* binv;
   const double* b;
   double scale_b;
@@ -344,18 +362,39 @@ __device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i, co
   return acc;
 }
 
+__device__ __forceinline__ void ebe_block_of(const EbeArgs& a, int64_t i, int& sb, int& mb, int& ro) {
+  if (a.bc.n == 0) { sb = a.bstart[i]; mb = a.bsize[i]; ro = a.rowoff[i]; return; }
+  int k = 0;
+  if (a.bc.n > 1 && i >= a.bc.start[1]) k = 1;
+  if (a.bc.n > 2 && i >= a.bc.start[2]) k = 2;
+  const int m = a.bc.size[k], d = (int)i - a.bc.start[k];
+  const int g = m == 3 ? d / 3 : (m == 2 ? d >> 1 : (m == 1 ? d : d / m));
+  sb = a.bc.start[k] + g * m; mb = m; ro = a.bc.off[k] + (g * m + (d - g * m)) * m;
+}
+
+// first two sources of row i (the common case) and the range of the remaining ones
+__device__ __forceinline__ void ebe_row_sources(const EbeArgs& a, int64_t i, bool ok, int32_t& lo, int32_t& hi, int32_t& s0, int32_t& s1) {
+  if (a.uni2) {
+    const int2 v = ok ? __ldg(reinterpret_cast<const int2*>(a.vsrc) + i) : make_int2(-1, -1);
+    lo = hi = 0; s0 = v.x; s1 = v.y;
+  } else {
+    lo = ok ? a.vptr[i] : 0; hi = ok ? a.vptr[i + 1] : 0;
+    s0 = lo < hi ? a.vsrc[lo] : -1; s1 = lo + 1 < hi ? a.vsrc[lo + 1] : -1;
+  }
+}
+
 // S_c p_c for one cell, p gathered through `load`
 template <int MB, bool CLS, typename Load>
 __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, double* __restrict__ out, Load load) {
   const int64_t nc = a.nc, ns = CLS ? a.ns : a.nc;
   const int64_t k = CLS ? a.cls[c] : c;
-  const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
   double pe[MB], acc[MB];
+  unsigned neg = 0;  // bit j: local DOF j carries a -1 sign around the class operator
 #pragma unroll
   for (int j = 0; j < MB; ++j) {
-    const int32_t d = a.cell_dofs[c * a.mloc + j];
-    pe[j] = d >= 0 ? load(d) : 0.0;
-    if (sg) pe[j] *= (double)sg[j];
+    const int32_t e = __ldg(a.dofT + (int64_t)j * nc + c);
+    pe[j] = e >= 0 ? load(e >> 1) : 0.0;
+    if (CLS && e >= 0 && (e & 1)) { pe[j] = -pe[j]; neg |= 1u << j; }
     acc[j] = 0.0;
   }
 #pragma unroll
@@ -367,7 +406,7 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, doub
       if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
     }
 #pragma unroll
-  for (int j = 0; j < MB; ++j) out[(int64_t)j * nc + c] = sg ? acc[j] * (double)sg[j] : acc[j];
+  for (int j = 0; j < MB; ++j) out[(int64_t)j * nc + c] = (neg >> j) & 1u ? -acc[j] : acc[j];
 }
 
 // Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; the owner of a
@@ -435,12 +474,10 @@ k_pcg_ebe(const EbeArgs a) {
     for (int u = 0; u < UNR; ++u) {
       const int64_t i = i0 + u * nth;
       const bool ok = i < n;
-      lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
+      ebe_row_sources(a, i, ok, lo[u], hi[u], s0[u], s1[u]);
       bt[u] = ok ? a.scale_b * a.b[i] : 0.0;
       rw[u] = 0.0;
     }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       if (MI > 0) {
@@ -485,7 +522,9 @@ k_pcg_ebe(const EbeArgs a) {
       const int64_t i = i0 + u * nth;
       const bool ok = i < n;
       own[u] = ok && (!owned || owned[i]);
-      sb[u] = ok ? a.bstart[i] : 0; mb[u] = own[u] ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
+      sb[u] = 0; mb[u] = 0; ro[u] = 0;
+      if (ok) ebe_block_of(a, i, sb[u], mb[u], ro[u]);
+      if (!own[u]) mb[u] = 0;
       ri[u] = ok ? r_old[i] : 0.0;
       zi[u] = 0.0;
       if (ok) a.p[i] = 0.0;
@@ -543,11 +582,9 @@ k_pcg_ebe(const EbeArgs a) {
           // the ownership byte is loaded alongside the row data, not ahead of it (no extra dependent-load level);
           // ghost rows gather too (harmless, few) but are not stored
           own[u] = ok && (!owned || owned[i]);
-          lo[u] = ok ? a.vptr[i] : 0; hi[u] = ok ? a.vptr[i + 1] : 0;
+          ebe_row_sources(a, i, ok, lo[u], hi[u], s0[u], s1[u]);
           pv[u] = ok ? fma(beta, a.p[i], __ldcg(a.z + i)) : 0.0;
         }
-#pragma unroll
-        for (int u = 0; u < UNRB; ++u) { s0[u] = lo[u] < hi[u] ? a.vsrc[lo[u]] : -1; s1[u] = lo[u] + 1 < hi[u] ? a.vsrc[lo[u] + 1] : -1; }
 #pragma unroll
         for (int u = 0; u < UNRB; ++u) {
           acc[u] = s0[u] >= 0 ? a.ev[s0[u]] : 0.0;
@@ -587,7 +624,8 @@ k_pcg_ebe(const EbeArgs a) {
           const int64_t i = i0 + u * nth;
           const bool ok = i < n;
           ob[u] = ok ? (owned ? owned[i] : (uint8_t)1) : (uint8_t)0;
-          sb[u] = ok ? a.bstart[i] : 0; mb[u] = ok ? a.bsize[i] : 0; ro[u] = ok ? a.rowoff[i] : 0;
+          sb[u] = 0; mb[u] = 0; ro[u] = 0;
+          if (ok) ebe_block_of(a, i, sb[u], mb[u], ro[u]);
           ri[u] = ok ? fma(-alpha, a.Ap[i], r_old[i]) : 0.0;
           xi[u] = ok ? a.x[i] : 0.0; pi[u] = ok ? a.p[i] : 0.0;
           zi[u] = 0.0;
@@ -659,9 +697,9 @@ k_pcg_ebe(const EbeArgs a) {
       for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
-        const int32_t d = a.cell_dofs[c * a.mloc + j];
-        xf[j] = d >= 0 ? a.x[d] : 0.0;
-        if (sg) xf[j] *= (double)sg[j];
+        const int32_t e = __ldg(a.dofT + (int64_t)j * nc + c);
+        xf[j] = e >= 0 ? a.x[e >> 1] : 0.0;
+        if (CLS && e >= 0 && (e & 1)) xf[j] = -xf[j];
       }
 #pragma unroll
       for (int t = 0; t < MI; ++t) {
@@ -767,6 +805,23 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   GG_REQUIRE(covered == n, GG_ERR_INVALID, "DOF block classes do not cover the boundary DOFs");
   GG_REQUIRE(off < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "block preconditioner too large");
   s->n_blocks = (int64_t)blk_off.size();
+  {
+    // runs of equally sized blocks -> arithmetic block lookup in the solver kernel (at most 3 runs, else the index arrays are read)
+    int nrun = 0;
+    int64_t cov = 0, o = 0;
+    bool fits = true;
+    for (const auto& bc : sp->blocks) {
+      if (bc.start >= n) break;
+      if (bc.count == 0) continue;
+      if (nrun == 3) { fits = false; break; }
+      s->bc_start[nrun] = (int)cov; s->bc_size[nrun] = bc.size; s->bc_off[nrun] = (int)o;
+      cov += bc.count * bc.size; o += bc.count * (int64_t)bc.size * bc.size;
+      ++nrun;
+    }
+    // measured on B200 (RT_2, 256^2 per panel): the arithmetic lookup saves 21 MB of index traffic per iteration but phase C is not
+    // bound by it (62.0 -> 63.0 us), so the arrays stay the default; GG_EBE_BLOCK_CLASSES=1 switches the lookup on
+    s->bc_n = fits && getenv("GG_EBE_BLOCK_CLASSES") != nullptr ? nrun : 0;
+  }
   s->bstart.upload(bstart, st); s->rowoff.upload(rowoff, st); s->bsize.upload(bsize, st);
   s->blk_off.upload(blk_off, st); s->blk_size.upload(blk_size, st);
   s->binv.alloc(off);
@@ -777,7 +832,24 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   s->ev.alloc((size_t)MB * std::max<int64_t>(nc, 1));
   s->ev2.alloc((size_t)MB * std::max<int64_t>(nc, 1));
   s->r.alloc(n); s->r2.alloc(n); s->z.alloc(n); s->p.alloc(n); s->Ap.alloc(n);
+  GG_REQUIRE(sp->n_free < (int64_t)1 << 30, GG_ERR_UNSUPPORTED, "too many DOFs for the sign-tagged DOF table");
+  s->dofT.alloc((size_t)MB * std::max<int64_t>(nc, 1));
+  if (nc) {
+    k_ebe_dof_table<<<nblk(nc * MB, 256), 256, 0, st>>>(nc, sp->ndofs_loc, MB, sp->d_cell_dofs.p,
+                                                        sp->d_cell_signs.n ? sp->d_cell_signs.p : nullptr, s->dofT.p);
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  }
   build_vec_map(sp);
+  {
+    // closed surface on one rank: every facet / edge DOF has exactly two cells -> no row pointers in the solver kernel
+    std::vector<int32_t> vp((size_t)n + 1);
+    if (n) GG_CUDA(cudaMemcpyAsync(vp.data(), sp->d_vptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    bool u2 = n > 0 && getenv("GG_EBE_ROW_POINTERS") == nullptr;
+    for (int64_t i = 0; u2 && i <= n; ++i) u2 = vp[i] == 2 * i;
+    s->uni2 = u2 ? 1 : 0;
+  }
   void* fn = ebe_kernel(MB, MI);
   int per_sm = 0;
   GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0));
@@ -925,12 +997,14 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   gg_space* sp = s->sp;
   if (sp->n_free == 0) return;
   EbeArgs a;
-  a.nb = s->nb; a.nc = s->nc; a.mloc = sp->ndofs_loc; a.cell_dofs = sp->d_cell_dofs.p;
+  a.nb = s->nb; a.nc = s->nc; a.mloc = sp->ndofs_loc; a.cell_dofs = sp->d_cell_dofs.p; a.dofT = s->dofT.p;
   a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p; a.ev2 = s->ev2.p;
   a.ns = s->compressed ? s->ns : s->nc;
   a.cls = s->compressed ? s->cls.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
-  a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p;
+  a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.uni2 = s->uni2;
+  a.bc.n = s->bc_n;
+  for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;

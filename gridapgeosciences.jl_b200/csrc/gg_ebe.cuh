@@ -13,12 +13,15 @@ struct EbeSolver {
   // geometry classes (constant operators on meshes whose cells repeat chart boxes, e.g. the 6 congruent panels of the cubed
   // sphere): S, T, W are stored once per class for the UNSIGNED reference basis; cls[c] = class of cell c, ns = classes
   DevBuf<int32_t> cls;
+  DevBuf<int32_t> dofT;      // [MB][nc] boundary DOF ids, (dof << 1) | (sign < 0), -1: none (EbeArgs::dofT)
   int64_t ns = 0;            // stride of S, T, W (= nc when not compressed)
   bool compressed = false;
   DevBuf<int32_t> bstart, rowoff, blk_off;
   DevBuf<uint8_t> bsize, blk_size;
   DevBuf<double> binv;
   int64_t n_blocks = 0;
+  int bc_n = 0, bc_start[3] = {0, 0, 0}, bc_size[3] = {1, 1, 1}, bc_off[3] = {0, 0, 0};  // runs of equally sized blocks (0: use the arrays)
+  int uni2 = 0;              // every boundary row has exactly two element sources: the kernel skips the row pointers
   DevBuf<double> r, r2, z, p, Ap, ev, ev2, partials;
   DevBuf<double> stats;      // [0] iterations of the last solve, [1] its relative residual, [2..5] phase timers (ns) + iterations
   double rtol = 1e-12;
