@@ -290,6 +290,14 @@ __global__ void k_ebe_dof_table(int64_t nc, int mloc, int MB, const int32_t* __r
   dofT[t] = d < 0 ? -1 : ((d << 1) | ((sg && sg[c * mloc + j] < 0) ? 1 : 0));
 }
 
+// first two element sources of every boundary row (EbeArgs::pair)
+__global__ void k_ebe_source_pairs(int64_t n, const int32_t* __restrict__ vptr, const int32_t* __restrict__ vsrc, int2* __restrict__ pair) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t lo = vptr[i], hi = vptr[i + 1];
+  pair[i] = make_int2(lo < hi ? vsrc[lo] : -1, lo + 1 < hi ? vsrc[lo + 1] : -1);
+}
+
 // ---- the solve -------------------------------------------------------------------------------------------------------
 struct EbeArgs {
   int64_t nb, nc;
@@ -305,7 +313,10 @@ struct EbeArgs {
   double* ev;   // [MB][nc]
   double* ev2;  // [MB][nc] second element-vector buffer (S x of the warm start, next to the condensed right-hand side)
   const int32_t *vptr, *vsrc;
-  int uni2;               // every boundary row has exactly two sources, vsrc[2 i] and vsrc[2 i + 1] (closed surface, one rank): vptr is not read
+  // first two sources of every boundary row, -1 padded (facet DOFs never have more): one 8-byte load instead of the dependent
+  // vptr -> vsrc chain in the latency-bound gather phases; the row pointers are only read when some row has a tail (tail != 0)
+  const int2* pair;
+  int tail;
   const int32_t *bstart, *rowoff;
   const uint8_t* bsize;
   // block classes of the builtin numberings (runs of equally sized blocks: RT_k one class, CG_p vertices + edges): block start,
@@ -374,13 +385,10 @@ __device__ __forceinline__ void ebe_block_of(const EbeArgs& a, int64_t i, int& s
 
 // first two sources of row i (the common case) and the range of the remaining ones
 __device__ __forceinline__ void ebe_row_sources(const EbeArgs& a, int64_t i, bool ok, int32_t& lo, int32_t& hi, int32_t& s0, int32_t& s1) {
-  if (a.uni2) {
-    const int2 v = ok ? __ldg(reinterpret_cast<const int2*>(a.vsrc) + i) : make_int2(-1, -1);
-    lo = hi = 0; s0 = v.x; s1 = v.y;
-  } else {
-    lo = ok ? a.vptr[i] : 0; hi = ok ? a.vptr[i + 1] : 0;
-    s0 = lo < hi ? a.vsrc[lo] : -1; s1 = lo + 1 < hi ? a.vsrc[lo + 1] : -1;
-  }
+  const int2 v = ok ? __ldg(a.pair + i) : make_int2(-1, -1);
+  s0 = v.x; s1 = v.y;
+  lo = hi = 0;
+  if (a.tail && ok) { lo = a.vptr[i]; hi = a.vptr[i + 1]; }
 }
 
 // S_c p_c for one cell, p gathered through `load`
@@ -842,13 +850,18 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   }
   build_vec_map(sp);
   {
-    // closed surface on one rank: every facet / edge DOF has exactly two cells -> no row pointers in the solver kernel
     std::vector<int32_t> vp((size_t)n + 1);
     if (n) GG_CUDA(cudaMemcpyAsync(vp.data(), sp->d_vptr.p, (n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GG_CUDA(cudaStreamSynchronize(st));
-    bool u2 = n > 0 && getenv("GG_EBE_ROW_POINTERS") == nullptr;
-    for (int64_t i = 0; u2 && i <= n; ++i) u2 = vp[i] == 2 * i;
-    s->uni2 = u2 ? 1 : 0;
+    bool tail = getenv("GG_EBE_ROW_POINTERS") != nullptr;   // measurement: always walk the row pointers
+    for (int64_t i = 0; !tail && i < n; ++i) tail = vp[i + 1] - vp[i] > 2;
+    s->tail = tail ? 1 : 0;
+    s->pair.alloc(std::max<int64_t>(n, 1));
+    if (n) {
+      k_ebe_source_pairs<<<nblk(n, 256), 256, 0, st>>>(n, sp->d_vptr.p, sp->d_vsrc.p, s->pair.p);
+      ctx->launches++;
+      GG_CUDA(cudaGetLastError());
+    }
   }
   void* fn = ebe_kernel(MB, MI);
   int per_sm = 0;
@@ -1002,7 +1015,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.ns = s->compressed ? s->ns : s->nc;
   a.cls = s->compressed ? s->cls.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
-  a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.uni2 = s->uni2;
+  a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
   a.bc.n = s->bc_n;
   for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
