@@ -1028,6 +1028,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   int grid = s->grid;
   const int64_t want = (std::max(s->nb, s->nc) + 255) / 256;
   if (want < grid) grid = (int)std::max<int64_t>(want, 1);
+  if (const char* g = getenv("GG_EBE_GRID")) grid = std::max(1, std::min(grid, atoi(g)));  // measurement: barrier latency against work per thread
   void* args[] = {&a};
   ProfScope ps(ctx, "k_pcg_ebe");
   GG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, ctx->stream));
