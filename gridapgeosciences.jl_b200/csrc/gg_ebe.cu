@@ -321,7 +321,10 @@ struct EbeArgs {
   const uint8_t* bsize;
   // block classes of the builtin numberings (runs of equally sized blocks: RT_k one class, CG_p vertices + edges): block start,
   // size and offset into binv by arithmetic instead of 9 bytes of index arrays per row; n == 0: read the arrays
-  struct { int n; int start[3], size[3], off[3]; } bc;
+  struct { int n; int start[3], size[3], off[3], b0[3]; } bc;   // b0: index of the first block of the run
+  int64_t n_blocks;
+  int bc_rows;            // the row loops also use the arithmetic lookup (measured: 1 us slower than the arrays; GG_EBE_BLOCK_CLASSES=1)
+  int cblk;               // phase C walks the preconditioner blocks (one thread per block) instead of the rows
   const double* binv;
   const double* b;
   double scale_b;
@@ -374,7 +377,7 @@ __device__ __forceinline__ double ebe_gather_row(const EbeArgs& a, int64_t i, co
 }
 
 __device__ __forceinline__ void ebe_block_of(const EbeArgs& a, int64_t i, int& sb, int& mb, int& ro) {
-  if (a.bc.n == 0) { sb = a.bstart[i]; mb = a.bsize[i]; ro = a.rowoff[i]; return; }
+  if (a.bc.n == 0 || !a.bc_rows) { sb = a.bstart[i]; mb = a.bsize[i]; ro = a.rowoff[i]; return; }
   int k = 0;
   if (a.bc.n > 1 && i >= a.bc.start[1]) k = 1;
   if (a.bc.n > 2 && i >= a.bc.start[2]) k = 2;
@@ -432,6 +435,8 @@ k_pcg_ebe(const EbeArgs a) {
   __shared__ double sh[32];
   constexpr int MIa = MI > 0 ? MI : 1;
   constexpr int UNR = 4;
+  constexpr int UNRH = 2;
+  constexpr int MBU = 3;   // preconditioner block rows loaded without a loop (facet blocks of RT_0..2, vertex / edge blocks of CG_1..3)
 #ifndef GG_EBE_UNRB
 #define GG_EBE_UNRB 4
 #endif
@@ -537,10 +542,25 @@ k_pcg_ebe(const EbeArgs a) {
       zi[u] = 0.0;
       if (ok) a.p[i] = 0.0;
     }
+    {
+      // block rows: the first MBU entries through predicated, fully unrolled loads (all in flight at once; a loop with a run-time
+      // trip count serialises one DRAM round trip per row), longer blocks finish in the loop
+      double bv[UNR][MBU], rv[UNR][MBU];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const double* bi_row = a.binv + ro[u];
-      for (int j = 0; j < mb[u]; ++j) zi[u] = fma(bi_row[j], r_old[sb[u] + j], zi[u]);
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int j = 0; j < MBU; ++j) {
+          const bool on = j < mb[u];
+          bv[u][j] = on ? a.binv[ro[u] + j] : 0.0;
+          rv[u][j] = on ? r_old[sb[u] + j] : 0.0;
+        }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int j = 0; j < MBU; ++j)
+          if (j < mb[u]) zi[u] = fma(bv[u][j], rv[u][j], zi[u]);
+        for (int j = MBU; j < mb[u]; ++j) zi[u] = fma(a.binv[ro[u] + j], r_old[sb[u] + j], zi[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -623,6 +643,48 @@ k_pcg_ebe(const EbeArgs a) {
       const unsigned long long tc0 = ebe_now();
       // -- C: x += alpha p ; r -= alpha Ap ; z = Binv r (block rows recomputed: no barrier) ; rz, rr  (owned rows only)
       double lrz2 = 0.0, lrr = 0.0;
+      if (a.cblk) {
+        // one thread per preconditioner block (<= 3 rows: the DOFs of a facet / vertex / edge): every operand of the block is
+        // loaded once, all loads are independent of each other (block position by arithmetic) and in flight together -- the row
+        // loop below needs two dependent DRAM round trips per round (index arrays, then the block rows)
+        for (int64_t b = tid; b < a.n_blocks; b += nth) {
+          int k = 0;
+          if (a.bc.n > 1 && b >= a.bc.b0[1]) k = 1;
+          if (a.bc.n > 2 && b >= a.bc.b0[2]) k = 2;
+          const int m = a.bc.size[k], g = (int)b - a.bc.b0[k];
+          const int64_t s0 = a.bc.start[k] + (int64_t)g * m;
+          const double* __restrict__ B = a.binv + a.bc.off[k] + (int64_t)g * m * m;
+          double Av[3], Rv[3], Xv[3], Pv[3], Bm[9];
+          uint8_t ob[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const bool on = j < m;
+            Av[j] = on ? a.Ap[s0 + j] : 0.0; Rv[j] = on ? r_old[s0 + j] : 0.0;
+            Xv[j] = on ? a.x[s0 + j] : 0.0; Pv[j] = on ? a.p[s0 + j] : 0.0;
+            ob[j] = on ? (owned ? owned[s0 + j] : (uint8_t)1) : (uint8_t)0;
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) Bm[j * 3 + l] = (j < m && l < m) ? B[j * m + l] : 0.0;
+          double rn[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) rn[j] = fma(-alpha, Av[j], Rv[j]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (!ob[j]) continue;
+            double zj = 0.0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+              if (l < m) zj = fma(Bm[j * 3 + l], rn[l], zj);
+            a.x[s0 + j] = fma(alpha, Pv[j], Xv[j]);
+            r_new[s0 + j] = rn[j]; a.z[s0 + j] = zj;
+            lrz2 = fma(rn[j], zj, lrz2);
+            lrr = fma(rn[j], rn[j], lrr);
+            if (ob[j] == 2) dist_push_row(a.dist, s0 + j, zj);
+          }
+        }
+      } else
       for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
         int sb[UNR], mb[UNR], ro[UNR];
         double ri[UNR], zi[UNR], xi[UNR], pi[UNR];
@@ -639,10 +701,26 @@ k_pcg_ebe(const EbeArgs a) {
           zi[u] = 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const double* bi_row = a.binv + ro[u];
-          const int s = sb[u];
-          for (int j = 0; j < mb[u]; ++j) zi[u] = fma(bi_row[j], fma(-alpha, a.Ap[s + j], r_old[s + j]), zi[u]);
+        for (int h = 0; h < UNR; h += UNRH) {   // UNRH rows at a time: 9 loads per row in flight, within the register budget
+          double bv[UNRH][MBU], av[UNRH][MBU], rv[UNRH][MBU];
+#pragma unroll
+          for (int v = 0; v < UNRH; ++v)
+#pragma unroll
+            for (int j = 0; j < MBU; ++j) {
+              const int u = h + v;
+              const bool on = j < mb[u];
+              bv[v][j] = on ? a.binv[ro[u] + j] : 0.0;
+              av[v][j] = on ? a.Ap[sb[u] + j] : 0.0;
+              rv[v][j] = on ? r_old[sb[u] + j] : 0.0;
+            }
+#pragma unroll
+          for (int v = 0; v < UNRH; ++v) {
+            const int u = h + v;
+#pragma unroll
+            for (int j = 0; j < MBU; ++j)
+              if (j < mb[u]) zi[u] = fma(bv[v][j], fma(-alpha, av[v][j], rv[v][j]), zi[u]);
+            for (int j = MBU; j < mb[u]; ++j) zi[u] = fma(a.binv[ro[u] + j], fma(-alpha, a.Ap[sb[u] + j], r_old[sb[u] + j]), zi[u]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
@@ -816,19 +894,23 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter) {
   {
     // runs of equally sized blocks -> arithmetic block lookup in the solver kernel (at most 3 runs, else the index arrays are read)
     int nrun = 0;
-    int64_t cov = 0, o = 0;
-    bool fits = true;
+    int64_t cov = 0, o = 0, nblk_seen = 0;
+    bool fits = true, small = true;
     for (const auto& bc : sp->blocks) {
       if (bc.start >= n) break;
       if (bc.count == 0) continue;
       if (nrun == 3) { fits = false; break; }
-      s->bc_start[nrun] = (int)cov; s->bc_size[nrun] = bc.size; s->bc_off[nrun] = (int)o;
+      s->bc_start[nrun] = (int)cov; s->bc_size[nrun] = bc.size; s->bc_off[nrun] = (int)o; s->bc_b0[nrun] = (int)nblk_seen;
+      if (bc.size > 3) small = false;
+      nblk_seen += bc.count;
       cov += bc.count * bc.size; o += bc.count * (int64_t)bc.size * bc.size;
       ++nrun;
     }
-    // measured on B200 (RT_2, 256^2 per panel): the arithmetic lookup saves 21 MB of index traffic per iteration but phase C is not
-    // bound by it (62.0 -> 63.0 us), so the arrays stay the default; GG_EBE_BLOCK_CLASSES=1 switches the lookup on
-    s->bc_n = fits && getenv("GG_EBE_BLOCK_CLASSES") != nullptr ? nrun : 0;
+    // measured on B200 (RT_2, 256^2 per panel): inside the ROW loops the arithmetic lookup is 1 us slower than the index arrays
+    // (GG_EBE_BLOCK_CLASSES=1 switches it on there); the block-wise update phase below is built on it
+    s->bc_n = fits ? nrun : 0;
+    // block-wise update phase: needs the arithmetic block positions and blocks of at most 3 rows; GG_EBE_ROW_UPDATE=1 keeps the row loop
+    s->cblk = fits && small && nrun > 0 && getenv("GG_EBE_ROW_UPDATE") == nullptr ? 1 : 0;
   }
   s->bstart.upload(bstart, st); s->rowoff.upload(rowoff, st); s->bsize.upload(bsize, st);
   s->blk_off.upload(blk_off, st); s->blk_size.upload(blk_size, st);
@@ -1016,8 +1098,8 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.cls = s->compressed ? s->cls.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
-  a.bc.n = s->bc_n;
-  for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; }
+  a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr;
+  for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; a.bc.b0[k] = s->bc_b0[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;

@@ -20,7 +20,7 @@ struct EbeSolver {
   DevBuf<uint8_t> bsize, blk_size;
   DevBuf<double> binv;
   int64_t n_blocks = 0;
-  int bc_n = 0, bc_start[3] = {0, 0, 0}, bc_size[3] = {1, 1, 1}, bc_off[3] = {0, 0, 0};  // runs of equally sized blocks (0: use the arrays)
+  int bc_n = 0, bc_start[3] = {0, 0, 0}, bc_size[3] = {1, 1, 1}, bc_off[3] = {0, 0, 0}, bc_b0[3] = {0, 0, 0}, cblk = 0;  // runs of equally sized blocks (0: use the arrays)
   DevBuf<int2> pair;         // [nb] first two element sources of every boundary row, -1 padded (EbeArgs::pair)
   int tail = 0;              // some row has more than two sources: the kernel also walks vptr / vsrc beyond the pair
   DevBuf<double> r, r2, z, p, Ap, ev, ev2, partials;
