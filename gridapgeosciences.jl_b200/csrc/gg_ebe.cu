@@ -309,6 +309,9 @@ struct EbeArgs {
   const double *S, *T, *W;
   int64_t ns;             // stride of S, T, W: cells, or geometry classes when cls != nullptr
   const int32_t* cls;     // cell -> geometry class (nullptr: one operator per cell, DOF signs folded in)
+  // class -> its (at most EBE_TILE_REP) cells, -1 padded; when set, the condensation passes of the solve walk the classes in tiles
+  // of EBE_TILE_CLS: a CTA stages T (and W) of a tile in shared memory once and serves every congruent cell from there
+  const int32_t* ccell;
   const int8_t* sg;       // [nc][mloc] DOF signs applied around the class operators (nullptr: none)
   double* ev;   // [MB][nc]
   double* ev2;  // [MB][nc] second element-vector buffer (S x of the warm start, next to the condensed right-hand side)
@@ -335,6 +338,17 @@ struct EbeArgs {
   double* stats;
   DistDev dist;  // world == 1: single GPU
 };
+
+constexpr int EBE_TILE_CLS = 32, EBE_TILE_REP = 6;
+extern __shared__ double ebe_tile[];   // [entries][EBE_TILE_CLS]
+
+// stage `n_ent` entry planes of a class operator (src[ent * ns + k]) for the classes [k0, k0 + EBE_TILE_CLS) at dst
+__device__ __forceinline__ void ebe_stage_tile(double* dst, const double* __restrict__ src, int n_ent, int64_t ns, int64_t k0) {
+  for (int e = threadIdx.x; e < n_ent * EBE_TILE_CLS; e += blockDim.x) {
+    const int ent = e / EBE_TILE_CLS, kk = e - ent * EBE_TILE_CLS;
+    dst[e] = k0 + kk < ns ? src[(int64_t)ent * ns + k0 + kk] : 0.0;
+  }
+}
 
 __device__ __forceinline__ unsigned long long ebe_now() {
   unsigned long long t;
@@ -456,24 +470,46 @@ k_pcg_ebe(const EbeArgs a) {
 
   const unsigned long long tp0 = ebe_now();
   // ---- one pass over the cells: condensed right-hand side  ev = T_c^T (s b_i)  and, for a warm start, ev2 = S_c x_c ----
+  // condensed right-hand side of cell c, T_c read through ldT(entry)
+  auto condensed_rhs = [&](int64_t c, auto ldT) {
+    double bi[MIa];
+    const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
+#pragma unroll
+    for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
+#pragma unroll
+    for (int j = 0; j < MB; ++j) {
+      double acc = 0.0;
+#pragma unroll
+      for (int t = 0; t < MI; ++t) acc = fma(ldT(t * MB + j), bi[t], acc);
+      a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
+    }
+  };
+  const bool tiles = CLS && MI > 0 && a.ccell != nullptr;
   if (MI > 0 || a.warm) {
-    for (int64_t c = tid; c < nc; c += nth) {
-      if (MI > 0) {
-        double bi[MIa];
-        const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
-        const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
-#pragma unroll
-        for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
-#pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          double acc = 0.0;
-#pragma unroll
-          for (int t = 0; t < MI; ++t) acc = fma(a.T[(int64_t)(t * MB + j) * ns + k], bi[t], acc);
-          a.ev[(int64_t)j * nc + c] = sg ? acc * (double)sg[j] : acc;
+    if (tiles) {
+      const int64_t ntiles = (a.ns + EBE_TILE_CLS - 1) / EBE_TILE_CLS;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t k0 = tile * EBE_TILE_CLS;
+        __syncthreads();
+        ebe_stage_tile(ebe_tile, a.T, MI * MB, a.ns, k0);
+        __syncthreads();
+        const int kk = threadIdx.x % EBE_TILE_CLS;
+        for (int r = threadIdx.x / EBE_TILE_CLS; r < EBE_TILE_REP; r += blockDim.x / EBE_TILE_CLS) {
+          const int64_t c = k0 + kk < a.ns ? a.ccell[(k0 + kk) * EBE_TILE_REP + r] : -1;
+          if (c < 0) continue;
+          condensed_rhs(c, [&](int ent) { return ebe_tile[ent * EBE_TILE_CLS + kk]; });
+          if (a.warm) ebe_apply_cell<MB, CLS>(a, c, a.ev2, [&](int32_t d) { return a.x[d]; });
         }
       }
-      // initial guess = what the output vector holds (the solution of the previous stage / step)
-      if (a.warm) ebe_apply_cell<MB, CLS>(a, c, a.ev2, [&](int32_t d) { return a.x[d]; });
+    } else {
+      for (int64_t c = tid; c < nc; c += nth) {
+        if (MI > 0) {
+          const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
+          condensed_rhs(c, [&](int ent) { return a.T[(int64_t)ent * ns + k]; });
+        }
+        // initial guess = what the output vector holds (the solution of the previous stage / step)
+        if (a.warm) ebe_apply_cell<MB, CLS>(a, c, a.ev2, [&](int32_t d) { return a.x[d]; });
+      }
     }
     grid.sync();
   }
@@ -774,30 +810,52 @@ k_pcg_ebe(const EbeArgs a) {
   }
   const unsigned long long tp4 = ebe_now();
   // ---- eliminated DOFs: x_i = W (s b_i) - T x_f ----
-  if (MI > 0) {
-    for (int64_t c = tid; c < nc; c += nth) {
-      double bi[MIa], xf[MB];
-      const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
-      const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
+  auto recover = [&](int64_t c, auto ldT, auto ldW) {
+    double bi[MIa], xf[MB];
+    const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-      for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
+    for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        const int32_t e = __ldg(a.dofT + (int64_t)j * nc + c);
-        xf[j] = e >= 0 ? a.x[e >> 1] : 0.0;
-        if (CLS && e >= 0 && (e & 1)) xf[j] = -xf[j];
+    for (int j = 0; j < MB; ++j) {
+      const int32_t e = __ldg(a.dofT + (int64_t)j * nc + c);
+      xf[j] = e >= 0 ? a.x[e >> 1] : 0.0;
+      if (CLS && e >= 0 && (e & 1)) xf[j] = -xf[j];
+    }
+#pragma unroll
+    for (int t = 0; t < MI; ++t) {
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < MI; ++s) {
+        const int lo = t < s ? t : s, hi = t < s ? s : t;
+        acc = fma(ldW(ebe_sym(MI, lo, hi)), bi[s], acc);
       }
 #pragma unroll
-      for (int t = 0; t < MI; ++t) {
-        double acc = 0.0;
-#pragma unroll
-        for (int s = 0; s < MI; ++s) {
-          const int lo = t < s ? t : s, hi = t < s ? s : t;
-          acc = fma(a.W[(int64_t)ebe_sym(MI, lo, hi) * ns + k], bi[s], acc);
+      for (int j = 0; j < MB; ++j) acc = fma(-ldT(t * MB + j), xf[j], acc);
+      a.x[n + c * MI + t] = sg ? acc * (double)sg[MB + t] : acc;
+    }
+  };
+  if (MI > 0) {
+    if (tiles) {
+      constexpr int NT = MI * MB, NW = MIa * (MIa + 1) / 2;
+      const int64_t ntiles = (a.ns + EBE_TILE_CLS - 1) / EBE_TILE_CLS;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t k0 = tile * EBE_TILE_CLS;
+        __syncthreads();
+        ebe_stage_tile(ebe_tile, a.T, NT, a.ns, k0);
+        ebe_stage_tile(ebe_tile + NT * EBE_TILE_CLS, a.W, NW, a.ns, k0);
+        __syncthreads();
+        const int kk = threadIdx.x % EBE_TILE_CLS;
+        for (int r = threadIdx.x / EBE_TILE_CLS; r < EBE_TILE_REP; r += blockDim.x / EBE_TILE_CLS) {
+          const int64_t c = k0 + kk < a.ns ? a.ccell[(k0 + kk) * EBE_TILE_REP + r] : -1;
+          if (c < 0) continue;
+          recover(c, [&](int ent) { return ebe_tile[ent * EBE_TILE_CLS + kk]; },
+                  [&](int ent) { return ebe_tile[(NT + ent) * EBE_TILE_CLS + kk]; });
         }
-#pragma unroll
-        for (int j = 0; j < MB; ++j) acc = fma(-a.T[(int64_t)(t * MB + j) * ns + k], xf[j], acc);
-        a.x[n + c * MI + t] = sg ? acc * (double)sg[MB + t] : acc;
+      }
+    } else {
+      for (int64_t c = tid; c < nc; c += nth) {
+        const int64_t k = CLS ? a.cls[c] : c, ns = CLS ? a.ns : nc;
+        recover(c, [&](int ent) { return a.T[(int64_t)ent * ns + k]; }, [&](int ent) { return a.W[(int64_t)ent * ns + k]; });
       }
     }
   }
@@ -1029,6 +1087,29 @@ static void ebe_compress(EbeSolver* s) {
   for (int i = 0; i < MI; ++i) for (int j = i; j < MI; ++j) { pa.push_back((uint8_t)(MB + i)); pb.push_back((uint8_t)(MB + j)); }
   compact(s->W, pa, pb);
   s->cls.upload(cls, st);
+  // class -> cells table of the tiled condensation passes (at most EBE_TILE_REP congruent cells per class, else the cell loops stay)
+  {
+    std::vector<int32_t> cc((size_t)ns * EBE_TILE_REP, -1), cnt((size_t)ns, 0);
+    bool ok = MI > 0 && !(getenv("GG_EBE_TILES") && getenv("GG_EBE_TILES")[0] == '0');
+    for (int64_t c = 0; ok && c < nc; ++c) {
+      const int32_t k = cls[c];
+      if (cnt[k] == EBE_TILE_REP) { ok = false; break; }
+      cc[(size_t)k * EBE_TILE_REP + cnt[k]++] = (int32_t)c;
+    }
+    s->tile_smem = 0;
+    if (ok) {
+      const size_t bytes = (size_t)(MI * MB + MI * (MI + 1) / 2) * EBE_TILE_CLS * sizeof(double);
+      void* fn = ebe_kernel(MB, MI, true);
+      int per_sm = 0;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, bytes) == cudaSuccess && per_sm * ctx->sm_count >= s->grid) {
+        s->ccell.upload(cc, st);
+        s->tile_smem = bytes;
+      } else {
+        (void)cudaGetLastError();   // the tiles would cost residency: keep the cell loops
+      }
+    }
+  }
   GG_CUDA(cudaStreamSynchronize(st));
   s->ns = ns; s->compressed = true;
 }
@@ -1096,6 +1177,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p; a.ev2 = s->ev2.p;
   a.ns = s->compressed ? s->ns : s->nc;
   a.cls = s->compressed ? s->cls.p : nullptr;
+  a.ccell = s->compressed && s->tile_smem ? s->ccell.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
   a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr;
@@ -1113,7 +1195,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   if (const char* g = getenv("GG_EBE_GRID")) grid = std::max(1, std::min(grid, atoi(g)));  // measurement: barrier latency against work per thread
   void* args[] = {&a};
   ProfScope ps(ctx, "k_pcg_ebe");
-  GG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, ctx->stream));
+  GG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, a.ccell ? s->tile_smem : 0, ctx->stream));
   ctx->launches++;
 }
 

@@ -13,6 +13,8 @@ struct EbeSolver {
   // geometry classes (constant operators on meshes whose cells repeat chart boxes, e.g. the 6 congruent panels of the cubed
   // sphere): S, T, W are stored once per class for the UNSIGNED reference basis; cls[c] = class of cell c, ns = classes
   DevBuf<int32_t> cls;
+  DevBuf<int32_t> ccell;     // [ns][6] cells of every class, -1 padded (tiled condensation passes of the solve)
+  size_t tile_smem = 0;      // dynamic shared memory of the tiled passes (0: cell loops)
   DevBuf<int32_t> dofT;      // [MB][nc] boundary DOF ids, (dof << 1) | (sign < 0), -1: none (EbeArgs::dofT)
   int64_t ns = 0;            // stride of S, T, W (= nc when not compressed)
   bool compressed = false;
