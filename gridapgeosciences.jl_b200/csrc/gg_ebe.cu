@@ -312,10 +312,6 @@ struct EbeArgs {
   // class -> its (at most EBE_TILE_REP) cells, -1 padded; when set, the condensation passes of the solve walk the classes in tiles
   // of EBE_TILE_CLS: a CTA stages T (and W) of a tile in shared memory once and serves every congruent cell from there
   const int32_t* ccell;
-  // the cell phase of the iterations tiled the same way (S of a tile in shared memory).  Measured on B200, RT_2, 256^2 per panel:
-  // 42.8 -> 73.0 us per iteration -- that phase is bound by the L1 wavefronts of the p / z gathers, not by the S reads, and the
-  // tile loop adds two CTA barriers per 192 cells and idles a quarter of the threads.  Off unless GG_EBE_TILE_S is exported.
-  int tile_S;
   const int8_t* sg;       // [nc][mloc] DOF signs applied around the class operators (nullptr: none)
   double* ev;   // [MB][nc]
   double* ev2;  // [MB][nc] second element-vector buffer (S x of the warm start, next to the condensed right-hand side)
@@ -413,9 +409,10 @@ __device__ __forceinline__ void ebe_row_sources(const EbeArgs& a, int64_t i, boo
 }
 
 // S_c p_c for one cell, p gathered through `load`
-template <int MB, bool CLS, typename Load, typename LoadS>
-__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, double* __restrict__ out, Load load, LoadS ldS) {
-  const int64_t nc = a.nc;
+template <int MB, bool CLS, typename Load>
+__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, double* __restrict__ out, Load load) {
+  const int64_t nc = a.nc, ns = CLS ? a.ns : a.nc;
+  const int64_t k = CLS ? a.cls[c] : c;
   double pe[MB], acc[MB];
   unsigned neg = 0;  // bit j: local DOF j carries a -1 sign around the class operator
 #pragma unroll
@@ -429,18 +426,12 @@ __device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, doub
   for (int i = 0; i < MB; ++i)
 #pragma unroll
     for (int j = i; j < MB; ++j) {
-      const double sv = ldS(ebe_sym(MB, i, j));
+      const double sv = a.S[(int64_t)ebe_sym(MB, i, j) * ns + k];
       acc[i] = fma(sv, pe[j], acc[i]);
       if (j != i) acc[j] = fma(sv, pe[i], acc[j]);
     }
 #pragma unroll
   for (int j = 0; j < MB; ++j) out[(int64_t)j * nc + c] = (neg >> j) & 1u ? -acc[j] : acc[j];
-}
-
-template <int MB, bool CLS, typename Load>
-__device__ __forceinline__ void ebe_apply_cell(const EbeArgs& a, int64_t c, double* __restrict__ out, Load load) {
-  const int64_t ns = CLS ? a.ns : a.nc, k = CLS ? a.cls[c] : c;
-  ebe_apply_cell<MB, CLS>(a, c, out, load, [&](int ent) { return a.S[(int64_t)ent * ns + k]; });
 }
 
 // Partitioned runs (a.dist.world > 1): rows of ghost DOFs are neither updated nor counted in the dot products; the owner of a
@@ -638,24 +629,10 @@ k_pcg_ebe(const EbeArgs a) {
     for (it = 1; it <= a.max_iter; ++it) {
       // -- A: element vectors of S p with p = z + beta p_old formed on the fly (z may have been written by a peer: L2 loads)
       unsigned long long t0 = ebe_now();
-      if (tiles && a.tile_S) {
-        const int64_t ntiles = (a.ns + EBE_TILE_CLS - 1) / EBE_TILE_CLS;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          const int64_t k0 = tile * EBE_TILE_CLS;
-          __syncthreads();
-          ebe_stage_tile(ebe_tile, a.S, MB * (MB + 1) / 2, a.ns, k0);
-          __syncthreads();
-          const int kk = threadIdx.x % EBE_TILE_CLS;
-          for (int r = threadIdx.x / EBE_TILE_CLS; r < EBE_TILE_REP; r += blockDim.x / EBE_TILE_CLS) {
-            const int64_t c = k0 + kk < a.ns ? a.ccell[(k0 + kk) * EBE_TILE_REP + r] : -1;
-            if (c >= 0)
-              ebe_apply_cell<MB, CLS>(a, c, a.ev, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); },
-                                      [&](int ent) { return ebe_tile[ent * EBE_TILE_CLS + kk]; });
-          }
-        }
-      } else {
-        for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, a.ev, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
-      }
+      // (tiling this phase like the condensation passes was measured and dropped: 42.8 -> 73.0 us per iteration on RT_2 / 256^2 --
+      // the phase is bound by the L1 wavefronts of the p / z gathers, not by the S reads, and the tile loop adds two CTA barriers
+      // per 192 cells, idles a quarter of the threads and lengthens the instruction stream of the iteration loop)
+      for (int64_t c = tid; c < nc; c += nth) ebe_apply_cell<MB, CLS>(a, c, a.ev, [&](int32_t d) { return fma(beta, a.p[d], __ldcg(a.z + d)); });
       grid.sync();
       unsigned long long t1 = ebe_now();
       tA += t1 - t0;
@@ -1203,8 +1180,9 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.S = s->S.p; a.T = s->T.p; a.W = s->W.p; a.ev = s->ev.p; a.ev2 = s->ev2.p;
   a.ns = s->compressed ? s->ns : s->nc;
   a.cls = s->compressed ? s->cls.p : nullptr;
-  a.ccell = s->compressed && s->tile_smem ? s->ccell.p : nullptr;
-  a.tile_S = getenv("GG_EBE_TILE_S") != nullptr;
+  // tiles pay once the cell loops take more than one round of the persistent grid; on small meshes (the 48^2 wave test: 72 tiles for
+  // 296 CTAs) the staging barriers cost 3 us per pass, so the cell loops stay
+  a.ccell = s->compressed && s->tile_smem && s->nc >= (int64_t)s->grid * 256 ? s->ccell.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
   a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr;

@@ -32,6 +32,12 @@ def main():
     ctx.synchronize()
     dt = time.perf_counter() - t0
     it, so = st.stats()
+    try:
+        a, su = st.solver_phase_ns(0), st.solver_phase_ns(10)
+        print("  us per iteration (cells, gather+dot, update):", [round(v / max(a[3], 1) / 1e3, 2) for v in a[:3]],
+              " us per solve (pre-pass, rows, first precond, recovery):", [round(v / 1e3, 2) for v in su])
+    except Exception as ex:  # wave steppers without the condensed solver
+        print("  no phase timers:", ex)
     print(f"n={args.n} grid={os.environ.get('GG_EBE_GRID', 'default')} steps/s={args.steps / dt:.1f} us/step={1e6 * dt / args.steps:.1f} iters/solve={it / max(so, 1):.2f}")
 
 
