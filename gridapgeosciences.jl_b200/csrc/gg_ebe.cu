@@ -1182,7 +1182,8 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.cls = s->compressed ? s->cls.p : nullptr;
   // tiles pay once the cell loops take more than one round of the persistent grid; on small meshes (the 48^2 wave test: 72 tiles for
   // 296 CTAs) the staging barriers cost 3 us per pass, so the cell loops stay
-  a.ccell = s->compressed && s->tile_smem && s->nc >= (int64_t)s->grid * 256 ? s->ccell.p : nullptr;
+  static const bool force_tiles = getenv("GG_EBE_TILES") && getenv("GG_EBE_TILES")[0] == '2';   // tests: tiles on small meshes too
+  a.ccell = s->compressed && s->tile_smem && (force_tiles || s->nc >= (int64_t)s->grid * 256) ? s->ccell.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
   a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr;

@@ -185,3 +185,18 @@ def test_alternative_mass_solvers_agree(gg, monkeypatch):
     ref = out[("ebe", "1")]
     for k, v in out.items():
         assert _rel(v, ref) < 1e-11, k
+
+
+def test_solver_variants_of_the_condensed_pcg_agree():
+    """The condensed solver picks its code paths by mesh size and structure: class-tiled condensation passes (large meshes only),
+    block-wise update phase, padded source pairs.  The switches are read once per process, so the stepping tests of this file are
+    re-run in child processes with the tiles forced on small meshes (partial tiles, classes with fewer than six cells) and with the
+    row-wise update / row-pointer walks that the defaults replace."""
+    import os
+    import subprocess
+    import sys
+    for extra in ({"GG_EBE_TILES": "2"}, {"GG_EBE_ROW_UPDATE": "1", "GG_EBE_ROW_POINTERS": "1", "GG_EBE_TILES": "0"}):
+        out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                              "steps_match_oracle or diagnostics_and_stage"], env=dict(os.environ, **extra), capture_output=True,
+                             text=True, timeout=900)
+        assert out.returncode == 0, (extra, out.stdout[-2000:], out.stderr[-1000:])
