@@ -327,6 +327,7 @@ struct EbeArgs {
   struct { int n; int start[3], size[3], off[3], b0[3]; } bc;   // b0: index of the first block of the run
   int64_t n_blocks;
   int bc_rows;            // the row loops also use the arithmetic lookup (measured: 1 us slower than the arrays; GG_EBE_BLOCK_CLASSES=1)
+  int row_setup;          // the two row-wise set-up passes (default); GG_EBE_BLOCK_SETUP=1: the merged block-wise pass
   int cblk;               // phase C walks the preconditioner blocks (one thread per block) instead of the rows
   const double* binv;
   const double* b;
@@ -514,111 +515,199 @@ k_pcg_ebe(const EbeArgs a) {
     grid.sync();
   }
   const unsigned long long tp1 = ebe_now();
-  // ---- one pass over the rows: bt = s b_f - gather(ev), |bt|^2, r = bt - gather(ev2)  (4 rows in flight per thread) ----
-  double lbb = 0.0;
-  for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
-    int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
-    double bt[UNR], rw[UNR];
+  double bb = 0.0, rz = 0.0, rr = 0.0;
+  int it = 0;
+  unsigned long long tp2 = 0;
+  if (a.cblk && !a.row_setup) {
+    // ---- block-wise set-up: bt = s b_f - gather(ev), |bt|^2, r = bt - gather(ev2) AND z = Binv r, r.z, r.r in one pass: the rows of a
+    //      preconditioner block belong to one thread, so no grid barrier is needed between the residual and the preconditioner ----
+    double lbb = 0.0, lrz = 0.0, lrr0 = 0.0;
+    for (int64_t b = tid; b < a.n_blocks; b += nth) {
+      int k = 0;
+      if (a.bc.n > 1 && b >= a.bc.b0[1]) k = 1;
+      if (a.bc.n > 2 && b >= a.bc.b0[2]) k = 2;
+      const int m = a.bc.size[k], g = (int)b - a.bc.b0[k];
+      const int64_t r0 = a.bc.start[k] + (int64_t)g * m;
+      const double* __restrict__ B = a.binv + a.bc.off[k] + (int64_t)g * m * m;
+      int2 pr[3];
+      double bt[3], rw[3], Bm[9], r3[3];
+      uint8_t ob[3];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int64_t i = i0 + u * nth;
-      const bool ok = i < n;
-      ebe_row_sources(a, i, ok, lo[u], hi[u], s0[u], s1[u]);
-      bt[u] = ok ? a.scale_b * a.b[i] : 0.0;
-      rw[u] = 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (MI > 0) {
-        if (s0[u] >= 0) bt[u] -= a.ev[s0[u]];
-        if (s1[u] >= 0) bt[u] -= a.ev[s1[u]];
+      for (int j = 0; j < 3; ++j) {
+        const bool on = j < m;
+        pr[j] = on ? __ldg(a.pair + r0 + j) : make_int2(-1, -1);
+        bt[j] = on ? a.scale_b * a.b[r0 + j] : 0.0;
+        ob[j] = on ? (owned ? owned[r0 + j] : (uint8_t)1) : (uint8_t)0;
+        rw[j] = 0.0;
       }
-      if (a.warm) {
-        if (s0[u] >= 0) rw[u] = a.ev2[s0[u]];
-        if (s1[u] >= 0) rw[u] += a.ev2[s1[u]];
-      }
-    }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int64_t i = i0 + u * nth;
-      if (i >= n) continue;
-      for (int32_t k = lo[u] + 2; k < hi[u]; ++k) {
-        if (MI > 0) bt[u] -= a.ev[a.vsrc[k]];
-        if (a.warm) rw[u] += a.ev2[a.vsrc[k]];
-      }
-      r_old[i] = bt[u] - rw[u];
-      if (!owned || owned[i]) lbb = fma(bt[u], bt[u], lbb);
-      if (!a.warm) a.x[i] = 0.0;
-    }
-  }
-  lbb = ebe_block_sum(lbb, sh);
-  if (threadIdx.x == 0) P1[blockIdx.x] = lbb;
-  grid.sync();
-  double bb = ebe_grid_total(P1, nbk, sh);
-  if (multi) {
-    double v[1] = {bb};
-    dist_allreduce<1>(grid, a.dist, epoch, v);
-    bb = v[0];
-  }
-  const unsigned long long tp2 = ebe_now();
-  double lrz = 0.0, lrr0 = 0.0;
-  for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
-    int sb[UNR], mb[UNR], ro[UNR];
-    double zi[UNR], ri[UNR];
-    bool own[UNR];
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int64_t i = i0 + u * nth;
-      const bool ok = i < n;
-      own[u] = ok && (!owned || owned[i]);
-      sb[u] = 0; mb[u] = 0; ro[u] = 0;
-      if (ok) ebe_block_of(a, i, sb[u], mb[u], ro[u]);
-      if (!own[u]) mb[u] = 0;
-      ri[u] = ok ? r_old[i] : 0.0;
-      zi[u] = 0.0;
-      if (ok) a.p[i] = 0.0;
-    }
-    {
-      // block rows: the first MBU entries through predicated, fully unrolled loads (all in flight at once; a loop with a run-time
-      // trip count serialises one DRAM round trip per row), longer blocks finish in the loop
-      double bv[UNR][MBU], rv[UNR][MBU];
+        for (int l = 0; l < 3; ++l) Bm[j * 3 + l] = (j < m && l < m) ? B[j * m + l] : 0.0;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u)
-#pragma unroll
-        for (int j = 0; j < MBU; ++j) {
-          const bool on = j < mb[u];
-          bv[u][j] = on ? a.binv[ro[u] + j] : 0.0;
-          rv[u][j] = on ? r_old[sb[u] + j] : 0.0;
+      for (int j = 0; j < 3; ++j) {
+        if (MI > 0) {
+          if (pr[j].x >= 0) bt[j] -= a.ev[pr[j].x];
+          if (pr[j].y >= 0) bt[j] -= a.ev[pr[j].y];
         }
+        if (a.warm) {
+          if (pr[j].x >= 0) rw[j] = a.ev2[pr[j].x];
+          if (pr[j].y >= 0) rw[j] += a.ev2[pr[j].y];
+        }
+      }
+      if (a.tail) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j >= m) continue;
+          for (int32_t q = a.vptr[r0 + j] + 2; q < a.vptr[r0 + j + 1]; ++q) {
+            if (MI > 0) bt[j] -= a.ev[a.vsrc[q]];
+            if (a.warm) rw[j] += a.ev2[a.vsrc[q]];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        r3[j] = bt[j] - rw[j];
+        if (j >= m) continue;
+        r_old[r0 + j] = r3[j];
+        a.p[r0 + j] = 0.0;
+        if (!a.warm) a.x[r0 + j] = 0.0;
+        if (ob[j]) lbb = fma(bt[j], bt[j], lbb);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (!ob[j]) continue;
+        double zj = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+          if (l < m) zj = fma(Bm[j * 3 + l], r3[l], zj);
+        a.z[r0 + j] = zj;
+        lrz = fma(r3[j], zj, lrz);
+        lrr0 = fma(r3[j], r3[j], lrr0);
+      }
+    }
+    lbb = ebe_block_sum(lbb, sh);
+    lrz = ebe_block_sum(lrz, sh);
+    lrr0 = ebe_block_sum(lrr0, sh);
+    if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; P2[blockIdx.x] = lrr0; }
+    grid.sync();
+    if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
+    rz = ebe_grid_total(P0, nbk, sh);
+    bb = ebe_grid_total(P1, nbk, sh);
+    rr = ebe_grid_total(P2, nbk, sh);
+    if (multi) {
+      double v[3] = {rz, rr, bb};
+      dist_allreduce<3>(grid, a.dist, epoch, v);
+      rz = v[0]; rr = v[1]; bb = v[2];
+      dist_unpack(a.dist, a.z, tid, nth, n);
+    }
+    tp2 = ebe_now();
+  } else {
+    // ---- one pass over the rows: bt = s b_f - gather(ev), |bt|^2, r = bt - gather(ev2)  (4 rows in flight per thread) ----
+    double lbb = 0.0;
+    for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+      int32_t lo[UNR], hi[UNR], s0[UNR], s1[UNR];
+      double bt[UNR], rw[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
+        const int64_t i = i0 + u * nth;
+        const bool ok = i < n;
+        ebe_row_sources(a, i, ok, lo[u], hi[u], s0[u], s1[u]);
+        bt[u] = ok ? a.scale_b * a.b[i] : 0.0;
+        rw[u] = 0.0;
+      }
 #pragma unroll
-        for (int j = 0; j < MBU; ++j)
-          if (j < mb[u]) zi[u] = fma(bv[u][j], rv[u][j], zi[u]);
-        for (int j = MBU; j < mb[u]; ++j) zi[u] = fma(a.binv[ro[u] + j], r_old[sb[u] + j], zi[u]);
+      for (int u = 0; u < UNR; ++u) {
+        if (MI > 0) {
+          if (s0[u] >= 0) bt[u] -= a.ev[s0[u]];
+          if (s1[u] >= 0) bt[u] -= a.ev[s1[u]];
+        }
+        if (a.warm) {
+          if (s0[u] >= 0) rw[u] = a.ev2[s0[u]];
+          if (s1[u] >= 0) rw[u] += a.ev2[s1[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t i = i0 + u * nth;
+        if (i >= n) continue;
+        for (int32_t k = lo[u] + 2; k < hi[u]; ++k) {
+          if (MI > 0) bt[u] -= a.ev[a.vsrc[k]];
+          if (a.warm) rw[u] += a.ev2[a.vsrc[k]];
+        }
+        r_old[i] = bt[u] - rw[u];
+        if (!owned || owned[i]) lbb = fma(bt[u], bt[u], lbb);
+        if (!a.warm) a.x[i] = 0.0;
       }
     }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (!own[u]) continue;
-      a.z[i0 + u * nth] = zi[u];
-      lrz = fma(ri[u], zi[u], lrz);
-      lrr0 = fma(ri[u], ri[u], lrr0);
+    lbb = ebe_block_sum(lbb, sh);
+    if (threadIdx.x == 0) P1[blockIdx.x] = lbb;
+    grid.sync();
+    bb = ebe_grid_total(P1, nbk, sh);
+    if (multi) {
+      double v[1] = {bb};
+      dist_allreduce<1>(grid, a.dist, epoch, v);
+      bb = v[0];
     }
-  }
-  lrz = ebe_block_sum(lrz, sh);
-  lrr0 = ebe_block_sum(lrr0, sh);
-  if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P2[blockIdx.x] = lrr0; }
-  grid.sync();
-  if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
-  double rz = ebe_grid_total(P0, nbk, sh);
-  int it = 0;
-  double rr = ebe_grid_total(P2, nbk, sh);
-  if (multi) {
-    double v[2] = {rz, rr};
-    dist_allreduce<2>(grid, a.dist, epoch, v);
-    rz = v[0]; rr = v[1];
-    dist_unpack(a.dist, a.z, tid, nth, n);  // ghost z: from the exchange slot into the vector (the barrier below orders it)
+    tp2 = ebe_now();
+    double lrz = 0.0, lrr0 = 0.0;
+    for (int64_t i0 = tid; i0 < n; i0 += UNR * nth) {
+      int sb[UNR], mb[UNR], ro[UNR];
+      double zi[UNR], ri[UNR];
+      bool own[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t i = i0 + u * nth;
+        const bool ok = i < n;
+        own[u] = ok && (!owned || owned[i]);
+        sb[u] = 0; mb[u] = 0; ro[u] = 0;
+        if (ok) ebe_block_of(a, i, sb[u], mb[u], ro[u]);
+        if (!own[u]) mb[u] = 0;
+        ri[u] = ok ? r_old[i] : 0.0;
+        zi[u] = 0.0;
+        if (ok) a.p[i] = 0.0;
+      }
+      {
+        // block rows: the first MBU entries through predicated, fully unrolled loads (all in flight at once; a loop with a run-time
+        // trip count serialises one DRAM round trip per row), longer blocks finish in the loop
+        double bv[UNR][MBU], rv[UNR][MBU];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int j = 0; j < MBU; ++j) {
+            const bool on = j < mb[u];
+            bv[u][j] = on ? a.binv[ro[u] + j] : 0.0;
+            rv[u][j] = on ? r_old[sb[u] + j] : 0.0;
+          }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+          for (int j = 0; j < MBU; ++j)
+            if (j < mb[u]) zi[u] = fma(bv[u][j], rv[u][j], zi[u]);
+          for (int j = MBU; j < mb[u]; ++j) zi[u] = fma(a.binv[ro[u] + j], r_old[sb[u] + j], zi[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (!own[u]) continue;
+        a.z[i0 + u * nth] = zi[u];
+        lrz = fma(ri[u], zi[u], lrz);
+        lrr0 = fma(ri[u], ri[u], lrr0);
+      }
+    }
+    lrz = ebe_block_sum(lrz, sh);
+    lrr0 = ebe_block_sum(lrr0, sh);
+    if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P2[blockIdx.x] = lrr0; }
+    grid.sync();
+    if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
+    rz = ebe_grid_total(P0, nbk, sh);
+    rr = ebe_grid_total(P2, nbk, sh);
+    if (multi) {
+      double v[2] = {rz, rr};
+      dist_allreduce<2>(grid, a.dist, epoch, v);
+      rz = v[0]; rr = v[1];
+      dist_unpack(a.dist, a.z, tid, nth, n);  // ghost z: from the exchange slot into the vector (the barrier below orders it)
+    }
   }
   double beta = 0.0;
   unsigned long long tA = 0, tB = 0, tC = 0, tR = 0, tP = 0;
@@ -1186,7 +1275,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.ccell = s->compressed && s->tile_smem && (force_tiles || s->nc >= (int64_t)s->grid * 256) ? s->ccell.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
-  a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr;
+  a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr; a.row_setup = getenv("GG_EBE_BLOCK_SETUP") == nullptr;
   for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; a.bc.b0[k] = s->bc_b0[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
