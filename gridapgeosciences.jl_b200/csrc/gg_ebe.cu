@@ -327,7 +327,7 @@ struct EbeArgs {
   struct { int n; int start[3], size[3], off[3], b0[3]; } bc;   // b0: index of the first block of the run
   int64_t n_blocks;
   int bc_rows;            // the row loops also use the arithmetic lookup (measured: 1 us slower than the arrays; GG_EBE_BLOCK_CLASSES=1)
-  int row_setup;          // the two row-wise set-up passes (default); GG_EBE_BLOCK_SETUP=1: the merged block-wise pass
+  int row_setup;          // the two row-wise set-up passes instead of the merged block-wise one (chosen by mesh size)
   int cblk;               // phase C walks the preconditioner blocks (one thread per block) instead of the rows
   const double* binv;
   const double* b;
@@ -1275,7 +1275,14 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   a.ccell = s->compressed && s->tile_smem && (force_tiles || s->nc >= (int64_t)s->grid * 256) ? s->ccell.p : nullptr;
   a.sg = s->compressed ? sp->d_cell_signs.p : nullptr;
   a.vptr = sp->d_vptr.p; a.vsrc = sp->d_vsrc.p; a.pair = s->pair.p; a.tail = s->tail;
-  a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr; a.row_setup = getenv("GG_EBE_BLOCK_SETUP") == nullptr;
+  a.bc.n = s->bc_n; a.n_blocks = s->n_blocks; a.cblk = s->cblk; a.bc_rows = getenv("GG_EBE_BLOCK_CLASSES") != nullptr; 
+  // merged block-wise set-up pass: one grid barrier less, which pays on small meshes (48^2 wave test: 14.3 -> 11.9 us per solve); on
+  // large ones its three dependent load levels lose to the two row passes (256^2 RT_2: 91 -> 106 us), so it is chosen by size
+  // (GG_EBE_BLOCK_SETUP=1 / 0 force it on / off)
+  {
+    const char* e = getenv("GG_EBE_BLOCK_SETUP");
+    a.row_setup = e ? (e[0] == '0') : (s->n_blocks > (int64_t)s->grid * 256);
+  }
   for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; a.bc.b0[k] = s->bc_b0[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
   a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;

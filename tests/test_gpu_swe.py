@@ -195,7 +195,8 @@ def test_solver_variants_of_the_condensed_pcg_agree():
     import os
     import subprocess
     import sys
-    for extra in ({"GG_EBE_TILES": "2"}, {"GG_EBE_ROW_UPDATE": "1", "GG_EBE_ROW_POINTERS": "1", "GG_EBE_TILES": "0"}):
+    for extra in ({"GG_EBE_TILES": "2", "GG_EBE_BLOCK_SETUP": "1"},
+                  {"GG_EBE_ROW_UPDATE": "1", "GG_EBE_ROW_POINTERS": "1", "GG_EBE_TILES": "0", "GG_EBE_BLOCK_SETUP": "0"}):
         out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                               "steps_match_oracle or diagnostics_and_stage"], env=dict(os.environ, **extra), capture_output=True,
                              text=True, timeout=900)
