@@ -76,3 +76,19 @@ def test_surface_stokes_driver_converges():
     assert np.polyfit(h, np.log10([e[0] for e in errs]), 1)[0] >= 2          # eu_h1: the slope the reference tests
     assert np.polyfit(h, np.log10([e[1] for e in errs]), 1)[0] >= 1.8        # Q1 pressure, pre-asymptotic on 2x2 panels
     assert np.polyfit(h, np.log10([e[2] for e in errs]), 1)[0] >= 3
+
+
+def test_divergence_coupling_matches_the_closed_form_surface_divergence():
+    """b(u, q) = int q D1(u) with D1(u) = div(sqrtg u) = sqrtg div_s(u): applied to the interpolant of uX it must approach
+    int q div_s(uX) sqrtg, div_s from the closed-form branch that the reference's SurfDiffOperatorTests pin (oracle/forms.py)."""
+    from oracle.spaces import CGSpace
+    res = []
+    for n in (4, 8):
+        mesh = CubedSphereMesh2D(n)
+        V, Q = vh.VectorCGSpace(mesh, 2), CGSpace(mesh, 1)
+        q = forms.CellQuadrature(mesh, 18)
+        B = forms.assemble_matrix(Q, V, ss.div_element_matrices(Q, V, q))
+        sigma = forms.surface_divergence(uX, grad_uX, mesh, q.x, mesh.cell_to_chart)
+        rhs = forms.assemble_vector(Q, forms.source_element_vectors(Q, q, sigma))
+        res.append(np.abs(B @ vh.interpolate(V, uX) - rhs).max() / np.abs(rhs).max())
+    assert res[0] < 2e-2 and res[1] < 0.3 * res[0]
