@@ -8,9 +8,11 @@ Metric (BASELINE.json): cells/s assembled (residual + Jacobian).  One step = one
 Jacobian (CSR values) + residual (DOF vector) assembly over all cells of the rank's mesh slice:
 CG-Q2, quadrature degree 18 (10x10 Gauss points per cell) -- the reference's own choice 6*(p+1)
 (test/Laplacian/LaplaceBeltrami.jl:29) -- on a 256x256-per-panel cubed sphere (393 216 cells) at N=1.
-N>1 is WEAK scaling: the global mesh has round(256*sqrt(N))^2 cells per panel, every rank assembles its slice of
-the reference's linear partition (owned cells + vertex-adjacent ghost layer, so that owned rows are complete
-without any reverse exchange); there is no data-path collective in assembly.
+N>1 is STRONG scaling by default (the named configuration, BASELINE configs[3]: 256x256 per panel partitioned over the N
+ranks): every rank assembles its slice of the reference's linear partition (owned cells + vertex-adjacent ghost layer, so
+that owned rows are complete without any reverse exchange); there is no data-path collective in assembly.  The weak-scaling
+numbers (round(256*sqrt(N))^2 cells per panel) are reported beside it under `weak`; `--scaling weak` makes them the headline.
+A small partitioned-vs-single-GPU parity run (tests/dist_worker.py) is embedded in every N>1 run (`dist_parity`).
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/c, OpenMP over cells) on the
 box's host cores: the real reference (Julia + Gridap) cannot run in this image (no Julia, no network).
 """
@@ -39,8 +41,16 @@ BYTES_RES = 36 + 72 + 32
 METRIC = "cells/s assembled (residual+Jacobian)"
 
 
-def mesh_n(nranks):
-    return int(round(N_BASE * math.sqrt(nranks)))
+def mesh_n(nranks, scaling="strong"):
+    return N_BASE if scaling == "strong" else int(round(N_BASE * math.sqrt(nranks)))
+
+
+def workload_config(n, world, scaling):
+    """`config` of the JSON line: the same keys and values in both arms (`--impl b200` and `--impl reference`)."""
+    return {"workload": f"laplace_beltrami_cgq2_deg18_n{n}_per_panel", "cells": 6 * n * n, "order": ORDER,
+            "quadrature_degree": DEGREE, "partition": f"linear x{world}" if world > 1 else "single", "scaling_mode": scaling,
+            "l2": "working set per step (element buffer, maps and CSR values of the rank's slice; ~0.6 GB at N=1) exceeds the 126 MB "
+                  "L2 for N <= 4; at N = 8 (75 MB per rank) an L2 flush (write of a 256 MB buffer) runs between timed steps"}
 
 
 class ClockSampler:
@@ -318,8 +328,8 @@ def cpu_baseline_run(nthreads, target_seconds=12.0):
     for _ in range(reps):
         Ke = c_oracle.lb_element_matrices(cc, 1.0, ORDER, DEGREE, nthreads)
         fe = c_oracle.lb_element_vectors(cc, 1.0, ORDER, DEGREE, ue[:ns], nthreads)
-        vals = c_oracle.scatter_csr(V.cell_dofs[:ns], Ke, rowptr, colind)
-        r = c_oracle.scatter_vector(V.cell_dofs[:ns], fe, V.num_free)
+        vals = c_oracle.scatter_csr(V.cell_dofs[:ns], Ke, rowptr, colind, nthreads)
+        r = c_oracle.scatter_vector(V.cell_dofs[:ns], fe, V.num_free, nthreads)
     dt = time.perf_counter() - t0
     assert np.isfinite(vals).all() and np.isfinite(r).all()
     return ns * reps / dt, threads, f"{reps} pass(es) over {ns} cells of the Q2/degree-18 Laplace-Beltrami residual+Jacobian " \
@@ -339,19 +349,180 @@ def run_reference(args):
         if i >= warm:
             vals.append(v)
     value = float(np.mean(vals))
-    ncells = 6 * mesh_n(args.gpus) ** 2
+    n = mesh_n(args.gpus, args.scaling)
+    ncells = 6 * n * n
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 * ncells / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * ncells / value, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"laplace_beltrami_cgq2_deg18_n{mesh_n(args.gpus)}_per_panel", "cells": ncells,
-                   "note": "CPU restatement of the reference algorithm (oracle/c, not Gridap: Julia is absent); "
-                           "ms_per_step extrapolates the sampled rate to the full mesh"},
+        "config": workload_config(n, args.gpus, args.scaling),
+        "note": "CPU restatement of the reference algorithm (oracle/c, not Gridap: Julia is absent), all host cores of this "
+                "process (OpenMP over cells stands in for the reference's MPI ranks); every step TIMES A BOUNDED SAMPLE of the "
+                "workload's cells (see cpu_baseline.sample) and `value` is that sampled rate; ms_per_step extrapolates it to the "
+                "full mesh of `config`",
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+class L2Flush:
+    """Write of a buffer larger than the 126 MB L2 between timed steps, for rank slices whose working set would otherwise stay
+    L2-resident from one step to the next (strong scaling at N >= 4)."""
+
+    def __init__(self, torch, stream, device):
+        self.torch, self.stream = torch, stream
+        with torch.cuda.stream(stream):
+            self.buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
+
+    def __call__(self):
+        with self.torch.cuda.stream(self.stream):
+            self.buf.fill_(1.0)
+
+
+def timed_steps(torch, stream, step, K, flush=None):
+    """ms per step on the library's stream with CUDA events.  Without flush: one event pair around K back-to-back steps.
+    With flush: the L2 is flushed before every step and each step has its own event pair (the flush is outside them)."""
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in ev:
+        flush()
+        a.record(stream)
+        step()
+        b.record(stream)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) / K
+
+
+def max_over_ranks(torch, dist, world, x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def assembly_leg(gg, ctx, torch, dist, stream, n, rank, world, W, K, profile=True):
+    """One rank's slice of the n x n-per-panel Laplace-Beltrami residual + Jacobian assembly (Q2, degree 18)."""
+    mesh = gg.CubedSphereMesh(1.0)
+    keep = None
+    if world > 1:
+        # linear partition of the reference + vertex-adjacent ghost layer; local DOF numbering = the global numbering
+        # restricted to the local cells (compact: vectors and row pointers have the size of the slice)
+        keep = gg.PartitionPlan(n, world, rank)
+        model = gg.partitioned_model(mesh, keep, None, ctx=ctx)
+        ncells_global, owned = keep.num_cells_global, keep.last_owned - keep.first_owned
+    else:
+        model = gg.AtlasDiscreteModel(mesh, n=n, ctx=ctx)
+        ncells_global = owned = model.num_cells
+    dΩ = gg.Measure(gg.Triangulation(model), DEGREE)
+    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, ORDER), conformity="H1")
+    assem = gg.SparseMatrixAssembler(V, V)           # device CSR pattern, built once
+    A = assem.matrix
+    u_host = torch.from_numpy(np.random.default_rng(SEED + rank).standard_normal(V.num_free_dofs)).pin_memory()
+    u = gg.DeviceVector.from_numpy(ctx, u_host.numpy())
+    b = gg.DeviceVector(ctx, V.num_free_dofs)
+    form = gg.LaplaceBeltrami(dΩ, u=u)
+
+    def step():
+        gg.assemble_matrix_and_vector(form, assem, b)
+
+    ws_bytes = 8.0 * (45 * model.num_cells + A.nnz) + 6.0 * 81 * model.num_cells
+    flush = L2Flush(torch, stream, ctx.device) if ws_bytes < 2 * 126e6 else None
+    ctx.set_async(True)
+    for _ in range(W):
+        step()
+    ctx.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    ms = timed_steps(torch, stream, step, K, flush)
+    launches = ctx.launches - l0
+    ms = max_over_ranks(torch, dist, world, ms)
+    out = {"n": n, "cells": ncells_global, "owned": owned, "cells_local_incl_ghosts": model.num_cells, "ms_per_step": ms,
+           "value": ncells_global / (ms * 1e-3), "launches": launches, "dofs_local": V.num_free_dofs, "nnz_local": A.nnz,
+           "l2_flush_between_steps": flush is not None}
+    if profile:
+        ctx.profile(True)
+        for _ in range(K):
+            if flush:
+                flush()
+            step()
+        ctx.synchronize()
+        out["prof"] = {name: ctx.profile_query(name) for name in ASSEMBLY_KERNELS}
+        ctx.profile(False)
+    ctx.set_async(False)
+    out["objs"] = (model, V, assem, A, u, u_host, b, form, step, keep, flush)
+    return out
+
+
+# FP64 operations the fused element kernel EXECUTES per cell (Q2, 10x10 points; counted from its SASS: 545 static DFMA, the
+# sum-factorised contractions run ~5.1 k DFMA per thread, plus the residual mat-vec, the metric and the rsqrt refinement)
+EXECUTED_FLOPS_PER_CELL = 2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60
+
+
+def assembly_roofline(prof, ncell_local, nnz, ms_per_step, fp64_peak, hbm_peak, have_peaks):
+    """Roofline block of the headline step from the per-kernel CUDA-event times of THIS run.  The FP64 element kernel is
+    reported against the DFMA probe run in this process, the CSR fill against the measured copy bandwidth."""
+    k_ms = prof["k_lb_fast"][1] / max(prof["k_lb_fast"][0], 1)
+    g_ms = prof["k_gather_chunks"][1] / max(prof["k_gather_chunks"][0], 1)
+    d_ms = prof["k_gather_dofs"][1] / max(prof["k_gather_dofs"][0], 1)
+    executed = EXECUTED_FLOPS_PER_CELL * ncell_local / (k_ms * 1e-3) / 1e12 if k_ms else None
+    naive = (FLOPS_JAC + FLOPS_RES) * ncell_local / (k_ms * 1e-3) / 1e12 if k_ms else None
+    # bytes the CSR fill must move at least: packed element entries in + values out (maps are extra traffic)
+    gather_bytes = 8.0 * (45 * ncell_local + nnz)
+    return {
+        "kernel": "k_lb_fast<3,10> (fused Q2 element matrix + residual, one thread per cell)",
+        "bound": "fp64", "unit": "TFLOP/s",
+        "achieved": executed, "peak": fp64_peak, "frac": executed / fp64_peak if (executed and fp64_peak) else None,
+        "achieved_is": "FP64 operations the kernel executes (sum-factorised: ~13 kFLOP per cell, EXECUTED_FLOPS_PER_CELL in bench.py) "
+                       "/ kernel time measured in this run with CUDA events on the library's stream",
+        "peak_source": "FP64 DFMA probe run in this process (gg_measure_fp64_peak, also `fp64_tflops_probe`); MEASURED_PEAKS.json has "
+                       "no FP64 figure",
+        "algorithmic": {"tflops": naive, "frac": naive / fp64_peak if (naive and fp64_peak) else None,
+                        "note": "SURVEY.md §8(d)'s per-cell count of the reference algorithm (45 600 + 14 000 FLOP) / the same kernel "
+                                "time: exceeds 1 because the kernel does not execute that many operations"},
+        "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
+        "step_level": {"fp64_work_ms_at_probe_peak": EXECUTED_FLOPS_PER_CELL * ncell_local / (fp64_peak * 1e12) * 1e3 if fp64_peak else None,
+                       "frac_of_step": (EXECUTED_FLOPS_PER_CELL * ncell_local / (fp64_peak * 1e12) * 1e3) / ms_per_step if fp64_peak else None,
+                       "kernels_ms": {"k_lb_fast": k_ms, "k_gather_chunks": g_ms, "k_gather_dofs": d_ms}},
+        "traffic": None,
+        "from_profile": {"file": "profiles/ncu_lb_assembly_r01_final.txt", "workload": "N=1, 393 216 cells",
+                         "k_lb_fast": {"dram_bytes_per_cell": 378.4, "fp64_pipe_active_pct": 81.3},
+                         "k_gather_chunks": {"dram_bytes_per_cell": 1462.8, "note": "575 MB per launch, of which 190 MB gather lists"}},
+        "csr_fill": {"kernel": "k_gather_chunks", "bound": "hbm", "unit": "GB/s", "kernel_ms": g_ms,
+                     "achieved": gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None, "peak": hbm_peak,
+                     "frac": gather_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
+                     "algorithmic_bytes": "8 B x (45 packed element entries per cell read + every CSR value written once)",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s"},
+    }
+
+
+def assembly_limiter(leg, roofline, world):
+    """What bounds the strong-scaled assembly step on this rank count, from this run's own numbers."""
+    k = roofline["step_level"]["kernels_ms"]
+    ksum = sum(v for v in k.values() if v)
+    ghost = leg["cells_local_incl_ghosts"] / max(leg["owned"], 1) - 1.0
+    gap = leg["ms_per_step"] - ksum
+    if gap > 0.25 * leg["ms_per_step"]:
+        what = f"launch / tail latency: the 3 kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step"
+    elif ghost > 0.1:
+        what = f"redundant ghost-layer cells: {100 * ghost:.1f} % more cells than owned"
+    else:
+        what = "the same kernels as at N=1 (FP64 pipe + CSR fill), on 1/N of the cells"
+    return {"what": what, "kernel_ms_sum": ksum, "ghost_cell_overhead": ghost, "cells_per_sm": leg["cells_local_incl_ghosts"] / 148.0}
+
+
+ASSEMBLY_KERNELS = ("k_lb_fast", "k_gather_chunks", "k_gather_dofs")
 
 
 def main():
@@ -360,6 +531,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the named 256x256-per-panel mesh partitioned over the ranks (default); weak = 256 sqrt(N)")
     ap.add_argument("--no-extras", action="store_true", help="skip the RK-steps/s, e2e and CPU-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -383,6 +556,7 @@ def main():
     ctx = gg.get_context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     W, K = max(args.warmup, 3), max(args.steps, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
@@ -390,115 +564,42 @@ def main():
         torch.cuda.synchronize()
         ctx.synchronize()
 
-    # ---- the rank's slice of the (weak-scaled) mesh --------------------------------------------------
-    n = mesh_n(world)
-    full = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n, ctx=ctx)
-    ncells_global = full.num_cells
-    if world > 1:
-        a, b = gg.partition_range(ncells_global, world, rank)
-        cells = np.sort(np.concatenate([np.arange(a, b), full.ghost_cells(a, b)]))
-        model = full.restrict(cells)
-        owned = b - a
-        del full
-    else:
-        model, owned = full, ncells_global
-    dΩ = gg.Measure(gg.Triangulation(model), DEGREE)
-    V = gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, ORDER), conformity="H1")
-    assem = gg.SparseMatrixAssembler(V, V)           # device CSR pattern, built once
-    A = assem.matrix
-    u_host = torch.from_numpy(np.random.default_rng(SEED + rank).standard_normal(V.num_free_dofs)).pin_memory()
-    u = gg.DeviceVector.from_numpy(ctx, u_host.numpy())
-    b = gg.DeviceVector(ctx, V.num_free_dofs)
-    form = gg.LaplaceBeltrami(dΩ, u=u)
-
-    def step():
-        gg.assemble_matrix_and_vector(form, assem, b)
-
-    # ---- device-resident timing ------------------------------------------------------------------------
-    ctx.set_async(True)
+    # ---- headline: the rank's slice of the mesh, device-resident timing --------------------------------------------
+    n = mesh_n(world, args.scaling)
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(W):
-        step()
-    barrier()
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        step()
-    e1.record(stream)
-    barrier()
-    launches = ctx.launches - l0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        tot = torch.tensor([float(owned)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot)
-        total_owned = int(tot.item())
-    else:
-        total_owned = owned
-    ms_per_step = ms / K
-    value = total_owned / (ms_per_step * 1e-3)
-
-    # ---- per-kernel timing of the dominant kernel (CUDA events on the launching stream) -------------------------
-    ctx.profile(True)
-    for _ in range(K):
-        step()
-    ctx.synchronize()
-    prof = {name: ctx.profile_query(name) for name in ("k_lb_fast", "k_gather_chunks", "k_gather_dofs")}
-    ctx.profile(False)
+    leg = assembly_leg(gg, ctx, torch, dist, stream, n, rank, world, W, K)
+    model, V, assem, A, u, u_host, b, form, step, _plan, flush = leg["objs"]
+    ms_per_step, value, launches, prof = leg["ms_per_step"], leg["value"], leg["launches"], leg["prof"]
+    total_owned, ncells_global, ncell_local = leg["cells"], leg["cells"], leg["cells_local_incl_ghosts"]
     # keep the GPU under the same load until the sampler has seen it (the timed region itself is a few ms long)
+    ctx.set_async(True)
     t_end = time.perf_counter() + 0.6
     while time.perf_counter() < t_end:
         for _ in range(K):
             step()
         ctx.synchronize()
+    ctx.set_async(False)
     clocks = sampler.stop() if sampler else None
     fp64_peak = ctx.measure_fp64_peak()
-    ncell_local = model.num_cells
-    k_ms = prof["k_lb_fast"][1] / max(prof["k_lb_fast"][0], 1)
-    achieved = (FLOPS_JAC + FLOPS_RES) * ncell_local / (k_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    g_ms = prof["k_gather_chunks"][1] / max(prof["k_gather_chunks"][0], 1)
-    # bytes the CSR fill must move at least: packed element entries in + values out (maps are extra traffic)
-    gather_bytes = 8.0 * (45 * ncell_local + A.nnz)
-    roofline = {
-        "kernel": "k_lb_fast<3,10> (fused Q2 element matrix + residual, one thread per cell)",
-        "bound": "fp64", "unit": "TFLOP/s",
-        "achieved": achieved, "peak": fp64_peak, "frac": achieved / fp64_peak if fp64_peak else None,
-        "peak_source": "FP64 DFMA probe run in this process (gg_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-        "achieved_is": "ALGORITHMIC FLOPs of SURVEY.md §8(d) (45 600 + 14 000 per cell) / measured kernel time; the kernel is "
-                       "sum-factorised and executes ~13 kFLOP per cell, so frac can exceed 1",
-        "executed_tflops": (2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60) * ncell_local / (k_ms * 1e-3) / 1e12,
-        "frac_executed": ((2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60) * ncell_local / (k_ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
-        "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-        # command (profiles/ncu_lb_assembly_r01_final.txt: 148.8 MB for 393 216 cells = 378.4 B/cell), scaled to this launch
-        "traffic": 378.4 * ncell_local, "traffic_unit": "bytes per launch (ncu, round 1 capture)",
-        "fp64_pipe_active_pct_ncu": 81.3,
-        "csr_fill": {"kernel": "k_gather_chunks", "bound": "hbm", "unit": "GB/s", "kernel_ms": g_ms,
-                     "achieved": gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None, "peak": hbm_peak,
-                     "frac": gather_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "traffic": 1462.8 * ncell_local, "traffic_note": "ncu: 575 MB per launch at 393 216 cells (5.06 TB/s = 78 % of the measured copy bandwidth), of which 190 MB gather lists"},
-    }
+    roofline = assembly_roofline(prof, ncell_local, A.nnz, ms_per_step, fp64_peak, hbm_peak, bool(peaks))
 
     line = {
         "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"laplace_beltrami_cgq2_deg18_n{n}_per_panel", "cells": ncells_global, "order": ORDER,
-                   "quadrature_degree": DEGREE, "dofs_local": V.num_free_dofs, "nnz_local": A.nnz,
-                   "cells_local_incl_ghosts": ncell_local, "partition": f"linear x{world}" if world > 1 else "single",
-                   "l2": "working set per step (~0.6 GB of element buffer, maps and CSR values) exceeds the 126 MB L2"},
-        "roofline": roofline, "clocks": clocks, "gpu_launches": launches,
+        "config": workload_config(n, world, args.scaling),
+        "sizes": {"dofs_local": V.num_free_dofs, "nnz_local": A.nnz, "cells_local_incl_ghosts": ncell_local,
+                  "cells_owned_rank0": leg["owned"], "l2_flush_between_steps": leg["l2_flush_between_steps"]},
+        "roofline": roofline, "fp64_tflops_probe": fp64_peak, "clocks": clocks, "gpu_launches": launches,
     }
+    if world > 1:
+        line["limiter"] = assembly_limiter(leg, roofline, world)
 
     # ---- opt-in variant: one element matrix per geometry class (the 6 panels are congruent), same numbers bit for bit ------
     if not args.no_extras and world == 1:
@@ -633,6 +734,7 @@ def main():
             except Exception as ex:
                 line["rk"]["thermal_shallow_water"] = {"error": str(ex)}
 
+
     # ---- 3-D shell (BASELINE configs[4]): hexahedral Q2 Laplace-Beltrami residual + Jacobian, 48^3 cells per panel ---------
     if not args.no_extras and rank == 0 and world == 1:
         try:
@@ -640,23 +742,59 @@ def main():
         except Exception as ex:
             line["shell"] = {"error": str(ex)}
 
-    # ---- RK steps/s on N GPUs: the partitioned shallow-water stepper, weak scaling (every rank takes part) -------------
-    if not args.no_extras and world > 1:
+    # ---- N > 1: partitioned-vs-single-GPU parity on a small mesh, then the RK legs on the partitioned models ----------------
+    if world > 1:
+        del leg, model, V, assem, A, u, b, form, step
         try:
-            sh = shell_leg(gg, ctx, torch, stream, e0, e1, n=int(round(48 * world ** (1.0 / 3.0))), dist=dist, rank=rank, world=world)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import dist_worker
+            dp = {}
+            for (pn, pp) in ((6, 1), (5, 2)):
+                r = dist_worker.run_checks(gg, ctx, rank, world, pn, pp)
+                dp[f"n{pn}_p{pp}"] = r
+            line["dist_parity"] = {"ok": True, "tolerances": {"wave": 1e-10, "swe": 1e-9, "pv": 1e-8, "thermal_swe": 1e-9, "advection": 1e-12},
+                                   "wave": max(v["wave"] for v in dp.values()), "swe": max(v["swe"] for v in dp.values()),
+                                   "advection": max(v["advection"] for v in dp.values()),
+                                   "pcg_iters_equal": all(v["pcg_iters_equal"] for v in dp.values()),
+                                   "consistent_exact": all(v["consistent_exact"] for v in dp.values()), "cases": dp,
+                                   "what": "tests/dist_worker.py run_checks: partitioned steppers (halo + all-reduce through peer memory) "
+                                           "against the single-GPU run of the same problem; max relative state difference after 3-4 steps"}
         except Exception as ex:
-            sh = {"error": str(ex)}
-        line["shell"] = sh
+            line["dist_parity"] = {"ok": False, "error": str(ex)[-400:]}
+    if not args.no_extras and world > 1:
+        nn = mesh_n(world, args.scaling)
         try:
-            sw = swe_leg(gg, ctx, torch, stream, e0, e1, n=n, dist=dist, rank=rank, world=world)
+            sw = swe_leg(gg, ctx, torch, stream, e0, e1, n=nn, dist=dist, rank=rank, world=world)
         except Exception as ex:
             sw = {"error": str(ex)}
         line.setdefault("rk", {})["shallow_water"] = sw
         try:
-            ad = adv_leg(gg, ctx, torch, stream, e0, e1, n=int(round(128 * math.sqrt(world))), dist=dist, rank=rank, world=world)
+            ad = adv_leg(gg, ctx, torch, stream, e0, e1, n=128 if args.scaling == "strong" else int(round(128 * math.sqrt(world))),
+                         dist=dist, rank=rank, world=world)
         except Exception as ex:
             ad = {"error": str(ex)}
         line["rk"]["advection"] = ad
+        try:
+            sh = shell_leg(gg, ctx, torch, stream, e0, e1, n=48 if args.scaling == "strong" else int(round(48 * world ** (1.0 / 3.0))),
+                           dist=dist, rank=rank, world=world)
+        except Exception as ex:
+            sh = {"error": str(ex)}
+        line["shell"] = sh
+        # the other scaling mode beside the headline: same legs, fewer steps
+        other = "weak" if args.scaling == "strong" else "strong"
+        try:
+            no = mesh_n(world, other)
+            lw = assembly_leg(gg, ctx, torch, dist, stream, no, rank, world, 3, max(5, K // 2), profile=False)
+            lw.pop("objs")
+            ow = {"assembly": {k: lw[k] for k in ("n", "cells", "ms_per_step", "value", "cells_local_incl_ghosts", "dofs_local")}}
+            del lw
+            try:
+                ow["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1, n=no, steps=6, dist=dist, rank=rank, world=world)
+            except Exception as ex:
+                ow["shallow_water"] = {"error": str(ex)}
+            line[other] = ow
+        except Exception as ex:
+            line[other] = {"error": str(ex)}
 
     # ---- CPU baseline beside it (rank 0, N=1) -------------------------------------------------------------------
     if not args.no_extras and rank == 0 and world == 1:

@@ -530,6 +530,22 @@ class CSRMatrix:
         rp, ci = self.pattern()
         return sp.csr_matrix((self.values(), ci, rp), shape=self.shape)
 
+    def to_scipy_csc(self, index_base=0):
+        """The matrix as Julia's SparseMatrixCSC sees it (`gg_csr_export_csc`): colptr, rowval, nzval."""
+        import scipy.sparse as sp
+        cp = np.empty(self.shape[1] + 1, dtype=np.int64)
+        rv = np.empty(self.nnz, dtype=np.int64)
+        nz = np.empty(self.nnz)
+        _lib.check(self.lib.gg_csr_export_csc(self.h, _ip64(cp), _ip64(rv), _dp(nz), index_base))
+        if index_base:
+            return cp, rv, nz
+        return sp.csc_matrix((nz, rv, cp), shape=self.shape)
+
+    def csc_values(self, out=None):
+        out = np.empty(self.nnz) if out is None else out
+        _lib.check(self.lib.gg_csr_export_csc(self.h, None, None, _dp(out), 0))
+        return out
+
     def spmv(self, x, y, alpha=1.0, beta=0.0):
         _lib.check(self.lib.gg_csr_spmv(self.h, alpha, x.h, beta, y.h))
 

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GG_LIB_PATH") or os.path.join(_HERE, "libgeosgpu.so")   # GG_LIB_PATH: development builds
 
 GG_OK = 0
-ERRORS = {-1: "GG_ERR_INVALID", -2: "GG_ERR_CUDA", -3: "GG_ERR_UNSUPPORTED", -4: "GG_ERR_NOMEM", -5: "GG_ERR_NOCONV"}
+ERRORS = {-1: "GG_ERR_INVALID", -2: "GG_ERR_CUDA", -3: "GG_ERR_UNSUPPORTED", -4: "GG_ERR_NOMEM", -5: "GG_ERR_NOCONV", -6: "GG_ERR_COMM"}
 
 SPACE_CG, SPACE_DG, SPACE_RT, SPACE_CGV = 0, 1, 2, 3
 CONSTRAINT_NONE, CONSTRAINT_ZEROMEAN = 0, 1
@@ -116,6 +116,7 @@ SIGNATURES = {
     "gg_assemble_advection": (C.c_int, [_P, C.c_int32, _PD, _PD, _P]),
     "gg_csr_info": (C.c_int, [_P, _PI64, _PI64, _PI64]),
     "gg_csr_export": (C.c_int, [_P, _PI64, _PI64, _PD, C.c_int]),
+    "gg_csr_export_csc": (C.c_int, [_P, _PI64, _PI64, _PD, C.c_int]),
     "gg_csr_device_values": (C.c_void_p, [_P]),
     "gg_csr_spmv": (C.c_int, [_P, C.c_double, _P, C.c_double, _P]),
     "gg_csr_destroy": (None, [_P]),

@@ -1,4 +1,5 @@
 // Context, error reporting and device vectors of the C ABI (include/geosgpu.h).
+#include <mutex>
 #include "gg_common.cuh"
 
 namespace gg {
@@ -30,6 +31,11 @@ using namespace gg;
 
 extern "C" {
 
+// live contexts per device: the __constant__ tables the contexts key (const_order, swe_key, ebe_key, ...) are per device and
+// per process, so a second context on the same device would run with the first one's tables
+static std::mutex g_live_mutex;
+static int g_live_ctx[64] = {0};
+
 int gg_init(int device_id, gg_ctx** out) {
   GG_API_BEGIN
   GG_REQUIRE(out, GG_ERR_INVALID, "null output");
@@ -45,6 +51,14 @@ int gg_init(int device_id, gg_ctx** out) {
   GG_REQUIRE(prop.major == 10, GG_ERR_UNSUPPORTED,
              std::string("libgeosgpu is built for sm_100a (B200) only; found ") + prop.name + " (sm_" +
                  std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  {
+    std::lock_guard<std::mutex> lock(g_live_mutex);
+    GG_REQUIRE(device_id < 64 && g_live_ctx[device_id] == 0, GG_ERR_INVALID,
+               "a context already exists on this device in this process (one gg_ctx per process and GPU: the resident "
+               "__constant__ tables are keyed per context); gg_finalize it first");
+    g_live_ctx[device_id] = 1;
+  }
+  struct Unclaim { int dev; bool armed = true; ~Unclaim() { if (armed) { std::lock_guard<std::mutex> l(g_live_mutex); g_live_ctx[dev] = 0; } } } unclaim{device_id};
   std::unique_ptr<gg_ctx> ctx(new gg_ctx);
   ctx->device = device_id;
   ctx->sm_count = prop.multiProcessorCount;
@@ -58,6 +72,7 @@ int gg_init(int device_id, gg_ctx** out) {
   for (auto& e : ctx->ev_batch) GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ctx->geometry_classes = getenv("GG_LB_CLASSES") && getenv("GG_LB_CLASSES")[0] == '1';
   GG_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  unclaim.armed = false;
   *out = ctx.release();
   GG_API_END
 }
@@ -65,6 +80,7 @@ int gg_init(int device_id, gg_ctx** out) {
 void gg_finalize(gg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  { std::lock_guard<std::mutex> lock(g_live_mutex); if (ctx->device >= 0 && ctx->device < 64) g_live_ctx[ctx->device] = 0; }
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
   }

@@ -276,6 +276,12 @@ struct gg_csr {
   static constexpr int N_BATCH = 8;   // upper bound; pipeline_batches() gives the count in use
   gg::DevBuf<int32_t> d_chunk_order;       // [n_chunks] chunk ids sorted by completing batch
   int64_t batch_chunk_ptr[N_BATCH + 1] = {0};
+  // CSC view (gg_csr_export_csc), built at the first export: column pointers and row indices on the host, and the
+  // CSC position -> CSR slot permutation on the device (values are gathered there and copied out in CSC order)
+  std::vector<int64_t> h_colptr;
+  std::vector<int32_t> h_rowval;
+  gg::DevBuf<int32_t> d_csc_perm;
+  gg::DevBuf<double> d_csc_vals;
 };
 
 struct gg_solver {

@@ -3,7 +3,9 @@
 // Replaces, on the cubed-sphere atlas, the distributed model of the reference
 //   src/Distributed/AtlasDistributedDiscreteModels.jl:20-73   linear cell partition `div((i-1)*P, Nc)+1` (:31), ghost layer
 //                                                             = cells sharing a vertex with an owned cell (:32-49),
-//                                                             local numbering owned + ghost (:51-66)
+//                                                             (the reference numbers a part's cells owned-first, then
+//                                                             ghosts, :51-66; here the local cells are sorted by global
+//                                                             id -- a local permutation only, gids are ABI outputs)
 // and PartitionedArrays' PRange / `consistent!` on the DOF vectors (call sites src/ODEs/StageOperators.jl:109,134,
 // src/ODEs/DAE.jl:291,314).  GridapDistributed's DOF ownership rule is not in the reference tree; here a DOF belongs to
 // the rank that owns the lowest-numbered cell touching it (any consistent rule gives the same numbers; gid parity with
@@ -183,6 +185,7 @@ DistDev dist_dev(gg_space* s) {
   d.rank = c->rank; d.world = c->world;
   d.timing = getenv("GG_COMM_STATS") ? 1 : 0;
   d.win = (WinHeader* const*)c->d_win.p; d.slot = (double* const*)c->d_slot.p;
+  d.slot_stride = std::max<int64_t>(c->slot_doubles, 1);
   d.owned = x.d_owned.p;
   d.send_idx = x.d_send_idx.p; d.send_remote = x.d_send_remote.p; d.send_peer = x.d_send_peer.p;
   d.push_first = x.d_push_first.p;
@@ -196,13 +199,21 @@ __global__ void __launch_bounds__(256) k_consistent(DistDev d, double* vec, int6
   cg::grid_group grid = cg::this_grid();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   unsigned long long epoch = d.win[d.rank]->epoch;
-  dist_push(d, vec, tid, nth, n);
+  dist_push(d, epoch, vec, tid, nth, n);
   grid.sync();
   double dummy[1] = {0.0};
   dist_allreduce<1>(grid, d, epoch, dummy);
-  dist_unpack(d, vec, tid, nth, n);
+  dist_unpack(d, epoch, vec, tid, nth, n);
   grid.sync();
   if (tid == 0) d.win[d.rank]->epoch = epoch;
+}
+
+void comm_check(gg_comm* c) {
+  if (!c || c->world == 1) return;
+  unsigned long long err = 0;
+  GG_CUDA(cudaMemcpy(&err, (char*)c->window + offsetof(WinHeader, error), sizeof(err), cudaMemcpyDeviceToHost));
+  if (err) throw Error(GG_ERR_COMM, "a wait on a peer window timed out in round " + std::to_string(err) +
+                                        " (a rank is lost or out of step); results since then are invalid");
 }
 
 void vec_consistent_async(gg_space* s, double* vec) {
@@ -314,7 +325,7 @@ int gg_comm_create(gg_ctx* ctx, int rank, int world, int64_t slot_doubles, gg_co
   GG_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<gg_comm> c(new gg_comm);
   c->ctx = ctx; c->rank = rank; c->world = world; c->slot_doubles = slot_doubles;
-  c->bytes = sizeof(WinHeader) + (size_t)std::max<int64_t>(slot_doubles, 1) * sizeof(double);
+  c->bytes = sizeof(WinHeader) + 2 * (size_t)std::max<int64_t>(slot_doubles, 1) * sizeof(double);  // two halves (round parity)
   GG_CUDA(cudaMalloc(&c->window, c->bytes));
   GG_CUDA(cudaMemset(c->window, 0, c->bytes));
   c->peer.assign(world, nullptr);
@@ -424,6 +435,7 @@ int gg_vec_consistent(gg_space* s, gg_vec* v) {
   GG_CUDA(cudaSetDevice(s->mesh->ctx->device));
   vec_consistent_async(s, v->d.p);
   GG_CUDA(cudaStreamSynchronize(s->mesh->ctx->stream));
+  comm_check(s->mesh->comm);
   GG_API_END
 }
 

@@ -12,8 +12,10 @@
 //            stores flag[me] = epoch into every peer window.  (A system-scope fence in every writer thread is not needed
 //            and is expensive.)
 //   reader:  one thread spins (volatile loads of its OWN window) until flag[r] >= epoch for all r ; grid barrier ; read data
-// Reduction operands are double-buffered by epoch parity (a rank can be at most one round ahead of a peer, because it
-// needs that peer's flag to finish a round); sums run over ranks in rank order on every rank => bitwise identical totals
+// Reduction operands AND the exchange slot are double-buffered by the parity of the round that completes them (a rank can be
+// at most one round ahead of a peer, because it needs that peer's flag to finish a round: data stored for round e is read
+// after round e and before the reader posts e+1; the next store into the same half belongs to round e+2, whose writer has
+// finished e+1, i.e. has seen the reader's flag e+1).  Sums run over ranks in rank order on every rank => bitwise identical totals
 // everywhere, so all ranks take the same convergence decisions.  A wait that exceeds ~10 s sets an error word and every
 // later wait returns at once: a lost peer becomes an error code, not a hung GPU.
 #pragma once
@@ -38,7 +40,8 @@ struct WinHeader {
 struct DistDev {
   int rank = 0, world = 1, force_multi = 0, timing = 0;
   WinHeader* const* win = nullptr;   // [world] window bases (peers' are IPC mappings)
-  double* const* slot = nullptr;     // [world] exchange slots (doubles) behind the headers
+  double* const* slot = nullptr;     // [world] exchange slots (doubles) behind the headers: two halves of slot_stride doubles
+  int64_t slot_stride = 0;           // half used by an exchange = parity of the round (epoch) that completes it
   const uint8_t* owned = nullptr;    // [n local DOFs] 0 ghost, 1 owned, 2 owned and a ghost of some neighbour
   // DOFs this rank owns and a neighbour holds as ghosts, sorted by local id: local id, the receiver's local id and rank
   const int32_t *send_idx = nullptr, *send_remote = nullptr, *send_peer = nullptr;
@@ -56,21 +59,27 @@ __device__ __forceinline__ unsigned long long dist_now() {
 }
 
 // every thread: store the owned values the neighbours need into THEIR exchange slots, at their local ids
-__device__ __forceinline__ void dist_push(const DistDev& d, const double* __restrict__ vec, int64_t tid, int64_t nth, int64_t limit) {
+// `epoch` is the caller's CURRENT round counter: the exchange is completed by the next round, epoch + 1
+__device__ __forceinline__ void dist_push(const DistDev& d, unsigned long long epoch, const double* __restrict__ vec, int64_t tid,
+                                          int64_t nth, int64_t limit) {
+  const int64_t half = (int64_t)((epoch + 1ull) & 1ull) * d.slot_stride;
   for (int64_t k = tid; k < d.n_send; k += nth) {
     const int32_t i = d.send_idx[k];
-    if (i < limit) d.slot[d.send_peer[k]][d.send_remote[k]] = vec[i];
+    if (i < limit) d.slot[d.send_peer[k]][half + d.send_remote[k]] = vec[i];
   }
 }
 
 // push one freshly computed value of row i (owned[i] == 2) to every rank that holds the row as a ghost
-__device__ __forceinline__ void dist_push_row(const DistDev& d, int64_t i, double v) {
-  for (int64_t k = d.push_first[i]; k < d.n_send && d.send_idx[k] == i; ++k) d.slot[d.send_peer[k]][d.send_remote[k]] = v;
+__device__ __forceinline__ void dist_push_row(const DistDev& d, unsigned long long epoch, int64_t i, double v) {
+  const int64_t half = (int64_t)((epoch + 1ull) & 1ull) * d.slot_stride;
+  for (int64_t k = d.push_first[i]; k < d.n_send && d.send_idx[k] == i; ++k) d.slot[d.send_peer[k]][half + d.send_remote[k]] = v;
 }
 
-// every thread: copy the received ghost values from this rank's slot into vec
-__device__ __forceinline__ void dist_unpack(const DistDev& d, double* __restrict__ vec, int64_t tid, int64_t nth, int64_t limit) {
-  const double* s = d.slot[d.rank];
+// every thread: copy the received ghost values from this rank's slot into vec; `epoch` is the round that completed the exchange
+// (the counter as dist_allreduce left it)
+__device__ __forceinline__ void dist_unpack(const DistDev& d, unsigned long long epoch, double* __restrict__ vec, int64_t tid,
+                                            int64_t nth, int64_t limit) {
+  const double* s = d.slot[d.rank] + (int64_t)(epoch & 1ull) * d.slot_stride;
   for (int64_t k = tid; k < d.n_recv; k += nth) {
     const int32_t i = d.recv_idx[k];
     if (i < limit) vec[i] = __ldcg(s + i);

@@ -21,6 +21,8 @@ struct SpacePlan {
 SpacePlan& plan_space(gg_plan* P, int kind, int order);
 DistDev dist_dev(gg_space* s);
 void vec_consistent_async(gg_space* s, double* vec);
+// throws GG_ERR_COMM if a wait on this communicator's window has timed out (the stream must be idle); no-op for nullptr
+void comm_check(gg_comm* c);
 }  // namespace gg
 
 struct gg_plan {

@@ -591,7 +591,7 @@ k_pcg_ebe(const EbeArgs a) {
     lrr0 = ebe_block_sum(lrr0, sh);
     if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; P2[blockIdx.x] = lrr0; }
     grid.sync();
-    if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
+    if (multi) { dist_push(a.dist, epoch, a.z, tid, nth, n); grid.sync(); }
     rz = ebe_grid_total(P0, nbk, sh);
     bb = ebe_grid_total(P1, nbk, sh);
     rr = ebe_grid_total(P2, nbk, sh);
@@ -599,7 +599,7 @@ k_pcg_ebe(const EbeArgs a) {
       double v[3] = {rz, rr, bb};
       dist_allreduce<3>(grid, a.dist, epoch, v);
       rz = v[0]; rr = v[1]; bb = v[2];
-      dist_unpack(a.dist, a.z, tid, nth, n);
+      dist_unpack(a.dist, epoch, a.z, tid, nth, n);
     }
     tp2 = ebe_now();
   } else {
@@ -699,14 +699,14 @@ k_pcg_ebe(const EbeArgs a) {
     lrr0 = ebe_block_sum(lrr0, sh);
     if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P2[blockIdx.x] = lrr0; }
     grid.sync();
-    if (multi) { dist_push(a.dist, a.z, tid, nth, n); grid.sync(); }
+    if (multi) { dist_push(a.dist, epoch, a.z, tid, nth, n); grid.sync(); }
     rz = ebe_grid_total(P0, nbk, sh);
     rr = ebe_grid_total(P2, nbk, sh);
     if (multi) {
       double v[2] = {rz, rr};
       dist_allreduce<2>(grid, a.dist, epoch, v);
       rz = v[0]; rr = v[1];
-      dist_unpack(a.dist, a.z, tid, nth, n);  // ghost z: from the exchange slot into the vector (the barrier below orders it)
+      dist_unpack(a.dist, epoch, a.z, tid, nth, n);  // ghost z: from the exchange slot into the vector (the barrier below orders it)
     }
   }
   double beta = 0.0;
@@ -809,7 +809,7 @@ k_pcg_ebe(const EbeArgs a) {
             r_new[s0 + j] = rn[j]; a.z[s0 + j] = zj;
             lrz2 = fma(rn[j], zj, lrz2);
             lrr = fma(rn[j], rn[j], lrr);
-            if (ob[j] == 2) dist_push_row(a.dist, s0 + j, zj);
+            if (ob[j] == 2) dist_push_row(a.dist, epoch, s0 + j, zj);
           }
         }
       } else
@@ -864,7 +864,7 @@ k_pcg_ebe(const EbeArgs a) {
         // barrier and the cumulative system-scope fence of the posting thread, gg_dist.cuh)
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
-          if (ob[u] == 2) dist_push_row(a.dist, i0 + u * nth, zi[u]);
+          if (ob[u] == 2) dist_push_row(a.dist, epoch, i0 + u * nth, zi[u]);
       }
       lrz2 = ebe_block_sum(lrz2, sh);
       lrr = ebe_block_sum(lrr, sh);
@@ -881,7 +881,7 @@ k_pcg_ebe(const EbeArgs a) {
         double v[2] = {rz_new, rr};
         dist_allreduce<2>(grid, a.dist, epoch, v);
         rz_new = v[0]; rr = v[1];
-        if (rr > tol2) { dist_unpack(a.dist, a.z, tid, nth, n); grid.sync(); }
+        if (rr > tol2) { dist_unpack(a.dist, epoch, a.z, tid, nth, n); grid.sync(); }
         tR += ebe_now() - t1;
       }
       if (rr <= tol2) break;  // uniform across the grid and across the ranks
@@ -892,11 +892,11 @@ k_pcg_ebe(const EbeArgs a) {
   if (multi) {
     // owner -> ghost update of the solution (the exchange slot is free again: z is dead)
     grid.sync();
-    dist_push(a.dist, a.x, tid, nth, n);
+    dist_push(a.dist, epoch, a.x, tid, nth, n);
     grid.sync();
     double v[1] = {0.0};
     dist_allreduce<1>(grid, a.dist, epoch, v);
-    dist_unpack(a.dist, a.x, tid, nth, n);
+    dist_unpack(a.dist, epoch, a.x, tid, nth, n);
     grid.sync();
     if (tid == 0) a.dist.win[a.dist.rank]->epoch = epoch;
   }

@@ -348,8 +348,8 @@ static void mf_load_tables(gg_ctx* ctx, int kind, int order, int nq) {
   if (cur == key) return;
   auto T = get_tab(ctx, kind, order, nq);
   GG_CUDA(cudaStreamSynchronize(st));
-  if (rt) GG_CUDA(cudaMemcpyToSymbol(c_mf_rt, T->val.p, T->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
-  else GG_CUDA(cudaMemcpyToSymbol(c_mf_sc, T->val.p, T->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+  if (rt) GG_CUDA(cudaMemcpyToSymbolAsync(c_mf_rt, T->val.p, T->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+  else GG_CUDA(cudaMemcpyToSymbolAsync(c_mf_sc, T->val.p, T->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
   cur = key;
 }
 

@@ -359,6 +359,14 @@ void gather_matrix_batch(gg_csr* A, int batch, const double* ebuf, double scale,
 
 using namespace gg;
 
+namespace gg {
+// values in CSC order: out[k] = vals[perm[k]]
+__global__ void k_permute_values(int64_t n, const int32_t* __restrict__ perm, const double* __restrict__ vals, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = vals[perm[k]];
+}
+}  // namespace gg
+
 extern "C" {
 
 int gg_pattern(gg_space* test, gg_space* trial, gg_csr** out) {
@@ -469,6 +477,44 @@ int gg_csr_export(gg_csr* A, int64_t* rowptr, int64_t* colind, double* vals, int
     for (int64_t i = 0; i < A->nnz; ++i) colind[i] = (int64_t)h[i] + index_base;
   }
   if (vals && A->nnz) A->d_vals.download(vals, st);
+  GG_API_END
+}
+
+int gg_csr_export_csc(gg_csr* A, int64_t* colptr, int64_t* rowval, double* nzval, int index_base) {
+  GG_API_BEGIN
+  GG_REQUIRE(A, GG_ERR_INVALID, "null matrix");
+  GG_REQUIRE(index_base == 0 || index_base == 1, GG_ERR_INVALID, "index_base must be 0 or 1");
+  GG_CUDA(cudaSetDevice(A->ctx->device));
+  cudaStream_t st = A->ctx->stream;
+  if (A->h_colptr.empty()) {
+    // one-off: stable counting sort of the CSR slots by column => rows ascending inside every column, as in
+    // SparseMatrixCSC; the permutation stays on the device for the numeric exports
+    std::vector<int32_t> rp(A->n_rows + 1), ci(A->nnz), perm(A->nnz);
+    A->d_rowptr.download(rp.data(), st);
+    if (A->nnz) A->d_colind.download(ci.data(), st);
+    A->h_colptr.assign(A->n_cols + 1, 0);
+    for (int64_t k = 0; k < A->nnz; ++k) A->h_colptr[ci[k] + 1]++;
+    for (int64_t j = 0; j < A->n_cols; ++j) A->h_colptr[j + 1] += A->h_colptr[j];
+    std::vector<int64_t> next(A->h_colptr.begin(), A->h_colptr.end() - 1);
+    A->h_rowval.resize(A->nnz);
+    for (int64_t i = 0; i < A->n_rows; ++i)
+      for (int32_t k = rp[i]; k < rp[i + 1]; ++k) {
+        const int64_t pos = next[ci[k]]++;
+        A->h_rowval[pos] = (int32_t)i;
+        perm[pos] = k;
+      }
+    A->d_csc_perm.upload(perm, st);
+    GG_CUDA(cudaStreamSynchronize(st));
+  }
+  if (colptr) for (int64_t j = 0; j <= A->n_cols; ++j) colptr[j] = A->h_colptr[j] + index_base;
+  if (rowval) for (int64_t k = 0; k < A->nnz; ++k) rowval[k] = (int64_t)A->h_rowval[k] + index_base;
+  if (nzval && A->nnz) {
+    if ((int64_t)A->d_csc_vals.n != A->nnz) A->d_csc_vals.alloc(A->nnz);
+    k_permute_values<<<(unsigned)((A->nnz + 255) / 256), 256, 0, st>>>(A->nnz, A->d_csc_perm.p, A->d_vals.p, A->d_csc_vals.p);
+    A->ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+    A->d_csc_vals.download(nzval, st);
+  }
   GG_API_END
 }
 

@@ -21,6 +21,7 @@
 #include "gg_refel.cuh"
 
 #include "gg_rk.cuh"
+#include "gg_dist_host.cuh"
 
 namespace gg {
 
@@ -115,8 +116,11 @@ __global__ void k_combine(int64_t n, const double* x0, int ns, double c0, const 
   out[i] = v;
 }
 
-__global__ void k_accumulate_stats(const double* __restrict__ solver_stats, double* __restrict__ accum) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { accum[0] += solver_stats[0]; accum[1] += 1.0; }
+__global__ void k_accumulate_stats(const double* __restrict__ solver_stats, double rtol, double* __restrict__ accum) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    accum[0] += solver_stats[0]; accum[1] += 1.0;
+    if (!(solver_stats[1] <= rtol * 1.0000001)) accum[2] += 1.0;   // stopped at max_iter (or NaN): reported by gg_rk_step
+  }
 }
 
 static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
@@ -130,8 +134,8 @@ static void rk_residual_async(gg_rk* rk, const double* x, double* r) {
   GG_CUDA(cudaGetLastError());
 }
 
-void rk_accumulate_stats(gg_rk* rk, const double* solver_stats) {
-  k_accumulate_stats<<<1, 32, 0, rk->ctx->stream>>>(solver_stats, rk->iter_accum.p);
+void rk_accumulate_stats(gg_rk* rk, const double* solver_stats, double rtol) {
+  k_accumulate_stats<<<1, 32, 0, rk->ctx->stream>>>(solver_stats, rtol, rk->iter_accum.p);
   rk->ctx->launches++;
 }
 
@@ -177,7 +181,7 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
       }
     }
     ebe_solve_async(e, b, scale, x, rk->warm_start);
-    rk_accumulate_stats(rk, e->stats.p);
+    rk_accumulate_stats(rk, e->stats.p, e->rtol);
     if (H) {
       // newest slot moves forward; the oldest level is overwritten
       const int R = rk->extrap_order;
@@ -188,7 +192,7 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
   } else {
     gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
     solver_solve_async(s, b, scale, x);
-    rk_accumulate_stats(rk, s->stats.p);
+    rk_accumulate_stats(rk, s->stats.p, s->rtol);
   }
 }
 
@@ -329,8 +333,8 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
     rk->x.alloc(n); rk->xi.alloc(n); rk->r.alloc(n);
     rk->k.resize(s);
     for (int i = 0; i < s; ++i) rk->k[i].alloc(n);
-    rk->iter_accum.alloc(2);
-    GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
+    rk->iter_accum.alloc(3);
+    GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 3 * sizeof(double), ctx->stream));
     if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
     adv_create(rk, a);
     GG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -385,8 +389,8 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
     GG_CUDA(cudaMemsetAsync(rk->xi.p, 0, n * sizeof(double), ctx->stream));
     GG_CUDA(cudaMemsetAsync(rk->r.p, 0, n * sizeof(double), ctx->stream));
   }
-  rk->iter_accum.alloc(2);
-  GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 2 * sizeof(double), ctx->stream));
+  rk->iter_accum.alloc(3);
+  GG_CUDA(cudaMemsetAsync(rk->iter_accum.p, 0, 3 * sizeof(double), ctx->stream));
   if (n) GG_CUDA(cudaMemsetAsync(rk->x.p, 0, n * sizeof(double), ctx->stream));
   if (a->problem == GG_PROBLEM_SHALLOW_WATER || thermal) {
     swe_create(rk, a);
@@ -453,6 +457,17 @@ int gg_rk_step(gg_rk* rk, int32_t n_steps) {
   GG_CUDA(cudaSetDevice(rk->ctx->device));
   for (int32_t i = 0; i < n_steps; ++i) rk_step_async(rk);
   GG_CUDA(cudaStreamSynchronize(rk->ctx->stream));
+  // a march that lost a peer or a mass solve that stopped at max_iter must not return GG_OK with a garbage state
+  comm_check(rk->mesh->comm);
+  if (rk->iter_accum.n >= 3) {
+    double h[3];
+    rk->iter_accum.download(h, rk->ctx->stream);
+    if (h[2] > rk->noconv_seen) {
+      const int64_t fresh = (int64_t)(h[2] - rk->noconv_seen);
+      rk->noconv_seen = h[2];
+      throw Error(GG_ERR_NOCONV, std::to_string(fresh) + " mass / diagnostic solve(s) of this march stopped at max_iter without reaching rtol");
+    }
+  }
   GG_API_END
 }
 
@@ -545,7 +560,7 @@ int gg_rk_stats(gg_rk* rk, int64_t* pcg_iters_total, int64_t* solves_total) {
   GG_API_BEGIN
   GG_REQUIRE(rk, GG_ERR_INVALID, "null stepper");
   GG_CUDA(cudaSetDevice(rk->ctx->device));
-  double h[2];
+  double h[3] = {0, 0, 0};
   rk->iter_accum.download(h, rk->ctx->stream);
   if (pcg_iters_total) *pcg_iters_total = (int64_t)h[0];
   if (solves_total) *solves_total = (int64_t)h[1];

@@ -31,7 +31,8 @@ struct gg_rk {
   int diag_slot = -1;                   // history slot of the diagnostic solves in flight (-1: none)
   gg::DevBuf<double> x, xi, r, MpInv, Bhat;
   std::vector<gg::DevBuf<double>> k;
-  gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves
+  gg::DevBuf<double> iter_accum;  // [0] total PCG iterations, [1] number of solves, [2] solves that stopped at max_iter
+  double noconv_seen = 0.0;       // [2] as last reported by gg_rk_step
   // ---- shallow water (DAE) only -------------------------------------------------------------------
   gg_space* R = nullptr;          // CG_{k+1} (potential vorticity)
   gg_csr* Mq = nullptr;           // int q p w sqrtg, re-assembled for every diagnostic solve
@@ -70,7 +71,7 @@ void tswe_residual_async(gg_rk* rk, const double* x, const double* y, double* rB
 std::vector<double> build_bhat(int order, int degree);
 // inverses of the DG mass blocks int psi_i psi_j sqrtg, entry-major [(i*mq+j)][cell] -> rk->MpInv
 void build_dg_mass_inverse(gg_rk* rk);
-void rk_accumulate_stats(gg_rk* rk, const double* solver_stats);
+void rk_accumulate_stats(gg_rk* rk, const double* solver_stats, double rtol);
 // k = A^-1 (scale b) with the RT mass (which = 0) or the potential-vorticity mass (which = 1), whichever solver is active
 // slot >= 0 names the solve across steps (stage / unknown) for the extrapolated initial guess
 void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot = -1);

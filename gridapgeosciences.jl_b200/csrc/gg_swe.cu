@@ -343,11 +343,11 @@ static SweTabs swe_tabs(gg_rk* rk, bool* use_const) {
   const int64_t key = ((int64_t)rk->order << 8) | rk->nq1;
   if (*use_const && ctx->swe_key != key) {
     GG_CUDA(cudaStreamSynchronize(ctx->stream));  // earlier launches may still read the old tables
-    GG_CUDA(cudaMemcpyToSymbol(c_swe_w, tdg->w.p, tdg->w.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
-    GG_CUDA(cudaMemcpyToSymbol(c_swe_rt, trt->val.p, trt->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
-    GG_CUDA(cudaMemcpyToSymbol(c_swe_dg, tdg->val.p, tdg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
-    GG_CUDA(cudaMemcpyToSymbol(c_swe_cg, tcg->val.p, tcg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
-    GG_CUDA(cudaMemcpyToSymbol(c_swe_cgd, tcg->der.p, tcg->der.n * sizeof(double), 0, cudaMemcpyDeviceToDevice));
+    GG_CUDA(cudaMemcpyToSymbolAsync(c_swe_w, tdg->w.p, tdg->w.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    GG_CUDA(cudaMemcpyToSymbolAsync(c_swe_rt, trt->val.p, trt->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    GG_CUDA(cudaMemcpyToSymbolAsync(c_swe_dg, tdg->val.p, tdg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    GG_CUDA(cudaMemcpyToSymbolAsync(c_swe_cg, tcg->val.p, tcg->val.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
+    GG_CUDA(cudaMemcpyToSymbolAsync(c_swe_cgd, tcg->der.p, tcg->der.n * sizeof(double), 0, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->swe_key = key;
   }
   return T;

@@ -18,8 +18,9 @@
  *   - ids crossing the ABI are 1-based Int32 (Gridap `Table{Int32}`), Dirichlet DOFs are negative;
  *     CSR export is Int64 (SparseMatrixCSC{Float64,Int}), 0- or 1-based on request.
  *   - all floating point data is FP64.
- *   - one gg_ctx per process = one GPU (one process per GPU; multi-GPU runs exchange halos with NCCL
- *     on the device pointers exposed by gg_vec_device_ptr()).  Calls on one context are serialised by
+ *   - one gg_ctx per process = one GPU (one process per GPU; a second gg_init on the same device fails until the first
+ *     context is finalised).  Multi-GPU runs exchange halos and dot-product operands through CUDA-IPC peer windows
+ *     (gg_comm_*), stored by the solver kernels themselves; no NCCL call in the data path.  Calls on one context are serialised by
  *     the caller; work is enqueued on the context's stream and the call returns after the stream
  *     has been synchronised unless stated otherwise.
  *   - there is NO CPU fallback: if no CUDA device is usable gg_init fails with GG_ERR_CUDA.
@@ -39,6 +40,7 @@ extern "C" {
 #define GG_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels implement (never a silent fallback) */
 #define GG_ERR_NOMEM (-4)
 #define GG_ERR_NOCONV (-5)      /* iterative solver did not reach the requested tolerance */
+#define GG_ERR_COMM (-6)        /* a wait on a peer window timed out (lost rank): results of the call are invalid */
 
 typedef struct gg_ctx gg_ctx;
 typedef struct gg_mesh gg_mesh;
@@ -146,7 +148,8 @@ void gg_comm_destroy(gg_comm* c);
  * (sum the results over the ranks).  The plan (and comm) must outlive the mesh. */
 int gg_mesh_partitioned(gg_ctx* ctx, gg_plan* p, gg_comm* comm, gg_mesh** out);
 int gg_space_global_dofs(gg_space* s, int64_t* l2g /* 1-based global DOF ids */, int32_t* owner);
-/* consistent!(v): owner -> ghost update through the peer windows (collective: every rank must call it) */
+/* consistent!(v): owner -> ghost update through the peer windows (collective: every rank must call it); GG_ERR_COMM after a
+ * peer-window timeout */
 int gg_vec_consistent(gg_space* s, gg_vec* v);
 
 /* ---- FE spaces -------------------------------------------------------------------------------
@@ -200,6 +203,12 @@ int gg_assemble_advection(gg_space* dg_space, int32_t degree, const double* velo
 int gg_csr_info(gg_csr* A, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
 /* index_base 0 or 1.  Any of rowptr/colind/vals may be NULL to skip it. */
 int gg_csr_export(gg_csr* A, int64_t* rowptr, int64_t* colind, double* vals, int index_base);
+/* The same matrix as SparseMatrixCSC{Float64,Int}(m, n, colptr, rowval, nzval) -- what allocate_matrix / assemble_matrix!
+ * hand back in the reference (src/ODEs/ODEOpsFromTFEOps.jl:154-160,385-408) -- for ANY test x trial pair (rectangular and
+ * non-symmetric blocks such as GG_FORM_DIV, GG_FORM_VECTOR_DIV or the advection operator included): colptr [n_cols+1],
+ * rowval [nnz] with rows ascending inside each column, nzval [nnz].  The structure is built at the first call; later calls
+ * with colptr = rowval = NULL only permute the current values on the device and copy them out. */
+int gg_csr_export_csc(gg_csr* A, int64_t* colptr, int64_t* rowval, double* nzval, int index_base);
 double* gg_csr_device_values(gg_csr* A);
 /* y = alpha * A x + beta * y on the device */
 int gg_csr_spmv(gg_csr* A, double alpha, gg_vec* x, double beta, gg_vec* y);
@@ -373,6 +382,7 @@ int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p);
 int gg_rk_set_state(gg_rk* rk, const double* x /* [n_u + n_p] host */);
 int gg_rk_get_state(gg_rk* rk, double* x);
 double* gg_rk_state_device_ptr(gg_rk* rk);
+/* returns GG_ERR_NOCONV if a mass / diagnostic solve of the march stopped at max_iter, GG_ERR_COMM after a peer-window timeout */
 int gg_rk_step(gg_rk* rk, int32_t n_steps);
 /* matrix-free stage residual r = res(x) (parity hook), host in/out.  Shallow water: the diagnostics are solved
  * at x first and q0 aliases q. */

@@ -141,9 +141,15 @@ void oracle_lb_element_vectors(int64_t nc, const double* chart_coords, double ra
 }
 
 /* COO -> CSR numeric phase: vals[slot(i,j)] += Ke[c][i][j] for all cells, rows/cols < 0 dropped.
- * The pattern (rowptr, colind sorted in each row) is given.  Serial in cell order = sparse(I,J,V). */
+ * The pattern (rowptr, colind sorted in each row) is given.  nthreads == 1: serial in cell order = sparse(I,J,V);
+ * otherwise the cells are shared out over the threads and the adds are atomic (the summation order of a slot then
+ * depends on the schedule: results agree to round-off, not bit for bit, with the serial order). */
 void oracle_scatter_csr(int64_t nc, int m, const int64_t* cell_dofs, const double* Ke, const int64_t* rowptr,
-                        const int64_t* colind, double* vals) {
+                        const int64_t* colind, double* vals, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) if (nthreads != 1)
   for (int64_t c = 0; c < nc; ++c)
     for (int i = 0; i < m; ++i) {
       int64_t r = cell_dofs[c * m + i];
@@ -156,15 +162,25 @@ void oracle_scatter_csr(int64_t nc, int m, const int64_t* cell_dofs, const doubl
           int64_t mid = (lo + hi) >> 1;
           if (colind[mid] < col) lo = mid + 1; else hi = mid;
         }
-        vals[lo] += Ke[((size_t)c * m + i) * m + j];
+        const double v = Ke[((size_t)c * m + i) * m + j];
+#pragma omp atomic
+        vals[lo] += v;
       }
     }
 }
 
-void oracle_scatter_vector(int64_t nc, int m, const int64_t* cell_dofs, const double* fe, double* out) {
+void oracle_scatter_vector(int64_t nc, int m, const int64_t* cell_dofs, const double* fe, double* out, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) if (nthreads != 1)
   for (int64_t c = 0; c < nc; ++c)
     for (int i = 0; i < m; ++i) {
       int64_t r = cell_dofs[c * m + i];
-      if (r >= 0) out[r] += fe[c * m + i];
+      if (r >= 0) {
+        const double v = fe[c * m + i];
+#pragma omp atomic
+        out[r] += v;
+      }
     }
 }

@@ -59,20 +59,20 @@ def lb_element_vectors(chart_coords, radius, p, degree, ue, nthreads=0):
     return fe
 
 
-def scatter_csr(cell_dofs, Ke, rowptr, colind):
+def scatter_csr(cell_dofs, Ke, rowptr, colind, nthreads=1):
     ids = np.ascontiguousarray(cell_dofs, dtype=np.int64)
     rp = np.ascontiguousarray(rowptr, dtype=np.int64)
     ci = np.ascontiguousarray(colind, dtype=np.int64)
     vals = np.zeros(len(ci))
     Ke = np.ascontiguousarray(Ke)
     lib().oracle_scatter_csr(C.c_int64(ids.shape[0]), C.c_int(ids.shape[1]), _p(ids, C.c_int64), _p(Ke), _p(rp, C.c_int64),
-                             _p(ci, C.c_int64), _p(vals))
+                             _p(ci, C.c_int64), _p(vals), C.c_int(nthreads))
     return vals
 
 
-def scatter_vector(cell_dofs, fe, n):
+def scatter_vector(cell_dofs, fe, n, nthreads=1):
     ids = np.ascontiguousarray(cell_dofs, dtype=np.int64)
     out = np.zeros(n)
     fe = np.ascontiguousarray(fe)
-    lib().oracle_scatter_vector(C.c_int64(ids.shape[0]), C.c_int(ids.shape[1]), _p(ids, C.c_int64), _p(fe), _p(out))
+    lib().oracle_scatter_vector(C.c_int64(ids.shape[0]), C.c_int(ids.shape[1]), _p(ids, C.c_int64), _p(fe), _p(out), C.c_int(nthreads))
     return out

@@ -34,13 +34,12 @@ def rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    gg = load_package()
-    ctx = gg.get_context(local)
-    n, p = int(sys.argv[1]) if len(sys.argv) > 1 else 6, int(sys.argv[2]) if len(sys.argv) > 2 else 1
+def run_checks(gg, ctx, rank, world, n, p):
+    """Partitioned (one rank per GPU, or per process on a shared GPU) against single-GPU runs of the same problems; asserts the
+    tolerances and returns the measured differences.  Collective: every rank calls it.  Also embedded in `bench.py --gpus N`
+    (`dist_parity`), so that the multi-GPU parity is on the driver's record of the scaling run."""
+    cpu = dist.get_backend() != "nccl"
+    dev = torch.device("cpu") if cpu else torch.device("cuda", ctx.device)
     mesh = gg.CubedSphereMesh(1.0)
     plan = gg.PartitionPlan(n, world, rank)
     comm = gg.PeerWindow(ctx, rank, world, gg.window_doubles(plan, p))
@@ -71,7 +70,7 @@ def main():
     u0, h0 = gg.interpolate(velocity, V).get(), gg.interpolate(depth, Q).get()
     u0f, h0f = gg.interpolate(velocity, Vf).get(), gg.interpolate(depth, Qf).get()
     assert rel(u0, u0f[lv]) < 1e-13 and rel(h0, h0f[lq]) < 1e-13
-    nsq = torch.tensor([gg.norm(u0, V, 8) ** 2, gg.norm(h0, Q, 8) ** 2], device="cuda", dtype=torch.float64)
+    nsq = torch.tensor([gg.norm(u0, V, 8) ** 2, gg.norm(h0, Q, 8) ** 2], device=dev, dtype=torch.float64)
     dist.all_reduce(nsq)
     assert abs(nsq[0].item() - gg.norm(u0f, Vf, 8) ** 2) < 1e-12 * nsq[0].item()
     assert abs(nsq[1].item() - gg.norm(h0f, Qf, 8) ** 2) < 1e-12 * nsq[1].item()
@@ -151,11 +150,42 @@ def main():
     e_a = rel(sa.get_state(), saf.get_state()[lq])
     assert e_a < 1e-12, f"advection: partitioned and single-GPU states differ by {e_a}"
     assert comm.error_epoch() == 0
-    dist.barrier()
-    if rank == 0:
-        print(f"DIST_OK world={world} n={n} p={p} wave_err={e_w:.2e} swe_err={e_s:.2e} pv_err={e_q:.2e} adv_err={e_a:.2e} "
-              f"pcg_iters={its} (single GPU {itf}) solves={sol}")
     del sa, saf
+    # back-to-back exchanges with one rank delayed: the exchange slot is double-buffered by round parity, so a fast rank
+    # cannot overwrite values a slow peer has not unpacked yet
+    g = np.cos(0.3 * np.arange(lv.max() + 1)) + 3.0
+    for rep_ in range(6):
+        v = gg.DeviceVector.from_numpy(ctx, np.where(ov == rank, (rep_ + 1) * g[lv], -1.0))
+        if rank == rep_ % world:
+            import time
+            time.sleep(0.02)
+        gg.consistent(v, V)
+        assert (v.get() == (rep_ + 1) * g[lv]).all(), "consistent! under skew returned stale ghost values"
+    assert comm.error_epoch() == 0
+    dist.barrier()
+    return {"world": world, "n": n, "p": p, "wave": e_w, "swe": e_s, "pv": e_q, "advection": e_a,
+            "thermal_swe": e_t if p >= 1 else None, "pcg_iters": int(its), "pcg_iters_single_gpu": int(itf),
+            "pcg_iters_equal": bool(its == itf), "solves": int(sol), "consistent_exact": True}
+
+
+def main():
+    """torchrun worker.  GG_DIST_BACKEND=gloo + GG_DIST_SHARE_GPU=1: all ranks on GPU 0 (time-sliced processes; CUDA IPC works
+    between processes on one device), for boxes with a single GPU."""
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    share = os.environ.get("GG_DIST_SHARE_GPU") == "1"
+    local = 0 if share else local
+    torch.cuda.set_device(local)
+    if os.environ.get("GG_DIST_BACKEND", "nccl") == "gloo":
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gg = load_package()
+    ctx = gg.get_context(local)
+    n, p = int(sys.argv[1]) if len(sys.argv) > 1 else 6, int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    r = run_checks(gg, ctx, rank, world, n, p)
+    if rank == 0:
+        print(f"DIST_OK world={world} n={n} p={p} wave_err={r['wave']:.2e} swe_err={r['swe']:.2e} pv_err={r['pv']:.2e} "
+              f"adv_err={r['advection']:.2e} pcg_iters={r['pcg_iters']} (single GPU {r['pcg_iters_single_gpu']}) solves={r['solves']}")
     dist.destroy_process_group()
 
 
