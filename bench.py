@@ -471,17 +471,21 @@ EXECUTED_FLOPS_PER_CELL = 2 * 5100 + 2 * 81 + 12 * 100 + 20 * 60
 
 
 def assembly_roofline(prof, ncell_local, nnz, ms_per_step, fp64_peak, hbm_peak, have_peaks):
-    """Roofline block of the headline step from the per-kernel CUDA-event times of THIS run.  The FP64 element kernel is
-    reported against the DFMA probe run in this process, the CSR fill against the measured copy bandwidth."""
-    k_ms = prof["k_lb_fast"][1] / max(prof["k_lb_fast"][0], 1)
-    g_ms = prof["k_gather_chunks"][1] / max(prof["k_gather_chunks"][0], 1)
-    d_ms = prof["k_gather_dofs"][1] / max(prof["k_gather_dofs"][0], 1)
+    """Roofline block of the headline step from the per-kernel CUDA-event times of THIS run (taken in a separate profiled
+    pass over the same steps).  The fused tile kernel does the FP64 element arithmetic AND writes the CSR values, so it is
+    reported against both bounds: the DFMA probe run in this process and the measured copy bandwidth."""
+    ms = {k: (v[1] / v[0] if v[0] else 0.0) for k, v in prof.items()}
+    fused = ms.get("k_lb_tile", 0.0) > 0.0
+    k_name = "k_lb_tile" if fused else "k_lb_fast"
+    k_ms = ms[k_name]
     executed = EXECUTED_FLOPS_PER_CELL * ncell_local / (k_ms * 1e-3) / 1e12 if k_ms else None
     naive = (FLOPS_JAC + FLOPS_RES) * ncell_local / (k_ms * 1e-3) / 1e12 if k_ms else None
-    # bytes the CSR fill must move at least: packed element entries in + values out (maps are extra traffic)
-    gather_bytes = 8.0 * (45 * ncell_local + nnz)
-    return {
-        "kernel": "k_lb_fast<3,10> (fused Q2 element matrix + residual, one thread per cell)",
+    work_ms = EXECUTED_FLOPS_PER_CELL * ncell_local / (fp64_peak * 1e12) * 1e3 if fp64_peak else None
+    # algorithmic HBM bytes of the step: every CSR value and residual entry written once, DOF ids and state read once
+    alg_bytes = 8.0 * nnz + (36 + 72 + 32) * ncell_local
+    out = {
+        "kernel": ("k_lb_tile<3,10> (fused: Q2 element matrices in registers / shared memory -> CSR values and residual, one CTA per "
+                   "16x8-cell tile)" if fused else "k_lb_fast<3,10> (fused Q2 element matrix + residual, one thread per cell)"),
         "bound": "fp64", "unit": "TFLOP/s",
         "achieved": executed, "peak": fp64_peak, "frac": executed / fp64_peak if (executed and fp64_peak) else None,
         "achieved_is": "FP64 operations the kernel executes (sum-factorised: ~13 kFLOP per cell, EXECUTED_FLOPS_PER_CELL in bench.py) "
@@ -492,19 +496,29 @@ def assembly_roofline(prof, ncell_local, nnz, ms_per_step, fp64_peak, hbm_peak, 
                         "note": "SURVEY.md §8(d)'s per-cell count of the reference algorithm (45 600 + 14 000 FLOP) / the same kernel "
                                 "time: exceeds 1 because the kernel does not execute that many operations"},
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
-        "step_level": {"fp64_work_ms_at_probe_peak": EXECUTED_FLOPS_PER_CELL * ncell_local / (fp64_peak * 1e12) * 1e3 if fp64_peak else None,
-                       "frac_of_step": (EXECUTED_FLOPS_PER_CELL * ncell_local / (fp64_peak * 1e12) * 1e3) / ms_per_step if fp64_peak else None,
-                       "kernels_ms": {"k_lb_fast": k_ms, "k_gather_chunks": g_ms, "k_gather_dofs": d_ms}},
+        "step_level": {"fp64_work_ms_at_probe_peak": work_ms, "frac_of_step": work_ms / ms_per_step if (work_ms and ms_per_step) else None,
+                       "kernels_ms": ms},
+        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None,
+                "peak_gbs": hbm_peak, "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak if k_ms else None,
+                "algorithmic_bytes": "8 B x nnz (every CSR value written once) + 140 B per cell (DOF ids, state gather, residual)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s"},
         "traffic": None,
-        "from_profile": {"file": "profiles/ncu_lb_assembly_r01_final.txt", "workload": "N=1, 393 216 cells",
-                         "k_lb_fast": {"dram_bytes_per_cell": 378.4, "fp64_pipe_active_pct": 81.3},
-                         "k_gather_chunks": {"dram_bytes_per_cell": 1462.8, "note": "575 MB per launch, of which 190 MB gather lists"}},
-        "csr_fill": {"kernel": "k_gather_chunks", "bound": "hbm", "unit": "GB/s", "kernel_ms": g_ms,
-                     "achieved": gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None, "peak": hbm_peak,
-                     "frac": gather_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
-                     "algorithmic_bytes": "8 B x (45 packed element entries per cell read + every CSR value written once)",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s"},
+        "from_profile": PROFILE_FIGURES,
     }
+    if not fused:
+        g_ms = ms.get("k_gather_chunks", 0.0)
+        gather_bytes = 8.0 * (45 * ncell_local + nnz)
+        out["csr_fill"] = {"kernel": "k_gather_chunks", "bound": "hbm", "unit": "GB/s", "kernel_ms": g_ms,
+                           "achieved": gather_bytes / (g_ms * 1e-3) / 1e9 if g_ms else None, "peak": hbm_peak,
+                           "frac": gather_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
+                           "algorithmic_bytes": "8 B x (45 packed element entries per cell read + every CSR value written once)"}
+    return out
+
+
+# figures that only a profiler gives (ncu capture of this command, committed under profiles/); NOT measured by bench.py itself
+PROFILE_FIGURES = {"file": "profiles/ncu_lb_assembly_r01_final.txt", "workload": "N=1, 393 216 cells, two-kernel path of round 1",
+                   "k_lb_fast": {"dram_bytes_per_cell": 378.4, "fp64_pipe_active_pct": 81.3},
+                   "k_gather_chunks": {"dram_bytes_per_cell": 1462.8, "note": "575 MB per launch, of which 190 MB gather lists"}}
 
 
 def assembly_limiter(leg, roofline, world):
@@ -514,7 +528,7 @@ def assembly_limiter(leg, roofline, world):
     ghost = leg["cells_local_incl_ghosts"] / max(leg["owned"], 1) - 1.0
     gap = leg["ms_per_step"] - ksum
     if gap > 0.25 * leg["ms_per_step"]:
-        what = f"launch / tail latency: the 3 kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step"
+        what = f"launch / tail latency: the kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step"
     elif ghost > 0.1:
         what = f"redundant ghost-layer cells: {100 * ghost:.1f} % more cells than owned"
     else:
@@ -522,7 +536,7 @@ def assembly_limiter(leg, roofline, world):
     return {"what": what, "kernel_ms_sum": ksum, "ghost_cell_overhead": ghost, "cells_per_sm": leg["cells_local_incl_ghosts"] / 148.0}
 
 
-ASSEMBLY_KERNELS = ("k_lb_fast", "k_gather_chunks", "k_gather_dofs")
+ASSEMBLY_KERNELS = ("k_lb_tile", "k_lb_fast", "k_gather_chunks", "k_gather_dofs")
 
 
 def main():
@@ -621,7 +635,7 @@ def main():
             for _ in range(K):
                 gg.assemble_matrix_and_vector(form, assem_c, b_c)
             ctx.synchronize()
-            pc = {name: ctx.profile_query(name) for name in ("k_lb_fast", "k_lb_residual_classes", "k_gather_chunks", "k_gather_dofs")}
+            pc = {name: ctx.profile_query(name) for name in ("k_lb_tile", "k_lb_fast", "k_lb_residual_classes", "k_gather_chunks", "k_gather_dofs")}
             ctx.profile(False)
             same = bool((assem_c.matrix.values() == A.values()).all())
             line["geometry_classes"] = {

@@ -90,7 +90,7 @@ struct DevBuf {
 }  // namespace gg
 
 // ---- handle types (opaque at the ABI) ---------------------------------------------------------------
-namespace gg { struct FormTab; }
+namespace gg { struct FormTab; struct TilePlan; }
 struct gg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -282,6 +282,9 @@ struct gg_csr {
   std::vector<int32_t> h_rowval;
   gg::DevBuf<int32_t> d_csc_perm;
   gg::DevBuf<double> d_csc_vals;
+  // fused tile assembly (gg_tile.cuh): plans per mode (0 per cell, 1 geometry classes), built at first use
+  std::shared_ptr<gg::TilePlan> tiles[2];
+  bool tiles_tried[2] = {false, false};
 };
 
 struct gg_solver {

@@ -16,6 +16,7 @@
 #include "gg_refel.cuh"
 #include "gg_geom.cuh"
 #include "gg_lb_fast.cuh"
+#include "gg_lb_tile.cuh"
 #include "gg_hex.cuh"
 
 namespace gg {
@@ -413,6 +414,8 @@ struct FillPipe {
   gg_csr* A;
   double scale;
   int add;
+  double* vec_out = nullptr;   // fused residual goes straight into this DOF vector (tile path); set by gg_assemble_matrix_and_vector
+  bool vec_done = false;       // out: the residual has been written (no element-vector gather needed)
 };
 
 // fast-path availability: scalar Q1/Q2, test == trial numbering family, the quadrature sizes the reference uses
@@ -433,6 +436,50 @@ static void run_lb_fast_range(gg_mesh* m, int order, int nq, bool extrinsic, int
   GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
 #undef GG_CASE
   throw Error(GG_ERR_UNSUPPORTED, "no fast Laplace-Beltrami kernel for this (order, degree)");
+}
+
+// fused tile path (gg_tile.cuh, gg_lb_tile.cuh): one kernel computes the element matrices and writes the CSR values (and the
+// residual); on by default, GG_LB_TILES=0 selects the two-kernel path (element buffer + k_gather_chunks)
+template <int NB, int NQ>
+static void launch_lb_tile(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, const TileArgs& a, const CellGeo& g, bool extrinsic) {
+  constexpr int M = NB * NB, NP = M * (M + 1) / 2;
+  const size_t smem = (size_t)(NP + M) * TILE_CELLS * sizeof(double) + TILE_ROWCAP * sizeof(int32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GG_CUDA(cudaFuncSetAttribute(k_lb_tile<NB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_CUDA(cudaFuncSetAttribute(k_lb_tile<NB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  ProfScope ps(ctx, "k_lb_tile");
+  if (extrinsic) k_lb_tile<NB, NQ, true><<<(unsigned)plan.n_super, TILE_CELLS, smem, ctx->stream>>>(T, a, g);
+  else k_lb_tile<NB, NQ, false><<<(unsigned)plan.n_super, TILE_CELLS, smem, ctx->stream>>>(T, a, g);
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+static bool run_lb_tile(gg_mesh* m, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u, double dir,
+                        FillPipe* pipe) {
+  static const bool enabled = !(getenv("GG_LB_TILES") && getenv("GG_LB_TILES")[0] == '0');
+  gg_ctx* ctx = m->ctx;
+  gg_csr* A = pipe->A;
+  if (!enabled || A->test != A->trial) return false;
+  const int mode = (ctx->geometry_classes && !extrinsic) ? 1 : 0;
+  if (!A->tiles_tried[mode]) {
+    A->tiles_tried[mode] = true;
+    A->tiles[mode] = build_tile_plan(A, mode == 1);
+  }
+  if (!A->tiles[mode]) return false;
+  const TilePlan& plan = *A->tiles[mode];
+  load_const_tables(ctx, order, nq);
+  CellGeo g = cell_geo(m, nq);
+  TileDev T = plan.dev();
+  TileArgs a{dofs, pipe->vec_out ? u : nullptr, dir, pipe->scale, pipe->add, A->d_vals.p, pipe->vec_out};
+#define GG_CASE(NB_, NQ_) \
+  if (order + 1 == NB_ && nq == NQ_) { launch_lb_tile<NB_, NQ_>(ctx, plan, T, a, g, extrinsic); pipe->vec_done = pipe->vec_out != nullptr; return true; }
+  GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)
+  GG_CASE(3, 3) GG_CASE(3, 4) GG_CASE(3, 5) GG_CASE(3, 7) GG_CASE(3, 10)
+#undef GG_CASE
+  return false;
 }
 
 static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u,
@@ -757,7 +804,7 @@ static void run_hex_lb(gg_mesh* m, int order, int nq, const int32_t* dofs, const
 
 // element matrices into ctx->ebuf; returns the buffer layout (0 full entry-major, 1 symmetric packed entry-major)
 static int compute_element_matrices(gg_form form, const gg_form_args* a, const Plan& P, bool want_fused_vector, double** vbuf_out,
-                                    const FillPipe* pipe = nullptr) {
+                                    FillPipe* pipe = nullptr) {
   gg_ctx* ctx = P.ctx;
   Geo g = geo_of(P.mesh);
   cudaStream_t st = ctx->stream;
@@ -795,12 +842,17 @@ static int compute_element_matrices(gg_form form, const gg_form_args* a, const P
     double cM, cK; bool ext;
     form_coefficients(form, &cM, &cK, &ext);
     if (stiffness && !a->qdata && P.test->order == P.trial->order && fast_lb_available(P.test->order, P.nq)) {
+      if (want_fused_vector) {
+        GG_REQUIRE(a->u, GG_ERR_INVALID, "fused residual needs args->u");
+        GG_REQUIRE(gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u has the wrong length");
+      }
+      if (pipe && (!want_fused_vector || pipe->vec_out) &&
+          run_lb_tile(P.mesh, P.test->order, P.nq, ext, P.trial->d_cell_dofs.p, a->u ? a->u->d.p : nullptr, a->dirichlet, pipe))
+        return -1;  // CSR values (and the residual, pipe->vec_done) written by the fused tile kernel
       size_t np = (size_t)P.mt * (P.mt + 1) / 2;
       double* eb = scratch(ctx->ebuf, np * nc);
       double* vb = nullptr;
       if (want_fused_vector) {
-        GG_REQUIRE(a->u, GG_ERR_INVALID, "fused residual needs args->u");
-        GG_REQUIRE(gg_vec_size(a->u) == P.trial->n_free, GG_ERR_INVALID, "args->u has the wrong length");
         vb = scratch(ctx->vbuf, (size_t)P.mt * nc);
         *vbuf_out = vb;
       }
@@ -991,10 +1043,10 @@ int gg_assemble_matrix_and_vector(gg_form form, const gg_form_args* args, gg_csr
   GG_REQUIRE(A->test == P.test && A->trial == P.trial, GG_ERR_INVALID, "matrix pattern was built for different spaces");
   GG_REQUIRE(gg_vec_size(b) == P.test->n_free, GG_ERR_INVALID, "output vector has the wrong length");
   double* vb = nullptr;
-  FillPipe pipe{A, P.scale, 0};
+  FillPipe pipe{A, P.scale, 0, b->d.p};
   int layout = compute_element_matrices(form, args, P, true, &vb, &pipe);
   if (layout >= 0) gather_matrix(A, layout, P.ctx->ebuf.p, P.scale, 0);
-  gather_vector(P.test, vb, b->d.p, P.scale, 0);
+  if (!pipe.vec_done) gather_vector(P.test, vb, b->d.p, P.scale, 0);
   finish_call(P.ctx);
   GG_API_END
 }

@@ -169,10 +169,11 @@ def run_checks(gg, ctx, rank, world, n, p):
 
 
 def main():
-    """torchrun worker.  GG_DIST_BACKEND=gloo + GG_DIST_SHARE_GPU=1: all ranks on GPU 0 (time-sliced processes; CUDA IPC works
-    between processes on one device), for boxes with a single GPU."""
+    """torchrun worker.  GG_DIST_BACKEND=gloo + GG_DIST_SHARE_GPU=1 are for the world-of-one run of the partitioned code path
+    (GG_FORCE_MULTI=1); several ranks must never share a GPU (their kernels wait on one another)."""
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     share = os.environ.get("GG_DIST_SHARE_GPU") == "1"
+    assert not share or world == 1, "ranks whose kernels wait on one another must not share a GPU"
     local = 0 if share else local
     torch.cuda.set_device(local)
     if os.environ.get("GG_DIST_BACKEND", "nccl") == "gloo":
