@@ -536,7 +536,7 @@ def assembly_limiter(leg, roofline, world):
     return {"what": what, "kernel_ms_sum": ksum, "ghost_cell_overhead": ghost, "cells_per_sm": leg["cells_local_incl_ghosts"] / 148.0}
 
 
-ASSEMBLY_KERNELS = ("k_lb_tile", "k_lb_fast", "k_gather_chunks", "k_gather_dofs")
+ASSEMBLY_KERNELS = ("k_lb_tile", "k_lb_tile_groups", "k_lb_fast", "k_gather_chunks", "k_gather_dofs")
 
 
 def main():
@@ -635,7 +635,7 @@ def main():
             for _ in range(K):
                 gg.assemble_matrix_and_vector(form, assem_c, b_c)
             ctx.synchronize()
-            pc = {name: ctx.profile_query(name) for name in ("k_lb_tile", "k_lb_fast", "k_lb_residual_classes", "k_gather_chunks", "k_gather_dofs")}
+            pc = {name: ctx.profile_query(name) for name in ("k_lb_tile", "k_lb_tile_groups", "k_lb_fast", "k_lb_residual_classes", "k_gather_chunks", "k_gather_dofs")}
             ctx.profile(False)
             same = bool((assem_c.matrix.values() == A.values()).all())
             line["geometry_classes"] = {

@@ -440,20 +440,31 @@ static void run_lb_fast_range(gg_mesh* m, int order, int nq, bool extrinsic, int
 
 // fused tile path (gg_tile.cuh, gg_lb_tile.cuh): one kernel computes the element matrices and writes the CSR values (and the
 // residual); on by default, GG_LB_TILES=0 selects the two-kernel path (element buffer + k_gather_chunks)
-template <int NB, int NQ>
-static void launch_lb_tile(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, const TileArgs& a, const CellGeo& g, bool extrinsic) {
-  constexpr int M = NB * NB, NP = M * (M + 1) / 2;
-  const size_t smem = (size_t)(NP + M) * TILE_CELLS * sizeof(double) + TILE_ROWCAP * sizeof(int32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GG_CUDA(cudaFuncSetAttribute(k_lb_tile<NB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GG_CUDA(cudaFuncSetAttribute(k_lb_tile<NB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+template <int NB, int NQ, bool EXT, bool MULTI>
+static void launch_lb_tile_k(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, const TileArgs& a, const CellGeo& g) {
+  constexpr int M = NB * NB;
+  const size_t smem = tile_smem_bytes(M, a.n_acc, a.n_vacc, a.n_rows);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    GG_CUDA(cudaFuncSetAttribute(k_lb_tile<NB, NQ, EXT, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
   }
   ProfScope ps(ctx, "k_lb_tile");
-  if (extrinsic) k_lb_tile<NB, NQ, true><<<(unsigned)plan.n_super, TILE_CELLS, smem, ctx->stream>>>(T, a, g);
-  else k_lb_tile<NB, NQ, false><<<(unsigned)plan.n_super, TILE_CELLS, smem, ctx->stream>>>(T, a, g);
+  k_lb_tile<NB, NQ, EXT, MULTI><<<(unsigned)plan.n_super, TILE_CELLS, smem, ctx->stream>>>(T, a, g);
   ctx->launches++;
+}
+
+template <int NB, int NQ>
+static void launch_lb_tile(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, const TileArgs& a, const CellGeo& g, bool extrinsic) {
+  constexpr int M = NB * NB;
+  if (extrinsic) launch_lb_tile_k<NB, NQ, true, false>(ctx, plan, T, a, g);     // geometry classes are an intrinsic-form feature
+  else if (plan.classes) launch_lb_tile_k<NB, NQ, false, true>(ctx, plan, T, a, g);
+  else launch_lb_tile_k<NB, NQ, false, false>(ctx, plan, T, a, g);
+  if (plan.n_groups) {
+    ProfScope ps(ctx, "k_lb_tile_groups");
+    k_lb_tile_groups<M><<<(unsigned)plan.n_groups, TILE_CELLS, 0, ctx->stream>>>(T, a);
+    ctx->launches++;
+  }
   GG_CUDA(cudaGetLastError());
 }
 
@@ -473,7 +484,9 @@ static bool run_lb_tile(gg_mesh* m, int order, int nq, bool extrinsic, const int
   load_const_tables(ctx, order, nq);
   CellGeo g = cell_geo(m, nq);
   TileDev T = plan.dev();
-  TileArgs a{dofs, pipe->vec_out ? u : nullptr, dir, pipe->scale, pipe->add, A->d_vals.p, pipe->vec_out};
+  auto even = [](int x) { return (x + 1) & ~1; };
+  TileArgs a{dofs, pipe->vec_out ? u : nullptr, dir, pipe->scale, pipe->add, A->d_vals.p, pipe->vec_out,
+             even(plan.max_slots + 32), even(plan.max_rows + 32), even(plan.max_rows)};
 #define GG_CASE(NB_, NQ_) \
   if (order + 1 == NB_ && nq == NQ_) { launch_lb_tile<NB_, NQ_>(ctx, plan, T, a, g, extrinsic); pipe->vec_done = pipe->vec_out != nullptr; return true; }
   GG_CASE(2, 2) GG_CASE(2, 3) GG_CASE(2, 4) GG_CASE(2, 7)

@@ -14,49 +14,93 @@ struct TileArgs {
   int add;
   double* vals;           // CSR values
   double* vec_out;        // residual (nullptr: matrix only)
+  // shared-memory layout of k_lb_tile (sized by the plan): value accumulators, residual accumulators, rows staged
+  int32_t n_acc, n_vacc, n_rows;
 };
 
-__device__ __forceinline__ double tile_sum4(const double* __restrict__ s, ushort4 q) {
-  double v = s[q.x];
-  if (q.y != TILE_NONE) v += s[q.y];
-  if (q.z != TILE_NONE) v += s[q.z];
-  if (q.w != TILE_NONE) v += s[q.w];
-  return v;
+__device__ __forceinline__ void tile_cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tile_cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tile_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared-memory layout of k_lb_tile: double A_s[n_acc] value accumulators (incl. 32 dummies; the parked state values u_e
+// [M][128] alias their head), double V_s[n_vacc] residual accumulators (incl. 32 dummies), int32 base_s[n_rows] / dof_s[n_rows]
+// CSR bases and DOF ids of the tile's rows.  n_acc, n_vacc, n_rows are even.
+inline size_t tile_smem_bytes(int M, int n_acc, int n_vacc, int n_rows) {
+  const size_t acc = (size_t)(n_acc > M * TILE_CELLS ? n_acc : M * TILE_CELLS);
+  return (acc + (size_t)n_vacc + (size_t)n_rows) * sizeof(double);
 }
 
-template <int NB, int NQ, bool EXTRINSIC>
+template <int M>
+__host__ __device__ constexpr int tile_packed(int I, int J) {  // I <= J
+  return I * M - (I * (I - 1)) / 2 + (J - I);
+}
+
+// MULTI: geometry-class mode, a CTA serves several tiles with the same chart boxes from one set of element matrices
+template <int NB, int NQ, bool EXTRINSIC, bool MULTI>
 __global__ void __launch_bounds__(TILE_CELLS, 3)
 k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
   constexpr int M = NB * NB, NS = NB * (NB + 1) / 2, NP = M * (M + 1) / 2;
   constexpr int ROW = 2 * NS + M;
   constexpr int ONN = 0, ODD = NS, OND = 2 * NS;
   extern __shared__ double sm[];
-  double* Ks = sm;                                  // [NP][TILE_CELLS] packed element matrices of the tile
-  double* Rs = Ks + NP * TILE_CELLS;                // [M][TILE_CELLS] element residuals (Gridap local order)
-  int32_t* rowbase = (int32_t*)(Rs + M * TILE_CELLS);   // [TILE_ROWCAP] first CSR slot of the rows being written
-  __shared__ int32_t s_ready[32];
-  __shared__ int32_t s_geo[4], s_gvo[4], s_gnb[4];   // border-buffer offsets / border counts of the tiles of the group at hand
-  const int lc = threadIdx.x;
-  const int i0 = T.inst_ptr[blockIdx.x], i1 = T.inst_ptr[blockIdx.x + 1];
-  const int32_t crep = T.tile_cells[(int64_t)T.inst_tile[i0] * TILE_CELLS + lc];
+  double* A_s = sm;
+  double* U_s = sm;                                  // parked u_e: consumed before the accumulators are zeroed
+  double* V_s = sm + (a.n_acc > M * TILE_CELLS ? a.n_acc : M * TILE_CELLS);
+  int32_t* base_s = (int32_t*)(V_s + a.n_vacc);
+  int32_t* dof_s = base_s + a.n_rows;
+  const int lc = threadIdx.x, lane = lc & 31, warp = lc >> 5;
+  // without geometry classes supertile b is tile b
+  const int i0 = MULTI ? T.inst_ptr[blockIdx.x] : (int)blockIdx.x, i1 = MULTI ? T.inst_ptr[blockIdx.x + 1] : i0 + 1;
+  const int32_t tile0 = MULTI ? T.inst_tile[i0] : (int32_t)blockIdx.x;
+  const int32_t crep = T.tile_cells[(int64_t)tile0 * TILE_CELLS + lc];
+
+  // ---- prologue: the row bases the write-out will need start their way into shared memory now (cp.async); the state values of
+  //      the thread's cell are gathered while the geometry loads are in flight and parked in shared memory ----
+  auto prefetch_rows = [&](int32_t tile) {
+    const int nrows = T.pats[T.tile_pat[tile]].nrows;
+    const int32_t r0 = T.tile_row0[tile];
+    for (int k = lc; k < nrows; k += TILE_CELLS) {
+      tile_cp_async4(base_s + k, T.trow_base + r0 + k);
+      if (a.vec_out) tile_cp_async4(dof_s + k, T.trow_dof + r0 + k);
+    }
+  };
+  auto gather_state = [&](int32_t tile) {
+    if (a.vec_out) {
+      const int32_t* __restrict__ td = T.tc_dofs + (int64_t)tile * (M * TILE_CELLS) + lc;
+      int32_t d[M];
+#pragma unroll
+      for (int I = 0; I < M; ++I) d[I] = td[I * TILE_CELLS];
+#pragma unroll
+      for (int I = 0; I < M; ++I) U_s[I * TILE_CELLS + lc] = d[I] >= 0 ? a.u[d[I]] : a.dirichlet;
+    }
+  };
+  prefetch_rows(tile0);
+  gather_state(tile0);
 
   // ---- element matrix of the thread's cell (the instances of a supertile have the same chart boxes) ----
   double acc[NP];
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = 0.0;
   if (crep >= 0) {
-    const int64_t c = crep;
-    const double HX = g.hx[c], HY = g.hy[c];
+    const int64_t tl = (int64_t)tile0 * TILE_CELLS + lc;
+    const double HX = T.tc_hx[tl], HY = T.tc_hy[tl];
     const double rx = HY / HX, ry = HX / HY;
-    const double* __restrict__ ta = g.tx + (int64_t)g.ix[c] * NQ;
-    const double* __restrict__ tb = g.ty + (int64_t)g.iy[c] * NQ;
+    const double* __restrict__ ta = g.tx + (int64_t)T.tc_ix[tl] * NQ;
+    const double* __restrict__ tb = g.ty + (int64_t)T.tc_iy[tl] * NQ;
     int panel = 0;
-    if (EXTRINSIC) panel = g.chart[c];
-    // 1 + b^2 is recomputed at every point (one DFMA) instead of being kept for the whole cell: the 2 NQ registers it would
-    // hold are what the scatter bookkeeping of this kernel needs to stay clear of spills in the hot loop
-    double b[NQ];
+    if (EXTRINSIC) panel = g.chart[crep];
+    double b[NQ], sb[NQ];
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) b[j] = tb[j];
+    for (int j = 0; j < NQ; ++j) {
+      b[j] = tb[j];
+      sb[j] = fma(b[j], b[j], 1.0);
+    }
 #pragma unroll 1
     for (int q1 = 0; q1 < NQ; ++q1) {
       const double av = ta[q1];
@@ -72,7 +116,7 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
         if (!EXTRINSIC) {
           const double rinv = fast_rsqrt(fma(b[q2], b[q2], sa));
           const double ar = av * rinv;
-          G11 = fma(b[q2], b[q2], 1.0) * rinv;
+          G11 = sb[q2] * rinv;
           G12 = ar * b[q2];
           G22 = sa * rinv;
         } else {
@@ -111,205 +155,193 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
             }
     }
   }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) Ks[c_plane[p] * TILE_CELLS + lc] = acc[p];
+
 
   for (int inst = i0; inst < i1; ++inst) {
-    const int32_t tile = T.inst_tile[inst];
+    const int32_t tile = MULTI ? T.inst_tile[inst] : tile0;
     const int32_t patid = T.tile_pat[tile];
-    const TilePat P = T.pats[patid];
     const int32_t c = T.tile_cells[(int64_t)tile * TILE_CELLS + lc];
-    const int bi = T.bidx[(int64_t)patid * TILE_CELLS + lc];
-    // the thread's own element matrix, back from shared memory (so that it is not live in registers across the scatter phases)
-    double kv[NP];
-    if (c >= 0 && (a.vec_out || bi != 0xFF)) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) kv[p] = Ks[c_plane[p] * TILE_CELLS + lc];
+    const bool border = T.bidx[(int64_t)patid * TILE_CELLS + lc] != 0xFF && c >= 0;
+    const TilePat* __restrict__ P = T.pats + patid;
+    const int nslots = P->nslots, nrows = P->nrows;
+    if (MULTI && inst > i0) {
+      __syncthreads();            // the previous instance has been written out
+      prefetch_rows(tile);
+      gather_state(tile);
     }
-    // ---- element residual r_e = K_e u_e of this instance's cell ----
+    // ---- element residual r_e = K_e u_e; border cells leave their element matrix / vector in the global border buffers ----
+    double re[M], ue[M];
     if (a.vec_out && c >= 0) {
-      double ue[M], re[M];
 #pragma unroll
-      for (int I = 0; I < M; ++I) {
-        const int32_t d = a.cell_dofs[(int64_t)c * M + c_lex2loc[I]];
-        ue[I] = d >= 0 ? a.u[d] : a.dirichlet;
-        re[I] = 0.0;
-      }
-      int p = 0;
+      for (int I = 0; I < M; ++I) ue[I] = U_s[I * TILE_CELLS + lc];
+    }
+    __syncthreads();              // everybody has its u_e: the area becomes the accumulators
+    if (a.vec_out && c >= 0) {
+#pragma unroll
+      for (int I = 0; I < M; ++I) re[I] = 0.0;
 #pragma unroll
       for (int I = 0; I < M; ++I)
 #pragma unroll
         for (int J = I; J < M; ++J) {
-          re[I] = fma(kv[p], ue[J], re[I]);
-          if (J != I) re[J] = fma(kv[p], ue[I], re[J]);
-          ++p;
+          re[I] = fma(acc[tile_packed<M>(I, J)], ue[J], re[I]);
+          if (J != I) re[J] = fma(acc[tile_packed<M>(I, J)], ue[I], re[J]);
         }
-#pragma unroll
-      for (int I = 0; I < M; ++I) Rs[c_lex2loc[I] * TILE_CELLS + lc] = re[I];
-      if (bi != 0xFF) {
+      if (border) {
         double* vb = T.vbuf_b + T.tile_voff[tile];
 #pragma unroll
-        for (int I = 0; I < M; ++I) __stcg(vb + c_lex2loc[I] * P.nborder + bi, re[I]);
+        for (int I = 0; I < M; ++I) vb[c_lex2loc[I] * TILE_CELLS + lc] = re[I];
       }
     }
-    // ---- border cells: element matrix to the global border buffer, for the rows shared with other tiles ----
-    if (bi != 0xFF && c >= 0) {
+    if (border) {
       double* eb = T.ebuf_b + T.tile_eoff[tile];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) __stcg(eb + c_plane[p] * P.nborder + bi, kv[p]);
+      for (int p = 0; p < NP; ++p) eb[c_plane[p] * TILE_CELLS + lc] = acc[p];
     }
-    __threadfence();
-    __syncthreads();
-    // ---- complete rows: first CSR slot of every row into shared memory; residual entries of the rows ----
+    // ---- conflict-free accumulation in rounds.  Every (cell, entry) knows the shared-memory slot it feeds and its ROUND: its
+    //      rank among the cells that feed the slot, in ascending cell order.  Round 0 stores, rounds 1..3 add, with a barrier in
+    //      between: no atomics, no zeroing, and every value is summed in ascending cell order.  Only entries whose two DOFs lie on
+    //      one edge of the cell can have a later round (tile_shared_pair), only a corner's diagonal entry a third or fourth ----
+    constexpr int PW = (M * M + 1) / 2, VW = (M + 1) / 2, P_ = NB - 1;
+    uint32_t pw[PW], vw[VW];
     {
-      const int32_t* __restrict__ tb = T.trow_base + T.tile_row0[tile];
-      const int32_t* __restrict__ td = T.trow_dof + T.tile_row0[tile];
-      const ushort4* __restrict__ vs = T.rowvsrc + P.row0;
-      for (int k0 = lc; k0 < P.nrows; k0 += 4 * TILE_CELLS) {
-        int32_t rb[4], d[4];
-        ushort4 s4[4];
+      const uint32_t* __restrict__ pi = T.pair_idx + (size_t)patid * (PW * TILE_CELLS) + lc;
+      const uint32_t* __restrict__ vi = T.vec_idx + (size_t)patid * (VW * TILE_CELLS) + lc;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int k = k0 + w * TILE_CELLS;
-          if (k < P.nrows) {
-            rb[w] = tb[k];
-            if (a.vec_out) { d[w] = td[k]; s4[w] = vs[k]; }
-          }
+      for (int q = 0; q < PW; ++q) pw[q] = __ldg(pi + q * TILE_CELLS);
+      if (a.vec_out) {
+#pragma unroll
+        for (int q = 0; q < VW; ++q) vw[q] = __ldg(vi + q * TILE_CELLS);
+      }
+    }
+    auto entry = [&](int e) { return (e & 1) ? (pw[e >> 1] >> 16) : (pw[e >> 1] & 0xFFFFu); };
+    auto ventry = [&](int I) { return (I & 1) ? (vw[I >> 1] >> 16) : (vw[I >> 1] & 0xFFFFu); };
+    if (c >= 0) {
+#pragma unroll
+      for (int I = 0; I < M; ++I)
+#pragma unroll
+        for (int J = 0; J < M; ++J) {
+          const uint32_t w = entry(I * M + J);
+          const double v = acc[I <= J ? tile_packed<M>(I, J) : tile_packed<M>(J, I)];
+          if (!tile_shared_pair(P_, I, J) || (w >> 14) == 0u) A_s[w & 0x3FFFu] = v;
         }
+      if (a.vec_out) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int k = k0 + w * TILE_CELLS;
-          if (k < P.nrows) {
-            rowbase[k] = rb[w];
-            if (a.vec_out) {
-              const double v = a.scale * tile_sum4(Rs, s4[w]);
-              a.vec_out[d[w]] = a.add ? a.vec_out[d[w]] + v : v;
-            }
+        for (int I = 0; I < M; ++I) {
+          const uint32_t w = ventry(I);
+          if (!tile_shared_dof(P_, I) || (w >> 14) == 0u) V_s[w & 0x3FFFu] = re[I];
+        }
+      }
+    }
+#pragma unroll
+    for (int round = 1; round < 4; ++round) {
+      __syncthreads();
+      if (c >= 0) {
+#pragma unroll
+        for (int I = 0; I < M; ++I)
+#pragma unroll
+          for (int J = 0; J < M; ++J) {
+            if (!tile_shared_pair(P_, I, J)) continue;
+            if (round > 1 && !(I == J && tile_corner_dof(P_, I))) continue;
+            const uint32_t w = entry(I * M + J);
+            if ((w >> 14) == (uint32_t)round) A_s[w & 0x3FFFu] += acc[I <= J ? tile_packed<M>(I, J) : tile_packed<M>(J, I)];
+          }
+        if (a.vec_out) {
+#pragma unroll
+          for (int I = 0; I < M; ++I) {
+            if (!tile_shared_dof(P_, I)) continue;
+            if (round > 1 && !tile_corner_dof(P_, I)) continue;
+            const uint32_t w = ventry(I);
+            if ((w >> 14) == (uint32_t)round) V_s[w & 0x3FFFu] += re[I];
           }
         }
       }
     }
+    tile_cp_async_wait();
     __syncthreads();
-    // ---- complete rows: every CSR value summed from shared memory in ascending cell order, written once ----
-    {
-      const uint32_t* __restrict__ em = T.emeta + P.ent0;
-      const ushort4* __restrict__ es = T.esrc + P.ent0;
-      constexpr int U = 8;
-      for (int e0 = lc; e0 < P.nent; e0 += U * TILE_CELLS) {
-        uint32_t mt[U];
-        ushort4 s4[U];
-#pragma unroll
-        for (int w = 0; w < U; ++w) {
-          const int e = e0 + w * TILE_CELLS;
-          if (e < P.nent) { mt[w] = em[e]; s4[w] = es[e]; }
-        }
-#pragma unroll
-        for (int w = 0; w < U; ++w) {
-          const int e = e0 + w * TILE_CELLS;
-          if (e < P.nent) {
-            const double v = a.scale * tile_sum4(Ks, s4[w]);
-            double* dst = a.vals + rowbase[mt[w] >> 8] + (mt[w] & 255u);
-            *dst = a.add ? *dst + v : v;
-          }
-        }
+    // ---- write-out: a warp takes floor(32 / len) rows at a time, one lane per CSR value (consecutive lanes -> consecutive
+    //      addresses); the accumulators of a class are laid out row after row ----
+    const int ncls = P->ncls;
+    for (int q = 0; q < ncls; ++q) {
+      const int len = P->cls[q].len, first = P->cls[q].first, count = P->cls[q].count, slot0 = P->cls[q].slot0;
+      const int rpw = 32 / len;
+      const int r = lane / len, jj = lane - r * len;
+      if (r >= rpw) continue;
+#pragma unroll 4
+      for (int k = warp * rpw + r; k < count; k += 4 * rpw) {
+        const double t = a.scale * A_s[slot0 + k * len + jj];
+        double* dst = a.vals + base_s[first + k] + jj;
+        *dst = a.add ? *dst + t : t;
       }
     }
-    // ---- groups of rows shared with other tiles: the last tile to arrive sums them from the border buffers ----
-    const int gb = T.tg_ptr[tile], ge = T.tg_ptr[tile + 1];
-    for (int g0 = gb; g0 < ge; g0 += 32) {
-      __syncthreads();
-      if (lc < 32) {
-        int ready = -1;
-        if (g0 + lc < ge) {
-          const int32_t gidx = T.tg_idx[g0 + lc];
-          const int old = atomicAdd(&T.gcount[gidx], 1);
-          if (old == T.groups[gidx].need - 1) { ready = gidx; T.gcount[gidx] = 0; }
-        }
-        s_ready[lc] = ready;
-      }
-      __syncthreads();
-      for (int q = 0; q < 32 && g0 + q < ge; ++q) {
-        const int32_t gidx = s_ready[q];
-        if (gidx < 0) continue;                 // uniform across the CTA
-        __threadfence();
-        const GroupInst* __restrict__ Gp = T.groups + gidx;
-        const int32_t g_row0 = Gp->row0;
-        const GroupPat GP = T.gpats[Gp->pat];
-        __syncthreads();                        // rowbase and the group slots are free again
-        if (lc < 4) { s_geo[lc] = Gp->eoff[lc]; s_gvo[lc] = Gp->voff[lc]; s_gnb[lc] = Gp->nb[lc]; }
-        __syncthreads();
-        {
-          const int32_t* __restrict__ tb = T.grow_base + g_row0;
-          const int32_t* __restrict__ td = T.grow_dof + g_row0;
-          const ushort4* __restrict__ vs = T.g_rowvsrc + GP.row0;
-          for (int k = lc; k < GP.nrows; k += TILE_CELLS) {
-            rowbase[k] = tb[k];
-            if (a.vec_out) {
-              const ushort4 s4 = vs[k];
-              const int32_t d = td[k];
-              auto ld = [&](uint16_t code) {
-                const int ts = code >> 11;
-                return __ldcg(T.vbuf_b + s_gvo[ts] + (code & 15) * s_gnb[ts] + ((code >> 4) & 127));
-              };
-              const double v0 = ld(s4.x);
-              const double v1 = s4.y != TILE_NONE ? ld(s4.y) : 0.0;
-              const double v2 = s4.z != TILE_NONE ? ld(s4.z) : 0.0;
-              const double v3 = s4.w != TILE_NONE ? ld(s4.w) : 0.0;
-              double v = v0;
-              if (s4.y != TILE_NONE) v += v1;
-              if (s4.z != TILE_NONE) v += v2;
-              if (s4.w != TILE_NONE) v += v3;
-              v *= a.scale;
-              a.vec_out[d] = a.add ? a.vec_out[d] + v : v;
-            }
-          }
-        }
-        __syncthreads();
-        {
-          const uint32_t* __restrict__ em = T.g_emeta + GP.ent0;
-          const ushort4* __restrict__ es = T.g_esrc + GP.ent0;
-          constexpr int U = 4;
-          for (int e0 = lc; e0 < GP.nent; e0 += U * TILE_CELLS) {
-            uint32_t mt[U];
-            ushort4 s4[U];
-            double v[U][4];
-#pragma unroll
-            for (int w = 0; w < U; ++w) {
-              const int e = e0 + w * TILE_CELLS;
-              if (e < GP.nent) { mt[w] = em[e]; s4[w] = es[e]; }
-            }
-            auto ld = [&](uint16_t code) {
-              const int ts = code >> 13;
-              return __ldcg(T.ebuf_b + s_geo[ts] + (code & 63) * s_gnb[ts] + ((code >> 6) & 127));
-            };
-#pragma unroll
-            for (int w = 0; w < U; ++w) {
-              const int e = e0 + w * TILE_CELLS;
-              if (e < GP.nent) {
-                v[w][0] = ld(s4[w].x);
-                v[w][1] = s4[w].y != TILE_NONE ? ld(s4[w].y) : 0.0;
-                v[w][2] = s4[w].z != TILE_NONE ? ld(s4[w].z) : 0.0;
-                v[w][3] = s4[w].w != TILE_NONE ? ld(s4[w].w) : 0.0;
-              }
-            }
-#pragma unroll
-            for (int w = 0; w < U; ++w) {
-              const int e = e0 + w * TILE_CELLS;
-              if (e < GP.nent) {
-                double t = v[w][0];                       // same order of additions as the sources are listed (ascending cell)
-                if (s4[w].y != TILE_NONE) t += v[w][1];
-                if (s4[w].z != TILE_NONE) t += v[w][2];
-                if (s4[w].w != TILE_NONE) t += v[w][3];
-                t *= a.scale;
-                double* dst = a.vals + rowbase[mt[w] >> 8] + (mt[w] & 255u);
-                *dst = a.add ? *dst + t : t;
-              }
-            }
-          }
-        }
+    if (a.vec_out) {
+      for (int k = lc; k < nrows; k += TILE_CELLS) {
+        const double t = a.scale * V_s[k];
+        const int32_t d = dof_s[k];
+        a.vec_out[d] = a.add ? a.vec_out[d] + t : t;
       }
     }
-    __syncthreads();   // Rs / rowbase are reused by the next instance
+  }
+}
+
+// Rows shared by several tiles (tile edges and corners): one CTA per group sums them from the border buffers the tile kernel
+// has just written (mostly L2 hits), in the same ascending cell order.
+template <int M>
+__global__ void __launch_bounds__(TILE_CELLS)
+k_lb_tile_groups(TileDev T, TileArgs a) {
+  const GroupInst* __restrict__ G = T.groups + blockIdx.x;
+  const TilePat* __restrict__ P = T.gpats + G->pat;
+  const GroupRow* __restrict__ rows = T.grows + P->row0;
+  const int32_t* __restrict__ base = T.grow_base + G->row0;
+  const int32_t* __restrict__ dofs = T.grow_dof + G->row0;
+  __shared__ int32_t s_eo[4], s_vo[4];
+  const int lc = threadIdx.x, lane = lc & 31, warp = lc >> 5;
+  if (lc < 4) { s_eo[lc] = G->eoff[lc]; s_vo[lc] = G->voff[lc]; }
+  __syncthreads();
+  const int ncls = P->ncls;
+  for (int q = 0; q < ncls; ++q) {
+    const int len = P->cls[q].len, first = P->cls[q].first, count = P->cls[q].count;
+    const int rpw = 32 / len;
+    const int r = lane / len, jj = lane - r * len;
+    if (r >= rpw) continue;
+    const int last = first + count;
+#pragma unroll 2
+    for (int k = first + warp * rpw + r; k < last; k += 4 * rpw) {
+      const GroupRow R = rows[k];
+      const uint32_t s4 = __ldg((const uint32_t*)T.types[R.type].src[jj]);
+      double v[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t code = (s4 >> (8 * w)) & 255u;
+        v[w] = 0.0;
+        if (code != 255u) {
+          const uint32_t cc = R.cell[code >> 6];
+          v[w] = __ldcg(T.ebuf_b + s_eo[cc >> 7] + (int)(code & 63u) * TILE_CELLS + (cc & 127u));
+        }
+      }
+      const double t = a.scale * (((v[0] + v[1]) + v[2]) + v[3]);
+      double* dst = a.vals + base[k] + jj;
+      *dst = a.add ? *dst + t : t;
+    }
+  }
+  if (a.vec_out) {
+    const int nrows = P->nrows;
+    for (int k = lc; k < nrows; k += TILE_CELLS) {
+      const GroupRow R = rows[k];
+      const uint32_t s4 = __ldg((const uint32_t*)T.types[R.type].vsrc);
+      double v[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t code = (s4 >> (8 * w)) & 255u;
+        v[w] = 0.0;
+        if (code != 255u) {
+          const uint32_t cc = R.cell[(code >> 4) & 3u];
+          v[w] = __ldcg(T.vbuf_b + s_vo[cc >> 7] + (int)(code & 15u) * TILE_CELLS + (cc & 127u));
+        }
+      }
+      const double t = a.scale * (((v[0] + v[1]) + v[2]) + v[3]);
+      const int32_t d = dofs[k];
+      a.vec_out[d] = a.add ? a.vec_out[d] + t : t;
+    }
   }
 }
 

@@ -5,6 +5,7 @@
 #include <map>
 #include <unordered_map>
 #include "gg_common.cuh"
+#include "gg_refel.cuh"
 #include "gg_tile.cuh"
 
 namespace gg {
@@ -12,8 +13,6 @@ namespace gg {
 namespace {
 
 constexpr int TX = 16, TY = 8;
-
-struct Src4 { uint16_t s[4]; };
 
 // byte-wise identity of a pattern: FNV hash + full comparison
 struct Blob {
@@ -53,12 +52,13 @@ inline int plane_of(int M, int i, int j) {
 
 TileDev TilePlan::dev() const {
   TileDev T;
-  T.n_super = (int32_t)n_super;
+  T.n_super = (int32_t)n_super; T.n_groups = (int32_t)n_groups;
   T.inst_ptr = inst_ptr.p; T.inst_tile = inst_tile.p;
   T.tile_cells = tile_cells.p; T.tile_pat = tile_pat.p; T.tile_eoff = tile_eoff.p; T.tile_voff = tile_voff.p;
-  T.pats = pats.p; T.tile_row0 = tile_row0.p; T.trow_base = trow_base.p; T.trow_dof = trow_dof.p; T.rowvsrc = rowvsrc.p; T.emeta = emeta.p; T.esrc = esrc.p; T.bidx = bidx.p;
-  T.tg_ptr = tg_ptr.p; T.tg_idx = tg_idx.p; T.groups = groups.p; T.gcount = gcount.p; T.gpats = gpats.p;
-  T.grow_base = grow_base.p; T.grow_dof = grow_dof.p; T.g_rowvsrc = g_rowvsrc.p; T.g_emeta = g_emeta.p; T.g_esrc = g_esrc.p;
+  T.tile_row0 = tile_row0.p; T.trow_base = trow_base.p; T.trow_dof = trow_dof.p;
+  T.pats = pats.p; T.pair_idx = pair_idx.p; T.vec_idx = vec_idx.p;
+  T.tc_ix = tc_ix.p; T.tc_iy = tc_iy.p; T.tc_dofs = tc_dofs.p; T.tc_hx = tc_hx.p; T.tc_hy = tc_hy.p; T.bidx = bidx.p; T.types = types.p;
+  T.groups = groups.p; T.gpats = gpats.p; T.grows = grows.p; T.grow_base = grow_base.p; T.grow_dof = grow_dof.p;
   T.ebuf_b = ebuf_b.p; T.vbuf_b = vbuf_b.p;
   return T;
 }
@@ -70,7 +70,7 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
   cudaStream_t st = ctx->stream;
   const int M = S->ndofs_loc, NP = M * (M + 1) / 2;
   const int64_t nc = m->n_cells, nd = S->n_free;
-  if (A->test != A->trial || m->dim != 2 || M > 16 || NP > 64 || nc == 0 || A->nnz == 0) return nullptr;
+  if (A->test != A->trial || m->dim != 2 || M > 16 || NP > 63 || nc == 0 || A->nnz == 0) return nullptr;
   if ((int64_t)m->h_ix.size() != nc || (int64_t)m->h_iy.size() != nc || (int64_t)S->cell_dofs.size() != nc * M) return nullptr;
   if (classes) {
     mesh_geometry_classes(m);
@@ -120,15 +120,50 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
   std::vector<int32_t> dtiles(nd * 4, -1);
   std::vector<uint8_t> dnt(nd, 0);
   for (int64_t d = 0; d < nd; ++d) {
+    if (dptr[d + 1] - dptr[d] > 4 || rp[d + 1] - rp[d] > TILE_MAXLEN) return nullptr;   // more than four cells around a DOF / long rows
     for (int32_t k = dptr[d]; k < dptr[d + 1]; ++k) {
       const int32_t t = cell_tile[dsrc[k] / M];
       bool seen = false;
       for (int q = 0; q < dnt[d]; ++q) seen |= dtiles[d * 4 + q] == t;
-      if (seen) continue;
-      if (dnt[d] == 4) return nullptr;   // more than four tiles around a DOF: not a quadrilateral-like tiling
-      dtiles[d * 4 + dnt[d]++] = t;
+      if (!seen) dtiles[d * 4 + dnt[d]++] = t;
     }
     std::sort(&dtiles[d * 4], &dtiles[d * 4] + dnt[d]);
+  }
+
+  // ---- row types ------------------------------------------------------------------------------------------------------------------
+  std::vector<RowType> types;
+  std::map<std::vector<uint8_t>, int32_t> type_id;
+  std::vector<int32_t> dof_type(nd);
+  for (int64_t d = 0; d < nd; ++d) {
+    RowType R;
+    std::memset(&R, 0xFF, sizeof(R));
+    R.len = rp[d + 1] - rp[d];
+    for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {        // slot = position in the ascending cell list
+      const int s_ = q - dptr[d];
+      const int32_t c = dsrc[q] / M, i = dsrc[q] % M;
+      R.vsrc[s_] = (uint8_t)((s_ << 4) | i);
+      for (int j2 = 0; j2 < M; ++j2) {
+        const int32_t col = dofs[(int64_t)c * M + j2];
+        if (col < 0) continue;
+        const int32_t* b = &ci[rp[d]];
+        const int32_t* e = &ci[rp[d + 1]];
+        const int32_t* it = std::lower_bound(b, e, col);
+        if (it == e || *it != col) return nullptr;
+        uint8_t* src = R.src[it - b];
+        int w = 0;
+        while (w < 4 && src[w] != 0xFF) ++w;
+        if (w == 4) return nullptr;
+        src[w] = (uint8_t)((s_ << 6) | plane_of(M, i, j2));
+      }
+    }
+    std::vector<uint8_t> k((const uint8_t*)&R, (const uint8_t*)&R + sizeof(R));
+    auto it = type_id.find(k);
+    if (it == type_id.end()) {
+      it = type_id.emplace(std::move(k), (int32_t)types.size()).first;
+      types.push_back(R);
+      if (types.size() > 60000) return nullptr;
+    }
+    dof_type[d] = it->second;
   }
 
   // position of column q in row d
@@ -144,7 +179,7 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
 
   // ---- border cells of every tile (cells with a DOF shared with another tile) -------------------------------------------------
   std::vector<uint8_t> bidx_tile(n_tiles * TILE_CELLS, 0xFF);
-  std::vector<int32_t> nborder(n_tiles, 0), tile_eoff(n_tiles), tile_voff(n_tiles);
+  std::vector<int32_t> tile_eoff(n_tiles), tile_voff(n_tiles);
   for (int64_t t = 0; t < n_tiles; ++t)
     for (int lc = 0; lc < TILE_CELLS; ++lc) {
       const int32_t c = tile_cells[t * TILE_CELLS + lc];
@@ -154,88 +189,148 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
         const int32_t d = dofs[(int64_t)c * M + i];
         border |= d >= 0 && dnt[d] > 1;
       }
-      if (border) bidx_tile[t * TILE_CELLS + lc] = (uint8_t)nborder[t]++;
+      if (border) { bidx_tile[t * TILE_CELLS + lc] = 1; plan->border_cells++; }
     }
   {
+    // [plane][local cell] per tile; only border cells are ever written / read
     int64_t eo = 0, vo = 0;
     for (int64_t t = 0; t < n_tiles; ++t) {
       tile_eoff[t] = (int32_t)eo; tile_voff[t] = (int32_t)vo;
-      eo += (int64_t)nborder[t] * NP; vo += (int64_t)nborder[t] * M;
-      plan->border_cells += nborder[t];
+      eo += (int64_t)TILE_CELLS * NP; vo += (int64_t)TILE_CELLS * M;
     }
     if (eo >= (int64_t)INT32_MAX) return nullptr;
     plan->ebuf_b.alloc((size_t)std::max<int64_t>(eo, 1));
     plan->vbuf_b.alloc((size_t)std::max<int64_t>(vo, 1));
   }
 
+  // rows of one pattern: sorted by (length, DOF id), cut into classes of equal length
+  auto sort_rows = [&](std::vector<int32_t>& rows) {
+    std::sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) {
+      const int la = rp[a + 1] - rp[a], lb = rp[b + 1] - rp[b];
+      return la != lb ? la > lb : a < b;
+    });
+  };
+  auto make_classes = [&](const std::vector<int32_t>& rows, TilePat& P) -> bool {
+    P.nrows = (int32_t)rows.size(); P.ncls = 0; P.nslots = 0;
+    std::memset(P.cls, 0, sizeof(P.cls));
+    for (size_t k = 0; k < rows.size(); ++k) {
+      const int len = rp[rows[k] + 1] - rp[rows[k]];
+      if (P.ncls == 0 || P.cls[P.ncls - 1].len != len) {
+        if (P.ncls == TILE_MAXCLS) return false;
+        P.cls[P.ncls++] = RowClass{len, (int32_t)k, 0, 0};
+      }
+      P.cls[P.ncls - 1].count++;
+    }
+    return true;
+  };
+
   // ---- complete rows of every tile -> patterns ----------------------------------------------------------------------------------
+  std::vector<int32_t> l2x(M);                 // Gridap local dof -> lexicographic index (the order of the kernel's registers)
+  {
+    std::vector<int32_t> t = quad_local_to_lex(S->order);   // the same table the kernel's c_lex2loc is built from
+    if ((int)t.size() != M) return nullptr;
+    for (int i = 0; i < M; ++i) l2x[i] = t[i];
+  }
   std::vector<TilePat> pats;
+  std::vector<uint32_t> pair_idx, vec_idx;
+  const int PW = (M * M + 1) / 2, VW = (M + 1) / 2;
   std::vector<int32_t> tile_row0(n_tiles), trow_base, trow_dof;
-  std::vector<Src4> rowvsrc, esrc;
-  std::vector<uint32_t> emeta;
   std::vector<uint8_t> bidx;
   std::vector<int32_t> tile_pat(n_tiles);
   PatStore store;
   std::vector<std::vector<int32_t>> tile_rows(n_tiles);
   for (int64_t d = 0; d < nd; ++d)
-    if (dnt[d] == 1) tile_rows[dtiles[d * 4]].push_back((int32_t)d);   // ascending d
+    if (dnt[d] == 1) tile_rows[dtiles[d * 4]].push_back((int32_t)d);
+  std::vector<int32_t> row_slot0(nd, -1), row_k(nd, -1);    // scratch: first shared-memory slot / row index of a complete row
   for (int64_t t = 0; t < n_tiles; ++t) {
-    const auto& rows = tile_rows[t];
+    auto& rows = tile_rows[t];
     if ((int)rows.size() > TILE_ROWCAP) return nullptr;
-    std::vector<Src4> p_rowvsrc, p_esrc;
-    std::vector<uint32_t> p_emeta;
+    sort_rows(rows);
+    TilePat P;
+    P.row0 = 0;
+    if (!make_classes(rows, P)) return nullptr;
+    int nslots = 0;
+    for (int q = 0; q < P.ncls; ++q) { P.cls[q].slot0 = nslots; nslots += P.cls[q].len * P.cls[q].count; }
+    if (nslots + 32 > 16384) return nullptr;      // 14-bit slots
+    P.nslots = nslots;
     tile_row0[t] = (int32_t)trow_base.size();
-    for (size_t k = 0; k < rows.size(); ++k) {
-      const int32_t d = rows[k];
-      const int len = rp[d + 1] - rp[d];
-      if (len > 255) return nullptr;
-      trow_base.push_back(rp[d]);
-      trow_dof.push_back(d);
-      Src4 vs{{TILE_NONE, TILE_NONE, TILE_NONE, TILE_NONE}};
-      if (dptr[d + 1] - dptr[d] > 4) return nullptr;
-      for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q)
-        vs.s[q - dptr[d]] = (uint16_t)(((dsrc[q] % M) << 7) | cell_lc[dsrc[q] / M]);
-      p_rowvsrc.push_back(vs);
-      const size_t e0 = p_esrc.size();
-      p_esrc.resize(e0 + len, Src4{{TILE_NONE, TILE_NONE, TILE_NONE, TILE_NONE}});
-      for (int j = 0; j < len; ++j) p_emeta.push_back((uint32_t)((k << 8) | (uint32_t)j));
-      for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {        // ascending cell
-        const int32_t c = dsrc[q] / M, i = dsrc[q] % M;
+    {
+      int q = 0;
+      for (size_t k = 0; k < rows.size(); ++k) {
+        const int32_t d = rows[k];
+        while (q + 1 < P.ncls && (int)k >= P.cls[q + 1].first) ++q;
+        row_slot0[d] = P.cls[q].slot0 + ((int)k - P.cls[q].first) * P.cls[q].len;
+        row_k[d] = (int)k;
+        trow_base.push_back(rp[d]);
+        trow_dof.push_back(d);
+        plan->complete_slots += rp[d + 1] - rp[d];
+      }
+    }
+    // slot of every (local cell, I, J) in lexicographic local order, with the ROUND of the contribution in the two top bits: the
+    // rank of the cell among the cells that feed the slot (ascending cell id).  Round 0 stores, rounds 1..3 add, with a barrier
+    // between rounds: conflict-free without atomics, and every slot is summed in ascending cell order.  Entries of rows that are
+    // not complete here (or Dirichlet) go, as round 0, to one of 32 dummy slots (one per lane) past the real ones
+    std::vector<uint32_t> p_pair((size_t)PW * TILE_CELLS, 0), p_vec((size_t)VW * TILE_CELLS, 0);
+    auto put16 = [](std::vector<uint32_t>& v, int idx, int lc, uint16_t val) {
+      uint32_t& w = v[(size_t)(idx >> 1) * TILE_CELLS + lc];
+      w = (idx & 1) ? (w & 0xFFFFu) | ((uint32_t)val << 16) : (w & 0xFFFF0000u) | val;
+    };
+    for (int lc = 0; lc < TILE_CELLS; ++lc) {
+      const int32_t c = tile_cells[t * TILE_CELLS + lc];
+      const uint16_t dummy = (uint16_t)(nslots + (lc & 31)), vdummy = (uint16_t)((int)rows.size() + (lc & 31));
+      for (int i = 0; i < M; ++i) {
+        const int I = l2x[i];
+        const int32_t d = c >= 0 ? dofs[(int64_t)c * M + i] : -1;
+        const bool complete = d >= 0 && dnt[d] == 1;
+        int vround = 0;
+        if (complete)
+          for (int32_t q = dptr[d]; q < dptr[d + 1] && dsrc[q] / M != c; ++q) ++vround;   // cells before this one around the DOF
+        if (vround > 0 && !tile_shared_dof(S->order, I)) return nullptr;
+        put16(p_vec, I, lc, complete ? (uint16_t)(row_k[d] | (vround << 14)) : vdummy);
         for (int j2 = 0; j2 < M; ++j2) {
-          const int32_t col = dofs[(int64_t)c * M + j2];
-          if (col < 0) continue;
-          const int pos = col_pos(d, col);
-          if (pos < 0) return nullptr;
-          Src4& e = p_esrc[e0 + pos];
-          int w = 0;
-          while (w < 4 && e.s[w] != TILE_NONE) ++w;
-          if (w == 4) return nullptr;
-          e.s[w] = (uint16_t)(plane_of(M, i, j2) * TILE_CELLS + cell_lc[c]);
+          const int J = l2x[j2];
+          uint16_t slot = dummy;
+          const int32_t col = c >= 0 ? dofs[(int64_t)c * M + j2] : -1;
+          if (complete && col >= 0) {
+            const int pos = col_pos(d, col);
+            if (pos < 0) return nullptr;
+            int round = 0;                     // cells before this one that hold both DOFs
+            for (int32_t q = dptr[d]; q < dptr[d + 1] && dsrc[q] / M != c; ++q) {
+              const int32_t c2 = dsrc[q] / M;
+              bool has = false;
+              for (int j3 = 0; j3 < M; ++j3) has |= dofs[(int64_t)c2 * M + j3] == col;
+              round += has;
+            }
+            // the kernel only looks for later rounds where the local geometry allows them
+            if (round > 0 && !tile_shared_pair(S->order, I, J)) return nullptr;
+            if (round > 1 && !(I == J && tile_corner_dof(S->order, I))) return nullptr;
+            slot = (uint16_t)((row_slot0[d] + pos) | (round << 14));
+          }
+          put16(p_pair, I * M + J, lc, slot);
         }
       }
     }
     std::vector<uint8_t> p_bidx(&bidx_tile[t * TILE_CELLS], &bidx_tile[t * TILE_CELLS] + TILE_CELLS);
+    std::vector<RowClass> p_cls(P.cls, P.cls + TILE_MAXCLS);
     Blob key2;
-    key2.put(p_rowvsrc); key2.put(p_emeta); key2.put(p_esrc); key2.put(p_bidx);
+    key2.put(p_pair); key2.put(p_vec); key2.put(p_bidx); key2.put(p_cls);
     bool is_new = false;
     const int32_t id = store.find_or_add(std::move(key2), (int32_t)pats.size(), &is_new);
     tile_pat[t] = id;
     if (is_new) {
-      TilePat P{(int32_t)rowvsrc.size(), (int32_t)p_rowvsrc.size(), (int32_t)emeta.size(), (int32_t)p_emeta.size(), nborder[t], 0};
       pats.push_back(P);
-      rowvsrc.insert(rowvsrc.end(), p_rowvsrc.begin(), p_rowvsrc.end());
-      emeta.insert(emeta.end(), p_emeta.begin(), p_emeta.end());
-      esrc.insert(esrc.end(), p_esrc.begin(), p_esrc.end());
+      pair_idx.insert(pair_idx.end(), p_pair.begin(), p_pair.end());
+      vec_idx.insert(vec_idx.end(), p_vec.begin(), p_vec.end());
       bidx.insert(bidx.end(), p_bidx.begin(), p_bidx.end());
     }
-    plan->complete_slots += (int64_t)p_emeta.size();
-    plan->max_rows = std::max(plan->max_rows, (int)p_rowvsrc.size());
+    plan->max_rows = std::max(plan->max_rows, (int)rows.size());
+    plan->max_slots = std::max(plan->max_slots, nslots);
   }
 
   // ---- incomplete rows: groups by the set of tiles around the row ------------------------------------------------------------
   std::map<std::array<int32_t, 4>, int32_t> gid;
   std::vector<std::array<int32_t, 4>> gtiles;
-  std::vector<std::vector<int32_t>> grows;
+  std::vector<std::vector<int32_t>> grows_of;
   for (int64_t d = 0; d < nd; ++d) {
     if (dnt[d] <= 1) continue;
     std::array<int32_t, 4> k{dtiles[d * 4], dtiles[d * 4 + 1], dtiles[d * 4 + 2], dtiles[d * 4 + 3]};
@@ -243,92 +338,59 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
     if (it == gid.end()) {
       it = gid.emplace(k, (int32_t)gtiles.size()).first;
       gtiles.push_back(k);
-      grows.emplace_back();
+      grows_of.emplace_back();
     }
-    grows[it->second].push_back((int32_t)d);
+    grows_of[it->second].push_back((int32_t)d);
   }
   const int64_t ng = (int64_t)gtiles.size();
-  std::vector<GroupPat> gpats;
+  std::vector<TilePat> gpats;
   std::vector<GroupInst> groups(ng);
+  std::vector<GroupRow> grows_all;
   std::vector<int32_t> grow_base, grow_dof;
-  std::vector<Src4> g_rowvsrc, g_esrc;
-  std::vector<uint32_t> g_emeta;
   PatStore gstore;
-  std::vector<std::vector<int32_t>> tile_groups(n_tiles);
   for (int64_t g = 0; g < ng; ++g) {
     const auto& tl = gtiles[g];
-    const auto& rows = grows[g];
-    if ((int)rows.size() > TILE_ROWCAP) return nullptr;
-    int need = 0;
-    for (int q = 0; q < 4; ++q)
-      if (tl[q] >= 0) { ++need; tile_groups[tl[q]].push_back((int32_t)g); }
+    auto& rows = grows_of[g];
+    sort_rows(rows);
     auto slot_of = [&](int32_t tile) { for (int q = 0; q < 4; ++q) if (tl[q] == tile) return q; return -1; };
-    std::vector<Src4> p_rowvsrc, p_esrc;
-    std::vector<uint32_t> p_emeta;
+    std::vector<GroupRow> p_rows(rows.size());
+    std::memset(&groups[g], 0, sizeof(GroupInst));
     groups[g].row0 = (int32_t)grow_base.size();
     for (size_t k = 0; k < rows.size(); ++k) {
       const int32_t d = rows[k];
-      const int len = rp[d + 1] - rp[d];
-      if (len > 255) return nullptr;
       grow_base.push_back(rp[d]);
       grow_dof.push_back(d);
-      if (dptr[d + 1] - dptr[d] > 4) return nullptr;
-      Src4 vs{{TILE_NONE, TILE_NONE, TILE_NONE, TILE_NONE}};
+      GroupRow R{(uint16_t)dof_type[d], {0, 0, 0, 0}, {0, 0, 0}};
       for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {
         const int32_t c = dsrc[q] / M;
-        const int b = bidx_tile[(int64_t)cell_tile[c] * TILE_CELLS + cell_lc[c]];
-        vs.s[q - dptr[d]] = (uint16_t)((slot_of(cell_tile[c]) << 11) | (b << 4) | (dsrc[q] % M));
+        R.cell[q - dptr[d]] = (uint16_t)((slot_of(cell_tile[c]) << 7) | cell_lc[c]);
       }
-      p_rowvsrc.push_back(vs);
-      const size_t e0 = p_esrc.size();
-      p_esrc.resize(e0 + len, Src4{{TILE_NONE, TILE_NONE, TILE_NONE, TILE_NONE}});
-      for (int j = 0; j < len; ++j) p_emeta.push_back((uint32_t)((k << 8) | (uint32_t)j));
-      for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {
-        const int32_t c = dsrc[q] / M, i = dsrc[q] % M;
-        const int b = bidx_tile[(int64_t)cell_tile[c] * TILE_CELLS + cell_lc[c]];
-        const int ts = slot_of(cell_tile[c]);
-        for (int j2 = 0; j2 < M; ++j2) {
-          const int32_t col = dofs[(int64_t)c * M + j2];
-          if (col < 0) continue;
-          const int pos = col_pos(d, col);
-          if (pos < 0) return nullptr;
-          Src4& e = p_esrc[e0 + pos];
-          int w = 0;
-          while (w < 4 && e.s[w] != TILE_NONE) ++w;
-          if (w == 4) return nullptr;
-          e.s[w] = (uint16_t)((ts << 13) | (b << 6) | plane_of(M, i, j2));
-        }
-      }
+      p_rows[k] = R;
+      plan->group_slots += rp[d + 1] - rp[d];
     }
     Blob key2;
-    key2.put(p_rowvsrc); key2.put(p_emeta); key2.put(p_esrc);
+    key2.put(p_rows);
     bool is_new = false;
     const int32_t id = gstore.find_or_add(std::move(key2), (int32_t)gpats.size(), &is_new);
     if (is_new) {
-      gpats.push_back(GroupPat{(int32_t)g_rowvsrc.size(), (int32_t)p_rowvsrc.size(), (int32_t)g_emeta.size(), (int32_t)p_emeta.size()});
-      g_rowvsrc.insert(g_rowvsrc.end(), p_rowvsrc.begin(), p_rowvsrc.end());
-      g_emeta.insert(g_emeta.end(), p_emeta.begin(), p_emeta.end());
-      g_esrc.insert(g_esrc.end(), p_esrc.begin(), p_esrc.end());
+      TilePat P;
+      P.row0 = (int32_t)grows_all.size();
+      if (!make_classes(rows, P)) return nullptr;
+      gpats.push_back(P);
+      grows_all.insert(grows_all.end(), p_rows.begin(), p_rows.end());
     }
-    groups[g].pat = id; groups[g].need = need; groups[g].pad = 0;
+    groups[g].pat = id;
     for (int q = 0; q < 4; ++q) {
       groups[g].eoff[q] = tl[q] >= 0 ? tile_eoff[tl[q]] : 0;
       groups[g].voff[q] = tl[q] >= 0 ? tile_voff[tl[q]] : 0;
-      groups[g].nb[q] = tl[q] >= 0 ? nborder[tl[q]] : 0;
     }
-    plan->group_slots += (int64_t)p_emeta.size();
-  }
-  std::vector<int32_t> tg_ptr(n_tiles + 1, 0), tg_idx;
-  for (int64_t t = 0; t < n_tiles; ++t) {
-    tg_idx.insert(tg_idx.end(), tile_groups[t].begin(), tile_groups[t].end());
-    tg_ptr[t + 1] = (int32_t)tg_idx.size();
+    plan->max_group_rows = std::max(plan->max_group_rows, (int)rows.size());
   }
 
   // ---- supertiles: tiles that share their geometry (geometry classes) are served by one CTA --------------------------------------
   std::vector<int32_t> inst_ptr{0}, inst_tile;
   if (classes) {
     std::map<std::vector<int32_t>, std::vector<int32_t>> by_geom;
-    std::vector<const std::vector<int32_t>*> first_seen;
     for (int64_t t = 0; t < n_tiles; ++t) {
       std::vector<int32_t> k(TILE_CELLS);
       for (int lc = 0; lc < TILE_CELLS; ++lc) {
@@ -350,33 +412,41 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
   }
   plan->n_super = (int64_t)inst_ptr.size() - 1;
   plan->n_pat = (int64_t)pats.size(); plan->n_groups = ng; plan->n_gpat = (int64_t)gpats.size();
+  plan->n_types = (int64_t)types.size();
+
+  // ---- per (tile, local cell) copies of what a thread reads first ----------------------------------------------------------------------
+  std::vector<int32_t> tc_ix(n_tiles * TILE_CELLS, 0), tc_iy(n_tiles * TILE_CELLS, 0), tc_dofs((size_t)n_tiles * M * TILE_CELLS, -1);
+  std::vector<double> tc_hx(n_tiles * TILE_CELLS, 1.0), tc_hy(n_tiles * TILE_CELLS, 1.0);
+  for (int64_t t = 0; t < n_tiles; ++t)
+    for (int lc = 0; lc < TILE_CELLS; ++lc) {
+      const int32_t c = tile_cells[t * TILE_CELLS + lc];
+      if (c < 0) continue;
+      const double* q = &m->chart_coords[(size_t)c * 8];
+      tc_ix[t * TILE_CELLS + lc] = m->h_ix[c]; tc_iy[t * TILE_CELLS + lc] = m->h_iy[c];
+      tc_hx[t * TILE_CELLS + lc] = q[2] - q[0]; tc_hy[t * TILE_CELLS + lc] = q[5] - q[1];
+      for (int i = 0; i < M; ++i) tc_dofs[((size_t)t * M + l2x[i]) * TILE_CELLS + lc] = dofs[(int64_t)c * M + i];
+    }
+  plan->tc_ix.upload(tc_ix, st); plan->tc_iy.upload(tc_iy, st); plan->tc_dofs.upload(tc_dofs, st);
+  plan->tc_hx.upload(tc_hx, st); plan->tc_hy.upload(tc_hy, st);
 
   // ---- upload ------------------------------------------------------------------------------------------------------------------------
-  auto up4 = [&](DevBuf<ushort4>& d, const std::vector<Src4>& h) {
-    static_assert(sizeof(Src4) == sizeof(ushort4), "source quad layout");
-    d.upload((const ushort4*)h.data(), h.size(), st);
-  };
   plan->inst_ptr.upload(inst_ptr, st); plan->inst_tile.upload(inst_tile, st);
   plan->tile_cells.upload(tile_cells, st); plan->tile_pat.upload(tile_pat, st);
   plan->tile_eoff.upload(tile_eoff, st); plan->tile_voff.upload(tile_voff, st);
-  plan->pats.upload(pats, st); up4(plan->rowvsrc, rowvsrc);
   plan->tile_row0.upload(tile_row0, st); plan->trow_base.upload(trow_base, st); plan->trow_dof.upload(trow_dof, st);
   plan->grow_base.upload(grow_base, st); plan->grow_dof.upload(grow_dof, st);
-  plan->emeta.upload(emeta, st); up4(plan->esrc, esrc); plan->bidx.upload(bidx, st);
-  plan->tg_ptr.upload(tg_ptr, st); plan->tg_idx.upload(tg_idx, st);
-  plan->groups.upload(groups, st); plan->gpats.upload(gpats, st);
-  up4(plan->g_rowvsrc, g_rowvsrc);
-  plan->g_emeta.upload(g_emeta, st); up4(plan->g_esrc, g_esrc);
-  plan->gcount.alloc((size_t)std::max<int64_t>(ng, 1));
-  GG_CUDA(cudaMemsetAsync(plan->gcount.p, 0, plan->gcount.n * sizeof(int32_t), st));
+  plan->pats.upload(pats, st); plan->pair_idx.upload(pair_idx, st); plan->vec_idx.upload(vec_idx, st); plan->bidx.upload(bidx, st);
+  plan->types.upload(types, st);
+  plan->groups.upload(groups, st); plan->gpats.upload(gpats, st); plan->grows.upload(grows_all, st);
   GG_CUDA(cudaStreamSynchronize(st));
-  plan->pattern_bytes = (int64_t)(rowvsrc.size() * 8 + emeta.size() * 4 + esrc.size() * 8 + bidx.size() +
-                                  g_rowvsrc.size() * 8 + g_emeta.size() * 4 + g_esrc.size() * 8);
+  plan->pattern_bytes = (int64_t)((pair_idx.size() + vec_idx.size()) * sizeof(uint32_t) + grows_all.size() * sizeof(GroupRow) + bidx.size() +
+                                  types.size() * sizeof(RowType) + pats.size() * sizeof(TilePat) + gpats.size() * sizeof(TilePat));
   if (getenv("GG_TILE_STATS"))
-    fprintf(stderr, "[gg_tile] %lld tiles, %lld supertiles, %lld tile patterns, %lld groups (%lld patterns); slots: %lld complete + %lld in "
-                    "groups of %lld; border cells %lld of %lld; patterns %.2f MB\n", (long long)n_tiles, (long long)plan->n_super,
-            (long long)plan->n_pat, (long long)ng, (long long)plan->n_gpat, (long long)plan->complete_slots, (long long)plan->group_slots,
-            (long long)A->nnz, (long long)plan->border_cells, (long long)nc, plan->pattern_bytes / 1e6);
+    fprintf(stderr, "[gg_tile] %lld tiles, %lld supertiles, %lld tile patterns, %lld groups (%lld patterns), %lld row types; slots: %lld "
+                    "complete + %lld in groups of %lld; border cells %lld of %lld; types + patterns %.3f MB, row bases %.2f MB\n",
+            (long long)n_tiles, (long long)plan->n_super, (long long)plan->n_pat, (long long)ng, (long long)plan->n_gpat,
+            (long long)plan->n_types, (long long)plan->complete_slots, (long long)plan->group_slots, (long long)A->nnz,
+            (long long)plan->border_cells, (long long)nc, plan->pattern_bytes / 1e6, (trow_base.size() + grow_base.size()) * 8 / 1e6);
   return plan;
 }
 

@@ -3,16 +3,22 @@
 // the element-matrix round trip through HBM.
 //
 // One CTA owns a TILE of up to 128 cells (a TX x TY block of one panel, found from the cells' chart intervals, so it works for
-// any cell order and for caller-supplied meshes).  CSR rows whose cells all lie in one tile are COMPLETE: the CTA sums them
-// from the element matrices it holds in shared memory and writes their values once.  The other rows are grouped by the set
-// of tiles around them (two tiles across a tile edge, up to four around a tile corner): every tile stores the element matrices
-// of its border cells to a small global buffer and bumps the counters of its groups; the CTA that brings a counter to its
-// final value sums the group's rows (reading the border data, which is still in L2).  Every slot is summed in ascending cell
-// order whoever does it: deterministic, atomic-free values, bit for bit those of the two-kernel path (k_gather_chunks).
+// any cell order and for caller-supplied meshes).  CSR rows whose cells all lie in one tile are COMPLETE: their values are
+// accumulated in shared memory straight from the registers that hold the element matrices and written once (k_lb_tile).
+// The accumulation is conflict-free without atomics: the cells of a tile are 4-coloured by the parity of their chart
+// intervals (cells of one colour share no DOF), warp w holds the cells of colour w, and the four warps add their
+// contributions one after the other -- every slot is summed in colour order, deterministically.  The other rows -- the DOFs
+// on tile edges and corners, about a tenth of the values -- are grouped by the set of tiles around them: every tile stores
+// the element matrices of its border cells to a (sparse) global buffer and a second, small kernel (k_lb_tile_groups) sums
+// these rows from it, in ascending cell order, while the data is still in L2.
 //
-// What a CTA needs to know about its rows (which local cell / entry feeds which position of which row) is the same for all
-// tiles with the same local connectivity, so these PATTERNS are stored once per distinct tile (interior tiles of a panel
-// share one) and stay L2-resident; nothing in them depends on how the DOFs are numbered, only the row pointers do.
+// What the kernels need to know about a row -- which cells around it feed which position -- is a ROW TYPE: the list of its
+// columns in CSR order, each with up to four (cell slot, packed element entry) sources.  On a structured panel a handful of
+// row types covers every row (vertex, the two edge orientations, cell interior, and their variants along panel borders), so
+// the table stays in L1; the group kernel works from them.  A tile PATTERN holds, for every (local cell, local DOF pair), the
+// shared-memory slot its element-matrix entry is added to; tiles with the same local connectivity share one pattern (the
+// interior tiles of a panel all do), so the patterns stay in L1 / L2.  Nothing in the types or patterns depends on how the DOFs
+// are numbered beyond the order of the columns inside a row; the numbering enters through the per-tile row bases only.
 #pragma once
 #include <memory>
 #include <stdint.h>
@@ -21,50 +27,78 @@
 namespace gg {
 
 constexpr int TILE_CELLS = 128;     // cells (threads) per tile
-constexpr int TILE_ROWCAP = 1024;   // rows per pattern the kernel can stage (a 16 x 8 Q2 tile has 465 complete rows)
-constexpr uint16_t TILE_NONE = 0xFFFFu;
+constexpr int TILE_ROWCAP = 640;    // rows of a tile the kernel stages in shared memory (a 16 x 8 Q2 tile has 465 complete rows)
+constexpr int TILE_MAXLEN = 32;     // longest CSR row a row type can describe (Q2: 25)
+constexpr int TILE_MAXCLS = 8;      // row-length classes per pattern
 
-struct TilePat { int32_t row0, nrows, ent0, nent, nborder, pad; };
-struct GroupPat { int32_t row0, nrows, ent0, nent; };
-// a group of rows shared by up to four tiles: pattern, arrivals needed, first row in grow_base / grow_dof, and per tile slot the
-// offsets of that tile's border buffers and its border-cell count
-struct GroupInst { int32_t pat, need, row0, pad; int32_t eoff[4], voff[4], nb[4]; };
+// one row type: len columns; column j sums the sources src[j][0..3] = (cell slot << 6) | packed plane, 0xFF = none, in that
+// order (ascending cell); vsrc = element-vector sources (cell slot << 4) | local dof
+struct RowType {
+  uint8_t src[TILE_MAXLEN][4];
+  uint8_t vsrc[4];
+  int32_t len;
+};
+// one row of a group pattern: its type and the cells in the type's four slots, (tile slot << 7) | local cell
+struct __align__(16) GroupRow { uint16_t type; uint16_t cell[4]; uint16_t pad[3]; };
+// rows of a pattern are sorted by (row length, DOF id); a class is a run of equal length
+struct RowClass { int32_t len, first, count, slot0; };   // slot0: first shared-memory slot of the class (tile patterns)
+struct TilePat { int32_t row0, nrows, ncls, nslots; RowClass cls[TILE_MAXCLS]; };
+struct GroupInst { int32_t pat, row0; int32_t eoff[4], voff[4]; int32_t pad[2]; };
 
-// device view handed to the kernel
+// Local geometry of Q_p on a quadrilateral (lexicographic DOF I = i1 + (p+1) i2): which element entries can have more than one
+// contributing cell.  (I, J) can only be shared if both DOFs lie on one edge of the cell; only a corner's diagonal entry
+// (I == J, a vertex) can have more than two cells.
+__host__ __device__ constexpr bool tile_on_edge(int p, int I, int e) {   // e: 0 left, 1 right, 2 bottom, 3 top
+  return e == 0 ? I % (p + 1) == 0 : e == 1 ? I % (p + 1) == p : e == 2 ? I / (p + 1) == 0 : I / (p + 1) == p;
+}
+__host__ __device__ constexpr bool tile_shared_pair(int p, int I, int J) {
+  return (tile_on_edge(p, I, 0) && tile_on_edge(p, J, 0)) || (tile_on_edge(p, I, 1) && tile_on_edge(p, J, 1)) ||
+         (tile_on_edge(p, I, 2) && tile_on_edge(p, J, 2)) || (tile_on_edge(p, I, 3) && tile_on_edge(p, J, 3));
+}
+__host__ __device__ constexpr bool tile_shared_dof(int p, int I) { return tile_shared_pair(p, I, I); }
+__host__ __device__ constexpr bool tile_corner_dof(int p, int I) {
+  return (I % (p + 1) == 0 || I % (p + 1) == p) && (I / (p + 1) == 0 || I / (p + 1) == p);
+}
+
+// device view handed to the kernels
 struct TileDev {
-  int32_t n_super;
+  int32_t n_super, n_groups;
   const int32_t *inst_ptr, *inst_tile;     // supertile -> tiles that share its geometry (1 each without geometry classes)
   const int32_t* tile_cells;               // [n_tiles][TILE_CELLS] cell ids, ascending, -1 padded
   const int32_t *tile_pat, *tile_eoff, *tile_voff;
-  const TilePat* pats;
   const int32_t *tile_row0, *trow_base, *trow_dof;   // per tile: first CSR slot and DOF id of its complete rows (numbering-dependent)
-  const ushort4* rowvsrc;                  // complete row k of a pattern: element-vector sources (local dof << 7) | local cell, TILE_NONE padded
-  const uint32_t* emeta;                   // entry: (row index in the pattern << 8) | position in the row
-  const ushort4* esrc;                     // its sources: plane * TILE_CELLS + local cell, ascending cell, TILE_NONE padded
-  const uint8_t* bidx;                     // [n_pat][TILE_CELLS] border index of a local cell (0xFF: interior cell)
-  const int32_t *tg_ptr, *tg_idx;          // tile -> groups it contributes to
+  const TilePat* pats;
+  // [n_pat][PW][TILE_CELLS], PW = (M*M+1)/2: shared-memory slots of the element entries (I, J) (lexicographic local DOFs, row-major)
+  // of a local cell, two 16-bit slots per word; [n_pat][VW][TILE_CELLS], VW = (M+1)/2: rows of its local DOFs.  Slots / rows past
+  // the pattern's own counts are dummies (rows that are not complete in this tile, Dirichlet DOFs)
+  const uint32_t *pair_idx, *vec_idx;
+  // per (tile, local cell), in tile order: chart-interval ids and extents of the cell, and its DOF ids [tile][I][local cell] in
+  // lexicographic local order -- what a thread reads first, with one level of indirection less than through the cell id
+  const int32_t *tc_ix, *tc_iy, *tc_dofs;
+  const double *tc_hx, *tc_hy;
+  const uint8_t* bidx;                     // [n_pat][TILE_CELLS] != 0xFF: the local cell is a border cell (its element matrix goes to ebuf_b)
+  const RowType* types;
   const GroupInst* groups;
-  int32_t* gcount;                         // arrivals per group (zero between launches)
-  const GroupPat* gpats;
+  const TilePat* gpats;
+  const GroupRow* grows;
   const int32_t *grow_base, *grow_dof;     // per group: first CSR slot and DOF id of its rows
-  const ushort4* g_rowvsrc;                // (tile slot << 11) | (border index << 4) | local dof
-  const uint32_t* g_emeta;
-  const ushort4* g_esrc;                   // (tile slot << 13) | (border index << 6) | plane
-  double *ebuf_b, *vbuf_b;                 // border element matrices [tile][plane][border cell] / vectors [tile][dof][border cell]
+  double *ebuf_b, *vbuf_b;                 // border element matrices [tile][plane][local cell] / vectors [tile][dof][local cell] (sparse)
 };
 
 struct TilePlan {
   bool classes = false;
   int M = 0, NP = 0;
-  int64_t n_tiles = 0, n_super = 0, n_pat = 0, n_groups = 0, n_gpat = 0;
-  int max_rows = 0;
-  DevBuf<int32_t> inst_ptr, inst_tile, tile_cells, tile_pat, tile_eoff, tile_voff, tg_ptr, tg_idx, gcount;
+  int64_t n_tiles = 0, n_super = 0, n_pat = 0, n_groups = 0, n_gpat = 0, n_types = 0;
+  int max_rows = 0, max_group_rows = 0, max_slots = 0;
+  DevBuf<int32_t> inst_ptr, inst_tile, tile_cells, tile_pat, tile_eoff, tile_voff;
   DevBuf<int32_t> tile_row0, trow_base, trow_dof, grow_base, grow_dof;
-  DevBuf<TilePat> pats;
-  DevBuf<GroupPat> gpats;
+  DevBuf<TilePat> pats, gpats;
+  DevBuf<uint32_t> pair_idx, vec_idx;
+  DevBuf<int32_t> tc_ix, tc_iy, tc_dofs;
+  DevBuf<double> tc_hx, tc_hy;
+  DevBuf<GroupRow> grows;
+  DevBuf<RowType> types;
   DevBuf<GroupInst> groups;
-  DevBuf<ushort4> rowvsrc, esrc, g_rowvsrc, g_esrc;
-  DevBuf<uint32_t> emeta, g_emeta;
   DevBuf<uint8_t> bidx;
   DevBuf<double> ebuf_b, vbuf_b;
   // statistics of the build (for DESIGN.md / bench)
