@@ -460,9 +460,9 @@ static void launch_lb_tile(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, 
   if (extrinsic) launch_lb_tile_k<NB, NQ, true, false>(ctx, plan, T, a, g);     // geometry classes are an intrinsic-form feature
   else if (plan.classes) launch_lb_tile_k<NB, NQ, false, true>(ctx, plan, T, a, g);
   else launch_lb_tile_k<NB, NQ, false, false>(ctx, plan, T, a, g);
-  if (plan.n_groups) {
+  if (plan.group_slots) {
     ProfScope ps(ctx, "k_lb_tile_groups");
-    k_lb_tile_groups<M><<<(unsigned)plan.n_groups, TILE_CELLS, 0, ctx->stream>>>(T, a);
+    k_lb_tile_groups<M><<<nblk(plan.group_slots, 2 * 256), 256, 0, ctx->stream>>>(T, a, plan.gcls);
     ctx->launches++;
   }
   GG_CUDA(cudaGetLastError());
@@ -475,6 +475,11 @@ static bool run_lb_tile(gg_mesh* m, int order, int nq, bool extrinsic, const int
   gg_csr* A = pipe->A;
   if (!enabled || A->test != A->trial) return false;
   const int mode = (ctx->geometry_classes && !extrinsic) ? 1 : 0;
+  // geometry classes: a CTA would serve the six congruent tiles of a class from one set of element matrices, but 512 long CTAs
+  // fill the 444 CTA slots of a B200 badly (measured 0.268 ms against 0.172 ms of the class path through k_gather_chunks), so
+  // that combination stays opt-in
+  static const bool tile_classes = getenv("GG_LB_TILES_CLASSES") && getenv("GG_LB_TILES_CLASSES")[0] == '1';
+  if (mode == 1 && !tile_classes) return false;
   if (!A->tiles_tried[mode]) {
     A->tiles_tried[mode] = true;
     A->tiles[mode] = build_tile_plan(A, mode == 1);

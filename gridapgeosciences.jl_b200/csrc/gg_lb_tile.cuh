@@ -82,6 +82,8 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
   };
   prefetch_rows(tile0);
   gather_state(tile0);
+  const int32_t patid0 = T.tile_pat[tile0];
+  const uint8_t bidx0 = T.bidx[(int64_t)patid0 * TILE_CELLS + lc];
 
   // ---- element matrix of the thread's cell (the instances of a supertile have the same chart boxes) ----
   double acc[NP];
@@ -159,9 +161,9 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
 
   for (int inst = i0; inst < i1; ++inst) {
     const int32_t tile = MULTI ? T.inst_tile[inst] : tile0;
-    const int32_t patid = T.tile_pat[tile];
-    const int32_t c = T.tile_cells[(int64_t)tile * TILE_CELLS + lc];
-    const bool border = T.bidx[(int64_t)patid * TILE_CELLS + lc] != 0xFF && c >= 0;
+    const int32_t patid = (!MULTI || inst == i0) ? patid0 : T.tile_pat[tile];
+    const int32_t c = (!MULTI || inst == i0) ? crep : T.tile_cells[(int64_t)tile * TILE_CELLS + lc];
+    const bool border = ((!MULTI || inst == i0) ? bidx0 : T.bidx[(int64_t)patid * TILE_CELLS + lc]) != 0xFF && c >= 0;
     const TilePat* __restrict__ P = T.pats + patid;
     const int nslots = P->nslots, nrows = P->nrows;
     if (MULTI && inst > i0) {
@@ -187,15 +189,16 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
           if (J != I) re[J] = fma(acc[tile_packed<M>(I, J)], ue[I], re[J]);
         }
       if (border) {
-        double* vb = T.vbuf_b + T.tile_voff[tile];
+        double* vb = T.vbuf_b + ((int64_t)tile * TILE_CELLS + lc) * (M + (M & 1));
 #pragma unroll
-        for (int I = 0; I < M; ++I) vb[c_lex2loc[I] * TILE_CELLS + lc] = re[I];
+        for (int I = 0; I < M; ++I) vb[c_lex2loc[I]] = re[I];
       }
     }
     if (border) {
-      double* eb = T.ebuf_b + T.tile_eoff[tile];
+      // cell-major: the NP entries of a border cell are contiguous, so the lanes that sum one row share their sectors
+      double* eb = T.ebuf_b + ((int64_t)tile * TILE_CELLS + lc) * (NP + (NP & 1));
 #pragma unroll
-      for (int p = 0; p < NP; ++p) eb[c_plane[p] * TILE_CELLS + lc] = acc[p];
+      for (int p = 0; p < NP; ++p) eb[c_plane[p]] = acc[p];
     }
     // ---- conflict-free accumulation in rounds.  Every (cell, entry) knows the shared-memory slot it feeds and its ROUND: its
     //      rank among the cells that feed the slot, in ascending cell order.  Round 0 stores, rounds 1..3 add, with a barrier in
@@ -283,64 +286,66 @@ k_lb_tile(TileDev T, TileArgs a, CellGeo g) {
   }
 }
 
-// Rows shared by several tiles (tile edges and corners): one CTA per group sums them from the border buffers the tile kernel
-// has just written (mostly L2 hits), in the same ascending cell order.
+// Rows shared by several tiles (tile edges and corners): one thread per CSR value, summed from the border buffers the tile kernel
+// has just written (mostly L2 hits) in ascending cell order.  The rows are sorted by length, so a thread finds its (row, column)
+// by one division inside its length class.
 template <int M>
-__global__ void __launch_bounds__(TILE_CELLS)
-k_lb_tile_groups(TileDev T, TileArgs a) {
-  const GroupInst* __restrict__ G = T.groups + blockIdx.x;
-  const TilePat* __restrict__ P = T.gpats + G->pat;
-  const GroupRow* __restrict__ rows = T.grows + P->row0;
-  const int32_t* __restrict__ base = T.grow_base + G->row0;
-  const int32_t* __restrict__ dofs = T.grow_dof + G->row0;
-  __shared__ int32_t s_eo[4], s_vo[4];
-  const int lc = threadIdx.x, lane = lc & 31, warp = lc >> 5;
-  if (lc < 4) { s_eo[lc] = G->eoff[lc]; s_vo[lc] = G->voff[lc]; }
-  __syncthreads();
-  const int ncls = P->ncls;
-  for (int q = 0; q < ncls; ++q) {
-    const int len = P->cls[q].len, first = P->cls[q].first, count = P->cls[q].count;
-    const int rpw = 32 / len;
-    const int r = lane / len, jj = lane - r * len;
-    if (r >= rpw) continue;
-    const int last = first + count;
-#pragma unroll 2
-    for (int k = first + warp * rpw + r; k < last; k += 4 * rpw) {
-      const GroupRow R = rows[k];
-      const uint32_t s4 = __ldg((const uint32_t*)T.types[R.type].src[jj]);
-      double v[4];
+__global__ void __launch_bounds__(256)
+k_lb_tile_groups(TileDev T, TileArgs a, GroupClasses G) {
+  constexpr int NP = M * (M + 1) / 2, U = 2;     // U values per thread, their load chains in flight together
+  const uint32_t n_ent = (uint32_t)G.ent0[G.ncls];
+  const uint32_t e0 = blockIdx.x * (blockDim.x * U) + threadIdx.x;
+  const GroupRow* R[U];
+  int jj[U];
+  uint32_t s4[U];
+  double v[U][4];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t code = (s4 >> (8 * w)) & 255u;
-        v[w] = 0.0;
-        if (code != 255u) {
-          const uint32_t cc = R.cell[code >> 6];
-          v[w] = __ldcg(T.ebuf_b + s_eo[cc >> 7] + (int)(code & 63u) * TILE_CELLS + (cc & 127u));
-        }
-      }
-      const double t = a.scale * (((v[0] + v[1]) + v[2]) + v[3]);
-      double* dst = a.vals + base[k] + jj;
-      *dst = a.add ? *dst + t : t;
+  for (int u = 0; u < U; ++u) {
+    const uint32_t e = e0 + u * blockDim.x;
+    R[u] = nullptr;
+    if (e < n_ent) {
+      // length class of the entry: compile-time indexed compares keep the class table in the parameter bank
+      uint32_t len = (uint32_t)G.cls[0].len, first = (uint32_t)G.cls[0].first, start = 0;
+#pragma unroll
+      for (int q = 1; q < TILE_MAXCLS; ++q)
+        if (q < G.ncls && e >= (uint32_t)G.ent0[q]) { len = (uint32_t)G.cls[q].len; first = (uint32_t)G.cls[q].first; start = (uint32_t)G.ent0[q]; }
+      const uint32_t le = e - start, row = le / len;
+      R[u] = T.grows + first + row;
+      jj[u] = (int)(le - row * len);
     }
   }
-  if (a.vec_out) {
-    const int nrows = P->nrows;
-    for (int k = lc; k < nrows; k += TILE_CELLS) {
-      const GroupRow R = rows[k];
-      const uint32_t s4 = __ldg((const uint32_t*)T.types[R.type].vsrc);
-      double v[4];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (R[u]) s4[u] = __ldg((const uint32_t*)T.types[__ldg(&R[u]->type)].src[jj[u]]);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      v[u][w] = 0.0;
+      if (R[u]) {
+        const uint32_t code = (s4[u] >> (8 * w)) & 255u;
+        if (code != 255u)    // border buffer: [tile * 128 + local cell][plane]
+          v[u][w] = __ldcg(T.ebuf_b + (int64_t)__ldg(&R[u]->col[code >> 6]) * (NP + (NP & 1)) + (int)(code & 63u));
+      }
+    }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!R[u]) continue;
+    const double t = a.scale * (((v[u][0] + v[u][1]) + v[u][2]) + v[u][3]);
+    double* dst = a.vals + __ldg(&R[u]->base) + jj[u];
+    *dst = a.add ? *dst + t : t;
+    if (jj[u] == 0 && a.vec_out) {
+      const uint32_t s4v = __ldg((const uint32_t*)T.types[__ldg(&R[u]->type)].vsrc);
+      double r[4];
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        const uint32_t code = (s4 >> (8 * w)) & 255u;
-        v[w] = 0.0;
-        if (code != 255u) {
-          const uint32_t cc = R.cell[(code >> 4) & 3u];
-          v[w] = __ldcg(T.vbuf_b + s_vo[cc >> 7] + (int)(code & 15u) * TILE_CELLS + (cc & 127u));
-        }
+        const uint32_t code = (s4v >> (8 * w)) & 255u;
+        r[w] = 0.0;
+        if (code != 255u) r[w] = __ldcg(T.vbuf_b + (int64_t)__ldg(&R[u]->col[(code >> 4) & 3u]) * (M + (M & 1)) + (int)(code & 15u));
       }
-      const double t = a.scale * (((v[0] + v[1]) + v[2]) + v[3]);
-      const int32_t d = dofs[k];
-      a.vec_out[d] = a.add ? a.vec_out[d] + t : t;
+      const double tv = a.scale * (((r[0] + r[1]) + r[2]) + r[3]);
+      const int32_t d = __ldg(&R[u]->dof);
+      a.vec_out[d] = a.add ? a.vec_out[d] + tv : tv;
     }
   }
 }

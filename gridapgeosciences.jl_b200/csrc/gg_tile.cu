@@ -52,13 +52,13 @@ inline int plane_of(int M, int i, int j) {
 
 TileDev TilePlan::dev() const {
   TileDev T;
-  T.n_super = (int32_t)n_super; T.n_groups = (int32_t)n_groups;
+  T.n_super = (int32_t)n_super; T.pad0 = 0;
   T.inst_ptr = inst_ptr.p; T.inst_tile = inst_tile.p;
   T.tile_cells = tile_cells.p; T.tile_pat = tile_pat.p; T.tile_eoff = tile_eoff.p; T.tile_voff = tile_voff.p;
   T.tile_row0 = tile_row0.p; T.trow_base = trow_base.p; T.trow_dof = trow_dof.p;
   T.pats = pats.p; T.pair_idx = pair_idx.p; T.vec_idx = vec_idx.p;
   T.tc_ix = tc_ix.p; T.tc_iy = tc_iy.p; T.tc_dofs = tc_dofs.p; T.tc_hx = tc_hx.p; T.tc_hy = tc_hy.p; T.bidx = bidx.p; T.types = types.p;
-  T.groups = groups.p; T.gpats = gpats.p; T.grows = grows.p; T.grow_base = grow_base.p; T.grow_dof = grow_dof.p;
+  T.grows = grows.p; T.n_grows = n_grows;
   T.ebuf_b = ebuf_b.p; T.vbuf_b = vbuf_b.p;
   return T;
 }
@@ -192,11 +192,11 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
       if (border) { bidx_tile[t * TILE_CELLS + lc] = 1; plan->border_cells++; }
     }
   {
-    // [plane][local cell] per tile; only border cells are ever written / read
+    // [tile * TILE_CELLS + local cell][plane] (rows padded to an even length); only border cells are ever written / read
     int64_t eo = 0, vo = 0;
     for (int64_t t = 0; t < n_tiles; ++t) {
       tile_eoff[t] = (int32_t)eo; tile_voff[t] = (int32_t)vo;
-      eo += (int64_t)TILE_CELLS * NP; vo += (int64_t)TILE_CELLS * M;
+      eo += (int64_t)TILE_CELLS * (NP + (NP & 1)); vo += (int64_t)TILE_CELLS * (M + (M & 1));
     }
     if (eo >= (int64_t)INT32_MAX) return nullptr;
     plan->ebuf_b.alloc((size_t)std::max<int64_t>(eo, 1));
@@ -327,65 +327,36 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
     plan->max_slots = std::max(plan->max_slots, nslots);
   }
 
-  // ---- incomplete rows: groups by the set of tiles around the row ------------------------------------------------------------
-  std::map<std::array<int32_t, 4>, int32_t> gid;
-  std::vector<std::array<int32_t, 4>> gtiles;
-  std::vector<std::vector<int32_t>> grows_of;
-  for (int64_t d = 0; d < nd; ++d) {
-    if (dnt[d] <= 1) continue;
-    std::array<int32_t, 4> k{dtiles[d * 4], dtiles[d * 4 + 1], dtiles[d * 4 + 2], dtiles[d * 4 + 3]};
-    auto it = gid.find(k);
-    if (it == gid.end()) {
-      it = gid.emplace(k, (int32_t)gtiles.size()).first;
-      gtiles.push_back(k);
-      grows_of.emplace_back();
-    }
-    grows_of[it->second].push_back((int32_t)d);
+  // ---- incomplete rows (DOFs on tile edges and corners): one record per row, sorted by (length, DOF id) ------------------------
+  std::vector<int32_t> inc;
+  for (int64_t d = 0; d < nd; ++d)
+    if (dnt[d] > 1) inc.push_back((int32_t)d);
+  sort_rows(inc);
+  std::vector<GroupRow> grows_all(inc.size());
+  {
+    TilePat P;
+    if (!make_classes(inc, P)) return nullptr;
+    GroupClasses& G = plan->gcls;
+    std::memset(&G, 0, sizeof(G));
+    G.ncls = P.ncls;
+    int64_t e = 0;
+    for (int q = 0; q < P.ncls; ++q) { G.cls[q] = P.cls[q]; G.ent0[q] = e; e += (int64_t)P.cls[q].len * P.cls[q].count; }
+    for (int q = P.ncls; q <= TILE_MAXCLS; ++q) G.ent0[q] = e;
+    plan->group_slots = e;
+    if (e >= (int64_t)INT32_MAX) return nullptr;
   }
-  const int64_t ng = (int64_t)gtiles.size();
-  std::vector<TilePat> gpats;
-  std::vector<GroupInst> groups(ng);
-  std::vector<GroupRow> grows_all;
-  std::vector<int32_t> grow_base, grow_dof;
-  PatStore gstore;
-  for (int64_t g = 0; g < ng; ++g) {
-    const auto& tl = gtiles[g];
-    auto& rows = grows_of[g];
-    sort_rows(rows);
-    auto slot_of = [&](int32_t tile) { for (int q = 0; q < 4; ++q) if (tl[q] == tile) return q; return -1; };
-    std::vector<GroupRow> p_rows(rows.size());
-    std::memset(&groups[g], 0, sizeof(GroupInst));
-    groups[g].row0 = (int32_t)grow_base.size();
-    for (size_t k = 0; k < rows.size(); ++k) {
-      const int32_t d = rows[k];
-      grow_base.push_back(rp[d]);
-      grow_dof.push_back(d);
-      GroupRow R{(uint16_t)dof_type[d], {0, 0, 0, 0}, {0, 0, 0}};
-      for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {
-        const int32_t c = dsrc[q] / M;
-        R.cell[q - dptr[d]] = (uint16_t)((slot_of(cell_tile[c]) << 7) | cell_lc[c]);
-      }
-      p_rows[k] = R;
-      plan->group_slots += rp[d + 1] - rp[d];
+  for (size_t k = 0; k < inc.size(); ++k) {
+    const int32_t d = inc[k];
+    GroupRow R;
+    std::memset(&R, 0, sizeof(R));
+    R.base = rp[d]; R.dof = d; R.type = dof_type[d];
+    for (int32_t q = dptr[d]; q < dptr[d + 1]; ++q) {
+      const int32_t c = dsrc[q] / M;
+      R.col[q - dptr[d]] = cell_tile[c] * TILE_CELLS + cell_lc[c];
     }
-    Blob key2;
-    key2.put(p_rows);
-    bool is_new = false;
-    const int32_t id = gstore.find_or_add(std::move(key2), (int32_t)gpats.size(), &is_new);
-    if (is_new) {
-      TilePat P;
-      P.row0 = (int32_t)grows_all.size();
-      if (!make_classes(rows, P)) return nullptr;
-      gpats.push_back(P);
-      grows_all.insert(grows_all.end(), p_rows.begin(), p_rows.end());
-    }
-    groups[g].pat = id;
-    for (int q = 0; q < 4; ++q) {
-      groups[g].eoff[q] = tl[q] >= 0 ? tile_eoff[tl[q]] : 0;
-      groups[g].voff[q] = tl[q] >= 0 ? tile_voff[tl[q]] : 0;
-    }
-    plan->max_group_rows = std::max(plan->max_group_rows, (int)rows.size());
+    grows_all[k] = R;
   }
+  plan->n_grows = (int64_t)inc.size();
 
   // ---- supertiles: tiles that share their geometry (geometry classes) are served by one CTA --------------------------------------
   std::vector<int32_t> inst_ptr{0}, inst_tile;
@@ -411,7 +382,7 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
     for (int64_t t = 0; t < n_tiles; ++t) { inst_tile.push_back((int32_t)t); inst_ptr.push_back((int32_t)t + 1); }
   }
   plan->n_super = (int64_t)inst_ptr.size() - 1;
-  plan->n_pat = (int64_t)pats.size(); plan->n_groups = ng; plan->n_gpat = (int64_t)gpats.size();
+  plan->n_pat = (int64_t)pats.size();
   plan->n_types = (int64_t)types.size();
 
   // ---- per (tile, local cell) copies of what a thread reads first ----------------------------------------------------------------------
@@ -434,19 +405,18 @@ std::shared_ptr<TilePlan> build_tile_plan(gg_csr* A, bool classes) {
   plan->tile_cells.upload(tile_cells, st); plan->tile_pat.upload(tile_pat, st);
   plan->tile_eoff.upload(tile_eoff, st); plan->tile_voff.upload(tile_voff, st);
   plan->tile_row0.upload(tile_row0, st); plan->trow_base.upload(trow_base, st); plan->trow_dof.upload(trow_dof, st);
-  plan->grow_base.upload(grow_base, st); plan->grow_dof.upload(grow_dof, st);
   plan->pats.upload(pats, st); plan->pair_idx.upload(pair_idx, st); plan->vec_idx.upload(vec_idx, st); plan->bidx.upload(bidx, st);
   plan->types.upload(types, st);
-  plan->groups.upload(groups, st); plan->gpats.upload(gpats, st); plan->grows.upload(grows_all, st);
+  plan->grows.upload(grows_all, st);
   GG_CUDA(cudaStreamSynchronize(st));
   plan->pattern_bytes = (int64_t)((pair_idx.size() + vec_idx.size()) * sizeof(uint32_t) + grows_all.size() * sizeof(GroupRow) + bidx.size() +
-                                  types.size() * sizeof(RowType) + pats.size() * sizeof(TilePat) + gpats.size() * sizeof(TilePat));
+                                  types.size() * sizeof(RowType) + pats.size() * sizeof(TilePat));
   if (getenv("GG_TILE_STATS"))
-    fprintf(stderr, "[gg_tile] %lld tiles, %lld supertiles, %lld tile patterns, %lld groups (%lld patterns), %lld row types; slots: %lld "
-                    "complete + %lld in groups of %lld; border cells %lld of %lld; types + patterns %.3f MB, row bases %.2f MB\n",
-            (long long)n_tiles, (long long)plan->n_super, (long long)plan->n_pat, (long long)ng, (long long)plan->n_gpat,
+    fprintf(stderr, "[gg_tile] %lld tiles, %lld supertiles, %lld tile patterns, %lld rows on tile borders, %lld row types; slots: %lld "
+                    "complete + %lld on borders of %lld; border cells %lld of %lld; types + patterns %.3f MB, row bases %.2f MB\n",
+            (long long)n_tiles, (long long)plan->n_super, (long long)plan->n_pat, (long long)plan->n_grows,
             (long long)plan->n_types, (long long)plan->complete_slots, (long long)plan->group_slots, (long long)A->nnz,
-            (long long)plan->border_cells, (long long)nc, plan->pattern_bytes / 1e6, (trow_base.size() + grow_base.size()) * 8 / 1e6);
+            (long long)plan->border_cells, (long long)nc, plan->pattern_bytes / 1e6, trow_base.size() * 8 / 1e6);
   return plan;
 }
 

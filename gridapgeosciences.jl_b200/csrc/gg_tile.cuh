@@ -38,12 +38,13 @@ struct RowType {
   uint8_t vsrc[4];
   int32_t len;
 };
-// one row of a group pattern: its type and the cells in the type's four slots, (tile slot << 7) | local cell
-struct __align__(16) GroupRow { uint16_t type; uint16_t cell[4]; uint16_t pad[3]; };
+// one row shared by several tiles: first CSR slot, DOF id, row type, and for the type's four cell slots the column of the cell in
+// the border buffers (tile * TILE_CELLS + local cell); the rows are sorted by length, a class is a run of equal length
+struct __align__(8) GroupRow { int32_t base, dof; int32_t type; int32_t col[4]; int32_t pad; };
 // rows of a pattern are sorted by (row length, DOF id); a class is a run of equal length
 struct RowClass { int32_t len, first, count, slot0; };   // slot0: first shared-memory slot of the class (tile patterns)
 struct TilePat { int32_t row0, nrows, ncls, nslots; RowClass cls[TILE_MAXCLS]; };
-struct GroupInst { int32_t pat, row0; int32_t eoff[4], voff[4]; int32_t pad[2]; };
+struct GroupClasses { int32_t ncls, pad; RowClass cls[TILE_MAXCLS]; int64_t ent0[TILE_MAXCLS + 1]; };   // ent0: first entry (thread) of a class
 
 // Local geometry of Q_p on a quadrilateral (lexicographic DOF I = i1 + (p+1) i2): which element entries can have more than one
 // contributing cell.  (I, J) can only be shared if both DOFs lie on one edge of the cell; only a corner's diagonal entry
@@ -62,7 +63,7 @@ __host__ __device__ constexpr bool tile_corner_dof(int p, int I) {
 
 // device view handed to the kernels
 struct TileDev {
-  int32_t n_super, n_groups;
+  int32_t n_super, pad0;
   const int32_t *inst_ptr, *inst_tile;     // supertile -> tiles that share its geometry (1 each without geometry classes)
   const int32_t* tile_cells;               // [n_tiles][TILE_CELLS] cell ids, ascending, -1 padded
   const int32_t *tile_pat, *tile_eoff, *tile_voff;
@@ -78,27 +79,25 @@ struct TileDev {
   const double *tc_hx, *tc_hy;
   const uint8_t* bidx;                     // [n_pat][TILE_CELLS] != 0xFF: the local cell is a border cell (its element matrix goes to ebuf_b)
   const RowType* types;
-  const GroupInst* groups;
-  const TilePat* gpats;
-  const GroupRow* grows;
-  const int32_t *grow_base, *grow_dof;     // per group: first CSR slot and DOF id of its rows
-  double *ebuf_b, *vbuf_b;                 // border element matrices [tile][plane][local cell] / vectors [tile][dof][local cell] (sparse)
+  const GroupRow* grows;                   // rows on tile edges / corners (k_lb_tile_groups)
+  int64_t n_grows;
+  double *ebuf_b, *vbuf_b;                 // border element matrices [tile * 128 + local cell][plane] / vectors [...][dof] (only border cells are touched)
 };
 
 struct TilePlan {
   bool classes = false;
   int M = 0, NP = 0;
-  int64_t n_tiles = 0, n_super = 0, n_pat = 0, n_groups = 0, n_gpat = 0, n_types = 0;
+  int64_t n_tiles = 0, n_super = 0, n_pat = 0, n_grows = 0, n_types = 0;
   int max_rows = 0, max_group_rows = 0, max_slots = 0;
   DevBuf<int32_t> inst_ptr, inst_tile, tile_cells, tile_pat, tile_eoff, tile_voff;
-  DevBuf<int32_t> tile_row0, trow_base, trow_dof, grow_base, grow_dof;
-  DevBuf<TilePat> pats, gpats;
+  DevBuf<int32_t> tile_row0, trow_base, trow_dof;
+  DevBuf<TilePat> pats;
+  GroupClasses gcls;
   DevBuf<uint32_t> pair_idx, vec_idx;
   DevBuf<int32_t> tc_ix, tc_iy, tc_dofs;
   DevBuf<double> tc_hx, tc_hy;
   DevBuf<GroupRow> grows;
   DevBuf<RowType> types;
-  DevBuf<GroupInst> groups;
   DevBuf<uint8_t> bidx;
   DevBuf<double> ebuf_b, vbuf_b;
   // statistics of the build (for DESIGN.md / bench)
