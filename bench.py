@@ -158,8 +158,39 @@ def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10, dist=None, ran
                                    "update_precond": v[2] / max(v[3], 1) / 1e3} for k, v in ph.items()},
            "solver": "statically condensed element-by-element block-Jacobi PCG, rtol 1e-12, warm-started from the previous "
                      "solution" + ("; halo + all-reduce through CUDA-IPC peer memory inside the kernel" if world > 1 else "")}
+    out["roofline"] = swe_roofline(out, model.num_cells, p)
     del st
     return out
+
+
+def swe_roofline(leg, ncell_local, p):
+    """HBM roofline of the dominant kernel of the shallow-water step, the persistent condensed PCG k_pcg_ebe (61 % of the step in
+    profiles/ncu_swe_r01.txt), per iteration of the RT mass solve, from the phase timers of THIS run (%globaltimer inside the
+    kernel) and the algorithmic bytes of one iteration: every operand once."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    mb = 4 * (p + 1)                                  # facet DOFs of a cell (RT_p: p + 1 per facet)
+    rows = ncell_local * 2 * (p + 1)                  # facet DOFs of the slice (2 facets per cell)
+    ncls = min(ncell_local, 65536 if ncell_local >= 65536 else ncell_local)   # geometry classes (256^2: one per (column, row) pair)
+    b_cells = ncls * 8.0 * (mb * (mb + 1) // 2) + ncell_local * (mb * 4 + mb * 8 + mb * 8)   # S once per class; ids, x_f in, S x out
+    b_gather = rows * (2 * (4 + 8) + 3 * 8)           # two element sources per row (index + value); p, Ap, partial dots
+    b_update = rows * (6 * 8 + 3 * (p + 1) * 8)       # x, r, z, p read / written; block-Jacobi rows
+    it = leg["pcg_us_per_iter"]["rt_mass"]
+    t_us = it["cells"] + it["gather_dot"] + it["update_precond"]
+    tot = b_cells + b_gather + b_update
+    return {"kernel": "k_pcg_ebe (condensed RT%d mass solve), one CG iteration" % p, "bound": "hbm", "unit": "GB/s",
+            "achieved": tot / (t_us * 1e-6) / 1e9 if t_us else None, "peak": hbm,
+            "frac": tot / (t_us * 1e-6) / 1e9 / hbm if t_us else None,
+            "algorithmic_bytes_per_iteration": tot, "us_per_iteration": t_us,
+            "phases": {"cells": {"bytes": b_cells, "us": it["cells"], "gbs": b_cells / (it["cells"] * 1e-6) / 1e9 if it["cells"] else None},
+                       "gather_dot": {"bytes": b_gather, "us": it["gather_dot"], "gbs": b_gather / (it["gather_dot"] * 1e-6) / 1e9 if it["gather_dot"] else None},
+                       "update_precond": {"bytes": b_update, "us": it["update_precond"], "gbs": b_update / (it["update_precond"] * 1e-6) / 1e9 if it["update_precond"] else None}},
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "traffic": None,
+            "from_profile": {"file": "profiles/ncu_swe_r01.txt", "dram_bytes_per_iteration": 6.0e8, "note": "ncu, round 1, N=1"}}
 
 
 def adv_leg(gg, ctx, torch, stream, e0, e1, n=128, p=2, steps=200, dist=None, rank=0, world=1):
@@ -334,6 +365,48 @@ def cpu_baseline_run(nthreads, target_seconds=12.0):
     assert np.isfinite(vals).all() and np.isfinite(r).all()
     return ns * reps / dt, threads, f"{reps} pass(es) over {ns} cells of the Q2/degree-18 Laplace-Beltrami residual+Jacobian " \
                                     f"(element matrices, element vectors, CSR/vector scatter), {threads} OpenMP thread(s), {dt:.1f} s"
+
+
+def cpu_rk_baseline():
+    """RK steps/s of the CPU restatement (oracle/c/gg_oracle_rk.c + oracle/c_oracle.py): the reference's structure -- stage
+    residual re-integrated cell by cell, the potential-vorticity block of jac_y re-assembled at every diagnostic solve, mass
+    solves by Jacobi-PCG at rtol 1e-12 (its tutorial's iterative option; LUSolver() is its default) -- serial and on all host
+    cores.  Wave: the full 48x48 configuration.  Shallow water: ONE step on a 16x16-per-panel sample of the order-2
+    configuration (same per-cell work), extrapolated to 256x256 by the cell count."""
+    from oracle import c_oracle, swe as oswe
+    from oracle import rk as ork
+    from oracle.mesh import CubedSphereMesh2D
+    allc = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    out = {"kind": "port", "solver": "Jacobi-PCG, rtol 1e-12 (test/Tutorials/ShallowWater.jl:175-176)"}
+    mesh = CubedSphereMesh2D(48)
+    for name, nt in (("serial", 1), ("all_cores", 0)):
+        W = c_oracle.CWaveProblem(mesh, 1, nthreads=nt)
+        x = np.concatenate([np.zeros(W.nu), ork.interpolate_scalar(W.T.Q, mesh, lambda X: 1.0 + 0.01 * np.exp(
+            -5.0 * ((X[..., 0] - 1.0) ** 2 + X[..., 1] ** 2 + X[..., 2] ** 2)))])
+        dt = ork.dx(mesh) * 0.1
+        x = W.step(x, dt)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            x = W.step(x, dt)
+        out.setdefault("wave", {})[name] = {"steps_per_s": 2 / (time.perf_counter() - t0), "cores": 1 if nt == 1 else allc}
+    out["wave"]["sample"] = "2 SSPRK(3,3) steps of the full 48x48-per-panel RT1 x DG1 configuration after one warm-up step"
+    ns = 16
+    mesh = CubedSphereMesh2D(ns)
+    for name, nt in (("serial", 1), ("all_cores", 0)):
+        S = c_oracle.CShallowWaterProblem(mesh, 2, oswe.coriolis(), oswe._g, nthreads=nt)
+        x0 = np.concatenate([ork.interpolate_rt(S.T.V, mesh, oswe.tangent_component(oswe.velocity())),
+                             ork.interpolate_scalar(S.T.Q, mesh, oswe.depth())])
+        dt = oswe.reference_dt(mesh, 2)
+        t0 = time.perf_counter()
+        S.step(x0, dt)
+        el = time.perf_counter() - t0
+        out.setdefault("shallow_water", {})[name] = {
+            "steps_per_s_sample": 1 / el, "steps_per_s_extrapolated_to_n256": 1 / el * (ns / 256.0) ** 2,
+            "cell_stage_evaluations_per_s": 6 * mesh.num_cells / el, "cores": 1 if nt == 1 else allc,
+            "pcg_iters_per_solve": S.iters / max(S.solves, 1)}
+    out["shallow_water"]["sample"] = (f"1 SSPRK(3,3) step (13 mass solves) of the order-2 configuration (RT2 x DG2 + CG3, degree 12, "
+                                      f"Williamson 2) on a {ns}x{ns}-per-panel mesh; n=256 figure = sample rate x ({ns}/256)^2")
+    return out
 
 
 def run_reference(args):
@@ -816,6 +889,10 @@ def main():
         vN, cN, sN = cpu_baseline_run(0, 12.0)
         line["cpu_baseline"] = {"value": vN, "unit": "cells/s", "cores": cN, "kind": "port", "sample": sN,
                                 "serial": {"value": v1, "cores": 1, "sample": s1}}
+        try:
+            line["cpu_baseline"]["rk"] = cpu_rk_baseline()
+        except Exception as ex:
+            line["cpu_baseline"]["rk"] = {"error": str(ex)[-300:]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
