@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_BASE, ORDER, DEGREE = 256, 2, 18
+SHELL_N_P4EST = 64   # BASELINE configs[4]: 3-D shell, p4est-refined (level 6: 64^3 octants per tree), order 2
 SEED = 20261019
 # algorithmic FLOPs per cell, Q = 100, m = 9, D = 2
 FLOPS_JAC = 100 * (81 * 4 + 9 * 8 + 60)          # 45 600: element matrix
@@ -270,13 +271,15 @@ def tswe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=1, steps=10):
     return out
 
 
-def shell_leg(gg, ctx, torch, stream, e0, e1, n=48, order=2, degree=18, steps=10, dist=None, rank=0, world=1):
+def shell_leg(gg, ctx, torch, stream, e0, e1, n=48, order=2, degree=18, steps=10, dist=None, rank=0, world=1, ordering=0):
     """cells/s of the Laplace-Beltrami residual + Jacobian assembly on the 3-D shell (hexahedral Q2, 10^3 points per cell in the
-    reference; here the tensor Gauss rule is factorised exactly into surface x radial integrals, gg_hex.cuh)."""
-    model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.19), n=n, ctx=ctx)
+    reference; here the tensor Gauss rule is factorised exactly into surface x radial integrals, gg_hex.cuh).  ordering = 2:
+    the cell order of the reference's uniformly refined p8est forest (Morton inside each tree); world > 1: every rank takes its
+    equal-count chunk of that order -- p4est's partition -- plus the vertex-adjacent ghost layer (BASELINE configs[4])."""
+    model = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(1.0, 0.19), n=n, ctx=ctx, ordering=ordering)
     ncells_global, owned = model.num_cells, model.num_cells
     if world > 1:
-        # weak scaling: every rank assembles its slice of the linear partition (owned + ghost cells; no data-path collective)
+        # every rank assembles its chunk of the (space-filling-curve) cell order (owned + ghost cells; no data-path collective)
         a, b = gg.partition_range(ncells_global, world, rank)
         full = model
         model = full.restrict(np.sort(np.concatenate([np.arange(a, b), full.ghost_cells(a, b)])))
@@ -318,7 +321,8 @@ def shell_leg(gg, ctx, torch, stream, e0, e1, n=48, order=2, degree=18, steps=10
     nnz = assem.matrix.nnz
     wr = 8.0 * (m * (m + 1) // 2 * model.num_cells)
     tensor = prof["k_hex_tensor_fill"] > 0
-    out = {"workload": f"laplace_beltrami_hexq{order}_deg{degree}_shell_n{n} ({n} layers, r = 1, t = 0.19)", "n_gpus": world,
+    out = {"workload": f"laplace_beltrami_hexq{order}_deg{degree}_shell_n{n} ({n} layers, r = 1, t = 0.19)"
+                       + (", p8est cell order, equal-count SFC chunks + ghost layer" if ordering == 2 else ""), "n_gpus": world,
            "cells": ncells_global, "cells_local_incl_ghosts": model.num_cells, "dofs_local": V.num_free_dofs, "nnz_local": nnz,
            "ms_per_step": ms, "cells_per_s": ncells_global / (ms * 1e-3), "kernels_ms": prof,
            "numeric_phase": "tensor-structured (complete shell): CSR values from assembled surface x radial factors" if tensor else
@@ -828,6 +832,10 @@ def main():
             line["shell"] = shell_leg(gg, ctx, torch, stream, e0, e1)
         except Exception as ex:
             line["shell"] = {"error": str(ex)}
+        try:
+            line["shell_p4est"] = shell_leg(gg, ctx, torch, stream, e0, e1, n=SHELL_N_P4EST, steps=5, ordering=2)
+        except Exception as ex:
+            line["shell_p4est"] = {"error": str(ex)}
 
     # ---- N > 1: partitioned-vs-single-GPU parity on a small mesh, then the RK legs on the partitioned models ----------------
     if world > 1:
@@ -862,11 +870,14 @@ def main():
             ad = {"error": str(ex)}
         line["rk"]["advection"] = ad
         try:
-            sh = shell_leg(gg, ctx, torch, stream, e0, e1, n=48 if args.scaling == "strong" else int(round(48 * world ** (1.0 / 3.0))),
-                           dist=dist, rank=rank, world=world)
+            # strong: the p8est-ordered 64^3-per-tree forest cut into `world` equal chunks of the space-filling curve
+            if args.scaling == "strong":
+                sh = shell_leg(gg, ctx, torch, stream, e0, e1, n=SHELL_N_P4EST, steps=5, dist=dist, rank=rank, world=world, ordering=2)
+            else:
+                sh = shell_leg(gg, ctx, torch, stream, e0, e1, n=int(round(48 * world ** (1.0 / 3.0))), dist=dist, rank=rank, world=world)
         except Exception as ex:
             sh = {"error": str(ex)}
-        line["shell"] = sh
+        line["shell_p4est" if args.scaling == "strong" else "shell"] = sh
         # the other scaling mode beside the headline: same legs, fewer steps
         other = "weak" if args.scaling == "strong" else "strong"
         try:

@@ -145,7 +145,7 @@ class AtlasDiscreteModel:
             h = C.c_void_p()
             if self.dim == 3:
                 # the reference refines the 6 coarse hexahedra isotropically: n cells through the shell unless n_layers is given
-                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 3, self.n, int(n_layers or 0), mesh.radius, mesh.thickness, 0, C.byref(h)))
+                _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 3, self.n, int(n_layers or 0), mesh.radius, mesh.thickness, int(ordering), C.byref(h)))
                 self.n_layers = int(n_layers or self.n)
             else:
                 _lib.check(self.lib.gg_mesh_cubed_sphere(self.ctx.h, 2, self.n, 1, mesh.radius, 0.0, int(ordering), C.byref(h)))

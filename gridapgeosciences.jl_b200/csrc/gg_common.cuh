@@ -333,7 +333,7 @@ void mesh_geometry_classes(gg_mesh* m);   // fills cls / cls_rep / n_classes (2-
 // host-side construction shared with the partition plans (gg_dist.cu); ctx == nullptr gives a host-only mesh
 gg_mesh* build_cubed_sphere(gg_ctx* ctx, int n, double radius, int ordering = 0);
 void upload_geometry(gg_mesh* m);
-gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int n_layers, double radius, double thickness);
+gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int n_layers, double radius, double thickness, int ordering = 0);
 std::vector<int32_t> hex_local_to_lex(int p);  // per-cell chart boxes, interval tables and the owned-cell mask -> device
 void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_space* s);
 void space_from_plan(gg_mesh* m, int kind, int order, gg_space* s);

@@ -263,7 +263,10 @@ static void ensure_hex_topology(gg_mesh* m) {
 // AtlasDiscreteModel(CubedSphereWithThicknessMesh(radius, thickness), l): n x n cells per panel, L cells through the shell
 // (src/Geometry/CubedSphereWithThicknessMesh.jl:33-124, AtlasGrids.jl:227-304; the reference refines isotropically, L = n).
 // Nodes are identified through their integer position on the cube-surface lattice and numbered by first encounter.
-gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, double thickness) {
+// ordering 0: gamma fastest, then alpha, then beta inside a panel.  ordering 2: the cell order of a uniformly refined p8est
+// forest (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208): Morton order inside each of the 6 trees, octant
+// coordinates (x, y, z) = (gamma, alpha, beta), x bit lowest (n = L = 2^l)
+gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, double thickness, int ordering) {
   std::unique_ptr<gg_mesh> m(new gg_mesh);
   m->ctx = ctx; m->dim = 3; m->n = n; m->n_layers = L; m->radius = radius; m->thickness = thickness;
   int64_t nc = 6LL * n * n * L;
@@ -273,10 +276,21 @@ gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, doub
   std::unordered_map<uint64_t, int32_t> nodes;
   nodes.reserve((size_t)(6LL * n * n + 2) * (L + 1) * 2);
   int64_t c = 0;
+  const int64_t per_panel = (int64_t)n * n * L;
   for (int p = 0; p < 6; ++p)
-    for (int jb = 0; jb < n; ++jb)
-      for (int ia = 0; ia < n; ++ia)
-        for (int kg = 0; kg < L; ++kg) {
+    for (int64_t t = 0; t < per_panel; ++t) {
+      int kg, ia, jb;
+      if (ordering == 0) {
+        kg = (int)(t % L); ia = (int)((t / L) % n); jb = (int)(t / ((int64_t)L * n));
+      } else {
+        kg = ia = jb = 0;
+        for (int b = 0; (1 << b) < n; ++b) {
+          kg |= (int)((t >> (3 * b)) & 1) << b;
+          ia |= (int)((t >> (3 * b + 1)) & 1) << b;
+          jb |= (int)((t >> (3 * b + 2)) & 1) << b;
+        }
+      }
+        {
           for (int v = 0; v < 8; ++v) {
             int dg = v & 1, da = (v >> 1) & 1, db = (v >> 2) & 1;
             int h[3] = {n, 2 * (ia + da) - n, 2 * (jb + db) - n};
@@ -292,6 +306,7 @@ gg_mesh* build_cubed_sphere_shell(gg_ctx* ctx, int n, int L, double radius, doub
           m->cell_layer[c] = kg;
           ++c;
         }
+    }
   m->n_nodes = (int64_t)nodes.size();
   m->surface.reset(build_cubed_sphere(ctx, n, radius, 0));
   if (ctx) {
@@ -352,14 +367,15 @@ int gg_mesh_cubed_sphere(gg_ctx* ctx, int dim, int n, int n_layers, double radiu
   GG_REQUIRE(radius > 0, GG_ERR_INVALID, "radius must be positive");
   GG_REQUIRE(ordering >= 0 && ordering <= 2, GG_ERR_INVALID, "ordering must be 0 (one-shot), 1 (recursive refinement) or 2 (Morton / p4est)");
   if (ordering != 0) {
-    GG_REQUIRE(dim == 2, GG_ERR_UNSUPPORTED, "Morton ordering is implemented for the 2-D surface");
+    GG_REQUIRE(dim == 2 || ordering == 2, GG_ERR_UNSUPPORTED, "on the 3-D shell orderings 0 and 2 (p8est Morton) are implemented");
     GG_REQUIRE((n & (n - 1)) == 0, GG_ERR_INVALID, "recursive / Morton ordering needs n = 2^l cells per panel edge");
+    if (dim == 3) GG_REQUIRE(n_layers == 0 || n_layers == n, GG_ERR_INVALID, "the p8est ordering refines isotropically: n_layers = n");
   }
   GG_CUDA(cudaSetDevice(ctx->device));
   if (dim == 3) {
     GG_REQUIRE(thickness > 0, GG_ERR_INVALID, "shell thickness must be positive");
     GG_REQUIRE(n_layers >= 0, GG_ERR_INVALID, "n_layers must be >= 0 (0: isotropic refinement, n layers)");
-    *out = build_cubed_sphere_shell(ctx, n, n_layers > 0 ? n_layers : n, radius, thickness);
+    *out = build_cubed_sphere_shell(ctx, n, n_layers > 0 ? n_layers : n, radius, thickness, ordering);
   } else {
     *out = build_cubed_sphere(ctx, n, radius, ordering);
   }

@@ -88,7 +88,9 @@ int gg_measure_fp64_peak(gg_ctx* ctx, double* tflops);
  *              1 = successive `refine` calls (src/Geometry/AtlasDiscreteModels.jl:248-262,286-344): recursive, the 4 children
  *                  of a parent stay together in Gridap order BL,BR,TL,TR  (n = 2^l)
  *              2 = uniformly refined p4est forest (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208): Morton
- *                  order inside each of the 6 trees -- the same cell order as 1  (n = 2^l)
+ *                  order inside each of the 6 trees -- the same cell order as 1  (n = 2^l).  dim 3: the p8est order, octant
+ *                  coordinates (x, y, z) = (gamma, alpha, beta), x bit lowest (n_layers = n = 2^l); equal-count chunks of
+ *                  this order (gg_partition_range) are p4est's partition (:286-294)
  * Cells [first_cell, first_cell + n_local) of the global panel-major order are instantiated (pass 0 and
  * -1 for all); a rank of the linear partition `div((i-1)*P, Nc)+1`
  * (src/Distributed/AtlasDistributedDiscreteModels.jl:31) uses its own slice, see gg_partition_range(). */

@@ -33,8 +33,13 @@ class CubedSphereShellMesh3D:
     """AtlasDiscreteModel(CubedSphereWithThicknessMesh(radius, thickness), l): n x n cells per panel, L cells through the shell
     (the reference refines isotropically: L = n)."""
 
-    def __init__(self, n, radius=1.0, thickness=0.1, n_layers=None):
+    def __init__(self, n, radius=1.0, thickness=0.1, n_layers=None, ordering=0):
+        """ordering 2: the cell order of a uniformly refined p8est forest
+        (/root/reference/src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208): Morton order inside each tree, octant
+        coordinates (x, y, z) = (gamma, alpha, beta) -- the coarse hexahedron's vertices are handed to p8est in Gridap's
+        lexicographic order -- with the x bit lowest."""
         L = n if n_layers is None else n_layers
+        assert ordering in (0, 2) and (ordering == 0 or (L == n and n & (n - 1) == 0))
         self.n, self.L, self.radius, self.thickness, self.D = n, L, radius, thickness, 3
         self.num_cells = 6 * n * n * L
         nodes = {}
@@ -45,10 +50,24 @@ class CubedSphereShellMesh3D:
         lay = np.empty(self.num_cells, dtype=np.int64)
         c = 0
         # cell order inside a panel: gamma fastest, then alpha, then beta
+        def cells_of_a_panel():
+            if ordering == 0:
+                for jb in range(n):
+                    for ia in range(n):
+                        for kg in range(L):
+                            yield kg, ia, jb
+            else:
+                for t in range(n * n * L):
+                    x = [0, 0, 0]
+                    for b in range(n.bit_length() - 1):
+                        for a in range(3):
+                            x[a] |= ((t >> (3 * b + a)) & 1) << b
+                    yield x[0], x[1], x[2]
+
         for p in range(6):
-            for jb in range(n):
-                for ia in range(n):
-                    for kg in range(L):
+            for kg, ia, jb in cells_of_a_panel():
+                if True:
+                    if True:
                         for v in range(8):
                             dg, da, db = v & 1, (v >> 1) & 1, (v >> 2) & 1
                             key = _cube_lattice_point(p, ia + da, jb + db, n) + (kg + dg,)

@@ -113,6 +113,61 @@ def test_shell_slices_assemble_the_owned_rows(gg):
     assert np.abs(A.data - Ao.data).max() < 1e-13 * np.abs(Ao.data).max()
 
 
+def test_p8est_ordering_and_sfc_partition(gg):
+    """BASELINE configs[4]: the distributed shell is a uniformly refined p8est forest -- Morton order inside each of the 6 trees
+    (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-208), partitioned into equal-count chunks of that order
+    (p4est's partition, :286-294) with a vertex-adjacent ghost layer.  The Morton-ordered mesh is the lexicographic mesh with
+    its cells permuted; a rank's slice assembles the same element matrices; the assembled operator is the same up to the
+    permutation of the DOFs that the different first-encounter numbering induces (checked through its action on a nodal field)."""
+    n, r, t, p, degree = 4, 1.0, 0.19, 2, 8
+    m0 = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=n)
+    m2 = gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=n, ordering=2)
+    o2 = shell.CubedSphereShellMesh3D(n, r, t, ordering=2)
+    assert (m2.num_cells, m2.num_nodes) == (o2.num_cells, o2.num_nodes) == (m0.num_cells, m0.num_nodes)
+    assert (m2.get_cell_node_ids() - 1 == o2.cell_nodes).all()
+    assert np.abs(m2.get_cell_coordinates() - o2.cell_chart_coords).max() < 1e-15
+    # Morton position of the lexicographic cell (kg, ia, jb) of a panel: bits interleaved, gamma lowest
+    kg, ia, jb = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    lex = (kg + n * (ia + n * jb)).reshape(-1)
+    mort = np.zeros_like(lex)
+    for b in range(2):
+        mort |= (((kg.reshape(-1) >> b) & 1) << (3 * b)) | (((ia.reshape(-1) >> b) & 1) << (3 * b + 1)) | (((jb.reshape(-1) >> b) & 1) << (3 * b + 2))
+    perm = np.empty(6 * n ** 3, dtype=np.int64)                 # lexicographic cell -> its position in the p8est order
+    for pn in range(6):
+        perm[pn * n ** 3 + lex] = pn * n ** 3 + mort
+    assert np.abs(m2.get_cell_coordinates()[perm] - m0.get_cell_coordinates()).max() == 0
+    assert (m2.get_cell_to_chart()[perm] == m0.get_cell_to_chart()).all()
+    # the 8 children of a parent octant are consecutive, x (gamma) fastest
+    cc = m2.get_cell_coordinates().reshape(-1, 8, 8, 3)[:, :, 0, :]
+    h = cc[:, 1, 0] - cc[:, 0, 0]
+    assert (h > 0).all() and np.abs(cc[:, 2, 1] - cc[:, 0, 1] - (cc[:, 2, 1] - cc[:, 0, 1])[0]).max() < 1e-14
+    assert np.abs(cc[:, 1, 1:] - cc[:, 0, 1:]).max() == 0 and np.abs(cc[:, 4, 2] - cc[:, 0, 2]).min() > 0
+    with pytest.raises(gg.GGError):
+        gg.AtlasDiscreteModel(gg.CubedSphereWithThicknessMesh(r, t), n=6, ordering=2)
+    # SFC chunk of rank 2 of 8 + ghost layer: same element matrices as the same cells of the complete forest
+    V2 = gg.TestFESpace(m2, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+    dO2 = gg.Measure(gg.Triangulation(m2), degree)
+    Ke = gg.element_matrices(gg.LaplaceBeltrami(dO2), V2, V2)
+    a, b = gg.partition_range(m2.num_cells, 8, 2)
+    assert b - a == m2.num_cells // 8
+    cells = np.sort(np.concatenate([np.arange(a, b), m2.ghost_cells(a, b)]))
+    sub = m2.restrict(cells)
+    Vs = gg.TestFESpace(sub, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+    Ks = gg.element_matrices(gg.LaplaceBeltrami(gg.Measure(gg.Triangulation(sub), degree)), Vs, Vs)
+    assert np.abs(Ks - Ke[cells]).max() < 1e-15 * np.abs(Ke).max()
+    # same operator: u^T A u for the interpolant of an ambient function does not depend on the cell order
+    V0 = gg.TestFESpace(m0, gg.ReferenceFE(gg.lagrangian, float, p), conformity="H1")
+    f = lambda X: X[..., 0] * X[..., 1] + X[..., 2] ** 2   # noqa: E731
+    en = []
+    for m_, V_ in ((m0, V0), (m2, V2)):
+        dO = gg.Measure(gg.Triangulation(m_), degree)
+        u = gg.interpolate(f, V_)
+        A = gg.assemble_matrix(gg.LaplaceBeltrami(dO), V_, V_).to_scipy()
+        uh = u.get()
+        en.append(float(uh @ (A @ uh)))
+    assert abs(en[0] - en[1]) < 1e-12 * abs(en[0])
+
+
 @pytest.mark.parametrize("form", ["helmholtz", "mass"])
 @pytest.mark.parametrize("n,L,p,degree", [(2, 2, 2, 8), (2, 3, 1, 6)])
 def test_shell_helmholtz_and_mass_match_oracle(gg, form, n, L, p, degree):
