@@ -429,7 +429,7 @@ class FESpace:
             pass
 
 
-def TestFESpace(model_or_trian, reffe, conformity="H1", constraint=None):
+def TestFESpace(model_or_trian, reffe, conformity="H1", constraint=None, dirichlet_tags=None):
     model = model_or_trian.model if isinstance(model_or_trian, Triangulation) else model_or_trian
     name, order = reffe[0], reffe[1]
     conformity = conformity.lstrip(":")
@@ -444,6 +444,11 @@ def TestFESpace(model_or_trian, reffe, conformity="H1", constraint=None):
     else:
         raise ValueError(f"unknown reference FE {name}")
     cons = {None: 0, "zeromean": 1, ":zeromean": 1}[constraint]
+    if dirichlet_tags is not None:
+        # test/Tutorials/LinearBoussinesq.jl:55-57: RT space on the shell with no flux through the bottom and top boundaries
+        if kind != _lib.SPACE_RT or model.dim != 3 or sorted(dirichlet_tags) != ["bottom_boundary", "top_boundary"] or cons:
+            raise ValueError('dirichlet_tags=["bottom_boundary", "top_boundary"] on a 3-D Raviart-Thomas space is what is implemented')
+        cons = _lib.CONSTRAINT_NOFLUX
     return FESpace(model, kind, order, cons)
 
 
@@ -982,6 +987,19 @@ class ThermalShallowWaterOperator(ShallowWaterOperator):
         super().__init__(model, p_fe, f, gravity=0.0, degree=degree, q0_mode=q0_mode, tau=tau)
 
 
+class BoussinesqOperator:
+    """TransientSemilinearFEOperator(mass, res, (jac, jac_t), X, Y; constant_mass=true) of test/Tutorials/LinearBoussinesq.jl:112-134
+    on AtlasDiscreteModel(CubedSphereWithThicknessMesh(r, t), l): RT_order x DG_order x DG_order, rotation rate `omega(xyz)`."""
+
+    def __init__(self, model, order, omega, c=1.0, N=1.48, degree=None):
+        self.model, self.p_fe = model, order
+        self.degree = 4 * (order + 1) if degree is None else degree
+        dΩ = Measure(Triangulation(model), self.degree)
+        _, xyz = dΩ.quadrature_points(chart=False)
+        self.omega_q = np.ascontiguousarray(np.broadcast_to(omega(xyz), xyz.shape[:2]), dtype=np.float64)
+        self.c, self.N = float(c), float(N)
+
+
 class AdvectionOperator:
     """TransientSemilinearFEOperator(mass, res, (jac, jac_t), P, Q) of the DG upwind advection tutorial
     (test/Tutorials/AdvectionUpwinding.jl:107-137): Q = DG-Q_order, wind `beta(xyz)` given in ambient components."""
@@ -1031,6 +1049,10 @@ class RKStepper:
             a.q0_mode = {"alias": _lib.Q0_ALIAS, "start_of_step": _lib.Q0_START_OF_STEP}[op.q0_mode]
             a.coriolis = _dp(op.f_q)
             a.topography = _dp(op.b_q) if op.b_q is not None else None
+        elif isinstance(op, BoussinesqOperator):
+            a.problem = _lib.PROBLEM_BOUSSINESQ
+            a.coriolis = _dp(op.omega_q)
+            a.sound_speed, a.buoyancy_frequency = op.c, op.N
         elif isinstance(op, AdvectionOperator):
             a.problem = _lib.PROBLEM_ADVECTION
             a.velocity_cells, a.velocity_facets = _dp(op.beta_cells), _dp(op.beta_facets)

@@ -13,7 +13,7 @@ GG_OK = 0
 ERRORS = {-1: "GG_ERR_INVALID", -2: "GG_ERR_CUDA", -3: "GG_ERR_UNSUPPORTED", -4: "GG_ERR_NOMEM", -5: "GG_ERR_NOCONV", -6: "GG_ERR_COMM"}
 
 SPACE_CG, SPACE_DG, SPACE_RT, SPACE_CGV = 0, 1, 2, 3
-CONSTRAINT_NONE, CONSTRAINT_ZEROMEAN = 0, 1
+CONSTRAINT_NONE, CONSTRAINT_ZEROMEAN, CONSTRAINT_NOFLUX = 0, 1, 2
 FORM_LAPLACE_BELTRAMI = 1
 FORM_LAPLACE_BELTRAMI_EXTRINSIC = 2
 FORM_HELMHOLTZ = 3
@@ -28,6 +28,7 @@ PROBLEM_WAVE = 1
 PROBLEM_SHALLOW_WATER = 2
 PROBLEM_ADVECTION = 3
 PROBLEM_THERMAL_SHALLOW_WATER = 4
+PROBLEM_BOUSSINESQ = 5
 Q0_ALIAS, Q0_START_OF_STEP = 0, 1
 
 
@@ -48,7 +49,8 @@ class RKArgs(C.Structure):
                 ("dt", C.c_double), ("rtol", C.c_double),
                 ("gravity", C.c_double), ("tau", C.c_double), ("q0_mode", C.c_int32),
                 ("coriolis", C.POINTER(C.c_double)), ("topography", C.POINTER(C.c_double)),
-                ("velocity_cells", C.POINTER(C.c_double)), ("velocity_facets", C.POINTER(C.c_double))]
+                ("velocity_cells", C.POINTER(C.c_double)), ("velocity_facets", C.POINTER(C.c_double)),
+                ("sound_speed", C.c_double), ("buoyancy_frequency", C.c_double)]
 
 
 _P = C.c_void_p

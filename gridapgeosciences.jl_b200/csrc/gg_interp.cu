@@ -12,6 +12,7 @@
 #include "gg_geom.cuh"
 #include "gg_vec.cuh"
 #include "gg_hex_ops.cuh"
+#include "gg_rk.cuh"
 
 namespace gg {
 
@@ -294,8 +295,14 @@ int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* x
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   if (m->dim == 3) {
+    if (s->kind == GG_SPACE_RT) {
+      // moment points of the hexahedral Raviart-Thomas element (gg_bq.cu)
+      const int N = bq_interp_points(s, chart, xyz);
+      if (n_pts) *n_pts = N;
+      return GG_OK;
+    }
     // Lagrange nodes of the hexahedra in the LOCAL DOF order of the space
-    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian space");
+    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian or RT space");
     const int ml = s->ndofs_loc;
     if (n_pts) *n_pts = ml;
     const int64_t tot = m->n_cells * ml;
@@ -340,8 +347,13 @@ int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out) {
   int64_t nc = m->n_cells;
   if (s->n_free == 0) return GG_OK;
   build_vec_map(s);
+  if (m->dim == 3 && s->kind == GG_SPACE_RT) {
+    GG_CUDA(cudaMemsetAsync(out->d.p, 0, s->n_free * sizeof(double), st));
+    bq_interpolate(s, vals, out->d.p);
+    return GG_OK;
+  }
   if (m->dim == 3) {
-    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian space");
+    GG_REQUIRE(s->kind == GG_SPACE_CG || s->kind == GG_SPACE_DG, GG_ERR_UNSUPPORTED, "interpolation on the shell needs a Lagrangian or RT space");
     DevBuf<double> dv; dv.upload(vals, (size_t)nc * s->ndofs_loc, st);
     k_interp_pick_scalar<<<nblk(s->n_free, 256), 256, 0, st>>>(s->n_free, nc, s->ndofs_loc, s->d_vptr.p, s->d_vsrc.p, dv.p, out->d.p);
     ctx->launches++;

@@ -590,7 +590,48 @@ void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_spac
       std::iota(s->cell_dofs.begin(), s->cell_dofs.end(), 0);
       return;
     }
-    GG_REQUIRE(kind == GG_SPACE_CG && (order == 1 || order == 2), GG_ERR_UNSUPPORTED, "on the 3-D shell only CG Q1/Q2 and DG spaces are implemented");
+    if (kind == GG_SPACE_RT) {
+      // hexahedral RT_k (test/Tutorials/LinearBoussinesq.jl:55-57): (k+1)^2 DOFs per face, 3 k (k+1)^2 per cell; the slave
+      // (second) cell of a face sees them negated; GG_CONSTRAINT_NOFLUX drops the DOFs of the boundary faces -- on the closed
+      // shell these are the bottom and top faces (dirichlet_tags = ["bottom_boundary", "top_boundary"]) -- and numbers the rest
+      // in the order of the face ids
+      GG_REQUIRE(order >= 0 && order <= 1, GG_ERR_UNSUPPORTED, "hexahedral RT order must be 0 or 1");
+      GG_REQUIRE(constraint == GG_CONSTRAINT_NONE || constraint == GG_CONSTRAINT_NOFLUX, GG_ERR_INVALID, "unknown constraint for an RT space");
+      ensure_hex_topology(m);
+      const int nf = (order + 1) * (order + 1), ni = 3 * order * (order + 1) * (order + 1), mloc = 6 * nf + ni;
+      std::vector<int32_t> first(m->n_faces, -1), count(m->n_faces, 0), fid(m->n_faces, -1);
+      for (int64_t c = 0; c < nc; ++c)
+        for (int f = 0; f < 6; ++f) {
+          const int32_t g = m->cell_faces6[c * 6 + f];
+          if (first[g] < 0) first[g] = (int32_t)c;
+          count[g]++;
+        }
+      int64_t nfree_faces = 0;
+      for (int64_t g = 0; g < m->n_faces; ++g)
+        if (constraint == GG_CONSTRAINT_NONE || count[g] > 1) fid[g] = (int32_t)nfree_faces++;
+      s->ndofs_loc = mloc;
+      s->n_free = nfree_faces * nf + nc * ni;
+      s->n_dirichlet = (m->n_faces - nfree_faces) * nf;
+      GG_REQUIRE(s->n_free < (int64_t)INT32_MAX, GG_ERR_UNSUPPORTED, "too many DOFs");
+      s->cell_dofs.resize(nc * mloc);
+      s->cell_signs.assign(nc * mloc, 1);
+      s->blocks.push_back({0, nfree_faces, nf});
+      if (ni > 0) s->blocks.push_back({nfree_faces * nf, nc, ni});
+      for (int64_t c = 0; c < nc; ++c) {
+        int k = 0;
+        for (int f = 0; f < 6; ++f) {
+          const int32_t g = m->cell_faces6[c * 6 + f];
+          for (int t = 0; t < nf; ++t) {
+            s->cell_dofs[c * mloc + k] = fid[g] >= 0 ? fid[g] * nf + t : -1;
+            s->cell_signs[c * mloc + k] = first[g] == (int32_t)c ? 1 : -1;
+            ++k;
+          }
+        }
+        for (int t = 0; t < ni; ++t) s->cell_dofs[c * mloc + k++] = (int32_t)(nfree_faces * nf + c * ni + t);
+      }
+      return;
+    }
+    GG_REQUIRE(kind == GG_SPACE_CG && (order == 1 || order == 2), GG_ERR_UNSUPPORTED, "on the 3-D shell CG Q1/Q2, DG and RT0/RT1 spaces are implemented");
     int mloc = (order + 1) * (order + 1) * (order + 1);
     s->ndofs_loc = mloc;
     s->cell_dofs.resize(nc * mloc);

@@ -292,4 +292,142 @@ void RTRef::tabulate(int npts, const double* pts, std::vector<double>& val, std:
   }
 }
 
+// ---- Raviart-Thomas on the cube ------------------------------------------------------------------------------------------
+
+static const int HEXF_AXIS[6] = {2, 2, 1, 1, 0, 0};
+static const int HEXF_VAL[6] = {0, 1, 0, 1, 0, 1};
+
+void rt_hex_moment_functionals(int k, std::vector<double>& pts, std::vector<double>& W) {
+  GG_REQUIRE(k >= 0 && k <= 1, GG_ERR_UNSUPPORTED, "hexahedral Raviart-Thomas order must be 0 or 1");
+  const int nqf = k + 2, nqc = k > 0 ? num_points_1d(2 * (k + 1)) : 0;
+  const int nfp = nqf * nqf, N = 6 * nfp + nqc * nqc * nqc;
+  const int ndofs = 3 * (k + 2) * (k + 1) * (k + 1);
+  double xq[MAX_NQ], wq[MAX_NQ], xc[MAX_NQ], wc[MAX_NQ];
+  gauss_legendre_01(nqf, xq, wq);
+  if (nqc) gauss_legendre_01(nqc, xc, wc);
+  pts.assign((size_t)N * 3, 0.0);
+  W.assign((size_t)ndofs * N * 3, 0.0);
+  for (int f = 0; f < 6; ++f) {
+    const int ax = HEXF_AXIS[f];
+    int sp[2], t = 0;
+    for (int a = 0; a < 3; ++a) if (a != ax) sp[t++] = a;
+    for (int q2 = 0; q2 < nqf; ++q2)
+      for (int q1 = 0; q1 < nqf; ++q1) {
+        double* p = &pts[(size_t)(f * nfp + q1 + nqf * q2) * 3];
+        p[ax] = HEXF_VAL[f]; p[sp[0]] = xq[q1]; p[sp[1]] = xq[q2];
+      }
+  }
+  for (int q3 = 0; q3 < nqc; ++q3)
+    for (int q2 = 0; q2 < nqc; ++q2)
+      for (int q1 = 0; q1 < nqc; ++q1) {
+        double* p = &pts[(size_t)(6 * nfp + q1 + nqc * (q2 + nqc * q3)) * 3];
+        p[0] = xc[q1]; p[1] = xc[q2]; p[2] = xc[q3];
+      }
+  int row = 0;
+  for (int f = 0; f < 6; ++f)
+    for (int j = 0; j <= k; ++j)
+      for (int i = 0; i <= k; ++i) {
+        for (int q2 = 0; q2 < nqf; ++q2)
+          for (int q1 = 0; q1 < nqf; ++q1)
+            W[((size_t)row * N + f * nfp + q1 + nqf * q2) * 3 + HEXF_AXIS[f]] =
+                wq[q1] * wq[q2] * ipow(xq[q1], i) * ipow(xq[q2], j) * (HEXF_VAL[f] ? 1.0 : -1.0);
+        ++row;
+      }
+  if (k > 0)
+    for (int c = 0; c < 3; ++c) {
+      int deg[3] = {k, k, k};
+      deg[c] = k - 1;
+      for (int l = 0; l <= deg[2]; ++l)
+        for (int j = 0; j <= deg[1]; ++j)
+          for (int i = 0; i <= deg[0]; ++i) {
+            for (int q3 = 0; q3 < nqc; ++q3)
+              for (int q2 = 0; q2 < nqc; ++q2)
+                for (int q1 = 0; q1 < nqc; ++q1)
+                  W[((size_t)row * N + 6 * nfp + q1 + nqc * (q2 + nqc * q3)) * 3 + c] =
+                      wc[q1] * wc[q2] * wc[q3] * ipow(xc[q1], i) * ipow(xc[q2], j) * ipow(xc[q3], l);
+            ++row;
+          }
+    }
+  GG_REQUIRE(row == ndofs, GG_ERR_INVALID, "hexahedral RT moment count mismatch");
+}
+
+RTRefHex build_rt_hex_ref(int k) {
+  GG_REQUIRE(k >= 0 && k <= 1, GG_ERR_UNSUPPORTED, "hexahedral Raviart-Thomas order must be 0 or 1");
+  RTRefHex R;
+  R.k = k;
+  for (int c = 0; c < 3; ++c) {
+    int deg[3] = {k, k, k};
+    deg[c] = k + 1;
+    for (int l = 0; l <= deg[2]; ++l)
+      for (int j = 0; j <= deg[1]; ++j)
+        for (int i = 0; i <= deg[0]; ++i) { R.comp.push_back(c); R.ex.push_back(i); R.ey.push_back(j); R.ez.push_back(l); }
+  }
+  const int n = (int)R.comp.size();
+  R.ndofs = n;
+  std::vector<double> pts, W;
+  rt_hex_moment_functionals(k, pts, W);
+  const int N = (int)(pts.size() / 3);
+  std::vector<double> M((size_t)n * n, 0.0);
+  for (int m = 0; m < n; ++m)
+    for (int q = 0; q < N; ++q) {
+      const double* p = &pts[(size_t)q * 3];
+      for (int c = 0; c < n; ++c) {
+        const double w = W[((size_t)m * N + q) * 3 + R.comp[c]];
+        if (w != 0.0) M[(size_t)m * n + c] += w * ipow(p[0], R.ex[c]) * ipow(p[1], R.ey[c]) * ipow(p[2], R.ez[c]);
+      }
+    }
+  std::vector<double> Minv = M;
+  invert_dense(n, Minv);
+  std::vector<long double> Cl(Minv.begin(), Minv.end()), Rl((size_t)n * n), Tl((size_t)n * n);
+  for (int it = 0; it < 2; ++it) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        long double s = (i == j) ? 1.0L : 0.0L;
+        for (int k2 = 0; k2 < n; ++k2) s -= (long double)M[(size_t)i * n + k2] * Cl[(size_t)k2 * n + j];
+        Rl[(size_t)i * n + j] = s;
+      }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        long double s = 0.0L;
+        for (int k2 = 0; k2 < n; ++k2) s += Cl[(size_t)i * n + k2] * Rl[(size_t)k2 * n + j];
+        Tl[(size_t)i * n + j] = s;
+      }
+    for (size_t i = 0; i < (size_t)n * n; ++i) Cl[i] += Tl[i];
+  }
+  R.C.resize((size_t)n * n);
+  for (size_t i = 0; i < (size_t)n * n; ++i) R.C[i] = (double)Cl[i];
+  return R;
+}
+
+void RTRefHex::tabulate(int npts, const double* pts, std::vector<double>& val, std::vector<double>& div) const {
+  const int n = ndofs;
+  val.assign((size_t)npts * n * 3, 0.0);
+  div.assign((size_t)npts * n, 0.0);
+  std::vector<double> pv(n), pd(n);
+  for (int q = 0; q < npts; ++q) {
+    const double x = pts[3 * q], y = pts[3 * q + 1], z = pts[3 * q + 2];
+    for (int i = 0; i < n; ++i) {
+      pv[i] = ipow(x, ex[i]) * ipow(y, ey[i]) * ipow(z, ez[i]);
+      int e[3] = {ex[i], ey[i], ez[i]};
+      if (e[comp[i]] > 0) {
+        const double f = e[comp[i]];
+        e[comp[i]] -= 1;
+        pd[i] = f * ipow(x, e[0]) * ipow(y, e[1]) * ipow(z, e[2]);
+      } else {
+        pd[i] = 0.0;
+      }
+    }
+    for (int j = 0; j < n; ++j) {
+      double v[3] = {0, 0, 0}, d = 0;
+      for (int i = 0; i < n; ++i) {
+        const double c = C[(size_t)i * n + j];
+        v[comp[i]] += c * pv[i];
+        d += c * pd[i];
+      }
+      for (int a = 0; a < 3; ++a) val[((size_t)q * n + j) * 3 + a] = v[a];
+      div[(size_t)q * n + j] = d;
+    }
+  }
+}
+
 }  // namespace gg

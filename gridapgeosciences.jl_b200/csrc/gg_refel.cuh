@@ -44,4 +44,19 @@ RTRef build_rt_ref(int k);
 // points [N][2] and weights [ndofs][N][2] of the moment functionals of RT_k (interpolation of a reference-space field)
 void rt_moment_functionals(int k, std::vector<double>& pts, std::vector<double>& W);
 
+// Raviart-Thomas RT_k on the cube (same conventions one dimension up): prebasis Q_{k+1,k,k} x Q_{k,k+1,k} x Q_{k,k,k+1};
+// faces in Gridap order (z=0, z=1, y=0, y=1, x=0, x=1), each parametrised by its two spanning axes in increasing order, with
+// (k+1)^2 moments of the outward normal flux against s^i t^j (i fastest); then the interior moments of component a against
+// x^i y^j z^l with degree k-1 in x_a.  3 (k+2)(k+1)^2 DOFs.
+struct RTRefHex {
+  int k = 0, ndofs = 0;
+  std::vector<int> comp, ex, ey, ez;
+  std::vector<double> C;          // [ndofs(prebasis)][ndofs(basis)]
+  // tabulate at reference points [npts][3]: val [npts][ndofs][3], div [npts][ndofs]
+  void tabulate(int npts, const double* pts, std::vector<double>& val, std::vector<double>& div) const;
+};
+RTRefHex build_rt_hex_ref(int k);
+// points [N][3] and weights [ndofs][N][3] of the moment functionals of the hexahedral RT_k
+void rt_hex_moment_functionals(int k, std::vector<double>& pts, std::vector<double>& W);
+
 }  // namespace gg

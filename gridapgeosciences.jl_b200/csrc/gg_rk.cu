@@ -256,6 +256,7 @@ void build_dg_mass_inverse(gg_rk* rk) {
 static void rk_step_async(gg_rk* rk) {
   if (rk->problem == GG_PROBLEM_SHALLOW_WATER) { swe_step_async(rk); return; }
   if (rk->problem == GG_PROBLEM_ADVECTION) { adv_step_async(rk); return; }
+  if (rk->problem == GG_PROBLEM_BOUSSINESQ) { bq_step_async(rk); return; }
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
   int64_t n = rk_nx(rk);
@@ -307,12 +308,13 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   GG_API_BEGIN
   GG_REQUIRE(m && a && out, GG_ERR_INVALID, "null argument");
   GG_REQUIRE(a->problem == GG_PROBLEM_WAVE || a->problem == GG_PROBLEM_SHALLOW_WATER || a->problem == GG_PROBLEM_ADVECTION ||
-                 a->problem == GG_PROBLEM_THERMAL_SHALLOW_WATER, GG_ERR_UNSUPPORTED,
-             "unknown problem id (GG_PROBLEM_WAVE, GG_PROBLEM_SHALLOW_WATER, GG_PROBLEM_ADVECTION and GG_PROBLEM_THERMAL_SHALLOW_WATER are implemented)");
+                 a->problem == GG_PROBLEM_THERMAL_SHALLOW_WATER || a->problem == GG_PROBLEM_BOUSSINESQ, GG_ERR_UNSUPPORTED,
+             "unknown problem id (GG_PROBLEM_WAVE, _SHALLOW_WATER, _ADVECTION, _THERMAL_SHALLOW_WATER and _BOUSSINESQ are implemented)");
   GG_REQUIRE(a->n_stages >= 1 && a->n_stages <= 4 && a->A && a->b && a->c, GG_ERR_INVALID, "tableau must have 1..4 stages");
   GG_REQUIRE(a->order >= 0 && a->order <= 2, GG_ERR_UNSUPPORTED, "the RK steppers support RT_p x DG_p with p <= 2");
   GG_REQUIRE(a->dt > 0, GG_ERR_INVALID, "dt must be positive");
-  GG_REQUIRE(m->dim == 2, GG_ERR_UNSUPPORTED, "the RK steppers run on the 2-D cubed sphere");
+  GG_REQUIRE(m->dim == (a->problem == GG_PROBLEM_BOUSSINESQ ? 3 : 2), GG_ERR_UNSUPPORTED,
+             "the wave / shallow-water / advection steppers run on the 2-D cubed sphere, the Boussinesq stepper on the 3-D shell");
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   raw = new gg_rk;
@@ -324,6 +326,11 @@ int gg_rk_create(gg_mesh* m, const gg_rk_args* a, gg_rk** out) {
   for (int i = 0; i < s; ++i)
     for (int j = i; j < s; ++j) GG_REQUIRE(rk->A[i * s + j] == 0.0, GG_ERR_INVALID, "tableau is not explicit");
   auto chk = [](int code) { if (code != GG_OK) throw Error(code, gg_last_error(nullptr)); };
+  if (a->problem == GG_PROBLEM_BOUSSINESQ) {
+    bq_create(rk, a);
+    *out = raw;
+    return GG_OK;
+  }
   if (a->problem == GG_PROBLEM_ADVECTION) {
     // scalar DG state only: no RT space, no global solve
     chk(gg_space_builtin(m, GG_SPACE_DG, a->order, GG_CONSTRAINT_NONE, &rk->Q));
@@ -481,6 +488,8 @@ int gg_rk_residual(gg_rk* rk, const double* x, double* r) {
     rk->y_valid = false;
     swe_diagnostics_async(rk, rk->xi.p, rk->y.p);
     swe_residual_async(rk, rk->xi.p, rk->y.p, rk->y.p, rk->r.p, nullptr);
+  } else if (rk->problem == GG_PROBLEM_BOUSSINESQ) {
+    bq_residual_async(rk, rk->xi.p, rk->r.p, nullptr);
   } else if (rk->problem == GG_PROBLEM_ADVECTION) {
     adv_slope_async(rk, rk->xi.p, nullptr, rk->r.p);
   } else {

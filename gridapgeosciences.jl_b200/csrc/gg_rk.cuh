@@ -56,6 +56,9 @@ struct gg_rk {
   gg::DevBuf<double> adv_fval;                 // [4][nqf][m] basis at the facet points
   // ---- thermal shallow water only (gg_tswe.cu) -----------------------------------------------------------
   gg::DevBuf<double> tsw_fvn, tsw_wf;          // [4][nqf][mu] reference RT normal component at the facet points; [nqf] weights
+  // ---- linear Boussinesq on the shell only (gg_bq.cu) ----------------------------------------------------------
+  gg::DevBuf<double> bq_xi, bq_w, bq_rt_val, bq_rt_div, bq_dg_val;   // 1-D rule; reference tabulations at the nq^3 points
+  double bq_c2 = 1.0, bq_N2 = 1.0;
   int64_t diag_solves = 0;
   bool y_valid = false;           // y == diagnostics(x) (lets a step reuse the final diagnostics of the previous one)
 };
@@ -82,6 +85,12 @@ void swe_step_async(gg_rk* rk);
 void swe_diagnostics_async(gg_rk* rk, const double* x, double* y);
 void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp);
 void swe_destroy(gg_rk* rk);
+// linear Boussinesq on the 3-D shell (gg_bq.cu)
+void bq_create(gg_rk* rk, const gg_rk_args* a);
+void bq_step_async(gg_rk* rk);
+void bq_residual_async(gg_rk* rk, const double* x, double* r, double* k_pb);
+int bq_interp_points(gg_space* s, double* chart, double* xyz);
+void bq_interpolate(gg_space* s, const double* vals, double* out);
 // DG advection (gg_adv.cu)
 void adv_create(gg_rk* rk, const gg_rk_args* a);
 void facet_tables(gg_rk* rk, int nqf);  // adv_nbr_cell / adv_nbr_edge / adv_is_plus / adv_fval

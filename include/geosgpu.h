@@ -166,6 +166,9 @@ int gg_vec_consistent(gg_space* s, gg_vec* v);
 #define GG_SPACE_CGV 3
 #define GG_CONSTRAINT_NONE 0
 #define GG_CONSTRAINT_ZEROMEAN 1 /* constraint=:zeromean: last free DOF fixed (Gridap ZeroMeanFESpace) */
+/* raviart_thomas on the 3-D shell with dirichlet_tags=["bottom_boundary","top_boundary"] and zero Dirichlet value: no DOFs on
+ * the boundary faces (test/Tutorials/LinearBoussinesq.jl:55-57) */
+#define GG_CONSTRAINT_NOFLUX 2
 /* Built-in numbering = our restatement of Gridap's (parity unpinned). */
 int gg_space_builtin(gg_mesh* m, int kind, int order, int constraint, gg_space** out);
 /* Numbering owned by the caller (exact Gridap numbering when called from Julia):
@@ -304,8 +307,9 @@ void gg_solver_destroy(gg_solver* s);
  * (test/Transient/TransientShallowWater.jl:88-95, src/Helpers/Operators.jl:16-24): the caller evaluates its
  * ambient function at the points returned by gg_space_interp_points(); the pull-back sqrtg * pinvJ(J) . v,
  * the inverse contravariant Piola map and the reference moments run on the device.
- *   n_pts   points per cell (Lagrangian: the ndofs_loc nodes; RT_k: 4 (k+2) facet + (k+2)^2 interior moment points)
- *   chart   [n_cells][n_pts][2] or NULL;  xyz [n_cells][n_pts][3] or NULL */
+ *   n_pts   points per cell (Lagrangian: the ndofs_loc nodes; RT_k: 4 (k+2) facet + (k+2)^2 interior moment points; hexahedral
+ *           RT_k on the shell: 6 (k+2)^2 face + interior moment points)
+ *   chart   [n_cells][n_pts][dim] or NULL;  xyz [n_cells][n_pts][3] or NULL */
 int gg_space_interp_points(gg_space* s, int32_t* n_pts, double* chart, double* xyz);
 /* vals: Lagrangian [n_cells][n_pts] scalars; RT [n_cells][n_pts][3] ambient vectors.  out: free DOF values. */
 int gg_space_interpolate(gg_space* s, const double* vals, gg_vec* out);
@@ -356,6 +360,11 @@ int gg_chart_mean(gg_space* s, gg_vec* u, double dirichlet, double* out);
  * q0 handling as GG_PROBLEM_SHALLOW_WATER, plus the buoyancy cell terms and the skeleton terms u_s1, u_s2, B_s1, B_s2
  * (upwinding_sign threshold 1e-4).  `gravity` and `topography` are not used (B carries gravity). */
 #define GG_PROBLEM_THERMAL_SHALLOW_WATER 4
+/* Linearised Boussinesq equations on the 3-D shell (test/Tutorials/LinearBoussinesq.jl:112-134), RT_k x DG_k x DG_k on hexahedra
+ * with no flux through the bottom and top boundaries: state [u; p; b] (gg_rk_info reports n_p = 2 x the DG size), constant mass,
+ * marched with the explicit tableau.  `coriolis` holds the rotation rate omega at the quadrature points [n_cells][nq^3] (gamma
+ * fastest), `sound_speed` c and `buoyancy_frequency` N the two constants (1 if 0).  The mesh must be a builtin 3-D shell. */
+#define GG_PROBLEM_BOUSSINESQ 5
 #define GG_Q0_ALIAS 0         /* q0 aliases q, as in the reference (RungeKuttaEX.jl:69-75 pass one array twice) */
 #define GG_Q0_START_OF_STEP 1 /* q0 = potential vorticity at the beginning of the step */
 typedef struct {
@@ -378,6 +387,9 @@ typedef struct {
    * (gg_quadrature_points) and at the facet quadrature points of every cell side [n_cells][4][nq][3] (gg_skeleton_points) */
   const double* velocity_cells;
   const double* velocity_facets;
+  /* linear Boussinesq only */
+  double sound_speed;
+  double buoyancy_frequency;
 } gg_rk_args;
 int gg_rk_create(gg_mesh* m, const gg_rk_args* args, gg_rk** out);
 int gg_rk_info(gg_rk* rk, int64_t* n_u, int64_t* n_p);

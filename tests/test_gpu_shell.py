@@ -82,7 +82,9 @@ def test_unsupported_requests_on_the_shell_fail_loudly(gg):
     with pytest.raises(gg.GGError):
         gg.assemble_matrix(gg.ScalarMass(dΩ, qdata=np.ones(model.num_cells * dΩ.num_points)), V, V)
     with pytest.raises(gg.GGError):
-        gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, 0), conformity="HDiv")
+        gg.TestFESpace(model, gg.ReferenceFE(gg.raviart_thomas, float, 2), conformity="HDiv")    # hexahedral RT0 / RT1 only
+    with pytest.raises(gg.GGError):
+        gg.TestFESpace(model, gg.ReferenceFE(gg.lagrangian, float, 3), conformity="H1")
 
 
 def test_shell_slices_assemble_the_owned_rows(gg):
