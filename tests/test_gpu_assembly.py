@@ -311,3 +311,15 @@ def test_geometry_class_assembly_is_bitwise_the_per_cell_assembly(gg, n, p, degr
             assert (A2.values() == v0).all()
     finally:
         ctx.set_geometry_classes(False)
+
+
+def test_tile_path_on_small_meshes():
+    """The fused tile assembly is chosen by size (several waves of 128-cell tiles); GG_LB_TILES=1 forces it, so that partial tiles,
+    single-tile panels, constrained spaces, sub-meshes and the Morton order go through it too (tests/tile_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tile_worker.py")], capture_output=True, text=True, timeout=600,
+                         cwd=root, env=dict(os.environ, GG_LB_TILES="1"))
+    assert out.returncode == 0 and "TILE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
