@@ -179,7 +179,7 @@ def swe_roofline(leg, ncell_local, p):
     ncls = min(ncell_local, 65536 if ncell_local >= 65536 else ncell_local)   # geometry classes (256^2: one per (column, row) pair)
     b_cells = ncls * 8.0 * (mb * (mb + 1) // 2) + ncell_local * (mb * 4 + mb * 8 + mb * 8)   # S once per class; ids, x_f in, S x out
     b_gather = rows * (2 * (4 + 8) + 3 * 8)           # two element sources per row (index + value); p, Ap, partial dots
-    b_update = rows * (6 * 8 + 3 * (p + 1) * 8)       # x, r, z, p read / written; block-Jacobi rows
+    b_update = rows * (6 * 8 + (p + 1) * 8)           # x, r, z, p read / written; the row's slice of its (p+1)^2 block inverse
     it = leg["pcg_us_per_iter"]["rt_mass"]
     t_us = it["cells"] + it["gather_dot"] + it["update_precond"]
     tot = b_cells + b_gather + b_update
@@ -383,7 +383,8 @@ def cpu_rk_baseline():
     allc = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     out = {"kind": "port", "solver": "Jacobi-PCG, rtol 1e-12 (test/Tutorials/ShallowWater.jl:175-176)"}
     mesh = CubedSphereMesh2D(48)
-    for name, nt in (("serial", 1), ("all_cores", 0)):
+    # thread counts are passed explicitly (the box may export OMP_NUM_THREADS=1)
+    for name, nt in (("serial", 1), ("all_cores", allc)):
         W = c_oracle.CWaveProblem(mesh, 1, nthreads=nt)
         x = np.concatenate([np.zeros(W.nu), ork.interpolate_scalar(W.T.Q, mesh, lambda X: 1.0 + 0.01 * np.exp(
             -5.0 * ((X[..., 0] - 1.0) ** 2 + X[..., 1] ** 2 + X[..., 2] ** 2)))])
@@ -396,7 +397,7 @@ def cpu_rk_baseline():
     out["wave"]["sample"] = "2 SSPRK(3,3) steps of the full 48x48-per-panel RT1 x DG1 configuration after one warm-up step"
     ns = 16
     mesh = CubedSphereMesh2D(ns)
-    for name, nt in (("serial", 1), ("all_cores", 0)):
+    for name, nt in (("serial", 1), ("all_cores", allc)):
         S = c_oracle.CShallowWaterProblem(mesh, 2, oswe.coriolis(), oswe._g, nthreads=nt)
         x0 = np.concatenate([ork.interpolate_rt(S.T.V, mesh, oswe.tangent_component(oswe.velocity())),
                              ork.interpolate_scalar(S.T.Q, mesh, oswe.depth())])

@@ -32,7 +32,7 @@ std::shared_ptr<FormTab> get_tab(gg_ctx* ctx, int kind, int order, int nq) {
   uint64_t key = ((uint64_t)k << 32) | ((uint64_t)order << 16) | (uint64_t)nq;
   auto it = ctx->tabs.find(key);
   if (it != ctx->tabs.end()) return it->second;
-  GG_REQUIRE(nq >= 1 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree too high (max 31)");
+  GG_REQUIRE(nq >= 1 && nq <= MAX_NQ_NORMS, GG_ERR_UNSUPPORTED, "quadrature degree too high (max 63)");
   auto T = std::make_shared<FormTab>();
   T->kind = k; T->order = order; T->nq = nq; T->Q = nq * nq;
   std::vector<double> xi(nq), w(nq);
@@ -1121,7 +1121,7 @@ int gg_quadrature_points(gg_mesh* m, int32_t degree, double* out_chart, double* 
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= (m->dim == 3 ? MAX_NQ : MAX_NQ_NORMS), GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   if (m->dim == 3) {
     // [n_cells][nq^3][3]: chart (gamma, alpha, beta) / ambient, gamma index fastest
     hex_points(m, -1, nq, out_chart, out_xyz);

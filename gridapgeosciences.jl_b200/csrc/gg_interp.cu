@@ -403,7 +403,7 @@ int gg_norm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   GG_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= (m->dim == 3 ? MAX_NQ : MAX_NQ_NORMS), GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   if (m->dim == 3) {
     GG_REQUIRE(s->kind == GG_SPACE_CG, GG_ERR_UNSUPPORTED, "norms on the shell are implemented for CG spaces");
     *out = hex_cell_functional(s, 0, nq, e->d.p, 0.0, nullptr);
@@ -436,7 +436,7 @@ int gg_surface_laplacian(gg_mesh* m, int32_t degree, const double* grad_f, const
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   const int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= (m->dim == 3 ? MAX_NQ : MAX_NQ_NORMS), GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   const int64_t n = m->n_cells * nq * nq;
   GG_REQUIRE(gg_vec_size(out) == n, GG_ERR_INVALID, "output vector must have n_cells * Q entries");
   if (n == 0) return GG_OK;
@@ -470,7 +470,7 @@ int gg_l2_error_sq(gg_space* s, gg_vec* u, double dirichlet, gg_vec* fq, int32_t
   GG_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= (m->dim == 3 ? MAX_NQ : MAX_NQ_NORMS), GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   const int64_t nc = m->n_cells;
   const bool is_rt = s->kind == GG_SPACE_RT, is_vec = s->kind == GG_SPACE_CGV;
   if (fq) GG_REQUIRE(gg_vec_size(fq) == nc * nq * nq * (is_rt || is_vec ? 2 : 1), GG_ERR_INVALID,
@@ -547,7 +547,7 @@ static int surface_grad_div(gg_mesh* m, int32_t degree, const double* F, const d
   gg_ctx* ctx = m->ctx;
   GG_CUDA(cudaSetDevice(ctx->device));
   const int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= (m->dim == 3 ? MAX_NQ : MAX_NQ_NORMS), GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   const int64_t n = m->n_cells * nq * nq;
   GG_REQUIRE(gg_vec_size(out) == (mode == 0 ? 2 * n : n), GG_ERR_INVALID, "output vector has the wrong length");
   if (n == 0) return GG_OK;

@@ -8,7 +8,10 @@
 namespace gg {
 
 constexpr int MAX_NB = 5;   // 1-D basis size (order <= 4)
-constexpr int MAX_NQ = 16;  // 1-D quadrature points (degree <= 31)
+constexpr int MAX_NQ = 16;  // 1-D quadrature points of the form kernels (degree <= 31: fixed-size tables)
+// error measures, integrals and point sets work from dynamically sized tabulations: the Stokes drivers measure errors with
+// Measure(., 2 degree) = 36 and Measure(., 3 degree) = 54 (test/SurfaceStokes/VectorLaplacian2D.jl:30-33, SurfaceStokes_TaylorHood.jl:45-48)
+constexpr int MAX_NQ_NORMS = 32;  // degree <= 63
 
 // nq = ceil((degree+1)/2)
 int num_points_1d(int degree);

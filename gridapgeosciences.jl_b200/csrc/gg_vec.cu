@@ -448,7 +448,7 @@ int gg_h1_seminorm_sq(gg_space* s, gg_vec* e, int32_t degree, double* out) {
   GG_REQUIRE(s->kind == GG_SPACE_CGV && s->mesh->dim == 2, GG_ERR_UNSUPPORTED, "the H1 seminorm is implemented for vector H1 spaces on the 2-D sphere");
   GG_REQUIRE(gg_vec_size(e) == s->n_free, GG_ERR_INVALID, "vector has the wrong length");
   const int nq = num_points_1d(degree);
-  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
+  GG_REQUIRE(degree >= 0 && nq <= MAX_NQ_NORMS, GG_ERR_UNSUPPORTED, "quadrature degree out of range");
   GG_CUDA(cudaSetDevice(s->mesh->ctx->device));
   *out = vec_h1_seminorm_sq(s, e->d.p, nq);
   GG_API_END

@@ -16,9 +16,9 @@ from oracle.spaces import CGSpace
 from test_oracle_surface_stokes import grad_pX, grad_uX, pX, uX, uX_sym
 
 pytestmark = pytest.mark.gpu
-# the reference measures the errors with Measure(Ω, 2 degree) = 36 / Measure(Ω, 3 degree) = 54; the library's rules stop at degree
-# 31 (16 points per direction), used here on both sides (the integrand is a Q2 polynomial times the smooth metric)
-ERR_DEGREE = 31
+# the reference measures the errors with Measure(Ω, 2 degree) = 36 (VectorLaplacian2D.jl:30-33) and Measure(Ω, 3 degree) = 54
+# (SurfaceStokes_TaylorHood.jl:45-48): the same rules on both sides
+ERR_DEGREE_VL, ERR_DEGREE_ST = 36, 54
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -111,12 +111,12 @@ def test_vector_laplacian_driver_converges(gg):
         op = gg.AffineFEOperator(gg.VectorLaplacian(dΩ), gg.VectorSource(dΩ, rhs), V, V)
         uh = spla.spsolve(op.get_matrix().to_scipy().tocsc(), op.get_vector().get())
         e = gg.interpolate(uX, V).get() - uh
-        errs.append(gg.norm(e, V, ERR_DEGREE))
+        errs.append(gg.norm(e, V, ERR_DEGREE_VL))
         if lvl == 2:
             el2, eh1, _, _ = ss.vector_laplacian_2d(CubedSphereMesh2D(4), p, uX, rhs=lambda q: 2.0 * vh.contravariant(q.mesh, q, uX),
-                                                        error_degree=ERR_DEGREE)
+                                                        error_degree=ERR_DEGREE_VL)
             assert abs(errs[-1] - el2) <= 1e-8 * el2
-            assert abs(np.hypot(errs[-1], gg.h1_seminorm(e, V, ERR_DEGREE)) - eh1) <= 1e-8 * eh1
+            assert abs(np.hypot(errs[-1], gg.h1_seminorm(e, V, ERR_DEGREE_VL)) - eh1) <= 1e-8 * eh1
     assert np.polyfit(np.log10([1 / 2.0**lvl for lvl in levels]), np.log10(errs), 1)[0] >= p
 
 
@@ -131,7 +131,7 @@ def test_surface_stokes_driver_converges(gg):
         model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=2**lvl)
         V, Q = spaces(gg, model, p)
         Ω = gg.Triangulation(model)
-        dΩ, dΩe = gg.Measure(Ω, degree), gg.Measure(Ω, ERR_DEGREE)
+        dΩ, dΩe = gg.Measure(Ω, degree), gg.Measure(Ω, ERR_DEGREE_ST)
         u_c = gg.contravariant_components(dΩ, uX).get()
         rhs = (2.0 * nu + alpha) * u_c + gg.surface_gradient(dΩ, grad_pX).get()
         sigma = gg.surface_divergence(dΩ, uX, grad_uX)
@@ -143,7 +143,7 @@ def test_surface_stokes_driver_converges(gg):
         x = spla.spsolve(sp.bmat([[Auu, -B.T], [B, None]]).tocsc(), np.concatenate([bu, bq]))
         uh, ph = x[: V.num_free_dofs], x[V.num_free_dofs:]
         e = gg.interpolate(uX, V).get() - uh
-        eh1.append(np.hypot(gg.norm(e, V, ERR_DEGREE), gg.h1_seminorm(e, V, ERR_DEGREE)))
+        eh1.append(np.hypot(gg.norm(e, V, ERR_DEGREE_ST), gg.h1_seminorm(e, V, ERR_DEGREE_ST)))
         # ZeroMeanFESpace: solution and interpolant are both shifted to zero chart mean
         p_int = gg.interpolate(pX, Q)
         pi = p_int.get()
@@ -152,7 +152,7 @@ def test_surface_stokes_driver_converges(gg):
         ep_fixed = (d_int - gg.chart_mean(pi, Q, dirichlet=d_int)) - (0.0 - gg.chart_mean(ph, Q))
         epl2.append(gg.l2_error(ep, Q, dΩe, dirichlet=ep_fixed))
         if lvl == 2:
-            r_h1, r_p, _ = ss.surface_stokes(CubedSphereMesh2D(4), p, uX, pX, uX_sym, grad_pX, grad_uX, error_degree=ERR_DEGREE)
+            r_h1, r_p, _ = ss.surface_stokes(CubedSphereMesh2D(4), p, uX, pX, uX_sym, grad_pX, grad_uX, error_degree=ERR_DEGREE_ST)
             assert abs(eh1[-1] - r_h1) <= 1e-8 * r_h1 and abs(epl2[-1] - r_p) <= 1e-8 * r_p
     h = np.log10([1 / 2.0**lvl for lvl in levels])
     assert np.polyfit(h, np.log10(eh1), 1)[0] >= p
