@@ -605,12 +605,18 @@ def assembly_limiter(leg, roofline, world):
     ksum = sum(v for v in k.values() if v)
     ghost = leg["cells_local_incl_ghosts"] / max(leg["owned"], 1) - 1.0
     gap = leg["ms_per_step"] - ksum
-    if gap > 0.25 * leg["ms_per_step"]:
+    ctas = leg["cells_local_incl_ghosts"] / 128.0
+    if ctas < 3 * 148:
+        what = (f"less than one wave of CTAs: the slice is {ctas:.0f} 128-cell CTAs for 444 CTA slots (3 per SM), so the element kernel "
+                f"lasts one CTA lifetime (its warps are latency-bound) instead of scaling with the cell count; the 3 kernels of a step "
+                f"sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step (L2 flushed before every step)")
+    elif gap > 0.25 * leg["ms_per_step"]:
         what = f"launch / tail latency: the kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step"
     elif ghost > 0.1:
         what = f"redundant ghost-layer cells: {100 * ghost:.1f} % more cells than owned"
     else:
-        what = "the same kernels as at N=1 (FP64 pipe + CSR fill), on 1/N of the cells"
+        what = (f"the same kernels as at N=1 (FP64 pipe + CSR fill) on 1/N of the cells; {ctas / 444:.1f} waves of CTAs (wave quantisation) "
+                f"and {100 * ghost:.1f} % ghost cells")
     return {"what": what, "kernel_ms_sum": ksum, "ghost_cell_overhead": ghost, "cells_per_sm": leg["cells_local_incl_ghosts"] / 148.0}
 
 

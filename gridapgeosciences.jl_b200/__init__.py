@@ -294,9 +294,13 @@ class PeerWindow:
 
 
 def window_doubles(plan, p_fe):
-    """Exchange-slot size that fits every space of the RT_p x DG_p / CG_{p+1} steppers on this plan."""
+    """Exchange-slot size that fits every space of the RT_p x DG_p / CG_{p+1} steppers on this plan (and the vector H1 space
+    of order max(p, 1))."""
     cap = 0
-    for kind, order in ((_lib.SPACE_RT, p_fe), (_lib.SPACE_DG, p_fe), (_lib.SPACE_CG, p_fe + 1)):
+    spaces = [(_lib.SPACE_RT, p_fe), (_lib.SPACE_DG, p_fe), (_lib.SPACE_CG, p_fe + 1)]
+    if max(p_fe, 1) <= 2:
+        spaces.append((_lib.SPACE_CGV, max(p_fe, 1)))
+    for kind, order in spaces:
         cap = max(cap, plan.space(kind, order)["slot_capacity"])
     return cap
 

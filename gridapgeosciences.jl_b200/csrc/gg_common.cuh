@@ -210,6 +210,10 @@ struct gg_space {
   // 2x2 change-of-basis blocks [n_cells][n_nodes][2][2] (gg_vec.cu)
   std::vector<int32_t> cob_master_cell;
   std::vector<int8_t> cob_master_node;
+  // the same information as geometry, so that a rank's sub-model does not need the master cell itself (it may lie beyond the
+  // ghost layer): panel of the master (-1: identity block) and the chart point of the node in the master's chart
+  std::vector<int32_t> cob_master_panel;
+  std::vector<double> cob_master_point;
   gg::DevBuf<double> d_cob;
   // groups of consecutively numbered free DOFs owned by one mesh entity: (first dof, number of groups, dofs per group);
   // empty for caller-numbered spaces (the preconditioner then degenerates to point Jacobi)

@@ -49,7 +49,7 @@ SpacePlan& plan_space(gg_plan* P, int kind, int order) {
   const int key = kind * 16 + order;
   auto it = P->spaces.find(key);
   if (it != P->spaces.end()) return *it->second;
-  GG_REQUIRE(kind == GG_SPACE_CG || kind == GG_SPACE_DG || kind == GG_SPACE_RT, GG_ERR_INVALID, "unknown space kind");
+  GG_REQUIRE(kind == GG_SPACE_CG || kind == GG_SPACE_DG || kind == GG_SPACE_RT || kind == GG_SPACE_CGV, GG_ERR_INVALID, "unknown space kind");
   std::unique_ptr<SpacePlan> sp(new SpacePlan);
   gg_mesh* gm = P->gmesh.get();
   gg_space G;
@@ -97,6 +97,23 @@ SpacePlan& plan_space(gg_plan* P, int kind, int order) {
       sp->cell_dofs[i * m + j] = g2l[G.cell_dofs[lc[i] * m + j]];
       if (!G.cell_signs.empty()) sp->signs[i * m + j] = G.cell_signs[lc[i] * m + j];
     }
+  // vector H1: the change of basis of a local cell needs the chart of the entity's master cell -- the surrounding cell with the
+  // largest GLOBAL id (src/FESpaces/GradConformingFESpaces.jl:14-19), which may lie beyond the ghost layer.  The reference finds
+  // local masters and repairs the ghost cells' matrices with a `consistent!` of the flattened per-cell matrices
+  // (src/Distributed/GradConformingFESpaces.jl:7-35); here every rank holds the global mesh on the host (the plan is a pure
+  // function of (n, nparts)), so the exact master geometry of every local (cell, node) is copied from the global space: same
+  // blocks as the serial space, no exchange
+  if (kind == GG_SPACE_CGV) {
+    const int nn = m / 2;
+    sp->cob_master_panel.resize(lc.size() * nn);
+    sp->cob_master_point.resize(lc.size() * nn * 2);
+    for (size_t i = 0; i < lc.size(); ++i)
+      for (int a = 0; a < nn; ++a) {
+        sp->cob_master_panel[i * nn + a] = G.cob_master_panel[lc[i] * nn + a];
+        sp->cob_master_point[(i * nn + a) * 2] = G.cob_master_point[(lc[i] * nn + a) * 2];
+        sp->cob_master_point[(i * nn + a) * 2 + 1] = G.cob_master_point[(lc[i] * nn + a) * 2 + 1];
+      }
+  }
   // entity block classes of the local numbering (the DOFs of one entity stay consecutive under the restriction)
   for (const auto& bc : G.blocks) {
     const int64_t lo = bc.start, hi = bc.start + bc.count * bc.size;
@@ -136,6 +153,8 @@ void space_from_plan(gg_mesh* m, int kind, int order, gg_space* s) {
   s->n_free = (int64_t)sp.l2g.size();
   s->cell_dofs = sp.cell_dofs;
   s->cell_signs = sp.signs;
+  s->cob_master_panel = sp.cob_master_panel;
+  s->cob_master_point = sp.cob_master_point;
   s->blocks.clear();
   for (const auto& b : sp.blocks) s->blocks.push_back({b.start, b.count, b.size});
   s->dist.reset(new gg_space::Dist);

@@ -14,6 +14,8 @@ struct SpacePlan {
   std::vector<int32_t> owner;       // owner rank of every local DOF
   std::vector<int32_t> cell_dofs;   // [n_local_cells][mloc] local ids
   std::vector<int8_t> signs;        // RT: signs of the GLOBAL numbering
+  std::vector<int32_t> cob_master_panel;   // vector H1: master panel / chart point of every local (cell, node)
+  std::vector<double> cob_master_point;
   struct Block { int64_t start, count; int size; };
   std::vector<Block> blocks;
   std::vector<int32_t> peers, send_ptr, send_idx, send_remote, recv_ptr, recv_idx;

@@ -718,6 +718,9 @@ void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_spac
       }
     s->cob_master_cell.assign((size_t)nc * nn, -1);
     s->cob_master_node.assign((size_t)nc * nn, 0);
+    s->cob_master_panel.assign((size_t)nc * nn, -1);
+    s->cob_master_point.assign((size_t)nc * nn * 2, 0.0);
+    std::vector<int32_t> l2x_v = quad_local_to_lex(order);
     for (int64_t c = 0; c < nc; ++c)
       for (int a = 0; a < 4 + 4 * ne1; ++a) {
         const bool vert = a < 4;
@@ -729,7 +732,14 @@ void space_builtin_host(gg_mesh* m, int kind, int order, int constraint, gg_spac
         for (int j = 0; j < 4; ++j) if ((vert ? m->cell_nodes[mc * 4 + j] : m->cell_edges[mc * 4 + j]) == ent) fm = j;
         GG_REQUIRE(fm >= 0, GG_ERR_INVALID, "inconsistent topology");
         s->cob_master_cell[c * nn + a] = mc;
-        s->cob_master_node[c * nn + a] = (int8_t)(vert ? fm : 4 + fm * ne1 + k);
+        const int am = vert ? fm : 4 + fm * ne1 + k;
+        s->cob_master_node[c * nn + a] = (int8_t)am;
+        // chart point of the node in the master cell (axis-aligned chart box, Gridap vertex order BL, BR, TL, TR)
+        const double* q = &m->chart_coords[(size_t)mc * 8];
+        const double rx = (double)(l2x_v[am] % (order + 1)) / order, ry = (double)(l2x_v[am] / (order + 1)) / order;
+        s->cob_master_panel[c * nn + a] = m->cell_to_chart[mc];
+        s->cob_master_point[(c * nn + a) * 2] = q[0] + rx * (q[2] - q[0]);
+        s->cob_master_point[(c * nn + a) * 2 + 1] = q[1] + ry * (q[5] - q[1]);
       }
     s->blocks.push_back({0, Nv, 2});
     if (order > 1) {

@@ -19,20 +19,19 @@ static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) 
 // one thread per (cell, node): the 2x2 block, row = component in this cell's chart, column = component in the master's chart
 __global__ void k_vec_cob(int64_t nc, int nn, const double* __restrict__ ref, const double* __restrict__ x0,
                           const double* __restrict__ y0, const double* __restrict__ hx, const double* __restrict__ hy,
-                          const int32_t* __restrict__ chart, double radius, const int32_t* __restrict__ mcell,
-                          const int8_t* __restrict__ mnode, double* __restrict__ cob) {
+                          const int32_t* __restrict__ chart, double radius, const int32_t* __restrict__ mpanel,
+                          const double* __restrict__ mpoint, double* __restrict__ cob) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nc * nn) return;
   const int64_t c = t / nn;
   const int a = (int)(t - c * nn);
   double* o = cob + 4 * t;
-  const int32_t mc = mcell[t];
-  if (mc < 0) { o[0] = 1.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1.0; return; }
-  const int am = mnode[t];
+  const int32_t mp = mpanel[t];
+  if (mp < 0) { o[0] = 1.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1.0; return; }
   double JS[2][3], JM[2][3];
   const double as = tan(fma(hx[c], ref[2 * a], x0[c])), bs = tan(fma(hy[c], ref[2 * a + 1], y0[c]));
   csphere_jacobian(chart[c], as, bs, radius, JS);
-  csphere_jacobian(chart[mc], tan(fma(hx[mc], ref[2 * am], x0[mc])), tan(fma(hy[mc], ref[2 * am + 1], y0[mc])), radius, JM);
+  csphere_jacobian(mp, tan(mpoint[2 * t]), tan(mpoint[2 * t + 1]), radius, JM);
   const Metric2 m = csphere_metric_terms(as, bs, radius);
   // pinvJ = ginv . J  (src/Helpers/Operators.jl:16-24 for the 2x3 covariant basis)
 #pragma unroll
@@ -57,8 +56,12 @@ void vec_space_finish(gg_space* s) {
   for (int a = 0; a < nn; ++a) { ref[2 * a] = (double)(l2x[a] % nb) / s->order; ref[2 * a + 1] = (double)(l2x[a] / nb) / s->order; }
   DevBuf<double> dref;
   DevBuf<int32_t> dmc;
-  DevBuf<int8_t> dmn;
-  dref.upload(ref, st); dmc.upload(s->cob_master_cell, st); dmn.upload(s->cob_master_node, st);
+  DevBuf<double> dmn;
+  if (s->cob_master_panel.size() != (size_t)nc * nn) {   // caller-numbered space without master data: identity blocks
+    s->cob_master_panel.assign((size_t)nc * nn, -1);
+    s->cob_master_point.assign((size_t)nc * nn * 2, 0.0);
+  }
+  dref.upload(ref, st); dmc.upload(s->cob_master_panel, st); dmn.upload(s->cob_master_point, st);
   s->d_cob.alloc((size_t)nc * nn * 4);
   if (nc) {
     k_vec_cob<<<nblk(nc * nn, 128), 128, 0, st>>>(nc, nn, dref.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p, m->d_chart.p, m->radius,
@@ -322,9 +325,10 @@ __global__ void k_vec_error_cells(int64_t nc, int nq, int nn, const double* __re
                                   const double* __restrict__ val, const double* __restrict__ x0, const double* __restrict__ y0,
                                   const double* __restrict__ hx, const double* __restrict__ hy, double radius,
                                   const double* __restrict__ cob, const int32_t* __restrict__ dofs, const double* __restrict__ U,
-                                  const double* __restrict__ fq, double* __restrict__ sums) {
+                                  const double* __restrict__ fq, const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  if (cell_owned && !cell_owned[c]) { sums[c] = 0.0; return; }   // partitioned model: ghost cells are counted by their owner
   const double HX = hx[c], HY = hy[c];
   const int Q = nq * nq;
   double acc = 0.0;
@@ -358,7 +362,7 @@ double vec_error_sq(gg_space* s, const double* U, const double* fq, int nq) {
   auto T = get_tab(ctx, GG_SPACE_CG, s->order, nq);
   DevBuf<double> sums(nc), total(1);
   k_vec_error_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, nn, T->xi.p, T->w.p, T->val.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
-                                                   m->radius, s->d_cob.p, s->d_cell_dofs.p, U, fq, sums.p);
+                                                   m->radius, s->d_cob.p, s->d_cell_dofs.p, U, fq, m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;
   GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
   DevBuf<uint8_t> tmp(tb);
@@ -376,9 +380,10 @@ __global__ void k_vec_h1_cells(int64_t nc, int nq, int nn, const double* __restr
                                const double* __restrict__ der, const double* __restrict__ x0, const double* __restrict__ y0,
                                const double* __restrict__ hx, const double* __restrict__ hy, double radius,
                                const double* __restrict__ cob, const int32_t* __restrict__ dofs, const double* __restrict__ U,
-                               double* __restrict__ sums) {
+                               const uint8_t* __restrict__ cell_owned, double* __restrict__ sums) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
+  if (cell_owned && !cell_owned[c]) { sums[c] = 0.0; return; }
   const double HX = hx[c], HY = hy[c];
   double acc = 0.0;
   for (int q2 = 0; q2 < nq; ++q2) {
@@ -415,7 +420,7 @@ double vec_h1_seminorm_sq(gg_space* s, const double* U, int nq) {
   auto T = get_tab(ctx, GG_SPACE_CG, s->order, nq);
   DevBuf<double> sums(nc), total(1);
   k_vec_h1_cells<<<nblk(nc, 128), 128, 0, st>>>(nc, nq, nn, T->xi.p, T->w.p, T->der.p, m->d_x0.p, m->d_y0.p, m->d_hx.p, m->d_hy.p,
-                                                m->radius, s->d_cob.p, s->d_cell_dofs.p, U, sums.p);
+                                                m->radius, s->d_cob.p, s->d_cell_dofs.p, U, m->d_cell_owned.n ? m->d_cell_owned.p : nullptr, sums.p);
   size_t tb = 0;
   GG_CUDA(cub::DeviceReduce::Sum(nullptr, tb, sums.p, total.p, (int)nc, st));
   DevBuf<uint8_t> tmp(tb);

@@ -132,6 +132,35 @@ def run_checks(gg, ctx, rank, world, n, p):
         assert comm.error_epoch() == 0
         del stt, sttf
 
+    # -- vector-valued H1 space with the panel-interface change of basis on the partitioned model
+    #    (src/Distributed/GradConformingFESpaces.jl:7-35): the blocks of every local cell -- ghost cells included, whose master cell
+    #    may lie beyond the ghost layer -- equal those of the serial space; interpolation, element matrices, norms and consistent!
+    pv = max(p, 1)
+    if pv <= 2:
+        W_ = gg.TestFESpace(local_model, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, pv), conformity="H1")
+        Wf = gg.TestFESpace(full_model, gg.ReferenceFE(gg.lagrangian, gg.VectorValue, pv), conformity="H1")
+        lw, ow = gg.global_dof_ids(W_)
+        lw = lw - 1
+        cells = plan.local_cells()
+        Cl, Cf = gg.change_of_basis(W_), gg.change_of_basis(Wf)
+        e_cob = float(np.abs(Cl - Cf[cells]).max())
+        assert e_cob < 1e-14, f"vector H1: change-of-basis blocks of the sub-model differ by {e_cob}"
+        assert np.abs(Cf - np.eye(2)).max() > 0.1                       # the blocks are not trivially the identity
+        w0, w0f = gg.interpolate(velocity, W_).get(), gg.interpolate(velocity, Wf).get()
+        assert rel(w0, w0f[lw]) < 1e-13
+        dl, df = gg.Measure(gg.Triangulation(local_model), 4 * pv), gg.Measure(gg.Triangulation(full_model), 4 * pv)
+        Kl, Kf = gg.element_matrices(gg.VectorMass(dl), W_, W_), gg.element_matrices(gg.VectorMass(df), Wf, Wf)
+        assert rel(Kl, Kf[cells]) < 1e-13
+        nv = torch.tensor([gg.norm(w0, W_, 4 * pv) ** 2], device=dev, dtype=torch.float64)
+        dist.all_reduce(nv)
+        assert abs(nv[0].item() - gg.norm(w0f, Wf, 4 * pv) ** 2) < 1e-12 * nv[0].item()
+        gw = np.sin(0.2 * np.arange(lw.max() + 1)) - 0.5
+        vw = gg.DeviceVector.from_numpy(ctx, np.where(ow == rank, gw[lw], 123.0))
+        gg.consistent(vw, W_)
+        assert (vw.get() == gw[lw]).all(), "consistent! on the vector H1 space did not reproduce the owner values"
+    else:
+        e_cob = None
+
     # -- DG upwind advection: ghost cells of every stage state filled through peer memory
     def wind(X):
         return np.stack([-X[..., 1], X[..., 0], 0.2 * X[..., 0]], -1)
@@ -165,7 +194,7 @@ def run_checks(gg, ctx, rank, world, n, p):
     dist.barrier()
     return {"world": world, "n": n, "p": p, "wave": e_w, "swe": e_s, "pv": e_q, "advection": e_a,
             "thermal_swe": e_t if p >= 1 else None, "pcg_iters": int(its), "pcg_iters_single_gpu": int(itf),
-            "pcg_iters_equal": bool(its == itf), "solves": int(sol), "consistent_exact": True}
+            "pcg_iters_equal": bool(its == itf), "solves": int(sol), "consistent_exact": True, "vector_h1_cob": e_cob}
 
 
 def main():
