@@ -854,7 +854,11 @@ def main():
             for (pn, pp) in ((6, 1), (5, 2)):
                 r = dist_worker.run_checks(gg, ctx, rank, world, pn, pp)
                 dp[f"n{pn}_p{pp}"] = r
-            line["dist_parity"] = {"ok": True, "tolerances": {"wave": 1e-10, "swe": 1e-9, "pv": 1e-8, "thermal_swe": 1e-9, "advection": 1e-12},
+            try:
+                shell_par = dist_worker.run_shell_checks(gg, ctx, rank, world)
+            except Exception as ex:
+                shell_par = {"error": str(ex)[-300:]}
+            line["dist_parity"] = {"ok": "error" not in shell_par, "shell_p8est": shell_par, "tolerances": {"wave": 1e-10, "swe": 1e-9, "pv": 1e-8, "thermal_swe": 1e-9, "advection": 1e-12},
                                    "wave": max(v["wave"] for v in dp.values()), "swe": max(v["swe"] for v in dp.values()),
                                    "advection": max(v["advection"] for v in dp.values()),
                                    "pcg_iters_equal": all(v["pcg_iters_equal"] for v in dp.values()),

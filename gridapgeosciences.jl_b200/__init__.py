@@ -208,11 +208,17 @@ class PartitionPlan:
     (src/Distributed/AtlasDistributedDiscreteModels.jl:20-73): owned cell range, ghost layer, and per FE space the
     local -> global DOF map, DOF owners and exchange lists.  Pure host computation (no GPU, no communication)."""
 
-    def __init__(self, n, nparts, part, radius=1.0):
+    def __init__(self, n, nparts, part, radius=1.0, thickness=None, ordering=0, n_layers=0):
+        """thickness given: the 3-D shell (AtlasOctreeDistributedDiscreteModel on CubedSphereWithThicknessMesh; ordering 2 = the
+        p8est cell order, equal-count chunks of the space-filling curve)."""
         self.lib = _lib.load()
         self.n, self.nparts, self.part, self.radius = int(n), int(nparts), int(part), float(radius)
         h = C.c_void_p()
-        _lib.check(self.lib.gg_plan_create(self.n, self.radius, self.nparts, self.part, C.byref(h)))
+        if thickness is not None:
+            _lib.check(self.lib.gg_plan_create_shell(self.n, int(n_layers), self.radius, float(thickness), int(ordering), self.nparts,
+                                                     self.part, C.byref(h)))
+        else:
+            _lib.check(self.lib.gg_plan_create(self.n, self.radius, self.nparts, self.part, C.byref(h)))
         self.h = h
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_plan_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))

@@ -32,17 +32,35 @@ namespace gg {
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 static std::vector<int64_t> ghost_cells_of(const gg_mesh* m, int64_t first, int64_t last) {
+  const int nv = m->dim == 3 ? 8 : 4;
+  const std::vector<int32_t>& cn = m->dim == 3 ? m->cell_nodes8 : m->cell_nodes;
   std::vector<uint8_t> touched(m->n_nodes, 0);
   for (int64_t c = first; c < last; ++c)
-    for (int v = 0; v < 4; ++v) touched[m->cell_nodes[c * 4 + v]] = 1;
+    for (int v = 0; v < nv; ++v) touched[cn[c * nv + v]] = 1;
   std::vector<int64_t> out;
   for (int64_t c = 0; c < m->n_cells; ++c) {
     if (c >= first && c < last) continue;
     bool near = false;
-    for (int v = 0; v < 4; ++v) near = near || touched[m->cell_nodes[c * 4 + v]];
+    for (int v = 0; v < nv; ++v) near = near || touched[cn[c * nv + v]];
     if (near) out.push_back(c);
   }
   return out;
+}
+
+static void plan_partition(gg_plan* P) {
+  const int64_t Nc = P->gmesh->n_cells;
+  const int nparts = P->nparts;
+  GG_REQUIRE(Nc >= nparts, GG_ERR_INVALID, "fewer cells than parts");
+  P->first.resize(nparts); P->last.resize(nparts); P->cells.resize(nparts);
+  for (int r = 0; r < nparts; ++r) {
+    GG_REQUIRE(gg_partition_range(Nc, nparts, r, &P->first[r], &P->last[r]) == GG_OK, GG_ERR_INVALID, "partition range");
+    std::vector<int64_t> ghosts = ghost_cells_of(P->gmesh.get(), P->first[r], P->last[r]);
+    auto& L = P->cells[r];
+    L.reserve(P->last[r] - P->first[r] + ghosts.size());
+    for (int64_t c = P->first[r]; c < P->last[r]; ++c) L.push_back(c);
+    L.insert(L.end(), ghosts.begin(), ghosts.end());
+    std::sort(L.begin(), L.end());
+  }
 }
 
 SpacePlan& plan_space(gg_plan* P, int kind, int order) {
@@ -261,18 +279,22 @@ int gg_plan_create(int n, double radius, int nparts, int part, gg_plan** out) {
   std::unique_ptr<gg_plan> P(new gg_plan);
   P->n = n; P->radius = radius; P->nparts = nparts; P->part = part;
   P->gmesh.reset(build_cubed_sphere(nullptr, n, radius));
-  const int64_t Nc = P->gmesh->n_cells;
-  GG_REQUIRE(Nc >= nparts, GG_ERR_INVALID, "fewer cells than parts");
-  P->first.resize(nparts); P->last.resize(nparts); P->cells.resize(nparts);
-  for (int r = 0; r < nparts; ++r) {
-    GG_REQUIRE(gg_partition_range(Nc, nparts, r, &P->first[r], &P->last[r]) == GG_OK, GG_ERR_INVALID, "partition range");
-    std::vector<int64_t> ghosts = ghost_cells_of(P->gmesh.get(), P->first[r], P->last[r]);
-    auto& L = P->cells[r];
-    L.reserve(P->last[r] - P->first[r] + ghosts.size());
-    for (int64_t c = P->first[r]; c < P->last[r]; ++c) L.push_back(c);
-    L.insert(L.end(), ghosts.begin(), ghosts.end());
-    std::sort(L.begin(), L.end());
-  }
+  plan_partition(P.get());
+  *out = P.release();
+  GG_API_END
+}
+
+int gg_plan_create_shell(int n, int n_layers, double radius, double thickness, int ordering, int nparts, int part, gg_plan** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(out, GG_ERR_INVALID, "null output");
+  GG_REQUIRE(n >= 1 && radius > 0 && thickness > 0 && n_layers >= 0, GG_ERR_INVALID, "bad mesh parameters");
+  GG_REQUIRE(ordering == 0 || ordering == 2, GG_ERR_INVALID, "shell orderings: 0 (lexicographic) or 2 (p8est Morton)");
+  if (ordering == 2) GG_REQUIRE((n & (n - 1)) == 0 && (n_layers == 0 || n_layers == n), GG_ERR_INVALID, "the p8est ordering needs n = n_layers = 2^l");
+  GG_REQUIRE(nparts >= 1 && nparts <= GG_MAX_RANKS && part >= 0 && part < nparts, GG_ERR_INVALID, "bad partition request (at most 16 parts)");
+  std::unique_ptr<gg_plan> P(new gg_plan);
+  P->n = n; P->radius = radius; P->nparts = nparts; P->part = part;
+  P->gmesh.reset(build_cubed_sphere_shell(nullptr, n, n_layers > 0 ? n_layers : n, radius, thickness, ordering));
+  plan_partition(P.get());
   *out = P.release();
   GG_API_END
 }
@@ -420,6 +442,27 @@ int gg_mesh_partitioned(gg_ctx* ctx, gg_plan* p, gg_comm* comm, gg_mesh** out) {
   GG_CUDA(cudaSetDevice(ctx->device));
   const gg_mesh* g = p->gmesh.get();
   const auto& L = p->cells[p->part];
+  if (g->dim == 3) {
+    // rank-local sub-model of the shell: the listed hexahedra (global node ids kept; the DOF numbering of spaces comes from the plan)
+    std::unique_ptr<gg_mesh> s3(new gg_mesh);
+    s3->ctx = ctx; s3->dim = 3; s3->n = g->n; s3->n_layers = g->n_layers; s3->radius = g->radius; s3->thickness = g->thickness;
+    s3->n_cells = (int64_t)L.size(); s3->n_nodes = g->n_nodes;
+    s3->cell_nodes8.resize(L.size() * 8); s3->cell_to_chart.resize(L.size()); s3->cell_col.resize(L.size()); s3->cell_layer.resize(L.size());
+    s3->cell_owned.resize(L.size());
+    for (size_t i = 0; i < L.size(); ++i) {
+      const int64_t c = L[i];
+      std::copy(&g->cell_nodes8[c * 8], &g->cell_nodes8[c * 8] + 8, &s3->cell_nodes8[i * 8]);
+      s3->cell_to_chart[i] = g->cell_to_chart[c]; s3->cell_col[i] = g->cell_col[c]; s3->cell_layer[i] = g->cell_layer[c];
+      s3->cell_owned[i] = c >= p->first[p->part] && c < p->last[p->part];
+    }
+    s3->surface.reset(build_cubed_sphere(ctx, g->n, g->radius, 0));
+    s3->d_col.upload(s3->cell_col, ctx->stream); s3->d_layer.upload(s3->cell_layer, ctx->stream);
+    s3->d_chart.upload(s3->cell_to_chart, ctx->stream); s3->d_cell_owned.upload(s3->cell_owned, ctx->stream);
+    GG_CUDA(cudaStreamSynchronize(ctx->stream));
+    s3->plan = p; s3->comm = comm;
+    *out = s3.release();
+    return GG_OK;
+  }
   std::unique_ptr<gg_mesh> s(new gg_mesh);
   s->ctx = ctx; s->dim = 2; s->n = 0; s->radius = g->radius;
   s->n_cells = (int64_t)L.size(); s->n_nodes = g->n_nodes;

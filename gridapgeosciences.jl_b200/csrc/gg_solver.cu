@@ -17,6 +17,7 @@
 // an extra barrier.
 #include <cooperative_groups.h>
 #include "gg_common.cuh"
+#include "gg_dist_host.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -93,14 +94,19 @@ __device__ __forceinline__ double grid_total(const double* partials, int nblocks
   return bc;
 }
 
-// x = A^-1 (scale_b * b) by block-Jacobi PCG starting from x = 0 (the RK stages need -r on the right-hand side)
+// x = A^-1 (scale_b * b) by block-Jacobi PCG starting from x = 0 (the RK stages need -r on the right-hand side).
+// DIST: the matrix holds the rows of a rank's sub-model (owned rows complete thanks to the ghost cells); dot products run over
+// the owned rows and are all-reduced through the peer windows, the owner -> ghost update of z rides on the same round (as in
+// the condensed solver, gg_ebe.cu), so ghost p = z + beta p stays consistent without an exchange of its own: two rounds per
+// iteration, no host, no NCCL.
+template <bool DIST>
 __global__ void __launch_bounds__(256)
 k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                  const double* __restrict__ vals, const int32_t* __restrict__ bstart, const uint8_t* __restrict__ bsize,
                  const int32_t* __restrict__ rowoff, const double* __restrict__ binv, const double* __restrict__ b,
                  double scale_b, double* __restrict__ x, double* ra, double* rb, double* __restrict__ z,
                  double* __restrict__ p, double* __restrict__ Ap, double* __restrict__ partials, double rtol,
-                 int max_iter, double* __restrict__ stats) {
+                 int max_iter, double* __restrict__ stats, DistDev d) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sh[32];
   const int nb = gridDim.x;
@@ -111,10 +117,12 @@ k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* _
   double* P2 = partials + 2 * nb;  // [nb]
   double* r_old = ra;
   double* r_new = rb;
+  unsigned long long epoch = DIST ? d.win[d.rank]->epoch : 0ull;
 
   // r = scale_b b, z = Binv r, p = z, x = 0; rz, bb
   double lrz = 0.0, lbb = 0.0;
   for (int64_t i = tid; i < n; i += nth) {
+    if (DIST && !d.owned[i]) { x[i] = 0.0; r_old[i] = 0.0; r_new[i] = 0.0; z[i] = 0.0; p[i] = 0.0; Ap[i] = 0.0; continue; }
     const int s = bstart[i], m = bsize[i];
     const double* bi_row = binv + rowoff[i];
     double zi = 0.0;
@@ -123,13 +131,21 @@ k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* _
     x[i] = 0.0; r_old[i] = ri; z[i] = zi; p[i] = zi;
     lrz = fma(ri, zi, lrz);
     lbb = fma(ri, ri, lbb);
+    if (DIST && d.owned[i] == 2) dist_push_row(d, epoch, i, zi);
   }
   lrz = block_sum(lrz, sh);
   lbb = block_sum(lbb, sh);
   if (threadIdx.x == 0) { P0[blockIdx.x] = lrz; P1[blockIdx.x] = lbb; }
   grid.sync();
   double rz = grid_total(P0, nb, sh);
-  const double bb = grid_total(P1, nb, sh);
+  double bb = grid_total(P1, nb, sh);
+  if (DIST) {
+    double v[2] = {rz, bb};
+    dist_allreduce<2>(grid, d, epoch, v);
+    rz = v[0]; bb = v[1];
+    dist_unpack(d, epoch, p, tid, nth, n);     // ghost p = ghost z
+    grid.sync();
+  }
   int it = 0;
   double rr = bb;
   if (bb > 0.0) {
@@ -138,6 +154,7 @@ k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* _
       // Ap = A p ; pAp
       double lpap = 0.0;
       for (int64_t i = tid; i < n; i += nth) {
+        if (DIST && !d.owned[i]) continue;
         double acc = 0.0;
         for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) acc = fma(vals[k], p[colind[k]], acc);
         Ap[i] = acc;
@@ -146,10 +163,17 @@ k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* _
       lpap = block_sum(lpap, sh);
       if (threadIdx.x == 0) P2[blockIdx.x] = lpap;
       grid.sync();
-      const double alpha = rz / grid_total(P2, nb, sh);
+      double pap = grid_total(P2, nb, sh);
+      if (DIST) {
+        double v[1] = {pap};
+        dist_allreduce<1>(grid, d, epoch, v);
+        pap = v[0];
+      }
+      const double alpha = rz / pap;
       // x += alpha p ; r_new = r_old - alpha Ap ; z = Binv r_new (recomputing the block's residuals: no barrier needed)
       double lrz2 = 0.0, lrr = 0.0;
       for (int64_t i = tid; i < n; i += nth) {
+        if (DIST && !d.owned[i]) continue;
         const int s = bstart[i], m = bsize[i];
         const double* bi_row = binv + rowoff[i];
         double zi = 0.0;
@@ -159,20 +183,38 @@ k_pcg_persistent(int64_t n, const int32_t* __restrict__ rowptr, const int32_t* _
         r_new[i] = ri; z[i] = zi;
         lrz2 = fma(ri, zi, lrz2);
         lrr = fma(ri, ri, lrr);
+        if (DIST && d.owned[i] == 2) dist_push_row(d, epoch, i, zi);
       }
       lrz2 = block_sum(lrz2, sh);
       lrr = block_sum(lrr, sh);
       if (threadIdx.x == 0) { P0[blockIdx.x] = lrz2; P1[blockIdx.x] = lrr; }
       grid.sync();
       { double* t = r_old; r_old = r_new; r_new = t; }
-      const double rz_new = grid_total(P0, nb, sh);
+      double rz_new = grid_total(P0, nb, sh);
       rr = grid_total(P1, nb, sh);
-      if (rr <= tol2) break;  // uniform across the grid: every CTA computed the same rr
+      if (DIST) {
+        double v[2] = {rz_new, rr};
+        dist_allreduce<2>(grid, d, epoch, v);
+        rz_new = v[0]; rr = v[1];
+        if (rr > tol2) { dist_unpack(d, epoch, z, tid, nth, n); grid.sync(); }
+      }
+      if (rr <= tol2) break;  // uniform across the grid (and the ranks): every CTA computed the same rr
       const double beta = rz_new / rz;
       rz = rz_new;
       for (int64_t i = tid; i < n; i += nth) p[i] = fma(beta, p[i], z[i]);
       grid.sync();
     }
+  }
+  if (DIST) {
+    // owner -> ghost update of the solution
+    grid.sync();
+    dist_push(d, epoch, x, tid, nth, n);
+    grid.sync();
+    double v[1] = {0.0};
+    dist_allreduce<1>(grid, d, epoch, v);
+    dist_unpack(d, epoch, x, tid, nth, n);
+    grid.sync();
+    if (tid == 0) d.win[d.rank]->epoch = epoch;
   }
   if (tid == 0) {
     stats[0] = (double)(it > max_iter ? max_iter : it);
@@ -215,13 +257,19 @@ void solver_solve_async(gg_solver* s, const double* b, double scale_b, double* x
   double *r = s->r.p, *r2 = s->r2.p, *z = s->z.p, *p = s->p.p, *Ap = s->Ap.p, *pa = s->partials.p, *stt = s->stats.p;
   double rtol = s->rtol;
   int mi = s->max_iter;
-  void* args[] = {&n, &rp, &ci, &va, &bs, &bz, &ro, &bi, &b, &scale_b, &x, &r, &r2, &z, &p, &Ap, &pa, &rtol, &mi, &stt};
+  // partitioned space with connected peer windows: the distributed variant (halo of z and all-reduces through peer memory)
+  gg_space* sp = A->test;
+  const bool multi = sp && sp->dist && sp->mesh->comm && sp->mesh->comm->world > 1;
+  if (multi) GG_REQUIRE(A->test == A->trial, GG_ERR_UNSUPPORTED, "the distributed PCG needs a square operator on one partitioned space");
+  DistDev d = multi ? dist_dev(sp) : DistDev();
+  void* args[] = {&n, &rp, &ci, &va, &bs, &bz, &ro, &bi, &b, &scale_b, &x, &r, &r2, &z, &p, &Ap, &pa, &rtol, &mi, &stt, &d};
   // do not launch more CTAs than there is work for (fewer CTAs = cheaper grid barriers)
   int grid = s->grid;
   int64_t want = (n + s->block - 1) / s->block;
   if (want < grid) grid = (int)std::max<int64_t>(want, 1);
   ProfScope ps(A->ctx, "k_pcg_persistent");
-  GG_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(grid), dim3(s->block), args, 0, A->ctx->stream));
+  if (multi) GG_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent<true>, dim3(grid), dim3(s->block), args, 0, A->ctx->stream));
+  else GG_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent<false>, dim3(grid), dim3(s->block), args, 0, A->ctx->stream));
   A->ctx->launches++;
 }
 
@@ -284,7 +332,7 @@ int gg_solver_pcg_create(gg_csr* A, double rtol, int max_iter, gg_solver** out) 
   s->binv.alloc(off);
   s->r.alloc(n); s->r2.alloc(n); s->z.alloc(n); s->p.alloc(n); s->Ap.alloc(n);
   int per_sm = 0;
-  GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, s->block, 0));
+  GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent<true>, s->block, 0));
   GG_REQUIRE(per_sm >= 1, GG_ERR_CUDA, "persistent PCG kernel does not fit on an SM");
   s->grid = ctx->sm_count * std::min(per_sm, 2);
   s->partials.alloc(3 * (size_t)s->grid);
@@ -315,6 +363,7 @@ int gg_solver_solve(gg_solver* s, gg_vec* b, gg_vec* x, int32_t* iters, double* 
   if (s->A->n_rows) s->stats.download(st, s->A->ctx->stream);
   if (iters) *iters = (int32_t)st[0];
   if (rel_res) *rel_res = st[1];
+  if (s->A->test) comm_check(s->A->test->mesh->comm);   // a lost peer: GG_ERR_COMM, not a bogus "not converged"
   GG_REQUIRE(st[1] <= s->rtol * 1.0000001 || s->A->n_rows == 0, GG_ERR_NOCONV,
              "PCG did not converge: relative residual " + std::to_string(st[1]) + " after " + std::to_string((int)st[0]) + " iterations");
   GG_API_END

@@ -127,6 +127,11 @@ int gg_mesh_ghost_cells(gg_mesh* m, int64_t first, int64_t last, int64_t* n_ghos
  * windows.  At run time halo values and dot-product operands are stored straight into the peers' HBM over NVLink by the
  * solver kernels (no NCCL call inside a step).  DOF ownership: the rank owning the lowest-numbered cell around the DOF. */
 int gg_plan_create(int n, double radius, int nparts, int part, gg_plan** out);
+/* The same for the 3-D shell, AtlasOctreeDistributedDiscreteModel(ranks, CubedSphereWithThicknessMesh(r, t), l)
+ * (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:164-243,286-294): cells in the order `ordering` of gg_mesh_cubed_sphere
+ * (2 = p8est Morton), equal-count chunks of that order (p4est's partition of its space-filling curve), vertex-adjacent ghost
+ * layer; hexahedral CG / DG / RT spaces are exchanged through the same peer windows. */
+int gg_plan_create_shell(int n, int n_layers, double radius, double thickness, int ordering, int nparts, int part, gg_plan** out);
 void gg_plan_destroy(gg_plan* p);
 int gg_plan_info(gg_plan* p, int64_t* n_cells_global, int64_t* first_owned, int64_t* last_owned, int64_t* n_local);
 int gg_plan_local_cells(gg_plan* p, int64_t* out /* [n_local] global cell ids (0-based), ascending: owned + ghost */);
@@ -295,6 +300,9 @@ int gg_eval_geometry(gg_ctx* ctx, int panel, double radius, int64_t n, const dou
 /* ---- linear solver (mass solves of the RK stages) ------------------------------------------------
  * Stands in for LUSolver() / CGSolver(JacobiLinearSolver(); rtol=1e-12) (test/Tutorials/ShallowWater.jl:175-176)
  * at the `Algebra.solve!(x, ::LinearSolver, op, cache)` seam (src/ODEs/StageOperators.jl:55-88). */
+/* On a partitioned space with connected peer windows (gg_mesh_partitioned + gg_comm_connect) the solve is collective: dot products
+ * over the owned rows are all-reduced and the owner -> ghost update runs through peer memory inside the kernel; x comes back
+ * consistent (owned + ghost values).  GG_ERR_COMM after a peer-window time-out. */
 int gg_solver_pcg_create(gg_csr* A, double rtol, int max_iter, gg_solver** out);
 /* numerical_setup!: refresh the Jacobi preconditioner after A's values changed */
 int gg_solver_update(gg_solver* s);

@@ -197,6 +197,62 @@ def run_checks(gg, ctx, rank, world, n, p):
             "pcg_iters_equal": bool(its == itf), "solves": int(sol), "consistent_exact": True, "vector_h1_cob": e_cob}
 
 
+def run_shell_checks(gg, ctx, rank, world, n=4, order=2, degree=8):
+    """The distributed 3-D shell (BASELINE configs[4]; test/Laplacian/mpi/LaplaceBeltramiTests.jl:30-34): p8est cell order, equal-count
+    chunks of the space-filling curve + ghost layer, hexahedral CG space partitioned through the plan; halo exchange of its DOF
+    vectors and the distributed PCG (all-reduces and halo through peer memory) on the assembled operator (grad v . ginv grad u +
+    u v) sqrtg, against the single-GPU run."""
+    import math
+    L = gg._lib
+    r, t = 1.0, 0.19
+    shell = gg.CubedSphereWithThicknessMesh(r, t)
+    plan = gg.PartitionPlan(n, world, rank, radius=r, thickness=t, ordering=2)
+    comm = gg.PeerWindow(ctx, rank, world, plan.space(L.SPACE_CG, order)["slot_capacity"])
+    comm.connect()
+    local = gg.partitioned_model(shell, plan, comm, ctx=ctx)
+    full = gg.AtlasDiscreteModel(shell, n=n, ordering=2, ctx=ctx)
+    cells = plan.local_cells()
+    assert local.num_cells == len(cells) and (local.get_cell_node_ids() == full.get_cell_node_ids()[cells]).all()
+    a, b = gg.partition_range(full.num_cells, world, rank)
+    assert (plan.first_owned, plan.last_owned) == (a, b) and b - a in (full.num_cells // world, full.num_cells // world + 1)
+    V = gg.TestFESpace(local, gg.ReferenceFE(gg.lagrangian, float, order), conformity="H1")
+    Vf = gg.TestFESpace(full, gg.ReferenceFE(gg.lagrangian, float, order), conformity="H1")
+    l2g, own = gg.global_dof_ids(V)
+    l2g = l2g - 1
+    assert (V.get_cell_dof_ids() - 1 == l2g.searchsorted(Vf.get_cell_dof_ids()[cells] - 1)).all()      # the global numbering restricted
+    g = np.cos(0.05 * np.arange(Vf.num_free_dofs)) + 2.0
+    v = gg.DeviceVector.from_numpy(ctx, np.where(own == rank, g[l2g], -5.0))
+    gg.consistent(v, V)
+    assert (v.get() == g[l2g]).all(), "consistent! on the hexahedral CG space did not reproduce the owner values"
+
+    def system(model, W):
+        dO = gg.Measure(gg.Triangulation(model), degree)
+        assem = gg.SparseMatrixAssembler(W, W)
+        gg.assemble_matrix(gg.LaplaceBeltrami(dO), assem)
+        A = gg.assemble_matrix(gg.ScalarMass(dO), assem, add=True)
+        xyz = dO.quadrature_points(chart=False)[1]
+        f = xyz[..., 0] * xyz[..., 1] + np.sin(3 * xyz[..., 2])
+        return A, gg.assemble_vector(gg.Source(dO, f), W)
+
+    A, rhs = system(local, V)
+    Af, rhsf = system(full, Vf)
+    owned = own == rank
+    assert rel(rhs.get()[owned], rhsf.get()[l2g][owned]) < 1e-13          # owned rows are complete without any exchange
+    S, Sf = A.to_scipy(), Af.to_scipy()
+    xt = np.sin(0.01 * np.arange(Vf.num_free_dofs))
+    assert rel((S @ xt[l2g])[owned], (Sf @ xt)[l2g][owned]) < 1e-13
+    ns, nsf = gg.CGSolver(rtol=1e-12).numerical_setup(A), gg.CGSolver(rtol=1e-12).numerical_setup(Af)
+    x = ns.solve(rhs).get()
+    xf = nsf.solve(rhsf).get()
+    e_x = rel(x, xf[l2g])
+    assert e_x < 1e-9, f"distributed shell solve differs from the single-GPU solve by {e_x}"
+    assert comm.error_epoch() == 0
+    assert abs(ns.iterations - nsf.iterations) <= 1
+    dist.barrier()
+    return {"n": n, "order": order, "cells": int(full.num_cells), "dofs": int(Vf.num_free_dofs), "solution": e_x,
+            "pcg_iters": int(ns.iterations), "pcg_iters_single_gpu": int(nsf.iterations)}
+
+
 def main():
     """torchrun worker.  GG_DIST_BACKEND=gloo + GG_DIST_SHARE_GPU=1 are for the world-of-one run of the partitioned code path
     (GG_FORCE_MULTI=1); several ranks must never share a GPU (their kernels wait on one another)."""
@@ -213,6 +269,10 @@ def main():
     ctx = gg.get_context(local)
     n, p = int(sys.argv[1]) if len(sys.argv) > 1 else 6, int(sys.argv[2]) if len(sys.argv) > 2 else 1
     r = run_checks(gg, ctx, rank, world, n, p)
+    if world > 1 and p == 2:
+        rs = run_shell_checks(gg, ctx, rank, world)
+        if rank == 0:
+            print(f"SHELL_OK {rs}")
     if rank == 0:
         print(f"DIST_OK world={world} n={n} p={p} wave_err={r['wave']:.2e} swe_err={r['swe']:.2e} pv_err={r['pv']:.2e} "
               f"adv_err={r['advection']:.2e} pcg_iters={r['pcg_iters']} (single GPU {r['pcg_iters_single_gpu']}) solves={r['solves']}")

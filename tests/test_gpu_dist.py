@@ -25,6 +25,8 @@ def _run(world, n, p):
            "--master-port", "29617", os.path.join(ROOT, "tests", "dist_worker.py"), str(n), str(p)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    if p == 2:      # the distributed 3-D shell checks ride on the order-2 case
+        assert "SHELL_OK" in out.stdout, out.stdout[-3000:]
 
 
 @pytest.mark.parametrize("n,p", [(6, 1), (5, 2), (8, 0)])
