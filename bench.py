@@ -165,8 +165,8 @@ def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10, dist=None, ran
 
 
 def swe_roofline(leg, ncell_local, p):
-    """HBM roofline of the dominant kernel of the shallow-water step, the persistent condensed PCG k_pcg_ebe (61 % of the step in
-    profiles/ncu_swe_r01.txt), per iteration of the RT mass solve, from the phase timers of THIS run (%globaltimer inside the
+    """HBM roofline of the dominant kernel of the shallow-water step, the persistent condensed PCG k_pcg_ebe (the largest share of the step in
+    profiles/ncu_swe_r02.txt), per iteration of the RT mass solve, from the phase timers of THIS run (%globaltimer inside the
     kernel) and the algorithmic bytes of one iteration: every operand once."""
     peaks = {}
     try:
@@ -191,7 +191,9 @@ def swe_roofline(leg, ncell_local, p):
                        "gather_dot": {"bytes": b_gather, "us": it["gather_dot"], "gbs": b_gather / (it["gather_dot"] * 1e-6) / 1e9 if it["gather_dot"] else None},
                        "update_precond": {"bytes": b_update, "us": it["update_precond"], "gbs": b_update / (it["update_precond"] * 1e-6) / 1e9 if it["update_precond"] else None}},
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s", "traffic": None,
-            "from_profile": {"file": "profiles/ncu_swe_r01.txt", "dram_bytes_per_iteration": 6.0e8, "note": "ncu, round 1, N=1"}}
+            "from_profile": {"file": "profiles/ncu_swe_r02.txt", "k_pcg_ebe<12,12,1>": {"dram_bytes_per_launch": 4.537e9, "ms": 1.285,
+                                                                                  "dram_gbs": 3531, "l2_hit_pct": 40.4},
+                             "note": "ncu --set full, round 2, N=1, one launch = one whole RT2 mass solve"}}
 
 
 def adv_leg(gg, ctx, torch, stream, e0, e1, n=128, p=2, steps=200, dist=None, rank=0, world=1):
@@ -580,7 +582,10 @@ def assembly_roofline(prof, ncell_local, nnz, ms_per_step, fp64_peak, hbm_peak, 
                 "peak_gbs": hbm_peak, "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak if k_ms else None,
                 "algorithmic_bytes": "8 B x nnz (every CSR value written once) + 140 B per cell (DOF ids, state gather, residual)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if have_peaks else "fallback 6650 GB/s"},
-        "traffic": None,
+        # dram__bytes_read + write of the dominant kernel per launch: the ncu capture of this exact workload (N=1, full size), else unknown
+        "traffic": ((PROFILE_FIGURES["k_lb_tile"]["dram_bytes_per_launch"] if fused else
+                     PROFILE_FIGURES["two_kernel_path"]["k_lb_fast"]["dram_bytes_per_launch"]) if ncell_local == 393216 else None),
+        "traffic_source": "profiles/ncu_lb_tile_r02.txt (ncu --set full, not measured by this run)",
         "from_profile": PROFILE_FIGURES,
     }
     if not fused:
@@ -594,9 +599,12 @@ def assembly_roofline(prof, ncell_local, nnz, ms_per_step, fp64_peak, hbm_peak, 
 
 
 # figures that only a profiler gives (ncu capture of this command, committed under profiles/); NOT measured by bench.py itself
-PROFILE_FIGURES = {"file": "profiles/ncu_lb_assembly_r01_final.txt", "workload": "N=1, 393 216 cells, two-kernel path of round 1",
-                   "k_lb_fast": {"dram_bytes_per_cell": 378.4, "fp64_pipe_active_pct": 81.3},
-                   "k_gather_chunks": {"dram_bytes_per_cell": 1462.8, "note": "575 MB per launch, of which 190 MB gather lists"}}
+PROFILE_FIGURES = {"file": "profiles/ncu_lb_tile_r02.txt", "workload": "N=1, 393 216 cells, ncu --set full of this command, round 2",
+                   "k_lb_tile": {"dram_bytes_per_launch": 266.0e6, "dram_bytes_per_cell": 676.5, "fp64_pipe_active_pct": 56.1,
+                                 "note": "65 MB read + 201 MB written; algorithmic: 8 B x nnz = 201 MB of CSR values"},
+                   "k_lb_tile_groups": {"dram_bytes_per_launch": 100.4e6, "note": "tile-border rows: 84 MB read, 16 MB written"},
+                   "two_kernel_path": {"k_lb_fast": {"dram_bytes_per_launch": 149.0e6, "fp64_pipe_active_pct": 81.3},
+                                       "k_gather_chunks": {"dram_bytes_per_launch": 574.6e6}}}
 
 
 def assembly_limiter(leg, roofline, world):
