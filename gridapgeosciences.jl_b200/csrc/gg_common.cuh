@@ -107,6 +107,7 @@ struct gg_ctx {
   int const_order = -1, const_nq = -1;
   // tables resident in the __constant__ blocks of the matrix-free PCG (gg_mf.cu): nq of the weights, (order, nq) keys
   int64_t mf_key_w = -1, mf_key_rt = -1, mf_key_sc = -1;
+  gg::DevBuf<double> swe_lane_tab;   // the same tables as one block in global memory (gg_swe_lanes.cuh)
   int64_t swe_sf_key = -1;   // (order, nq) resident in the tables of the sum-factorised shallow-water kernels (gg_swe_sf.cuh)
   int hex_order = -1;    // order of the hexahedral index tables resident in gg_forms.cu's __constant__ block
   int64_t swe_key = -1;  // (order, nq) of the shallow-water tabulations resident in gg_swe.cu's __constant__ block

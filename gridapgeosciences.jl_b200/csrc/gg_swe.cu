@@ -96,6 +96,7 @@ __device__ __forceinline__ Stage2 stage2_of(double* gscratch, int64_t nc, int64_
 
 }  // namespace gg
 #include "gg_swe_sf.cuh"
+#include "gg_swe_lanes.cuh"
 namespace gg {
 
 // Right-hand sides of the three diagnostic equations, one thread per cell.
@@ -386,7 +387,111 @@ static void swe_sf_tabs(gg_rk* rk) {
   GG_CUDA(cudaMemcpyToSymbol(c_sf_la, la.data(), la.size() * sizeof(double)));
   GG_CUDA(cudaMemcpyToSymbol(c_sf_da, da.data(), da.size() * sizeof(double)));
   GG_CUDA(cudaMemcpyToSymbol(c_sf_lb, lb.data(), lb.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_w, w.data(), w.size() * sizeof(double)));
   ctx->swe_sf_key = key;
+  // ---- kernels with several lanes per cell (gg_swe_lanes.cuh): the RT basis as a tensor product of 1-D dual bases ----
+  // A_alpha in P_{K+1} dual to Lambda_0 f = -f(0), Lambda_1 f = f(1), Lambda_{2+i} f = int x^i f;  B_m in P_K dual to int s^m f
+  auto dual_basis = [](int n, const std::vector<long double>& L) {   // L[functional][monomial] -> coefficients [monomial][function]
+    std::vector<long double> M = L, I((size_t)n * n, 0.0L);
+    for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.0L;
+    for (int c = 0; c < n; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r) if (fabsl(M[(size_t)r * n + c]) > fabsl(M[(size_t)piv * n + c])) piv = r;
+      for (int k2 = 0; k2 < n; ++k2) { std::swap(M[(size_t)c * n + k2], M[(size_t)piv * n + k2]); std::swap(I[(size_t)c * n + k2], I[(size_t)piv * n + k2]); }
+      const long double d = 1.0L / M[(size_t)c * n + c];
+      for (int k2 = 0; k2 < n; ++k2) { M[(size_t)c * n + k2] *= d; I[(size_t)c * n + k2] *= d; }
+      for (int r = 0; r < n; ++r) {
+        if (r == c) continue;
+        const long double f = M[(size_t)r * n + c];
+        for (int k2 = 0; k2 < n; ++k2) { M[(size_t)r * n + k2] -= f * M[(size_t)c * n + k2]; I[(size_t)r * n + k2] -= f * I[(size_t)c * n + k2]; }
+      }
+    }
+    return I;   // L^-1: [monomial e][function alpha]
+  };
+  std::vector<long double> LA((size_t)NA * NA), LB((size_t)NB * NB);
+  for (int e = 0; e < NA; ++e) {
+    LA[(size_t)0 * NA + e] = e == 0 ? -1.0L : 0.0L;
+    LA[(size_t)1 * NA + e] = 1.0L;
+    for (int i = 0; i + 2 < NA; ++i) LA[(size_t)(2 + i) * NA + e] = 1.0L / (i + e + 1);
+  }
+  for (int m = 0; m < NB; ++m) for (int e = 0; e < NB; ++e) LB[(size_t)m * NB + e] = 1.0L / (m + e + 1);
+  const std::vector<long double> CA = dual_basis(NA, LA), CB = dual_basis(NB, LB);
+  std::vector<double> ra((size_t)nq * NA), rda((size_t)nq * NA), rb((size_t)nq * NB);
+  for (int q = 0; q < nq; ++q) {
+    const long double x = xi[q];
+    for (int al = 0; al < NA; ++al) {
+      long double v = 0.0L, d = 0.0L, xp = 1.0L, xm = 0.0L;   // xp = x^e, xm = e x^(e-1)
+      for (int e = 0; e < NA; ++e) { v += CA[(size_t)e * NA + al] * xp; d += CA[(size_t)e * NA + al] * xm; xm = (e + 1) * xp; xp *= x; }
+      ra[(size_t)q * NA + al] = (double)v; rda[(size_t)q * NA + al] = (double)d;
+    }
+    for (int m = 0; m < NB; ++m) {
+      long double v = 0.0L, xp = 1.0L;
+      for (int e = 0; e < NB; ++e) { v += CB[(size_t)e * NB + m] * xp; xp *= x; }
+      rb[(size_t)q * NB + m] = (double)v;
+    }
+  }
+  {
+    // check the factorisation against the tabulated basis at the tensor Gauss points
+    auto jx = [&](int al, int m) { return al == 0 ? 2 * NB + m : al == 1 ? 3 * NB + m : 4 * NB + m * K + (al - 2); };
+    auto jy = [&](int m, int be) { return be == 0 ? m : be == 1 ? NB + m : 4 * NB + K * NB + (be - 2) * NB + m; };
+    std::vector<double> tp, tv, td;
+    for (int q2 = 0; q2 < nq; ++q2) for (int q1 = 0; q1 < nq; ++q1) { tp.push_back(xi[q1]); tp.push_back(xi[q2]); }
+    R.tabulate(nq * nq, tp.data(), tv, td);
+    std::vector<double> ex(tv.size(), 0.0), exd(td.size(), 0.0);
+    for (int q2 = 0; q2 < nq; ++q2)
+      for (int q1 = 0; q1 < nq; ++q1) {
+        const size_t q = (size_t)q1 + (size_t)nq * q2;
+        for (int al = 0; al < NA; ++al)
+          for (int m = 0; m < NB; ++m) {
+            ex[(q * MU + jx(al, m)) * 2 + 0] = ra[(size_t)q1 * NA + al] * rb[(size_t)q2 * NB + m];
+            exd[q * MU + jx(al, m)] = rda[(size_t)q1 * NA + al] * rb[(size_t)q2 * NB + m];
+            ex[(q * MU + jy(m, al)) * 2 + 1] = rb[(size_t)q1 * NB + m] * ra[(size_t)q2 * NA + al];
+            exd[q * MU + jy(m, al)] = rb[(size_t)q1 * NB + m] * rda[(size_t)q2 * NA + al];
+          }
+      }
+    // (the tabulation goes through the monomial prebasis: 1e-12 relative for K = 2, values up to 1e3; the 1-D tables are exact
+    // to the last bit, so only the order of magnitude of a mismatch matters here)
+    double err = 0.0, scale = 1.0;
+    for (size_t i = 0; i < tv.size(); ++i) { err = std::max(err, std::fabs(tv[i] - ex[i])); scale = std::max(scale, std::fabs(tv[i])); }
+    for (size_t i = 0; i < td.size(); ++i) { err = std::max(err, std::fabs(td[i] - exd[i])); scale = std::max(scale, std::fabs(td[i])); }
+    GG_REQUIRE(err < 1e-9 * scale, GG_ERR_INVALID, "Raviart-Thomas basis does not factorise into the 1-D dual bases");
+  }
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_ra, ra.data(), ra.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_rda, rda.data(), rda.size() * sizeof(double)));
+  GG_CUDA(cudaMemcpyToSymbol(c_sf_rb, rb.data(), rb.size() * sizeof(double)));
+  std::vector<double> blk;   // SweLanes<K, NQ>::T_*
+  blk.insert(blk.end(), la.begin(), la.end());
+  blk.insert(blk.end(), da.begin(), da.end());
+  blk.insert(blk.end(), lb.begin(), lb.end());
+  blk.insert(blk.end(), ra.begin(), ra.end());
+  blk.insert(blk.end(), rda.begin(), rda.end());
+  blk.insert(blk.end(), rb.begin(), rb.end());
+  blk.insert(blk.end(), w.begin(), w.end());
+  blk.resize((blk.size() + 1) & ~(size_t)1, 0.0);
+  ctx->swe_lane_tab.upload(blk, ctx->stream);
+  GG_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// (order, points per direction) pairs the lane-parallel kernels are instantiated for: the default rules of the drivers
+// (degree 4 (K + 1): 3, 5, 7 points; thermal shallow water 4 K: 3 points for K = 1) and degree 8 for K = 2
+static bool swe_lanes_enabled(int K, int nq) {
+  static const bool on = !(getenv("GG_SWE_LANES") && getenv("GG_SWE_LANES")[0] == '0');
+  return on && ((K == 0 && nq == 3) || (K == 1 && (nq == 3 || nq == 5)) || (K == 2 && (nq == 5 || nq == 7)));
+}
+
+template <typename Kern, typename... Args>
+static void swe_launch_lanes(gg_ctx* ctx, Kern kern, int64_t nc, int cpb, size_t smem, Args... args) {
+  static std::map<const void*, int> per_sm;   // resident CTAs per SM of each instantiation
+  auto it = per_sm.find((const void*)kern);
+  if (it == per_sm.end()) {
+    if (smem > 48 * 1024) GG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    GG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 128, smem));
+    it = per_sm.emplace((const void*)kern, std::max(n, 1)).first;
+  }
+  const int64_t nblk = (nc + cpb - 1) / cpb;
+  const unsigned grid = (unsigned)std::min<int64_t>(nblk, (int64_t)ctx->sm_count * it->second);
+  kern<<<grid, 128, smem, ctx->stream>>>(nc, args...);
 }
 
 static bool swe_sf_enabled() {
@@ -406,7 +511,19 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
   double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
   const double *u = x, *p = x + rk->nu;
   unsigned nb = nblk(nc, 64);
-  {
+  if (swe_lanes_enabled(rk->order, rk->nq1)) {
+    ProfScope ps(ctx, "k_swe_diag");
+    swe_sf_tabs(rk);
+#define GG_LANES(K_, NQ_)                                                                                                  \
+  if (rk->order == K_ && rk->nq1 == NQ_)                                                                                   \
+    swe_launch_lanes(ctx, k_swe_diag_lanes<K_, NQ_>, nc, SweLanes<K_, NQ_>::CPB, SweLanes<K_, NQ_>::diag_smem(), g,        \
+                     ctx->swe_lane_tab.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, u, p, rk->fq.p,                     \
+                     rk->bq.n ? rk->bq.p : nullptr, rk->gravity, rk->MpInv.p, rk->pq->d.p, rk->evec_q.p, rk->evec_u.p, yP);
+    GG_LANES(0, 3) GG_LANES(1, 3) GG_LANES(1, 5) GG_LANES(2, 5) GG_LANES(2, 7)
+#undef GG_LANES
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  } else {
     ProfScope ps(ctx, "k_swe_diag");
     const size_t smem = swe_stage_smem(rk, 64);
     double* gs = smem ? nullptr : rk->stage2.p;
@@ -465,7 +582,23 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
   const double *yq = y, *yF = y + rk->nr, *yP = y + rk->nr + rk->nu;
   const bool alias = (q0 == yq);
   unsigned nb = nblk(nc, 64);
-  if (swe_sf_enabled()) {
+  if (swe_lanes_enabled(rk->order, rk->nq1)) {
+    ProfScope ps(ctx, "k_swe_stage");
+    swe_sf_tabs(rk);
+#define GG_LANES_A(K_, NQ_, A_)                                                                                            \
+  swe_launch_lanes(ctx, k_swe_stage_lanes<K_, A_, NQ_>, nc, SweLanes<K_, NQ_>::CPB, SweLanes<K_, NQ_>::stage_smem(), g,    \
+                   ctx->swe_lane_tab.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, rk->R->d_cell_dofs.p, x, yq, q0, yF,  \
+                   yP, rk->MpInv.p, rk->tau, rk->tau / rk->dt, rk->evec_u.p, r + rk->nu, kp);
+#define GG_LANES(K_, NQ_)                                                                                                  \
+  if (rk->order == K_ && rk->nq1 == NQ_) {                                                                                 \
+    if (alias) { GG_LANES_A(K_, NQ_, true) } else { GG_LANES_A(K_, NQ_, false) }                                           \
+  }
+    GG_LANES(0, 3) GG_LANES(1, 3) GG_LANES(1, 5) GG_LANES(2, 5) GG_LANES(2, 7)
+#undef GG_LANES
+#undef GG_LANES_A
+    ctx->launches++;
+    GG_CUDA(cudaGetLastError());
+  } else if (swe_sf_enabled()) {
     ProfScope ps(ctx, "k_swe_stage");
     swe_sf_tabs(rk);
     // the sum-factorised kernels are register-limited to 4 CTAs per SM, so the 50 KB staging buffer fits in shared memory
