@@ -19,6 +19,8 @@
 //   P5  the lanes write the entry-major element vectors ([entry][cell]: the 4 or 8 cells of the warp are consecutive, one sector per
 //       entry) and apply the inverse DG mass blocks, one row per lane.
 // A warp never waits for another one: no __syncthreads, the 4 warps of a CTA only share the 1-D tables.
+// (Measured and dropped: prefetch.global.L2 of the warp's next batch at the top of the loop -- 0.375 -> 0.39 ms, the exposed
+// latency of P0 / P5 is L2 latency at 20 warps per SM, not DRAM latency.)
 // The constant-coefficient terms -int Phi div(v) and int r div(F) ride on the same rows (div phi^x = A'_alpha B_m is a tensor
 // product too), the Jacobian determinant cancels under the contravariant Piola map: plain reference weights, exact for NQ >= K + 1.
 // Nothing is staged per quadrature point; 96 registers, 5 CTAs of 128 threads per SM.
@@ -91,6 +93,9 @@ k_swe_diag_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const i
   double* s_cell = lanes_sm + C::T_SIZE;
   const int tid = threadIdx.x;
   for (int i = tid; i < C::T_SIZE; i += TH) s_tab[i] = tabs[i];
+  __shared__ int s_lexp[MP], s_lexr[MR];   // Gridap local node order -> lexicographic, DG_K and CG_{K+1}
+  if (tid < MP) s_lexp[tid] = sf_loc2lex(K, tid);
+  if (tid < MR) s_lexr[tid] = sf_loc2lex(K + 1, tid);
   __syncthreads();
   const int cell = tid / G, l = tid % G;
   double* sc = s_cell + cell * S;
@@ -116,7 +121,7 @@ k_swe_diag_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const i
 #pragma unroll
     for (int m = 0; m < (MP + G - 1) / G; ++m) {
       const int i = l + G * m;
-      if (i < MP) sc[C::D_PE + sf_loc2lex(K, i)] = valid ? p[c * MP + i] : 0.0;
+      if (i < MP) sc[C::D_PE + s_lexp[i]] = valid ? p[c * MP + i] : 0.0;
     }
 #pragma unroll
     for (int m = 0; m < (Q + G - 1) / G; ++m) {
@@ -279,7 +284,7 @@ k_swe_diag_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const i
 #pragma unroll
       for (int m = 0; m < (MR + G - 1) / G; ++m) {
         const int i = l + G * m;
-        if (i < MR) eq[(int64_t)i * nc + c] = sc[C::D_EQ + sf_loc2lex(K + 1, i)];
+        if (i < MR) eq[(int64_t)i * nc + c] = sc[C::D_EQ + s_lexr[i]];
       }
 #pragma unroll
       for (int m = 0; m < (Q + G - 1) / G; ++m) {
@@ -317,6 +322,9 @@ k_swe_stage_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const 
   double* s_cell = lanes_sm + C::T_SIZE;
   const int tid = threadIdx.x;
   for (int i = tid; i < C::T_SIZE; i += TH) s_tab[i] = tabs[i];
+  __shared__ int s_lexp[MP], s_lexr[MR];   // Gridap local node order -> lexicographic, DG_K and CG_{K+1}
+  if (tid < MP) s_lexp[tid] = sf_loc2lex(K, tid);
+  if (tid < MR) s_lexr[tid] = sf_loc2lex(K + 1, tid);
   __syncthreads();
   const int cell = tid / G, l = tid % G;
   double* sc = s_cell + cell * S;
@@ -355,14 +363,14 @@ k_swe_stage_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const 
           // q - tau (q - q0)/dt = (1 - tau/dt) q + (tau/dt) q0
           if (!ALIAS) vc = fma(tau_over_dt, q0v[d] - v, v);
         }
-        sc[C::S_QN + sf_loc2lex(K + 1, i)] = v;
-        if (!ALIAS) sc[C::S_QC + sf_loc2lex(K + 1, i)] = vc;
+        sc[C::S_QN + s_lexr[i]] = v;
+        if (!ALIAS) sc[C::S_QC + s_lexr[i]] = vc;
       }
     }
 #pragma unroll
     for (int m = 0; m < (MP + G - 1) / G; ++m) {
       const int i = l + G * m;
-      if (i < MP) sc[C::S_PE + sf_loc2lex(K, i)] = valid ? Phi[c * MP + i] : 0.0;
+      if (i < MP) sc[C::S_PE + s_lexp[i]] = valid ? Phi[c * MP + i] : 0.0;
     }
     if (valid) {
       if (l < NQ) {
@@ -573,7 +581,7 @@ k_swe_stage_lanes(int64_t nc, CellGeo g, const double* __restrict__ tabs, const 
       for (int m = 0; m < (MP + G - 1) / G; ++m) {
         const int i = l + G * m;
         if (i < MP) {
-          rp[c * MP + i] = sc[C::S_RP + sf_loc2lex(K, i)];
+          rp[c * MP + i] = sc[C::S_RP + s_lexp[i]];
           if (kp) {
             double acc = 0.0;
 #pragma unroll
