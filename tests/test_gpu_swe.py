@@ -23,9 +23,9 @@ def _rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
 
-def _stepper(gg, n, p, dt, q0_mode="alias", rtol=1e-14):
+def _stepper(gg, n, p, dt, q0_mode="alias", rtol=1e-14, degree=None):
     model = gg.AtlasDiscreteModel(gg.CubedSphereMesh(1.0), n=n)
-    op = gg.ShallowWaterOperator(model, p, oswe.coriolis(), gravity=oswe._g, q0_mode=q0_mode)
+    op = gg.ShallowWaterOperator(model, p, oswe.coriolis(), gravity=oswe._g, q0_mode=q0_mode, degree=degree)
     return model, gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=rtol), None, dt, "EXRK_SSP_3_3"), op)
 
 
@@ -53,13 +53,15 @@ def test_interpolation_and_norms_match_oracle(gg, n, p):
     assert abs(gg.norm(e[P.nu:], Q, 2 * P.degree) - ep) < 1e-12 * ep
 
 
-@pytest.mark.parametrize("n,p", [(4, 0), (4, 1), (3, 2)])
-def test_diagnostics_and_stage_residual_match_oracle(gg, n, p):
+# default rules (degree 4 (p + 1): 3, 5, 7 points per direction) and degree 8 for p = 2 run the kernels with several lanes per
+# cell (gg_swe_lanes.cuh); the other rules (4 and 6 points) run the one-thread-per-cell kernels (gg_swe_sf.cuh)
+@pytest.mark.parametrize("n,p,degree", [(4, 0, None), (4, 1, None), (3, 2, None), (3, 2, 8), (4, 1, 6), (3, 2, 10)])
+def test_diagnostics_and_stage_residual_match_oracle(gg, n, p, degree):
     mesh = CubedSphereMesh2D(n)
-    P = oswe.ShallowWaterProblem(mesh, p)
+    P = oswe.ShallowWaterProblem(mesh, p, degree=degree)
     dt = oswe.reference_dt(mesh, max(p, 1))
     P.dt, P.tau = dt, dt / 2
-    model, st = _stepper(gg, n, p, dt)
+    model, st = _stepper(gg, n, p, dt, degree=degree)
     assert (st.nu, st.np_, st.nq) == (P.nu, P.np_, P.nq)
     rng = np.random.default_rng(11)
     x = P.initial_state()
