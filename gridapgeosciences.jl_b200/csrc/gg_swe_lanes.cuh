@@ -68,13 +68,16 @@ struct SweLanes {
   static constexpr int D_UE = 0, D_PE = MU;
   static constexpr int D_EF = D_R, D_AP = D_EF + MU, D_EQ = D_AP + MP, D_FQ = D_EQ + MR;              // Coriolis parameter at the points, overwritten by the depth (pq_out)
   static constexpr int D_GEO = D_FQ + Q;               // hx, hy, tangents of the abscissae in x [NQ] and y [NQ]
-  static constexpr int D_S = (D_GEO + 2 + 2 * NQ) | 1;
+  // cell stride = 8 mod 16 doubles: every shared-memory access has the lanes of a group on consecutive (or the same) doubles, so
+  // the two cells of a half-warp must sit half a bank row apart
+  static constexpr int pad8(int raw) { return (raw + 7) / 16 * 16 + 8; }
+  static constexpr int D_S = pad8(D_GEO + 2 + 2 * NQ);
   static constexpr size_t diag_smem() { return (size_t)(T_SIZE + CPB * D_S) * sizeof(double); }
   // ---- stage residual ----
   static constexpr int S_RS = (NA + 3 * NB) | 1;       // row record: Sx[NA] Sy[NB] SyD[NB] SPr[NB]
   static constexpr int S_FE = 0, S_UE = MU, S_QN = 2 * MU, S_QC = S_QN + MR, S_PE = S_QC + MR;
   static constexpr int S_R = cmax(NQ * S_RS, S_PE + MP);
-  static constexpr int S_EF = S_R, S_RP = S_EF + MU, S_GEO = S_RP + MP, S_S = (S_GEO + 2 + 2 * NQ) | 1;
+  static constexpr int S_EF = S_R, S_RP = S_EF + MU, S_GEO = S_RP + MP, S_S = pad8(S_GEO + 2 + 2 * NQ);
   static constexpr size_t stage_smem() { return (size_t)(T_SIZE + CPB * S_S) * sizeof(double); }
 };
 
