@@ -471,14 +471,15 @@ static void launch_lb_tile(gg_ctx* ctx, const TilePlan& plan, const TileDev& T, 
 static bool run_lb_tile(gg_mesh* m, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u, double dir,
                         FillPipe* pipe) {
   // GG_LB_TILES = 0 / 1 forces the two-kernel / the tile path; default: by size.  A tile CTA lives ~35 us (its warps are
-  // latency-bound), so the tile kernel needs several waves of CTAs to pay off: measured on B200, 3072 tiles (393 216 cells,
-  // 6.9 waves of 444 CTAs) 0.258 ms against 0.283 ms for the two-kernel path, but 391 tiles (an 8-way slice, less than one
-  // wave) 0.065 ms against ~0.04 ms -- so slices below 4 waves keep the two-kernel path
+  // latency-bound), so the tile kernel needs a few waves of CTAs to pay off: measured on B200 with the L2 flushed between
+  // steps (tools/tile_sizes.py), 3072 tiles (393 216 cells, 6.9 waves of 444 CTAs) 0.263 ms against 0.286 ms for the
+  // two-kernel path, 1536 tiles (a 2-way slice) 0.151 / 0.159, 1055 tiles 0.112 / 0.117, 768 tiles and fewer within 1 %
+  // (and slower with a warm L2) -- so slices below 2 waves keep the two-kernel path
   static const char* force = getenv("GG_LB_TILES");
   gg_ctx* ctx = m->ctx;
   gg_csr* A = pipe->A;
   if ((force && force[0] == '0') || A->test != A->trial) return false;
-  if (!(force && force[0] == '1') && (m->n_cells + TILE_CELLS - 1) / TILE_CELLS < 4LL * 3 * ctx->sm_count) return false;
+  if (!(force && force[0] == '1') && (m->n_cells + TILE_CELLS - 1) / TILE_CELLS < 2LL * 3 * ctx->sm_count) return false;
   const int mode = (ctx->geometry_classes && !extrinsic) ? 1 : 0;
   // geometry classes: a CTA would serve the six congruent tiles of a class from one set of element matrices, but 512 long CTAs
   // fill the 444 CTA slots of a B200 badly (measured 0.268 ms against 0.172 ms of the class path through k_gather_chunks), so
