@@ -13,7 +13,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "gridapgeosciences.jl_b200")
 HOT = ["k_lb_tileILi3ELi10ELb0ELb0", "k_lb_tile_groupsILi9", "k_lb_fastILi3ELi10ELb0ELb0", "k_gather_chunks", "k_pcg_ebeILi12ELi12ELb1",
-       "k_swe_stage_sfILi2ELi1ELb0", "k_swe_diagILi2ELi1", "k_ebe_scalar_massILi3", "k_bq_residualILi36ELi8", "k_hex_tensor_fill"]
+       "k_swe_diag_lanesILi2ELi7", "k_swe_stage_lanesILi2ELb1ELi7", "k_swe_stage_sfILi2ELi1ELb0", "k_swe_diagILi2ELi1", "k_ebe_scalar_massILi3", "k_bq_residualILi36ELi8", "k_hex_tensor_fill"]
 
 
 def demangle(name):
