@@ -19,8 +19,10 @@
 //   P5  the lanes write the entry-major element vectors ([entry][cell]: the 4 or 8 cells of the warp are consecutive, one sector per
 //       entry) and apply the inverse DG mass blocks, one row per lane.
 // A warp never waits for another one: no __syncthreads, the 4 warps of a CTA only share the 1-D tables.
-// (Measured and dropped: prefetch.global.L2 of the warp's next batch at the top of the loop -- 0.375 -> 0.39 ms, the exposed
-// latency of P0 / P5 is L2 latency at 20 warps per SM, not DRAM latency.)
+// (Measured and dropped: prefetch.global.L2 of the warp's next batch at the top of the loop, 0.375 -> 0.39 ms; and a register
+// software pipeline -- indices of the next batch loaded before the row phase, values right after it, committed to shared memory
+// at the top of the next iteration -- 0.355 -> 0.364 ms with 150 bytes more spills: the long-scoreboard samples on the P0 loads
+// are warps that wait while others run, not lost issue slots.)
 // The constant-coefficient terms -int Phi div(v) and int r div(F) ride on the same rows (div phi^x = A'_alpha B_m is a tensor
 // product too), the Jacobian determinant cancels under the contravariant Piola map: plain reference weights, exact for NQ >= K + 1.
 // Nothing is staged per quadrature point; 96 registers, 5 CTAs of 128 threads per SM.
