@@ -416,7 +416,7 @@ def cpu_rk_baseline():
     return out
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -444,7 +444,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 class L2Flush:
@@ -641,8 +641,18 @@ def main():
                     help="N > 1: strong = the named 256x256-per-panel mesh partitioned over the ranks (default); weak = 256 sqrt(N)")
     ap.add_argument("--no-extras", action="store_true", help="skip the RK-steps/s, e2e and CPU-baseline legs")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print on file descriptor 1 (the NCCL version banner
+    # of the first communicator, ...) goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import torch
@@ -924,7 +934,7 @@ def main():
         except Exception as ex:
             line["cpu_baseline"]["rk"] = {"error": str(ex)[-300:]}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
