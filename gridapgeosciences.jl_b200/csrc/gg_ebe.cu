@@ -331,6 +331,9 @@ struct EbeArgs {
   int cblk;               // phase C walks the preconditioner blocks (one thread per block) instead of the rows
   const double* binv;
   const double* b;
+  // right-hand side in element form instead (b == nullptr): the entry-major element vectors [mloc][nc] that gather_vector would
+  // sum into b.  Boundary rows sum their sources (the same `pair` / vsrc indices as ev), interior DOFs have one source each.
+  const double* be;
   double scale_b;
   double *x, *ra, *rb, *z, *p, *Ap, *partials;
   double rtol;
@@ -476,7 +479,8 @@ k_pcg_ebe(const EbeArgs a) {
     double bi[MIa];
     const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-    for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
+    for (int t = 0; t < MI; ++t)
+      bi[t] = a.scale_b * (a.be ? a.be[(int64_t)(MB + t) * nc + c] : a.b[n + c * MI + t]) * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
     for (int j = 0; j < MB; ++j) {
       double acc = 0.0;
@@ -536,9 +540,18 @@ k_pcg_ebe(const EbeArgs a) {
       for (int j = 0; j < 3; ++j) {
         const bool on = j < m;
         pr[j] = on ? __ldg(a.pair + r0 + j) : make_int2(-1, -1);
-        bt[j] = on ? a.scale_b * a.b[r0 + j] : 0.0;
+        bt[j] = (on && !a.be) ? a.scale_b * a.b[r0 + j] : 0.0;
         ob[j] = on ? (owned ? owned[r0 + j] : (uint8_t)1) : (uint8_t)0;
         rw[j] = 0.0;
+      }
+      if (a.be) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double v = 0.0;
+          if (pr[j].x >= 0) v = a.be[pr[j].x];
+          if (pr[j].y >= 0) v += a.be[pr[j].y];
+          bt[j] = a.scale_b * v;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -560,6 +573,7 @@ k_pcg_ebe(const EbeArgs a) {
         for (int j = 0; j < 3; ++j) {
           if (j >= m) continue;
           for (int32_t q = a.vptr[r0 + j] + 2; q < a.vptr[r0 + j + 1]; ++q) {
+            if (a.be) bt[j] = fma(a.scale_b, a.be[a.vsrc[q]], bt[j]);
             if (MI > 0) bt[j] -= a.ev[a.vsrc[q]];
             if (a.warm) rw[j] += a.ev2[a.vsrc[q]];
           }
@@ -613,11 +627,17 @@ k_pcg_ebe(const EbeArgs a) {
         const int64_t i = i0 + u * nth;
         const bool ok = i < n;
         ebe_row_sources(a, i, ok, lo[u], hi[u], s0[u], s1[u]);
-        bt[u] = ok ? a.scale_b * a.b[i] : 0.0;
+        bt[u] = (ok && !a.be) ? a.scale_b * a.b[i] : 0.0;
         rw[u] = 0.0;
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
+        if (a.be) {
+          double v = 0.0;
+          if (s0[u] >= 0) v = a.be[s0[u]];
+          if (s1[u] >= 0) v += a.be[s1[u]];
+          bt[u] = a.scale_b * v;
+        }
         if (MI > 0) {
           if (s0[u] >= 0) bt[u] -= a.ev[s0[u]];
           if (s1[u] >= 0) bt[u] -= a.ev[s1[u]];
@@ -632,6 +652,7 @@ k_pcg_ebe(const EbeArgs a) {
         const int64_t i = i0 + u * nth;
         if (i >= n) continue;
         for (int32_t k = lo[u] + 2; k < hi[u]; ++k) {
+          if (a.be) bt[u] = fma(a.scale_b, a.be[a.vsrc[k]], bt[u]);
           if (MI > 0) bt[u] -= a.ev[a.vsrc[k]];
           if (a.warm) rw[u] += a.ev2[a.vsrc[k]];
         }
@@ -906,7 +927,8 @@ k_pcg_ebe(const EbeArgs a) {
     double bi[MIa], xf[MB];
     const int8_t* __restrict__ sg = CLS ? a.sg + c * a.mloc : nullptr;
 #pragma unroll
-    for (int t = 0; t < MI; ++t) bi[t] = a.scale_b * a.b[n + c * MI + t] * (sg ? (double)sg[MB + t] : 1.0);
+    for (int t = 0; t < MI; ++t)
+      bi[t] = a.scale_b * (a.be ? a.be[(int64_t)(MB + t) * nc + c] : a.b[n + c * MI + t]) * (sg ? (double)sg[MB + t] : 1.0);
 #pragma unroll
     for (int j = 0; j < MB; ++j) {
       const int32_t e = __ldg(a.dofT + (int64_t)j * nc + c);
@@ -1260,7 +1282,7 @@ void ebe_set_scalar_mass(EbeSolver* s, int degree, const double* coef) {
 }
 
 // enqueue x = A^-1 (scale_b b), x and b over ALL free DOFs of the space (boundary first, then interior); no host sync
-void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm) {
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm, const double* be) {
   gg_ctx* ctx = s->ctx;
   gg_space* sp = s->sp;
   if (sp->n_free == 0) return;
@@ -1285,7 +1307,7 @@ void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, b
   }
   for (int k = 0; k < 3; ++k) { a.bc.start[k] = s->bc_start[k]; a.bc.size[k] = s->bc_size[k]; a.bc.off[k] = s->bc_off[k]; a.bc.b0[k] = s->bc_b0[k]; }
   a.bstart = s->bstart.p; a.rowoff = s->rowoff.p; a.bsize = s->bsize.p; a.binv = s->binv.p;
-  a.b = b; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
+  a.b = be ? nullptr : b; a.be = be; a.scale_b = scale_b; a.x = x; a.ra = s->r.p; a.rb = s->r2.p; a.z = s->z.p; a.p = s->p.p; a.Ap = s->Ap.p;
   a.partials = s->partials.p; a.rtol = s->rtol; a.max_iter = s->max_iter; a.stats = s->stats.p;
   a.warm = warm ? 1 : 0;
   a.dist = dist_dev(sp);

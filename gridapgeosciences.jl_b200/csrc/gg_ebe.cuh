@@ -37,7 +37,9 @@ EbeSolver* ebe_create(gg_space* sp, double rtol, int max_iter);
 void ebe_set_matrix(EbeSolver* s, const double* ebuf_full);
 void ebe_set_scalar_mass(EbeSolver* s, int degree, const double* coef);
 // warm: use the content of x as the initial guess (convergence is still measured against the right-hand side norm)
-void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm = false);
+// be != nullptr: the right-hand side in element form (entry-major element vectors [mloc][nc], what gather_vector would sum into
+// b) -- the set-up passes of the solve gather it themselves, b is not read
+void ebe_solve_async(EbeSolver* s, const double* b, double scale_b, double* x, bool warm = false, const double* be = nullptr);
 void ebe_destroy(EbeSolver* s);
 
 }  // namespace gg

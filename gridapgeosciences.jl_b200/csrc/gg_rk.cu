@@ -154,7 +154,7 @@ __global__ void k_extrapolate(int64_t n, int levels, HistPtrs H, double* __restr
   x[i] = v;
 }
 
-void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot) {
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot, const double* be) {
   EbeSolver* e = which == 0 ? rk->ebe_u : rk->ebe_q;
   if (e) {
     gg_rk_hist* H = nullptr;
@@ -180,7 +180,7 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
         rk->ctx->launches++;
       }
     }
-    ebe_solve_async(e, b, scale, x, rk->warm_start);
+    ebe_solve_async(e, b, scale, x, rk->warm_start, be);
     rk_accumulate_stats(rk, e->stats.p, e->rtol);
     if (H) {
       // newest slot moves forward; the oldest level is overwritten
@@ -191,6 +191,7 @@ void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* 
     }
   } else {
     gg_solver* s = which == 0 ? rk->solver : rk->solver_q;
+    GG_REQUIRE(!be, GG_ERR_INVALID, "element-form right-hand sides need the element-by-element solver");
     solver_solve_async(s, b, scale, x);
     rk_accumulate_stats(rk, s->stats.p, s->rtol);
   }

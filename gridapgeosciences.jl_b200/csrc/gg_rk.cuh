@@ -77,13 +77,15 @@ void build_dg_mass_inverse(gg_rk* rk);
 void rk_accumulate_stats(gg_rk* rk, const double* solver_stats, double rtol);
 // k = A^-1 (scale b) with the RT mass (which = 0) or the potential-vorticity mass (which = 1), whichever solver is active
 // slot >= 0 names the solve across steps (stage / unknown) for the extrapolated initial guess
-void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot = -1);
+// be != nullptr (element-by-element solver only): right-hand side as entry-major element vectors, gathered inside the solve
+void rk_mass_solve(gg_rk* rk, int which, const double* b, double scale, double* x, int slot = -1, const double* be = nullptr);
 void rk_combine(gg_rk* rk, int ns, const double* coef, double* out);  // out = x + sum_j coef[j] k_j
 // shallow water (gg_swe.cu)
 void swe_create(gg_rk* rk, const gg_rk_args* a);
 void swe_step_async(gg_rk* rk);
 void swe_diagnostics_async(gg_rk* rk, const double* x, double* y);
-void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp);
+// gather_u = false leaves r_u in element form (rk->evec_u) for a solve that gathers it itself
+void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp, bool gather_u = true);
 void swe_destroy(gg_rk* rk);
 // linear Boussinesq on the 3-D shell (gg_bq.cu)
 void bq_create(gg_rk* rk, const gg_rk_args* a);

@@ -560,18 +560,19 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
       gather_matrix(rk->Mq, layout, eb, 1.0, 0);
       solver_update(rk->solver_q);
     }
-    gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
-    rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq, rk->diag_slot >= 0 ? 100 + rk->diag_slot : -1);
+    // the element-by-element solver gathers the element vectors itself (one launch and one pass over the vector less per solve)
+    if (!rk->ebe_q) gather_vector(rk->R, rk->evec_q.p, rk->rhs_q.p, 1.0, 0);
+    rk_mass_solve(rk, 1, rk->rhs_q.p, 1.0, yq, rk->diag_slot >= 0 ? 100 + rk->diag_slot : -1, rk->ebe_q ? rk->evec_q.p : nullptr);
   }
   // mass flux
-  gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
-  rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF, rk->diag_slot >= 0 ? 200 + rk->diag_slot : -1);
+  if (!rk->ebe_u) gather_vector(rk->V, rk->evec_u.p, rk->rhs_F.p, 1.0, 0);
+  rk_mass_solve(rk, 0, rk->rhs_F.p, 1.0, yF, rk->diag_slot >= 0 ? 200 + rk->diag_slot : -1, rk->ebe_u ? rk->evec_u.p : nullptr);
   if (rk->thermal) tswe_diagnostics_async(rk, x, y);   // Phi += 0.5 B, b
   rk->diag_solves++;
 }
 
 // r = [r_u; r_p]; kp (optional) receives the depth slope -Mp^-1 r_p
-void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp) {
+void swe_residual_async(gg_rk* rk, const double* x, const double* y, const double* q0, double* r, double* kp, bool gather_u) {
   gg_ctx* ctx = rk->ctx;
   cudaStream_t st = ctx->stream;
   const int64_t nc = rk->mesh->n_cells;
@@ -647,7 +648,7 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
     GG_CUDA(cudaGetLastError());
   }
   if (rk->thermal) tswe_residual_async(rk, x, y, r + rk->nu + rk->np, kp ? kp + rk->np : nullptr);
-  gather_vector(rk->V, rk->evec_u.p, r, 1.0, 0);
+  if (gather_u) gather_vector(rk->V, rk->evec_u.p, r, 1.0, 0);
 }
 
 // one ode_march! (src/ODEs/RungeKuttaEX.jl:48-134).  The reference solves the diagnostics five times per SSPRK3 step; two of
@@ -683,8 +684,8 @@ void swe_step_async(gg_rk* rk) {
     }
     // :100-117 slope: M k = -(res_x + mass(0))
     const double* q0 = rk->q0_mode == GG_Q0_START_OF_STEP ? rk->q0.p : rk->y.p;
-    swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu);
-    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p, i);
+    swe_residual_async(rk, xs, rk->y.p, q0, rk->r.p, rk->k[i].p + rk->nu, rk->ebe_u == nullptr);
+    rk_mass_solve(rk, 0, rk->r.p, -1.0, rk->k[i].p, i, rk->ebe_u ? rk->evec_u.p : nullptr);
   }
   // :121-122 update, :125-127 final diagnostics
   double co[4] = {0, 0, 0, 0};
