@@ -23,6 +23,7 @@ namespace gg {
 
 void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int add);
 void gather_vector(gg_space* s, const double* ebuf, double* out, double scale, int add);
+void gather_matrix_and_vector(gg_csr* A, int layout, const double* ebuf, const double* vbuf, double* vec_out, double scale, int add);
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
@@ -507,7 +508,7 @@ static bool run_lb_tile(gg_mesh* m, int order, int nq, bool extrinsic, const int
 }
 
 static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int32_t* dofs, const double* u,
-                        double dir, double* ebuf, double* vbuf, const FillPipe* pipe) {
+                        double dir, double* ebuf, double* vbuf, FillPipe* pipe) {
   gg_ctx* ctx = m->ctx;
   load_const_tables(ctx, order, nq);
   CellGeo g = cell_geo(m, nq);
@@ -537,7 +538,13 @@ static void run_lb_fast(gg_mesh* m, int order, int nq, bool extrinsic, const int
   if (!pipe || !want_pipeline || nc < 64 * 1024 || ctx->profile) {
     // default, small meshes (launch-bound) and per-kernel profiling runs: one element launch, one fill launch
     run_lb_fast_range(m, order, nq, extrinsic, 0, nc, g, dofs, u, dir, ebuf, vbuf);
-    if (pipe) gather_matrix(pipe->A, 1, ebuf, pipe->scale, pipe->add);
+    if (pipe && pipe->vec_out && vbuf && !pipe->vec_done) {
+      // matrix and residual of one call: the DOF gather of the residual rides on the CSR fill launch
+      gather_matrix_and_vector(pipe->A, 1, ebuf, vbuf, pipe->vec_out, pipe->scale, pipe->add);
+      pipe->vec_done = true;
+    } else if (pipe) {
+      gather_matrix(pipe->A, 1, ebuf, pipe->scale, pipe->add);
+    }
     return;
   }
   prepare_gather(pipe->A, 1);

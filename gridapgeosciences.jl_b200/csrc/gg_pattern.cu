@@ -228,11 +228,32 @@ k_chunk_batch(int64_t nc, int R, int n_batch, const int32_t* __restrict__ roundp
   }
 }
 
+// optional second job of a k_gather_chunks launch: CTAs [first_cta, gridDim.x) gather a DOF vector
+struct VecGather {
+  unsigned first_cta = 0xffffffffu;
+  int64_t n_free = 0;
+  const int32_t *vptr = nullptr, *vsrc = nullptr;
+  const double* vbuf = nullptr;
+  double* out = nullptr;
+};
+
 __global__ void __launch_bounds__(256)
 k_gather_chunks(int64_t nnz, int R, const int32_t* __restrict__ chunk_order, const int32_t* __restrict__ roundptr,
                 const int32_t* __restrict__ lsrc, const uint16_t* __restrict__ lslot, const double* __restrict__ ebuf,
-                double* __restrict__ vals, double scale, int add) {
+                double* __restrict__ vals, double scale, int add, VecGather vg) {
   __shared__ double acc[GATHER_CHUNK];
+  if (blockIdx.x >= vg.first_cta) {
+    // the trailing CTAs of a fused launch gather the element vectors into the DOF vector (k_gather_dofs): on slices of a few
+    // hundred CTAs a separate launch costs more than the rows themselves
+    const int64_t d = (int64_t)(blockIdx.x - vg.first_cta) * blockDim.x + threadIdx.x;
+    if (d < vg.n_free) {
+      double a = 0.0;
+      for (int32_t k = vg.vptr[d]; k < vg.vptr[d + 1]; ++k) a += vg.vbuf[vg.vsrc[k]];
+      a *= scale;
+      vg.out[d] = add ? vg.out[d] + a : a;
+    }
+    return;
+  }
   const int64_t chunk = chunk_order[blockIdx.x];
   const int32_t* rp = roundptr + chunk * (R + 1);
   for (int r = 0; r < R; ++r) {
@@ -340,7 +361,28 @@ void gather_matrix(gg_csr* A, int layout, const double* ebuf, double scale, int 
   build_chunk_lists(A, layout);
   ProfScope ps(ctx, "k_gather_chunks");
   k_gather_chunks<<<(unsigned)A->n_chunks, 256, 0, ctx->stream>>>(A->nnz, A->n_rounds, A->d_chunk_order.p, A->d_roundptr.p,
-                                                                  A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add);
+                                                                  A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add,
+                                                                  VecGather());
+  ctx->launches++;
+  GG_CUDA(cudaGetLastError());
+}
+
+// CSR fill and DOF-vector gather of the test space in ONE launch (same scale / add for both)
+void gather_matrix_and_vector(gg_csr* A, int layout, const double* ebuf, const double* vbuf, double* vec_out, double scale, int add) {
+  gg_ctx* ctx = A->ctx;
+  gg_space* s = A->test;
+  if (A->nnz == 0 || s->n_free == 0) {
+    gather_matrix(A, layout, ebuf, scale, add);
+    gather_vector(s, vbuf, vec_out, scale, add);
+    return;
+  }
+  build_chunk_lists(A, layout);
+  build_vec_map(s);
+  VecGather vg;
+  vg.first_cta = (unsigned)A->n_chunks; vg.n_free = s->n_free; vg.vptr = s->d_vptr.p; vg.vsrc = s->d_vsrc.p; vg.vbuf = vbuf; vg.out = vec_out;
+  ProfScope ps(ctx, "k_gather_chunks");
+  k_gather_chunks<<<(unsigned)A->n_chunks + nblk(s->n_free, 256), 256, 0, ctx->stream>>>(
+      A->nnz, A->n_rounds, A->d_chunk_order.p, A->d_roundptr.p, A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add, vg);
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
 }
@@ -350,7 +392,7 @@ void gather_matrix_batch(gg_csr* A, int batch, const double* ebuf, double scale,
   int64_t c0 = A->batch_chunk_ptr[batch], c1 = A->batch_chunk_ptr[batch + 1];
   if (c1 == c0) return;
   k_gather_chunks<<<(unsigned)(c1 - c0), 256, 0, st>>>(A->nnz, A->n_rounds, A->d_chunk_order.p + c0, A->d_roundptr.p,
-                                                       A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add);
+                                                       A->d_lsrc.p, A->d_lslot.p, ebuf, A->d_vals.p, scale, add, VecGather());
   ctx->launches++;
   GG_CUDA(cudaGetLastError());
 }
