@@ -631,6 +631,29 @@ def assembly_limiter(leg, roofline, world):
 ASSEMBLY_KERNELS = ("k_lb_tile", "k_lb_tile_groups", "k_lb_fast", "k_gather_chunks", "k_gather_dofs")
 
 
+def bind_host_to_gpu(torch, device):
+    """Multi-rank runs: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned allocation (first touch
+    puts the pinned pages there), so that the 8 concurrent device -> host copies of the e2e leg do not cross the socket link.
+    Returns what was done for the JSON line; a box without the sysfs entries is left alone."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"pci": bus, "numa_node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"pci": bus, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as ex:   # no sysfs, no permission, older torch: not an error
+        return {"bound": False, "why": str(ex)[:120]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -663,6 +686,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
+    numa = bind_host_to_gpu(torch, local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -779,7 +803,8 @@ def main():
             t = torch.tensor([ms2], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms2 = float(t.item())
-        line["e2e"] = {"value": total_owned / (ms2 / Ke2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": 8 * V.num_free_dofs,
+        line["e2e"] = {"host_numa_binding_rank0": numa,
+                       "value": total_owned / (ms2 / Ke2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": 8 * V.num_free_dofs,
                        "d2h_bytes_per_step": 8 * (A.nnz + V.num_free_dofs), "ms_per_step": ms2 / Ke2e,
                        "api": "DeviceVector.set(host u) + assemble_matrix_and_vector + CSRMatrix.values(host) + DeviceVector.get(host)",
                        "bound": "PCIe: the 201 MB of CSR values dominate (the kernels are 0.28 ms of the step)"}
