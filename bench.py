@@ -809,9 +809,9 @@ def main():
                        "api": "DeviceVector.set(host u) + assemble_matrix_and_vector + CSRMatrix.values(host) + DeviceVector.get(host)",
                        "aggregate_d2h_gbs": world * 8 * (A.nnz + V.num_free_dofs) / (ms2 / Ke2e * 1e-3) / 1e9,
                        "bound": ("PCIe: the 201 MB of CSR values dominate (the kernels are 0.28 ms of the step)" if world == 1 else
-                                 "host side of PCIe: the ranks' device -> host copies of their CSR slices run concurrently and the box "
-                                 "delivers the same aggregate rate at N = 2, 4 and 8 (aggregate_d2h_gbs, about twice the single-GPU "
-                                 "rate; one NUMA node, see host_numa_binding_rank0), so the e2e step time stays at the N = 2 figure")}
+                                 "host side of PCIe: the ranks' device -> host copies of their CSR slices run concurrently; the "
+                                 "aggregate rate the box delivers (aggregate_d2h_gbs; 92-161 GB/s on the boxes of this pool, against "
+                                 "48 GB/s for one GPU) sets the step time, not the kernels")}
 
         # the same call when the Jacobian stays on the device for a device-side solver (GPULinearSolver in INTEGRATION.md):
         # only the state goes in and the residual comes out
