@@ -14,6 +14,7 @@ import torch.multiprocessing as mp
 from __graft_entry__ import load_package
 
 SPACES = [(2, 0), (2, 1), (2, 2), (0, 1), (0, 3), (1, 2)]   # (kind, order): RT0-2, CG1, CG3, DG2
+SPACES_SHELL = [(0, 1), (0, 2), (1, 1), (2, 0), (2, 1)]     # hexahedra: CG1, CG2, DG1, RT0, RT1
 
 
 def _free_port():
@@ -24,24 +25,37 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n):
+def _worker(rank, world, port, n, shell=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         gg = load_package()
-        plan = gg.PartitionPlan(n, world, rank)
-        nc = 6 * n * n
-        # linear partition of the reference: part(i) = div((i-1)*P, Nc) + 1 (1-based i)
-        cells = np.arange(nc)
-        mine = cells[(cells * world) // nc == rank]
+        if shell:
+            # 3-D shell in p8est order (Morton per tree), equal-count chunks of the space-filling curve
+            # (src/Distributed/AtlasOctreeDistributedDiscreteModels.jl:286-294)
+            plan = gg.PartitionPlan(n, world, rank, thickness=0.19, ordering=2, n_layers=n)
+            nc = 6 * n * n * n
+            ranges = [None] * world
+            dist.all_gather_object(ranges, (plan.first_owned, plan.last_owned))
+            assert ranges[0][0] == 0 and ranges[-1][1] == nc and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+            counts = [b - a for a, b in ranges]
+            assert max(counts) - min(counts) <= 1
+            mine = np.arange(plan.first_owned, plan.last_owned)
+        else:
+            plan = gg.PartitionPlan(n, world, rank)
+            nc = 6 * n * n
+            # linear partition of the reference: part(i) = div((i-1)*P, Nc) + 1 (1-based i)
+            cells = np.arange(nc)
+            mine = cells[(cells * world) // nc == rank]
+        assert plan.num_cells_global == nc
         assert plan.first_owned == mine[0] and plan.last_owned == mine[-1] + 1
         lc = plan.local_cells()
         assert (np.diff(lc) > 0).all() and set(mine) <= set(lc) and len(lc) > len(mine)
         owned_cells = torch.tensor([plan.last_owned - plan.first_owned])
         dist.all_reduce(owned_cells)
         assert owned_cells.item() == nc
-        for kind, order in SPACES:
+        for kind, order in (SPACES_SHELL if shell else SPACES):
             sp = plan.space(kind, order)
             l2g, owner = sp["l2g"], sp["owner"]
             assert (np.diff(l2g) > 0).all() and owner.min() >= 0 and owner.max() < world
@@ -88,6 +102,11 @@ def _worker(rank, world, port, n):
 @pytest.mark.parametrize("world,n", [(2, 4), (3, 5)])
 def test_partition_plans_of_all_ranks_fit_together(world, n):
     mp.spawn(_worker, args=(world, _free_port(), n), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,n", [(2, 2), (3, 4)])
+def test_shell_plans_in_p8est_order_fit_together(world, n):
+    mp.spawn(_worker, args=(world, _free_port(), n, True), nprocs=world, join=True)
 
 
 def test_single_rank_plan_is_the_whole_model():
