@@ -203,3 +203,22 @@ def test_solver_variants_of_the_condensed_pcg_agree():
                               "steps_match_oracle or diagnostics_and_stage"], env=dict(os.environ, **extra), capture_output=True,
                              text=True, timeout=900)
         assert out.returncode == 0, (extra, out.stdout[-2000:], out.stderr[-1000:])
+
+
+@pytest.mark.parametrize("n,p", [(9, 1), (7, 2)])
+def test_cell_kernels_are_deterministic(gg, n, p):
+    """The lane kernels exchange row records through shared memory between the lanes of a group with warp-level barriers only;
+    a missing barrier would show up as run-to-run differences.  Same input, repeated launches: bitwise equal output (sizes that
+    leave a partial warp batch at the end)."""
+    mesh = CubedSphereMesh2D(n)
+    P = oswe.ShallowWaterProblem(mesh, p)
+    dt = oswe.reference_dt(mesh, max(p, 1))
+    model, st = _stepper(gg, n, p, dt)
+    rng = np.random.default_rng(5)
+    x = P.initial_state()
+    x = x * (1 + 0.05 * rng.standard_normal(x.size))
+    y0 = st.diagnostics(x)
+    r0 = st.stage_residual(x, y0)
+    for _ in range(5):
+        assert np.array_equal(st.diagnostics(x), y0)
+        assert np.array_equal(st.stage_residual(x, y0), r0)

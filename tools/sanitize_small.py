@@ -42,6 +42,11 @@ for p in (0, 1, 2):
         st.set_state(x0)
         st.step(2)
         assert np.isfinite(st.get_state()).all()
+    if p == 1:
+        stt = gg.RKStepper(rk, gg.ThermalShallowWaterOperator(model, p, ic.coriolis))
+        stt.set_state(np.concatenate([x0, 0.1 * x0[Vr.num_free_dofs:]]))
+        stt.step(2)
+        assert np.isfinite(stt.get_state()).all()
     wind = lambda X: np.stack([-X[..., 1], X[..., 0], 0 * X[..., 0]], -1)   # noqa: E731
     sa = gg.RKStepper(gg.RungeKutta(None, None, 0.01, "EXRK_SSP_2_2"), gg.AdvectionOperator(model, p, wind, degree=max(4 * p, 2)))
     sa.set_state(gg.interpolate(ic.williamson2_depth, Q).get())
