@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--order", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--rtol", type=float, default=1e-12)
+    ap.add_argument("--thermal", action="store_true", help="thermal shallow water (adds the buoyancy field and its skeleton terms)")
     args = ap.parse_args()
     gg = load_package()
     ctx = gg.get_context(0)
@@ -51,6 +52,12 @@ def main():
     x0 = np.concatenate([gg.interpolate(velocity, V).get(), gg.interpolate(depth, Q).get()])
     dt = gg.dx(model) * 0.1 / (max(p, 1) * np.sqrt(G * H0))
     op = gg.ShallowWaterOperator(model, p, coriolis, gravity=G)
+    if args.thermal:
+        ic = gg.initial_conditions
+        x0 = np.concatenate([gg.interpolate(ic.williamson2_velocity, V).get(), gg.interpolate(ic.williamson2_depth, Q).get(),
+                             gg.interpolate(ic.thermogeostrophic_weighted_buoyancy, Q).get()])
+        dt = gg.dx(model) * 0.1 / (max(p, 1) * np.sqrt(ic.GRAVITY * ic.H0_W2))
+        op = gg.ThermalShallowWaterOperator(model, p, ic.coriolis)
     st = gg.RKStepper(gg.RungeKutta(gg.CGSolver(rtol=args.rtol), None, dt, "EXRK_SSP_3_3"), op)
     st.set_state(x0)
     setup_s = time.perf_counter() - t0
@@ -61,7 +68,7 @@ def main():
     it0, so0 = st.stats()
     ctx.profile(True)
     st.step(args.steps)
-    names = ["k_swe_diag", "k_swe_stage", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs", "k_block_inverse", "k_pcg_persistent", "k_pcg_mf", "k_pcg_ebe", "k_ebe_condense", "k_ebe_precond", "k_ebe_scalar_mass"]
+    names = ["k_swe_diag", "k_swe_stage", "k_scalar_matrix", "k_gather_chunks", "k_gather_dofs", "k_block_inverse", "k_pcg_persistent", "k_pcg_mf", "k_pcg_ebe", "k_ebe_condense", "k_ebe_precond", "k_ebe_scalar_mass", "k_tswe_buoyancy", "k_tswe_stage", "k_consistent", "k_extrapolate"]
     prof = {}
     for nme in names:
         cnt, ms = ctx.profile_query(nme)
