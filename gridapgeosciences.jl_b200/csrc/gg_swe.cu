@@ -473,10 +473,16 @@ static void swe_sf_tabs(gg_rk* rk) {
 }
 
 // (order, points per direction) pairs the lane-parallel kernels are instantiated for: the default rules of the drivers
-// (degree 4 (K + 1): 3, 5, 7 points; thermal shallow water 4 K: 3 points for K = 1) and degree 8 for K = 2
+// (degree 4 (K + 1): 3, 5, 7 points; thermal shallow water 4 K: 3 points for K = 1) and degree 8 for K = 2.
+// ONE list: the predicate and the two dispatches expand it, so they cannot disagree.
+#define GG_LANE_PAIRS(X) X(0, 3) X(1, 3) X(1, 5) X(2, 5) X(2, 7)
 static bool swe_lanes_enabled(int K, int nq) {
   static const bool on = !(getenv("GG_SWE_LANES") && getenv("GG_SWE_LANES")[0] == '0');
-  return on && ((K == 0 && nq == 3) || (K == 1 && (nq == 3 || nq == 5)) || (K == 2 && (nq == 5 || nq == 7)));
+  bool have = false;
+#define GG_PAIR(K_, NQ_) have = have || (K == K_ && nq == NQ_);
+  GG_LANE_PAIRS(GG_PAIR)
+#undef GG_PAIR
+  return on && have;
 }
 
 template <typename Kern, typename... Args>
@@ -519,7 +525,7 @@ void swe_diagnostics_async(gg_rk* rk, const double* x, double* y) {
     swe_launch_lanes(ctx, k_swe_diag_lanes<K_, NQ_>, nc, SweLanes<K_, NQ_>::CPB, SweLanes<K_, NQ_>::diag_smem(), g,        \
                      ctx->swe_lane_tab.p, rk->V->d_cell_dofs.p, rk->V->d_cell_signs.p, u, p, rk->fq.p,                     \
                      rk->bq.n ? rk->bq.p : nullptr, rk->gravity, rk->MpInv.p, rk->pq->d.p, rk->evec_q.p, rk->evec_u.p, yP);
-    GG_LANES(0, 3) GG_LANES(1, 3) GG_LANES(1, 5) GG_LANES(2, 5) GG_LANES(2, 7)
+    GG_LANE_PAIRS(GG_LANES)
 #undef GG_LANES
     ctx->launches++;
     GG_CUDA(cudaGetLastError());
@@ -594,7 +600,7 @@ void swe_residual_async(gg_rk* rk, const double* x, const double* y, const doubl
   if (rk->order == K_ && rk->nq1 == NQ_) {                                                                                 \
     if (alias) { GG_LANES_A(K_, NQ_, true) } else { GG_LANES_A(K_, NQ_, false) }                                           \
   }
-    GG_LANES(0, 3) GG_LANES(1, 3) GG_LANES(1, 5) GG_LANES(2, 5) GG_LANES(2, 7)
+    GG_LANE_PAIRS(GG_LANES)
 #undef GG_LANES
 #undef GG_LANES_A
     ctx->launches++;
