@@ -11,8 +11,7 @@
 //            __threadfence_system() -- fences are cumulative, so it also orders the other threads' stores -- and then
 //            stores flag[me] = epoch into every peer window.  (A system-scope fence in every writer thread is not needed
 //            and is expensive.)
-//   reader:  one thread of every CTA spins (volatile loads of its OWN window) until flag[r] >= epoch for all r, fences, and the
-//            CTA reads the data behind a __syncthreads (no second grid barrier)
+//   reader:  one thread spins (volatile loads of its OWN window) until flag[r] >= epoch for all r ; grid barrier ; read data
 // Reduction operands AND the exchange slot are double-buffered by the parity of the round that completes them (a rank can be
 // at most one round ahead of a peer, because it needs that peer's flag to finish a round: data stored for round e is read
 // after round e and before the reader posts e+1; the next store into the same half belongs to round e+2, whose writer has
@@ -89,22 +88,15 @@ __device__ __forceinline__ void dist_unpack(const DistDev& d, unsigned long long
 
 // One round: all-reduce of NV values (val holds the rank-local totals in every thread on entry, the global totals on exit)
 // and, implicitly, completion of every dist_push issued before the grid barrier that precedes this call.
-// Must be called by all threads of a cooperative grid, after a grid barrier (the caller's: it completes the pushes and the local
-// totals).  No grid barrier inside: one thread posts, and thread 0 of EVERY CTA waits for the peers' flags itself (its own
-// window: local L2 reads) and broadcasts the sums through shared memory -- a CTA leaves the round as soon as the data it is
-// about to read has arrived, instead of after a second grid-wide barrier (2-3 us on 296 CTAs, twice per CG iteration).  CTAs
-// cannot drift by a round: the next round starts behind the caller's next grid barrier.
+// Must be called by all threads of a cooperative grid; contains one grid barrier.
 template <int NV>
 __device__ __forceinline__ void dist_allreduce(cooperative_groups::grid_group& grid, const DistDev& d, unsigned long long& epoch,
                                                double (&val)[NV]) {
-  (void)grid;
   ++epoch;
   const int par = (int)(epoch & 1ull);
   WinHeader* mine = d.win[d.rank];
-  const bool poster = blockIdx.x == 0 && threadIdx.x == 0;
-  unsigned long long tp = 0;
-  if (poster) {
-    tp = dist_now();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long tp = dist_now();
     for (int r = 0; r < d.world; ++r) {
       volatile double* dst = d.win[r]->red[par][d.rank];
 #pragma unroll
@@ -113,11 +105,6 @@ __device__ __forceinline__ void dist_allreduce(cooperative_groups::grid_group& g
     __threadfence_system();
     for (int r = 0; r < d.world; ++r)
       if (r != d.rank) *(volatile unsigned long long*)&d.win[r]->flag[d.rank] = epoch;
-  }
-  // one thread per CTA waits and reads the operands (a volatile read by every thread of the grid serialises 2400 warps on one L2
-  // line: measured 35 us on B200) and broadcasts the sums through shared memory
-  __shared__ double bc[GG_RED_WIDTH];
-  if (threadIdx.x == 0) {
     const unsigned long long t0 = dist_now();
     for (int r = 0; r < d.world; ++r) {
       if (r == d.rank) continue;
@@ -128,13 +115,18 @@ __device__ __forceinline__ void dist_allreduce(cooperative_groups::grid_group& g
       }
     }
     __threadfence_system();
-    if (poster && d.timing) { mine->wait_ns += dist_now() - t0; mine->post_ns += t0 - tp; mine->rounds += 1; }
+    const unsigned long long t1 = dist_now();
+    if (d.timing) { mine->wait_ns += t1 - t0; mine->post_ns += t0 - tp; mine->rounds += 1; }
+  }
+  grid.sync();
+  // one thread per CTA reads the operands (a volatile read by every thread of the grid serialises 2400 warps on one L2
+  // line: measured 35 us on B200) and broadcasts the sums through shared memory
+  __shared__ double bc[GG_RED_WIDTH];
+  if (threadIdx.x == 0) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       double s = 0.0;
-      // own operand from the register (the poster's store into this rank's own window has no flag to wait for); the sum still
-      // runs over the ranks in rank order with the same operands on every rank
-      for (int r = 0; r < d.world; ++r) s += r == d.rank ? val[v] : *(volatile double*)&mine->red[par][r][v];
+      for (int r = 0; r < d.world; ++r) s += *(volatile double*)&mine->red[par][r][v];
       bc[v] = s;
     }
   }
