@@ -615,9 +615,11 @@ def assembly_limiter(leg, roofline, world):
     gap = leg["ms_per_step"] - ksum
     ctas = leg["cells_local_incl_ghosts"] / 128.0
     if ctas < 3 * 148:
+        nk = sum(1 for v in k.values() if v)
         what = (f"less than one wave of CTAs: the slice is {ctas:.0f} 128-cell CTAs for 444 CTA slots (3 per SM), so the element kernel "
-                f"lasts one CTA lifetime (its warps are latency-bound) instead of scaling with the cell count; the 3 kernels of a step "
-                f"sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step (L2 flushed before every step)")
+                f"runs as ONE wave at the FP64 pipe's rate with nothing to overlap its start-up, tail and the CSR fill behind it; the "
+                f"{nk} kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step (L2 flushed before every "
+                f"step); FP64 work of the slice at the probe's peak: {roofline['step_level']['fp64_work_ms_at_probe_peak'] * 1e3:.1f} us")
     elif gap > 0.25 * leg["ms_per_step"]:
         what = f"launch / tail latency: the kernels of a step sum to {ksum * 1e3:.1f} us of a {leg['ms_per_step'] * 1e3:.1f} us step"
     elif ghost > 0.1:
