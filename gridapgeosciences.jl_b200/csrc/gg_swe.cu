@@ -16,11 +16,13 @@
 // B200 design
 //   * state, slopes, diagnostics and every operator stay resident in HBM/L2; a step enqueues a fixed sequence of
 //     launches with no host synchronisation (PCG iteration counts are decided inside the persistent solver kernel);
-//   * the nonlinear cell integrals run one thread per cell with all accumulators in FP64 registers; tangents of the
-//     quadrature abscissae come from the per-mesh tables (no tan() in the kernels), basis tabulations are read
-//     warp-uniformly through L1;
-//   * terms that are linear with constant coefficients collapse to the reference matrix Bhat (the Jacobian determinant
-//     cancels in int q div(u) under the contravariant Piola map), so -int Phi div(v) and int r div(F) need no quadrature;
+//   * the nonlinear cell integrals are sum-factorised with 4 or 8 lanes of a warp per cell, one row of the tensor rule per lane
+//     (gg_swe_lanes.cuh; the rules the drivers use by default) -- or, for any other rule, one thread per cell with all accumulators
+//     in FP64 registers (gg_swe_sf.cuh and the direct kernels below); tangents of the quadrature abscissae come from the per-mesh
+//     tables (no tan() in the kernels), 1-D basis tables are immediate / warp-uniform constant operands;
+//   * terms that are linear with constant coefficients need no metric (the Jacobian determinant cancels in int q div(u) under the
+//     contravariant Piola map): the one-thread kernels apply the reference matrix Bhat, the lane kernels integrate them on the
+//     same rows with plain reference weights;
 //   * the Bernoulli potential and the depth slope are cell-local (DG): the inverse mass block is applied inside the
 //     kernel that computed the right-hand side; RT and CG right-hand sides go through the atomic-free DOF gather.
 #include <cstring>
