@@ -102,15 +102,15 @@ class ClockSampler:
 # reference does not contain it)
 
 
-def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10, dist=None, rank=0, world=1, state="galewsky"):
+def swe_leg(gg, ctx, torch, stream, e0, e1, n=256, p=2, steps=10, dist=None, rank=0, world=1, state="galewsky", partition="linear"):
     """RK steps/s of the shallow-water DAE stepper.  world > 1: the n x n-per-panel model is partitioned over the ranks
-    (linear partition + ghost layer of the reference); halo exchange and dot products go through peer memory inside the
-    solver kernels, the time is the max over ranks."""
+    (linear partition + ghost layer of the reference; partition="strips": the opt-in panel strips of gg_plan_create_strips);
+    halo exchange and dot products go through peer memory inside the solver kernels, the time is the max over ranks."""
     ctx.set_async(False)
     mesh = gg.CubedSphereMesh(1.0)
     keep = []
     if world > 1:
-        plan = gg.PartitionPlan(n, world, rank)
+        plan = gg.PartitionPlan(n, world, rank, partition=partition)
         comm = gg.PeerWindow(ctx, rank, world, gg.window_doubles(plan, p))
         comm.connect()
         model = gg.partitioned_model(mesh, plan, comm, ctx=ctx)
@@ -499,7 +499,7 @@ def assembly_leg(gg, ctx, torch, dist, stream, n, rank, world, W, K, profile=Tru
         # restricted to the local cells (compact: vectors and row pointers have the size of the slice)
         keep = gg.PartitionPlan(n, world, rank)
         model = gg.partitioned_model(mesh, keep, None, ctx=ctx)
-        ncells_global, owned = keep.num_cells_global, keep.last_owned - keep.first_owned
+        ncells_global, owned = keep.num_cells_global, keep.num_owned_cells
     else:
         model = gg.AtlasDiscreteModel(mesh, n=n, ctx=ctx)
         ncells_global = owned = model.num_cells
@@ -924,6 +924,14 @@ def main():
             sw = {"error": str(ex)}
         line.setdefault("rk", {})["shallow_water"] = sw
         try:
+            ss = swe_leg(gg, ctx, torch, stream, e0, e1, n=nn, dist=dist, rank=rank, world=world, partition="strips")
+            line["rk"]["shallow_water_panel_strips"] = {k: ss[k] for k in ("ms_per_step", "steps_per_s", "cells_local_incl_ghosts",
+                                                                           "pcg_iters_per_solve", "pcg_us_per_iter") if k in ss}
+            line["rk"]["shallow_water_panel_strips"]["what"] = ("the same step on the opt-in partition of gg_plan_create_strips (same rows of "
+                                                                "cells on all six panels) instead of the reference's linear cut")
+        except Exception as ex:
+            line["rk"]["shallow_water_panel_strips"] = {"error": str(ex)}
+        try:
             ad = adv_leg(gg, ctx, torch, stream, e0, e1, n=128 if args.scaling == "strong" else int(round(128 * math.sqrt(world))),
                          dist=dist, rank=rank, world=world)
         except Exception as ex:
@@ -950,6 +958,13 @@ def main():
                 ow["shallow_water"] = swe_leg(gg, ctx, torch, stream, e0, e1, n=no, steps=6, dist=dist, rank=rank, world=world)
             except Exception as ex:
                 ow["shallow_water"] = {"error": str(ex)}
+            try:
+                # the same leg on the opt-in panel-strip partition (every rank keeps the six congruent cells of a geometry class)
+                ss = swe_leg(gg, ctx, torch, stream, e0, e1, n=no, steps=6, dist=dist, rank=rank, world=world, partition="strips")
+                ow["shallow_water_panel_strips"] = {k: ss[k] for k in ("ms_per_step", "steps_per_s", "cells_local_incl_ghosts",
+                                                                        "pcg_iters_per_solve", "pcg_us_per_iter") if k in ss}
+            except Exception as ex:
+                ow["shallow_water_panel_strips"] = {"error": str(ex)}
             line[other] = ow
         except Exception as ex:
             line[other] = {"error": str(ex)}

@@ -208,13 +208,21 @@ class PartitionPlan:
     (src/Distributed/AtlasDistributedDiscreteModels.jl:20-73): owned cell range, ghost layer, and per FE space the
     local -> global DOF map, DOF owners and exchange lists.  Pure host computation (no GPU, no communication)."""
 
-    def __init__(self, n, nparts, part, radius=1.0, thickness=None, ordering=0, n_layers=0):
+    def __init__(self, n, nparts, part, radius=1.0, thickness=None, ordering=0, n_layers=0, partition="linear"):
         """thickness given: the 3-D shell (AtlasOctreeDistributedDiscreteModel on CubedSphereWithThicknessMesh; ordering 2 = the
-        p8est cell order, equal-count chunks of the space-filling curve)."""
+        p8est cell order, equal-count chunks of the space-filling curve).  partition="strips" (2-D sphere, opt-in): every rank owns
+        the same rows of cells on all six panels instead of the reference's linear cut (include/geosgpu.h, gg_plan_create_strips)."""
         self.lib = _lib.load()
         self.n, self.nparts, self.part, self.radius = int(n), int(nparts), int(part), float(radius)
+        if partition not in ("linear", "strips"):
+            raise ValueError("partition must be 'linear' or 'strips'")
+        self.partition = partition
         h = C.c_void_p()
-        if thickness is not None:
+        if partition == "strips":
+            if thickness is not None:
+                raise ValueError("panel strips are a partition of the 2-D sphere")
+            _lib.check(self.lib.gg_plan_create_strips(self.n, self.radius, self.nparts, self.part, C.byref(h)))
+        elif thickness is not None:
             _lib.check(self.lib.gg_plan_create_shell(self.n, int(n_layers), self.radius, float(thickness), int(ordering), self.nparts,
                                                      self.part, C.byref(h)))
         else:
@@ -223,6 +231,9 @@ class PartitionPlan:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.gg_plan_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         self.num_cells_global, self.first_owned, self.last_owned, self.num_local_cells = a.value, b.value, c.value, d.value
+        no = C.c_int64()
+        _lib.check(self.lib.gg_plan_owned_cells(self.h, C.byref(no)))
+        self.num_owned_cells = no.value
 
     def local_cells(self):
         out = np.empty(self.num_local_cells, dtype=np.int64)

@@ -86,6 +86,8 @@ SIGNATURES = {
     "gg_mesh_ghost_cells": (C.c_int, [_P, _I64, _I64, _PI64, _PI64]),
     "gg_plan_create": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, _PP]),
     "gg_plan_create_shell": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _PP]),
+    "gg_plan_create_strips": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, _PP]),
+    "gg_plan_owned_cells": (C.c_int, [_P, _PI64]),
     "gg_plan_destroy": (None, [_P]),
     "gg_plan_info": (C.c_int, [_P, _PI64, _PI64, _PI64, _PI64]),
     "gg_plan_local_cells": (C.c_int, [_P, _PI64]),

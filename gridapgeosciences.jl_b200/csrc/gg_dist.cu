@@ -31,15 +31,17 @@ namespace gg {
 
 static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-static std::vector<int64_t> ghost_cells_of(const gg_mesh* m, int64_t first, int64_t last) {
+// vertex-adjacent cells of the cells owned by rank r that r does not own
+static std::vector<int64_t> ghost_cells_of(const gg_mesh* m, const std::vector<int32_t>& cell_owner, int r) {
   const int nv = m->dim == 3 ? 8 : 4;
   const std::vector<int32_t>& cn = m->dim == 3 ? m->cell_nodes8 : m->cell_nodes;
   std::vector<uint8_t> touched(m->n_nodes, 0);
-  for (int64_t c = first; c < last; ++c)
-    for (int v = 0; v < nv; ++v) touched[cn[c * nv + v]] = 1;
+  for (int64_t c = 0; c < m->n_cells; ++c)
+    if (cell_owner[c] == r)
+      for (int v = 0; v < nv; ++v) touched[cn[c * nv + v]] = 1;
   std::vector<int64_t> out;
   for (int64_t c = 0; c < m->n_cells; ++c) {
-    if (c >= first && c < last) continue;
+    if (cell_owner[c] == r) continue;
     bool near = false;
     for (int v = 0; v < nv; ++v) near = near || touched[cn[c * nv + v]];
     if (near) out.push_back(c);
@@ -51,13 +53,29 @@ static void plan_partition(gg_plan* P) {
   const int64_t Nc = P->gmesh->n_cells;
   const int nparts = P->nparts;
   GG_REQUIRE(Nc >= nparts, GG_ERR_INVALID, "fewer cells than parts");
-  P->first.resize(nparts); P->last.resize(nparts); P->cells.resize(nparts);
+  P->first.assign(nparts, Nc); P->last.assign(nparts, 0); P->n_owned.assign(nparts, 0); P->cells.resize(nparts);
+  P->cell_owner.resize(Nc);
+  if (P->mode == 1) {
+    // panel strips: the in-panel index (the cell order is panel-major, AtlasGrids.jl:277-280) is cut like the linear partition
+    GG_REQUIRE(P->gmesh->dim == 2 && Nc % 6 == 0 && Nc / 6 >= nparts, GG_ERR_INVALID, "panel strips need the 2-D cubed sphere");
+    const int64_t per_panel = Nc / 6;
+    for (int64_t c = 0; c < Nc; ++c) P->cell_owner[c] = (int32_t)(((c % per_panel) * nparts) / per_panel);
+  } else {
+    // part(i) = floor(i * P / Nc) (0-based i): the same cut as gg_partition_range
+    for (int64_t c = 0; c < Nc; ++c) P->cell_owner[c] = (int32_t)((c * nparts) / Nc);
+  }
+  for (int64_t c = 0; c < Nc; ++c) {
+    const int r = P->cell_owner[c];
+    P->n_owned[r]++;
+    P->first[r] = std::min(P->first[r], c);
+    P->last[r] = std::max(P->last[r], c + 1);
+  }
   for (int r = 0; r < nparts; ++r) {
-    GG_REQUIRE(gg_partition_range(Nc, nparts, r, &P->first[r], &P->last[r]) == GG_OK, GG_ERR_INVALID, "partition range");
-    std::vector<int64_t> ghosts = ghost_cells_of(P->gmesh.get(), P->first[r], P->last[r]);
+    std::vector<int64_t> ghosts = ghost_cells_of(P->gmesh.get(), P->cell_owner, r);
     auto& L = P->cells[r];
-    L.reserve(P->last[r] - P->first[r] + ghosts.size());
-    for (int64_t c = P->first[r]; c < P->last[r]; ++c) L.push_back(c);
+    L.reserve(P->n_owned[r] + ghosts.size());
+    for (int64_t c = 0; c < Nc; ++c)
+      if (P->cell_owner[c] == r) L.push_back(c);
     L.insert(L.end(), ghosts.begin(), ghosts.end());
     std::sort(L.begin(), L.end());
   }
@@ -79,7 +97,7 @@ SpacePlan& plan_space(gg_plan* P, int kind, int order) {
   // owner of a DOF = owner of the lowest-numbered cell that touches it
   std::vector<int32_t> owner_g(NG, -1);
   for (int64_t c = 0; c < Nc; ++c) {
-    const int32_t r = (int32_t)((c * np) / Nc);
+    const int32_t r = P->cell_owner[c];
     for (int j = 0; j < m; ++j) {
       int32_t g = G.cell_dofs[c * m + j];
       if (owner_g[g] < 0) owner_g[g] = r;
@@ -284,6 +302,27 @@ int gg_plan_create(int n, double radius, int nparts, int part, gg_plan** out) {
   GG_API_END
 }
 
+int gg_plan_create_strips(int n, double radius, int nparts, int part, gg_plan** out) {
+  GG_API_BEGIN
+  GG_REQUIRE(out, GG_ERR_INVALID, "null output");
+  GG_REQUIRE(n >= 1 && radius > 0, GG_ERR_INVALID, "bad mesh parameters");
+  GG_REQUIRE(nparts >= 1 && nparts <= GG_MAX_RANKS && part >= 0 && part < nparts, GG_ERR_INVALID, "bad partition request (at most 16 parts)");
+  GG_REQUIRE((int64_t)n * n >= nparts, GG_ERR_INVALID, "fewer cells per panel than parts");
+  std::unique_ptr<gg_plan> P(new gg_plan);
+  P->n = n; P->radius = radius; P->nparts = nparts; P->part = part; P->mode = 1;
+  P->gmesh.reset(build_cubed_sphere(nullptr, n, radius));
+  plan_partition(P.get());
+  *out = P.release();
+  GG_API_END
+}
+
+int gg_plan_owned_cells(gg_plan* p, int64_t* n_owned) {
+  GG_API_BEGIN
+  GG_REQUIRE(p && n_owned, GG_ERR_INVALID, "null argument");
+  *n_owned = p->n_owned[p->part];
+  GG_API_END
+}
+
 int gg_plan_create_shell(int n, int n_layers, double radius, double thickness, int ordering, int nparts, int part, gg_plan** out) {
   GG_API_BEGIN
   GG_REQUIRE(out, GG_ERR_INVALID, "null output");
@@ -453,7 +492,7 @@ int gg_mesh_partitioned(gg_ctx* ctx, gg_plan* p, gg_comm* comm, gg_mesh** out) {
       const int64_t c = L[i];
       std::copy(&g->cell_nodes8[c * 8], &g->cell_nodes8[c * 8] + 8, &s3->cell_nodes8[i * 8]);
       s3->cell_to_chart[i] = g->cell_to_chart[c]; s3->cell_col[i] = g->cell_col[c]; s3->cell_layer[i] = g->cell_layer[c];
-      s3->cell_owned[i] = c >= p->first[p->part] && c < p->last[p->part];
+      s3->cell_owned[i] = p->cell_owner[c] == p->part;
     }
     s3->surface.reset(build_cubed_sphere(ctx, g->n, g->radius, 0));
     s3->d_col.upload(s3->cell_col, ctx->stream); s3->d_layer.upload(s3->cell_layer, ctx->stream);
@@ -473,7 +512,7 @@ int gg_mesh_partitioned(gg_ctx* ctx, gg_plan* p, gg_comm* comm, gg_mesh** out) {
     std::copy(&g->cell_nodes[c * 4], &g->cell_nodes[c * 4] + 4, &s->cell_nodes[i * 4]);
     s->cell_to_chart[i] = g->cell_to_chart[c];
     std::copy(&g->chart_coords[c * 8], &g->chart_coords[c * 8] + 8, &s->chart_coords[i * 8]);
-    s->cell_owned[i] = c >= p->first[p->part] && c < p->last[p->part];
+    s->cell_owned[i] = p->cell_owner[c] == p->part;
   }
   s->plan = p; s->comm = comm;
   upload_geometry(s.get());

@@ -31,7 +31,13 @@ struct gg_plan {
   int n = 0, nparts = 1, part = 0;
   double radius = 1.0;
   std::unique_ptr<gg_mesh> gmesh;              // global mesh, host arrays only
-  std::vector<int64_t> first, last;            // owned range of every rank
+  // 0: the reference's linear partition of the panel-major cell order (src/Distributed/AtlasDistributedDiscreteModels.jl:31);
+  // 1: panel strips -- rank r owns the same range of in-panel cell indices on all six panels, so that every rank keeps the six
+  //    congruent cells of a geometry class together (opt-in; the partition does not change any global result)
+  int mode = 0;
+  std::vector<int32_t> cell_owner;             // owner rank of every global cell
+  std::vector<int64_t> n_owned;                // owned cells of every rank
+  std::vector<int64_t> first, last;            // smallest owned cell / one past the largest (the owned RANGE when mode == 0)
   std::vector<std::vector<int64_t>> cells;     // local cells (owned + ghost, ascending global id) of every rank
   std::map<int, std::unique_ptr<gg::SpacePlan>> spaces;
 };

@@ -132,6 +132,14 @@ int gg_plan_create(int n, double radius, int nparts, int part, gg_plan** out);
  * (2 = p8est Morton), equal-count chunks of that order (p4est's partition of its space-filling curve), vertex-adjacent ghost
  * layer; hexahedral CG / DG / RT spaces are exchanged through the same peer windows. */
 int gg_plan_create_shell(int n, int n_layers, double radius, double thickness, int ordering, int nparts, int part, gg_plan** out);
+/* Opt-in alternative to the reference's cut of the 2-D sphere: "panel strips" -- the in-panel cell index (cells are panel-major)
+ * is cut like the linear partition, so rank r owns the same rows of cells on all six panels.  Every rank then holds the six
+ * congruent cells of a geometry class, whose condensed mass operators the RK solvers store once (the linear partition leaves a
+ * rank 3, 2 or 1 of them as the slice shrinks, which is what the per-iteration cell phase of the shallow-water solves loses under
+ * weak scaling).  Owned cells are not one range: gg_plan_info returns the smallest owned cell and one past the largest,
+ * gg_plan_owned_cells the count.  Global results do not depend on the partition. */
+int gg_plan_create_strips(int n, double radius, int nparts, int part, gg_plan** out);
+int gg_plan_owned_cells(gg_plan* p, int64_t* n_owned);
 void gg_plan_destroy(gg_plan* p);
 int gg_plan_info(gg_plan* p, int64_t* n_cells_global, int64_t* first_owned, int64_t* last_owned, int64_t* n_local);
 int gg_plan_local_cells(gg_plan* p, int64_t* out /* [n_local] global cell ids (0-based), ascending: owned + ghost */);

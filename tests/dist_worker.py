@@ -41,7 +41,7 @@ def run_checks(gg, ctx, rank, world, n, p):
     cpu = dist.get_backend() != "nccl"
     dev = torch.device("cpu") if cpu else torch.device("cuda", ctx.device)
     mesh = gg.CubedSphereMesh(1.0)
-    plan = gg.PartitionPlan(n, world, rank)
+    plan = gg.PartitionPlan(n, world, rank, partition=os.environ.get("GG_TEST_PARTITION", "linear"))
     comm = gg.PeerWindow(ctx, rank, world, gg.window_doubles(plan, p))
     comm.connect()
     local_model = gg.partitioned_model(mesh, plan, comm, ctx=ctx)

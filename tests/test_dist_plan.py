@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n, shell=False):
+def _worker(rank, world, port, n, shell=False, strips=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -42,17 +42,24 @@ def _worker(rank, world, port, n, shell=False):
             counts = [b - a for a, b in ranges]
             assert max(counts) - min(counts) <= 1
             mine = np.arange(plan.first_owned, plan.last_owned)
+        elif strips:
+            # opt-in panel strips: the same rows of cells on all six panels (include/geosgpu.h, gg_plan_create_strips)
+            plan = gg.PartitionPlan(n, world, rank, partition="strips")
+            nc = 6 * n * n
+            cells = np.arange(nc)
+            mine = cells[((cells % (n * n)) * world) // (n * n) == rank]
+            assert len(mine) % 6 == 0 and len(np.unique(mine // (n * n))) == 6
         else:
             plan = gg.PartitionPlan(n, world, rank)
             nc = 6 * n * n
             # linear partition of the reference: part(i) = div((i-1)*P, Nc) + 1 (1-based i)
             cells = np.arange(nc)
             mine = cells[(cells * world) // nc == rank]
-        assert plan.num_cells_global == nc
+        assert plan.num_cells_global == nc and plan.num_owned_cells == len(mine)
         assert plan.first_owned == mine[0] and plan.last_owned == mine[-1] + 1
         lc = plan.local_cells()
         assert (np.diff(lc) > 0).all() and set(mine) <= set(lc) and len(lc) > len(mine)
-        owned_cells = torch.tensor([plan.last_owned - plan.first_owned])
+        owned_cells = torch.tensor([plan.num_owned_cells])
         dist.all_reduce(owned_cells)
         assert owned_cells.item() == nc
         for kind, order in (SPACES_SHELL if shell else SPACES):
@@ -107,6 +114,11 @@ def test_partition_plans_of_all_ranks_fit_together(world, n):
 @pytest.mark.parametrize("world,n", [(2, 2), (3, 4)])
 def test_shell_plans_in_p8est_order_fit_together(world, n):
     mp.spawn(_worker, args=(world, _free_port(), n, True), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,n", [(2, 4), (3, 5)])
+def test_panel_strip_plans_fit_together(world, n):
+    mp.spawn(_worker, args=(world, _free_port(), n, False, True), nprocs=world, join=True)
 
 
 def test_single_rank_plan_is_the_whole_model():
