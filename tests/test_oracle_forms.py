@@ -277,3 +277,44 @@ def test_hodge_laplacian_scalar_convergence_p2():
     lv = np.log10([1 / 2.0**lvl for lvl in (1, 2, 3)])
     assert np.polyfit(lv, np.log10([e[0] for e in errs]), 1)[0] >= 2
     assert np.polyfit(lv, np.log10([e[1] for e in errs]), 1)[0] >= 2
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_rt_basis_is_a_tensor_product_of_1d_dual_bases(k):
+    """What the lane kernels of the shallow-water path rely on (gridapgeosciences.jl_b200/csrc/gg_swe_lanes.cuh): every moment
+    functional of RT_k on the square is a tensor product of 1-D functionals -- Lambda_0 f = -f(0), Lambda_1 f = f(1),
+    Lambda_{2+i} f = int x^i f (i < k) on P_{k+1} and mu_m f = int s^m f (m <= k) on P_k -- so the basis is
+    phi^x_{alpha,m} = A_alpha(x) B_m(y), phi^y_{m,beta} = B_m(x) A_beta(y) with the 1-D dual bases A, B, div phi^x = A' B."""
+    from oracle.refel import RaviartThomasQuad, gauss_legendre_01
+    NA, NB = k + 2, k + 1
+    LA = np.zeros((NA, NA))
+    LA[0, 0] = -1.0
+    LA[1, :] = 1.0
+    for i in range(k):
+        LA[2 + i, :] = 1.0 / (i + np.arange(NA) + 1.0)
+    LB = 1.0 / (np.arange(NB)[:, None] + np.arange(NB)[None, :] + 1.0)
+    CA, CB = np.linalg.inv(LA), np.linalg.inv(LB)            # [monomial][function]
+    x, _ = gauss_legendre_01(k + 3)
+    pw = lambda n: x[:, None] ** np.arange(n)[None, :]       # noqa: E731
+    dpw = lambda n: np.arange(n)[None, :] * x[:, None] ** np.maximum(np.arange(n) - 1, 0)[None, :]   # noqa: E731
+    A, dA, B = pw(NA) @ CA, dpw(NA) @ CA, pw(NB) @ CB        # [point][function]
+    jx = lambda al, m: 2 * NB + m if al == 0 else 3 * NB + m if al == 1 else 4 * NB + m * k + (al - 2)                  # noqa: E731
+    jy = lambda m, be: m if be == 0 else NB + m if be == 1 else 4 * NB + k * NB + (be - 2) * NB + m                      # noqa: E731
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    val, div = RaviartThomasQuad(k).tabulate(np.stack([X.ravel(), Y.ravel()], -1))
+    val, div = val.reshape(len(x), len(x), -1, 2), div.reshape(len(x), len(x), -1)
+    seen = set()
+    scale = max(1.0, np.abs(val).max(), np.abs(div).max())
+    for al in range(NA):
+        for m in range(NB):
+            j = jx(al, m)
+            seen.add(j)
+            assert np.abs(val[:, :, j, 0] - np.outer(A[:, al], B[:, m])).max() < 1e-10 * scale
+            assert np.abs(val[:, :, j, 1]).max() < 1e-10 * scale
+            assert np.abs(div[:, :, j] - np.outer(dA[:, al], B[:, m])).max() < 1e-9 * scale
+            j = jy(m, al)
+            seen.add(j)
+            assert np.abs(val[:, :, j, 1] - np.outer(B[:, m], A[:, al])).max() < 1e-10 * scale
+            assert np.abs(val[:, :, j, 0]).max() < 1e-10 * scale
+            assert np.abs(div[:, :, j] - np.outer(B[:, m], dA[:, al])).max() < 1e-9 * scale
+    assert seen == set(range(2 * NA * NB))
